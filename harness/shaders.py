@@ -1,0 +1,363 @@
+"""Hand-assembled SPIR-V shaders for the BASELINE.json configs and for opcode-coverage tests.
+
+Each function returns a numpy uint32 word array; entry points are always called "main".
+Only the subset the reference's front end accepts is used: scalar-only
+OpCompositeConstruct, no OpSelect/OpPhi, UBO members whose LLVM natural layout coincides with
+std140 (mat4 / vec4).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .spvasm import FRAGMENT, GLSL, SC, VERTEX, BuiltIn, Dec, Module, Op
+
+
+def _main(m: Module):
+    void = m.t_void()
+    f, _ = m.begin_function(void, m.t_func(void))
+    m.label()
+    return f
+
+
+def _finish(m: Module, model: int, f: int, iface) -> np.ndarray:
+    m.ret()
+    m.end_function()
+    m.entry_point(model, f, "main", iface)
+    return m.words()
+
+
+# ------------------------------------------------------------------ C1: passthrough
+def vs_passthrough() -> np.ndarray:
+    """in vec4 pos@0, vec4 col@1; gl_Position = pos; out vec4 col@0."""
+    m = Module()
+    v4 = m.t_fvec(4)
+    pos = m.input(v4, 0, "pos")
+    col = m.input(v4, 1, "col")
+    ocol = m.output(v4, 0, "ocol")
+    gl = m.per_vertex_out()
+    f = _main(m)
+    p = m.load(v4, pos)
+    m.store(m.access(SC.Output, v4, gl, m.const_i(0)), p)
+    m.store(ocol, m.load(v4, col))
+    return _finish(m, VERTEX, f, [pos, col, ocol, gl])
+
+
+def fs_color() -> np.ndarray:
+    """in vec4 col@0; out vec4 o@0 = col."""
+    m = Module()
+    v4 = m.t_fvec(4)
+    col = m.input(v4, 0, "col")
+    o = m.output(v4, 0, "o")
+    f = _main(m)
+    m.store(o, m.load(v4, col))
+    return _finish(m, FRAGMENT, f, [col, o])
+
+
+# ------------------------------------------------------------------ C2: textured cube
+def vs_mvp_uv() -> np.ndarray:
+    """UBO{mat4 mvp}@(0,0); in vec4 pos@0, vec2 uv@1; gl_Position = mvp*pos; out vec2 uv@0."""
+    m = Module()
+    v4, v2, mat4 = m.t_fvec(4), m.t_fvec(2), m.t_mat(4)
+    st = m.t_struct(mat4, tag="UBO")
+    m.member_decorate(st, 0, Dec.ColMajor)
+    m.member_decorate(st, 0, Dec.Offset, 0)
+    m.member_decorate(st, 0, Dec.MatrixStride, 16)
+    ubo = m.ubo(st, 0, 0, "ubo")
+    pos = m.input(v4, 0, "pos")
+    uv = m.input(v2, 1, "uv")
+    ouv = m.output(v2, 0, "ouv")
+    gl = m.per_vertex_out()
+    f = _main(m)
+    mvp = m.load(mat4, m.access(SC.Uniform, mat4, ubo, m.const_i(0)))
+    r = m.inst(Op.MatrixTimesVector, v4, mvp, m.load(v4, pos))
+    m.store(m.access(SC.Output, v4, gl, m.const_i(0)), r)
+    m.store(ouv, m.load(v2, uv))
+    return _finish(m, VERTEX, f, [pos, uv, ouv, gl])
+
+
+def fs_texture() -> np.ndarray:
+    """sampler2D tex@(0,1); in vec2 uv@0; out = texture(tex, uv)."""
+    m = Module()
+    v4, v2 = m.t_fvec(4), m.t_fvec(2)
+    tex = m.sampler2d(0, 1, "tex")
+    uv = m.input(v2, 0, "uv")
+    o = m.output(v4, 0, "o")
+    f = _main(m)
+    s = m.load(m.t_sampled_image(), tex)
+    c = m.inst(Op.ImageSampleImplicitLod, v4, s, m.load(v2, uv))
+    m.store(o, c)
+    return _finish(m, FRAGMENT, f, [uv, o])
+
+
+# ------------------------------------------------------------------ C3 / C5: lit mesh
+def vs_lit(with_uv: bool = False) -> np.ndarray:
+    """UBO{mat4 mvp; vec4 light; vec4 albedo; vec4 ambient}@(0,0);
+    in vec3 pos@0, vec3 nrm@1, vec2 uv@2.
+    gl_Position = mvp*vec4(pos,1); col = albedo*max(dot(nrm,light.xyz),0) + ambient -> out@0
+    (+ uv -> out@1)."""
+    m = Module()
+    fl, v4, v3, v2, mat4 = m.t_float(), m.t_fvec(4), m.t_fvec(3), m.t_fvec(2), m.t_mat(4)
+    st = m.t_struct(mat4, v4, v4, v4, tag="UBO")
+    m.member_decorate(st, 0, Dec.ColMajor)
+    m.member_decorate(st, 0, Dec.Offset, 0)
+    m.member_decorate(st, 0, Dec.MatrixStride, 16)
+    for i, off in ((1, 64), (2, 80), (3, 96)):
+        m.member_decorate(st, i, Dec.Offset, off)
+    ubo = m.ubo(st, 0, 0, "ubo")
+    pos = m.input(v3, 0, "pos")
+    nrm = m.input(v3, 1, "nrm")
+    uv = m.input(v2, 2, "uv") if with_uv else None
+    ocol = m.output(v4, 0, "ocol")
+    ouv = m.output(v2, 1, "ouv") if with_uv else None
+    gl = m.per_vertex_out()
+    f = _main(m)
+    p = m.load(v3, pos)
+    p4 = m.construct(v4, m.extract(fl, p, 0), m.extract(fl, p, 1), m.extract(fl, p, 2), m.const_f(1.0))
+    mvp = m.load(mat4, m.access(SC.Uniform, mat4, ubo, m.const_i(0)))
+    m.store(m.access(SC.Output, v4, gl, m.const_i(0)), m.inst(Op.MatrixTimesVector, v4, mvp, p4))
+    light = m.load(v4, m.access(SC.Uniform, v4, ubo, m.const_i(1)))
+    l3 = m.shuffle(v3, light, light, 0, 1, 2)
+    ndl = m.inst(Op.Dot, fl, m.load(v3, nrm), l3)
+    ndl = m.ext(fl, GLSL.FMax, ndl, m.const_f(0.0))
+    albedo = m.load(v4, m.access(SC.Uniform, v4, ubo, m.const_i(2)))
+    ambient = m.load(v4, m.access(SC.Uniform, v4, ubo, m.const_i(3)))
+    lit = m.inst(Op.VectorTimesScalar, v4, albedo, ndl)
+    m.store(ocol, m.inst(Op.FAdd, v4, lit, ambient))
+    iface = [pos, nrm, ocol, gl]
+    if with_uv:
+        m.store(ouv, m.load(v2, uv))
+        iface += [uv, ouv]
+    return _finish(m, VERTEX, f, iface)
+
+
+def fs_lit_tex() -> np.ndarray:
+    """sampler2D tex@(0,1); in vec4 col@0, vec2 uv@1; out = texture(tex,uv) * col."""
+    m = Module()
+    v4, v2 = m.t_fvec(4), m.t_fvec(2)
+    tex = m.sampler2d(0, 1, "tex")
+    col = m.input(v4, 0, "col")
+    uv = m.input(v2, 1, "uv")
+    o = m.output(v4, 0, "o")
+    f = _main(m)
+    s = m.load(m.t_sampled_image(), tex)
+    t = m.inst(Op.ImageSampleImplicitLod, v4, s, m.load(v2, uv))
+    m.store(o, m.inst(Op.FMul, v4, t, m.load(v4, col)))
+    return _finish(m, FRAGMENT, f, [col, uv, o])
+
+
+# ------------------------------------------------------------------ opcode coverage
+def vs_kitchen_sink() -> np.ndarray:
+    """Exercises most of Appendix B on the vertex side.
+
+    push constants {vec4 k} (offset 0); UBO{mat4 a; mat4 b; vec4 s}@(1,2);
+    in vec4 pos@0, vec3 nrm@1, float w@2, int flag@3 (R32_SINT), gl_VertexIndex.
+    out@0 vec4, out@1 vec3, out@2 float, out@3 int (flat), out@4 vec2, out@5..8 mat4.
+    Uses: function call with pointer param, loop (SLessThan/IAdd/ConvertSToF), branch, FMix, FClamp,
+    FMin, FMax, Normalize, Length, Reflect, Sqrt, InverseSqrt, FNegate, FDiv, FSub, VectorShuffle,
+    VectorTimesMatrix, MatrixTimesMatrix, MatrixTimesScalar, Transpose, MatrixInverse(=transpose),
+    Cross(=arg0), IMul, BitwiseAnd, ShiftLeftLogical(=shift right), IEqual, FOrdLessThan(Equal),
+    FOrdGreaterThan, CompositeExtract on matrix, CompositeConstruct of matrix.
+    """
+    m = Module()
+    fl, it = m.t_float(), m.t_int(1)
+    v4, v3, v2, mat4 = m.t_fvec(4), m.t_fvec(3), m.t_fvec(2), m.t_mat(4)
+    bl = m.t_bool()
+    pc_t = m.t_struct(v4, tag="PC")
+    m.member_decorate(pc_t, 0, Dec.Offset, 0)
+    pc = m.push_constants(pc_t, "pc")
+    ubo_t = m.t_struct(mat4, mat4, v4, tag="UBO")
+    for i, off in ((0, 0), (1, 64), (2, 128)):
+        m.member_decorate(ubo_t, i, Dec.Offset, off)
+    ubo = m.ubo(ubo_t, 1, 2, "ubo")
+    pos = m.input(v4, 0, "pos")
+    nrm = m.input(v3, 1, "nrm")
+    win = m.input(fl, 2, "w")
+    flag = m.input(it, 3, "flag")
+    vidx = m.builtin_input(it, BuiltIn.VertexIndex, "gl_VertexIndex")
+    o0 = m.output(v4, 0)
+    o1 = m.output(v3, 1)
+    o2 = m.output(fl, 2)
+    o3 = m.output(it, 3)
+    o4 = m.output(v2, 4)
+    o5 = m.output(mat4, 5)
+    gl = m.per_vertex_out()
+
+    void = m.t_void()
+    # float helper(inout float acc, vec3 n): acc = acc + length(n); return sqrt(acc)
+    pfl = m.t_ptr(SC.Function, fl)
+    hf, (h_acc, h_n) = m.begin_function(fl, m.t_func(fl, pfl, v3), [pfl, v3])
+    m.label()
+    a = m.load(fl, h_acc)
+    a2 = m.inst(Op.FAdd, fl, a, m.ext(fl, GLSL.Length, h_n))
+    m.store(h_acc, a2)
+    m.stmt(Op.ReturnValue, m.ext(fl, GLSL.Sqrt, a2))
+    m.end_function()
+
+    f, _ = m.begin_function(void, m.t_func(void))
+    m.label()
+    acc = m.local(fl, m.const_f(0.25))
+    i_var = m.local(it, m.const_i(0))
+    outsel = m.local(fl)
+    p = m.load(v4, pos)
+    n = m.load(v3, nrm)
+    k = m.load(v4, m.access(SC.PushConstant, v4, pc, m.const_i(0)))
+    ma = m.load(mat4, m.access(SC.Uniform, mat4, ubo, m.const_i(0)))
+    mb = m.load(mat4, m.access(SC.Uniform, mat4, ubo, m.const_i(1)))
+    s = m.load(v4, m.access(SC.Uniform, v4, ubo, m.const_i(2)))
+    # scalar member read through a deeper access chain: s.y
+    sy = m.load(fl, m.access(SC.Uniform, fl, ubo, m.const_i(2), m.const_i(1)))
+
+    mm = m.inst(Op.MatrixTimesMatrix, mat4, ma, mb)
+    mt = m.inst(Op.Transpose, mat4, mm)
+    ms = m.inst(Op.MatrixTimesScalar, mat4, mt, sy)
+    mi = m.ext(mat4, GLSL.MatrixInverse, ms)
+    pv = m.inst(Op.MatrixTimesVector, v4, ma, p)
+    vp = m.inst(Op.VectorTimesMatrix, v4, p, mb)
+    col1 = m.extract(v4, mi, 1)
+    e23 = m.extract(fl, mi, 2, 3)
+    rebuilt = m.construct(mat4, pv, vp, col1, k)
+
+    # loop: for (i = 0; i < 3; i++) acc += float(i) * w
+    head, body, cont, merge = m.new_id(), m.new_id(), m.new_id(), m.new_id()
+    m.stmt(Op.Branch, head)
+    m.label(head)
+    iv = m.load(it, i_var)
+    cond = m.inst(Op.SLessThan, bl, iv, m.const_i(3))
+    m.stmt(Op.LoopMerge, merge, cont, 0)
+    m.stmt(Op.BranchConditional, cond, body, merge)
+    m.label(body)
+    fi = m.inst(Op.ConvertSToF, fl, iv)
+    m.store(acc, m.inst(Op.FAdd, fl, m.load(fl, acc), m.inst(Op.FMul, fl, fi, m.load(fl, win))))
+    m.stmt(Op.Branch, cont)
+    m.label(cont)
+    m.store(i_var, m.inst(Op.IAdd, it, m.load(it, i_var), m.const_i(1)))
+    m.stmt(Op.Branch, head)
+    m.label(merge)
+
+    hres = m.inst(Op.FunctionCall, fl, hf, acc, n)
+
+    nn = m.ext(v3, GLSL.Normalize, n)
+    refl = m.ext(v3, GLSL.Reflect, m.shuffle(v3, p, p, 0, 1, 2), nn)
+    crs = m.ext(v3, GLSL.Cross, refl, nn)
+    mixv = m.ext(v4, GLSL.FMix, pv, vp, s)
+    clv = m.ext(v4, GLSL.FClamp, mixv, m.const_fvec(-0.5, -0.5, -0.5, -0.5), m.const_fvec(2, 2, 2, 2))
+    mn = m.ext(fl, GLSL.FMin, hres, e23)
+    mx = m.ext(fl, GLSL.FMax, hres, e23)
+    isq = m.ext(fl, GLSL.InverseSqrt, m.inst(Op.FAdd, fl, mx, m.const_f(1.5)))
+    neg = m.inst(Op.FNegate, fl, mn)
+    dv = m.inst(Op.FDiv, fl, neg, m.inst(Op.FAdd, fl, isq, m.const_f(3.0)))
+    sb = m.inst(Op.FSub, fl, dv, sy)
+
+    # integer ops + branch: flag2 = ((flag * 3) & 0xff) >> 1 [the reference emits lshr for SHL]
+    fg = m.load(it, flag)
+    f2 = m.inst(Op.IMul, it, fg, m.const_i(3))
+    f3 = m.inst(Op.BitwiseAnd, it, f2, m.const_i(0xFF))
+    f4 = m.inst(Op.ShiftLeftLogical, it, f3, m.const_i(1))
+    f5 = m.inst(Op.IAdd, it, f4, m.load(it, vidx))
+    m.store(outsel, sb)
+    is7 = m.inst(Op.IEqual, bl, fg, m.const_i(7))
+    t_lbl, e_lbl, j_lbl = m.new_id(), m.new_id(), m.new_id()
+    m.stmt(Op.SelectionMerge, j_lbl, 0)
+    m.stmt(Op.BranchConditional, is7, t_lbl, e_lbl)
+    m.label(t_lbl)
+    m.store(outsel, m.inst(Op.FMul, fl, sb, m.const_f(2.0)))
+    m.stmt(Op.Branch, j_lbl)
+    m.label(e_lbl)
+    lt = m.inst(Op.FOrdLessThan, bl, sb, m.const_f(0.0))
+    t2, j2 = m.new_id(), m.new_id()
+    m.stmt(Op.SelectionMerge, j2, 0)
+    m.stmt(Op.BranchConditional, lt, t2, j2)
+    m.label(t2)
+    m.store(outsel, m.inst(Op.FAdd, fl, sb, m.const_f(10.0)))
+    m.stmt(Op.Branch, j2)
+    m.label(j2)
+    m.stmt(Op.Branch, j_lbl)
+    m.label(j_lbl)
+    le = m.inst(Op.FOrdLessThanEqual, bl, m.load(fl, outsel), m.const_f(100.0))
+    t3, j3 = m.new_id(), m.new_id()
+    m.stmt(Op.SelectionMerge, j3, 0)
+    m.stmt(Op.BranchConditional, le, t3, j3)
+    m.label(t3)
+    gt = m.inst(Op.FOrdGreaterThan, bl, m.load(fl, outsel), m.const_f(-100.0))
+    t4, j4 = m.new_id(), m.new_id()
+    m.stmt(Op.SelectionMerge, j4, 0)
+    m.stmt(Op.BranchConditional, gt, t4, j4)
+    m.label(t4)
+    m.store(outsel, m.inst(Op.FAdd, fl, m.load(fl, outsel), m.const_f(0.125)))
+    m.stmt(Op.Branch, j4)
+    m.label(j4)
+    m.stmt(Op.Branch, j3)
+    m.label(j3)
+
+    m.store(m.access(SC.Output, v4, gl, m.const_i(0)), p)
+    m.store(o0, clv)
+    m.store(o1, crs)
+    m.store(o2, m.load(fl, outsel))
+    m.store(o3, f5)
+    m.store(o4, m.shuffle(v2, k, s, 1, 6))
+    m.store(o5, rebuilt)
+    return _finish(m, VERTEX, f, [pos, nrm, win, flag, vidx, o0, o1, o2, o3, o4, o5, gl])
+
+
+def fs_kitchen_sink() -> np.ndarray:
+    """in@0 vec4, @1 vec3, @2 float, @3 int (flat), @4 vec2, @5 mat4 (array of 4 slots);
+    push constants {vec4 k}; out = clamp-free mix of everything (kept inside [0,1] by the test)."""
+    m = Module()
+    fl, it = m.t_float(), m.t_int(1)
+    v4, v3, v2, mat4 = m.t_fvec(4), m.t_fvec(3), m.t_fvec(2), m.t_mat(4)
+    pc_t = m.t_struct(v4, tag="PC")
+    m.member_decorate(pc_t, 0, Dec.Offset, 0)
+    pc = m.push_constants(pc_t, "pc")
+    i0 = m.input(v4, 0)
+    i1 = m.input(v3, 1)
+    i2 = m.input(fl, 2)
+    i3 = m.input(it, 3)
+    m.decorate(i3, Dec.Flat)
+    i4 = m.input(v2, 4)
+    i5 = m.input(mat4, 5)
+    o = m.output(v4, 0)
+    f = _main(m)
+    a = m.load(v4, i0)
+    b = m.load(v3, i1)
+    c = m.load(fl, i2)
+    d = m.inst(Op.ConvertSToF, fl, m.load(it, i3))
+    e = m.load(v2, i4)
+    mt = m.load(mat4, i5)
+    k = m.load(v4, m.access(SC.PushConstant, v4, pc, m.const_i(0)))
+    mv = m.inst(Op.MatrixTimesVector, v4, mt, k)
+    r = m.inst(Op.FAdd, v4, a, mv)
+    r = m.inst(Op.VectorTimesScalar, v4, r, m.const_f(0.03125))
+    bx = m.extract(fl, b, 0)
+    ex = m.extract(fl, e, 1)
+    t = m.inst(Op.FMul, fl, m.inst(Op.FAdd, fl, m.inst(Op.FAdd, fl, bx, ex), c), m.const_f(0.015625))
+    t = m.inst(Op.FAdd, fl, t, m.inst(Op.FMul, fl, d, m.const_f(0.0009765625)))
+    tv = m.construct(v4, t, t, t, t)
+    m.store(o, m.inst(Op.FAdd, v4, r, tv))
+    return _finish(m, FRAGMENT, f, [i0, i1, i2, i3, i4, i5, o])
+
+
+def fs_cube() -> np.ndarray:
+    """samplerCube tex@(0,1); in vec3 dir@0; out = texture(tex, dir)."""
+    m = Module()
+    v4, v3 = m.t_fvec(4), m.t_fvec(3)
+    tex = m.sampler2d(0, 1, "tex", dim=3)
+    d = m.input(v3, 0, "dir")
+    o = m.output(v4, 0, "o")
+    f = _main(m)
+    s = m.load(m.t_sampled_image(3), tex)
+    m.store(o, m.inst(Op.ImageSampleImplicitLod, v4, s, m.load(v3, d)))
+    return _finish(m, FRAGMENT, f, [d, o])
+
+
+def vs_pos_dir() -> np.ndarray:
+    """in vec4 pos@0, vec3 dir@1; gl_Position = pos; out vec3 dir@0."""
+    m = Module()
+    v4, v3 = m.t_fvec(4), m.t_fvec(3)
+    pos = m.input(v4, 0)
+    d = m.input(v3, 1)
+    od = m.output(v3, 0)
+    gl = m.per_vertex_out()
+    f = _main(m)
+    m.store(m.access(SC.Output, v4, gl, m.const_i(0)), m.load(v4, pos))
+    m.store(od, m.load(v3, d))
+    return _finish(m, VERTEX, f, [pos, d, od, gl])

@@ -1,0 +1,472 @@
+/*
+ * oracle/ref/ref_glue.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * Everything the UNMODIFIED reference objects (rasterizer.cpp, texture_sampling.cpp, cmd_exec.cpp,
+ * ... compiled in place from /root/reference by oracle/Makefile) need to link and run headless on
+ * Linux, and nothing else:
+ *   1. spirv_compile.h (InitLLVM .. DestroyFunction): the reference implementation needs LLVM 6.0.0
+ *      and cannot be built; the boundary is served by the CPU restatement oracle/spirv_cpu.cpp.
+ *      VkPipeline_T stores raw VertexShader/FragmentShader function pointers (precompiled.h:53-55,
+ *      131-132) that rasterizer.cpp calls directly, so entries are bound to a fixed pool of
+ *      trampolines.
+ *   2. the accessors the JIT'd code resolves by name (spirv_compile.cpp:552-627), as ShaderEnv
+ *      callbacks reading the reference's own GPUState.
+ *   3. wsi.cpp (Win32 GDI) replaced by headless stubs.
+ *   4. vref_*: the product's C-ABI shape (include/visor_b200.h) adapted onto the reference's
+ *      ClearTarget / DrawTriangles / sample_tex_wrapped, so one Python harness drives the reference,
+ *      the restatement and the CUDA path with identical inputs.
+ * This file is compiled with -include shim.h -I/root/reference; it contains no reference code.
+ */
+#include "precompiled.h"
+#include "gpu.h"
+#include "spirv_compile.h"
+
+#include <deque>
+#include <map>
+#include <string>
+#include <utility>
+#include "../../include/visor_b200.h"
+#include "../spirv_cpu.h"
+
+// ---------------------------------------------------------------------------------------------
+// 2. resource accessors over GPUState
+// ---------------------------------------------------------------------------------------------
+static void refVertexAttr(void *user, uint32_t vertexIndex, uint32_t attr, float out[4])
+{
+  const GPUState &state = *(const GPUState *)user;
+  uint32_t vb = state.pipeline->vattrs[attr].vb;
+  byte *ptr = state.vbs[vb].buffer->bytes + state.vbs[vb].offset;
+  ptr += state.pipeline->vattrs[attr].offset;
+  ptr += state.pipeline->vattrs[attr].stride * vertexIndex;
+  if(!vor::fetch_vertex_attr((uint32_t)state.pipeline->vattrs[attr].format, ptr, out))
+    assert(false && "Unhandled vertex attribute format");
+}
+static const uint8_t *refBufferPtr(void *user, uint32_t set, uint32_t bind)
+{
+  const GPUState &state = *(const GPUState *)user;
+  const VkDescriptorBufferInfo &buf = state.sets[set]->binds[bind].data.bufferInfo;
+  return buf.buffer->bytes + buf.offset;
+}
+static const void *refImage(void *user, uint32_t set, uint32_t bind)
+{
+  const GPUState &state = *(const GPUState *)user;
+  return state.sets[set]->binds[bind].data.imageInfo.imageView->image;
+}
+static const uint8_t *refPush(void *user, uint32_t offset)
+{
+  return ((const GPUState *)user)->pushconsts + offset;
+}
+static void refSampleTex(void *, float u, float v, const void *img, uint64_t offs, float out[4])
+{
+  float4 o;
+  sample_tex_wrapped(u, v, (VkImage)img, offs, o);    // the reference's texture unit
+  memcpy(out, o.v, 16);
+}
+static void refSampleCube(void *, float x, float y, float z, const void *img, float out[4])
+{
+  float4 o;
+  sample_cube_wrapped(x, y, z, (VkImage)img, o);
+  memcpy(out, o.v, 16);
+}
+static vor::ShaderEnv refEnv(const GPUState &state)
+{
+  vor::ShaderEnv e;
+  e.user = (void *)&state;
+  e.vertex_attr = refVertexAttr;
+  e.buffer_ptr = refBufferPtr;
+  e.image = refImage;
+  e.push_ptr = refPush;
+  e.sample_tex = refSampleTex;
+  e.sample_cube = refSampleCube;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. spirv_compile.h served by the interpreter, through trampolines
+// ---------------------------------------------------------------------------------------------
+static const int kSlots = 256;
+static const vor::Entry *g_vsSlot[kSlots];
+static const vor::Entry *g_fsSlot[kSlots];
+
+static_assert(sizeof(VertexCacheEntry) == sizeof(float) * vor::kVertexFloats, "VertexCacheEntry layout");
+
+template <int I>
+static void vsTramp(const GPUState &state, uint32_t vertexIndex, VertexCacheEntry &out)
+{
+  vor::ShaderEnv env = refEnv(state);
+  vor::run_vertex(g_vsSlot[I], env, vertexIndex, (float *)&out);
+}
+template <int I>
+static void fsTramp(const GPUState &state, float pixdepth, const float4 &bary,
+                    const VertexCacheEntry tri[3], float4 &out)
+{
+  vor::ShaderEnv env = refEnv(state);
+  vor::run_fragment(g_fsSlot[I], env, pixdepth, bary.v, (const float *)tri, out.v);
+}
+template <int... Is>
+struct Seq
+{
+};
+template <int N, int... Is>
+struct MakeSeq : MakeSeq<N - 1, N - 1, Is...>
+{
+};
+template <int... Is>
+struct MakeSeq<0, Is...>
+{
+  typedef Seq<Is...> type;
+};
+template <int... Is>
+static void fillTables(VertexShader *vs, FragmentShader *fs, Seq<Is...>)
+{
+  VertexShader v[] = {&vsTramp<Is>...};
+  FragmentShader f[] = {&fsTramp<Is>...};
+  for(int i = 0; i < kSlots; i++)
+  {
+    vs[i] = v[i];
+    fs[i] = f[i];
+  }
+}
+static VertexShader g_vsTramp[kSlots];
+static FragmentShader g_fsTramp[kSlots];
+static bool g_tablesReady = false;
+
+struct LLVMFunction
+{
+  vor::Module *mod = NULL;
+  std::map<std::string, std::pair<int, int>> bound;    // name -> (stage, slot)
+};
+
+void InitLLVM()
+{
+  if(!g_tablesReady)
+  {
+    fillTables(g_vsTramp, g_fsTramp, MakeSeq<kSlots>::type());
+    g_tablesReady = true;
+  }
+}
+void ShutdownLLVM()
+{
+}
+
+LLVMFunction *CompileFunction(const uint32_t *pCode, size_t codeSize)
+{
+  InitLLVM();
+  std::string err;
+  vor::Module *m = vor::compile(pCode, codeSize, &err);
+  if(!m)
+  {
+    fprintf(stderr, "CompileFunction: %s\n", err.c_str());
+    return NULL;
+  }
+  LLVMFunction *f = new LLVMFunction;
+  f->mod = m;
+  return f;
+}
+
+Shader GetFuncPointer(LLVMFunction *func, const char *name)
+{
+  const vor::Entry *e = vor::find_entry(func->mod, name);
+  if(!e)
+    return NULL;
+  auto it = func->bound.find(name);
+  int stage = vor::entry_stage(e);
+  int slot = -1;
+  if(it != func->bound.end())
+    slot = it->second.second;
+  else
+  {
+    const vor::Entry **tab = stage == 0 ? g_vsSlot : g_fsSlot;
+    for(int i = 0; i < kSlots; i++)
+      if(!tab[i])
+      {
+        slot = i;
+        break;
+      }
+    if(slot < 0)
+    {
+      fprintf(stderr, "GetFuncPointer: out of trampolines\n");
+      return NULL;
+    }
+    tab[slot] = e;
+    func->bound[name] = std::make_pair(stage, slot);
+  }
+  return stage == 0 ? (Shader)g_vsTramp[slot] : (Shader)g_fsTramp[slot];
+}
+
+void DestroyFunction(LLVMFunction *func)
+{
+  if(!func)
+    return;
+  for(auto &kv : func->bound)
+    (kv.second.first == 0 ? g_vsSlot : g_fsSlot)[kv.second.second] = NULL;
+  vor::destroy(func->mod);
+  delete func;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. headless WSI (wsi.cpp is Win32-only). Entry points icd_interface.cpp:23-26,41-45 take the
+//    address of; rendering tests use plain VkImages, never a swapchain.
+// ---------------------------------------------------------------------------------------------
+VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfaceSupportKHR(VkPhysicalDevice, uint32_t,
+                                                                    VkSurfaceKHR, VkBool32 *pSupported)
+{
+  *pSupported = VK_FALSE;
+  return VK_SUCCESS;
+}
+VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfaceFormatsKHR(VkPhysicalDevice, VkSurfaceKHR,
+                                                                    uint32_t *pCount,
+                                                                    VkSurfaceFormatKHR *)
+{
+  *pCount = 0;
+  return VK_SUCCESS;
+}
+VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfaceCapabilitiesKHR(VkPhysicalDevice, VkSurfaceKHR,
+                                                                         VkSurfaceCapabilitiesKHR *p)
+{
+  memset(p, 0, sizeof(*p));
+  return VK_ERROR_SURFACE_LOST_KHR;
+}
+VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfacePresentModesKHR(VkPhysicalDevice, VkSurfaceKHR,
+                                                                         uint32_t *pCount,
+                                                                         VkPresentModeKHR *)
+{
+  *pCount = 0;
+  return VK_SUCCESS;
+}
+VKAPI_ATTR VkResult VKAPI_CALL vkCreateSwapchainKHR(VkDevice, const VkSwapchainCreateInfoKHR *,
+                                                    const VkAllocationCallbacks *, VkSwapchainKHR *)
+{
+  return VK_ERROR_SURFACE_LOST_KHR;
+}
+VKAPI_ATTR void VKAPI_CALL vkDestroySwapchainKHR(VkDevice, VkSwapchainKHR, const VkAllocationCallbacks *)
+{
+}
+VKAPI_ATTR VkResult VKAPI_CALL vkGetSwapchainImagesKHR(VkDevice, VkSwapchainKHR, uint32_t *pCount,
+                                                       VkImage *)
+{
+  *pCount = 0;
+  return VK_SUCCESS;
+}
+VKAPI_ATTR VkResult VKAPI_CALL vkAcquireNextImageKHR(VkDevice, VkSwapchainKHR, uint64_t, VkSemaphore,
+                                                     VkFence, uint32_t *)
+{
+  return VK_ERROR_SURFACE_LOST_KHR;
+}
+VKAPI_ATTR VkResult VKAPI_CALL vkQueuePresentKHR(VkQueue, const VkPresentInfoKHR *)
+{
+  return VK_ERROR_SURFACE_LOST_KHR;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. vref_*: visor_b200.h-shaped adapter onto the reference operators
+// ---------------------------------------------------------------------------------------------
+static bool g_threaded = false;
+static bool g_refInit = false;
+static std::string g_err;
+
+// The reference's texel cache is keyed on the VkImage address (texture_sampling.cpp:43) and is never
+// invalidated, so every adapted image gets a fresh, never-reused VkImage_T: a stale hit is impossible.
+static std::deque<VkImage_T> g_imagePool;
+static VkImage_T *freshImage()
+{
+  g_imagePool.emplace_back();
+  return &g_imagePool.back();
+}
+
+static void toImage(const vb200_image &in, VkImage_T &out)
+{
+  out.extent.width = in.width;
+  out.extent.height = in.height;
+  out.extent.depth = in.depth;
+  out.imageType = (VkImageType)in.image_type;
+  out.format = (VkFormat)in.format;
+  out.arrayLayers = in.array_layers;
+  out.mipLevels = in.mip_levels;
+  out.bytesPerPixel = in.bytes_per_pixel;
+  out.pixels = (byte *)in.pixels;
+}
+
+#define VREF_API extern "C" __attribute__((visibility("default")))
+
+// threaded = 1: the reference's shipped mode (7 workers + stealing main thread, racy) — timing only.
+// threaded = 0: no workers; DrawTriangles drains its own FIFO in order — the parity oracle.
+VREF_API int vref_init(int threaded)
+{
+  InitLLVM();
+  if(!g_refInit)
+  {
+    if(threaded)
+      InitRasterThreads();
+    else
+      InitTextureCache();
+    g_threaded = threaded != 0;
+    g_refInit = true;
+  }
+  else if(g_threaded != (threaded != 0))
+  {
+    if(g_threaded)
+    {
+      ShutdownRasterThreads();    // joins workers; main thread's TLS cache stays initialised
+      g_threaded = false;
+    }
+    else
+    {
+      g_err = "cannot restart raster threads after shutdown (rast.kill stays set)";
+      return VB200_ERR_INVALID;
+    }
+  }
+  return 0;
+}
+VREF_API const char *vref_last_error(void)
+{
+  return g_err.c_str();
+}
+VREF_API void *vref_shader_create(const uint32_t *code, size_t words)
+{
+  return CompileFunction(code, words);
+}
+VREF_API void *vref_shader_entry(void *shader, const char *name)
+{
+  return shader ? (void *)GetFuncPointer((LLVMFunction *)shader, name) : NULL;
+}
+VREF_API void vref_shader_destroy(void *shader)
+{
+  DestroyFunction((LLVMFunction *)shader);
+}
+VREF_API int vref_clear_color(const vb200_image *target, const float rgba[4])
+{
+  VkImage_T img;
+  toImage(*target, img);
+  VkClearColorValue c;
+  memcpy(c.float32, rgba, 16);
+  ClearTarget(&img, c);
+  return 0;
+}
+VREF_API int vref_clear_depth(const vb200_image *target, float depth)
+{
+  VkImage_T img;
+  toImage(*target, img);
+  VkClearDepthStencilValue c;
+  c.depth = depth;
+  c.stencil = 0;
+  ClearTarget(&img, c);
+  return 0;
+}
+VREF_API int vref_sample(const vb200_image *tex, int cube, uint64_t byteOffs, const float *uvw,
+                         float *out, size_t count)
+{
+  VkImage_T &img = *freshImage();
+  toImage(*tex, img);
+  for(size_t i = 0; i < count; i++)
+  {
+    float4 o;
+    if(cube)
+      sample_cube_wrapped(uvw[3 * i], uvw[3 * i + 1], uvw[3 * i + 2], &img, o);
+    else
+      sample_tex_wrapped(uvw[2 * i], uvw[2 * i + 1], &img, byteOffs, o);
+    memcpy(out + 4 * i, o.v, 16);
+  }
+  return 0;
+}
+
+VREF_API int vref_draw(const vb200_draw_state *s, int numVerts, uint32_t first, int indexed)
+{
+  GPUState state;
+  memset(&state, 0, sizeof(state));
+
+  VkBuffer_T ib, vbs[4];
+  ib.bytes = (byte *)s->ib.buffer.bytes;
+  ib.size = s->ib.buffer.size;
+  state.ib.buffer = &ib;
+  state.ib.offset = s->ib.offset;
+  state.ib.indexType = (VkIndexType)s->ib.index_type;
+  for(int i = 0; i < 4; i++)
+  {
+    vbs[i].bytes = (byte *)s->vbs[i].buffer.bytes;
+    vbs[i].size = s->vbs[i].buffer.size;
+    state.vbs[i].buffer = &vbs[i];
+    state.vbs[i].offset = s->vbs[i].offset;
+  }
+
+  VkImage_T col, depth;
+  toImage(s->color, col);
+  state.col[0] = &col;
+  if(s->depth.pixels)
+  {
+    toImage(s->depth, depth);
+    state.depth = &depth;
+  }
+
+  VkPipeline_T pipe;
+  const vb200_pipeline *p = s->pipeline;
+  for(int i = 0; i < 16; i++)
+  {
+    pipe.vattrs[i].format = (VkFormat)p->vattrs[i].format;
+    pipe.vattrs[i].stride = p->vattrs[i].stride;
+    pipe.vattrs[i].offset = p->vattrs[i].offset;
+    pipe.vattrs[i].vb = p->vattrs[i].vb;
+  }
+  pipe.topology = (VkPrimitiveTopology)p->topology;
+  pipe.frontFace = (VkFrontFace)p->front_face;
+  pipe.cullMode = p->cull_mode;
+  pipe.depthCompareOp = (VkCompareOp)p->depth_compare_op;
+  pipe.depthWriteEnable = p->depth_write_enable != 0;
+  memset(&pipe.blend, 0, sizeof(pipe.blend));
+  pipe.blend.blendEnable = p->blend_enable;
+  pipe.blend.srcColorBlendFactor = (VkBlendFactor)p->src_color_blend_factor;
+  pipe.blend.dstColorBlendFactor = (VkBlendFactor)p->dst_color_blend_factor;
+  pipe.blend.colorBlendOp = (VkBlendOp)p->color_blend_op;
+  pipe.vs = (VertexShader)p->vs;
+  pipe.fs = (FragmentShader)p->fs;
+  state.pipeline = &pipe;
+
+  // descriptor sets: sets[set]->binds[binding]
+  VkDescriptorSet_T sets[8];
+  std::vector<VkDescriptorSet_T::Bind> binds[8];
+  std::vector<VkBuffer_T> bufs(s->num_bindings);
+  std::vector<VkImage_T *> imgs(s->num_bindings, NULL);
+  std::vector<VkImageView_T> views(s->num_bindings);
+  for(uint32_t i = 0; i < s->num_bindings; i++)
+  {
+    const vb200_binding &b = s->bindings[i];
+    if(b.set >= 8)
+      continue;
+    if(binds[b.set].size() <= b.binding)
+      binds[b.set].resize(b.binding + 1);
+    VkDescriptorSet_T::Bind &dst = binds[b.set][b.binding];
+    dst.type = (VkDescriptorType)b.type;
+    if(b.is_image)
+    {
+      imgs[i] = freshImage();
+      toImage(b.image, *imgs[i]);
+      views[i].image = imgs[i];
+      dst.data.imageInfo.imageView = &views[i];
+    }
+    else
+    {
+      bufs[i].bytes = (byte *)b.buffer.bytes;
+      bufs[i].size = b.buffer.size;
+      dst.data.bufferInfo.buffer = &bufs[i];
+      dst.data.bufferInfo.offset = b.offset;
+      dst.data.bufferInfo.range = b.buffer.size - b.offset;
+    }
+  }
+  for(int i = 0; i < 8; i++)
+  {
+    sets[i].binds = binds[i].empty() ? NULL : binds[i].data();
+    state.sets[i] = &sets[i];
+  }
+  memcpy(state.pushconsts, s->pushconsts, 128);
+
+  DrawTriangles(state, numVerts, first, indexed != 0);
+  return 0;
+}
+VREF_API int vref_flush(void)
+{
+  return 0;
+}
+VREF_API int vref_threads(void)
+{
+  return g_threaded ? 8 : 1;
+}
