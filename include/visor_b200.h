@@ -87,6 +87,9 @@ VB200_API vb200_entry *vb200_shader_entry(vb200_shader *shader, const char *name
 VB200_API void vb200_shader_destroy(vb200_shader *shader);
 /* Debug/inspection: PTX text generated for an entry point (owned by the module). */
 VB200_API const char *vb200_entry_ptx(const vb200_entry *entry);
+/* Debug/CI: run only the nvJitLink step for a VS/FS pair (kernel scaffolds + both PTX functions ->
+ * sm_100a cubin). Needs no device; reports the size of the linked cubin. */
+VB200_API int vb200_link_check(const vb200_entry *vs, const vb200_entry *fs, uint64_t *cubin_size);
 /* 0 = vertex, 4 = fragment (spv::ExecutionModel). */
 VB200_API int vb200_entry_stage(const vb200_entry *entry);
 

@@ -1,0 +1,94 @@
+// device_types.h — structures shared by the host runtime, the CUDA kernels and the PTX the shader
+// compiler emits.  Offsets used by generated PTX are spelled out as VB200_ENV_* constants and
+// static_assert'ed against the struct so the three can never drift apart.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#define VB200_TILE 32            // screen tile edge in pixels (the reference's blockSize, rasterizer.cpp:454)
+#define VB200_MAX_SLOTS 10       // interpolant float4 slots per vertex (VertexCacheEntry::interps, gpu.h:56)
+#define VB200_MAX_RES 16         // descriptor slots a pipeline may reference
+#define VB200_MAX_IMAGES 8
+
+struct Vb200Attr    // VkPipeline_T::vattrs (precompiled.h:118-124)
+{
+  uint32_t format, stride, offset, vb;
+};
+
+struct Vb200Image    // device-side view of VkImage_T (precompiled.h:89-98)
+{
+  const uint8_t *pixels;    // device address of VkImage_T::pixels
+  uint32_t width, height;
+  uint32_t bpp, format;
+  uint32_t mips, layers;
+  uint64_t slice_bytes;    // full mip-chain size of one layer (CalcSubresourceByteOffset, precompiled.cpp:18-33)
+};
+
+// Everything a shader invocation can reach: the device-side GPUState (gpu.h:3-23).
+// Passed to the kernels as a __grid_constant__ parameter; the PTX shader functions get its address.
+struct alignas(16) Vb200Env    // 16-byte aligned: generated PTX reads push constants with v4 loads
+{
+  const uint8_t *vb[4];               // vbs[i].buffer->bytes + vbs[i].offset, as device addresses
+  Vb200Attr attrs[16];
+  const uint8_t *res[VB200_MAX_RES];  // UBO slot -> bufferInfo.buffer->bytes + offset (device address)
+  uint8_t push[128];                  // GPUState::pushconsts
+  Vb200Image images[VB200_MAX_IMAGES];
+};
+
+#define VB200_ENV_VB 0
+#define VB200_ENV_ATTRS 32
+#define VB200_ENV_RES 288
+#define VB200_ENV_PUSH 416
+#define VB200_ENV_IMAGES 544
+#define VB200_IMAGE_SIZE 40
+
+#ifdef __cplusplus
+static_assert(offsetof(Vb200Env, vb) == VB200_ENV_VB, "env layout");
+static_assert(offsetof(Vb200Env, attrs) == VB200_ENV_ATTRS, "env layout");
+static_assert(offsetof(Vb200Env, res) == VB200_ENV_RES, "env layout");
+static_assert(offsetof(Vb200Env, push) == VB200_ENV_PUSH, "env layout");
+static_assert(offsetof(Vb200Env, images) == VB200_ENV_IMAGES, "env layout");
+static_assert(sizeof(Vb200Image) == VB200_IMAGE_SIZE, "image layout");
+static_assert(sizeof(Vb200Env) <= 1024, "env must stay a cheap kernel parameter");
+#endif
+
+// Per-vertex raster record written by the vertex kernel: ToWindow (rasterizer.cpp:248-249) and the
+// per-vertex part of triangle setup (invw, depth = z*invw, rasterizer.cpp:449-452).
+struct Vb200RasterVertex
+{
+  int32_t x, y;
+  float invw, depth;
+};
+
+// Per-triangle setup record (64 B) written by the setup kernel, read by the tile kernels.
+struct Vb200TriSetup
+{
+  int32_t x0, y0, x1, y1, x2, y2;    // window coordinates of the three corners
+  float invw0, invw1, invw2;
+  float d0, d1, d2;
+  uint32_t s0, s1, s2;               // post-VS record slot of each corner
+  uint32_t tiles;                    // minTx | minTy<<8 | maxTx<<16 | maxTy<<24 (inclusive); 0xffffffff = dead
+};
+#ifdef __cplusplus
+static_assert(sizeof(Vb200TriSetup) == 64, "setup record");
+#endif
+
+struct Vb200DrawCounters
+{
+  unsigned long long triangles_out, tile_pairs, fragments_covered, fragments_shaded;
+};
+
+// Fixed-function state of one draw, uniform across the grid.
+struct Vb200RasterState
+{
+  uint32_t width, height;
+  uint32_t tiles_x, tiles_y;
+  uint32_t depth_op;         // VkCompareOp; 7 (ALWAYS) or no depth image -> no test
+  uint32_t depth_write;
+  uint32_t has_depth;
+  uint32_t blend_enable, src_factor, dst_factor, blend_op;
+  uint32_t nslots;           // float4 slots per post-VS vertex record
+  uint32_t owner_rank, owner_world;    // sort-first tile ownership (tile % world == rank)
+  uint32_t count_fragments;
+  uint32_t color_bpp;
+};

@@ -1,0 +1,514 @@
+// fixed.cu — the shader-independent sm_100a kernels of the draw path.
+//
+//   K0  clear                     ClearTarget                      rasterizer.cpp:312-361
+//   K2  triangle assembly+setup   GetIndex, ShadeVerts assembly,   rasterizer.cpp:100-232, 385-452
+//                                 DrawTriangles setup / cull / bbox
+//   K3  binning                   the per-triangle 32x32 block      rasterizer.cpp:454-515
+//                                 split + FIFO queue, restated as
+//                                 per-screen-tile ordered lists:
+//                                 count -> exclusive scan -> fill -> per-tile sort by triangle id
+//   K5' stand-alone sampler       sample_tex_wrapped/_cube_wrapped texture_sampling.cpp:139-250
+//   K6  tile pack / unpack        (sort-first multi-GPU; no reference equivalent)
+#include "kernels.h"
+#include "raster_common.cuh"
+
+namespace vb200
+{
+namespace
+{
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// K0: clears. 16-byte stores, grid-stride; grid sized to a multiple of the SM count by the caller.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_clear_u32(uint32_t *dst, uint32_t value, size_t count)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n4 = count / 4;
+  uint4 *d4 = (uint4 *)dst;
+  const uint4 v4 = make_uint4(value, value, value, value);
+  for(size_t k = i; k < n4; k += stride)
+    d4[k] = v4;
+  for(size_t k = n4 * 4 + i; k < count; k += stride)
+    dst[k] = value;
+}
+
+__global__ void __launch_bounds__(kThreads) k_clear_u8(uint8_t *dst, uint8_t value, size_t count)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    dst[k] = value;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index range: min/max of the index values a draw references (bounds the unique-vertex VS launch)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_index(const void *ib, uint32_t index_type, uint32_t i)
+{
+  // GetIndex (rasterizer.cpp:100-119)
+  if(index_type == 0u)
+    return (uint32_t)__ldg((const uint16_t *)ib + i);
+  return __ldg((const uint32_t *)ib + i);
+}
+
+__global__ void __launch_bounds__(kThreads) k_index_range(const void *ib, uint32_t index_type, uint32_t first,
+                                                         uint32_t count, uint32_t *range)
+{
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+  {
+    const uint32_t v = load_index(ib, index_type, first + i);
+    lo = min(lo, v);
+    hi = max(hi, v);
+  }
+  for(int o = 16; o > 0; o >>= 1)
+  {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if((threadIdx.x & 31) == 0 && lo <= hi)
+  {
+    atomicMin(&range[0], lo);
+    atomicMax(&range[1], hi);
+  }
+}
+
+__global__ void k_init_range(uint32_t *range)
+{
+  range[0] = 0xffffffffu;
+  range[1] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 + K3 count/fill share the triangle -> tile-range traversal.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tile_owned(uint32_t tile, uint32_t rank, uint32_t world)
+{
+  return world <= 1u || (tile % world) == rank;
+}
+
+// Visit every owned tile of the inclusive range packed in `tiles`. Small ranges are walked by the
+// owning thread; large ones (full-screen triangles cover thousands of tiles) are spread over the warp.
+template <typename F>
+__device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32_t tiles_x, uint32_t rank,
+                                              uint32_t world, uint32_t tri, F f)
+{
+  const uint32_t tx0 = tiles & 0xffu, ty0 = (tiles >> 8) & 0xffu, tx1 = (tiles >> 16) & 0xffu, ty1 = tiles >> 24;
+  const uint32_t nx = alive ? (tx1 - tx0 + 1u) : 0u, ny = alive ? (ty1 - ty0 + 1u) : 0u;
+  const uint32_t nt = nx * ny;
+  const bool big = nt > 16u;
+  if(alive && !big)
+  {
+    for(uint32_t ty = ty0; ty <= ty1; ty++)
+      for(uint32_t tx = tx0; tx <= tx1; tx++)
+      {
+        const uint32_t tile = ty * tiles_x + tx;
+        if(tile_owned(tile, rank, world))
+          f(tile, tri);
+      }
+  }
+  uint32_t mask = __ballot_sync(0xffffffffu, alive && big);
+  const uint32_t lane = threadIdx.x & 31u;
+  while(mask)
+  {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    const uint32_t b_tx0 = __shfl_sync(0xffffffffu, tx0, src), b_ty0 = __shfl_sync(0xffffffffu, ty0, src);
+    const uint32_t b_nx = __shfl_sync(0xffffffffu, nx, src), b_nt = __shfl_sync(0xffffffffu, nt, src);
+    const uint32_t b_tri = __shfl_sync(0xffffffffu, tri, src);
+    for(uint32_t k = lane; k < b_nt; k += 32u)
+    {
+      const uint32_t tile = (b_ty0 + k / b_nx) * tiles_x + b_tx0 + k % b_nx;
+      if(tile_owned(tile, rank, world))
+        f(tile, b_tri);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = t < p.num_tris;
+  Vb200TriSetup su;
+  su.tiles = 0xffffffffu;
+
+  if(alive)
+  {
+    // triangle assembly (rasterizer.cpp:128-232): list = (3t, 3t+1, 3t+2); strip alternates
+    // (t, t+1, t+2) / (t+1, t, t+2) to preserve winding
+    uint32_t c0, c1, c2;
+    if(p.topology == 3u)
+    {
+      c0 = p.first + 3u * t;
+      c1 = c0 + 1u;
+      c2 = c0 + 2u;
+    }
+    else
+    {
+      const uint32_t b = p.first + t;
+      c0 = (t & 1u) ? b + 1u : b;
+      c1 = (t & 1u) ? b : b + 1u;
+      c2 = b + 2u;
+    }
+    uint32_t base = p.base_vertex;
+    if(p.indexed)
+    {
+      c0 = load_index(p.ib, p.index_type, c0);
+      c1 = load_index(p.ib, p.index_type, c1);
+      c2 = load_index(p.ib, p.index_type, c2);
+      base = p.range[0];
+    }
+    su.s0 = c0 - base;
+    su.s1 = c1 - base;
+    su.s2 = c2 - base;
+    alive = su.s0 < p.capacity && su.s1 < p.capacity && su.s2 < p.capacity;
+  }
+  if(alive)
+  {
+    const int4 a = __ldg((const int4 *)(p.rv + su.s0));
+    const int4 b = __ldg((const int4 *)(p.rv + su.s1));
+    const int4 c = __ldg((const int4 *)(p.rv + su.s2));
+    su.x0 = a.x; su.y0 = a.y; su.x1 = b.x; su.y1 = b.y; su.x2 = c.x; su.y2 = c.y;
+    su.invw0 = __int_as_float(a.z); su.invw1 = __int_as_float(b.z); su.invw2 = __int_as_float(c.z);
+    su.d0 = __int_as_float(a.w); su.d1 = __int_as_float(b.w); su.d2 = __int_as_float(c.w);
+
+    // double_triarea (rasterizer.cpp:272-275), zero-area skip (:398), facing / cull (:401-424)
+    const int area2 = (su.x1 - su.x0) * (su.y2 - su.y0) - (su.y1 - su.y0) * (su.x2 - su.x0);
+    int flipped = (p.front_face == 1u) ? -area2 : area2;
+    if(area2 == 0)
+      alive = false;
+    else if(flipped > 0 && (p.cull_mode & 1u))
+      alive = false;
+    else if(flipped < 0 && (p.cull_mode & 2u))
+      alive = false;
+  }
+  const uint32_t survivors = __popc(__ballot_sync(0xffffffffu, alive));
+  if((threadIdx.x & 31) == 0 && survivors)
+    atomicAdd(&p.counters->triangles_out, (unsigned long long)survivors);
+
+  if(alive)
+  {
+    // MinMax + clamp (rasterizer.cpp:428-435); the pixel loops run over [min, max) (:538-540)
+    const int minx = max(0, min(su.x0, min(su.x1, su.x2)));
+    const int miny = max(0, min(su.y0, min(su.y1, su.y2)));
+    const int maxx = min((int)p.width - 1, max(su.x0, max(su.x1, su.x2)));
+    const int maxy = min((int)p.height - 1, max(su.y0, max(su.y1, su.y2)));
+    if(minx < maxx && miny < maxy)
+      su.tiles = (uint32_t)(minx / VB200_TILE) | ((uint32_t)(miny / VB200_TILE) << 8) |
+                 ((uint32_t)((maxx - 1) / VB200_TILE) << 16) | ((uint32_t)((maxy - 1) / VB200_TILE) << 24);
+    else
+      alive = false;
+  }
+  if(t < p.num_tris)
+  {
+    int4 *q = (int4 *)(p.setup + t);
+    q[0] = make_int4(su.x0, su.y0, su.x1, su.y1);
+    q[1] = make_int4(su.x2, su.y2, __float_as_int(su.invw0), __float_as_int(su.invw1));
+    q[2] = make_int4(__float_as_int(su.invw2), __float_as_int(su.d0), __float_as_int(su.d1), __float_as_int(su.d2));
+    q[3] = make_int4((int)su.s0, (int)su.s1, (int)su.s2, (int)(alive ? su.tiles : 0xffffffffu));
+  }
+  uint32_t *cnt = p.tile_count;
+  for_each_tile(su.tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
+                [cnt](uint32_t tile, uint32_t) { atomicAdd(&cnt[tile], 1u); });
+}
+
+// exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also resets the fill cursors
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint32_t *tile_offset,
+                                              uint32_t *tile_cursor, uint32_t ntiles, uint32_t *total)
+{
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+  const uint32_t begin = threadIdx.x * per, end = min(begin + per, ntiles);
+  uint32_t sum = 0;
+  for(uint32_t i = begin; i < end; i++)
+    sum += tile_count[i];
+  // inclusive warp scan of the per-thread sums
+  uint32_t incl = sum;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for(int o = 1; o < 32; o <<= 1)
+  {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if(lane >= (uint32_t)o)
+      incl += v;
+  }
+  if(lane == 31u)
+    warp_sums[warp] = incl;
+  __syncthreads();
+  if(warp == 0)
+  {
+    uint32_t w = warp_sums[lane];
+    uint32_t wi = w;
+    for(int o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+      if(lane >= (uint32_t)o)
+        wi += v;
+    }
+    warp_sums[lane] = wi - w;    // exclusive
+    if(lane == 31u)
+      *total = wi;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[warp] + incl - sum;
+  for(uint32_t i = begin; i < end; i++)
+  {
+    tile_offset[i] = run;
+    tile_cursor[i] = 0u;
+    run += tile_count[i];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill(const Vb200SetupParams p, const uint32_t *tile_offset,
+                                                  uint32_t *tile_cursor, uint32_t *list, uint32_t capacity)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t tiles = 0xffffffffu;
+  if(t < p.num_tris)
+    tiles = __ldg(&((const uint32_t *)(p.setup + t))[15]);
+  const bool alive = tiles != 0xffffffffu;
+  for_each_tile(tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
+                [=](uint32_t tile, uint32_t tri) {
+                  const uint32_t pos = tile_offset[tile] + atomicAdd(&tile_cursor[tile], 1u);
+                  if(pos < capacity)
+                    list[pos] = tri;
+                });
+}
+
+// Per-tile sort by triangle id: restores submission order after the unordered atomic append, which
+// is what makes every pixel see its fragments in draw order (the serial FIFO of the reference).
+// Padding-friendly bitonic network (all compare-exchanges put the minimum at the lower index, so
+// virtual +inf elements past n never move).
+__device__ __forceinline__ void cmpxchg(uint32_t *a, uint32_t lo, uint32_t hi)
+{
+  const uint32_t x = a[lo], y = a[hi];
+  if(x > y)
+  {
+    a[lo] = y;
+    a[hi] = x;
+  }
+}
+
+__device__ void bitonic_sort(uint32_t *a, uint32_t n)
+{
+  uint32_t N = 1;
+  while(N < n)
+    N <<= 1;
+  const uint32_t half = N >> 1;
+  for(uint32_t k = 2; k <= N; k <<= 1)
+  {
+    const uint32_t hk = k >> 1;
+    for(uint32_t i = threadIdx.x; i < half; i += blockDim.x)
+    {
+      const uint32_t blk = i / hk, pos = i % hk;
+      const uint32_t lo = blk * k + pos, hi = blk * k + (k - 1u - pos);
+      if(hi < n)
+        cmpxchg(a, lo, hi);
+    }
+    __syncthreads();
+    for(uint32_t j = k >> 2; j > 0; j >>= 1)
+    {
+      for(uint32_t i = threadIdx.x; i < half; i += blockDim.x)
+      {
+        const uint32_t lo = (i / j) * 2u * j + (i % j), hi = lo + j;
+        if(hi < n)
+          cmpxchg(a, lo, hi);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+constexpr uint32_t kSortSmem = 8192;    // entries (32 KB)
+
+__global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_t *tile_offset,
+                                                  const uint32_t *tile_count)
+{
+  __shared__ uint32_t s[kSortSmem];
+  const uint32_t tile = blockIdx.x;
+  const uint32_t n = tile_count[tile];
+  if(n < 2u)
+    return;
+  uint32_t *a = list + tile_offset[tile];
+  int unsorted = 0;
+  for(uint32_t i = threadIdx.x; i + 1u < n; i += blockDim.x)
+    unsorted |= a[i] > a[i + 1u];
+  if(!__syncthreads_or(unsorted))
+    return;
+  if(n <= kSortSmem)
+  {
+    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      s[i] = a[i];
+    __syncthreads();
+    bitonic_sort(s, n);
+    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      a[i] = s[i];
+  }
+  else
+    bitonic_sort(a, n);    // rare: > 8192 triangles over one tile; sorted in place through L2
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone sampler (parity tests of the texture unit)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_sample(const Vb200Image img, int cube, unsigned long long byte_offset,
+                                                    const float *uvw, float4 *out, size_t count)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= count)
+    return;
+  if(cube)
+    out[i] = vb200_sample_cube_impl(uvw[3 * i], uvw[3 * i + 1], uvw[3 * i + 2], &img);
+  else
+    out[i] = vb200_sample_tex_impl(uvw[2 * i], uvw[2 * i + 1], &img, byte_offset);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: sort-first tile exchange. Tile t is owned by rank t % world; the k-th owned tile of a rank is
+// t = rank + k*world and occupies 4096 bytes (32 rows x 128 B) at slot k of the rank's send buffer.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_tiles_pack(const uint32_t *color, uint32_t width, uint32_t height,
+                                                        uint32_t tiles_x, uint32_t ntiles, uint32_t rank,
+                                                        uint32_t world, uint32_t *dst)
+{
+  const uint32_t k = blockIdx.x;
+  const uint32_t tile = rank + k * world;
+  if(tile >= ntiles)
+    return;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  for(uint32_t i = threadIdx.x; i < VB200_TILE * VB200_TILE; i += blockDim.x)
+  {
+    const uint32_t x = tx * VB200_TILE + (i & 31u), y = ty * VB200_TILE + (i >> 5);
+    dst[(size_t)k * 1024u + i] = (x < width && y < height) ? color[(size_t)y * width + x] : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_tiles_unpack(uint32_t *color, uint32_t width, uint32_t height,
+                                                          uint32_t tiles_x, uint32_t ntiles, uint32_t world,
+                                                          uint32_t slots_per_rank, const uint32_t *src)
+{
+  const uint32_t tile = blockIdx.x;
+  if(tile >= ntiles)
+    return;
+  const uint32_t owner = tile % world, k = tile / world;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  const uint32_t *s = src + ((size_t)owner * slots_per_rank + k) * 1024u;
+  for(uint32_t i = threadIdx.x; i < VB200_TILE * VB200_TILE; i += blockDim.x)
+  {
+    const uint32_t x = tx * VB200_TILE + (i & 31u), y = ty * VB200_TILE + (i >> 5);
+    if(x < width && y < height)
+      color[(size_t)y * width + x] = s[i];
+  }
+}
+
+int sm_count()
+{
+  static int n = 0;
+  if(!n)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if(n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+uint32_t grid_for(size_t work_items, int per_thread = 1)
+{
+  // grid-stride kernels: a whole number of waves of (SM count x 8 CTAs), capped by the work
+  const size_t need = (work_items + (size_t)kThreads * per_thread - 1) / ((size_t)kThreads * per_thread);
+  const size_t wave = (size_t)sm_count() * 8;
+  const size_t g = need < wave * 4 ? need : wave * 4;
+  return (uint32_t)(g ? g : 1);
+}
+}    // namespace
+
+int launch_clear_u32(uint32_t *dst, uint32_t value, size_t count, cudaStream_t s)
+{
+  if(!count)
+    return 0;
+  k_clear_u32<<<grid_for(count, 16), kThreads, 0, s>>>(dst, value, count);
+  return 1;
+}
+
+int launch_clear_u8(uint8_t *dst, uint8_t value, size_t count, cudaStream_t s)
+{
+  if(!count)
+    return 0;
+  k_clear_u8<<<grid_for(count, 16), kThreads, 0, s>>>(dst, value, count);
+  return 1;
+}
+
+int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint32_t count, uint32_t *range,
+                       cudaStream_t s)
+{
+  k_init_range<<<1, 1, 0, s>>>(range);
+  if(!count)
+    return 1;
+  k_index_range<<<grid_for(count, 8), kThreads, 0, s>>>(ib, index_type, first, count, range);
+  return 2;
+}
+
+int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
+{
+  if(!p.num_tris)
+    return 0;
+  k_setup<<<(p.num_tris + kThreads - 1) / kThreads, kThreads, 0, s>>>(p);
+  return 1;
+}
+
+int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
+                uint32_t *total, cudaStream_t s)
+{
+  k_scan<<<1, 1024, 0, s>>>(tile_count, tile_offset, tile_cursor, ntiles, total);
+  return 1;
+}
+
+int launch_fill(const Vb200SetupParams &p, const uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t *list,
+                uint32_t capacity, cudaStream_t s)
+{
+  if(!p.num_tris)
+    return 0;
+  k_fill<<<(p.num_tris + kThreads - 1) / kThreads, kThreads, 0, s>>>(p, tile_offset, tile_cursor, list, capacity);
+  return 1;
+}
+
+int launch_sort(uint32_t *list, const uint32_t *tile_offset, const uint32_t *tile_count, uint32_t ntiles,
+                cudaStream_t s)
+{
+  k_sort<<<ntiles, kThreads, 0, s>>>(list, tile_offset, tile_count);
+  return 1;
+}
+
+int launch_sample(const Vb200Image &img, int cube, uint64_t byte_offset, const float *uvw, float4 *out,
+                  size_t count, cudaStream_t s)
+{
+  if(!count)
+    return 0;
+  k_sample<<<(uint32_t)((count + kThreads - 1) / kThreads), kThreads, 0, s>>>(img, cube, byte_offset, uvw, out,
+                                                                               count);
+  return 1;
+}
+
+int launch_tiles_pack(const uint32_t *color, uint32_t width, uint32_t height, uint32_t rank, uint32_t world,
+                      uint32_t *dst, cudaStream_t s)
+{
+  const uint32_t tiles_x = (width + VB200_TILE - 1) / VB200_TILE, tiles_y = (height + VB200_TILE - 1) / VB200_TILE;
+  const uint32_t ntiles = tiles_x * tiles_y;
+  const uint32_t slots = (ntiles + world - 1) / world;
+  k_tiles_pack<<<slots, kThreads, 0, s>>>(color, width, height, tiles_x, ntiles, rank, world, dst);
+  return 1;
+}
+
+int launch_tiles_unpack(uint32_t *color, uint32_t width, uint32_t height, uint32_t world, uint32_t slots_per_rank,
+                        const uint32_t *src, cudaStream_t s)
+{
+  const uint32_t tiles_x = (width + VB200_TILE - 1) / VB200_TILE, tiles_y = (height + VB200_TILE - 1) / VB200_TILE;
+  const uint32_t ntiles = tiles_x * tiles_y;
+  k_tiles_unpack<<<ntiles, kThreads, 0, s>>>(color, width, height, tiles_x, ntiles, world, slots_per_rank, src);
+  return 1;
+}
+}    // namespace vb200

@@ -1,0 +1,67 @@
+// kernels.h — host-callable launchers of the shader-independent kernels (fixed.cu) and the parameter
+// blocks of the JIT-linked kernels (scaffold.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "device_types.h"
+
+struct Vb200SetupParams
+{
+  const void *ib;    // device address of ib.buffer->bytes + ib.offset
+  uint32_t index_type, indexed, first, num_tris, topology;
+  const uint32_t *range;    // indexed: device {minIndex, maxIndex}; slot = index - minIndex
+  uint32_t base_vertex;     // non-indexed: slot = vertex - base_vertex
+  uint32_t capacity;        // number of valid post-VS records
+  const Vb200RasterVertex *rv;
+  Vb200TriSetup *setup;
+  uint32_t *tile_count;
+  Vb200DrawCounters *counters;
+  uint32_t front_face, cull_mode;
+  uint32_t width, height, tiles_x, tiles_y, owner_rank, owner_world;
+};
+
+// parameter blocks of scaffold.cu (must match the definitions there)
+struct Vb200VertexParams
+{
+  const uint32_t *range;
+  uint32_t base_vertex;
+  uint32_t count;
+  Vb200RasterVertex *rv;
+  float4 *interps;
+  uint32_t nslots;
+  uint32_t width, height;
+};
+struct Vb200TileParams
+{
+  const Vb200TriSetup *setup;
+  const uint32_t *list;
+  const uint32_t *tile_offset;
+  const uint32_t *tile_count;
+  uint32_t *color;
+  float *depth;
+  const float4 *interps;
+  Vb200DrawCounters *counters;
+  Vb200RasterState rs;
+};
+
+namespace vb200
+{
+// every launcher returns the number of kernel launches it issued (for vb200_stats::kernel_launches)
+int launch_clear_u32(uint32_t *dst, uint32_t value, size_t count, cudaStream_t s);
+int launch_clear_u8(uint8_t *dst, uint8_t value, size_t count, cudaStream_t s);
+int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint32_t count, uint32_t *range,
+                       cudaStream_t s);
+int launch_setup(const Vb200SetupParams &p, cudaStream_t s);
+int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
+                uint32_t *total, cudaStream_t s);
+int launch_fill(const Vb200SetupParams &p, const uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t *list,
+                uint32_t capacity, cudaStream_t s);
+int launch_sort(uint32_t *list, const uint32_t *tile_offset, const uint32_t *tile_count, uint32_t ntiles,
+                cudaStream_t s);
+int launch_sample(const Vb200Image &img, int cube, uint64_t byte_offset, const float *uvw, float4 *out,
+                  size_t count, cudaStream_t s);
+int launch_tiles_pack(const uint32_t *color, uint32_t width, uint32_t height, uint32_t rank, uint32_t world,
+                      uint32_t *dst, cudaStream_t s);
+int launch_tiles_unpack(uint32_t *color, uint32_t width, uint32_t height, uint32_t world, uint32_t slots_per_rank,
+                        const uint32_t *src, cudaStream_t s);
+}    // namespace vb200

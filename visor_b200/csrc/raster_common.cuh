@@ -1,0 +1,180 @@
+// raster_common.cuh — device helpers shared by scaffold.cu (JIT-linked kernels) and fixed.cu.
+// All float arithmetic is explicit round-to-nearest, unfused, in the reference's order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "device_types.h"
+
+// int(float) as the reference's x86-64 build performs it (cvttss2si): truncation toward zero,
+// 0x80000000 for NaN and out-of-range inputs.
+__device__ __forceinline__ int vb200_cvtt(float f)
+{
+  return (fabsf(f) < 2147483648.0f) ? __float2int_rz(f) : (int)0x80000000;
+}
+
+__device__ __forceinline__ float vb200_ld_f32_unaligned(const uint8_t *p)
+{
+  if((((uintptr_t)p) & 3) == 0)
+    return __ldg((const float *)p);
+  uint32_t u = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
+               ((uint32_t)__ldg(p + 3) << 24);
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ Vb200TriSetup vb200_load_setup(const Vb200TriSetup *s)
+{
+  // 64-byte record = four 16-byte read-only loads
+  const int4 *q = (const int4 *)s;
+  const int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  Vb200TriSetup r;
+  r.x0 = a.x; r.y0 = a.y; r.x1 = a.z; r.y1 = a.w;
+  r.x2 = b.x; r.y2 = b.y; r.invw0 = __int_as_float(b.z); r.invw1 = __int_as_float(b.w);
+  r.invw2 = __int_as_float(c.x); r.d0 = __int_as_float(c.y); r.d1 = __int_as_float(c.z); r.d2 = __int_as_float(c.w);
+  r.s0 = (uint32_t)d.x; r.s1 = (uint32_t)d.y; r.s2 = (uint32_t)d.z; r.tiles = (uint32_t)d.w;
+  return r;
+}
+
+// rasterizer.cpp:562-576
+__device__ __forceinline__ bool vb200_depth_pass(uint32_t op, float pixdepth, float curdepth)
+{
+  switch(op)
+  {
+    case 0: return false;                   // NEVER
+    case 1: return pixdepth < curdepth;     // LESS
+    case 2: return pixdepth == curdepth;    // EQUAL
+    case 3: return pixdepth <= curdepth;    // LESS_OR_EQUAL
+    case 4: return pixdepth > curdepth;     // GREATER
+    case 5: return pixdepth != curdepth;    // NOT_EQUAL
+    case 6: return pixdepth >= curdepth;    // GREATER_OR_EQUAL
+    default: return true;
+  }
+}
+
+__device__ __forceinline__ float vb200_clamp01(float in)
+{
+  return in > 1.0f ? 1.0f : (in < 0.0f ? 0.0f : in);    // rasterizer.cpp:277-280
+}
+
+__device__ __forceinline__ float vb200_blend_factor(uint32_t f, float alpha)
+{
+  switch(f)    // rasterizer.cpp:601-653: four factors, anything else stays 1.0
+  {
+    case 0: return 0.0f;                      // ZERO
+    case 1: return 1.0f;                      // ONE
+    case 6: return alpha;                     // SRC_ALPHA
+    case 7: return __fsub_rn(1.0f, alpha);    // ONE_MINUS_SRC_ALPHA
+    default: return 1.0f;
+  }
+}
+
+// blend (rasterizer.cpp:593-672) + truncating BGR store, alpha byte untouched (:674-676).
+// `cur` is the pixel's 32-bit word: byte0 = B, byte1 = G, byte2 = R, byte3 = A.
+__device__ __forceinline__ uint32_t vb200_blend_store(const Vb200RasterState &rs, float4 pix, uint32_t cur)
+{
+  if(rs.blend_enable)
+  {
+    const float ex = __fdiv_rn((float)((cur >> 16) & 0xffu), 255.0f);
+    const float ey = __fdiv_rn((float)((cur >> 8) & 0xffu), 255.0f);
+    const float ez = __fdiv_rn((float)(cur & 0xffu), 255.0f);
+    const float srcF = vb200_blend_factor(rs.src_factor, pix.w);
+    const float dstF = vb200_blend_factor(rs.dst_factor, pix.w);
+    if(rs.blend_op == 0u)    // VK_BLEND_OP_ADD; other ops are outside the reference's defined domain
+    {
+      pix.x = __fadd_rn(__fmul_rn(srcF, pix.x), __fmul_rn(dstF, ex));
+      pix.y = __fadd_rn(__fmul_rn(srcF, pix.y), __fmul_rn(dstF, ey));
+      pix.z = __fadd_rn(__fmul_rn(srcF, pix.z), __fmul_rn(dstF, ez));
+    }
+  }
+  const uint32_t r = (uint32_t)__float2int_rz(__fmul_rn(vb200_clamp01(pix.x), 255.0f)) & 0xffu;
+  const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(vb200_clamp01(pix.y), 255.0f)) & 0xffu;
+  const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(vb200_clamp01(pix.z), 255.0f)) & 0xffu;
+  return (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
+}
+
+__device__ __forceinline__ void vb200_count_fragments(Vb200DrawCounters *c, uint32_t covered, uint32_t shaded)
+{
+  for(int o = 16; o > 0; o >>= 1)
+  {
+    covered += __shfl_down_sync(0xffffffffu, covered, o);
+    shaded += __shfl_down_sync(0xffffffffu, shaded, o);
+  }
+  if((threadIdx.x & 31) == 0 && (covered | shaded))
+  {
+    atomicAdd(&c->fragments_covered, (unsigned long long)covered);
+    atomicAdd(&c->fragments_shaded, (unsigned long long)shaded);
+  }
+}
+
+// ---- texture unit --------------------------------------------------------------------------
+// One texel as CacheCoord converts it (texture_sampling.cpp:121-133): channel c = float(byte[c])/255.0f,
+// address base + (y*width + x)*bpp.  The reference's 4x4 LRU block cache is a pure cache; here the
+// read-only L1/texture path (ld.global.nc) plays that role.
+__device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t width, uint32_t bpp, int x, int y)
+{
+  const uint8_t *p = base + ((size_t)y * width + (size_t)x) * bpp;
+  uint32_t u;
+  if(bpp == 4)
+    u = __ldg((const uint32_t *)p);
+  else
+    u = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
+        ((uint32_t)__ldg(p + 3) << 24);
+  return make_float4(__fdiv_rn((float)(u & 0xffu), 255.0f), __fdiv_rn((float)((u >> 8) & 0xffu), 255.0f),
+                     __fdiv_rn((float)((u >> 16) & 0xffu), 255.0f), __fdiv_rn((float)(u >> 24), 255.0f));
+}
+
+// sample_tex_wrapped (texture_sampling.cpp:139-184): repeat wrap, bilinear, mip 0, no half-texel offset
+__device__ __forceinline__ float4 vb200_sample_tex_impl(float u, float v, const Vb200Image *img,
+                                                        unsigned long long byteOffs)
+{
+  const uint32_t width = img->width, height = img->height, bpp = img->bpp;
+  const uint8_t *base = img->pixels + byteOffs;
+  u = __fsub_rn(u, floorf(u));
+  v = __fsub_rn(v, floorf(v));
+  u = __fmul_rn(u, (float)width);
+  v = __fmul_rn(v, (float)height);
+  const int iu0 = vb200_cvtt(u), iv0 = vb200_cvtt(v);
+  int iu1 = iu0 + 1, iv1 = iv0 + 1;
+  if(iu1 >= (int)width)
+    iu1 -= (int)width;
+  if(iv1 >= (int)height)
+    iv1 -= (int)height;
+  const float fu = __fsub_rn(u, (float)iu0), fv = __fsub_rn(v, (float)iv0);
+  const float inv_fu = __fsub_rn(1.0f, fu), inv_fv = __fsub_rn(1.0f, fv);
+  const float4 TL = vb200_texel(base, width, bpp, iu0, iv0);
+  const float4 TR = vb200_texel(base, width, bpp, iu1, iv0);
+  const float4 BL = vb200_texel(base, width, bpp, iu0, iv1);
+  const float4 BR = vb200_texel(base, width, bpp, iu1, iv1);
+  float4 top, bottom, out;
+  top.x = __fadd_rn(__fmul_rn(TL.x, inv_fu), __fmul_rn(TR.x, fu));
+  top.y = __fadd_rn(__fmul_rn(TL.y, inv_fu), __fmul_rn(TR.y, fu));
+  top.z = __fadd_rn(__fmul_rn(TL.z, inv_fu), __fmul_rn(TR.z, fu));
+  top.w = __fadd_rn(__fmul_rn(TL.w, inv_fu), __fmul_rn(TR.w, fu));
+  bottom.x = __fadd_rn(__fmul_rn(BL.x, inv_fu), __fmul_rn(BR.x, fu));
+  bottom.y = __fadd_rn(__fmul_rn(BL.y, inv_fu), __fmul_rn(BR.y, fu));
+  bottom.z = __fadd_rn(__fmul_rn(BL.z, inv_fu), __fmul_rn(BR.z, fu));
+  bottom.w = __fadd_rn(__fmul_rn(BL.w, inv_fu), __fmul_rn(BR.w, fu));
+  out.x = __fadd_rn(__fmul_rn(top.x, inv_fv), __fmul_rn(bottom.x, fv));
+  out.y = __fadd_rn(__fmul_rn(top.y, inv_fv), __fmul_rn(bottom.y, fv));
+  out.z = __fadd_rn(__fmul_rn(top.z, inv_fv), __fmul_rn(bottom.z, fv));
+  out.w = __fadd_rn(__fmul_rn(top.w, inv_fv), __fmul_rn(bottom.w, fv));
+  return out;
+}
+
+// sample_cube_wrapped (texture_sampling.cpp:186-250): six tests in sequence, later matches win;
+// layer offset = CalcSubresourceByteOffset(tex, 0, face) = face * full-mip-chain size.
+__device__ __forceinline__ float4 vb200_sample_cube_impl(float x, float y, float z, const Vb200Image *img)
+{
+  const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+  const bool px = x > 0.0f, py = y > 0.0f, pz = z > 0.0f;
+  float axis = 0.0f, u = 0.0f, v = 0.0f;
+  uint32_t face = 0;
+  if(px && ax >= ay && ax >= az)  { axis = ax; u = -z; v = -y; face = 0; }
+  if(!px && ax >= ay && ax >= az) { axis = ax; u = z;  v = -y; face = 1; }
+  if(py && ay >= ax && ay >= az)  { axis = ay; u = x;  v = z;  face = 2; }
+  if(!py && ay >= ax && ay >= az) { axis = ay; u = x;  v = -z; face = 3; }
+  if(pz && az >= ax && az >= ay)  { axis = az; u = x;  v = -y; face = 4; }
+  if(!pz && az >= ax && az >= ay) { axis = az; u = -x; v = -y; face = 5; }
+  const float su = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(u, axis), 1.0f));
+  const float sv = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(v, axis), 1.0f));
+  return vb200_sample_tex_impl(su, sv, img, (unsigned long long)face * img->slice_bytes);
+}

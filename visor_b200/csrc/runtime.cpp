@@ -1,0 +1,1211 @@
+// runtime.cpp — implementation of the C-ABI in include/visor_b200.h.
+//
+// Host side of the B200 draw path: owns the CUDA stream, the HBM mirrors of the application's host
+// memory (VkDeviceMemory semantics, memory.cpp:5-41), the per-pipeline JIT cache
+// (SPIR-V -> PTX -> nvJitLink -> cudaLibrary) and the launch sequence that replaces DrawTriangles
+// (rasterizer.cpp:363-520):
+//
+//   [index range] -> K1 vertex (JIT) -> K2 setup+count -> scan -> fill -> per-tile sort -> K4 tiles (JIT)
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point
+// returns VB200_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <nvJitLink.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/visor_b200.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "spirv_ptx.h"
+
+extern "C" const unsigned char vb200_scaffold_cubin[];
+extern "C" const unsigned long long vb200_scaffold_cubin_size;
+
+struct vb200_entry
+{
+  vb200::ShaderEntry e;
+  vb200_shader *owner;
+  uint64_t serial;
+};
+struct vb200_shader
+{
+  std::unique_ptr<vb200::ShaderModule> mod;
+  std::vector<std::unique_ptr<vb200_entry>> entries;
+};
+
+namespace
+{
+std::string g_error;
+uint64_t g_serial = 1;
+
+int setError(int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+struct Pipeline
+{
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t k_vertex = nullptr, k_tile_ordered = nullptr;
+  uint32_t nslots = 1;
+};
+
+struct Mirror
+{
+  uint8_t *host = nullptr;
+  size_t size = 0;
+  uint8_t *dev = nullptr;
+  bool pinned = false;       // page-locked by vb200_mem_register (caller guarantees lifetime)
+  bool explicitReg = false;
+  uint64_t lastUse = 0;
+  std::vector<std::pair<size_t, size_t>> uploaded;    // (offset, size) uploaded this epoch
+  std::vector<std::pair<size_t, size_t>> written;     // (offset, size) written by kernels this epoch
+};
+
+template <typename T>
+struct DevBuf
+{
+  T *p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t n)
+  {
+    if(n <= cap)
+      return true;
+    if(p)
+      cudaFree(p);
+    p = nullptr;
+    size_t want = std::max(n, cap + cap / 2);
+    if(cudaMalloc((void **)&p, want * sizeof(T)) != cudaSuccess)
+    {
+      cap = 0;
+      return false;
+    }
+    cap = want;
+    return true;
+  }
+  void release()
+  {
+    if(p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Context
+{
+  bool ready = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int syncMode = VB200_SYNC_COHERENT;
+  uint64_t epoch = 1;
+  std::map<uintptr_t, Mirror> mirrors;
+  std::map<std::pair<uint64_t, uint64_t>, Pipeline> pipelines;
+  // scratch
+  DevBuf<Vb200RasterVertex> rv;
+  DevBuf<float4> interps;
+  DevBuf<Vb200TriSetup> setup;
+  DevBuf<uint32_t> tileCount, tileOffset, tileCursor, list;
+  uint32_t *range = nullptr;                // device {min,max}
+  uint32_t *total = nullptr;                // device
+  uint32_t *totalHost = nullptr;            // pinned
+  Vb200DrawCounters *counters = nullptr;    // device
+  vb200_stats stats;
+  uint32_t ownerRank = 0, ownerWorld = 1;
+  int64_t optRasterPath = 0, optCountFragments = 0;
+  int stickyCuda = 0;
+} g;
+
+#define CU(call)                                                                                       \
+  do                                                                                                   \
+  {                                                                                                    \
+    cudaError_t _e = (call);                                                                           \
+    if(_e != cudaSuccess)                                                                              \
+    {                                                                                                  \
+      g.stickyCuda = 1;                                                                                \
+      return setError(VB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                      __LINE__);                                                                       \
+    }                                                                                                  \
+  } while(0)
+
+int requireReady()
+{
+  if(!g.ready)
+  {
+    int rc = vb200_init(0);
+    if(rc != VB200_OK)
+      return rc;
+  }
+  if(g.stickyCuda)
+    return setError(VB200_ERR_CUDA, "a previous CUDA error is sticky: %s", g_error.c_str());
+  return VB200_OK;
+}
+
+bool isDevicePointer(const void *p)
+{
+  cudaPointerAttributes a;
+  if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ---- residency -------------------------------------------------------------------------------
+Mirror *findMirror(const void *host, size_t size)
+{
+  uintptr_t a = (uintptr_t)host;
+  auto it = g.mirrors.upper_bound(a);
+  if(it == g.mirrors.begin())
+    return nullptr;
+  --it;
+  Mirror &m = it->second;
+  if(a >= (uintptr_t)m.host && a + size <= (uintptr_t)m.host + m.size)
+    return &m;
+  return nullptr;
+}
+
+int createMirror(void *host, size_t size, bool pin, Mirror **out)
+{
+  // merge with anything the new range overlaps (aliased buffers of one allocation)
+  uintptr_t lo = (uintptr_t)host, hi = lo + size;
+  std::vector<uintptr_t> victims;
+  for(auto &kv : g.mirrors)
+  {
+    uintptr_t mlo = (uintptr_t)kv.second.host, mhi = mlo + kv.second.size;
+    if(mlo < hi && lo < mhi)
+    {
+      victims.push_back(kv.first);
+      lo = std::min(lo, mlo);
+      hi = std::max(hi, mhi);
+    }
+  }
+  Mirror nm;
+  nm.host = (uint8_t *)lo;
+  nm.size = hi - lo;
+  CU(cudaMalloc((void **)&nm.dev, std::max<size_t>(nm.size + 16, 256)));
+  for(uintptr_t key : victims)
+  {
+    Mirror &old = g.mirrors[key];
+    // keep device-side contents (attachments may hold results not yet downloaded)
+    CU(cudaMemcpyAsync(nm.dev + ((uintptr_t)old.host - lo), old.dev, old.size, cudaMemcpyDeviceToDevice, g.stream));
+    for(auto &w : old.written)
+      nm.written.push_back({w.first + ((uintptr_t)old.host - lo), w.second});
+    for(auto &u : old.uploaded)
+      nm.uploaded.push_back({u.first + ((uintptr_t)old.host - lo), u.second});
+    if(old.pinned)
+      cudaHostUnregister(old.host);
+    CU(cudaStreamSynchronize(g.stream));
+    cudaFree(old.dev);
+    nm.explicitReg |= old.explicitReg;
+    g.mirrors.erase(key);
+  }
+  if(pin)
+  {
+    if(cudaHostRegister(nm.host, nm.size, cudaHostRegisterDefault) == cudaSuccess)
+      nm.pinned = true;
+    else
+      cudaGetLastError();    // pageable copies still work
+    nm.explicitReg = true;
+  }
+  nm.lastUse = g.epoch;
+  auto ins = g.mirrors.emplace(lo, nm);
+  *out = &ins.first->second;
+  return VB200_OK;
+}
+
+bool rangeCovered(const std::vector<std::pair<size_t, size_t>> &v, size_t off, size_t size)
+{
+  for(auto &r : v)
+    if(off >= r.first && off + size <= r.first + r.second)
+      return true;
+  return false;
+}
+
+enum Access
+{
+  ACC_READ = 1,       // kernel reads host-authored data: upload on first use per epoch (coherent mode)
+  ACC_WRITE = 2,      // kernel writes: download at flush (coherent mode)
+  ACC_OVERWRITE = 4,  // the whole range is overwritten first: no upload needed
+};
+
+// host (or device) pointer -> device pointer usable by kernels
+int resolve(const void *ptr, size_t size, int access, uint8_t **out)
+{
+  *out = nullptr;
+  if(!ptr)
+    return setError(VB200_ERR_INVALID, "NULL resource pointer");
+  if(isDevicePointer(ptr))
+  {
+    *out = (uint8_t *)ptr;
+    return VB200_OK;
+  }
+  Mirror *m = findMirror(ptr, size);
+  if(!m)
+  {
+    int rc = createMirror((void *)ptr, size, false, &m);
+    if(rc)
+      return rc;
+  }
+  m->lastUse = g.epoch;
+  const size_t off = (uintptr_t)ptr - (uintptr_t)m->host;
+  if(g.syncMode == VB200_SYNC_COHERENT)
+  {
+    const bool devNewer = rangeCovered(m->written, off, size);
+    if((access & ACC_READ) && !(access & ACC_OVERWRITE) && !devNewer && !rangeCovered(m->uploaded, off, size))
+    {
+      CU(cudaMemcpyAsync(m->dev + off, ptr, size, cudaMemcpyHostToDevice, g.stream));
+      g.stats.h2d_bytes += size;
+      m->uploaded.push_back({off, size});
+    }
+    if((access & (ACC_WRITE | ACC_OVERWRITE)) && !devNewer)
+      m->written.push_back({off, size});
+  }
+  *out = m->dev + off;
+  return VB200_OK;
+}
+
+// ---- JIT -------------------------------------------------------------------------------------
+// nvJitLink step: scaffold cubin + VS PTX + FS PTX -> one sm_100a cubin. Needs no device.
+int linkCubin(const vb200_entry *vs, const vb200_entry *fs, std::vector<char> &cubin)
+{
+  nvJitLinkHandle h;
+  const char *opts[] = {"-arch=sm_100a", "-lineinfo"};
+  if(nvJitLinkCreate(&h, 2, opts) != NVJITLINK_SUCCESS)
+    return setError(VB200_ERR_LINK, "nvJitLinkCreate failed");
+  auto logOf = [&](std::string &s) {
+    size_t n = 0;
+    if(nvJitLinkGetErrorLogSize(h, &n) == NVJITLINK_SUCCESS && n > 1)
+    {
+      s.resize(n);
+      nvJitLinkGetErrorLog(h, &s[0]);
+    }
+  };
+  nvJitLinkResult r = nvJitLinkAddData(h, NVJITLINK_INPUT_CUBIN, vb200_scaffold_cubin,
+                                       (size_t)vb200_scaffold_cubin_size, "scaffold");
+  if(r == NVJITLINK_SUCCESS)
+    r = nvJitLinkAddData(h, NVJITLINK_INPUT_PTX, vs->e.ptx.c_str(), vs->e.ptx.size() + 1, "vs");
+  if(r == NVJITLINK_SUCCESS)
+    r = nvJitLinkAddData(h, NVJITLINK_INPUT_PTX, fs->e.ptx.c_str(), fs->e.ptx.size() + 1, "fs");
+  if(r == NVJITLINK_SUCCESS)
+    r = nvJitLinkComplete(h);
+  if(r != NVJITLINK_SUCCESS)
+  {
+    std::string log;
+    logOf(log);
+    nvJitLinkDestroy(&h);
+    return setError(VB200_ERR_LINK, "nvJitLink failed (%d): %s", (int)r, log.c_str());
+  }
+  size_t sz = 0;
+  nvJitLinkGetLinkedCubinSize(h, &sz);
+  cubin.resize(sz);
+  nvJitLinkGetLinkedCubin(h, cubin.data());
+  nvJitLinkDestroy(&h);
+  return VB200_OK;
+}
+
+int linkPipeline(const vb200_entry *vs, const vb200_entry *fs, Pipeline **out)
+{
+  auto key = std::make_pair(vs->serial, fs->serial);
+  auto it = g.pipelines.find(key);
+  if(it != g.pipelines.end())
+  {
+    *out = &it->second;
+    return VB200_OK;
+  }
+  std::vector<char> cubin;
+  int lrc = linkCubin(vs, fs, cubin);
+  if(lrc)
+    return lrc;
+
+  Pipeline p;
+  cudaError_t e = cudaLibraryLoadData(&p.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if(e != cudaSuccess)
+    return setError(VB200_ERR_LINK, "cudaLibraryLoadData failed: %s", cudaGetErrorString(e));
+  e = cudaLibraryGetKernel(&p.k_vertex, p.lib, "vb200_k_vertex");
+  if(e == cudaSuccess)
+    e = cudaLibraryGetKernel(&p.k_tile_ordered, p.lib, "vb200_k_tile_ordered");
+  if(e != cudaSuccess)
+  {
+    cudaLibraryUnload(p.lib);
+    return setError(VB200_ERR_LINK, "cudaLibraryGetKernel failed: %s", cudaGetErrorString(e));
+  }
+  uint32_t mask = vs->e.out_slot_mask | fs->e.in_slot_mask;
+  p.nslots = 1;
+  for(uint32_t s = 0; s < VB200_MAX_SLOTS; s++)
+    if(mask & (1u << s))
+      p.nslots = s + 1;
+  auto ins = g.pipelines.emplace(key, p);
+  *out = &ins.first->second;
+  return VB200_OK;
+}
+
+uint32_t formatBytes(uint32_t fmt)
+{
+  switch(fmt)
+  {
+    case 109: case 107: case 108: return 16;
+    case 106: case 104: case 105: return 12;
+    case 103: case 101: case 102: return 8;
+    case 100: case 98: case 99: return 4;
+    case 37: return 4;
+    default: return 0;
+  }
+}
+
+uint64_t sliceBytes(const vb200_image &im)
+{
+  // CalcSubresourceByteOffset (precompiled.cpp:18-33): full mip chain of one layer
+  uint32_t mw = im.width, mh = im.height;
+  uint64_t slice = 0;
+  for(uint32_t m = 0; m < im.mip_levels; m++)
+  {
+    slice += (uint64_t)(mw * mh * im.bytes_per_pixel);
+    mw = std::max(1u, mw >> 1);
+    mh = std::max(1u, mh >> 1);
+  }
+  return slice;
+}
+
+uint64_t imageBytes(const vb200_image &im)
+{
+  // vkGetImageMemoryRequirements (images.cpp:51-65)
+  uint64_t sz = (uint64_t)im.width * im.height * std::max(1u, im.array_layers) * im.bytes_per_pixel;
+  if(im.mip_levels > 1)
+    sz *= 2;
+  return sz;
+}
+
+const vb200_binding *findBinding(const vb200_draw_state *s, uint32_t set, uint32_t binding)
+{
+  for(uint32_t i = 0; i < s->num_bindings; i++)
+    if(s->bindings[i].set == set && s->bindings[i].binding == binding)
+      return &s->bindings[i];
+  return nullptr;
+}
+
+int fillResources(const vb200_draw_state *s, const vb200::ShaderEntry &e, Vb200Env &env)
+{
+  for(const vb200::ResourceSlot &r : e.resources)
+  {
+    const vb200_binding *b = findBinding(s, r.set, r.binding);
+    if(!b)
+      return setError(VB200_ERR_INVALID, "shader reads descriptor (set %u, binding %u) which is not bound", r.set,
+                      r.binding);
+    if(r.is_image)
+    {
+      if(!b->is_image)
+        return setError(VB200_ERR_INVALID, "descriptor (%u,%u) is not an image", r.set, r.binding);
+      const vb200_image &im = b->image;
+      if(im.format == 135 || im.format == 137)    // BC2 / BC3
+        return setError(VB200_ERR_INVALID, "BC2/BC3 sampling is not implemented on the device path yet");
+      if((im.width & 3) || (im.height & 3))
+        return setError(VB200_ERR_INVALID, "texture size must be a multiple of 4 (texture_sampling.cpp:123-133)");
+      uint8_t *dev;
+      int rc = resolve(im.pixels, imageBytes(im) + 4, ACC_READ, &dev);    // +4: bpp<4 reads 4 bytes per texel
+      if(rc)
+        return rc;
+      Vb200Image &d = env.images[r.slot];
+      d.pixels = dev;
+      d.width = im.width;
+      d.height = im.height;
+      d.bpp = im.bytes_per_pixel;
+      d.format = im.format;
+      d.mips = im.mip_levels;
+      d.layers = im.array_layers;
+      d.slice_bytes = sliceBytes(im);
+    }
+    else
+    {
+      if(b->is_image)
+        return setError(VB200_ERR_INVALID, "descriptor (%u,%u) is not a buffer", r.set, r.binding);
+      if(b->offset > b->buffer.size)
+        return setError(VB200_ERR_INVALID, "descriptor offset beyond buffer");
+      uint8_t *dev;
+      int rc = resolve(b->buffer.bytes, b->buffer.size, ACC_READ, &dev);
+      if(rc)
+        return rc;
+      if(((uintptr_t)(dev + b->offset)) & 15)
+        return setError(VB200_ERR_INVALID, "uniform buffer address must be 16-byte aligned");
+      env.res[r.slot] = dev + b->offset;
+    }
+  }
+  return VB200_OK;
+}
+
+int launchKernel(cudaKernel_t k, dim3 grid, dim3 block, void **args)
+{
+  CU(cudaLaunchKernel((const void *)k, grid, block, args, 0, g.stream));
+  g.stats.kernel_launches++;
+  return VB200_OK;
+}
+
+int checkTarget(const vb200_image *im, const char *what)
+{
+  if(!im || !im->pixels)
+    return setError(VB200_ERR_INVALID, "%s: no image memory", what);
+  if(im->width == 0 || im->height == 0 || im->width > 8192 || im->height > 8192)
+    return setError(VB200_ERR_INVALID, "%s: extent %ux%u outside 1..8192", what, im->width, im->height);
+  return VB200_OK;
+}
+}    // namespace
+
+// =================================================================================================
+extern "C" {
+
+int vb200_abi_version(void)
+{
+  return VB200_ABI_VERSION;
+}
+
+const char *vb200_last_error(void)
+{
+  return g_error.c_str();
+}
+
+int vb200_init(int device)
+{
+  if(g.ready)
+    return VB200_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if(e != cudaSuccess || n <= 0)
+  {
+    cudaGetLastError();
+    return setError(VB200_ERR_NO_DEVICE, "no CUDA device available (%s); visor_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if(device < 0 || device >= n)
+    return setError(VB200_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  CU(cudaSetDevice(device));
+  g.device = device;
+  CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CU(cudaMalloc((void **)&g.range, 2 * sizeof(uint32_t)));
+  CU(cudaMalloc((void **)&g.total, sizeof(uint32_t)));
+  CU(cudaMallocHost((void **)&g.totalHost, sizeof(uint32_t)));
+  CU(cudaMalloc((void **)&g.counters, sizeof(Vb200DrawCounters)));
+  CU(cudaMemsetAsync(g.counters, 0, sizeof(Vb200DrawCounters), g.stream));
+  memset(&g.stats, 0, sizeof(g.stats));
+  g.ready = true;
+  g.stickyCuda = 0;
+  return VB200_OK;
+}
+
+void vb200_shutdown(void)
+{
+  if(!g.ready)
+    return;
+  cudaStreamSynchronize(g.stream);
+  for(auto &kv : g.pipelines)
+    cudaLibraryUnload(kv.second.lib);
+  g.pipelines.clear();
+  for(auto &kv : g.mirrors)
+  {
+    if(kv.second.pinned)
+      cudaHostUnregister(kv.second.host);
+    cudaFree(kv.second.dev);
+  }
+  g.mirrors.clear();
+  g.rv.release();
+  g.interps.release();
+  g.setup.release();
+  g.tileCount.release();
+  g.tileOffset.release();
+  g.tileCursor.release();
+  g.list.release();
+  cudaFree(g.range);
+  cudaFree(g.total);
+  cudaFreeHost(g.totalHost);
+  cudaFree(g.counters);
+  cudaStreamDestroy(g.stream);
+  g.ready = false;
+}
+
+void *vb200_stream(void)
+{
+  return g.ready ? (void *)g.stream : nullptr;
+}
+
+// ---- shaders ---------------------------------------------------------------------------------
+vb200_shader *vb200_shader_create(const uint32_t *code, size_t words)
+{
+  if(!code || words < 5)
+  {
+    setError(VB200_ERR_SPIRV, "empty SPIR-V module");
+    return nullptr;
+  }
+  std::string err;
+  vb200::ShaderModule *m = vb200::compile_spirv(code, words, &err);
+  if(!m)
+  {
+    setError(VB200_ERR_SPIRV, "CompileFunction: %s", err.c_str());
+    return nullptr;
+  }
+  vb200_shader *s = new vb200_shader;
+  s->mod.reset(m);
+  for(vb200::ShaderEntry &e : m->entries)
+  {
+    std::unique_ptr<vb200_entry> en(new vb200_entry);
+    en->e = e;
+    en->owner = s;
+    en->serial = g_serial++;
+    s->entries.push_back(std::move(en));
+  }
+  return s;
+}
+
+vb200_entry *vb200_shader_entry(vb200_shader *shader, const char *name)
+{
+  if(!shader || !name)
+    return nullptr;
+  for(auto &e : shader->entries)
+    if(e->e.name == name)
+      return e.get();
+  setError(VB200_ERR_INVALID, "GetFuncPointer: no entry point named '%s'", name);
+  return nullptr;
+}
+
+void vb200_shader_destroy(vb200_shader *shader)
+{
+  if(!shader)
+    return;
+  // drop pipelines linked from this module's entries
+  for(auto &e : shader->entries)
+    for(auto it = g.pipelines.begin(); it != g.pipelines.end();)
+    {
+      if(it->first.first == e->serial || it->first.second == e->serial)
+      {
+        if(g.ready)
+        {
+          cudaStreamSynchronize(g.stream);
+          cudaLibraryUnload(it->second.lib);
+        }
+        it = g.pipelines.erase(it);
+      }
+      else
+        ++it;
+    }
+  delete shader;
+}
+
+int vb200_link_check(const vb200_entry *vs, const vb200_entry *fs, uint64_t *cubin_size)
+{
+  if(!vs || !fs || vs->e.stage != vb200::STAGE_VERTEX || fs->e.stage != vb200::STAGE_FRAGMENT)
+    return setError(VB200_ERR_INVALID, "link_check needs one vertex and one fragment entry");
+  std::vector<char> cubin;
+  int rc = linkCubin(vs, fs, cubin);
+  if(rc == VB200_OK && cubin_size)
+    *cubin_size = cubin.size();
+  return rc;
+}
+
+const char *vb200_entry_ptx(const vb200_entry *entry)
+{
+  return entry ? entry->e.ptx.c_str() : nullptr;
+}
+
+int vb200_entry_stage(const vb200_entry *entry)
+{
+  return entry ? entry->e.stage : -1;
+}
+
+// ---- residency -------------------------------------------------------------------------------
+int vb200_set_sync_mode(int mode)
+{
+  if(mode != VB200_SYNC_COHERENT && mode != VB200_SYNC_EXPLICIT)
+    return setError(VB200_ERR_INVALID, "unknown sync mode %d", mode);
+  g.syncMode = mode;
+  return VB200_OK;
+}
+
+int vb200_mem_register(void *host, uint64_t size)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(!host || !size)
+    return setError(VB200_ERR_INVALID, "mem_register: empty range");
+  if(isDevicePointer(host))
+    return VB200_OK;
+  Mirror *m = findMirror(host, size);
+  if(m)
+  {
+    if(!m->pinned && cudaHostRegister(m->host, m->size, cudaHostRegisterDefault) == cudaSuccess)
+      m->pinned = true;
+    else
+      cudaGetLastError();
+    m->explicitReg = true;
+    return VB200_OK;
+  }
+  return createMirror(host, size, true, &m);
+}
+
+int vb200_mem_unregister(void *host)
+{
+  if(!g.ready)
+    return VB200_OK;
+  auto it = g.mirrors.find((uintptr_t)host);
+  if(it == g.mirrors.end())
+  {
+    Mirror *m = findMirror(host, 1);
+    if(!m)
+      return VB200_OK;
+    it = g.mirrors.find((uintptr_t)m->host);
+  }
+  cudaStreamSynchronize(g.stream);
+  if(it->second.pinned)
+    cudaHostUnregister(it->second.host);
+  cudaFree(it->second.dev);
+  g.mirrors.erase(it);
+  return VB200_OK;
+}
+
+int vb200_mem_upload(const void *host, uint64_t size)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(isDevicePointer(host))
+    return VB200_OK;
+  Mirror *m = findMirror(host, size);
+  if(!m)
+  {
+    rc = createMirror((void *)host, size, false, &m);
+    if(rc)
+      return rc;
+  }
+  const size_t off = (uintptr_t)host - (uintptr_t)m->host;
+  CU(cudaMemcpyAsync(m->dev + off, host, size, cudaMemcpyHostToDevice, g.stream));
+  g.stats.h2d_bytes += size;
+  return VB200_OK;
+}
+
+int vb200_mem_download(void *host, uint64_t size)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(isDevicePointer(host))
+    return VB200_OK;
+  Mirror *m = findMirror(host, size);
+  if(!m)
+    return setError(VB200_ERR_INVALID, "mem_download: range is not mirrored");
+  const size_t off = (uintptr_t)host - (uintptr_t)m->host;
+  CU(cudaMemcpyAsync(host, m->dev + off, size, cudaMemcpyDeviceToHost, g.stream));
+  g.stats.d2h_bytes += size;
+  return VB200_OK;
+}
+
+void *vb200_mem_device_ptr(const void *host)
+{
+  if(!g.ready || !host)
+    return nullptr;
+  if(isDevicePointer(host))
+    return (void *)host;
+  Mirror *m = findMirror(host, 1);
+  return m ? (void *)(m->dev + ((uintptr_t)host - (uintptr_t)m->host)) : nullptr;
+}
+
+int vb200_flush(void)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(g.syncMode == VB200_SYNC_COHERENT)
+  {
+    for(auto &kv : g.mirrors)
+    {
+      Mirror &m = kv.second;
+      for(auto &w : m.written)
+      {
+        CU(cudaMemcpyAsync(m.host + w.first, m.dev + w.first, w.second, cudaMemcpyDeviceToHost, g.stream));
+        g.stats.d2h_bytes += w.second;
+      }
+    }
+  }
+  CU(cudaStreamSynchronize(g.stream));
+  cudaError_t e = cudaGetLastError();
+  if(e != cudaSuccess)
+  {
+    g.stickyCuda = 1;
+    return setError(VB200_ERR_CUDA, "asynchronous CUDA error: %s", cudaGetErrorString(e));
+  }
+  // new epoch: host memory is authoritative again
+  size_t autoBytes = 0;
+  for(auto &kv : g.mirrors)
+  {
+    kv.second.written.clear();
+    kv.second.uploaded.clear();
+    if(!kv.second.explicitReg)
+      autoBytes += kv.second.size;
+  }
+  g.epoch++;
+  if(autoBytes > ((size_t)8 << 30))
+  {
+    // drop auto-created mirrors that have not been touched for a while
+    for(auto it = g.mirrors.begin(); it != g.mirrors.end();)
+    {
+      if(!it->second.explicitReg && it->second.lastUse + 4 < g.epoch)
+      {
+        cudaFree(it->second.dev);
+        it = g.mirrors.erase(it);
+      }
+      else
+        ++it;
+    }
+  }
+  return VB200_OK;
+}
+
+// ---- operators -------------------------------------------------------------------------------
+int vb200_clear_color(const vb200_image *target, const float rgba[4])
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if((rc = checkTarget(target, "ClearTarget")))
+    return rc;
+  if(!rgba)
+    return setError(VB200_ERR_INVALID, "ClearTarget: NULL colour");
+  // rasterizer.cpp:341-345: byte(f * 255.0f) per channel (x86 truncating convert, low 8 bits), B,G,R,A order
+  auto toByte = [](float f) -> uint32_t {
+    float v = f * 255.0f;
+    int i = (v > -2147483648.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000;
+    return (uint32_t)i & 0xffu;
+  };
+  const uint32_t r = toByte(rgba[0]), gch = toByte(rgba[1]), b = toByte(rgba[2]), a = toByte(rgba[3]);
+  const size_t px = (size_t)target->width * target->height;
+  uint8_t *dev;
+  if(target->bytes_per_pixel == 4)
+  {
+    if((rc = resolve(target->pixels, px * 4, ACC_OVERWRITE, &dev)))
+      return rc;
+    g.stats.kernel_launches += vb200::launch_clear_u32((uint32_t *)dev, b | (gch << 8) | (r << 16) | (a << 24), px, g.stream);
+  }
+  else if(target->bytes_per_pixel == 1)
+  {
+    if((rc = resolve(target->pixels, px, ACC_OVERWRITE, &dev)))
+      return rc;
+    g.stats.kernel_launches += vb200::launch_clear_u8(dev, (uint8_t)r, px, g.stream);
+  }
+  // other bpp: the reference does nothing (rasterizer.cpp:347-360)
+  CU(cudaGetLastError());
+  return VB200_OK;
+}
+
+int vb200_clear_depth(const vb200_image *target, float depth)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if((rc = checkTarget(target, "ClearTarget")))
+    return rc;
+  if(target->bytes_per_pixel != 4)
+    return setError(VB200_ERR_INVALID, "depth clear requires 4 bytes per pixel (assert rasterizer.cpp:321)");
+  const size_t px = (size_t)target->width * target->height;
+  uint8_t *dev;
+  if((rc = resolve(target->pixels, px * 4, ACC_OVERWRITE, &dev)))
+    return rc;
+  uint32_t bits;
+  memcpy(&bits, &depth, 4);
+  g.stats.kernel_launches += vb200::launch_clear_u32((uint32_t *)dev, bits, px, g.stream);
+  CU(cudaGetLastError());
+  return VB200_OK;
+}
+
+int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int indexed)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(!s || !s->pipeline)
+    return setError(VB200_ERR_INVALID, "DrawTriangles: no pipeline bound");
+  const vb200_pipeline *pl = s->pipeline;
+  if(!pl->vs || !pl->fs)
+    return setError(VB200_ERR_INVALID, "DrawTriangles: pipeline has no vertex/fragment shader");
+  if(pl->vs->e.stage != vb200::STAGE_VERTEX || pl->fs->e.stage != vb200::STAGE_FRAGMENT)
+    return setError(VB200_ERR_INVALID, "DrawTriangles: shader stages do not match");
+  if((rc = checkTarget(&s->color, "DrawTriangles colour target")))
+    return rc;
+  if(s->color.bytes_per_pixel != 4)
+    return setError(VB200_ERR_INVALID, "colour target must have 4 bytes per pixel");
+  const bool hasDepth = s->depth.pixels != nullptr;
+  if(hasDepth && (s->depth.width != s->color.width || s->depth.height != s->color.height ||
+                  s->depth.bytes_per_pixel != 4))
+    return setError(VB200_ERR_INVALID, "depth target must match the colour extent and be 32-bit");
+
+  g.stats.draws++;
+  // triangle count (rasterizer.cpp:133-136: whole triangles only; :152 strips need >= 3)
+  uint32_t numTris = 0;
+  if(pl->topology == 3u)
+    numTris = num_verts >= 3 ? (uint32_t)num_verts / 3u : 0u;
+  else if(pl->topology == 4u)
+  {
+    if(num_verts < 3)
+      return setError(VB200_ERR_INVALID, "triangle strip needs >= 3 vertices (assert rasterizer.cpp:152)");
+    numTris = (uint32_t)num_verts - 2u;
+  }
+  else
+  {
+    // "Unsupported primitive topology!" (rasterizer.cpp:235): draws nothing
+    return VB200_OK;
+  }
+  g.stats.triangles_in += numTris;
+  if(numTris == 0)
+    return VB200_OK;
+  const uint32_t usedVerts = pl->topology == 3u ? numTris * 3u : numTris + 2u;
+
+  Pipeline *pipe = nullptr;
+  if((rc = linkPipeline(pl->vs, pl->fs, &pipe)))
+    return rc;
+
+  // ---- environment (device-side GPUState)
+  Vb200Env env;
+  memset(&env, 0, sizeof(env));
+  uint32_t vertexBound = 0xffffffffu;    // how many vertices the bound buffers can hold
+  for(uint32_t a = 0; a < 16; a++)
+  {
+    env.attrs[a].format = pl->vattrs[a].format;
+    env.attrs[a].stride = pl->vattrs[a].stride;
+    env.attrs[a].offset = pl->vattrs[a].offset;
+    env.attrs[a].vb = pl->vattrs[a].vb;
+    if(!(pl->vs->e.attr_mask & (1u << a)))
+      continue;
+    const uint32_t fb = formatBytes(pl->vattrs[a].format);
+    if(!fb)
+      return setError(VB200_ERR_INVALID, "Unhandled vertex attribute format %u at location %u (assert spirv_compile.cpp:625)",
+                      pl->vattrs[a].format, a);
+    if(pl->vattrs[a].vb >= 4)
+      return setError(VB200_ERR_INVALID, "vertex binding %u out of range", pl->vattrs[a].vb);
+    const auto &vb = s->vbs[pl->vattrs[a].vb];
+    if(!vb.buffer.bytes)
+      return setError(VB200_ERR_INVALID, "vertex buffer slot %u is not bound", pl->vattrs[a].vb);
+    const uint64_t start = vb.offset + pl->vattrs[a].offset;
+    if(start + fb > vb.buffer.size)
+      return setError(VB200_ERR_INVALID, "vertex attribute %u lies outside its buffer", a);
+    if(pl->vattrs[a].stride)
+    {
+      const uint64_t n = (vb.buffer.size - start - fb) / pl->vattrs[a].stride + 1;
+      vertexBound = (uint32_t)std::min<uint64_t>(vertexBound, n);
+    }
+  }
+  for(uint32_t i = 0; i < 4; i++)
+    if(s->vbs[i].buffer.bytes)
+    {
+      uint8_t *dev;
+      if((rc = resolve(s->vbs[i].buffer.bytes, s->vbs[i].buffer.size, ACC_READ, &dev)))
+        return rc;
+      env.vb[i] = dev + s->vbs[i].offset;
+    }
+  if((rc = fillResources(s, pl->vs->e, env)))
+    return rc;
+  if((rc = fillResources(s, pl->fs->e, env)))
+    return rc;
+  memcpy(env.push, s->pushconsts, 128);
+
+  // ---- index buffer / vertex range
+  const uint8_t *ibDev = nullptr;
+  uint32_t capacity, baseVertex = first;
+  if(indexed)
+  {
+    if(!s->ib.buffer.bytes)
+      return setError(VB200_ERR_INVALID, "indexed draw without an index buffer");
+    const uint32_t isz = s->ib.index_type == 0u ? 2u : 4u;
+    if(s->ib.offset + (uint64_t)(first + usedVerts) * isz > s->ib.buffer.size)
+      return setError(VB200_ERR_INVALID, "index range lies outside the index buffer");
+    uint8_t *dev;
+    if((rc = resolve(s->ib.buffer.bytes, s->ib.buffer.size, ACC_READ, &dev)))
+      return rc;
+    ibDev = dev + s->ib.offset;
+    if(((uintptr_t)ibDev) & (isz - 1))
+      return setError(VB200_ERR_INVALID, "index buffer offset is not aligned to the index size");
+    g.stats.kernel_launches += vb200::launch_index_range(ibDev, s->ib.index_type, first, usedVerts, g.range, g.stream);
+    if(vertexBound == 0xffffffffu)
+    {
+      // no strided attribute bounds the vertex count: read the range back (rare: index-only shaders)
+      uint32_t r2[2];
+      CU(cudaMemcpyAsync(r2, g.range, 8, cudaMemcpyDeviceToHost, g.stream));
+      CU(cudaStreamSynchronize(g.stream));
+      capacity = r2[1] >= r2[0] ? r2[1] - r2[0] + 1u : 0u;
+    }
+    else
+      capacity = vertexBound;
+    baseVertex = 0;
+  }
+  else
+  {
+    capacity = usedVerts;
+    if(vertexBound != 0xffffffffu && (uint64_t)first + usedVerts > vertexBound)
+      return setError(VB200_ERR_INVALID, "draw reads vertices beyond the bound vertex buffers");
+  }
+  if(capacity == 0)
+    return VB200_OK;
+
+  // ---- scratch
+  const uint32_t W = s->color.width, H = s->color.height;
+  const uint32_t tilesX = (W + VB200_TILE - 1) / VB200_TILE, tilesY = (H + VB200_TILE - 1) / VB200_TILE;
+  const uint32_t ntiles = tilesX * tilesY;
+  if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * pipe->nslots) || !g.setup.reserve(numTris) ||
+     !g.tileCount.reserve(ntiles) || !g.tileOffset.reserve(ntiles) || !g.tileCursor.reserve(ntiles))
+  {
+    g.stickyCuda = 1;
+    return setError(VB200_ERR_CUDA, "out of device memory for draw scratch");
+  }
+
+  // ---- targets
+  uint8_t *colorDev, *depthDev = nullptr;
+  if((rc = resolve(s->color.pixels, (size_t)W * H * 4, ACC_READ | ACC_WRITE, &colorDev)))
+    return rc;
+  const bool depthTest = hasDepth && pl->depth_compare_op != 7u;
+  const bool depthWrite = hasDepth && pl->depth_write_enable;
+  if(hasDepth && (depthTest || depthWrite))
+    if((rc = resolve(s->depth.pixels, (size_t)W * H * 4, ACC_READ | (depthWrite ? ACC_WRITE : 0), &depthDev)))
+      return rc;
+
+  // ---- K1: vertex stage
+  Vb200VertexParams vp;
+  vp.range = indexed ? g.range : nullptr;
+  vp.base_vertex = baseVertex;
+  vp.count = capacity;
+  vp.rv = g.rv.p;
+  vp.interps = g.interps.p;
+  vp.nslots = pipe->nslots;
+  vp.width = W;
+  vp.height = H;
+  {
+    void *args[] = {&env, &vp};
+    if((rc = launchKernel(pipe->k_vertex, dim3((capacity + 127) / 128), dim3(128), args)))
+      return rc;
+  }
+
+  // ---- K2: setup + per-tile counts
+  Vb200SetupParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.ib = ibDev;
+  sp.index_type = s->ib.index_type;
+  sp.indexed = indexed ? 1u : 0u;
+  sp.first = first;
+  sp.num_tris = numTris;
+  sp.topology = pl->topology;
+  sp.range = g.range;
+  sp.base_vertex = baseVertex;
+  sp.capacity = capacity;
+  sp.rv = g.rv.p;
+  sp.setup = g.setup.p;
+  sp.tile_count = g.tileCount.p;
+  sp.counters = g.counters;
+  sp.front_face = pl->front_face;
+  sp.cull_mode = pl->cull_mode;
+  sp.width = W;
+  sp.height = H;
+  sp.tiles_x = tilesX;
+  sp.tiles_y = tilesY;
+  sp.owner_rank = g.ownerRank;
+  sp.owner_world = g.ownerWorld;
+  CU(cudaMemsetAsync(g.tileCount.p, 0, ntiles * sizeof(uint32_t), g.stream));
+  g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);
+
+  // ---- K3: scan -> (host reads the pair total to size the list) -> fill -> sort
+  g.stats.kernel_launches += vb200::launch_scan(g.tileCount.p, g.tileOffset.p, g.tileCursor.p, ntiles, g.total, g.stream);
+  CU(cudaMemcpyAsync(g.totalHost, g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  const uint32_t pairs = *g.totalHost;
+  g.stats.tile_pairs += pairs;
+  if(pairs == 0)
+    return VB200_OK;
+  if(!g.list.reserve(pairs))
+  {
+    g.stickyCuda = 1;
+    return setError(VB200_ERR_CUDA, "out of device memory for %u tile-list entries", pairs);
+  }
+  g.stats.kernel_launches += vb200::launch_fill(sp, g.tileOffset.p, g.tileCursor.p, g.list.p, pairs, g.stream);
+  g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileOffset.p, g.tileCount.p, ntiles, g.stream);
+
+  // ---- K4: tiles
+  Vb200TileParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.setup = g.setup.p;
+  tp.list = g.list.p;
+  tp.tile_offset = g.tileOffset.p;
+  tp.tile_count = g.tileCount.p;
+  tp.color = (uint32_t *)colorDev;
+  tp.depth = (float *)depthDev;
+  tp.interps = g.interps.p;
+  tp.counters = g.counters;
+  tp.rs.width = W;
+  tp.rs.height = H;
+  tp.rs.tiles_x = tilesX;
+  tp.rs.tiles_y = tilesY;
+  tp.rs.depth_op = pl->depth_compare_op;
+  tp.rs.depth_write = depthWrite ? 1u : 0u;
+  tp.rs.has_depth = depthDev ? 1u : 0u;
+  tp.rs.blend_enable = pl->blend_enable ? 1u : 0u;
+  tp.rs.src_factor = pl->src_color_blend_factor;
+  tp.rs.dst_factor = pl->dst_color_blend_factor;
+  tp.rs.blend_op = pl->color_blend_op;
+  tp.rs.nslots = pipe->nslots;
+  tp.rs.owner_rank = g.ownerRank;
+  tp.rs.owner_world = g.ownerWorld;
+  tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
+  tp.rs.color_bpp = 4;
+  {
+    void *args[] = {&env, &tp};
+    if((rc = launchKernel(pipe->k_tile_ordered, dim3(ntiles), dim3(256), args)))
+      return rc;
+  }
+  CU(cudaGetLastError());
+  return VB200_OK;
+}
+
+int vb200_sample(const vb200_image *tex, int cube, uint64_t byte_offset, const float *uvw, float *out_rgba,
+                 size_t count)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(!tex || !tex->pixels || !uvw || !out_rgba)
+    return setError(VB200_ERR_INVALID, "sample: NULL argument");
+  if(tex->format == 135 || tex->format == 137)
+    return setError(VB200_ERR_INVALID, "BC2/BC3 sampling is not implemented on the device path yet");
+  if(count == 0)
+    return VB200_OK;
+  uint8_t *dev;
+  uint64_t bytes = cube ? sliceBytes(*tex) * 6 : imageBytes(*tex);
+  if((rc = resolve(tex->pixels, bytes + 4, ACC_READ, &dev)))
+    return rc;
+  Vb200Image d;
+  d.pixels = dev;
+  d.width = tex->width;
+  d.height = tex->height;
+  d.bpp = tex->bytes_per_pixel;
+  d.format = tex->format;
+  d.mips = tex->mip_levels;
+  d.layers = tex->array_layers;
+  d.slice_bytes = sliceBytes(*tex);
+  const size_t nin = count * (cube ? 3 : 2);
+  float *din = nullptr;
+  float4 *dout = nullptr;
+  CU(cudaMalloc((void **)&din, nin * sizeof(float)));
+  CU(cudaMalloc((void **)&dout, count * sizeof(float4)));
+  CU(cudaMemcpyAsync(din, uvw, nin * sizeof(float), cudaMemcpyHostToDevice, g.stream));
+  g.stats.kernel_launches += vb200::launch_sample(d, cube, byte_offset, din, dout, count, g.stream);
+  CU(cudaMemcpyAsync(out_rgba, dout, count * sizeof(float4), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFree(din);
+  cudaFree(dout);
+  return VB200_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------
+int vb200_set_tile_owner(int rank, int world)
+{
+  if(world < 1 || rank < 0 || rank >= world)
+    return setError(VB200_ERR_INVALID, "bad tile owner %d/%d", rank, world);
+  g.ownerRank = (uint32_t)rank;
+  g.ownerWorld = (uint32_t)world;
+  return VB200_OK;
+}
+
+uint32_t vb200_tiles_per_rank(uint32_t width, uint32_t height, int world)
+{
+  const uint32_t tiles = ((width + VB200_TILE - 1) / VB200_TILE) * ((height + VB200_TILE - 1) / VB200_TILE);
+  return world > 0 ? (tiles + (uint32_t)world - 1) / (uint32_t)world : tiles;
+}
+
+int vb200_tiles_pack(const vb200_image *image, void *dst_device, uint64_t dst_size)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if((rc = checkTarget(image, "tiles_pack")))
+    return rc;
+  const uint32_t slots = vb200_tiles_per_rank(image->width, image->height, (int)g.ownerWorld);
+  if(dst_size < (uint64_t)slots * 4096)
+    return setError(VB200_ERR_INVALID, "tiles_pack: destination too small");
+  if(!isDevicePointer(dst_device))
+    return setError(VB200_ERR_INVALID, "tiles_pack: destination must be device memory");
+  uint8_t *dev;
+  if((rc = resolve(image->pixels, (size_t)image->width * image->height * 4, ACC_READ, &dev)))
+    return rc;
+  g.stats.kernel_launches += vb200::launch_tiles_pack((const uint32_t *)dev, image->width, image->height, g.ownerRank,
+                                                      g.ownerWorld, (uint32_t *)dst_device, g.stream);
+  CU(cudaGetLastError());
+  return VB200_OK;
+}
+
+int vb200_tiles_unpack(const vb200_image *image, const void *src_device, uint64_t src_size, int world)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if((rc = checkTarget(image, "tiles_unpack")))
+    return rc;
+  if(world < 1)
+    return setError(VB200_ERR_INVALID, "tiles_unpack: bad world size");
+  const uint32_t slots = vb200_tiles_per_rank(image->width, image->height, world);
+  if(src_size < (uint64_t)slots * 4096 * world)
+    return setError(VB200_ERR_INVALID, "tiles_unpack: source too small");
+  if(!isDevicePointer(src_device))
+    return setError(VB200_ERR_INVALID, "tiles_unpack: source must be device memory");
+  uint8_t *dev;
+  if((rc = resolve(image->pixels, (size_t)image->width * image->height * 4, ACC_READ | ACC_WRITE, &dev)))
+    return rc;
+  g.stats.kernel_launches += vb200::launch_tiles_unpack((uint32_t *)dev, image->width, image->height, (uint32_t)world,
+                                                        slots, (const uint32_t *)src_device, g.stream);
+  CU(cudaGetLastError());
+  return VB200_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------
+int vb200_get_stats(vb200_stats *out)
+{
+  if(!out)
+    return setError(VB200_ERR_INVALID, "get_stats: NULL");
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  Vb200DrawCounters c;
+  CU(cudaMemcpyAsync(&c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  *out = g.stats;
+  out->triangles_out = c.triangles_out;
+  out->fragments_covered = c.fragments_covered;
+  out->fragments_shaded = c.fragments_shaded;
+  return VB200_OK;
+}
+
+void vb200_reset_stats(void)
+{
+  memset(&g.stats, 0, sizeof(g.stats));
+  if(g.ready)
+    cudaMemsetAsync(g.counters, 0, sizeof(Vb200DrawCounters), g.stream);
+}
+
+int vb200_set_option(const char *name, int64_t value)
+{
+  if(!name)
+    return setError(VB200_ERR_INVALID, "set_option: NULL name");
+  if(!strcmp(name, "raster_path"))
+    g.optRasterPath = value;
+  else if(!strcmp(name, "count_fragments"))
+    g.optCountFragments = value;
+  else
+    return setError(VB200_ERR_INVALID, "unknown option '%s'", name);
+  return VB200_OK;
+}
+}    // extern "C"
