@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — throughput of visor's draw-execution hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1..c5]
+
+A "step" is one pass of the hot path over one synthetic frame: ClearTarget(colour), ClearTarget(depth),
+DrawTriangles — the reference's own operator sequence for a render pass (cmd_exec.cpp:35-142).
+
+N = 1   workload c3: 1 000 000-triangle indexed lit mesh, depth LESS + write, 3840x2160 (BASELINE.json
+        configs[2], the scene the north-star roofline target is stated on).
+N > 1   workload c5: 4 000 000-triangle textured mesh at 7680x4320, sort-first over screen tiles
+        (tile t on rank t % N), geometry replicated, colour assembled by an NCCL all-gather.
+
+value   Mtri/s with inputs already resident in HBM, timed with CUDA events on the library stream,
+        L2 flushed (512 MB write) before every timed step, max over ranks.
+e2e     the same metric through the C-ABI with HOST buffers: every step uploads the vertex/index/
+        uniform data from pinned host memory and downloads colour + depth (the reference's coherent
+        host-visible memory semantics), wall-clock around submit..flush.
+roofline  for the dominant kernel (tile raster): algorithmic bytes = 8 B/pixel (colour + depth written
+        once) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference: visor's own rasterizer.cpp + texture_sampling.cpp compiled unmodified
+        (oracle/_ref), timed on this box's host cores on the same scene.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from harness import abi, scenes  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index: int) -> None:
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv = None
+            self.err = str(e)
+
+    def _run(self) -> None:
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_scene(workload: str) -> scenes.Scene:
+    return {
+        "c1": lambda: scenes.c1_triangle(),
+        "c2": lambda: scenes.c2_cube(),
+        "c3": lambda: scenes.c3_mesh(),
+        "c4": lambda: scenes.c4_particles(),
+        "c5": lambda: scenes.c5_textured(),
+    }[workload]()
+
+
+WORKLOAD_DESC = {
+    "c1": "c1: single vkCmdDraw triangle, passthrough VS/FS, 1280x720",
+    "c2": "c2: textured cube, D32 depth LESS, bilinear RGBA8, 1920x1080",
+    "c3": "c3: 1M-triangle indexed mesh, per-vertex lighting, depth LESS+write, 3840x2160",
+    "c4": "c4: 200k alpha-blended quads (400k triangles), ~8x overdraw, 1920x1080",
+    "c5": "c5: 4M-triangle textured lit mesh, depth LESS+write, 7680x4320",
+}
+
+
+def scene_host_buffers(bound: scenes.BoundScene):
+    """Every host array a frame touches: (array, is_input)."""
+    seen, out = set(), []
+    for _, d in bound.calls:
+        arrs = [v for v, _ in d.vbs] + ([d.ib[0]] if d.ib is not None else []) + \
+            [u[2] for u in d.ubos] + [t[2] for t in d.textures]
+        for a in arrs:
+            if id(a) not in seen:
+                seen.add(id(a))
+                out.append((a, True))
+    out.append((bound.color, False))
+    if bound.depth is not None:
+        out.append((bound.depth, False))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps: int = 1):
+    """visor's own CPU rasterizer (oracle/_ref) on this box's host cores: threaded as shipped
+    (7 workers + main, rasterizer.cpp:8) and serial (the deterministic parity mode)."""
+    if not abi.available("vref"):
+        return None
+    res = {}
+    tris = scene.triangles()
+    # threaded must come first: the pool cannot be restarted once shut down (rast.kill stays set)
+    ref = abi.backend("vref", 1)
+    b = scenes.BoundScene(ref, scene)
+    if ref.fn("threads")() == 8:
+        ts = []
+        for _ in range(max(1, threaded_steps)):
+            t0 = time.perf_counter()
+            b.run()
+            ts.append(time.perf_counter() - t0)
+        res["threaded"] = {"s_per_frame": min(ts), "mtri_s": tris / min(ts) / 1e6, "threads": 8}
+    ref.fn("init")(0)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        b.run()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    res["serial"] = {"s_per_frame": float(np.mean(ts)), "mtri_s": tris / float(np.mean(ts)) / 1e6, "threads": 1}
+    res["hash"] = scenes.image_hash(b.color, b.depth)
+    return res
+
+
+def run_reference_arm(args, workload: str) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = build_scene(workload)
+    # bounded: serial frame ~1-5 s on the 4K/8K meshes; threaded (6-25 s) gets a single frame
+    steps = max(1, min(args.steps, 8))
+    warm = max(0, min(args.warmup, 1))
+    r = time_reference(scene, steps, warm, threaded_steps=1)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvisor_ref.so not built"}))
+        return
+    best = max((k for k in ("serial", "threaded") if k in r), key=lambda k: r[k]["mtri_s"])
+    v = r[best]["mtri_s"]
+    line = {
+        "impl": "reference", "metric": "triangle throughput", "value": v, "unit": "Mtri/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r[best]["s_per_frame"] * 1e3,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[workload], "timing": "host wall clock around vkQueueSubmit-equivalent"},
+        "cpu_baseline": {"value": v, "unit": "Mtri/s", "cores": r[best]["threads"], "kind": "reference",
+                         "sample": f"{steps} full frames, best of serial/threaded modes ({best})",
+                         "serial_mtri_s": r["serial"]["mtri_s"],
+                         "threaded_mtri_s": r.get("threaded", {}).get("mtri_s"), "host_cpus": os.cpu_count()},
+        "e2e": {"value": v, "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, workload: str) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if multi:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    gpu = abi.backend("vb200", local)
+    L = gpu.lib
+    L.vb200_event_elapsed_ms.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.vb200_get_phase_times.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
+    L.vb200_set_option.argtypes = [C.c_char_p, C.c_int64]
+    L.vb200_mem_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.vb200_mem_upload.argtypes = [C.c_void_p, C.c_uint64]
+    L.vb200_mem_download.argtypes = [C.c_void_p, C.c_uint64]
+    L.vb200_mem_device_ptr.argtypes = [C.c_void_p]
+    L.vb200_mem_device_ptr.restype = C.c_void_p
+    L.vb200_stream.restype = C.c_void_p
+    L.vb200_tiles_pack.argtypes = [C.POINTER(abi.Image), C.c_void_p, C.c_uint64]
+    L.vb200_tiles_unpack.argtypes = [C.POINTER(abi.Image), C.c_void_p, C.c_uint64, C.c_int]
+    L.vb200_tiles_per_rank.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.vb200_tiles_per_rank.restype = C.c_uint32
+
+    scene = build_scene(workload)
+    tris = scene.triangles()
+    bound = scenes.BoundScene(gpu, scene)
+    bufs = scene_host_buffers(bound)
+    for a, _ in bufs:
+        gpu.check(L.vb200_mem_register(a.ctypes.data, a.nbytes), "mem_register")
+    in_bytes = sum(a.nbytes for a, is_in in bufs if is_in)
+    out_bytes = sum(a.nbytes for a, is_in in bufs if not is_in)
+
+    if multi:
+        gpu.check(L.vb200_set_tile_owner(rank, world), "set_tile_owner")
+        slots = L.vb200_tiles_per_rank(scene.width, scene.height, world)
+        ext = torch.cuda.ExternalStream(L.vb200_stream())
+        send = torch.empty(slots * 4096, dtype=torch.uint8, device="cuda")
+        recv = torch.empty(world * slots * 4096, dtype=torch.uint8, device="cuda")
+
+    def exchange():
+        """sort-first assemble: owned colour tiles -> all ranks -> linear image (on the library stream)."""
+        gpu.check(L.vb200_tiles_pack(C.byref(bound.color_img), send.data_ptr(), send.numel()), "tiles_pack")
+        with torch.cuda.stream(ext):
+            dist.all_gather_into_tensor(recv, send)
+        gpu.check(L.vb200_tiles_unpack(C.byref(bound.color_img), recv.data_ptr(), recv.numel(), world), "tiles_unpack")
+
+    def barrier():
+        gpu.flush()
+        if multi:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM, device-timed --------------------------------
+    gpu.check(L.vb200_set_sync_mode(1), "set_sync_mode")
+    for a, is_in in bufs:
+        if is_in:
+            gpu.check(L.vb200_mem_upload(a.ctypes.data, a.nbytes), "mem_upload")
+
+    def step_device():
+        bound.submit()
+        if multi:
+            exchange()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    gpu.reset_stats()
+    ms = C.c_float()
+    times = []
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            gpu.check(L.vb200_l2_flush(), "l2_flush")
+            if multi:
+                dist.barrier()
+            gpu.check(L.vb200_event_record(0), "event")
+            step_device()
+            gpu.check(L.vb200_event_record(1), "event")
+            gpu.check(L.vb200_event_elapsed_ms(0, 1, C.byref(ms)), "elapsed")
+            times.append(ms.value)
+    barrier()
+    launches = gpu.stats()["kernel_launches"] / max(1, args.steps)
+    t_local = float(np.mean(times))
+    if multi:
+        tt = torch.tensor([t_local], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_step = float(tt.item())
+    else:
+        t_step = t_local
+
+    # ---------------- diagnostics: per-phase device time, fragment counts ------------------------
+    L.vb200_set_option(b"time_kernels", 1)
+    for _ in range(3):
+        gpu.check(L.vb200_l2_flush(), "l2_flush")
+        bound.submit()
+    gpu.flush()
+    pm = (C.c_double * 5)()
+    pc = (C.c_uint64 * 5)()
+    L.vb200_get_phase_times(pm, pc, 5)
+    phase = {n: (pm[i] / pc[i] if pc[i] else 0.0) for i, n in enumerate(["clear", "vertex", "setup", "bin", "tiles"])}
+    phase["clear"] *= (2 if scene.depth else 1)  # colour + depth clears per frame
+    L.vb200_set_option(b"time_kernels", 0)
+    L.vb200_set_option(b"count_fragments", 1)
+    gpu.reset_stats()
+    bound.submit()
+    gpu.flush()
+    st = gpu.stats()
+    L.vb200_set_option(b"count_fragments", 0)
+
+    # ---------------- e2e: host buffers through the C-ABI, copies inside the timed region --------
+    gpu.check(L.vb200_set_sync_mode(0), "set_sync_mode")
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        bound.submit()
+        if multi:
+            exchange()
+        gpu.flush()
+    barrier()
+    gpu.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        bound.submit()
+        if multi:
+            exchange()
+        gpu.flush()
+    if multi:
+        torch.cuda.synchronize()
+    t_e2e_local = (time.perf_counter() - t0) / e2e_steps
+    st2 = gpu.stats()
+    if multi:
+        tt = torch.tensor([t_e2e_local], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+    else:
+        t_e2e = t_e2e_local
+    img_hash = scenes.image_hash(bound.color, bound.depth if not multi else None)
+
+    if rank != 0:
+        if multi:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline (rank 0, N = 1): the reference's own rasterizer ----------------
+    cpu = None
+    parity = None
+    if not multi and not args.no_cpu_baseline:
+        r = time_reference(scene, 2, 0, threaded_steps=1)
+        if r is not None:
+            best = max((k for k in ("serial", "threaded") if k in r), key=lambda k: r[k]["mtri_s"])
+            cpu = {"value": r[best]["mtri_s"], "unit": "Mtri/s", "cores": r[best]["threads"], "kind": "reference",
+                   "sample": f"2 full frames of the same scene, best mode = {best}; serial "
+                             f"{r['serial']['mtri_s']:.3f} Mtri/s (1 thread), threaded "
+                             f"{r.get('threaded', {}).get('mtri_s', float('nan')):.3f} Mtri/s (8 threads as shipped)",
+                   "host_cpus": os.cpu_count()}
+            parity = "bit-exact vs reference serial path" if r["hash"] == img_hash else "MISMATCH vs reference"
+
+    peak, peak_src = measured_peak_gbs()
+    px = scene.width * scene.height
+    per_px = 8 if scene.depth else 4
+    tile_bytes = px * per_px
+    tiles_ms = phase["tiles"]
+    achieved = tile_bytes / (tiles_ms * 1e-3) / 1e9 if tiles_ms > 0 else 0.0
+    frame_bytes = scene.algorithmic_bytes()
+    frame_gbs = frame_bytes / (t_step * 1e-3) / 1e9
+    line = {
+        "metric": "triangle throughput", "value": tris / (t_step * 1e-3) / 1e6, "unit": "Mtri/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step,
+        "higher_is_better": True, "scaling": "strong" if multi else "weak", "vs_baseline": None,
+        "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[workload], "triangles": tris,
+                   "resolution": [scene.width, scene.height], "l2": "flushed (512 MB write) before each timed step",
+                   "parallelism": f"sort-first x{world}" if multi else "single GPU",
+                   "raster_path": "ordered 32x32 tiles"},
+        "gfrag_s": st["fragments_covered"] / (t_step * 1e-3) / 1e9,
+        "fragments": {"covered": st["fragments_covered"], "shaded": st["fragments_shaded"],
+                      "triangles_out": st["triangles_out"], "tile_pairs": st["tile_pairs"]},
+        "phase_ms": phase,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "kernel": "vb200_k_tile_ordered",
+                     "algorithmic_bytes": tile_bytes, "kernel_ms": tiles_ms, "peak_source": peak_src,
+                     "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_gbs, "frac": frame_gbs / peak}},
+        "e2e": {"value": tris / t_e2e / 1e6, "unit": "Mtri/s", "ms_per_step": t_e2e * 1e3,
+                "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps, "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
+                "steps": e2e_steps, "host_buffers": {"inputs": in_bytes, "attachments": out_bytes}},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    if parity:
+        line["parity"] = parity
+    print(json.dumps(line))
+    if multi:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    workload = args.workload
+    if workload == "auto":
+        workload = "c3" if args.gpus <= 1 else "c5"
+    if args.impl == "reference":
+        run_reference_arm(args, workload)
+    else:
+        run_ours(args, workload)
+
+
+if __name__ == "__main__":
+    main()

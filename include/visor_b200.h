@@ -216,13 +216,22 @@ typedef struct vb200_stats { /* counters of the reference (rasterizer.cpp:517-51
   uint64_t h2d_bytes, d2h_bytes;
 } vb200_stats;
 
+/* Benchmark hygiene: writes a 512 MB scratch buffer on the library stream (evicts the 126 MB L2). */
+VB200_API int vb200_l2_flush(void);
+/* Device-side timing for benchmarks: CUDA events recorded on the library stream (slots 0..15). */
+VB200_API int vb200_event_record(int slot);
+VB200_API int vb200_event_elapsed_ms(int start_slot, int end_slot, float *ms); /* syncs on end_slot */
+/* Per-phase device time accumulated while option "time_kernels" is 1 (diagnostic: it syncs per draw). */
+enum { VB200_PHASE_CLEAR = 0, VB200_PHASE_VERTEX = 1, VB200_PHASE_SETUP = 2, VB200_PHASE_BIN = 3,
+       VB200_PHASE_TILES = 4, VB200_PHASES = 5 };
+VB200_API int vb200_get_phase_times(double *ms, uint64_t *counts, int n);
 VB200_API int vb200_get_stats(vb200_stats *out);   /* syncs the stream */
 VB200_API void vb200_reset_stats(void);
 VB200_API void *vb200_stream(void);                /* cudaStream_t the library launches on */
 VB200_API const char *vb200_last_error(void);
 VB200_API int vb200_abi_version(void);
 /* Tuning/debug knobs by name ("raster_path": 0 auto, 1 ordered tiles, 2 visibility resolve;
- * "count_fragments": 0/1). Unknown names return VB200_ERR_INVALID. */
+ * "count_fragments": 0/1, "time_kernels": 0/1). Unknown names return VB200_ERR_INVALID. */
 VB200_API int vb200_set_option(const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -12,6 +12,17 @@ from harness import abi, scenes
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "ordered"], autouse=True)
+def raster_path(request, gpu):
+    """Every scene runs through both tile back ends: "auto" picks the visibility-resolve kernel when the
+    pass is order independent, "ordered" forces the in-order kernel (exact for any state)."""
+    import ctypes as C
+    gpu.lib.vb200_set_option.argtypes = [C.c_char_p, C.c_int64]
+    assert gpu.lib.vb200_set_option(b"raster_path", 1 if request.param == "ordered" else 0) == 0
+    yield request.param
+    gpu.lib.vb200_set_option(b"raster_path", 0)
+
+
 def _check(gpu, vor, sc, exact=True):
     c_gpu, d_gpu = scenes.render(gpu, sc)
     c_cpu, d_cpu = scenes.render(vor, sc)
@@ -62,6 +73,30 @@ def test_cull_strip_index16(gpu, vor):
     _check(gpu, vor, scenes.random_triangles(320, 200, 200, 9, index_type=abi.INDEX_U16, cull=abi.CULL_BACK,
                                              front=abi.FRONT_CW))
     _check(gpu, vor, scenes.random_triangles(320, 200, 200, 10, index_type=abi.INDEX_U32, cull=abi.CULL_FRONT))
+
+
+def test_depth_test_without_write_and_never(gpu, vor):
+    for op in (abi.CMP_LESS, abi.CMP_GEQUAL, abi.CMP_NEVER, abi.CMP_NOTEQUAL, abi.CMP_EQUAL):
+        sc = scenes.random_triangles(300, 200, 200, 40 + op, depth_op=op, depth_write=False)
+        sc.clear_depth = 0.5
+        _check(gpu, vor, sc)
+    sc = scenes.random_triangles(300, 200, 200, 50, depth_op=abi.CMP_ALWAYS, depth_write=True)
+    _check(gpu, vor, sc)
+
+
+def test_large_and_small_mix(gpu, vor):
+    """full-screen triangles (row-swept by the whole CTA) interleaved with tiny ones"""
+    big = scenes.random_triangles(500, 300, 12, 60, max_size=1.5)
+    small = scenes.random_triangles(500, 300, 3000, 61, max_size=0.02)
+    big.draws += small.draws
+    _check(gpu, vor, big)
+
+
+def test_two_draws_accumulate_depth(gpu, vor):
+    a = scenes.random_triangles(300, 200, 150, 70)
+    b = scenes.random_triangles(300, 200, 150, 71, depth_op=abi.CMP_LEQUAL)
+    a.draws += b.draws
+    _check(gpu, vor, a)
 
 
 def test_no_clear_loads_host_contents(gpu, vor):

@@ -61,6 +61,7 @@ struct Pipeline
 {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k_vertex = nullptr, k_tile_ordered = nullptr;
+  cudaKernel_t k_tile_resolve[5] = {};
   uint32_t nslots = 1;
 };
 
@@ -126,9 +127,40 @@ struct Context
   Vb200DrawCounters *counters = nullptr;    // device
   vb200_stats stats;
   uint32_t ownerRank = 0, ownerWorld = 1;
-  int64_t optRasterPath = 0, optCountFragments = 0;
+  int64_t optRasterPath = 0, optCountFragments = 0, optTimeKernels = 0;
   int stickyCuda = 0;
+  cudaEvent_t userEvents[16] = {};
+  cudaEvent_t phaseEvents[8] = {};
+  double phaseMs[VB200_PHASES] = {};
+  uint64_t phaseCount[VB200_PHASES] = {};
 } g;
+
+// phase timing (diagnostic, enabled by option "time_kernels"): CUDA events on the library stream
+// around each stage of a draw; accumulated per phase.
+int phaseMark(int i)
+{
+  if(!g.optTimeKernels)
+    return VB200_OK;
+  if(!g.phaseEvents[i] && cudaEventCreate(&g.phaseEvents[i]) != cudaSuccess)
+    return setError(VB200_ERR_CUDA, "cudaEventCreate failed");
+  if(cudaEventRecord(g.phaseEvents[i], g.stream) != cudaSuccess)
+    return setError(VB200_ERR_CUDA, "cudaEventRecord failed");
+  return VB200_OK;
+}
+void phaseAccumulate(int phase, int a, int b)
+{
+  if(!g.optTimeKernels || !g.phaseEvents[a] || !g.phaseEvents[b])
+    return;
+  float ms = 0.0f;
+  cudaEventSynchronize(g.phaseEvents[b]);
+  if(cudaEventElapsedTime(&ms, g.phaseEvents[a], g.phaseEvents[b]) == cudaSuccess)
+  {
+    g.phaseMs[phase] += ms;
+    g.phaseCount[phase]++;
+  }
+  else
+    cudaGetLastError();
+}
 
 #define CU(call)                                                                                       \
   do                                                                                                   \
@@ -340,6 +372,11 @@ int linkPipeline(const vb200_entry *vs, const vb200_entry *fs, Pipeline **out)
   e = cudaLibraryGetKernel(&p.k_vertex, p.lib, "vb200_k_vertex");
   if(e == cudaSuccess)
     e = cudaLibraryGetKernel(&p.k_tile_ordered, p.lib, "vb200_k_tile_ordered");
+  static const char *resolveNames[5] = {"vb200_k_tile_resolve_min_first", "vb200_k_tile_resolve_min_last",
+                                        "vb200_k_tile_resolve_max_first", "vb200_k_tile_resolve_max_last",
+                                        "vb200_k_tile_resolve_last_wins"};
+  for(int i = 0; i < 5 && e == cudaSuccess; i++)
+    e = cudaLibraryGetKernel(&p.k_tile_resolve[i], p.lib, resolveNames[i]);
   if(e != cudaSuccess)
   {
     cudaLibraryUnload(p.lib);
@@ -611,6 +648,15 @@ int vb200_link_check(const vb200_entry *vs, const vb200_entry *fs, uint64_t *cub
   int rc = linkCubin(vs, fs, cubin);
   if(rc == VB200_OK && cubin_size)
     *cubin_size = cubin.size();
+  if(rc == VB200_OK && getenv("VB200_DUMP_CUBIN"))
+  {
+    // developer aid: keep the linked cubin for cuobjdump -sass / -res-usage
+    if(FILE *f = fopen(getenv("VB200_DUMP_CUBIN"), "wb"))
+    {
+      fwrite(cubin.data(), 1, cubin.size(), f);
+      fclose(f);
+    }
+  }
   return rc;
 }
 
@@ -795,7 +841,10 @@ int vb200_clear_color(const vb200_image *target, const float rgba[4])
   {
     if((rc = resolve(target->pixels, px * 4, ACC_OVERWRITE, &dev)))
       return rc;
+    phaseMark(0);
     g.stats.kernel_launches += vb200::launch_clear_u32((uint32_t *)dev, b | (gch << 8) | (r << 16) | (a << 24), px, g.stream);
+    phaseMark(1);
+    phaseAccumulate(VB200_PHASE_CLEAR, 0, 1);
   }
   else if(target->bytes_per_pixel == 1)
   {
@@ -823,7 +872,10 @@ int vb200_clear_depth(const vb200_image *target, float depth)
     return rc;
   uint32_t bits;
   memcpy(&bits, &depth, 4);
+  phaseMark(0);
   g.stats.kernel_launches += vb200::launch_clear_u32((uint32_t *)dev, bits, px, g.stream);
+  phaseMark(1);
+  phaseAccumulate(VB200_PHASE_CLEAR, 0, 1);
   CU(cudaGetLastError());
   return VB200_OK;
 }
@@ -934,6 +986,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     ibDev = dev + s->ib.offset;
     if(((uintptr_t)ibDev) & (isz - 1))
       return setError(VB200_ERR_INVALID, "index buffer offset is not aligned to the index size");
+    phaseMark(0);
     g.stats.kernel_launches += vb200::launch_index_range(ibDev, s->ib.index_type, first, usedVerts, g.range, g.stream);
     if(vertexBound == 0xffffffffu)
     {
@@ -978,6 +1031,8 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
       return rc;
 
   // ---- K1: vertex stage
+  if(!indexed)
+    phaseMark(0);
   Vb200VertexParams vp;
   vp.range = indexed ? g.range : nullptr;
   vp.base_vertex = baseVertex;
@@ -994,6 +1049,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   }
 
   // ---- K2: setup + per-tile counts
+  phaseMark(1);
   Vb200SetupParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.ib = ibDev;
@@ -1021,6 +1077,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);
 
   // ---- K3: scan -> (host reads the pair total to size the list) -> fill -> sort
+  phaseMark(2);
   g.stats.kernel_launches += vb200::launch_scan(g.tileCount.p, g.tileOffset.p, g.tileCursor.p, ntiles, g.total, g.stream);
   CU(cudaMemcpyAsync(g.totalHost, g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
@@ -1034,9 +1091,35 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     return setError(VB200_ERR_CUDA, "out of device memory for %u tile-list entries", pairs);
   }
   g.stats.kernel_launches += vb200::launch_fill(sp, g.tileOffset.p, g.tileCursor.p, g.list.p, pairs, g.stream);
-  g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileOffset.p, g.tileCount.p, ntiles, g.stream);
+
+  // Raster back end. A pass is order-independent ("resolvable") unless it blends or runs
+  // NOT_EQUAL against a depth buffer it also writes; see scaffold.cu.
+  int resolveMode = -1;
+  if(!pl->blend_enable)
+  {
+    if(!depthTest)
+      resolveMode = 4;
+    else if(!depthWrite)
+      resolveMode = 4;    // static test
+    else
+      switch(pl->depth_compare_op)
+      {
+        case 0: resolveMode = 4; break;    // NEVER: nothing passes
+        case 1: resolveMode = 0; break;    // LESS
+        case 2: resolveMode = 4; break;    // EQUAL + write keeps the buffer's value: static test
+        case 3: resolveMode = 1; break;    // LESS_OR_EQUAL
+        case 4: resolveMode = 2; break;    // GREATER
+        case 6: resolveMode = 3; break;    // GREATER_OR_EQUAL
+        default: resolveMode = -1; break;  // NOT_EQUAL + write is order dependent
+      }
+  }
+  if(g.optRasterPath == 1)
+    resolveMode = -1;
+  if(resolveMode < 0)    // ordered path needs each tile's list in submission order
+    g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileOffset.p, g.tileCount.p, ntiles, g.stream);
 
   // ---- K4: tiles
+  phaseMark(3);
   Vb200TileParams tp;
   memset(&tp, 0, sizeof(tp));
   tp.setup = g.setup.p;
@@ -1065,9 +1148,15 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.rs.color_bpp = 4;
   {
     void *args[] = {&env, &tp};
-    if((rc = launchKernel(pipe->k_tile_ordered, dim3(ntiles), dim3(256), args)))
+    cudaKernel_t k = resolveMode >= 0 ? pipe->k_tile_resolve[resolveMode] : pipe->k_tile_ordered;
+    if((rc = launchKernel(k, dim3(ntiles), dim3(256), args)))
       return rc;
   }
+  phaseMark(4);
+  phaseAccumulate(VB200_PHASE_VERTEX, 0, 1);
+  phaseAccumulate(VB200_PHASE_SETUP, 1, 2);
+  phaseAccumulate(VB200_PHASE_BIN, 2, 3);
+  phaseAccumulate(VB200_PHASE_TILES, 3, 4);
   CU(cudaGetLastError());
   return VB200_OK;
 }
@@ -1196,6 +1285,56 @@ void vb200_reset_stats(void)
     cudaMemsetAsync(g.counters, 0, sizeof(Vb200DrawCounters), g.stream);
 }
 
+int vb200_get_phase_times(double *ms, uint64_t *counts, int n)
+{
+  for(int i = 0; i < n && i < VB200_PHASES; i++)
+  {
+    if(ms)
+      ms[i] = g.phaseMs[i];
+    if(counts)
+      counts[i] = g.phaseCount[i];
+  }
+  return VB200_OK;
+}
+
+int vb200_l2_flush(void)
+{
+  // benchmark hygiene: overwrite a buffer larger than the 126 MB L2 so the next step starts cold
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  static void *scratch = nullptr;
+  const size_t bytes = (size_t)512 << 20;
+  if(!scratch)
+    CU(cudaMalloc(&scratch, bytes));
+  static int v = 0;
+  CU(cudaMemsetAsync(scratch, ++v & 0xff, bytes, g.stream));
+  return VB200_OK;
+}
+
+int vb200_event_record(int slot)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(slot < 0 || slot >= 16)
+    return setError(VB200_ERR_INVALID, "event slot out of range");
+  if(!g.userEvents[slot])
+    CU(cudaEventCreate(&g.userEvents[slot]));
+  CU(cudaEventRecord(g.userEvents[slot], g.stream));
+  return VB200_OK;
+}
+
+int vb200_event_elapsed_ms(int start_slot, int end_slot, float *ms)
+{
+  if(start_slot < 0 || start_slot >= 16 || end_slot < 0 || end_slot >= 16 || !ms || !g.userEvents[start_slot] ||
+     !g.userEvents[end_slot])
+    return setError(VB200_ERR_INVALID, "event_elapsed: bad slots");
+  CU(cudaEventSynchronize(g.userEvents[end_slot]));
+  CU(cudaEventElapsedTime(ms, g.userEvents[start_slot], g.userEvents[end_slot]));
+  return VB200_OK;
+}
+
 int vb200_set_option(const char *name, int64_t value)
 {
   if(!name)
@@ -1204,6 +1343,15 @@ int vb200_set_option(const char *name, int64_t value)
     g.optRasterPath = value;
   else if(!strcmp(name, "count_fragments"))
     g.optCountFragments = value;
+  else if(!strcmp(name, "time_kernels"))
+  {
+    g.optTimeKernels = value;
+    for(int i = 0; i < VB200_PHASES; i++)
+    {
+      g.phaseMs[i] = 0.0;
+      g.phaseCount[i] = 0;
+    }
+  }
   else
     return setError(VB200_ERR_INVALID, "unknown option '%s'", name);
   return VB200_OK;

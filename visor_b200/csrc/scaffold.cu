@@ -304,3 +304,276 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   if(rs.count_fragments)
     vb200_count_fragments(p.counters, covered, shaded);
 }
+
+// ------------------------------------------------------------------------------------------------
+// K4 (resolve): the same tile decomposition for passes whose per-pixel result does not depend on
+// the ORDER fragments arrive in, only on which fragment wins:
+//   depth LESS / LESS_OR_EQUAL / GREATER / GREATER_OR_EQUAL with depth write, no blending:
+//       the surviving fragment is the min (max) depth; ties go to the first (LESS, GREATER) or last
+//       (.._OR_EQUAL) triangle in draw order, exactly what the serial loop of the reference yields
+//       (rasterizer.cpp:560-576,680-683: a fragment passes against the depth left by its predecessors);
+//   no depth test, or a test against a depth buffer the pass does not modify (write off, or EQUAL):
+//       the last passing triangle in draw order wins.
+// The supported SPIR-V subset has no side effects or discard, so shading only the winner is exact.
+//
+// Phase A (triangle-parallel): each thread rasterises whole small triangles of the tile's list
+// (bbox <= 64 px in the tile); larger ones are queued in shared memory and swept row by row, one
+// 32-pixel row per warp step. Winners are resolved with a 64-bit (depth key, triangle id) atomic
+// min in shared memory — no global atomics, lists need no sorting.
+// Phase B (pixel-parallel): each thread recomputes the winner's barycentrics bit-exactly, runs the
+// fragment stage once per pixel and writes colour/depth rows as full 128-byte lines.
+// ------------------------------------------------------------------------------------------------
+enum
+{
+  VB200_RES_MIN_FIRST = 0,    // LESS + write
+  VB200_RES_MIN_LAST = 1,     // LESS_OR_EQUAL + write
+  VB200_RES_MAX_FIRST = 2,    // GREATER + write
+  VB200_RES_MAX_LAST = 3,     // GREATER_OR_EQUAL + write
+  VB200_RES_LAST_WINS = 4,    // no test / static test: highest triangle id that passes
+};
+
+struct TriCoef
+{
+  int A1, B1, C1, A2;
+  int B2, C2, area, x0;
+  int y0, x1, y1;
+  uint32_t id;    // triangle index + 1
+  float invarea, d0, d1, d2;
+};
+
+// float -> uint32 whose unsigned order equals the float order (-0 == +0); callers exclude NaN
+__device__ __forceinline__ uint32_t vb200_depth_key(float d)
+{
+  uint32_t b = __float_as_uint(d);
+  if((b << 1) == 0u)
+    b = 0u;
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <int MODE>
+__device__ __forceinline__ unsigned long long vb200_existing_key(float e)
+{
+  if(MODE == VB200_RES_LAST_WINS)
+    return ~0ull;
+  if(e != e)
+    return 0ull;    // NaN in the depth buffer: every comparison fails, nothing can replace it
+  uint32_t k = vb200_depth_key(e);
+  if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
+    k = ~k;
+  const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? 0u : 0xffffffffu;
+  return ((unsigned long long)k << 32) | low;
+}
+
+template <int MODE>
+__device__ __forceinline__ void vb200_resolve_pixel(const TriCoef &c, int x, int y, int tileX0, int tileY0,
+                                                    unsigned long long *vis, const float *s_depth, bool depthTest,
+                                                    uint32_t depthOp, uint32_t &covered)
+{
+  const int b1 = c.A1 * x + c.B1 * y + c.C1;
+  const int b2 = c.A2 * x + c.B2 * y + c.C2;
+  const int b0 = c.area - (b1 + b2);
+  if((b0 | b1 | b2) < 0)
+    return;
+  covered++;
+  const int idx = (y - tileY0) * VB200_TILE + (x - tileX0);
+  unsigned long long key;
+  if(MODE == VB200_RES_LAST_WINS && !depthTest)
+    key = (unsigned long long)(~c.id);
+  else
+  {
+    const float n0 = __fmul_rn((float)b0, c.invarea);
+    const float n1 = __fmul_rn((float)b1, c.invarea);
+    const float n2 = __fmul_rn((float)b2, c.invarea);
+    const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, c.d0), __fmul_rn(n1, c.d1)), __fmul_rn(n2, c.d2));
+    if(MODE == VB200_RES_LAST_WINS)
+    {
+      if(!vb200_depth_pass(depthOp, pixdepth, s_depth[idx]))
+        return;
+      key = (unsigned long long)(~c.id);
+    }
+    else
+    {
+      if(pixdepth != pixdepth)
+        return;    // NaN never passes an ordered comparison
+      uint32_t k = vb200_depth_key(pixdepth);
+      if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
+        k = ~k;
+      const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? c.id : ~c.id;
+      key = ((unsigned long long)k << 32) | low;
+    }
+  }
+  if(key < vis[idx])
+    atomicMin(&vis[idx], key);
+}
+
+#define VB200_SMALL_AREA 64
+
+template <int MODE>
+__device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, const Vb200TileParams &p)
+{
+  __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
+  __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
+  __shared__ TriCoef s_big[256];
+  __shared__ uint32_t s_nbig;
+
+  const uint32_t tile = blockIdx.x;
+  const uint32_t n = p.tile_count[tile];
+  if(n == 0)
+    return;
+  const uint32_t off = p.tile_offset[tile];
+  const Vb200RasterState &rs = p.rs;
+  const uint32_t tx = tile % rs.tiles_x, ty = tile / rs.tiles_x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tileX0 = (int)(tx * VB200_TILE), tileY0 = (int)(ty * VB200_TILE);
+  const bool depthTest = rs.has_depth && rs.depth_op != 7u;
+  const bool depthWrite = rs.has_depth && rs.depth_write;
+
+  // ---- init: one visibility key per pixel, seeded with the depth already in the buffer
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    const int ly = warp + 8 * j;
+    const int x = tileX0 + lane, y = tileY0 + ly;
+    const bool in = x < (int)rs.width && y < (int)rs.height;
+    float e = 0.0f;
+    if(MODE != VB200_RES_LAST_WINS || depthTest)
+      e = in ? p.depth[(size_t)y * rs.width + x] : 0.0f;
+    vis[ly * VB200_TILE + lane] = vb200_existing_key<MODE>(e);
+    if(MODE == VB200_RES_LAST_WINS)
+      s_depth[ly * VB200_TILE + lane] = e;
+  }
+  if(threadIdx.x == 0)
+    s_nbig = 0;
+  __syncthreads();
+
+  // ---- phase A: coverage + visibility, triangle-parallel
+  uint32_t covered = 0, shaded = 0;
+  for(uint32_t base = 0; base < n; base += 256)
+  {
+    const uint32_t i = base + threadIdx.x;
+    if(i < n)
+    {
+      const uint32_t t = p.list[off + i];
+      const Vb200TriSetup su = vb200_load_setup(p.setup + t);
+      TriCoef c;
+      const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
+      const int area2 = ABx * ACy - ABy * ACx;
+      const int sgn = area2 > 0 ? 1 : -1;
+      c.A1 = sgn * ACy;
+      c.B1 = -sgn * ACx;
+      c.C1 = sgn * (ACx * su.y0 - ACy * su.x0);
+      c.A2 = -sgn * ABy;
+      c.B2 = sgn * ABx;
+      c.C2 = sgn * (ABy * su.x0 - ABx * su.y0);
+      c.area = sgn * area2;
+      c.x0 = max(max(0, min(su.x0, min(su.x1, su.x2))), tileX0);
+      c.y0 = max(max(0, min(su.y0, min(su.y1, su.y2))), tileY0);
+      c.x1 = min(min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2))), tileX0 + VB200_TILE);
+      c.y1 = min(min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2))), tileY0 + VB200_TILE);
+      c.id = t + 1u;
+      c.invarea = __fdiv_rn(1.0f, (float)c.area);
+      c.d0 = su.d0;
+      c.d1 = su.d1;
+      c.d2 = su.d2;
+      const int w = c.x1 - c.x0, h = c.y1 - c.y0;
+      if(w > 0 && h > 0)
+      {
+        if(w * h <= VB200_SMALL_AREA)
+        {
+          for(int y = c.y0; y < c.y1; y++)
+            for(int x = c.x0; x < c.x1; x++)
+              vb200_resolve_pixel<MODE>(c, x, y, tileX0, tileY0, vis, s_depth, depthTest, rs.depth_op, covered);
+        }
+        else
+          s_big[atomicAdd(&s_nbig, 1u)] = c;
+      }
+    }
+    __syncthreads();
+    const uint32_t nb = s_nbig;
+    if(nb)
+    {
+      for(uint32_t q = 0; q < nb; q++)
+      {
+        const TriCoef &c = s_big[q];
+        const int x = tileX0 + lane;
+        if(x >= c.x0 && x < c.x1)
+          for(int y = c.y0 + warp; y < c.y1; y += 8)
+            vb200_resolve_pixel<MODE>(c, x, y, tileX0, tileY0, vis, s_depth, depthTest, rs.depth_op, covered);
+      }
+      __syncthreads();
+      if(threadIdx.x == 0)
+        s_nbig = 0;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase B: shade the winner of every pixel, write back
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    const int ly = warp + 8 * j;
+    const int x = tileX0 + lane, y = tileY0 + ly;
+    const unsigned long long key = vis[ly * VB200_TILE + lane];
+    const uint32_t low = (uint32_t)key;
+    bool won;
+    uint32_t id;
+    if(MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST)
+    {
+      won = low != 0u;
+      id = low;
+    }
+    else if(MODE == VB200_RES_LAST_WINS)
+    {
+      won = key != ~0ull;
+      id = ~low;
+    }
+    else
+    {
+      won = low != 0xffffffffu;
+      id = ~low;
+    }
+    if(!won || x >= (int)rs.width || y >= (int)rs.height)
+      continue;
+    shaded++;
+    const Vb200TriSetup su = vb200_load_setup(p.setup + (id - 1u));
+    // recompute exactly what the reference computes for this pixel (rasterizer.cpp:303-309,545-558)
+    const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
+    const int area2 = ABx * ACy - ABy * ACx;
+    const int sgn = area2 > 0 ? 1 : -1;
+    const int PAx = su.x0 - x, PAy = su.y0 - y;
+    const int ux = ACx * PAy - ACy * PAx, uy = PAx * ABy - PAy * ABx;
+    const int b0 = (area2 - (ux + uy)) * sgn, b1 = ux * sgn, b2 = uy * sgn;
+    const float invarea = __fdiv_rn(1.0f, (float)(sgn * area2));
+    float n0 = __fmul_rn((float)b0, invarea);
+    float n1 = __fmul_rn((float)b1, invarea);
+    float n2 = __fmul_rn((float)b2, invarea);
+    const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, su.d0), __fmul_rn(n1, su.d1)), __fmul_rn(n2, su.d2));
+    n0 = __fmul_rn(n0, su.invw0);
+    n1 = __fmul_rn(n1, su.invw1);
+    n2 = __fmul_rn(n2, su.invw2);
+    const float invlen = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(n0, n1), n2));
+    n0 = __fmul_rn(n0, invlen);
+    n1 = __fmul_rn(n1, invlen);
+    n2 = __fmul_rn(n2, invlen);
+    const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)su.s0 * rs.nslots,
+                                p.interps + (size_t)su.s1 * rs.nslots, p.interps + (size_t)su.s2 * rs.nslots);
+    const size_t gi = (size_t)y * rs.width + x;
+    p.color[gi] = vb200_blend_store(rs, pix, p.color[gi]);
+    if(depthWrite)
+      p.depth[gi] = pixdepth;
+  }
+  if(rs.count_fragments)
+    vb200_count_fragments(p.counters, covered, shaded);
+}
+
+#define VB200_RESOLVE_KERNEL(NAME, MODE)                                                              \
+  extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ Vb200Env env,       \
+                                                         const __grid_constant__ Vb200TileParams p) \
+  {                                                                                                   \
+    vb200_tile_resolve_body<MODE>(env, p);                                                            \
+  }
+VB200_RESOLVE_KERNEL(vb200_k_tile_resolve_min_first, VB200_RES_MIN_FIRST)
+VB200_RESOLVE_KERNEL(vb200_k_tile_resolve_min_last, VB200_RES_MIN_LAST)
+VB200_RESOLVE_KERNEL(vb200_k_tile_resolve_max_first, VB200_RES_MAX_FIRST)
+VB200_RESOLVE_KERNEL(vb200_k_tile_resolve_max_last, VB200_RES_MAX_LAST)
+VB200_RESOLVE_KERNEL(vb200_k_tile_resolve_last_wins, VB200_RES_LAST_WINS)
