@@ -313,7 +313,10 @@ def _grid_mesh(qx: int, qy: int, seed: int, amp: float = 0.22) -> Tuple[np.ndarr
     dz = np.gradient(hgt, zs, axis=0)
     nrm = np.stack([-dx, np.ones_like(dx), -dz], axis=-1)
     nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
-    uv = np.stack([X * 2.0, Z * 2.0], axis=-1)
+    # strictly positive uv: for v in (-2^-25, 0) the reference's `v - floor(v)` rounds to exactly 1.0
+    # and it then reads the texel row at y == height, past the end of the texture (texture_sampling.cpp
+    # :142-149) — undefined behaviour the scenes must stay clear of (SURVEY.md §7 hard part 6)
+    uv = np.stack([(X + 2.5) * 2.0, (Z + 2.0) * 2.0], axis=-1)
     v = np.concatenate([np.stack([X, hgt, Z], axis=-1), nrm, uv], axis=-1).astype(np.float32)
     v = np.ascontiguousarray(v.reshape(-1, 8))
     j, i = np.meshgrid(np.arange(qy), np.arange(qx), indexing="ij")

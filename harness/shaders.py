@@ -361,3 +361,103 @@ def vs_pos_dir() -> np.ndarray:
     m.store(m.access(SC.Output, v4, gl, m.const_i(0)), m.load(v4, pos))
     m.store(od, m.load(v3, d))
     return _finish(m, VERTEX, f, [pos, d, od, gl])
+
+
+# ------------------------------------------------------------------ single-op shaders (known-answer tests)
+UNIT_OPS = ("fadd", "fsub", "fmul", "fdiv", "fneg", "vts", "dot4", "dot3", "fmin", "fmax", "fclamp", "fmix",
+            "sqrt", "invsqrt", "normalize3", "length3", "reflect3", "cross3", "shuffle", "mxv", "vxm", "mxm",
+            "transpose", "mxs", "minverse", "sin", "cos", "pow")
+
+
+def vs_unit(op: str) -> np.ndarray:
+    """in vec4 a@0, b@1, c@2; UBO{mat4 m; mat4 n}@(0,0); gl_Position = a; out vec4 r@0 = op(a,b,c,m,n)."""
+    m = Module()
+    fl, v4, v3, mat4 = m.t_float(), m.t_fvec(4), m.t_fvec(3), m.t_mat(4)
+    st = m.t_struct(mat4, mat4, tag="UBO")
+    m.member_decorate(st, 0, Dec.Offset, 0)
+    m.member_decorate(st, 1, Dec.Offset, 64)
+    ubo = m.ubo(st, 0, 0, "ubo")
+    ia, ib, ic = m.input(v4, 0, "a"), m.input(v4, 1, "b"), m.input(v4, 2, "c")
+    out = m.output(v4, 0, "r")
+    gl = m.per_vertex_out()
+    f = _main(m)
+    a, b, c = m.load(v4, ia), m.load(v4, ib), m.load(v4, ic)
+    M = m.load(mat4, m.access(SC.Uniform, mat4, ubo, m.const_i(0)))
+    N = m.load(mat4, m.access(SC.Uniform, mat4, ubo, m.const_i(1)))
+    a3, b3 = m.shuffle(v3, a, a, 0, 1, 2), m.shuffle(v3, b, b, 0, 1, 2)
+    ax, bx = m.extract(fl, a, 0), m.extract(fl, b, 0)
+
+    def splat(s):
+        return m.construct(v4, s, s, s, s)
+
+    def pad3(v):
+        return m.construct(v4, m.extract(fl, v, 0), m.extract(fl, v, 1), m.extract(fl, v, 2), m.const_f(0.0))
+
+    def col_sum(mat):
+        # fold a matrix into a vec4: sum of its columns, left to right
+        r = m.extract(v4, mat, 0)
+        for i in (1, 2, 3):
+            r = m.inst(Op.FAdd, v4, r, m.extract(v4, mat, i))
+        return r
+
+    if op == "fadd":
+        r = m.inst(Op.FAdd, v4, a, b)
+    elif op == "fsub":
+        r = m.inst(Op.FSub, v4, a, b)
+    elif op == "fmul":
+        r = m.inst(Op.FMul, v4, a, b)
+    elif op == "fdiv":
+        r = m.inst(Op.FDiv, v4, a, b)
+    elif op == "fneg":
+        r = m.inst(Op.FNegate, v4, a)
+    elif op == "vts":
+        r = m.inst(Op.VectorTimesScalar, v4, a, bx)
+    elif op == "dot4":
+        r = splat(m.inst(Op.Dot, fl, a, b))
+    elif op == "dot3":
+        r = splat(m.inst(Op.Dot, fl, a3, b3))
+    elif op == "fmin":
+        r = m.ext(v4, GLSL.FMin, a, b)
+    elif op == "fmax":
+        r = m.ext(v4, GLSL.FMax, a, b)
+    elif op == "fclamp":
+        r = m.ext(v4, GLSL.FClamp, a, b, c)
+    elif op == "fmix":
+        r = m.ext(v4, GLSL.FMix, a, b, c)
+    elif op == "sqrt":
+        r = splat(m.ext(fl, GLSL.Sqrt, ax))
+    elif op == "invsqrt":
+        r = splat(m.ext(fl, GLSL.InverseSqrt, ax))
+    elif op == "normalize3":
+        r = pad3(m.ext(v3, GLSL.Normalize, a3))
+    elif op == "length3":
+        r = splat(m.ext(fl, GLSL.Length, a3))
+    elif op == "reflect3":
+        r = pad3(m.ext(v3, GLSL.Reflect, a3, b3))
+    elif op == "cross3":
+        r = pad3(m.ext(v3, GLSL.Cross, a3, b3))
+    elif op == "shuffle":
+        r = m.shuffle(v4, a, b, 3, 4, 1, 6)
+    elif op == "mxv":
+        r = m.inst(Op.MatrixTimesVector, v4, M, a)
+    elif op == "vxm":
+        r = m.inst(Op.VectorTimesMatrix, v4, a, M)
+    elif op == "mxm":
+        r = col_sum(m.inst(Op.MatrixTimesMatrix, mat4, M, N))
+    elif op == "transpose":
+        r = m.extract(v4, m.inst(Op.Transpose, mat4, M), 1)
+    elif op == "mxs":
+        r = m.extract(v4, m.inst(Op.MatrixTimesScalar, mat4, M, ax), 2)
+    elif op == "minverse":
+        r = m.extract(v4, m.ext(mat4, GLSL.MatrixInverse, M), 3)
+    elif op == "sin":
+        r = splat(m.ext(fl, GLSL.Sin, ax))
+    elif op == "cos":
+        r = splat(m.ext(fl, GLSL.Cos, ax))
+    elif op == "pow":
+        r = m.ext(v4, GLSL.Pow, a, b)
+    else:
+        raise ValueError(op)
+    m.store(m.access(SC.Output, v4, gl, m.const_i(0)), a)
+    m.store(out, r)
+    return _finish(m, VERTEX, f, [ia, ib, ic, out, gl])

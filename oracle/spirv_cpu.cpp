@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <set>
 #include <vector>
@@ -130,6 +131,7 @@ struct Entry
 
 struct Module
 {
+  uint64_t serial = 0;    // unique per compile: a freed module's address may be reused by the next one
   std::vector<uint32_t> code;
   uint32_t idbound = 0;
   uint32_t glsl = 0;
@@ -710,6 +712,7 @@ static float dotN(const float *a, const float *b, int n)
 struct State
 {
   const Module *mod = NULL;
+  uint64_t serial = 0;
   std::vector<Val> vals;
   std::vector<uint8_t> arena;
   size_t top = 0;
@@ -733,10 +736,11 @@ static State &stateFor(const Module *m)
   // the reference's threaded path calls shaders from 8 threads (rasterizer.cpp:49-72)
   static thread_local std::vector<State *> cache;
   for(State *s : cache)
-    if(s->mod == m)
+    if(s->mod == m && s->serial == m->serial)
       return *s;
   State *s = new State;
   s->mod = m;
+  s->serial = m->serial;
   s->vals = m->consts;
   s->arena.resize(1 << 16);
   s->globals.assign(m->globalsSize, 0);
@@ -1210,7 +1214,9 @@ bool fetch_vertex_attr(uint32_t format, const uint8_t *ptr, float out[4])
 
 Module *compile(const uint32_t *code, size_t words, std::string *err)
 {
+  static std::atomic<uint64_t> nextSerial{1};
   Module *m = new Module;
+  m->serial = nextSerial++;
   m->code.assign(code, code + words);
   try
   {

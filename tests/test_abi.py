@@ -1,0 +1,174 @@
+"""The C-ABI library: loads without a GPU, exports every symbol include/visor_b200.h declares, its
+struct layouts match the ctypes mirror, shaders lower to unfused IEEE PTX that nvJitLink accepts for
+sm_100a, errors are reported (never thrown), and there is NO CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from harness import abi, shaders
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "visor_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import visor_b200
+    L = visor_b200.lib()
+    L.vb200_shader_create.restype = C.c_void_p
+    L.vb200_shader_create.argtypes = [C.c_void_p, C.c_size_t]
+    L.vb200_shader_entry.restype = C.c_void_p
+    L.vb200_shader_entry.argtypes = [C.c_void_p, C.c_char_p]
+    L.vb200_shader_destroy.argtypes = [C.c_void_p]
+    L.vb200_entry_ptx.restype = C.c_char_p
+    L.vb200_entry_ptx.argtypes = [C.c_void_p]
+    L.vb200_entry_stage.argtypes = [C.c_void_p]
+    L.vb200_last_error.restype = C.c_char_p
+    L.vb200_link_check.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    return L
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"VB200_API\s+[^;(]*?\b(vb200_\w+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in visor_b200.h but not exported: {missing}"
+    assert lib.vb200_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    """sizeof/offsetof from a C compiler vs the ctypes mirror in harness/abi.py"""
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "visor_b200.h"
+int main(void){
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(vb200_image), sizeof(vb200_buffer), sizeof(vb200_vertex_attr),
+         sizeof(vb200_pipeline), sizeof(vb200_binding), sizeof(vb200_draw_state), sizeof(vb200_stats));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(vb200_draw_state, vbs), offsetof(vb200_draw_state, color),
+         offsetof(vb200_draw_state, pipeline), offsetof(vb200_draw_state, pushconsts), offsetof(vb200_pipeline, vs));
+  return 0; }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
+                        os.path.join(d, "t.c")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [int(x) for x in out]
+    assert sizes[:7] == [C.sizeof(abi.Image), C.sizeof(abi.Buffer), C.sizeof(abi.VertexAttr), C.sizeof(abi.Pipeline),
+                         C.sizeof(abi.Binding), C.sizeof(abi.DrawState), C.sizeof(abi.Stats)]
+    assert sizes[7:] == [abi.DrawState.vbs.offset, abi.DrawState.color.offset, abi.DrawState.pipeline.offset,
+                         abi.DrawState.pushconsts.offset, abi.Pipeline.vs.offset]
+    assert C.sizeof(abi.Image) == 40  # VkImage_T is 40 bytes too
+
+
+def _entry(lib, words):
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    mod = lib.vb200_shader_create(w.ctypes.data, w.size)
+    assert mod, lib.vb200_last_error()
+    e = lib.vb200_shader_entry(mod, b"main")
+    assert e
+    return mod, e
+
+
+PAIRS = {
+    "c1": (shaders.vs_passthrough, shaders.fs_color),
+    "c2": (shaders.vs_mvp_uv, shaders.fs_texture),
+    "c3": (lambda: shaders.vs_lit(False), shaders.fs_color),
+    "c5": (lambda: shaders.vs_lit(True), shaders.fs_lit_tex),
+    "kitchen_sink": (shaders.vs_kitchen_sink, shaders.fs_kitchen_sink),
+    "cube": (shaders.vs_pos_dir, shaders.fs_cube),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PAIRS))
+def test_shaders_lower_to_ieee_ptx_and_link_for_sm100a(lib, name):
+    vs, fs = PAIRS[name]
+    m1, ve = _entry(lib, vs())
+    m2, fe = _entry(lib, fs())
+    assert lib.vb200_entry_stage(ve) == 0 and lib.vb200_entry_stage(fe) == 4
+    for e in (ve, fe):
+        ptx = lib.vb200_entry_ptx(e).decode()
+        assert ".target sm_100a" in ptx
+        # arithmetic contract: explicit .rn, never fused, never flushed
+        assert not re.search(r"\b(fma|mad)\.(rn\.)?f32", ptx)
+        assert ".ftz" not in ptx
+        for ins in re.findall(r"^\s*(add|sub|mul|div)\.(\S*)f32", ptx, flags=re.M):
+            assert ins[1] == "rn.", ins
+    sz = C.c_uint64()
+    rc = lib.vb200_link_check(ve, fe, C.byref(sz))
+    assert rc == 0, lib.vb200_last_error()
+    assert sz.value > 10000
+    lib.vb200_shader_destroy(m1)
+    lib.vb200_shader_destroy(m2)
+
+
+@pytest.mark.parametrize("op", shaders.UNIT_OPS)
+def test_unit_op_shaders_compile(lib, op):
+    mod, e = _entry(lib, shaders.vs_unit(op))
+    assert b"vb200_vs" in lib.vb200_entry_ptx(e)
+    lib.vb200_shader_destroy(mod)
+
+
+def test_compile_errors_return_null_with_message(lib):
+    """CompileFunction == NULL -> VK_ERROR_DEVICE_LOST in the reference (shaders.cpp:13-14)."""
+    good = shaders.vs_passthrough()
+    bad_magic = good.copy()
+    bad_magic[0] = 0xDEADBEEF
+    assert not lib.vb200_shader_create(bad_magic.ctypes.data, bad_magic.size)
+    assert b"magic" in lib.vb200_last_error()
+    newer = good.copy()
+    newer[1] = 0x00010300  # SPIR-V 1.3 > 1.1 (spirv_compile.cpp:652)
+    assert not lib.vb200_shader_create(newer.ctypes.data, newer.size)
+    # an opcode outside the reference's subset: OpSelect (169)
+    from harness.spvasm import Module, Op, VERTEX
+    m = Module()
+    v4, bl = m.t_fvec(4), m.t_bool()
+    a = m.input(v4, 0)
+    gl = m.per_vertex_out()
+    void = m.t_void()
+    f, _ = m.begin_function(void, m.t_func(void))
+    m.label()
+    x = m.load(v4, a)
+    c = m.inst(Op.FOrdLessThan, m.t_vec(bl, 4), x, x)
+    m.inst(Op.Select, v4, c, x, x)
+    m.ret()
+    m.end_function()
+    m.entry_point(VERTEX, f, "main", [a, gl])
+    w = m.words()
+    assert not lib.vb200_shader_create(w.ctypes.data, w.size)
+    assert b"Unhandled SPIR-V opcode 169" in lib.vb200_last_error()
+    truncated = good[:8].copy()  # cuts OpMemoryModel (3 words) in half
+    assert not lib.vb200_shader_create(truncated.ctypes.data, truncated.size)
+    mod, _ = _entry(lib, good)
+    assert not lib.vb200_shader_entry(mod, b"does_not_exist")
+    lib.vb200_shader_destroy(mod)
+
+
+def test_oracle_and_product_accept_the_same_modules(lib, vor):
+    for name, (vs, fs) in PAIRS.items():
+        for words in (vs(), fs()):
+            mod = vor.CompileFunction(words)
+            vor.DestroyFunction(mod)
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    """On a machine without CUDA the compute entry points must fail loudly, not emulate."""
+    import shutil
+    if shutil.which("nvidia-smi") and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0:
+        pytest.skip("a GPU is present")
+    assert lib.vb200_init(0) == -1  # VB200_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.vb200_last_error()
+    img = abi.make_image(np.zeros((4, 4, 4), np.uint8), 4, 4, abi.FMT_B8G8R8A8_UNORM)
+    col = (C.c_float * 4)(0, 0, 0, 1)
+    assert lib.vb200_clear_color(C.byref(img), col) == -1
+    assert lib.vb200_flush() == -1

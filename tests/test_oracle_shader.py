@@ -1,0 +1,244 @@
+"""Known-answer tests that pin oracle/spirv_cpu.cpp (the CPU restatement of the reference's SPIR-V
+front end + JIT wrappers, spirv_compile.cpp) op by op against an independent numpy float32
+re-computation written from the reference's semantics.
+
+The reference's LLVM-6 JIT cannot be built here, so this is what pins the shader stage
+("parity unpinned" against the reference's own binary; pinned against its documented arithmetic).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from harness import abi, shaders
+
+f32 = np.float32
+
+
+def _dot(a, b, n):
+    acc = f32(a[0] * b[0])
+    for i in range(1, n):
+        acc = f32(acc + f32(a[i] * b[i]))
+    return acc
+
+
+def _mxv(Mc, v):  # Mc[col][row]; Float4x4TimesVec4: out[r] = 0; out[r] += m[c*4+r]*v[c]
+    out = []
+    for r in range(4):
+        acc = f32(0.0)
+        for c in range(4):
+            acc = f32(acc + f32(Mc[c][r] * v[c]))
+        out.append(acc)
+    return np.array(out, dtype=f32)
+
+
+def _vxm(Mc, v):  # Vec4TimesFloat4x4: out[r] += m[r*4+c]*v[c]
+    out = []
+    for r in range(4):
+        acc = f32(0.0)
+        for c in range(4):
+            acc = f32(acc + f32(Mc[r][c] * v[c]))
+        out.append(acc)
+    return np.array(out, dtype=f32)
+
+
+def _mxm(A, B):  # Float4x4TimesFloat4x4(a, b): out[x][y] = ((b[x][0]*a[0][y] + b[x][1]*a[1][y]) + ..)
+    out = np.zeros((4, 4), dtype=f32)
+    for x in range(4):
+        for y in range(4):
+            acc = f32(B[x][0] * A[0][y])
+            for k in range(1, 4):
+                acc = f32(acc + f32(B[x][k] * A[k][y]))
+            out[x][y] = acc
+    return out
+
+
+def expected(op, a, b, c, M, N):
+    one = f32(1.0)
+    if op == "fadd":
+        return a + b
+    if op == "fsub":
+        return a - b
+    if op == "fmul":
+        return a * b
+    if op == "fdiv":
+        return a / b
+    if op == "fneg":
+        return f32(-0.0) - a
+    if op == "vts":
+        return a * b[0]
+    if op == "dot4":
+        return np.full(4, _dot(a, b, 4), dtype=f32)
+    if op == "dot3":
+        return np.full(4, _dot(a, b, 3), dtype=f32)
+    if op == "fmin":
+        return np.where(a < b, a, b)
+    if op == "fmax":
+        return np.where(a > b, a, b)
+    if op == "fclamp":  # val=a, lower=b, upper=c
+        up = np.where(a < c, a, c)
+        return np.where(up > b, up, b)
+    if op == "fmix":  # x=a, y=b, a=c: (1-c)*x + c*y
+        return (one - c) * a + c * b
+    if op == "sqrt":
+        return np.full(4, np.sqrt(a[0]), dtype=f32)
+    if op == "invsqrt":
+        return np.full(4, one / np.sqrt(a[0]), dtype=f32)
+    if op == "normalize3":
+        inv = one / np.sqrt(_dot(a, a, 3))
+        return np.array([a[0] * inv, a[1] * inv, a[2] * inv, 0], dtype=f32)
+    if op == "length3":
+        return np.full(4, np.sqrt(_dot(a, a, 3)), dtype=f32)
+    if op == "reflect3":
+        d2 = f32(_dot(a, b, 3) * f32(2.0))
+        return np.array([a[i] - f32(d2 * b[i]) for i in range(3)] + [0], dtype=f32)
+    if op == "cross3":  # the reference returns operand 0 (spirv_compile.cpp:1661)
+        return np.array([a[0], a[1], a[2], 0], dtype=f32)
+    if op == "shuffle":
+        return np.array([a[3], b[0], a[1], b[2]], dtype=f32)
+    if op == "mxv":
+        return _mxv(M, a)
+    if op == "vxm":
+        return _vxm(M, a)
+    if op == "mxm":
+        P = _mxm(M, N)
+        r = P[0].copy()
+        for i in (1, 2, 3):
+            r = r + P[i]
+        return r
+    if op == "transpose":
+        return np.array([M[r][1] for r in range(4)], dtype=f32)
+    if op == "mxs":
+        return M[2] * a[0]
+    if op == "minverse":  # the reference calls Float4x4Transpose (spirv_compile.cpp:1721)
+        return np.array([M[r][3] for r in range(4)], dtype=f32)
+    if op == "sin":
+        return np.full(4, np.sin(a[0]), dtype=f32)
+    if op == "cos":
+        return np.full(4, np.cos(a[0]), dtype=f32)
+    if op == "pow":
+        return np.power(a, b).astype(f32)
+    raise ValueError(op)
+
+
+def unit_inputs(seed=0, n=64):
+    rng = np.random.default_rng(seed)
+    verts = rng.uniform(0.1, 3.0, size=(n, 12)).astype(f32)
+    verts[:, 0:4] *= rng.choice([-1.0, 1.0], size=(n, 4)).astype(f32)
+    verts[:, 4:8] *= rng.choice([-1.0, 1.0], size=(n, 4)).astype(f32)
+    ubo = rng.uniform(-2.0, 2.0, size=32).astype(f32)
+    return verts, ubo
+
+
+def unit_state(be, op, verts, ubo):
+    """A draw state good enough for vor_run_vertex: three vec4 attributes from one interleaved VB."""
+    mod = be.CompileFunction(shaders.vs_unit(op))
+    pl = abi.Pipeline()
+    for loc in range(3):
+        pl.vattrs[loc].format, pl.vattrs[loc].stride = abi.FMT_R32G32B32A32_SFLOAT, 48
+        pl.vattrs[loc].offset, pl.vattrs[loc].vb = 16 * loc, 0
+    st = abi.DrawState()
+    st.vbs[0].buffer = abi.make_buffer(verts)
+    st.pipeline = C.pointer(pl)
+    arr = (abi.Binding * 1)()
+    arr[0].set, arr[0].binding, arr[0].type = 0, 0, abi.DESC_UNIFORM_BUFFER
+    arr[0].buffer = abi.make_buffer(ubo)
+    st.bindings = C.cast(arr, C.POINTER(abi.Binding))
+    st.num_bindings = 1
+    return mod, st, (pl, arr)
+
+
+@pytest.mark.parametrize("op", shaders.UNIT_OPS)
+def test_unit_op_matches_numpy(vor, op):
+    verts, ubo = unit_inputs()
+    if op in ("sqrt", "invsqrt", "pow"):
+        verts[:, 0:4] = np.abs(verts[:, 0:4])
+    mod, st, keep = unit_state(vor, op, verts, ubo)
+    entry = vor.GetFuncPointer(mod, "main")
+    run = vor.lib.vor_run_vertex
+    run.argtypes = [C.POINTER(abi.DrawState), C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    M = ubo[:16].reshape(4, 4)  # M[col][row]
+    N = ubo[16:].reshape(4, 4)
+    out = (C.c_float * 44)()
+    for i in range(verts.shape[0]):
+        assert run(C.byref(st), entry, i, out) == 0
+        got = np.array(out[4:8], dtype=f32)
+        pos = np.array(out[0:4], dtype=f32)
+        a, b, c = verts[i, 0:4], verts[i, 4:8], verts[i, 8:12]
+        assert np.array_equal(pos.view(np.uint32), a.view(np.uint32))
+        with np.errstate(all="ignore"):
+            exp = np.asarray(expected(op, a, b, c, M, N), dtype=f32)
+        if op in ("sin", "cos", "pow"):  # libm vs numpy: not bit-reproducible by construction
+            assert np.allclose(got, exp, rtol=1e-5, atol=1e-6)
+        else:
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (op, i, got, exp)
+    vor.DestroyFunction(mod)
+
+
+def test_fragment_interpolation_kat(vor):
+    """FS input = ((b0*v0 + b1*v1) + b2*v2) + bw*0 per component (spirv_compile.cpp:629-643,2196-2214)."""
+    mod = vor.CompileFunction(shaders.fs_color())
+    entry = vor.GetFuncPointer(mod, "main")
+    run = vor.lib.vor_run_fragment
+    run.argtypes = [C.POINTER(abi.DrawState), C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                    C.POINTER(C.c_float)]
+    rng = np.random.default_rng(5)
+    st = abi.DrawState()
+    for _ in range(50):
+        tri = rng.uniform(-4, 4, size=(3, 44)).astype(f32)
+        bary = rng.uniform(0, 1, size=4).astype(f32)
+        bary[3] = 0
+        out = (C.c_float * 4)()
+        assert run(C.byref(st), entry, bary.ctypes.data_as(C.POINTER(C.c_float)),
+                   tri.ctypes.data_as(C.POINTER(C.c_float)), out) == 0
+        exp = []
+        for comp in range(4):
+            v = [tri[k, 4 + comp] for k in range(3)]
+            acc = f32(f32(bary[0] * v[0]) + f32(bary[1] * v[1]))
+            acc = f32(acc + f32(bary[2] * v[2]))
+            acc = f32(acc + f32(bary[3] * f32(0.0)))
+            exp.append(acc)
+        assert np.array_equal(np.array(out[:], dtype=f32).view(np.uint32), np.array(exp, dtype=f32).view(np.uint32))
+
+
+def test_vertex_output_padding_rules(vor):
+    """vec<4 outputs repeat .x, scalars splat, ints are bit-cast (spirv_compile.cpp:2057-2092)."""
+    mod = vor.CompileFunction(shaders.vs_kitchen_sink())
+    entry = vor.GetFuncPointer(mod, "main")
+    rng = np.random.default_rng(9)
+    verts = np.zeros(6, dtype=[("pos", f32, 4), ("nrm", f32, 3), ("w", f32), ("flag", np.int32)])
+    verts["pos"] = rng.uniform(-1, 1, (6, 4))
+    verts["nrm"] = rng.uniform(-1, 1, (6, 3))
+    verts["w"] = 0.75
+    verts["flag"] = 7
+    vb = verts.view(np.uint8)
+    ubo = rng.uniform(-1, 1, 36).astype(f32)
+    pl = abi.Pipeline()
+    for loc, (fmt, off) in enumerate([(abi.FMT_R32G32B32A32_SFLOAT, 0), (abi.FMT_R32G32B32_SFLOAT, 16),
+                                      (abi.FMT_R32_SFLOAT, 28), (abi.FMT_R32_SINT, 32)]):
+        pl.vattrs[loc].format, pl.vattrs[loc].stride, pl.vattrs[loc].offset = fmt, 36, off
+    st = abi.DrawState()
+    st.vbs[0].buffer = abi.make_buffer(vb)
+    st.pipeline = C.pointer(pl)
+    arr = (abi.Binding * 1)()
+    arr[0].set, arr[0].binding = 1, 2
+    arr[0].buffer = abi.make_buffer(ubo)
+    st.bindings = C.cast(arr, C.POINTER(abi.Binding))
+    st.num_bindings = 1
+    push = np.array([0.5, -0.25, 2.0, 1.5], dtype=f32)
+    C.memmove(st.pushconsts, push.ctypes.data, 16)
+    run = vor.lib.vor_run_vertex
+    run.argtypes = [C.POINTER(abi.DrawState), C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    out = (C.c_float * 44)()
+    assert run(C.byref(st), entry, 5, out) == 0
+    o = np.array(out[:], dtype=f32).reshape(11, 4)
+    assert np.array_equal(o[0], verts["pos"][5])                 # gl_Position = pos (vertex 5)
+    assert o[2][3] == o[2][0]                                    # vec3 @1 padded with .x
+    assert o[3][0] == o[3][1] == o[3][2] == o[3][3]              # float @2 splat
+    flag_bits = o[4].view(np.int32)
+    assert (flag_bits == flag_bits[0]).all()
+    # ((7*3) & 0xff) >> 1 [OpShiftLeftLogical is a right shift in the reference] + gl_VertexIndex(5)
+    assert flag_bits[0] == ((7 * 3) & 0xFF) // 2 + 5
+    assert o[5][2] == o[5][0] and o[5][3] == o[5][0]             # vec2 @4 padded with .x
+    assert o[5][0] == push[1] and o[5][1] == ubo[34]             # shuffle(k, s, 1, 6) = (k.y, s.z)
+    assert np.array_equal(o[9], push)                            # mat4 @5..8: last column = k

@@ -9,6 +9,7 @@
 //                                 count -> exclusive scan -> fill -> per-tile sort by triangle id
 //   K5' stand-alone sampler       sample_tex_wrapped/_cube_wrapped texture_sampling.cpp:139-250
 //   K6  tile pack / unpack        (sort-first multi-GPU; no reference equivalent)
+#include <algorithm>
 #include "kernels.h"
 #include "raster_common.cuh"
 
@@ -55,23 +56,56 @@ __device__ __forceinline__ uint32_t load_index(const void *ib, uint32_t index_ty
 __global__ void __launch_bounds__(kThreads) k_index_range(const void *ib, uint32_t index_type, uint32_t first,
                                                          uint32_t count, uint32_t *range)
 {
+  // persistent grid-stride reduction: one atomic pair per CTA (the L2 atomic unit serialises per
+  // address, so per-warp atomics on two words would dominate the kernel)
+  __shared__ uint32_t s_lo[kThreads / 32], s_hi[kThreads / 32];
   uint32_t lo = 0xffffffffu, hi = 0u;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if(index_type != 0u && ((((uintptr_t)ib) + 4ull * first) & 15) == 0)
   {
-    const uint32_t v = load_index(ib, index_type, first + i);
-    lo = min(lo, v);
-    hi = max(hi, v);
+    // 16-byte vector loads of 4 indices
+    const uint4 *v4 = (const uint4 *)((const uint32_t *)ib + first);
+    const uint32_t n4 = count / 4u;
+    for(uint32_t i = tid; i < n4; i += stride)
+    {
+      const uint4 v = __ldg(v4 + i);
+      lo = min(min(lo, v.x), min(min(v.y, v.z), v.w));
+      hi = max(max(hi, v.x), max(max(v.y, v.z), v.w));
+    }
+    for(uint32_t i = n4 * 4u + tid; i < count; i += stride)
+    {
+      const uint32_t v = load_index(ib, index_type, first + i);
+      lo = min(lo, v);
+      hi = max(hi, v);
+    }
   }
-  for(int o = 16; o > 0; o >>= 1)
+  else
+    for(uint32_t i = tid; i < count; i += stride)
+    {
+      const uint32_t v = load_index(ib, index_type, first + i);
+      lo = min(lo, v);
+      hi = max(hi, v);
+    }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if((threadIdx.x & 31) == 0)
   {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
   }
-  if((threadIdx.x & 31) == 0 && lo <= hi)
+  __syncthreads();
+  if(threadIdx.x < 32)
   {
-    atomicMin(&range[0], lo);
-    atomicMax(&range[1], hi);
+    lo = threadIdx.x < kThreads / 32 ? s_lo[threadIdx.x] : 0xffffffffu;
+    hi = threadIdx.x < kThreads / 32 ? s_hi[threadIdx.x] : 0u;
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if(threadIdx.x == 0 && lo <= hi)
+    {
+      atomicMin(&range[0], lo);
+      atomicMax(&range[1], hi);
+    }
   }
 }
 
@@ -448,7 +482,9 @@ int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint
   k_init_range<<<1, 1, 0, s>>>(range);
   if(!count)
     return 1;
-  k_index_range<<<grid_for(count, 8), kThreads, 0, s>>>(ib, index_type, first, count, range);
+  // one wave: 4 CTAs per SM
+  const uint32_t g = (uint32_t)std::min<size_t>((size_t)sm_count() * 4, (count + kThreads - 1) / kThreads);
+  k_index_range<<<g ? g : 1, kThreads, 0, s>>>(ib, index_type, first, count, range);
   return 2;
 }
 

@@ -332,13 +332,13 @@ enum
   VB200_RES_LAST_WINS = 4,    // no test / static test: highest triangle id that passes
 };
 
+// Per-triangle raster record staged in shared memory (64 B, one per lane of the warp that loaded it).
 struct TriCoef
 {
-  int A1, B1, C1, A2;
-  int B2, C2, area, x0;
-  int y0, x1, y1;
-  uint32_t id;    // triangle index + 1
+  int A1, B1, C1, A2;              // b1 = A1*x + B1*y + C1, b2 = A2*x + B2*y + C2 (barymul folded in)
+  int B2, C2, area, xy0;           // |area2|; bbox origin clipped to the tile: x0 | y0 << 16
   float invarea, d0, d1, d2;
+  uint32_t id, excl, w, magic;     // triangle index + 1; first slot in the pixel stream; bbox width; ceil(2^16/w)
 };
 
 // float -> uint32 whose unsigned order equals the float order (-0 == +0); callers exclude NaN
@@ -365,56 +365,11 @@ __device__ __forceinline__ unsigned long long vb200_existing_key(float e)
 }
 
 template <int MODE>
-__device__ __forceinline__ void vb200_resolve_pixel(const TriCoef &c, int x, int y, int tileX0, int tileY0,
-                                                    unsigned long long *vis, const float *s_depth, bool depthTest,
-                                                    uint32_t depthOp, uint32_t &covered)
-{
-  const int b1 = c.A1 * x + c.B1 * y + c.C1;
-  const int b2 = c.A2 * x + c.B2 * y + c.C2;
-  const int b0 = c.area - (b1 + b2);
-  if((b0 | b1 | b2) < 0)
-    return;
-  covered++;
-  const int idx = (y - tileY0) * VB200_TILE + (x - tileX0);
-  unsigned long long key;
-  if(MODE == VB200_RES_LAST_WINS && !depthTest)
-    key = (unsigned long long)(~c.id);
-  else
-  {
-    const float n0 = __fmul_rn((float)b0, c.invarea);
-    const float n1 = __fmul_rn((float)b1, c.invarea);
-    const float n2 = __fmul_rn((float)b2, c.invarea);
-    const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, c.d0), __fmul_rn(n1, c.d1)), __fmul_rn(n2, c.d2));
-    if(MODE == VB200_RES_LAST_WINS)
-    {
-      if(!vb200_depth_pass(depthOp, pixdepth, s_depth[idx]))
-        return;
-      key = (unsigned long long)(~c.id);
-    }
-    else
-    {
-      if(pixdepth != pixdepth)
-        return;    // NaN never passes an ordered comparison
-      uint32_t k = vb200_depth_key(pixdepth);
-      if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
-        k = ~k;
-      const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? c.id : ~c.id;
-      key = ((unsigned long long)k << 32) | low;
-    }
-  }
-  if(key < vis[idx])
-    atomicMin(&vis[idx], key);
-}
-
-#define VB200_SMALL_AREA 64
-
-template <int MODE>
 __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, const Vb200TileParams &p)
 {
   __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
   __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
-  __shared__ TriCoef s_big[256];
-  __shared__ uint32_t s_nbig;
+  __shared__ int4 s_coef[8][32][4];    // TriCoef records, one per lane of each warp
 
   const uint32_t tile = blockIdx.x;
   const uint32_t n = p.tile_count[tile];
@@ -442,70 +397,121 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     if(MODE == VB200_RES_LAST_WINS)
       s_depth[ly * VB200_TILE + lane] = e;
   }
-  if(threadIdx.x == 0)
-    s_nbig = 0;
   __syncthreads();
 
-  // ---- phase A: coverage + visibility, triangle-parallel
+  // ---- phase A: coverage + visibility.
+  // Each warp takes 32 triangles of the list at a time. Their tile-clipped bboxes are laid end to
+  // end into one stream of candidate pixels (exclusive prefix sum of the pixel counts); every step
+  // the 32 lanes test 32 consecutive pixels of that stream, whichever triangles they belong to, so
+  // 6-pixel and full-tile triangles keep the lanes equally busy. Every listed triangle has a
+  // non-empty clipped bbox (the binning walked exactly these pixel ranges), so valid lanes are
+  // 0..m-1 and "rank among triangles" is the lane that staged the record.
   uint32_t covered = 0, shaded = 0;
-  for(uint32_t base = 0; base < n; base += 256)
+  int4(*wc)[4] = s_coef[warp];
+  // spread the list evenly over the 8 warps: ceil(n/8) triangles per warp per round, at most 32
+  const uint32_t chunk = min(32u, (n + 7u) >> 3);
+  for(uint32_t base = warp * chunk; base < n; base += 8u * chunk)
   {
-    const uint32_t i = base + threadIdx.x;
-    if(i < n)
+    const uint32_t i = base + lane;
+    uint32_t cnt = 0;
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = make_int4(0, 0, 1, 65536);
+    if(i < n && (uint32_t)lane < chunk)
     {
       const uint32_t t = p.list[off + i];
       const Vb200TriSetup su = vb200_load_setup(p.setup + t);
-      TriCoef c;
       const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
       const int area2 = ABx * ACy - ABy * ACx;
       const int sgn = area2 > 0 ? 1 : -1;
-      c.A1 = sgn * ACy;
-      c.B1 = -sgn * ACx;
-      c.C1 = sgn * (ACx * su.y0 - ACy * su.x0);
-      c.A2 = -sgn * ABy;
-      c.B2 = sgn * ABx;
-      c.C2 = sgn * (ABy * su.x0 - ABx * su.y0);
-      c.area = sgn * area2;
-      c.x0 = max(max(0, min(su.x0, min(su.x1, su.x2))), tileX0);
-      c.y0 = max(max(0, min(su.y0, min(su.y1, su.y2))), tileY0);
-      c.x1 = min(min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2))), tileX0 + VB200_TILE);
-      c.y1 = min(min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2))), tileY0 + VB200_TILE);
-      c.id = t + 1u;
-      c.invarea = __fdiv_rn(1.0f, (float)c.area);
-      c.d0 = su.d0;
-      c.d1 = su.d1;
-      c.d2 = su.d2;
-      const int w = c.x1 - c.x0, h = c.y1 - c.y0;
-      if(w > 0 && h > 0)
+      const int x0 = max(max(0, min(su.x0, min(su.x1, su.x2))), tileX0);
+      const int y0 = max(max(0, min(su.y0, min(su.y1, su.y2))), tileY0);
+      const int x1 = min(min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2))), tileX0 + VB200_TILE);
+      const int y1 = min(min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2))), tileY0 + VB200_TILE);
+      const int w = max(x1 - x0, 1), h = max(y1 - y0, 0);
+      cnt = (x1 > x0) ? (uint32_t)(w * h) : 0u;
+      r0 = make_int4(sgn * ACy, -sgn * ACx, sgn * (ACx * su.y0 - ACy * su.x0), -sgn * ABy);
+      r1 = make_int4(sgn * ABx, sgn * (ABy * su.x0 - ABx * su.y0), sgn * area2, x0 | (y0 << 16));
+      r2 = make_int4(__float_as_int(__fdiv_rn(1.0f, (float)(sgn * area2))), __float_as_int(su.d0),
+                     __float_as_int(su.d1), __float_as_int(su.d2));
+      // floor(i / w) == (i * magic) >> 16 for i < 1024, w <= 32
+      r3 = make_int4((int)(t + 1u), 0, w, (int)(65535u / (uint32_t)w + 1u));
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if(lane >= o)
+        incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t myStart = incl - cnt;
+    r3.y = (int)myStart;
+    __syncwarp();
+    wc[lane][0] = r0;
+    wc[lane][1] = r1;
+    wc[lane][2] = r2;
+    wc[lane][3] = r3;
+    __syncwarp();
+    const bool hasPixels = cnt != 0u;
+    for(uint32_t k = 0; k < total; k += 32u)
+    {
+      // owner of stream slot k + lane = (#triangles starting before this step) + (#starts inside the
+      // step at or before this lane) - 1
+      const uint32_t before = __popc(__ballot_sync(0xffffffffu, hasPixels && myStart < k));
+      const uint32_t rel = myStart - k;
+      const uint32_t starts = __reduce_or_sync(0xffffffffu, (hasPixels && rel < 32u) ? (1u << rel) : 0u);
+      const uint32_t g = k + lane;
+      if(g >= total)
+        continue;
+      // lanes with an empty bbox cannot occur between valid ones (see above), so rank == lane index
+      const uint32_t owner = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u;
+      const int4 c0 = wc[owner][0], c1 = wc[owner][1], c3 = wc[owner][3];
+      const uint32_t li = g - (uint32_t)c3.y;
+      const uint32_t yq = (li * (uint32_t)c3.w) >> 16;
+      const uint32_t xq = li - yq * (uint32_t)c3.z;
+      const int x = (c1.w & 0xffff) + (int)xq, y = (c1.w >> 16) + (int)yq;
+      const int b1 = c0.x * x + c0.y * y + c0.z;
+      const int b2 = c0.w * x + c1.x * y + c1.y;
+      const int b0 = c1.z - (b1 + b2);
+      if((b0 | b1 | b2) < 0)
+        continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
+      covered++;
+      const int idx = (y - tileY0) * VB200_TILE + (x - tileX0);
+      const uint32_t id = (uint32_t)c3.x;
+      unsigned long long key;
+      if(MODE == VB200_RES_LAST_WINS && !depthTest)
+        key = (unsigned long long)(~id);
+      else
       {
-        if(w * h <= VB200_SMALL_AREA)
+        const int4 c2 = wc[owner][2];
+        const float invarea = __int_as_float(c2.x);
+        const float n0 = __fmul_rn((float)b0, invarea);
+        const float n1 = __fmul_rn((float)b1, invarea);
+        const float n2 = __fmul_rn((float)b2, invarea);
+        const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, __int_as_float(c2.y)), __fmul_rn(n1, __int_as_float(c2.z))),
+                                         __fmul_rn(n2, __int_as_float(c2.w)));
+        if(MODE == VB200_RES_LAST_WINS)
         {
-          for(int y = c.y0; y < c.y1; y++)
-            for(int x = c.x0; x < c.x1; x++)
-              vb200_resolve_pixel<MODE>(c, x, y, tileX0, tileY0, vis, s_depth, depthTest, rs.depth_op, covered);
+          if(!vb200_depth_pass(rs.depth_op, pixdepth, s_depth[idx]))
+            continue;
+          key = (unsigned long long)(~id);
         }
         else
-          s_big[atomicAdd(&s_nbig, 1u)] = c;
+        {
+          if(pixdepth != pixdepth)
+            continue;    // NaN never passes an ordered comparison
+          uint32_t dk = vb200_depth_key(pixdepth);
+          if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
+            dk = ~dk;
+          const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? id : ~id;
+          key = ((unsigned long long)dk << 32) | low;
+        }
       }
+      if(key < vis[idx])
+        atomicMin(&vis[idx], key);
     }
-    __syncthreads();
-    const uint32_t nb = s_nbig;
-    if(nb)
-    {
-      for(uint32_t q = 0; q < nb; q++)
-      {
-        const TriCoef &c = s_big[q];
-        const int x = tileX0 + lane;
-        if(x >= c.x0 && x < c.x1)
-          for(int y = c.y0 + warp; y < c.y1; y += 8)
-            vb200_resolve_pixel<MODE>(c, x, y, tileX0, tileY0, vis, s_depth, depthTest, rs.depth_op, covered);
-      }
-      __syncthreads();
-      if(threadIdx.x == 0)
-        s_nbig = 0;
-    }
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- phase B: shade the winner of every pixel, write back
 #pragma unroll
