@@ -92,6 +92,11 @@ VB200_API const char *vb200_entry_ptx(const vb200_entry *entry);
 VB200_API int vb200_link_check(const vb200_entry *vs, const vb200_entry *fs, uint64_t *cubin_size);
 /* 0 = vertex, 4 = fragment (spv::ExecutionModel). */
 VB200_API int vb200_entry_stage(const vb200_entry *entry);
+/* The descriptors an entry point dereferences, so the binding can pick exactly those out of
+ * GPUState::sets[] (VkDescriptorSet_T does not record how many binds it holds, precompiled.h:140-156). */
+VB200_API int vb200_entry_num_resources(const vb200_entry *entry);
+VB200_API int vb200_entry_resource(const vb200_entry *entry, int index, uint32_t *set, uint32_t *binding,
+                                   uint32_t *is_image);
 
 /* ---- fixed-function + draw state: mirror VkPipeline_T / GPUState ------------------------ */
 
@@ -187,6 +192,10 @@ VB200_API int vb200_mem_register(void *host, uint64_t size);
 VB200_API int vb200_mem_unregister(void *host);
 VB200_API int vb200_mem_upload(const void *host, uint64_t size);   /* host -> HBM mirror, async */
 VB200_API int vb200_mem_download(void *host, uint64_t size);       /* HBM mirror -> host, async */
+/* The host is about to write [host, host+size) mid-submit (vkCmdCopyBuffer / vkCmdCopyBufferToImage are
+ * replayed as memcpy, cmd_exec.cpp:143-182): orders the write after in-flight uploads of the range and
+ * makes later draws re-upload it. */
+VB200_API int vb200_mem_host_write(const void *host, uint64_t size);
 /* Device address of a mirrored host pointer (NULL if not mirrored); for interop (NCCL, torch). */
 VB200_API void *vb200_mem_device_ptr(const void *host);
 

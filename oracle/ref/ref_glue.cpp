@@ -204,59 +204,7 @@ void DestroyFunction(LLVMFunction *func)
   delete func;
 }
 
-// ---------------------------------------------------------------------------------------------
-// 3. headless WSI (wsi.cpp is Win32-only). Entry points icd_interface.cpp:23-26,41-45 take the
-//    address of; rendering tests use plain VkImages, never a swapchain.
-// ---------------------------------------------------------------------------------------------
-VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfaceSupportKHR(VkPhysicalDevice, uint32_t,
-                                                                    VkSurfaceKHR, VkBool32 *pSupported)
-{
-  *pSupported = VK_FALSE;
-  return VK_SUCCESS;
-}
-VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfaceFormatsKHR(VkPhysicalDevice, VkSurfaceKHR,
-                                                                    uint32_t *pCount,
-                                                                    VkSurfaceFormatKHR *)
-{
-  *pCount = 0;
-  return VK_SUCCESS;
-}
-VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfaceCapabilitiesKHR(VkPhysicalDevice, VkSurfaceKHR,
-                                                                         VkSurfaceCapabilitiesKHR *p)
-{
-  memset(p, 0, sizeof(*p));
-  return VK_ERROR_SURFACE_LOST_KHR;
-}
-VKAPI_ATTR VkResult VKAPI_CALL vkGetPhysicalDeviceSurfacePresentModesKHR(VkPhysicalDevice, VkSurfaceKHR,
-                                                                         uint32_t *pCount,
-                                                                         VkPresentModeKHR *)
-{
-  *pCount = 0;
-  return VK_SUCCESS;
-}
-VKAPI_ATTR VkResult VKAPI_CALL vkCreateSwapchainKHR(VkDevice, const VkSwapchainCreateInfoKHR *,
-                                                    const VkAllocationCallbacks *, VkSwapchainKHR *)
-{
-  return VK_ERROR_SURFACE_LOST_KHR;
-}
-VKAPI_ATTR void VKAPI_CALL vkDestroySwapchainKHR(VkDevice, VkSwapchainKHR, const VkAllocationCallbacks *)
-{
-}
-VKAPI_ATTR VkResult VKAPI_CALL vkGetSwapchainImagesKHR(VkDevice, VkSwapchainKHR, uint32_t *pCount,
-                                                       VkImage *)
-{
-  *pCount = 0;
-  return VK_SUCCESS;
-}
-VKAPI_ATTR VkResult VKAPI_CALL vkAcquireNextImageKHR(VkDevice, VkSwapchainKHR, uint64_t, VkSemaphore,
-                                                     VkFence, uint32_t *)
-{
-  return VK_ERROR_SURFACE_LOST_KHR;
-}
-VKAPI_ATTR VkResult VKAPI_CALL vkQueuePresentKHR(VkQueue, const VkPresentInfoKHR *)
-{
-  return VK_ERROR_SURFACE_LOST_KHR;
-}
+// 3. headless WSI: oracle/ref/wsi_headless.cpp (shared with the CUDA ICD build)
 
 // ---------------------------------------------------------------------------------------------
 // 4. vref_*: visor_b200.h-shaped adapter onto the reference operators

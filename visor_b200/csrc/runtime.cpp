@@ -670,6 +670,25 @@ int vb200_entry_stage(const vb200_entry *entry)
   return entry ? entry->e.stage : -1;
 }
 
+int vb200_entry_num_resources(const vb200_entry *entry)
+{
+  return entry ? (int)entry->e.resources.size() : 0;
+}
+
+int vb200_entry_resource(const vb200_entry *entry, int index, uint32_t *set, uint32_t *binding, uint32_t *is_image)
+{
+  if(!entry || index < 0 || index >= (int)entry->e.resources.size())
+    return setError(VB200_ERR_INVALID, "entry_resource: index out of range");
+  const vb200::ResourceSlot &r = entry->e.resources[index];
+  if(set)
+    *set = r.set;
+  if(binding)
+    *binding = r.binding;
+  if(is_image)
+    *is_image = r.is_image ? 1u : 0u;
+  return VB200_OK;
+}
+
 // ---- residency -------------------------------------------------------------------------------
 int vb200_set_sync_mode(int mode)
 {
@@ -754,6 +773,38 @@ int vb200_mem_download(void *host, uint64_t size)
   const size_t off = (uintptr_t)host - (uintptr_t)m->host;
   CU(cudaMemcpyAsync(host, m->dev + off, size, cudaMemcpyDeviceToHost, g.stream));
   g.stats.d2h_bytes += size;
+  return VB200_OK;
+}
+
+int vb200_mem_host_write(const void *host, uint64_t size)
+{
+  // The host is about to modify [host, host+size) in the middle of a submit (vkCmdCopyBuffer /
+  // vkCmdCopyBufferToImage replayed as memcpy, cmd_exec.cpp:143-182): wait for in-flight uploads that
+  // read the old contents, then forget that the range was uploaded so the next draw re-reads it.
+  if(!g.ready || !host || !size || isDevicePointer(host))
+    return VB200_OK;
+  const uintptr_t lo = (uintptr_t)host, hi = lo + size;
+  bool pending = false;
+  for(auto &kv : g.mirrors)
+  {
+    Mirror &m = kv.second;
+    const uintptr_t mlo = (uintptr_t)m.host, mhi = mlo + m.size;
+    if(mlo >= hi || lo >= mhi)
+      continue;
+    for(auto it = m.uploaded.begin(); it != m.uploaded.end();)
+    {
+      const uintptr_t ulo = mlo + it->first, uhi = ulo + it->second;
+      if(ulo < hi && lo < uhi)
+      {
+        pending = true;
+        it = m.uploaded.erase(it);
+      }
+      else
+        ++it;
+    }
+  }
+  if(pending)
+    CU(cudaStreamSynchronize(g.stream));
   return VB200_OK;
 }
 
