@@ -202,3 +202,26 @@ def test_full_size_c3_properties(gpu):
     untouched = d1 == np.float32(1.0)
     assert (c1[untouched] == np.array([51, 51, 51, 255], dtype=np.uint8)).all()
     assert (d1 <= np.float32(1.0)).all() and untouched.mean() < 0.5
+
+
+def test_tile_list_guess_overflow_is_retried(gpu, vor):
+    """40 near-full-screen triangles at 2048x2048 produce far more (triangle, tile) pairs than the
+    4-per-triangle guess the speculative binning launch is sized for: the no-op + retry path."""
+    sc = scenes.random_triangles(2048, 2048, 40, 80, max_size=1.6, offscreen=0.0)
+    _check(gpu, vor, sc)
+
+
+def test_clear_fusion_variants(gpu, vor):
+    """deferred clears: consumed by the first draw, materialised for a second target/draw, depth clear
+    without a depth-using pipeline, colour cleared but depth loaded"""
+    a = scenes.random_triangles(300, 200, 100, 90)
+    a.clear_depth = None                       # colour cleared, depth loaded from host
+    _check(gpu, vor, a)
+    b = scenes.random_triangles(300, 200, 100, 91, depth_op=abi.CMP_ALWAYS, depth_write=False)
+    _check(gpu, vor, b)                        # depth attachment cleared but never touched by the draw
+    c = scenes.random_triangles(333, 211, 100, 92)
+    c.draws += scenes.random_triangles(333, 211, 100, 93, blend=(abi.BF_SRC_ALPHA, abi.BF_ONE_MINUS_SRC_ALPHA, 0),
+                                       depth_op=abi.CMP_LESS, depth_write=False).draws
+    _check(gpu, vor, c)
+    d = scenes.random_triangles(64, 48, 3, 94, max_size=0.05)   # most tiles untouched: they still get cleared
+    _check(gpu, vor, d)

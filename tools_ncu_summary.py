@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Developer aid: condense an .ncu-rep (ncu --set full) into the handful of metrics DESIGN.md / bench.py
+quote. usage: tools_ncu_summary.py <report.ncu-rep> [out.txt]"""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg",
+]
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h, units = rows[0], rows[1]
+lines = []
+for r in rows[2:]:
+    name = r[h.index("Kernel Name")]
+    lines.append(f"== {name}")
+    for i, n in enumerate(h):
+        if n in WANT or ("warp_issue_stalled" in n and n.endswith("per_warp_active.pct")):
+            try:
+                v = float(r[i].replace(",", ""))
+            except ValueError:
+                continue
+            if "stalled" in n and v < 2.0:
+                continue
+            lines.append(f"  {n:75s} {v:16.3f} {units[i]}")
+text = "\n".join(lines) + "\n"
+if len(sys.argv) > 2:
+    open(sys.argv[2], "w").write(text)
+print(text)

@@ -123,8 +123,12 @@ __device__ __forceinline__ bool tile_owned(uint32_t tile, uint32_t rank, uint32_
   return world <= 1u || (tile % world) == rank;
 }
 
-// Visit every owned tile of the inclusive range packed in `tiles`. Small ranges are walked by the
-// owning thread; large ones (full-screen triangles cover thousands of tiles) are spread over the warp.
+// Visit every owned tile of the inclusive range packed in `tiles`, handing `f` a group of lanes that
+// target the SAME tile: f(tile, tri, rank_in_group, group_size, is_leader). Neighbouring triangles of a
+// mesh land in the same tile, so per-lane atomics on the tile counters would serialise in the L2
+// atomic unit; __match_any_sync lets one lane per (warp, tile) do the atomic for the whole group.
+// Ranges of up to 2x2 tiles (every triangle smaller than a tile) take the matched path; larger ones
+// (full-screen triangles cover thousands of tiles) are spread over the warp, one tile per lane.
 template <typename F>
 __device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32_t tiles_x, uint32_t rank,
                                               uint32_t world, uint32_t tri, F f)
@@ -132,19 +136,27 @@ __device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32
   const uint32_t tx0 = tiles & 0xffu, ty0 = (tiles >> 8) & 0xffu, tx1 = (tiles >> 16) & 0xffu, ty1 = tiles >> 24;
   const uint32_t nx = alive ? (tx1 - tx0 + 1u) : 0u, ny = alive ? (ty1 - ty0 + 1u) : 0u;
   const uint32_t nt = nx * ny;
-  const bool big = nt > 16u;
-  if(alive && !big)
+  const bool big = nx > 2u || ny > 2u;
+  const uint32_t lane = threadIdx.x & 31u;
+  if(__any_sync(0xffffffffu, alive && !big))
   {
-    for(uint32_t ty = ty0; ty <= ty1; ty++)
-      for(uint32_t tx = tx0; tx <= tx1; tx++)
+#pragma unroll
+    for(uint32_t q = 0; q < 4u; q++)
+    {
+      const uint32_t qx = q & 1u, qy = q >> 1;
+      uint32_t tile = 0xffffffffu;
+      if(alive && !big && qx < nx && qy < ny)
       {
-        const uint32_t tile = ty * tiles_x + tx;
-        if(tile_owned(tile, rank, world))
-          f(tile, tri);
+        tile = (ty0 + qy) * tiles_x + tx0 + qx;
+        if(!tile_owned(tile, rank, world))
+          tile = 0xffffffffu;
       }
+      const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+      if(tile != 0xffffffffu)
+        f(tile, tri, __popc(peers & ((1u << lane) - 1u)), __popc(peers), (uint32_t)(__ffs(peers) - 1) == lane, peers);
+    }
   }
   uint32_t mask = __ballot_sync(0xffffffffu, alive && big);
-  const uint32_t lane = threadIdx.x & 31u;
   while(mask)
   {
     const int src = __ffs(mask) - 1;
@@ -156,7 +168,7 @@ __device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32
     {
       const uint32_t tile = (b_ty0 + k / b_nx) * tiles_x + b_tx0 + k % b_nx;
       if(tile_owned(tile, rank, world))
-        f(tile, b_tri);
+        f(tile, b_tri, 0u, 1u, true, 0u);    // distinct tiles per lane: every lane is its own group
     }
   }
 }
@@ -243,14 +255,20 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     q[2] = make_int4(__float_as_int(su.invw2), __float_as_int(su.d0), __float_as_int(su.d1), __float_as_int(su.d2));
     q[3] = make_int4((int)su.s0, (int)su.s1, (int)su.s2, (int)(alive ? su.tiles : 0xffffffffu));
   }
+  if(t < p.num_tris)
+    p.tri_tiles[t] = alive ? su.tiles : 0xffffffffu;
   uint32_t *cnt = p.tile_count;
   for_each_tile(su.tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
-                [cnt](uint32_t tile, uint32_t) { atomicAdd(&cnt[tile], 1u); });
+                [cnt](uint32_t tile, uint32_t, uint32_t, uint32_t group, bool leader, uint32_t) {
+                  if(leader)
+                    atomicAdd(&cnt[tile], group);
+                });
 }
 
 // exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also resets the fill cursors
 __global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint32_t *tile_offset,
-                                              uint32_t *tile_cursor, uint32_t ntiles, uint32_t *total)
+                                              uint32_t *tile_cursor, uint32_t ntiles, uint32_t *total,
+                                              volatile unsigned long long *host_total, uint32_t seq)
 {
   __shared__ uint32_t warp_sums[32];
   const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
@@ -282,7 +300,15 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint3
     }
     warp_sums[lane] = wi - w;    // exclusive
     if(lane == 31u)
+    {
       *total = wi;
+      if(host_total)
+      {
+        // mapped pinned host word the host polls instead of synchronising the stream
+        *host_total = ((unsigned long long)seq << 32) | wi;
+        __threadfence_system();
+      }
+    }
   }
   __syncthreads();
   uint32_t run = warp_sums[warp] + incl - sum;
@@ -295,16 +321,26 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint3
 }
 
 __global__ void __launch_bounds__(kThreads) k_fill(const Vb200SetupParams p, const uint32_t *tile_offset,
-                                                  uint32_t *tile_cursor, uint32_t *list, uint32_t capacity)
+                                                  uint32_t *tile_cursor, uint32_t *list, uint32_t capacity,
+                                                  const uint32_t *total)
 {
+  // speculative launch: the host sized `list` before the pair total was known; if it does not fit,
+  // do nothing (the tile kernel does the same) and let the host retry with a larger list
+  if(*total > capacity)
+    return;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t tiles = 0xffffffffu;
   if(t < p.num_tris)
-    tiles = __ldg(&((const uint32_t *)(p.setup + t))[15]);
+    tiles = __ldg(p.tri_tiles + t);
   const bool alive = tiles != 0xffffffffu;
   for_each_tile(tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
-                [=](uint32_t tile, uint32_t tri) {
-                  const uint32_t pos = tile_offset[tile] + atomicAdd(&tile_cursor[tile], 1u);
+                [=](uint32_t tile, uint32_t tri, uint32_t rank, uint32_t group, bool leader, uint32_t peers) {
+                  uint32_t base = 0;
+                  if(leader)
+                    base = tile_offset[tile] + atomicAdd(&tile_cursor[tile], group);
+                  if(peers)
+                    base = __shfl_sync(peers, base, __ffs(peers) - 1);
+                  const uint32_t pos = base + rank;
                   if(pos < capacity)
                     list[pos] = tri;
                 });
@@ -357,9 +393,12 @@ __device__ void bitonic_sort(uint32_t *a, uint32_t n)
 constexpr uint32_t kSortSmem = 8192;    // entries (32 KB)
 
 __global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_t *tile_offset,
-                                                  const uint32_t *tile_count)
+                                                  const uint32_t *tile_count, const uint32_t *total,
+                                                  uint32_t capacity)
 {
   __shared__ uint32_t s[kSortSmem];
+  if(*total > capacity)
+    return;
   const uint32_t tile = blockIdx.x;
   const uint32_t n = tile_count[tile];
   if(n < 2u)
@@ -497,25 +536,26 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
 }
 
 int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
-                uint32_t *total, cudaStream_t s)
+                uint32_t *total, unsigned long long *host_total_dev, uint32_t seq, cudaStream_t s)
 {
-  k_scan<<<1, 1024, 0, s>>>(tile_count, tile_offset, tile_cursor, ntiles, total);
+  k_scan<<<1, 1024, 0, s>>>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total_dev, seq);
   return 1;
 }
 
 int launch_fill(const Vb200SetupParams &p, const uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t *list,
-                uint32_t capacity, cudaStream_t s)
+                uint32_t capacity, const uint32_t *total, cudaStream_t s)
 {
   if(!p.num_tris)
     return 0;
-  k_fill<<<(p.num_tris + kThreads - 1) / kThreads, kThreads, 0, s>>>(p, tile_offset, tile_cursor, list, capacity);
+  k_fill<<<(p.num_tris + kThreads - 1) / kThreads, kThreads, 0, s>>>(p, tile_offset, tile_cursor, list, capacity,
+                                                                      total);
   return 1;
 }
 
 int launch_sort(uint32_t *list, const uint32_t *tile_offset, const uint32_t *tile_count, uint32_t ntiles,
-                cudaStream_t s)
+                const uint32_t *total, uint32_t capacity, cudaStream_t s)
 {
-  k_sort<<<ntiles, kThreads, 0, s>>>(list, tile_offset, tile_count);
+  k_sort<<<ntiles, kThreads, 0, s>>>(list, tile_offset, tile_count, total, capacity);
   return 1;
 }
 

@@ -14,6 +14,7 @@ struct Vb200SetupParams
   uint32_t capacity;        // number of valid post-VS records
   const Vb200RasterVertex *rv;
   Vb200TriSetup *setup;
+  uint32_t *tri_tiles;    // packed tile range per triangle (0xffffffff = dead), read by the fill pass
   uint32_t *tile_count;
   Vb200DrawCounters *counters;
   uint32_t front_face, cull_mode;
@@ -37,6 +38,13 @@ struct Vb200TileParams
   const uint32_t *list;
   const uint32_t *tile_offset;
   const uint32_t *tile_count;
+  const uint32_t *total;      // (triangle, tile) pairs binned; > list_capacity = speculative launch must no-op
+  uint32_t list_capacity;
+  // pending ClearTarget()s folded into this launch: bit 0 colour, bit 1 depth. The kernel then takes the
+  // attachment's prior contents from these constants instead of loading them and writes EVERY pixel of
+  // every tile (including tiles no triangle touches), so no separate clear kernel runs.
+  uint32_t clear_flags, clear_color;
+  float clear_depth;
   uint32_t *color;
   float *depth;
   const float4 *interps;
@@ -53,11 +61,11 @@ int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint
                        cudaStream_t s);
 int launch_setup(const Vb200SetupParams &p, cudaStream_t s);
 int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
-                uint32_t *total, cudaStream_t s);
+                uint32_t *total, unsigned long long *host_total_dev, uint32_t seq, cudaStream_t s);
 int launch_fill(const Vb200SetupParams &p, const uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t *list,
-                uint32_t capacity, cudaStream_t s);
+                uint32_t capacity, const uint32_t *total, cudaStream_t s);
 int launch_sort(uint32_t *list, const uint32_t *tile_offset, const uint32_t *tile_count, uint32_t ntiles,
-                cudaStream_t s);
+                const uint32_t *total, uint32_t capacity, cudaStream_t s);
 int launch_sample(const Vb200Image &img, int cube, uint64_t byte_offset, const float *uvw, float4 *out,
                   size_t count, cudaStream_t s);
 int launch_tiles_pack(const uint32_t *color, uint32_t width, uint32_t height, uint32_t rank, uint32_t world,

@@ -120,17 +120,29 @@ struct Context
   DevBuf<Vb200RasterVertex> rv;
   DevBuf<float4> interps;
   DevBuf<Vb200TriSetup> setup;
-  DevBuf<uint32_t> tileCount, tileOffset, tileCursor, list;
+  DevBuf<uint32_t> tileCount, tileOffset, tileCursor, list, triTiles;
   uint32_t *range = nullptr;                // device {min,max}
   uint32_t *total = nullptr;                // device
-  uint32_t *totalHost = nullptr;            // pinned
+  volatile unsigned long long *totalHost = nullptr;    // mapped pinned: (draw seq << 32) | pair total
+  unsigned long long *totalHostDev = nullptr;          // its device address
+  uint32_t drawSeq = 0;
+  // ClearTarget()s not yet executed: device address of the attachment -> fill word and pixel count.
+  // The next draw into the attachment folds them into its tile kernel; anything else that touches the
+  // memory (another reader, a download) materialises them with the fill kernel first.
+  struct PendingClear
+  {
+    uint32_t value;
+    size_t count;
+  };
+  std::map<uint8_t *, PendingClear> pendingClears;
+  int64_t optFuseClears = 1;
   Vb200DrawCounters *counters = nullptr;    // device
   vb200_stats stats;
   uint32_t ownerRank = 0, ownerWorld = 1;
   int64_t optRasterPath = 0, optCountFragments = 0, optTimeKernels = 0;
   int stickyCuda = 0;
   cudaEvent_t userEvents[16] = {};
-  cudaEvent_t phaseEvents[8] = {};
+  cudaEvent_t phaseEvents[8] = {};    // 0..4 draw stages, 5..6 clears
   double phaseMs[VB200_PHASES] = {};
   uint64_t phaseCount[VB200_PHASES] = {};
 } g;
@@ -198,6 +210,8 @@ bool isDevicePointer(const void *p)
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+int materializeClears(const uint8_t *dev, size_t bytes);
+
 // ---- residency -------------------------------------------------------------------------------
 Mirror *findMirror(const void *host, size_t size)
 {
@@ -234,6 +248,8 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
   for(uintptr_t key : victims)
   {
     Mirror &old = g.mirrors[key];
+    if(int mrc = materializeClears(old.dev, old.size))    // deferred clears are keyed by the old address
+      return mrc;
     // keep device-side contents (attachments may hold results not yet downloaded)
     CU(cudaMemcpyAsync(nm.dev + ((uintptr_t)old.host - lo), old.dev, old.size, cudaMemcpyDeviceToDevice, g.stream));
     for(auto &w : old.written)
@@ -261,6 +277,30 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
   return VB200_OK;
 }
 
+int phaseMark(int i);
+void phaseAccumulate(int phase, int a, int b);
+
+// run the deferred clears that overlap [dev, dev+bytes)
+int materializeClears(const uint8_t *dev, size_t bytes)
+{
+  for(auto it = g.pendingClears.begin(); it != g.pendingClears.end();)
+  {
+    const uint8_t *lo = it->first, *hi = lo + it->second.count * 4;
+    if(lo < dev + bytes && dev < hi)
+    {
+      phaseMark(5);
+      g.stats.kernel_launches += vb200::launch_clear_u32((uint32_t *)it->first, it->second.value, it->second.count, g.stream);
+      phaseMark(6);
+      phaseAccumulate(VB200_PHASE_CLEAR, 5, 6);
+      it = g.pendingClears.erase(it);
+    }
+    else
+      ++it;
+  }
+  CU(cudaGetLastError());
+  return VB200_OK;
+}
+
 bool rangeCovered(const std::vector<std::pair<size_t, size_t>> &v, size_t off, size_t size)
 {
   for(auto &r : v)
@@ -271,9 +311,10 @@ bool rangeCovered(const std::vector<std::pair<size_t, size_t>> &v, size_t off, s
 
 enum Access
 {
-  ACC_READ = 1,       // kernel reads host-authored data: upload on first use per epoch (coherent mode)
-  ACC_WRITE = 2,      // kernel writes: download at flush (coherent mode)
-  ACC_OVERWRITE = 4,  // the whole range is overwritten first: no upload needed
+  ACC_READ = 1,           // kernel reads host-authored data: upload on first use per epoch (coherent mode)
+  ACC_WRITE = 2,          // kernel writes: download at flush (coherent mode)
+  ACC_OVERWRITE = 4,      // the whole range is overwritten first: no upload needed
+  ACC_KEEP_PENDING = 8,   // caller deals with deferred clears of the range itself
 };
 
 // host (or device) pointer -> device pointer usable by kernels
@@ -285,6 +326,8 @@ int resolve(const void *ptr, size_t size, int access, uint8_t **out)
   if(isDevicePointer(ptr))
   {
     *out = (uint8_t *)ptr;
+    if(!(access & ACC_KEEP_PENDING) && !g.pendingClears.empty())
+      return materializeClears(*out, size);
     return VB200_OK;
   }
   Mirror *m = findMirror(ptr, size);
@@ -309,6 +352,8 @@ int resolve(const void *ptr, size_t size, int access, uint8_t **out)
       m->written.push_back({off, size});
   }
   *out = m->dev + off;
+  if(!(access & ACC_KEEP_PENDING) && !g.pendingClears.empty())
+    return materializeClears(*out, size);
   return VB200_OK;
 }
 
@@ -534,7 +579,9 @@ int vb200_init(int device)
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CU(cudaMalloc((void **)&g.range, 2 * sizeof(uint32_t)));
   CU(cudaMalloc((void **)&g.total, sizeof(uint32_t)));
-  CU(cudaMallocHost((void **)&g.totalHost, sizeof(uint32_t)));
+  CU(cudaHostAlloc((void **)&g.totalHost, sizeof(unsigned long long), cudaHostAllocMapped));
+  *g.totalHost = 0;
+  CU(cudaHostGetDevicePointer((void **)&g.totalHostDev, (void *)g.totalHost, 0));
   CU(cudaMalloc((void **)&g.counters, sizeof(Vb200DrawCounters)));
   CU(cudaMemsetAsync(g.counters, 0, sizeof(Vb200DrawCounters), g.stream));
   memset(&g.stats, 0, sizeof(g.stats));
@@ -567,7 +614,8 @@ void vb200_shutdown(void)
   g.list.release();
   cudaFree(g.range);
   cudaFree(g.total);
-  cudaFreeHost(g.totalHost);
+  cudaFreeHost((void *)g.totalHost);
+  g.triTiles.release();
   cudaFree(g.counters);
   cudaStreamDestroy(g.stream);
   g.ready = false;
@@ -733,6 +781,9 @@ int vb200_mem_unregister(void *host)
     it = g.mirrors.find((uintptr_t)m->host);
   }
   cudaStreamSynchronize(g.stream);
+  for(auto pc = g.pendingClears.begin(); pc != g.pendingClears.end();)    // nobody will ever see them
+    pc = (pc->first >= it->second.dev && pc->first < it->second.dev + it->second.size) ? g.pendingClears.erase(pc)
+                                                                                         : std::next(pc);
   if(it->second.pinned)
     cudaHostUnregister(it->second.host);
   cudaFree(it->second.dev);
@@ -771,6 +822,8 @@ int vb200_mem_download(void *host, uint64_t size)
   if(!m)
     return setError(VB200_ERR_INVALID, "mem_download: range is not mirrored");
   const size_t off = (uintptr_t)host - (uintptr_t)m->host;
+  if((rc = materializeClears(m->dev + off, size)))
+    return rc;
   CU(cudaMemcpyAsync(host, m->dev + off, size, cudaMemcpyDeviceToHost, g.stream));
   g.stats.d2h_bytes += size;
   return VB200_OK;
@@ -823,6 +876,12 @@ int vb200_flush(void)
   int rc = requireReady();
   if(rc)
     return rc;
+  while(!g.pendingClears.empty())
+  {
+    auto it = g.pendingClears.begin();
+    if((rc = materializeClears(it->first, it->second.count * 4)))
+      return rc;
+  }
   if(g.syncMode == VB200_SYNC_COHERENT)
   {
     for(auto &kv : g.mirrors)
@@ -890,12 +949,11 @@ int vb200_clear_color(const vb200_image *target, const float rgba[4])
   uint8_t *dev;
   if(target->bytes_per_pixel == 4)
   {
-    if((rc = resolve(target->pixels, px * 4, ACC_OVERWRITE, &dev)))
+    if((rc = resolve(target->pixels, px * 4, ACC_OVERWRITE | ACC_KEEP_PENDING, &dev)))
       return rc;
-    phaseMark(0);
-    g.stats.kernel_launches += vb200::launch_clear_u32((uint32_t *)dev, b | (gch << 8) | (r << 16) | (a << 24), px, g.stream);
-    phaseMark(1);
-    phaseAccumulate(VB200_PHASE_CLEAR, 0, 1);
+    g.pendingClears[dev] = {b | (gch << 8) | (r << 16) | (a << 24), px};
+    if(!g.optFuseClears && (rc = materializeClears(dev, px * 4)))
+      return rc;
   }
   else if(target->bytes_per_pixel == 1)
   {
@@ -919,15 +977,13 @@ int vb200_clear_depth(const vb200_image *target, float depth)
     return setError(VB200_ERR_INVALID, "depth clear requires 4 bytes per pixel (assert rasterizer.cpp:321)");
   const size_t px = (size_t)target->width * target->height;
   uint8_t *dev;
-  if((rc = resolve(target->pixels, px * 4, ACC_OVERWRITE, &dev)))
+  if((rc = resolve(target->pixels, px * 4, ACC_OVERWRITE | ACC_KEEP_PENDING, &dev)))
     return rc;
   uint32_t bits;
   memcpy(&bits, &depth, 4);
-  phaseMark(0);
-  g.stats.kernel_launches += vb200::launch_clear_u32((uint32_t *)dev, bits, px, g.stream);
-  phaseMark(1);
-  phaseAccumulate(VB200_PHASE_CLEAR, 0, 1);
-  CU(cudaGetLastError());
+  g.pendingClears[dev] = {bits, px};
+  if(!g.optFuseClears && (rc = materializeClears(dev, px * 4)))
+    return rc;
   return VB200_OK;
 }
 
@@ -1064,8 +1120,12 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   const uint32_t W = s->color.width, H = s->color.height;
   const uint32_t tilesX = (W + VB200_TILE - 1) / VB200_TILE, tilesY = (H + VB200_TILE - 1) / VB200_TILE;
   const uint32_t ntiles = tilesX * tilesY;
+  // tile-list capacity is a guess (the pair total is only known on the device): 4 pairs per triangle
+  // covers every triangle smaller than a tile; kernels that find it too small do nothing and are rerun
+  const size_t listGuess = std::max<size_t>(g.list.cap, (size_t)numTris * 4 + 65536);
   if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * pipe->nslots) || !g.setup.reserve(numTris) ||
-     !g.tileCount.reserve(ntiles) || !g.tileOffset.reserve(ntiles) || !g.tileCursor.reserve(ntiles))
+     !g.triTiles.reserve(numTris) || !g.list.reserve(listGuess) || !g.tileCount.reserve(ntiles) ||
+     !g.tileOffset.reserve(ntiles) || !g.tileCursor.reserve(ntiles))
   {
     g.stickyCuda = 1;
     return setError(VB200_ERR_CUDA, "out of device memory for draw scratch");
@@ -1073,13 +1133,37 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
 
   // ---- targets
   uint8_t *colorDev, *depthDev = nullptr;
-  if((rc = resolve(s->color.pixels, (size_t)W * H * 4, ACC_READ | ACC_WRITE, &colorDev)))
+  if((rc = resolve(s->color.pixels, (size_t)W * H * 4, ACC_READ | ACC_WRITE | ACC_KEEP_PENDING, &colorDev)))
     return rc;
   const bool depthTest = hasDepth && pl->depth_compare_op != 7u;
   const bool depthWrite = hasDepth && pl->depth_write_enable;
   if(hasDepth && (depthTest || depthWrite))
-    if((rc = resolve(s->depth.pixels, (size_t)W * H * 4, ACC_READ | (depthWrite ? ACC_WRITE : 0), &depthDev)))
+    if((rc = resolve(s->depth.pixels, (size_t)W * H * 4, ACC_READ | ACC_WRITE | ACC_KEEP_PENDING, &depthDev)))
       return rc;
+  // deferred clears of exactly these attachments are folded into the tile kernel (single GPU only:
+  // with sort-first ownership a rank does not write every tile); anything else is materialised now
+  uint32_t clearFlags = 0, clearColorWord = 0;
+  float clearDepthValue = 0.0f;
+  {
+    auto take = [&](uint8_t *dev, uint32_t bit, uint32_t *word) {
+      auto it = g.pendingClears.find(dev);
+      if(it != g.pendingClears.end() && it->second.count == (size_t)W * H && g.ownerWorld == 1)
+      {
+        clearFlags |= bit;
+        *word = it->second.value;
+        g.pendingClears.erase(it);
+      }
+    };
+    uint32_t depthBits = 0;
+    take(colorDev, 1u, &clearColorWord);
+    if(depthDev)
+      take(depthDev, 2u, &depthBits);
+    memcpy(&clearDepthValue, &depthBits, 4);
+    if((rc = materializeClears(colorDev, (size_t)W * H * 4)))
+      return rc;
+    if(depthDev && (rc = materializeClears(depthDev, (size_t)W * H * 4)))
+      return rc;
+  }
 
   // ---- K1: vertex stage
   if(!indexed)
@@ -1114,6 +1198,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.capacity = capacity;
   sp.rv = g.rv.p;
   sp.setup = g.setup.p;
+  sp.tri_tiles = g.triTiles.p;
   sp.tile_count = g.tileCount.p;
   sp.counters = g.counters;
   sp.front_face = pl->front_face;
@@ -1126,22 +1211,6 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.owner_world = g.ownerWorld;
   CU(cudaMemsetAsync(g.tileCount.p, 0, ntiles * sizeof(uint32_t), g.stream));
   g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);
-
-  // ---- K3: scan -> (host reads the pair total to size the list) -> fill -> sort
-  phaseMark(2);
-  g.stats.kernel_launches += vb200::launch_scan(g.tileCount.p, g.tileOffset.p, g.tileCursor.p, ntiles, g.total, g.stream);
-  CU(cudaMemcpyAsync(g.totalHost, g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, g.stream));
-  CU(cudaStreamSynchronize(g.stream));
-  const uint32_t pairs = *g.totalHost;
-  g.stats.tile_pairs += pairs;
-  if(pairs == 0)
-    return VB200_OK;
-  if(!g.list.reserve(pairs))
-  {
-    g.stickyCuda = 1;
-    return setError(VB200_ERR_CUDA, "out of device memory for %u tile-list entries", pairs);
-  }
-  g.stats.kernel_launches += vb200::launch_fill(sp, g.tileOffset.p, g.tileCursor.p, g.list.p, pairs, g.stream);
 
   // Raster back end. A pass is order-independent ("resolvable") unless it blends or runs
   // NOT_EQUAL against a depth buffer it also writes; see scaffold.cu.
@@ -1166,17 +1235,13 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   }
   if(g.optRasterPath == 1)
     resolveMode = -1;
-  if(resolveMode < 0)    // ordered path needs each tile's list in submission order
-    g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileOffset.p, g.tileCount.p, ntiles, g.stream);
 
-  // ---- K4: tiles
-  phaseMark(3);
   Vb200TileParams tp;
   memset(&tp, 0, sizeof(tp));
   tp.setup = g.setup.p;
-  tp.list = g.list.p;
   tp.tile_offset = g.tileOffset.p;
   tp.tile_count = g.tileCount.p;
+  tp.total = g.total;
   tp.color = (uint32_t *)colorDev;
   tp.depth = (float *)depthDev;
   tp.interps = g.interps.p;
@@ -1197,12 +1262,68 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.rs.owner_world = g.ownerWorld;
   tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
   tp.rs.color_bpp = 4;
+  tp.clear_flags = clearFlags;
+  tp.clear_color = clearColorWord;
+  tp.clear_depth = clearDepthValue;
+
+  // ---- K3 + K4, launched speculatively: scan publishes the pair total to a mapped host word; fill,
+  // sort and the tile kernel are enqueued right behind it against the guessed list capacity and turn
+  // into no-ops if the total does not fit. The host polls the word while the GPU works; only on a
+  // miss (never for triangles smaller than a tile) the list is grown and the three are enqueued again.
+  phaseMark(2);
+  const uint32_t seq = ++g.drawSeq;
+  g.stats.kernel_launches += vb200::launch_scan(g.tileCount.p, g.tileOffset.p, g.tileCursor.p, ntiles, g.total,
+                                                g.totalHostDev, seq, g.stream);
+  uint32_t pairs = 0;
+  for(int attempt = 0; attempt < 2; attempt++)
   {
-    void *args[] = {&env, &tp};
-    cudaKernel_t k = resolveMode >= 0 ? pipe->k_tile_resolve[resolveMode] : pipe->k_tile_ordered;
-    if((rc = launchKernel(k, dim3(ntiles), dim3(256), args)))
-      return rc;
+    const uint32_t listCap = (uint32_t)std::min<size_t>(g.list.cap, 0xffffffffu);
+    tp.list = g.list.p;
+    tp.list_capacity = listCap;
+    g.stats.kernel_launches += vb200::launch_fill(sp, g.tileOffset.p, g.tileCursor.p, g.list.p, listCap, g.total, g.stream);
+    if(resolveMode < 0)    // ordered path needs each tile's list in submission order
+      g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileOffset.p, g.tileCount.p, ntiles, g.total, listCap,
+                                                    g.stream);
+    if(attempt == 0)
+      phaseMark(3);
+    {
+      void *args[] = {&env, &tp};
+      cudaKernel_t k = resolveMode >= 0 ? pipe->k_tile_resolve[resolveMode] : pipe->k_tile_ordered;
+      if((rc = launchKernel(k, dim3(ntiles), dim3(256), args)))
+        return rc;
+    }
+    if(attempt == 1)
+      break;
+    // wait for the scan's total (the GPU keeps running the kernels queued behind it)
+    for(uint64_t spins = 0;; spins++)
+    {
+      const unsigned long long v = *g.totalHost;
+      if((uint32_t)(v >> 32) == seq)
+      {
+        pairs = (uint32_t)v;
+        break;
+      }
+      if((spins & 0xfff) == 0xfff)
+      {
+        cudaError_t q = cudaStreamQuery(g.stream);
+        if(q != cudaSuccess && q != cudaErrorNotReady)
+          CU(q);
+        if(q == cudaSuccess && (uint32_t)(*g.totalHost >> 32) != seq)
+          return setError(VB200_ERR_CUDA, "binning total was never published");
+      }
+    }
+    if(pairs <= listCap)
+      break;
+    // guessed capacity too small: the speculative kernels did nothing; grow and go again
+    CU(cudaStreamSynchronize(g.stream));
+    if(!g.list.reserve((size_t)pairs + pairs / 4))
+    {
+      g.stickyCuda = 1;
+      return setError(VB200_ERR_CUDA, "out of device memory for %u tile-list entries", pairs);
+    }
+    CU(cudaMemsetAsync(g.tileCursor.p, 0, ntiles * sizeof(uint32_t), g.stream));
   }
+  g.stats.tile_pairs += pairs;
   phaseMark(4);
   phaseAccumulate(VB200_PHASE_VERTEX, 0, 1);
   phaseAccumulate(VB200_PHASE_SETUP, 1, 2);
@@ -1394,6 +1515,8 @@ int vb200_set_option(const char *name, int64_t value)
     g.optRasterPath = value;
   else if(!strcmp(name, "count_fragments"))
     g.optCountFragments = value;
+  else if(!strcmp(name, "fuse_clears"))
+    g.optFuseClears = value;
   else if(!strcmp(name, "time_kernels"))
   {
     g.optTimeKernels = value;

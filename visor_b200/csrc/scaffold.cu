@@ -169,8 +169,11 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   __shared__ TriSmem s_tri[VB200_BATCH];
 
   const uint32_t tile = blockIdx.x;
+  if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
+    return;
   const uint32_t n = p.tile_count[tile];
-  if(n == 0)
+  const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
+  if(n == 0 && !p.clear_flags)
     return;
   const uint32_t off = p.tile_offset[tile];
   const Vb200RasterState &rs = p.rs;
@@ -190,8 +193,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     const int y = ybase + 8 * j;
     const bool in = xin && y < (int)rs.height;
     const size_t idx = (size_t)y * rs.width + x;
-    col[j] = in ? p.color[idx] : 0u;
-    dep[j] = (in && rs.has_depth) ? p.depth[idx] : 0.0f;
+    col[j] = clearColor ? p.clear_color : (in ? p.color[idx] : 0u);
+    dep[j] = clearDepth ? p.clear_depth : ((in && rs.has_depth) ? p.depth[idx] : 0.0f);
   }
   uint32_t covered = 0, shaded = 0;
 
@@ -297,7 +300,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     {
       const size_t idx = (size_t)y * rs.width + x;
       p.color[idx] = col[j];
-      if(depthWrite)
+      if(depthWrite || (clearDepth && rs.has_depth))
         p.depth[idx] = dep[j];
     }
   }
@@ -372,14 +375,36 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __shared__ int4 s_coef[8][32][4];    // TriCoef records, one per lane of each warp
 
   const uint32_t tile = blockIdx.x;
-  const uint32_t n = p.tile_count[tile];
-  if(n == 0)
+  if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
     return;
-  const uint32_t off = p.tile_offset[tile];
+  const uint32_t n = p.tile_count[tile];
+  const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   const Vb200RasterState &rs = p.rs;
   const uint32_t tx = tile % rs.tiles_x, ty = tile / rs.tiles_x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tileX0 = (int)(tx * VB200_TILE), tileY0 = (int)(ty * VB200_TILE);
+  if(n == 0)
+  {
+    // no triangle touches this tile: it only has to receive the folded clears
+    if(p.clear_flags)
+    {
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+      {
+        const int x = tileX0 + lane, y = tileY0 + warp + 8 * j;
+        if(x < (int)rs.width && y < (int)rs.height)
+        {
+          const size_t gi = (size_t)y * rs.width + x;
+          if(clearColor)
+            p.color[gi] = p.clear_color;
+          if(clearDepth && rs.has_depth)
+            p.depth[gi] = p.clear_depth;
+        }
+      }
+    }
+    return;
+  }
+  const uint32_t off = p.tile_offset[tile];
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
 
@@ -392,7 +417,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const bool in = x < (int)rs.width && y < (int)rs.height;
     float e = 0.0f;
     if(MODE != VB200_RES_LAST_WINS || depthTest)
-      e = in ? p.depth[(size_t)y * rs.width + x] : 0.0f;
+      e = clearDepth ? p.clear_depth : (in ? p.depth[(size_t)y * rs.width + x] : 0.0f);
     vis[ly * VB200_TILE + lane] = vb200_existing_key<MODE>(e);
     if(MODE == VB200_RES_LAST_WINS)
       s_depth[ly * VB200_TILE + lane] = e;
@@ -538,8 +563,20 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       won = low != 0xffffffffu;
       id = ~low;
     }
-    if(!won || x >= (int)rs.width || y >= (int)rs.height)
+    if(x >= (int)rs.width || y >= (int)rs.height)
       continue;
+    if(!won)
+    {
+      if(p.clear_flags)
+      {
+        const size_t gi = (size_t)y * rs.width + x;
+        if(clearColor)
+          p.color[gi] = p.clear_color;
+        if(clearDepth && rs.has_depth)
+          p.depth[gi] = p.clear_depth;
+      }
+      continue;
+    }
     shaded++;
     const Vb200TriSetup su = vb200_load_setup(p.setup + (id - 1u));
     // recompute exactly what the reference computes for this pixel (rasterizer.cpp:303-309,545-558)
@@ -564,9 +601,11 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)su.s0 * rs.nslots,
                                 p.interps + (size_t)su.s1 * rs.nslots, p.interps + (size_t)su.s2 * rs.nslots);
     const size_t gi = (size_t)y * rs.width + x;
-    p.color[gi] = vb200_blend_store(rs, pix, p.color[gi]);
+    p.color[gi] = vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]);
     if(depthWrite)
       p.depth[gi] = pixdepth;
+    else if(clearDepth && rs.has_depth)
+      p.depth[gi] = p.clear_depth;
   }
   if(rs.count_fragments)
     vb200_count_fragments(p.counters, covered, shaded);
