@@ -21,7 +21,11 @@ for l in out.splitlines():
     m = re.search(r'/\*([0-9a-f]{4,})\*/\s+(.*?);', l)
     if m:
         addr2line[int(m.group(1), 16)] = (cur, m.group(2).strip())
-rows = list(csv.reader(open(csvp)))
+allrows = list(csv.reader(open(csvp)))
+# the export holds one block per profiled kernel: ["Kernel Name", name], header row, instruction rows
+starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+blocks = [(allrows[i][1], allrows[i:(starts[k + 1] if k + 1 < len(starts) else len(allrows))]) for k, i in enumerate(starts)]
+rows = [b for n, b in blocks if kern in n][-1]
 h = rows[1]
 ai, ie, si, ti = h.index('Address'), h.index('Instructions Executed'), h.index('# Samples'), h.index('Thread Instructions Executed')
 base, byline, tot, tots = None, {}, 0, 0

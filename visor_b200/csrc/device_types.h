@@ -67,7 +67,7 @@ struct Vb200TriSetup
   float invw0, invw1, invw2;
   float d0, d1, d2;
   uint32_t s0, s1, s2;               // post-VS record slot of each corner
-  uint32_t tiles;                    // minTx | minTy<<8 | maxTx<<16 | maxTy<<24 (inclusive); 0xffffffff = dead
+  float invarea;                     // 1.0f / float(|area2|) (rasterizer.cpp:448); undefined for dead triangles
 };
 #ifdef __cplusplus
 static_assert(sizeof(Vb200TriSetup) == 64, "setup record");

@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = t < p.num_tris;
   Vb200TriSetup su;
-  su.tiles = 0xffffffffu;
+  uint32_t tiles = 0xffffffffu;
+  su.invarea = 0.0f;
 
   if(alive)
   {
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
 
     // double_triarea (rasterizer.cpp:272-275), zero-area skip (:398), facing / cull (:401-424)
     const int area2 = (su.x1 - su.x0) * (su.y2 - su.y0) - (su.y1 - su.y0) * (su.x2 - su.x0);
+    su.invarea = __fdiv_rn(1.0f, (float)(area2 < 0 ? -area2 : area2));    // rasterizer.cpp:448
     int flipped = (p.front_face == 1u) ? -area2 : area2;
     if(area2 == 0)
       alive = false;
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     const int maxx = min((int)p.width - 1, max(su.x0, max(su.x1, su.x2)));
     const int maxy = min((int)p.height - 1, max(su.y0, max(su.y1, su.y2)));
     if(minx < maxx && miny < maxy)
-      su.tiles = (uint32_t)(minx / VB200_TILE) | ((uint32_t)(miny / VB200_TILE) << 8) |
+      tiles = (uint32_t)(minx / VB200_TILE) | ((uint32_t)(miny / VB200_TILE) << 8) |
                  ((uint32_t)((maxx - 1) / VB200_TILE) << 16) | ((uint32_t)((maxy - 1) / VB200_TILE) << 24);
     else
       alive = false;
@@ -253,12 +255,11 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     q[0] = make_int4(su.x0, su.y0, su.x1, su.y1);
     q[1] = make_int4(su.x2, su.y2, __float_as_int(su.invw0), __float_as_int(su.invw1));
     q[2] = make_int4(__float_as_int(su.invw2), __float_as_int(su.d0), __float_as_int(su.d1), __float_as_int(su.d2));
-    q[3] = make_int4((int)su.s0, (int)su.s1, (int)su.s2, (int)(alive ? su.tiles : 0xffffffffu));
+    q[3] = make_int4((int)su.s0, (int)su.s1, (int)su.s2, __float_as_int(su.invarea));
+    p.tri_tiles[t] = alive ? tiles : 0xffffffffu;
   }
-  if(t < p.num_tris)
-    p.tri_tiles[t] = alive ? su.tiles : 0xffffffffu;
   uint32_t *cnt = p.tile_count;
-  for_each_tile(su.tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
+  for_each_tile(tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
                 [cnt](uint32_t tile, uint32_t, uint32_t, uint32_t group, bool leader, uint32_t) {
                   if(leader)
                     atomicAdd(&cnt[tile], group);

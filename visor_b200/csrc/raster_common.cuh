@@ -30,7 +30,7 @@ __device__ __forceinline__ Vb200TriSetup vb200_load_setup(const Vb200TriSetup *s
   r.x0 = a.x; r.y0 = a.y; r.x1 = a.z; r.y1 = a.w;
   r.x2 = b.x; r.y2 = b.y; r.invw0 = __int_as_float(b.z); r.invw1 = __int_as_float(b.w);
   r.invw2 = __int_as_float(c.x); r.d0 = __int_as_float(c.y); r.d1 = __int_as_float(c.z); r.d2 = __int_as_float(c.w);
-  r.s0 = (uint32_t)d.x; r.s1 = (uint32_t)d.y; r.s2 = (uint32_t)d.z; r.tiles = (uint32_t)d.w;
+  r.s0 = (uint32_t)d.x; r.s1 = (uint32_t)d.y; r.s2 = (uint32_t)d.z; r.invarea = __int_as_float(d.w);
   return r;
 }
 
@@ -85,9 +85,11 @@ __device__ __forceinline__ uint32_t vb200_blend_store(const Vb200RasterState &rs
       pix.z = __fadd_rn(__fmul_rn(srcF, pix.z), __fmul_rn(dstF, ez));
     }
   }
-  const uint32_t r = (uint32_t)__float2int_rz(__fmul_rn(vb200_clamp01(pix.x), 255.0f)) & 0xffu;
-  const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(vb200_clamp01(pix.y), 255.0f)) & 0xffu;
-  const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(vb200_clamp01(pix.z), 255.0f)) & 0xffu;
+  // byte(clamp01(c) * 255.0f): __saturatef clamps to [0,1] in one instruction; it maps NaN to 0 where
+  // clamp01 keeps NaN, but byte(NaN * 255) is 0 on the reference's x86 too, so the stored byte is equal
+  const uint32_t r = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.x), 255.0f));
+  const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.y), 255.0f));
+  const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.z), 255.0f));
   return (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
 }
 

@@ -1369,7 +1369,8 @@ int vb200_sample(const vb200_image *tex, int cube, uint64_t byte_offset, const f
   CU(cudaStreamSynchronize(g.stream));
   cudaFree(din);
   cudaFree(dout);
-  return VB200_OK;
+  // synchronous call: it is its own "submit", so host memory becomes authoritative again afterwards
+  return vb200_flush();
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------------

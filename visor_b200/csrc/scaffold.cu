@@ -225,7 +225,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
       s.miny = max(0, min(su.y0, min(su.y1, su.y2)));
       s.maxx = min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2)));
       s.maxy = min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2)));
-      s.invarea = __fdiv_rn(1.0f, (float)s.area);
+      s.invarea = su.invarea;
       s.invw0 = su.invw0;
       s.invw1 = su.invw1;
       s.invw2 = su.invw2;
@@ -336,20 +336,23 @@ enum
 };
 
 // Per-triangle raster record staged in shared memory (64 B, one per lane of the warp that loaded it).
+// A candidate pixel is addressed by its index li inside the triangle's tile-clipped bbox (row-major,
+// width w): yq = li / w. With everything re-based to that index,
+//   b1 = A1*li + D1*yq + E1,  b2 = A2*li + D2*yq + E2,  b0 = |area2| - (b1 + b2)
+//   tile pixel index = base + li + yq*(32 - w)
+// so phase A never reconstructs x or y. (Same int32 ring arithmetic as rasterizer.cpp:303-309.)
 struct TriCoef
 {
-  int A1, B1, C1, A2;              // b1 = A1*x + B1*y + C1, b2 = A2*x + B2*y + C2 (barymul folded in)
-  int B2, C2, area, xy0;           // |area2|; bbox origin clipped to the tile: x0 | y0 << 16
+  int A1, D1, E1, A2;
+  int D2, E2, area, base;          // base = (y0 - tileY0)*32 + (x0 - tileX0)
   float invarea, d0, d1, d2;
-  uint32_t id, excl, w, magic;     // triangle index + 1; first slot in the pixel stream; bbox width; ceil(2^16/w)
+  uint32_t id, excl, skip, magic;  // triangle index + 1; first slot in the pixel stream; 32 - w; floor(2^16/w) + 1
 };
 
 // float -> uint32 whose unsigned order equals the float order (-0 == +0); callers exclude NaN
 __device__ __forceinline__ uint32_t vb200_depth_key(float d)
 {
-  uint32_t b = __float_as_uint(d);
-  if((b << 1) == 0u)
-    b = 0u;
+  const uint32_t b = __float_as_uint(__fadd_rn(d, 0.0f));    // -0 + 0 = +0; every other value unchanged
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
@@ -439,7 +442,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   {
     const uint32_t i = base + lane;
     uint32_t cnt = 0;
-    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = make_int4(0, 0, 1, 65536);
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = make_int4(0, 0, 0, 65537);
     if(i < n && (uint32_t)lane < chunk)
     {
       const uint32_t t = p.list[off + i];
@@ -453,12 +456,15 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       const int y1 = min(min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2))), tileY0 + VB200_TILE);
       const int w = max(x1 - x0, 1), h = max(y1 - y0, 0);
       cnt = (x1 > x0) ? (uint32_t)(w * h) : 0u;
-      r0 = make_int4(sgn * ACy, -sgn * ACx, sgn * (ACx * su.y0 - ACy * su.x0), -sgn * ABy);
-      r1 = make_int4(sgn * ABx, sgn * (ABy * su.x0 - ABx * su.y0), sgn * area2, x0 | (y0 << 16));
-      r2 = make_int4(__float_as_int(__fdiv_rn(1.0f, (float)(sgn * area2))), __float_as_int(su.d0),
-                     __float_as_int(su.d1), __float_as_int(su.d2));
-      // floor(i / w) == (i * magic) >> 16 for i < 1024, w <= 32
-      r3 = make_int4((int)(t + 1u), 0, w, (int)(65535u / (uint32_t)w + 1u));
+      const int A1 = sgn * ACy, B1 = -sgn * ACx, C1 = sgn * (ACx * su.y0 - ACy * su.x0);
+      const int A2 = -sgn * ABy, B2 = sgn * ABx, C2 = sgn * (ABy * su.x0 - ABx * su.y0);
+      r0 = make_int4(A1, B1 - A1 * w, C1 + A1 * x0 + B1 * y0, A2);
+      r1 = make_int4(B2 - A2 * w, C2 + A2 * x0 + B2 * y0, sgn * area2, (y0 - tileY0) * VB200_TILE + (x0 - tileX0));
+      r2 = make_int4(__float_as_int(su.invarea), __float_as_int(su.d0), __float_as_int(su.d1), __float_as_int(su.d2));
+      // floor(li / w) == (li * magic) >> 16 for li < 1024, w <= 32 with magic = floor(65536 / w) + 1
+      // (65536/w is either an integer or at least 1/32 away from one: far more than the 2-ulp error
+      // of the fast division)
+      r3 = make_int4((int)(t + 1u), 0, VB200_TILE - w, (int)(__float2uint_rz(__fdividef(65536.0f, (float)w)) + 1u));
     }
     uint32_t incl = cnt;
 #pragma unroll
@@ -491,17 +497,15 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       // lanes with an empty bbox cannot occur between valid ones (see above), so rank == lane index
       const uint32_t owner = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u;
       const int4 c0 = wc[owner][0], c1 = wc[owner][1], c3 = wc[owner][3];
-      const uint32_t li = g - (uint32_t)c3.y;
-      const uint32_t yq = (li * (uint32_t)c3.w) >> 16;
-      const uint32_t xq = li - yq * (uint32_t)c3.z;
-      const int x = (c1.w & 0xffff) + (int)xq, y = (c1.w >> 16) + (int)yq;
-      const int b1 = c0.x * x + c0.y * y + c0.z;
-      const int b2 = c0.w * x + c1.x * y + c1.y;
+      const int li = (int)(g - (uint32_t)c3.y);
+      const int yq = (int)(((uint32_t)li * (uint32_t)c3.w) >> 16);
+      const int b1 = c0.x * li + c0.y * yq + c0.z;
+      const int b2 = c0.w * li + c1.x * yq + c1.y;
       const int b0 = c1.z - (b1 + b2);
       if((b0 | b1 | b2) < 0)
         continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
       covered++;
-      const int idx = (y - tileY0) * VB200_TILE + (x - tileX0);
+      const int idx = c1.w + li + yq * c3.z;
       const uint32_t id = (uint32_t)c3.x;
       unsigned long long key;
       if(MODE == VB200_RES_LAST_WINS && !depthTest)
@@ -586,10 +590,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const int PAx = su.x0 - x, PAy = su.y0 - y;
     const int ux = ACx * PAy - ACy * PAx, uy = PAx * ABy - PAy * ABx;
     const int b0 = (area2 - (ux + uy)) * sgn, b1 = ux * sgn, b2 = uy * sgn;
-    const float invarea = __fdiv_rn(1.0f, (float)(sgn * area2));
-    float n0 = __fmul_rn((float)b0, invarea);
-    float n1 = __fmul_rn((float)b1, invarea);
-    float n2 = __fmul_rn((float)b2, invarea);
+    float n0 = __fmul_rn((float)b0, su.invarea);
+    float n1 = __fmul_rn((float)b1, su.invarea);
+    float n2 = __fmul_rn((float)b2, su.invarea);
     const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, su.d0), __fmul_rn(n1, su.d1)), __fmul_rn(n2, su.d2));
     n0 = __fmul_rn(n0, su.invw0);
     n1 = __fmul_rn(n1, su.invw1);
