@@ -10,6 +10,8 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point
 // returns VB200_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#define NVJITLINK_NO_INLINE    // types/enums only: the library is bound at run time (see NvJitLinkApi)
 #include <nvJitLink.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -358,9 +360,85 @@ int resolve(const void *ptr, size_t size, int access, uint8_t **out)
 }
 
 // ---- JIT -------------------------------------------------------------------------------------
+// nvJitLink is bound with dlopen/dlsym instead of a link-time dependency: a host process may already
+// have mapped ANOTHER libnvJitLink.so.12 (PyTorch wheels bundle the 12.8 one), whose versioned symbols
+// (__nvJitLinkCreate_12_8) would shadow the 12.9 ones this library was built against and cannot link
+// cubins produced by nvcc 12.9. Opening the toolkit's copy by absolute path gives a private instance.
+struct NvJitLinkApi
+{
+  void *lib = nullptr;
+  nvJitLinkResult (*create)(nvJitLinkHandle *, uint32_t, const char **) = nullptr;
+  nvJitLinkResult (*destroy)(nvJitLinkHandle *) = nullptr;
+  nvJitLinkResult (*addData)(nvJitLinkHandle, nvJitLinkInputType, const void *, size_t, const char *) = nullptr;
+  nvJitLinkResult (*complete)(nvJitLinkHandle) = nullptr;
+  nvJitLinkResult (*getCubinSize)(nvJitLinkHandle, size_t *) = nullptr;
+  nvJitLinkResult (*getCubin)(nvJitLinkHandle, void *) = nullptr;
+  nvJitLinkResult (*getLogSize)(nvJitLinkHandle, size_t *) = nullptr;
+  nvJitLinkResult (*getLog)(nvJitLinkHandle, char *) = nullptr;
+  std::string path;
+} nvj;
+
+bool loadNvJitLink()
+{
+  if(nvj.create)
+    return true;
+  std::vector<std::string> candidates;
+  if(const char *e = getenv("VB200_NVJITLINK"))
+    candidates.push_back(e);
+  if(const char *e = getenv("CUDA_HOME"))
+    candidates.push_back(std::string(e) + "/lib64/libnvJitLink.so.12");
+  candidates.push_back("/usr/local/cuda/lib64/libnvJitLink.so.12");
+  candidates.push_back("/usr/local/cuda-12.9/lib64/libnvJitLink.so.12");
+  candidates.push_back("libnvJitLink.so.12");
+  for(const std::string &c : candidates)
+  {
+    void *lib = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if(!lib)
+      continue;
+    auto sym = [&](const char *base) -> void * {
+      // newest first: the cubins this library embeds come from nvcc 12.9
+      for(const char *suffix : {"_12_9", "_12_8", "_12_6", "_12_4", "_12_0", ""})
+      {
+        std::string n = suffix[0] ? std::string("__") + base + suffix : std::string(base);
+        if(void *p = dlsym(lib, n.c_str()))
+          return p;
+      }
+      return nullptr;
+    };
+    NvJitLinkApi a;
+    a.lib = lib;
+    a.create = (decltype(a.create))sym("nvJitLinkCreate");
+    a.destroy = (decltype(a.destroy))sym("nvJitLinkDestroy");
+    a.addData = (decltype(a.addData))sym("nvJitLinkAddData");
+    a.complete = (decltype(a.complete))sym("nvJitLinkComplete");
+    a.getCubinSize = (decltype(a.getCubinSize))sym("nvJitLinkGetLinkedCubinSize");
+    a.getCubin = (decltype(a.getCubin))sym("nvJitLinkGetLinkedCubin");
+    a.getLogSize = (decltype(a.getLogSize))sym("nvJitLinkGetErrorLogSize");
+    a.getLog = (decltype(a.getLog))sym("nvJitLinkGetErrorLog");
+    if(a.create && a.destroy && a.addData && a.complete && a.getCubinSize && a.getCubin && a.getLogSize && a.getLog)
+    {
+      a.path = c;
+      nvj = a;
+      return true;
+    }
+    dlclose(lib);
+  }
+  return false;
+}
+
 // nvJitLink step: scaffold cubin + VS PTX + FS PTX -> one sm_100a cubin. Needs no device.
 int linkCubin(const vb200_entry *vs, const vb200_entry *fs, std::vector<char> &cubin)
 {
+  if(!loadNvJitLink())
+    return setError(VB200_ERR_LINK, "libnvJitLink.so.12 (CUDA 12.9) not found; set VB200_NVJITLINK to its path");
+  auto nvJitLinkCreate = nvj.create;
+  auto nvJitLinkDestroy = nvj.destroy;
+  auto nvJitLinkAddData = nvj.addData;
+  auto nvJitLinkComplete = nvj.complete;
+  auto nvJitLinkGetLinkedCubinSize = nvj.getCubinSize;
+  auto nvJitLinkGetLinkedCubin = nvj.getCubin;
+  auto nvJitLinkGetErrorLogSize = nvj.getLogSize;
+  auto nvJitLinkGetErrorLog = nvj.getLog;
   nvJitLinkHandle h;
   const char *opts[] = {"-arch=sm_100a", "-lineinfo"};
   if(nvJitLinkCreate(&h, 2, opts) != NVJITLINK_SUCCESS)
