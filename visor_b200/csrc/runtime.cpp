@@ -117,6 +117,7 @@ struct Context
   int syncMode = VB200_SYNC_COHERENT;
   uint64_t epoch = 1;
   std::map<uintptr_t, Mirror> mirrors;
+  std::vector<uint8_t *> zombies;    // device memory of merged mirrors, freed at the next flush
   std::map<std::pair<uint64_t, uint64_t>, Pipeline> pipelines;
   // scratch
   DevBuf<Vb200RasterVertex> rv;
@@ -260,8 +261,9 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
       nm.uploaded.push_back({u.first + ((uintptr_t)old.host - lo), u.second});
     if(old.pinned)
       cudaHostUnregister(old.host);
-    CU(cudaStreamSynchronize(g.stream));
-    cudaFree(old.dev);
+    // Launches already enqueued (and the draw being assembled right now) may hold device addresses
+    // inside the old mirror: it stays allocated until the next flush has drained the stream.
+    g.zombies.push_back(old.dev);
     nm.explicitReg |= old.explicitReg;
     g.mirrors.erase(key);
   }
@@ -979,6 +981,9 @@ int vb200_flush(void)
     g.stickyCuda = 1;
     return setError(VB200_ERR_CUDA, "asynchronous CUDA error: %s", cudaGetErrorString(e));
   }
+  for(uint8_t *z : g.zombies)
+    cudaFree(z);
+  g.zombies.clear();
   // new epoch: host memory is authoritative again
   size_t autoBytes = 0;
   for(auto &kv : g.mirrors)

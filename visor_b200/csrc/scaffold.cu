@@ -149,7 +149,13 @@ extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_co
 // K4 (ordered): one CTA per 32x32 screen tile, 256 threads, 4 pixels per thread held in registers.
 // The tile's triangle list is streamed through shared memory in draw order, so every pixel sees its
 // fragments in submission order — exact for blending, depth ties, EQUAL/NOT_EQUAL, test-without-write.
-// Colour and depth are read once and written back once, as full 128-byte rows per warp.
+// Colour and depth are read once and written back once.
+//
+// Pixel ownership: warp w covers the 16x8 region at ((w&1)*16, (w>>1)*8) of the tile; lane l owns column
+// l&15 of rows (l>>4) + 2j, j = 0..3, so pass j of the fragment loop works on one 16x2 row pair with
+// all 32 lanes. A compact region per warp makes the warp-uniform bbox reject effective, and a row-pair
+// pass keeps most lanes busy when a primitive overlaps it (a 9-pixel-wide particle fills 18 of the 32
+// lanes of a 16x2 pass, but only 9 lanes of a 32x1 row and ~5 of a pass over scattered 2x2 quads).
 // ------------------------------------------------------------------------------------------------
 #define VB200_BATCH 64
 
@@ -163,10 +169,19 @@ struct TriSmem
   uint32_t s0, s1, s2, pad2;
 };
 
+// blend factor (rasterizer.cpp:601-653) as selects on the uniform factor enum
+__device__ __forceinline__ float vb200_factor_sel(uint32_t f, float alpha, float oneMinusAlpha)
+{
+  return f == 6u ? alpha : (f == 7u ? oneMinusAlpha : (f == 0u ? 0.0f : 1.0f));
+}
+
+// (no min-blocks hint: the linked fragment function's register count is shader dependent and nvJitLink
+// rejects a callee that needs more registers than the kernel's cap)
 extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __grid_constant__ Vb200Env env,
                                                                      const __grid_constant__ Vb200TileParams p)
 {
   __shared__ TriSmem s_tri[VB200_BATCH];
+  __shared__ float s_unorm[256];    // float(byte) / 255.0f, the reference's destination read (rasterizer.cpp:595-599)
 
   const uint32_t tile = blockIdx.x;
   if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
@@ -179,19 +194,21 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   const Vb200RasterState &rs = p.rs;
   const uint32_t tx = tile % rs.tiles_x, ty = tile / rs.tiles_x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x = (int)(tx * VB200_TILE) + lane;
-  const int ybase = (int)(ty * VB200_TILE) + warp;
-  const bool xin = x < (int)rs.width;
+  const int rx0 = (int)(tx * VB200_TILE) + (warp & 1) * 16, ry0 = (int)(ty * VB200_TILE) + (warp >> 1) * 8;
+  const int x0 = rx0 + (lane & 15), y0 = ry0 + (lane >> 4);    // pixel j of this thread: (x0, y0 + 2j)
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
+  const bool blend = rs.blend_enable != 0u && rs.blend_op == 0u;    // only ADD is defined (rasterizer.cpp:657-669)
+
+  s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
 
   uint32_t col[4];
   float dep[4];
 #pragma unroll
   for(int j = 0; j < 4; j++)
   {
-    const int y = ybase + 8 * j;
-    const bool in = xin && y < (int)rs.height;
+    const int x = x0, y = y0 + 2 * j;
+    const bool in = x < (int)rs.width && y < (int)rs.height;
     const size_t idx = (size_t)y * rs.width + x;
     col[j] = clearColor ? p.clear_color : (in ? p.color[idx] : 0u);
     dep[j] = clearDepth ? p.clear_depth : ((in && rs.has_depth) ? p.depth[idx] : 0.0f);
@@ -245,35 +262,41 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     for(uint32_t k = 0; k < cnt; k++)
     {
       const TriSmem &t = s_tri[k];
-      // warp-uniform reject on rows, per-lane reject on columns
-      if(ybase + 24 < t.miny || ybase >= t.maxy)
+      // warp-uniform reject: bbox against this warp's 16x8 region
+      if(t.maxx <= rx0 || t.minx >= rx0 + 16 || t.maxy <= ry0 || t.miny >= ry0 + 8)
         continue;
-      if(x < t.minx || x >= t.maxx)
-        continue;
-      const int e1 = t.A1 * x + t.C1, e2 = t.A2 * x + t.C2;
+      // coverage of the thread's four pixels first (cheap, integer), fragment work only where needed
+      const int e1 = t.A1 * x0 + t.B1 * y0 + t.C1, e2 = t.A2 * x0 + t.B2 * y0 + t.C2;
+      uint32_t mask = 0;
+      const bool xin = x0 >= t.minx && x0 < t.maxx;
 #pragma unroll
       for(int j = 0; j < 4; j++)
       {
-        const int y = ybase + 8 * j;
-        if(y < t.miny || y >= t.maxy)
-          continue;
-        const int b1 = e1 + t.B1 * y;
-        const int b2 = e2 + t.B2 * y;
+        const int y = y0 + 2 * j;
+        const int b1 = e1 + 2 * j * t.B1, b2 = e2 + 2 * j * t.B2;
         const int b0 = t.area - (b1 + b2);
-        if((b0 | b1 | b2) < 0)
-          continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
-        covered++;
-
+        const bool inside = ((b0 | b1 | b2) >= 0) && xin && y >= t.miny && y < t.maxy;
+        mask |= inside ? (1u << j) : 0u;    // covered iff all three >= 0 (rasterizer.cpp:549)
+      }
+      if(!__any_sync(0xffffffffu, mask != 0u))
+        continue;
+      covered += __popc(mask);
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+      {
+        if(!__any_sync(0xffffffffu, (mask >> j) & 1u))    // nothing of this row pair is covered
+          continue;
+        if(!(mask & (1u << j)))
+          continue;
+        const int b1 = e1 + 2 * j * t.B1, b2 = e2 + 2 * j * t.B2, b0 = t.area - (b1 + b2);
         // rasterizer.cpp:552-558
         float n0 = __fmul_rn((float)b0, t.invarea);
         float n1 = __fmul_rn((float)b1, t.invarea);
         float n2 = __fmul_rn((float)b2, t.invarea);
         const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, t.d0), __fmul_rn(n1, t.d1)), __fmul_rn(n2, t.d2));
-
         if(depthTest && !vb200_depth_pass(rs.depth_op, pixdepth, dep[j]))
           continue;
         shaded++;
-
         // perspective correction (rasterizer.cpp:581-588)
         n0 = __fmul_rn(n0, t.invw0);
         n1 = __fmul_rn(n1, t.invw1);
@@ -285,7 +308,23 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
 
         float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)t.s0 * rs.nslots,
                               p.interps + (size_t)t.s1 * rs.nslots, p.interps + (size_t)t.s2 * rs.nslots);
-        col[j] = vb200_blend_store(rs, pix, col[j]);
+        const uint32_t cur = col[j];
+        if(blend)
+        {
+          // blend (rasterizer.cpp:593-672): existing = bytes (2,1,0) / 255.0f from the exact table
+          const float ex = s_unorm[(cur >> 16) & 0xffu], ey = s_unorm[(cur >> 8) & 0xffu], ez = s_unorm[cur & 0xffu];
+          const float oma = __fsub_rn(1.0f, pix.w);
+          const float srcF = vb200_factor_sel(rs.src_factor, pix.w, oma);
+          const float dstF = vb200_factor_sel(rs.dst_factor, pix.w, oma);
+          pix.x = __fadd_rn(__fmul_rn(srcF, pix.x), __fmul_rn(dstF, ex));
+          pix.y = __fadd_rn(__fmul_rn(srcF, pix.y), __fmul_rn(dstF, ey));
+          pix.z = __fadd_rn(__fmul_rn(srcF, pix.z), __fmul_rn(dstF, ez));
+        }
+        // truncating BGR store, alpha byte untouched (rasterizer.cpp:674-676)
+        const uint32_t r = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.x), 255.0f));
+        const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.y), 255.0f));
+        const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.z), 255.0f));
+        col[j] = (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
         if(depthWrite)
           dep[j] = pixdepth;
       }
@@ -295,8 +334,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
 #pragma unroll
   for(int j = 0; j < 4; j++)
   {
-    const int y = ybase + 8 * j;
-    if(xin && y < (int)rs.height)
+    const int x = x0, y = y0 + 2 * j;
+    if(x < (int)rs.width && y < (int)rs.height)
     {
       const size_t idx = (size_t)y * rs.width + x;
       p.color[idx] = col[j];
