@@ -146,27 +146,29 @@ extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4 (ordered): one CTA per 32x32 screen tile, 256 threads, 4 pixels per thread held in registers.
-// The tile's triangle list is streamed through shared memory in draw order, so every pixel sees its
-// fragments in submission order — exact for blending, depth ties, EQUAL/NOT_EQUAL, test-without-write.
-// Colour and depth are read once and written back once.
+// K4 (ordered): one CTA per 32x32 screen tile; exact for ANY state because every pixel sees its
+// fragments in submission order (blending, depth ties, EQUAL/NOT_EQUAL, test-without-write).
 //
-// Pixel ownership: warp w covers the 16x8 region at ((w&1)*16, (w>>1)*8) of the tile; lane l owns column
-// l&15 of rows (l>>4) + 2j, j = 0..3, so pass j of the fragment loop works on one 16x2 row pair with
-// all 32 lanes. A compact region per warp makes the warp-uniform bbox reject effective, and a row-pair
-// pass keeps most lanes busy when a primitive overlaps it (a 9-pixel-wide particle fills 18 of the 32
-// lanes of a 16x2 pass, but only 9 lanes of a 32x1 row and ~5 of a pass over scattered 2x2 quads).
+// Warp-autonomous: warp w owns the 16x8 pixel region at ((w&1)*16, (w>>1)*8) of the tile and walks the
+// tile's (sorted) triangle list by itself — no CTA barrier inside the loop, so a warp whose region is
+// busy never stalls the others.
+//   1. 32 triangles at a time: each lane loads one setup record, derives the edge coefficients and tests
+//      the bbox against the warp's region; a ballot leaves only the triangles that touch the region.
+//   2. per surviving triangle, in list order: every lane tests its 4 pixels (integer edge functions),
+//      the covered pixels of the whole region are ranked with ballots + popc and their indices are
+//      compacted into a per-warp queue;
+//   3. the queue is consumed 32 fragments per pass, all lanes busy: depth test, perspective, the PTX
+//      fragment function, blend, truncating BGR pack. Colour/depth of the region live in shared memory
+//      so any lane can shade any pixel; they are read from HBM once and written back once.
 // ------------------------------------------------------------------------------------------------
-#define VB200_BATCH 64
-
-struct TriSmem
+struct TriSmem    // 80 B
 {
   int A1, B1, C1, A2;
-  int B2, C2, area, minx;
-  int miny, maxx, maxy, pad;
+  int B2, C2, area, box;    // box: bbox clipped to the region, region-relative: x0 | x1<<8 | y0<<16 | y1<<24 (half open)
   float invarea, invw0, invw1, invw2;
-  float d0, d1, d2, padf;
-  uint32_t s0, s1, s2, pad2;
+  float d0, d1, d2;
+  uint32_t s0;
+  uint32_t s1, s2, pad0, pad1;
 };
 
 // blend factor (rasterizer.cpp:601-653) as selects on the uniform factor enum
@@ -180,7 +182,10 @@ __device__ __forceinline__ float vb200_factor_sel(uint32_t f, float alpha, float
 extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __grid_constant__ Vb200Env env,
                                                                      const __grid_constant__ Vb200TileParams p)
 {
-  __shared__ TriSmem s_tri[VB200_BATCH];
+  __shared__ __align__(16) TriSmem s_tri[8][32];
+  __shared__ uint32_t s_col[8][128];
+  __shared__ float s_dep[8][128];
+  __shared__ uint8_t s_queue[8][128];
   __shared__ float s_unorm[256];    // float(byte) / 255.0f, the reference's destination read (rasterizer.cpp:595-599)
 
   const uint32_t tile = blockIdx.x;
@@ -195,106 +200,122 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   const uint32_t tx = tile % rs.tiles_x, ty = tile / rs.tiles_x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rx0 = (int)(tx * VB200_TILE) + (warp & 1) * 16, ry0 = (int)(ty * VB200_TILE) + (warp >> 1) * 8;
-  const int x0 = rx0 + (lane & 15), y0 = ry0 + (lane >> 4);    // pixel j of this thread: (x0, y0 + 2j)
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
   const bool blend = rs.blend_enable != 0u && rs.blend_op == 0u;    // only ADD is defined (rasterizer.cpp:657-669)
 
   s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  uint32_t *wcol = s_col[warp];
+  float *wdep = s_dep[warp];
+  uint8_t *wq = s_queue[warp];
+  TriSmem *wtri = s_tri[warp];
 
-  uint32_t col[4];
-  float dep[4];
+  // region pixel i (0..127): x = rx0 + (i & 15), y = ry0 + (i >> 4); lane l loads/tests pixels l + 32j
 #pragma unroll
   for(int j = 0; j < 4; j++)
   {
-    const int x = x0, y = y0 + 2 * j;
+    const int i = lane + 32 * j;
+    const int x = rx0 + (i & 15), y = ry0 + (i >> 4);
     const bool in = x < (int)rs.width && y < (int)rs.height;
     const size_t idx = (size_t)y * rs.width + x;
-    col[j] = clearColor ? p.clear_color : (in ? p.color[idx] : 0u);
-    dep[j] = clearDepth ? p.clear_depth : ((in && rs.has_depth) ? p.depth[idx] : 0.0f);
+    wcol[i] = clearColor ? p.clear_color : (in ? p.color[idx] : 0u);
+    wdep[i] = clearDepth ? p.clear_depth : ((in && rs.has_depth) ? p.depth[idx] : 0.0f);
   }
+  __syncthreads();    // s_unorm is shared by all warps; after this the warps run independently
   uint32_t covered = 0, shaded = 0;
+  const int lx = lane & 15, ly = lane >> 4;    // lane's pixel column / first row inside the region
 
-  for(uint32_t base = 0; base < n; base += VB200_BATCH)
+  for(uint32_t base = 0; base < n; base += 32u)
   {
-    const uint32_t cnt = min((uint32_t)VB200_BATCH, n - base);
-    __syncthreads();
-    if(threadIdx.x < cnt)
+    // ---- 1. load + setup 32 triangles, keep those whose bbox touches this warp's region
+    bool touches = false;
+    if(base + lane < n)
     {
-      const uint32_t t = p.list[off + base + threadIdx.x];
+      const uint32_t t = p.list[off + base + lane];
       const Vb200TriSetup su = vb200_load_setup(p.setup + t);
-      TriSmem s;
-      // rasterizer.cpp:395-448 — area2, barymul = sign(area2), |area2|
-      const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
-      const int area2 = ABx * ACy - ABy * ACx;
-      const int sgn = area2 > 0 ? 1 : -1;
-      // barycentric() (rasterizer.cpp:303-309) with barymul folded in; exact in int32 ring arithmetic:
-      //   b1 = ux*s = A1*x + B1*y + C1,  b2 = uy*s = A2*x + B2*y + C2,  b0 = |area2| - (b1 + b2)
-      s.A1 = sgn * ACy;
-      s.B1 = -sgn * ACx;
-      s.C1 = sgn * (ACx * su.y0 - ACy * su.x0);
-      s.A2 = -sgn * ABy;
-      s.B2 = sgn * ABx;
-      s.C2 = sgn * (ABy * su.x0 - ABx * su.y0);
-      s.area = sgn * area2;
       // MinMax + clamp (rasterizer.cpp:428-435); pixels iterate the half-open box [min, max)
-      s.minx = max(0, min(su.x0, min(su.x1, su.x2)));
-      s.miny = max(0, min(su.y0, min(su.y1, su.y2)));
-      s.maxx = min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2)));
-      s.maxy = min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2)));
-      s.invarea = su.invarea;
-      s.invw0 = su.invw0;
-      s.invw1 = su.invw1;
-      s.invw2 = su.invw2;
-      s.d0 = su.d0;
-      s.d1 = su.d1;
-      s.d2 = su.d2;
-      s.s0 = su.s0;
-      s.s1 = su.s1;
-      s.s2 = su.s2;
-      s.pad = 0;
-      s.padf = 0.0f;
-      s.pad2 = 0;
-      s_tri[threadIdx.x] = s;
+      const int minx = max(0, min(su.x0, min(su.x1, su.x2))), miny = max(0, min(su.y0, min(su.y1, su.y2)));
+      const int maxx = min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2)));
+      const int maxy = min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2)));
+      const int bx0 = max(minx, rx0) - rx0, bx1 = min(maxx, rx0 + 16) - rx0;
+      const int by0 = max(miny, ry0) - ry0, by1 = min(maxy, ry0 + 8) - ry0;
+      touches = bx0 < bx1 && by0 < by1;
+      if(touches)
+      {
+        // rasterizer.cpp:395-448 — area2, barymul = sign(area2), |area2|; barycentric() (:303-309)
+        // with barymul folded in and re-based to region-relative pixel coordinates (exact in the
+        // int32 ring): b1 = A1*x + B1*y + C1, b2 = A2*x + B2*y + C2, b0 = |area2| - (b1 + b2)
+        const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
+        const int area2 = ABx * ACy - ABy * ACx;
+        const int sgn = area2 > 0 ? 1 : -1;
+        TriSmem s;
+        s.A1 = sgn * ACy;
+        s.B1 = -sgn * ACx;
+        s.C1 = sgn * (ACx * su.y0 - ACy * su.x0) + s.A1 * rx0 + s.B1 * ry0;
+        s.A2 = -sgn * ABy;
+        s.B2 = sgn * ABx;
+        s.C2 = sgn * (ABy * su.x0 - ABx * su.y0) + s.A2 * rx0 + s.B2 * ry0;
+        s.area = sgn * area2;
+        s.box = bx0 | (bx1 << 8) | (by0 << 16) | (by1 << 24);
+        s.invarea = su.invarea;
+        s.invw0 = su.invw0;
+        s.invw1 = su.invw1;
+        s.invw2 = su.invw2;
+        s.d0 = su.d0;
+        s.d1 = su.d1;
+        s.d2 = su.d2;
+        s.s0 = su.s0;
+        s.s1 = su.s1;
+        s.s2 = su.s2;
+        s.pad0 = s.pad1 = 0;
+        wtri[lane] = s;
+      }
     }
-    __syncthreads();
+    uint32_t hits = __ballot_sync(0xffffffffu, touches);
+    __syncwarp();
 
-    for(uint32_t k = 0; k < cnt; k++)
+    // ---- 2./3. surviving triangles in list order
+    while(hits)
     {
-      const TriSmem &t = s_tri[k];
-      // warp-uniform reject: bbox against this warp's 16x8 region
-      if(t.maxx <= rx0 || t.minx >= rx0 + 16 || t.maxy <= ry0 || t.miny >= ry0 + 8)
-        continue;
-      // coverage of the thread's four pixels first (cheap, integer), fragment work only where needed
-      const int e1 = t.A1 * x0 + t.B1 * y0 + t.C1, e2 = t.A2 * x0 + t.B2 * y0 + t.C2;
-      uint32_t mask = 0;
-      const bool xin = x0 >= t.minx && x0 < t.maxx;
+      const int k = __ffs(hits) - 1;
+      hits &= hits - 1u;
+      const TriSmem &t = wtri[k];
+      const int bx0 = t.box & 0xff, bx1 = (t.box >> 8) & 0xff, by0 = (t.box >> 16) & 0xff, by1 = (int)((uint32_t)t.box >> 24);
+      const int e1 = t.A1 * lx + t.B1 * ly + t.C1, e2 = t.A2 * lx + t.B2 * ly + t.C2;
+      const bool xin = lx >= bx0 && lx < bx1;
+      uint32_t m[4];
 #pragma unroll
       for(int j = 0; j < 4; j++)
       {
-        const int y = y0 + 2 * j;
+        const int y = ly + 2 * j;
         const int b1 = e1 + 2 * j * t.B1, b2 = e2 + 2 * j * t.B2;
         const int b0 = t.area - (b1 + b2);
-        const bool inside = ((b0 | b1 | b2) >= 0) && xin && y >= t.miny && y < t.maxy;
-        mask |= inside ? (1u << j) : 0u;    // covered iff all three >= 0 (rasterizer.cpp:549)
+        // covered iff all three >= 0 (rasterizer.cpp:549), inside the half-open clipped bbox
+        const bool inside = ((b0 | b1 | b2) >= 0) && xin && y >= by0 && y < by1;
+        m[j] = __ballot_sync(0xffffffffu, inside);
       }
-      if(!__any_sync(0xffffffffu, mask != 0u))
+      const uint32_t c0 = __popc(m[0]), c1 = c0 + __popc(m[1]), c2 = c1 + __popc(m[2]), total = c2 + __popc(m[3]);
+      if(total == 0u)
         continue;
-      covered += __popc(mask);
-#pragma unroll
-      for(int j = 0; j < 4; j++)
+      covered += (lane == 0) ? total : 0u;
+      // compact the covered pixel indices of the region into the warp's queue (row-major order)
+      const uint32_t below = (1u << lane) - 1u;
+      if(m[0] & (1u << lane)) wq[__popc(m[0] & below)] = (uint8_t)lane;
+      if(m[1] & (1u << lane)) wq[c0 + __popc(m[1] & below)] = (uint8_t)(lane + 32);
+      if(m[2] & (1u << lane)) wq[c1 + __popc(m[2] & below)] = (uint8_t)(lane + 64);
+      if(m[3] & (1u << lane)) wq[c2 + __popc(m[3] & below)] = (uint8_t)(lane + 96);
+      __syncwarp();
+      for(uint32_t f = lane; f < total; f += 32u)
       {
-        if(!__any_sync(0xffffffffu, (mask >> j) & 1u))    // nothing of this row pair is covered
-          continue;
-        if(!(mask & (1u << j)))
-          continue;
-        const int b1 = e1 + 2 * j * t.B1, b2 = e2 + 2 * j * t.B2, b0 = t.area - (b1 + b2);
+        const int i = wq[f];
+        const int x = i & 15, y = i >> 4;
+        const int b1 = t.A1 * x + t.B1 * y + t.C1, b2 = t.A2 * x + t.B2 * y + t.C2, b0 = t.area - (b1 + b2);
         // rasterizer.cpp:552-558
         float n0 = __fmul_rn((float)b0, t.invarea);
         float n1 = __fmul_rn((float)b1, t.invarea);
         float n2 = __fmul_rn((float)b2, t.invarea);
         const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, t.d0), __fmul_rn(n1, t.d1)), __fmul_rn(n2, t.d2));
-        if(depthTest && !vb200_depth_pass(rs.depth_op, pixdepth, dep[j]))
+        if(depthTest && !vb200_depth_pass(rs.depth_op, pixdepth, wdep[i]))
           continue;
         shaded++;
         // perspective correction (rasterizer.cpp:581-588)
@@ -308,7 +329,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
 
         float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)t.s0 * rs.nslots,
                               p.interps + (size_t)t.s1 * rs.nslots, p.interps + (size_t)t.s2 * rs.nslots);
-        const uint32_t cur = col[j];
+        const uint32_t cur = wcol[i];
         if(blend)
         {
           // blend (rasterizer.cpp:593-672): existing = bytes (2,1,0) / 255.0f from the exact table
@@ -324,23 +345,26 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
         const uint32_t r = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.x), 255.0f));
         const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.y), 255.0f));
         const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.z), 255.0f));
-        col[j] = (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
+        wcol[i] = (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
         if(depthWrite)
-          dep[j] = pixdepth;
+          wdep[i] = pixdepth;
       }
+      __syncwarp();    // the next triangle may touch the same pixels / reuse the queue
     }
+    __syncwarp();    // wtri is overwritten by the next 32 triangles
   }
 
 #pragma unroll
   for(int j = 0; j < 4; j++)
   {
-    const int x = x0, y = y0 + 2 * j;
+    const int i = lane + 32 * j;
+    const int x = rx0 + (i & 15), y = ry0 + (i >> 4);
     if(x < (int)rs.width && y < (int)rs.height)
     {
       const size_t idx = (size_t)y * rs.width + x;
-      p.color[idx] = col[j];
+      p.color[idx] = wcol[i];
       if(depthWrite || (clearDepth && rs.has_depth))
-        p.depth[idx] = dep[j];
+        p.depth[idx] = wdep[i];
     }
   }
   if(rs.count_fragments)
