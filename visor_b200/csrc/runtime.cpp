@@ -442,8 +442,15 @@ int linkCubin(const vb200_entry *vs, const vb200_entry *fs, std::vector<char> &c
   auto nvJitLinkGetErrorLogSize = nvj.getLogSize;
   auto nvJitLinkGetErrorLog = nvj.getLog;
   nvJitLinkHandle h;
-  const char *opts[] = {"-arch=sm_100a", "-lineinfo"};
-  if(nvJitLinkCreate(&h, 2, opts) != NVJITLINK_SUCCESS)
+  std::string maxreg;
+  const char *opts[3] = {"-arch=sm_100a", "-lineinfo", nullptr};
+  uint32_t nopts = 2;
+  if(const char *mr = getenv("VB200_JIT_MAXRREGCOUNT"))    // tuning aid: cap the shader functions' registers
+  {
+    maxreg = std::string("-maxrregcount=") + mr;
+    opts[nopts++] = maxreg.c_str();
+  }
+  if(nvJitLinkCreate(&h, nopts, opts) != NVJITLINK_SUCCESS)
     return setError(VB200_ERR_LINK, "nvJitLinkCreate failed");
   auto logOf = [&](std::string &s) {
     size_t n = 0;

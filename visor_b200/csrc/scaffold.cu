@@ -438,7 +438,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 {
   __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
   __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
-  __shared__ int4 s_coef[8][32][4];    // TriCoef records, one per lane of each warp
+  __shared__ int4 s_coef[256][4];     // TriCoef records of the current round, one per thread
+  __shared__ uint32_t s_start[257];   // first stream slot of each record; [count] = stream length
+  __shared__ uint32_t s_wsum[8];
 
   const uint32_t tile = blockIdx.x;
   if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
@@ -488,25 +490,21 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     if(MODE == VB200_RES_LAST_WINS)
       s_depth[ly * VB200_TILE + lane] = e;
   }
-  __syncthreads();
 
   // ---- phase A: coverage + visibility.
-  // Each warp takes 32 triangles of the list at a time. Their tile-clipped bboxes are laid end to
-  // end into one stream of candidate pixels (exclusive prefix sum of the pixel counts); every step
-  // the 32 lanes test 32 consecutive pixels of that stream, whichever triangles they belong to, so
-  // 6-pixel and full-tile triangles keep the lanes equally busy. Every listed triangle has a
-  // non-empty clipped bbox (the binning walked exactly these pixel ranges), so valid lanes are
-  // 0..m-1 and "rank among triangles" is the lane that staged the record.
+  // Up to 256 triangles of the list per round, one per thread. Their tile-clipped bboxes are laid end
+  // to end into ONE stream of candidate pixels (block-wide exclusive prefix sum of the pixel counts),
+  // which is cut into 32-pixel steps; warp w takes the w-th eighth of the steps, so every warp does the
+  // same amount of work whatever the triangle sizes are and all 32 lanes test a pixel every step.
+  // Every listed triangle has a non-empty clipped bbox (the binning walked exactly these pixel ranges).
   uint32_t covered = 0, shaded = 0;
-  int4(*wc)[4] = s_coef[warp];
-  // spread the list evenly over the 8 warps: ceil(n/8) triangles per warp per round, at most 32
-  const uint32_t chunk = min(32u, (n + 7u) >> 3);
-  for(uint32_t base = warp * chunk; base < n; base += 8u * chunk)
+  for(uint32_t base = 0; base < n; base += 256u)
   {
-    const uint32_t i = base + lane;
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t m = min(256u, n - base);    // records in this round
     uint32_t cnt = 0;
     int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = make_int4(0, 0, 0, 65537);
-    if(i < n && (uint32_t)lane < chunk)
+    if(i < n)
     {
       const uint32_t t = p.list[off + i];
       const Vb200TriSetup su = vb200_load_setup(p.setup + t);
@@ -517,8 +515,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       const int y0 = max(max(0, min(su.y0, min(su.y1, su.y2))), tileY0);
       const int x1 = min(min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2))), tileX0 + VB200_TILE);
       const int y1 = min(min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2))), tileY0 + VB200_TILE);
-      const int w = max(x1 - x0, 1), h = max(y1 - y0, 0);
-      cnt = (x1 > x0) ? (uint32_t)(w * h) : 0u;
+      const int w = max(x1 - x0, 1), h = max(y1 - y0, 1);
+      cnt = (uint32_t)(w * h);
       const int A1 = sgn * ACy, B1 = -sgn * ACx, C1 = sgn * (ACx * su.y0 - ACy * su.x0);
       const int A2 = -sgn * ABy, B2 = sgn * ABx, C2 = sgn * (ABy * su.x0 - ABx * su.y0);
       r0 = make_int4(A1, B1 - A1 * w, C1 + A1 * x0 + B1 * y0, A2);
@@ -529,6 +527,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       // of the fast division)
       r3 = make_int4((int)(t + 1u), 0, VB200_TILE - w, (int)(__float2uint_rz(__fdividef(65536.0f, (float)w)) + 1u));
     }
+    // block-wide exclusive scan of cnt
     uint32_t incl = cnt;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1)
@@ -537,70 +536,103 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       if(lane >= o)
         incl += v;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint32_t myStart = incl - cnt;
-    r3.y = (int)myStart;
-    __syncwarp();
-    wc[lane][0] = r0;
-    wc[lane][1] = r1;
-    wc[lane][2] = r2;
-    wc[lane][3] = r3;
-    __syncwarp();
-    const bool hasPixels = cnt != 0u;
-    for(uint32_t k = 0; k < total; k += 32u)
+    __syncthreads();    // previous round (or the init) is done with s_coef / s_start / s_wsum
+    if(lane == 31)
+      s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for(int q = 0; q < 8; q++)
     {
-      // owner of stream slot k + lane = (#triangles starting before this step) + (#starts inside the
-      // step at or before this lane) - 1
-      const uint32_t before = __popc(__ballot_sync(0xffffffffu, hasPixels && myStart < k));
-      const uint32_t rel = myStart - k;
-      const uint32_t starts = __reduce_or_sync(0xffffffffu, (hasPixels && rel < 32u) ? (1u << rel) : 0u);
-      const uint32_t g = k + lane;
-      if(g >= total)
-        continue;
-      // lanes with an empty bbox cannot occur between valid ones (see above), so rank == lane index
-      const uint32_t owner = before + __popc(starts & (0xffffffffu >> (31 - lane))) - 1u;
-      const int4 c0 = wc[owner][0], c1 = wc[owner][1], c3 = wc[owner][3];
-      const int li = (int)(g - (uint32_t)c3.y);
-      const int yq = (int)(((uint32_t)li * (uint32_t)c3.w) >> 16);
-      const int b1 = c0.x * li + c0.y * yq + c0.z;
-      const int b2 = c0.w * li + c1.x * yq + c1.y;
-      const int b0 = c1.z - (b1 + b2);
-      if((b0 | b1 | b2) < 0)
-        continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
-      covered++;
-      const int idx = c1.w + li + yq * c3.z;
-      const uint32_t id = (uint32_t)c3.x;
-      unsigned long long key;
-      if(MODE == VB200_RES_LAST_WINS && !depthTest)
-        key = (unsigned long long)(~id);
-      else
+      const uint32_t v = s_wsum[q];
+      wbase += (q < warp) ? v : 0u;
+      total += v;
+    }
+    const uint32_t myStart = wbase + incl - cnt;
+    r3.y = (int)myStart;
+    s_coef[threadIdx.x][0] = r0;
+    s_coef[threadIdx.x][1] = r1;
+    s_coef[threadIdx.x][2] = r2;
+    s_coef[threadIdx.x][3] = r3;
+    s_start[threadIdx.x] = (i < n) ? myStart : total;
+    if(threadIdx.x == 0)
+      s_start[256] = total;
+    __syncthreads();
+
+    const uint32_t steps = (total + 31u) >> 5;
+    const uint32_t firstStep = (steps * (uint32_t)warp) >> 3, lastStep = (steps * (uint32_t)(warp + 1)) >> 3;
+    if(firstStep < lastStep)
+    {
+      // record that owns stream slot firstStep*32: last record whose start is <= that slot
+      uint32_t owner0;
       {
-        const int4 c2 = wc[owner][2];
-        const float invarea = __int_as_float(c2.x);
-        const float n0 = __fmul_rn((float)b0, invarea);
-        const float n1 = __fmul_rn((float)b1, invarea);
-        const float n2 = __fmul_rn((float)b2, invarea);
-        const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, __int_as_float(c2.y)), __fmul_rn(n1, __int_as_float(c2.z))),
-                                         __fmul_rn(n2, __int_as_float(c2.w)));
-        if(MODE == VB200_RES_LAST_WINS)
+        const uint32_t k = firstStep << 5;
+        uint32_t lo = 0, hi = m;    // invariant: s_start[lo] <= k < s_start[hi] (s_start[m] = total > k)
+        while(hi - lo > 1u)
         {
-          if(!vb200_depth_pass(rs.depth_op, pixdepth, s_depth[idx]))
-            continue;
-          key = (unsigned long long)(~id);
+          const uint32_t mid = (lo + hi) >> 1;
+          if(s_start[mid] <= k)
+            lo = mid;
+          else
+            hi = mid;
         }
+        owner0 = lo;
+      }
+      for(uint32_t step = firstStep; step < lastStep; step++)
+      {
+        const uint32_t k = step << 5;
+        // lane l looks at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
+        const uint32_t rel = s_start[min(owner0 + 1u + (uint32_t)lane, 256u)] - k;
+        const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+        const uint32_t nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
+        const uint32_t g = k + lane;
+        const uint32_t owner = owner0 + __popc(starts & (0xffffffffu >> (31 - lane)));
+        owner0 = nextOwner0;
+        if(g >= total)
+          continue;
+        const int4 c0 = s_coef[owner][0], c1 = s_coef[owner][1], c3 = s_coef[owner][3];
+        const int li = (int)(g - (uint32_t)c3.y);
+        const int yq = (int)(((uint32_t)li * (uint32_t)c3.w) >> 16);
+        const int b1 = c0.x * li + c0.y * yq + c0.z;
+        const int b2 = c0.w * li + c1.x * yq + c1.y;
+        const int b0 = c1.z - (b1 + b2);
+        if((b0 | b1 | b2) < 0)
+          continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
+        covered++;
+        const int idx = c1.w + li + yq * c3.z;
+        const uint32_t id = (uint32_t)c3.x;
+        unsigned long long key;
+        if(MODE == VB200_RES_LAST_WINS && !depthTest)
+          key = (unsigned long long)(~id);
         else
         {
-          if(pixdepth != pixdepth)
-            continue;    // NaN never passes an ordered comparison
-          uint32_t dk = vb200_depth_key(pixdepth);
-          if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
-            dk = ~dk;
-          const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? id : ~id;
-          key = ((unsigned long long)dk << 32) | low;
+          const int4 c2 = s_coef[owner][2];
+          const float invarea = __int_as_float(c2.x);
+          const float n0 = __fmul_rn((float)b0, invarea);
+          const float n1 = __fmul_rn((float)b1, invarea);
+          const float n2 = __fmul_rn((float)b2, invarea);
+          const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, __int_as_float(c2.y)), __fmul_rn(n1, __int_as_float(c2.z))),
+                                           __fmul_rn(n2, __int_as_float(c2.w)));
+          if(MODE == VB200_RES_LAST_WINS)
+          {
+            if(!vb200_depth_pass(rs.depth_op, pixdepth, s_depth[idx]))
+              continue;
+            key = (unsigned long long)(~id);
+          }
+          else
+          {
+            if(pixdepth != pixdepth)
+              continue;    // NaN never passes an ordered comparison
+            uint32_t dk = vb200_depth_key(pixdepth);
+            if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
+              dk = ~dk;
+            const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? id : ~id;
+            key = ((unsigned long long)dk << 32) | low;
+          }
         }
+        if(key < vis[idx])
+          atomicMin(&vis[idx], key);
       }
-      if(key < vis[idx])
-        atomicMin(&vis[idx], key);
     }
   }
   __syncthreads();
