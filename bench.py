@@ -143,7 +143,7 @@ def scene_host_buffers(bound: scenes.BoundScene):
 
 
 # ------------------------------------------------------------------------------------------------
-def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps: int = 1):
+def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps: int = 1, hash_depth: bool = True):
     """visor's own CPU rasterizer (oracle/_ref) on this box's host cores: threaded as shipped
     (7 workers + main, rasterizer.cpp:8) and serial (the deterministic parity mode)."""
     if not abi.available("vref"):
@@ -151,9 +151,9 @@ def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps:
     res = {}
     tris = scene.triangles()
     # threaded must come first: the pool cannot be restarted once shut down (rast.kill stays set)
-    ref = abi.backend("vref", 1)
+    ref = abi.backend("vref", 1 if threaded_steps > 0 else 0)
     b = scenes.BoundScene(ref, scene)
-    if ref.fn("threads")() == 8:
+    if threaded_steps > 0 and ref.fn("threads")() == 8:
         ts = []
         for _ in range(max(1, threaded_steps)):
             t0 = time.perf_counter()
@@ -168,7 +168,7 @@ def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps:
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     res["serial"] = {"s_per_frame": float(np.mean(ts)), "mtri_s": tris / float(np.mean(ts)) / 1e6, "threads": 1}
-    res["hash"] = scenes.image_hash(b.color, b.depth)
+    res["hash"] = scenes.image_hash(b.color, b.depth if hash_depth else None)
     return res
 
 
@@ -234,26 +234,55 @@ def run_ours(args, workload: str) -> None:
         gpu.check(L.vb200_set_option(b"raster_path", 1), "set_option")
     scene = build_scene(workload)
     tris = scene.triangles()
-    bound = scenes.BoundScene(gpu, scene)
+    npx = scene.width * scene.height
+    fused = False
+    if multi:
+        gpu.check(L.vb200_set_tile_owner(rank, world), "set_tile_owner")
+        ext = torch.cuda.ExternalStream(L.vb200_stream())
+        L.vb200_set_peer_targets.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+        if args.exchange == "fused":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                color_t = symm.empty(npx, dtype=torch.int32, device="cuda")
+                hdl = symm.rendezvous(color_t, dist.group.WORLD)
+                peers = [int(hdl.buffer_ptrs[r]) for r in range(world) if r != rank]
+                arr = (C.c_void_p * len(peers))(*peers)
+                gpu.check(L.vb200_set_peer_targets(color_t.data_ptr(), arr, len(peers)), "set_peer_targets")
+                fused = True
+            except Exception as e:  # symmetric memory unavailable: NCCL all-gather baseline
+                if rank == 0:
+                    print(f"bench: fused exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
+        if not fused:
+            color_t = torch.empty(npx, dtype=torch.int32, device="cuda")
+        depth_t = torch.empty(npx, dtype=torch.float32, device="cuda")
+        bound = scenes.BoundScene(gpu, scene, color_device_ptr=color_t.data_ptr(), depth_device_ptr=depth_t.data_ptr())
+        color_host = torch.empty(npx, dtype=torch.int32, pin_memory=True)
+        if not fused:
+            slots = L.vb200_tiles_per_rank(scene.width, scene.height, world)
+            send = torch.empty(slots * 4096, dtype=torch.uint8, device="cuda")
+            recv = torch.empty(world * slots * 4096, dtype=torch.uint8, device="cuda")
+    else:
+        bound = scenes.BoundScene(gpu, scene)
     bufs = scene_host_buffers(bound)
+    if multi:
+        bufs = [(a, is_in) for a, is_in in bufs if is_in]    # attachments live in device memory
     for a, _ in bufs:
         gpu.check(L.vb200_mem_register(a.ctypes.data, a.nbytes), "mem_register")
     in_bytes = sum(a.nbytes for a, is_in in bufs if is_in)
     out_bytes = sum(a.nbytes for a, is_in in bufs if not is_in)
 
-    if multi:
-        gpu.check(L.vb200_set_tile_owner(rank, world), "set_tile_owner")
-        slots = L.vb200_tiles_per_rank(scene.width, scene.height, world)
-        ext = torch.cuda.ExternalStream(L.vb200_stream())
-        send = torch.empty(slots * 4096, dtype=torch.uint8, device="cuda")
-        recv = torch.empty(world * slots * 4096, dtype=torch.uint8, device="cuda")
-
     def exchange():
-        """sort-first assemble: owned colour tiles -> all ranks -> linear image (on the library stream)."""
-        gpu.check(L.vb200_tiles_pack(C.byref(bound.color_img), send.data_ptr(), send.numel()), "tiles_pack")
+        """sort-first assemble on the library stream. fused: the tile kernels already stored every pixel
+        into all ranks' images over NVLink, only a cross-rank barrier is left. all-gather: owned colour
+        tiles -> NCCL all-gather -> un-tile."""
         with torch.cuda.stream(ext):
-            dist.all_gather_into_tensor(recv, send)
-        gpu.check(L.vb200_tiles_unpack(C.byref(bound.color_img), recv.data_ptr(), recv.numel(), world), "tiles_unpack")
+            if fused:
+                hdl.barrier()
+            else:
+                gpu.check(L.vb200_tiles_pack(C.byref(bound.color_img), send.data_ptr(), send.numel()), "tiles_pack")
+                dist.all_gather_into_tensor(recv, send)
+                gpu.check(L.vb200_tiles_unpack(C.byref(bound.color_img), recv.data_ptr(), recv.numel(), world),
+                          "tiles_unpack")
 
     def barrier():
         gpu.flush()
@@ -304,8 +333,8 @@ def run_ours(args, workload: str) -> None:
     L.vb200_set_option(b"time_kernels", 1)
     for _ in range(3):
         gpu.check(L.vb200_l2_flush(), "l2_flush")
-        bound.submit()
-    gpu.flush()
+        step_device()
+    barrier()
     pm = (C.c_double * 5)()
     pc = (C.c_uint64 * 5)()
     L.vb200_get_phase_times(pm, pc, 5)
@@ -314,49 +343,65 @@ def run_ours(args, workload: str) -> None:
     L.vb200_set_option(b"time_kernels", 0)
     L.vb200_set_option(b"count_fragments", 1)
     gpu.reset_stats()
-    bound.submit()
-    gpu.flush()
+    step_device()
+    barrier()
     st = gpu.stats()
+    if multi:    # fragment / pair counters are per rank (each rank rasterises only its own tiles)
+        cnt = torch.tensor([st["fragments_covered"], st["fragments_shaded"], st["tile_pairs"]], device="cuda")
+        dist.all_reduce(cnt)
+        st["fragments_covered"], st["fragments_shaded"], st["tile_pairs"] = (int(v) for v in cnt.tolist())
     L.vb200_set_option(b"count_fragments", 0)
 
     # ---------------- e2e: host buffers through the C-ABI, copies inside the timed region --------
     gpu.check(L.vb200_set_sync_mode(0), "set_sync_mode")
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    def step_e2e():
+        """one frame as an application sees it: inputs come from host memory (uploaded by the library),
+        the finished frame ends up in host memory (N>1: rank 0 reads the assembled image back)."""
         bound.submit()
         if multi:
             exchange()
+            if rank == 0:
+                with torch.cuda.stream(ext):
+                    color_host.copy_(color_t, non_blocking=True)
         gpu.flush()
+
+    for _ in range(2):
+        step_e2e()
     barrier()
     gpu.reset_stats()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        bound.submit()
-        if multi:
-            exchange()
-        gpu.flush()
+        step_e2e()
     if multi:
         torch.cuda.synchronize()
     t_e2e_local = (time.perf_counter() - t0) / e2e_steps
     st2 = gpu.stats()
+    if multi:
+        st2["d2h_bytes"] += npx * 4 * e2e_steps
     if multi:
         tt = torch.tensor([t_e2e_local], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.item())
     else:
         t_e2e = t_e2e_local
-    img_hash = scenes.image_hash(bound.color, bound.depth if not multi else None)
-
-    if rank != 0:
-        if multi:
-            dist.destroy_process_group()
-        return
+    if multi:
+        barrier()    # nobody tears down memory that peers may still be storing into
+        final = color_host.numpy().view(np.uint8).reshape(scene.height, scene.width, 4)
+        img_hash = scenes.image_hash(final, None)
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    else:
+        img_hash = scenes.image_hash(bound.color, bound.depth)
 
     # ---------------- CPU baseline (rank 0, N = 1): the reference's own rasterizer ----------------
     cpu = None
     parity = None
-    if not multi and not args.no_cpu_baseline:
-        r = time_reference(scene, 2, 0, threaded_steps=1)
+    if not args.no_cpu_baseline:
+        # N>1: serial mode only (a threaded 8K frame takes ~25 s); the colour image is what is compared
+        r = time_reference(scene, 2 if not multi else 1, 0, threaded_steps=0 if multi else 1,
+                           hash_depth=not multi)
         if r is not None:
             best = max((k for k in ("serial", "threaded") if k in r), key=lambda k: r[k]["mtri_s"])
             cpu = {"value": r[best]["mtri_s"], "unit": "Mtri/s", "cores": r[best]["threads"], "kind": "reference",
@@ -381,7 +426,9 @@ def run_ours(args, workload: str) -> None:
         "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[workload], "triangles": tris,
                    "resolution": [scene.width, scene.height], "l2": "flushed (512 MB write) before each timed step",
-                   "parallelism": f"sort-first x{world}" if multi else "single GPU",
+                   "parallelism": (f"sort-first x{world}, " + ("fused NVLink peer stores from the tile kernel + barrier"
+                                                                if fused else "NCCL all-gather of owned tiles"))
+                   if multi else "single GPU",
                    "raster_path": ("ordered tiles (forced)" if args.raster_path == "ordered" else
                                    "auto: visibility-resolve tiles for order-independent passes, ordered tiles otherwise")},
         "gfrag_s": st["fragments_covered"] / (t_step * 1e-3) / 1e9,
@@ -403,8 +450,6 @@ def run_ours(args, workload: str) -> None:
     if parity:
         line["parity"] = parity
     print(json.dumps(line))
-    if multi:
-        dist.destroy_process_group()
 
 
 def main() -> None:
@@ -415,6 +460,9 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "allgather"],
+                    help="N>1: fused = tile kernels store into every rank's image over NVLink peer pointers; "
+                         "allgather = pack + NCCL all-gather + unpack")
     ap.add_argument("--raster-path", default="auto", choices=["auto", "ordered"],
                     help="diagnostic: force the in-order tile kernel even for order-independent passes")
     args = ap.parse_args()

@@ -104,7 +104,10 @@ class BoundScene:
     """A Scene lowered to ctypes structs for one backend; keeps every buffer alive."""
 
     def __init__(self, be: Backend, scene: Scene, color: Optional[np.ndarray] = None,
-                 depth: Optional[np.ndarray] = None) -> None:
+                 depth: Optional[np.ndarray] = None, color_device_ptr: Optional[int] = None,
+                 depth_device_ptr: Optional[int] = None) -> None:
+        """color/depth: host arrays to render into (allocated if omitted). color_device_ptr /
+        depth_device_ptr: CUDA device addresses to use as attachments instead (vb200 only)."""
         self.be, self.scene = be, scene
         w, h = scene.width, scene.height
         self.color = color if color is not None else np.full((h, w, 4), 0xCD, dtype=np.uint8)
@@ -113,6 +116,10 @@ class BoundScene:
             self.depth = depth if depth is not None else np.full((h, w), 0.75, dtype=np.float32)
         self.color_img = abi.make_image(self.color, w, h, abi.FMT_B8G8R8A8_UNORM)
         self.depth_img = abi.make_image(self.depth, w, h, abi.FMT_D32_SFLOAT)
+        if color_device_ptr is not None:
+            self.color_img.pixels = color_device_ptr
+        if depth_device_ptr is not None and scene.depth:
+            self.depth_img.pixels = depth_device_ptr
         self.keep: List[object] = []
         self.calls: List[Tuple[abi.DrawState, Draw]] = []
         pipes: Dict[int, abi.Pipeline] = {}

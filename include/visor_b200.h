@@ -211,6 +211,13 @@ VB200_API int vb200_tiles_pack(const vb200_image *image, void *dst_device, uint6
 VB200_API int vb200_tiles_unpack(const vb200_image *image, const void *src_device, uint64_t src_size,
                                  int world);
 VB200_API uint32_t vb200_tiles_per_rank(uint32_t width, uint32_t height, int world);
+/* Fused exchange (preferred over pack/all-gather/unpack): `local_color_device` is this rank's colour
+ * image (a device pointer used as vb200_draw_state::color.pixels); `peer_color_device[i]` are the
+ * peer-mapped device addresses of the SAME image on the other ranks (e.g. torch symmetric memory
+ * buffer_ptrs, CUDA IPC or cuMem handles). While tile ownership is on, the tile kernels store every
+ * colour word they produce into all of them over NVLink, so after all ranks finish (one cross-rank
+ * barrier) every rank holds the whole image. num_peers = 0 removes the association. */
+VB200_API int vb200_set_peer_targets(const void *local_color_device, void *const *peer_color_device, int num_peers);
 
 /* ---- introspection ----------------------------------------------------------------------- */
 

@@ -45,6 +45,11 @@ struct Vb200TileParams
   // every tile (including tiles no triangle touches), so no separate clear kernel runs.
   uint32_t clear_flags, clear_color;
   float clear_depth;
+  // sort-first exchange fused into the write-back: the colour image of every OTHER rank (peer-mapped
+  // device addresses over NVLink). Each pixel this rank produces is stored locally and to all peers,
+  // so when every rank's tile kernel has finished, every rank holds the complete image.
+  uint32_t num_peers;
+  uint32_t *peer_color[7];
   uint32_t *color;
   float *depth;
   const float4 *interps;

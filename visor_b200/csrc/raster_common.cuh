@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "device_types.h"
+#include "kernels.h"
 
 // int(float) as the reference's x86-64 build performs it (cvttss2si): truncation toward zero,
 // 0x80000000 for NaN and out-of-range inputs.
@@ -91,6 +92,14 @@ __device__ __forceinline__ uint32_t vb200_blend_store(const Vb200RasterState &rs
   const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.y), 255.0f));
   const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.z), 255.0f));
   return (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
+}
+
+// colour store of the tile kernels: local image + every peer's image (fused sort-first exchange)
+__device__ __forceinline__ void vb200_store_color(const Vb200TileParams &p, size_t gi, uint32_t v)
+{
+  p.color[gi] = v;
+  for(uint32_t r = 0; r < p.num_peers; r++)
+    p.peer_color[r][gi] = v;
 }
 
 __device__ __forceinline__ void vb200_count_fragments(Vb200DrawCounters *c, uint32_t covered, uint32_t shaded)

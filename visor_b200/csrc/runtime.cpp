@@ -139,6 +139,8 @@ struct Context
   };
   std::map<uint8_t *, PendingClear> pendingClears;
   int64_t optFuseClears = 1;
+  // fused sort-first exchange: colour target (device address on this rank) -> the same image on the peers
+  std::map<uint8_t *, std::vector<uint32_t *>> peerTargets;
   Vb200DrawCounters *counters = nullptr;    // device
   vb200_stats stats;
   uint32_t ownerRank = 0, ownerWorld = 1;
@@ -1237,7 +1239,9 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   {
     auto take = [&](uint8_t *dev, uint32_t bit, uint32_t *word) {
       auto it = g.pendingClears.find(dev);
-      if(it != g.pendingClears.end() && it->second.count == (size_t)W * H && g.ownerWorld == 1)
+      // with sort-first ownership a rank clears only the tiles it owns: colour of the others arrives from
+      // their owners (peer stores or the all-gather), their depth is never read on this rank
+      if(it != g.pendingClears.end() && it->second.count == (size_t)W * H)
       {
         clearFlags |= bit;
         *word = it->second.value;
@@ -1355,6 +1359,15 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.clear_flags = clearFlags;
   tp.clear_color = clearColorWord;
   tp.clear_depth = clearDepthValue;
+  {
+    auto pt = g.peerTargets.find(colorDev);
+    if(pt != g.peerTargets.end() && g.ownerWorld > 1)
+    {
+      tp.num_peers = (uint32_t)pt->second.size();
+      for(uint32_t r = 0; r < tp.num_peers; r++)
+        tp.peer_color[r] = pt->second[r];
+    }
+  }
 
   // ---- K3 + K4, launched speculatively: scan publishes the pair total to a mapped host word; fill,
   // sort and the tile kernel are enqueued right behind it against the guessed list capacity and turn
@@ -1470,6 +1483,26 @@ int vb200_set_tile_owner(int rank, int world)
     return setError(VB200_ERR_INVALID, "bad tile owner %d/%d", rank, world);
   g.ownerRank = (uint32_t)rank;
   g.ownerWorld = (uint32_t)world;
+  return VB200_OK;
+}
+
+int vb200_set_peer_targets(const void *local_color_device, void *const *peer_color_device, int num_peers)
+{
+  if(!local_color_device || num_peers < 0 || num_peers > 7 || (num_peers && !peer_color_device))
+    return setError(VB200_ERR_INVALID, "set_peer_targets: bad arguments (at most 7 peers)");
+  if(num_peers == 0)
+  {
+    g.peerTargets.erase((uint8_t *)local_color_device);
+    return VB200_OK;
+  }
+  std::vector<uint32_t *> v;
+  for(int i = 0; i < num_peers; i++)
+  {
+    if(!peer_color_device[i])
+      return setError(VB200_ERR_INVALID, "set_peer_targets: NULL peer pointer");
+    v.push_back((uint32_t *)peer_color_device[i]);
+  }
+  g.peerTargets[(uint8_t *)local_color_device] = v;
   return VB200_OK;
 }
 

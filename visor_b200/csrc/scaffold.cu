@@ -191,6 +191,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   const uint32_t tile = blockIdx.x;
   if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
     return;
+  if(p.rs.owner_world > 1u && tile % p.rs.owner_world != p.rs.owner_rank)
+    return;    // sort-first: another rank owns (clears, draws and publishes) this tile
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   if(n == 0 && !p.clear_flags)
@@ -362,7 +364,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     if(x < (int)rs.width && y < (int)rs.height)
     {
       const size_t idx = (size_t)y * rs.width + x;
-      p.color[idx] = wcol[i];
+      vb200_store_color(p, idx, wcol[i]);
       if(depthWrite || (clearDepth && rs.has_depth))
         p.depth[idx] = wdep[i];
     }
@@ -445,6 +447,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   const uint32_t tile = blockIdx.x;
   if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
     return;
+  if(p.rs.owner_world > 1u && tile % p.rs.owner_world != p.rs.owner_rank)
+    return;    // sort-first: another rank owns (clears, draws and publishes) this tile
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   const Vb200RasterState &rs = p.rs;
@@ -464,7 +468,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         {
           const size_t gi = (size_t)y * rs.width + x;
           if(clearColor)
-            p.color[gi] = p.clear_color;
+            vb200_store_color(p, gi, p.clear_color);
           if(clearDepth && rs.has_depth)
             p.depth[gi] = p.clear_depth;
         }
@@ -670,7 +674,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       {
         const size_t gi = (size_t)y * rs.width + x;
         if(clearColor)
-          p.color[gi] = p.clear_color;
+          vb200_store_color(p, gi, p.clear_color);
         if(clearDepth && rs.has_depth)
           p.depth[gi] = p.clear_depth;
       }
@@ -699,7 +703,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)su.s0 * rs.nslots,
                                 p.interps + (size_t)su.s1 * rs.nslots, p.interps + (size_t)su.s2 * rs.nslots);
     const size_t gi = (size_t)y * rs.width + x;
-    p.color[gi] = vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]);
+    vb200_store_color(p, gi, vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]));
     if(depthWrite)
       p.depth[gi] = pixdepth;
     else if(clearDepth && rs.has_depth)
