@@ -237,6 +237,20 @@ static void toImage(const vb200_image &in, VkImage_T &out)
 
 #define VREF_API extern "C" __attribute__((visibility("default")))
 
+// The reference's own InitTextureCache, compiled under this name (see oracle/Makefile). Callers
+// (InitRasterThreads per worker + main thread, vref_init, a second vkCreateInstance) reach it through
+// the guard below, so each thread's cache is linked exactly once.
+void InitTextureCache_ref();
+void InitTextureCache()
+{
+  static thread_local bool done = false;
+  if(!done)
+  {
+    done = true;
+    InitTextureCache_ref();
+  }
+}
+
 // threaded = 1: the reference's shipped mode (7 workers + stealing main thread, racy) — timing only.
 // threaded = 0: no workers; DrawTriangles drains its own FIFO in order — the parity oracle.
 VREF_API int vref_init(int threaded)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Developer aid: join an `ncu --page source --csv` SASS export with `nvdisasm -g` line info of the
 same linked cubin, and rank CUDA source lines by executed warp instructions / stall samples.
-usage: tools_sass_lines.py <ncu_sass.csv> <linked.cubin> <kernel_name> [top_n]"""
+usage: tools_sass_lines.py <ncu_sass.csv> <linked.cubin> <kernel_name> [top_n]
+(kernel_name is matched as a substring of both the demangled ncu name and the mangled .text section)"""
 import csv, re, subprocess, sys, os
 csvp, cubin, kern = sys.argv[1:4]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
@@ -10,7 +11,7 @@ addr2line, cur, insec = {}, None, False
 for l in out.splitlines():
     m = re.match(r'\s*\.section\s+\.text\.(\S+?),', l)
     if m:
-        insec = (m.group(1) == kern)
+        insec = (kern in m.group(1))
         continue
     if not insec:
         continue

@@ -73,9 +73,15 @@ struct Vb200TriSetup
 static_assert(sizeof(Vb200TriSetup) == 64, "setup record");
 #endif
 
+// Statistics counters. Same-address atomics serialise in the L2 atomic unit (~0.6 ns each), so every
+// counter is spread over 32 slots (slot = blockIdx & 31, 128-byte stride) and summed on read.
+#define VB200_COUNTER_SLOTS 32
 struct Vb200DrawCounters
 {
-  unsigned long long triangles_out, tile_pairs, fragments_covered, fragments_shaded;
+  struct alignas(128) Slot
+  {
+    unsigned long long triangles_out, fragments_covered, fragments_shaded, pad;
+  } slot[VB200_COUNTER_SLOTS];
 };
 
 // Fixed-function state of one draw, uniform across the grid.

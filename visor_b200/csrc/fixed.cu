@@ -232,9 +232,11 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     else if(flipped < 0 && (p.cull_mode & 2u))
       alive = false;
   }
-  const uint32_t survivors = __popc(__ballot_sync(0xffffffffu, alive));
-  if((threadIdx.x & 31) == 0 && survivors)
-    atomicAdd(&p.counters->triangles_out, (unsigned long long)survivors);
+  // statistics: one atomic per CTA on a spread counter (a per-warp atomic on ONE word costs ~20 us per
+  // million triangles: same-address atomics serialise in L2)
+  const uint32_t survivors = (uint32_t)__syncthreads_count(alive);
+  if(threadIdx.x == 0 && survivors)
+    atomicAdd(&p.counters->slot[blockIdx.x & (VB200_COUNTER_SLOTS - 1)].triangles_out, (unsigned long long)survivors);
 
   if(alive)
   {
@@ -266,20 +268,29 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
                 });
 }
 
-// exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also resets the fill cursors
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint32_t *tile_offset,
-                                              uint32_t *tile_cursor, uint32_t ntiles, uint32_t *total,
-                                              volatile unsigned long long *host_total, uint32_t seq)
+// exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also resets the fill cursors.
+// Each thread owns 4*V consecutive counters held in registers (16-byte loads/stores; the arrays are
+// allocated with padding to a multiple of 4096 entries), so the kernel is one load, one block scan,
+// one store.
+template <int V>
+__device__ __forceinline__ void scan_body(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor,
+                                          uint32_t ntiles, uint32_t *total, volatile unsigned long long *host_total,
+                                          uint32_t seq)
 {
   __shared__ uint32_t warp_sums[32];
-  const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
-  const uint32_t begin = threadIdx.x * per, end = min(begin + per, ntiles);
+  const uint32_t begin = threadIdx.x * 4u * V;
+  uint4 c[V];
   uint32_t sum = 0;
-  for(uint32_t i = begin; i < end; i++)
-    sum += tile_count[i];
-  // inclusive warp scan of the per-thread sums
+#pragma unroll
+  for(int v = 0; v < V; v++)
+  {
+    c[v] = (begin + 4u * v < ntiles) ? *(const uint4 *)(tile_count + begin + 4u * v) : make_uint4(0, 0, 0, 0);
+    // entries past ntiles inside the last vector are padding and hold 0
+    sum += c[v].x + c[v].y + c[v].z + c[v].w;
+  }
   uint32_t incl = sum;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
   for(int o = 1; o < 32; o <<= 1)
   {
     const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -291,8 +302,9 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint3
   __syncthreads();
   if(warp == 0)
   {
-    uint32_t w = warp_sums[lane];
+    const uint32_t w = warp_sums[lane];
     uint32_t wi = w;
+#pragma unroll
     for(int o = 1; o < 32; o <<= 1)
     {
       const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
@@ -313,12 +325,36 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint3
   }
   __syncthreads();
   uint32_t run = warp_sums[warp] + incl - sum;
-  for(uint32_t i = begin; i < end; i++)
+#pragma unroll
+  for(int v = 0; v < V; v++)
   {
-    tile_offset[i] = run;
-    tile_cursor[i] = 0u;
-    run += tile_count[i];
+    if(begin + 4u * v >= ntiles)
+      break;
+    uint4 o;
+    o.x = run;
+    o.y = o.x + c[v].x;
+    o.z = o.y + c[v].y;
+    o.w = o.z + c[v].z;
+    run = o.w + c[v].w;
+    *(uint4 *)(tile_offset + begin + 4u * v) = o;
+    *(uint4 *)(tile_cursor + begin + 4u * v) = make_uint4(0, 0, 0, 0);
   }
+}
+
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint32_t *tile_offset,
+                                              uint32_t *tile_cursor, uint32_t ntiles, uint32_t *total,
+                                              volatile unsigned long long *host_total, uint32_t seq)
+{
+  if(ntiles <= 4096u)
+    scan_body<1>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
+  else if(ntiles <= 8192u)
+    scan_body<2>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
+  else if(ntiles <= 16384u)
+    scan_body<4>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
+  else if(ntiles <= 32768u)
+    scan_body<8>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
+  else
+    scan_body<16>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
 }
 
 __global__ void __launch_bounds__(kThreads) k_fill(const Vb200SetupParams p, const uint32_t *tile_offset,

@@ -111,8 +111,9 @@ __device__ __forceinline__ void vb200_count_fragments(Vb200DrawCounters *c, uint
   }
   if((threadIdx.x & 31) == 0 && (covered | shaded))
   {
-    atomicAdd(&c->fragments_covered, (unsigned long long)covered);
-    atomicAdd(&c->fragments_shaded, (unsigned long long)shaded);
+    Vb200DrawCounters::Slot &s = c->slot[blockIdx.x & (VB200_COUNTER_SLOTS - 1)];
+    atomicAdd(&s.fragments_covered, (unsigned long long)covered);
+    atomicAdd(&s.fragments_shaded, (unsigned long long)shaded);
   }
 }
 

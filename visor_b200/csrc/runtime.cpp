@@ -1212,12 +1212,13 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   const uint32_t W = s->color.width, H = s->color.height;
   const uint32_t tilesX = (W + VB200_TILE - 1) / VB200_TILE, tilesY = (H + VB200_TILE - 1) / VB200_TILE;
   const uint32_t ntiles = tilesX * tilesY;
+  const uint32_t ntilesPad = (ntiles + 4095u) & ~4095u;    // the scan kernel moves 16-byte vectors
   // tile-list capacity is a guess (the pair total is only known on the device): 4 pairs per triangle
   // covers every triangle smaller than a tile; kernels that find it too small do nothing and are rerun
   const size_t listGuess = std::max<size_t>(g.list.cap, (size_t)numTris * 4 + 65536);
   if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * pipe->nslots) || !g.setup.reserve(numTris) ||
-     !g.triTiles.reserve(numTris) || !g.list.reserve(listGuess) || !g.tileCount.reserve(ntiles) ||
-     !g.tileOffset.reserve(ntiles) || !g.tileCursor.reserve(ntiles))
+     !g.triTiles.reserve(numTris) || !g.list.reserve(listGuess) || !g.tileCount.reserve(ntilesPad) ||
+     !g.tileOffset.reserve(ntilesPad) || !g.tileCursor.reserve(ntilesPad))
   {
     g.stickyCuda = 1;
     return setError(VB200_ERR_CUDA, "out of device memory for draw scratch");
@@ -1303,7 +1304,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.tiles_y = tilesY;
   sp.owner_rank = g.ownerRank;
   sp.owner_world = g.ownerWorld;
-  CU(cudaMemsetAsync(g.tileCount.p, 0, ntiles * sizeof(uint32_t), g.stream));
+  CU(cudaMemsetAsync(g.tileCount.p, 0, ntilesPad * sizeof(uint32_t), g.stream));
   g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);
 
   // Raster back end. A pass is order-independent ("resolvable") unless it blends or runs
@@ -1564,13 +1565,17 @@ int vb200_get_stats(vb200_stats *out)
   int rc = requireReady();
   if(rc)
     return rc;
-  Vb200DrawCounters c;
+  static Vb200DrawCounters c;
   CU(cudaMemcpyAsync(&c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   *out = g.stats;
-  out->triangles_out = c.triangles_out;
-  out->fragments_covered = c.fragments_covered;
-  out->fragments_shaded = c.fragments_shaded;
+  out->triangles_out = out->fragments_covered = out->fragments_shaded = 0;
+  for(int i = 0; i < VB200_COUNTER_SLOTS; i++)
+  {
+    out->triangles_out += c.slot[i].triangles_out;
+    out->fragments_covered += c.slot[i].fragments_covered;
+    out->fragments_shaded += c.slot[i].fragments_shaded;
+  }
   return VB200_OK;
 }
 
