@@ -99,6 +99,16 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant (tile) kernel, from the
+# `ncu --set full` captures summarised under profiles/ (a profiler cannot run inside the timed bench, so
+# the per-launch figure of the same build and workload is recorded here; null when none was captured).
+NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_c3_resolve.txt, profiles/r01_ncu_c4_ordered.txt (ncu --set full, per launch)"
+NCU_TRAFFIC = {
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 52638976 + 18938112,
+    ("c4", 1, "vb200_k_tile_ordered"): 40868352 + 384768,
+}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -411,6 +421,8 @@ def run_ours(args, workload: str) -> None:
                    "host_cpus": os.cpu_count()}
             parity = "bit-exact vs reference serial path" if r["hash"] == img_hash else "MISMATCH vs reference"
 
+    L.vb200_last_tile_kernel.restype = C.c_char_p
+    tile_kernel = (L.vb200_last_tile_kernel() or b"").decode()
     peak, peak_src = measured_peak_gbs()
     px = scene.width * scene.height
     per_px = 8 if scene.depth else 4
@@ -436,7 +448,9 @@ def run_ours(args, workload: str) -> None:
                       "triangles_out": st["triangles_out"], "tile_pairs": st["tile_pairs"]},
         "phase_ms": phase,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": "vb200_k_tile_ordered",
+                     "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((workload, world, tile_kernel)),
+                     "traffic_source": NCU_TRAFFIC_SOURCE if (workload, world, tile_kernel) in NCU_TRAFFIC else None,
+                     "kernel": tile_kernel,
                      "algorithmic_bytes": tile_bytes, "kernel_ms": tiles_ms, "peak_source": peak_src,
                      "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_gbs, "frac": frame_gbs / peak}},
         "e2e": {"value": tris / t_e2e / 1e6, "unit": "Mtri/s", "ms_per_step": t_e2e * 1e3,

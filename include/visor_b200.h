@@ -246,6 +246,9 @@ VB200_API void vb200_reset_stats(void);
 VB200_API void *vb200_stream(void);                /* cudaStream_t the library launches on */
 VB200_API const char *vb200_last_error(void);
 VB200_API int vb200_abi_version(void);
+/* Name of the tile kernel the most recent vb200_draw launched ("vb200_k_tile_ordered",
+ * "vb200_k_tile_resolve_min_first", ...; "" before the first draw). For benchmark reports. */
+VB200_API const char *vb200_last_tile_kernel(void);
 /* Tuning/debug knobs by name ("raster_path": 0 auto, 1 ordered tiles, 2 visibility resolve;
  * "count_fragments": 0/1, "time_kernels": 0/1). Unknown names return VB200_ERR_INVALID. */
 VB200_API int vb200_set_option(const char *name, int64_t value);

@@ -26,12 +26,21 @@ def raster_path(request, gpu):
 def _check(gpu, vor, sc, exact=True):
     c_gpu, d_gpu = scenes.render(gpu, sc)
     c_cpu, d_cpu = scenes.render(vor, sc)
+    def where(mask):
+        ys, xs = np.nonzero(mask)
+        return f"x {xs.min()}..{xs.max()}, y {ys.min()}..{ys.max()}, first at ({xs[0]},{ys[0]})"
+
     if d_cpu is not None:
-        bad = (d_gpu.view(np.uint32) != d_cpu.view(np.uint32)).sum()
-        assert bad == 0, f"{sc.name}: {bad} depth words differ"
+        badmask = d_gpu.view(np.uint32) != d_cpu.view(np.uint32)
+        bad = badmask.sum()
+        assert bad == 0, (f"{sc.name}: {bad} depth words differ ({where(badmask.reshape(sc.height, sc.width))}); "
+                          f"gpu {d_gpu[badmask][:4]} cpu {d_cpu[badmask][:4]}")
     diff = np.abs(c_gpu.astype(np.int16) - c_cpu.astype(np.int16))
     if exact:
-        assert diff.max() == 0, f"{sc.name}: {(diff > 0).any(-1).sum()} pixels differ (max {diff.max()} LSB)"
+        badmask = (diff > 0).any(-1)
+        assert diff.max() == 0, (f"{sc.name}: {badmask.sum()} pixels differ (max {diff.max()} LSB; "
+                                 f"{where(badmask.reshape(sc.height, sc.width))}); gpu {c_gpu[badmask][:3].tolist()} "
+                                 f"cpu {c_cpu[badmask][:3].tolist()}")
     else:
         assert diff.max() <= 1, f"{sc.name}: max colour difference {diff.max()} LSB"
     return float((diff > 0).any(-1).mean())

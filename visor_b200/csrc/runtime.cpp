@@ -2,7 +2,7 @@
 //
 // Host side of the B200 draw path: owns the CUDA stream, the HBM mirrors of the application's host
 // memory (VkDeviceMemory semantics, memory.cpp:5-41), the per-pipeline JIT cache
-// (SPIR-V -> PTX -> nvJitLink -> cudaLibrary) and the launch sequence that replaces DrawTriangles
+// (SPIR-V -> PTX -> ptxas -> cudaLibrary) and the launch sequence that replaces DrawTriangles
 // (rasterizer.cpp:363-520):
 //
 //   [index range] -> K1 vertex (JIT) -> K2 setup+count -> scan -> fill -> per-tile sort -> K4 tiles (JIT)
@@ -11,8 +11,7 @@
 // returns VB200_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
-#define NVJITLINK_NO_INLINE    // types/enums only: the library is bound at run time (see NvJitLinkApi)
-#include <nvJitLink.h>
+#include <nvPTXCompiler.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,8 +27,8 @@
 #include "kernels.h"
 #include "spirv_ptx.h"
 
-extern "C" const unsigned char vb200_scaffold_cubin[];
-extern "C" const unsigned long long vb200_scaffold_cubin_size;
+extern "C" const char vb200_scaffold_ptx[];
+extern "C" const unsigned long long vb200_scaffold_ptx_size;
 
 struct vb200_entry
 {
@@ -59,12 +58,28 @@ int setError(int code, const char *fmt, ...)
   return code;
 }
 
-struct Pipeline
+// The kernels of scaffold.cu. Each is compiled per shader function: K_VERTEX with a vertex entry, the
+// tile kernels with a fragment entry, on first use.
+enum
+{
+  K_VERTEX = 0,
+  K_TILE_ORDERED = 1,
+  K_TILE_RESOLVE = 2,    // + resolve mode 0..4
+  K_COUNT = 7
+};
+const char *const kKernelNames[K_COUNT] = {
+    "vb200_k_vertex",
+    "vb200_k_tile_ordered",
+    "vb200_k_tile_resolve_min_first",
+    "vb200_k_tile_resolve_min_last",
+    "vb200_k_tile_resolve_max_first",
+    "vb200_k_tile_resolve_max_last",
+    "vb200_k_tile_resolve_last_wins",
+};
+struct JitKernel
 {
   cudaLibrary_t lib = nullptr;
-  cudaKernel_t k_vertex = nullptr, k_tile_ordered = nullptr;
-  cudaKernel_t k_tile_resolve[5] = {};
-  uint32_t nslots = 1;
+  cudaKernel_t kernel = nullptr;
 };
 
 struct Mirror
@@ -118,7 +133,7 @@ struct Context
   uint64_t epoch = 1;
   std::map<uintptr_t, Mirror> mirrors;
   std::vector<uint8_t *> zombies;    // device memory of merged mirrors, freed at the next flush
-  std::map<std::pair<uint64_t, uint64_t>, Pipeline> pipelines;
+  std::map<std::pair<uint64_t, int>, JitKernel> kernels;    // (shader entry serial, K_*) -> loaded kernel
   // scratch
   DevBuf<Vb200RasterVertex> rv;
   DevBuf<float4> interps;
@@ -142,6 +157,7 @@ struct Context
   // fused sort-first exchange: colour target (device address on this rank) -> the same image on the peers
   std::map<uint8_t *, std::vector<uint32_t *>> peerTargets;
   Vb200DrawCounters *counters = nullptr;    // device
+  const char *lastTileKernel = "";
   vb200_stats stats;
   uint32_t ownerRank = 0, ownerWorld = 1;
   int64_t optRasterPath = 0, optCountFragments = 0, optTimeKernels = 0;
@@ -364,166 +380,180 @@ int resolve(const void *ptr, size_t size, int access, uint8_t **out)
 }
 
 // ---- JIT -------------------------------------------------------------------------------------
-// nvJitLink is bound with dlopen/dlsym instead of a link-time dependency: a host process may already
-// have mapped ANOTHER libnvJitLink.so.12 (PyTorch wheels bundle the 12.8 one), whose versioned symbols
-// (__nvJitLinkCreate_12_8) would shadow the 12.9 ones this library was built against and cannot link
-// cubins produced by nvcc 12.9. Opening the toolkit's copy by absolute path gives a private instance.
-struct NvJitLinkApi
+// ---- kernel + shader -> cubin --------------------------------------------------------------------
+// scaffold.cu is shipped as PTX. A shader function (vb200_vs / vb200_fs, PTX from spirv_ptx.cpp) is
+// spliced into the text of the ONE kernel that calls it and the module is compiled whole by ptxas
+// (the nvPTXCompiler library, linked statically: no toolkit or driver JIT is needed at run time). Compared with linking a prebuilt cubin against the shader, the call disappears: ptxas inlines
+// the shader, schedules its loads across the kernel's unrolled pixel rows, turns its reads of the
+// kernel-parameter environment into constant-bank loads and allocates registers for the whole (the
+// C3 resolve kernel drops from 54 to 45 registers, the vertex kernel from 62 + a stack frame to 34).
+struct ScaffoldText
 {
-  void *lib = nullptr;
-  nvJitLinkResult (*create)(nvJitLinkHandle *, uint32_t, const char **) = nullptr;
-  nvJitLinkResult (*destroy)(nvJitLinkHandle *) = nullptr;
-  nvJitLinkResult (*addData)(nvJitLinkHandle, nvJitLinkInputType, const void *, size_t, const char *) = nullptr;
-  nvJitLinkResult (*complete)(nvJitLinkHandle) = nullptr;
-  nvJitLinkResult (*getCubinSize)(nvJitLinkHandle, size_t *) = nullptr;
-  nvJitLinkResult (*getCubin)(nvJitLinkHandle, void *) = nullptr;
-  nvJitLinkResult (*getLogSize)(nvJitLinkHandle, size_t *) = nullptr;
-  nvJitLinkResult (*getLog)(nvJitLinkHandle, char *) = nullptr;
-  std::string path;
-} nvj;
+  bool parsed = false, ok = false;
+  std::string prologue;    // .version/.target, shared-memory declarations
+  std::string helpers;     // vb200_fetch_attr, vb200_sample_tex, vb200_sample_cube
+  std::string entries[K_COUNT];
+  std::string epilogue;    // .section .debug_str: names the -lineinfo .loc directives refer to
+} scaffold;
 
-bool loadNvJitLink()
+// removes every `.extern .func ... ;` prototype (the definitions are spliced in instead)
+void stripExternFuncs(std::string &t)
 {
-  if(nvj.create)
-    return true;
-  std::vector<std::string> candidates;
-  if(const char *e = getenv("VB200_NVJITLINK"))
-    candidates.push_back(e);
-  if(const char *e = getenv("CUDA_HOME"))
-    candidates.push_back(std::string(e) + "/lib64/libnvJitLink.so.12");
-  candidates.push_back("/usr/local/cuda/lib64/libnvJitLink.so.12");
-  candidates.push_back("/usr/local/cuda-12.9/lib64/libnvJitLink.so.12");
-  candidates.push_back("libnvJitLink.so.12");
-  for(const std::string &c : candidates)
+  for(size_t at = t.find(".extern .func"); at != std::string::npos; at = t.find(".extern .func", at))
   {
-    void *lib = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
-    if(!lib)
-      continue;
-    auto sym = [&](const char *base) -> void * {
-      // newest first: the cubins this library embeds come from nvcc 12.9
-      for(const char *suffix : {"_12_9", "_12_8", "_12_6", "_12_4", "_12_0", ""})
-      {
-        std::string n = suffix[0] ? std::string("__") + base + suffix : std::string(base);
-        if(void *p = dlsym(lib, n.c_str()))
-          return p;
-      }
-      return nullptr;
-    };
-    NvJitLinkApi a;
-    a.lib = lib;
-    a.create = (decltype(a.create))sym("nvJitLinkCreate");
-    a.destroy = (decltype(a.destroy))sym("nvJitLinkDestroy");
-    a.addData = (decltype(a.addData))sym("nvJitLinkAddData");
-    a.complete = (decltype(a.complete))sym("nvJitLinkComplete");
-    a.getCubinSize = (decltype(a.getCubinSize))sym("nvJitLinkGetLinkedCubinSize");
-    a.getCubin = (decltype(a.getCubin))sym("nvJitLinkGetLinkedCubin");
-    a.getLogSize = (decltype(a.getLogSize))sym("nvJitLinkGetErrorLogSize");
-    a.getLog = (decltype(a.getLog))sym("nvJitLinkGetErrorLog");
-    if(a.create && a.destroy && a.addData && a.complete && a.getCubinSize && a.getCubin && a.getLogSize && a.getLog)
-    {
-      a.path = c;
-      nvj = a;
-      return true;
-    }
-    dlclose(lib);
+    const size_t end = t.find(';', at);
+    if(end == std::string::npos)
+      break;
+    t.erase(at, end + 1 - at);
   }
-  return false;
 }
 
-// nvJitLink step: scaffold cubin + VS PTX + FS PTX -> one sm_100a cubin. Needs no device.
-int linkCubin(const vb200_entry *vs, const vb200_entry *fs, std::vector<char> &cubin)
+bool parseScaffold()
 {
-  if(!loadNvJitLink())
-    return setError(VB200_ERR_LINK, "libnvJitLink.so.12 (CUDA 12.9) not found; set VB200_NVJITLINK to its path");
-  auto nvJitLinkCreate = nvj.create;
-  auto nvJitLinkDestroy = nvj.destroy;
-  auto nvJitLinkAddData = nvj.addData;
-  auto nvJitLinkComplete = nvj.complete;
-  auto nvJitLinkGetLinkedCubinSize = nvj.getCubinSize;
-  auto nvJitLinkGetLinkedCubin = nvj.getCubin;
-  auto nvJitLinkGetErrorLogSize = nvj.getLogSize;
-  auto nvJitLinkGetErrorLog = nvj.getLog;
-  nvJitLinkHandle h;
-  std::string maxreg;
-  const char *opts[3] = {"-arch=sm_100a", "-lineinfo", nullptr};
-  uint32_t nopts = 2;
-  if(const char *mr = getenv("VB200_JIT_MAXRREGCOUNT"))    // tuning aid: cap the shader functions' registers
+  if(scaffold.parsed)
+    return scaffold.ok;
+  scaffold.parsed = true;
+  std::string t(vb200_scaffold_ptx, (size_t)vb200_scaffold_ptx_size);
+  while(!t.empty() && t.back() == '\0')
+    t.pop_back();
+  stripExternFuncs(t);
+  const size_t dbg = t.find("\n\t.section\t.debug_str");
+  if(dbg != std::string::npos)
   {
-    maxreg = std::string("-maxrregcount=") + mr;
+    scaffold.epilogue = t.substr(dbg + 1);
+    t.erase(dbg + 1);
+  }
+  const size_t firstEntry = t.find("\n.visible .entry ");
+  size_t firstFunc = std::string::npos;
+  for(const char *pat : {"\n.visible .func", "\n.func", "\n.weak .func"})
+    firstFunc = std::min(firstFunc, t.find(pat));
+  if(firstEntry == std::string::npos || firstFunc == std::string::npos || firstFunc > firstEntry)
+    return false;
+  scaffold.prologue = t.substr(0, firstFunc + 1);
+  scaffold.helpers = t.substr(firstFunc + 1, firstEntry - firstFunc);
+  for(size_t at = firstEntry; at != std::string::npos;)
+  {
+    const size_t next = t.find("\n.visible .entry ", at + 1);
+    const size_t nameAt = at + strlen("\n.visible .entry ");
+    const std::string name = t.substr(nameAt, t.find('(', nameAt) - nameAt);
+    const std::string body = t.substr(at + 1, (next == std::string::npos ? t.size() : next) - at);
+    if(body.find("\n.func") != std::string::npos || body.find("\n.visible .func") != std::string::npos)
+      return false;    // layout assumption broken: a function defined between kernels
+    for(int k = 0; k < K_COUNT; k++)
+      if(name == kKernelNames[k])
+        scaffold.entries[k] = body;
+    at = next;
+  }
+  for(int k = 0; k < K_COUNT; k++)
+    if(scaffold.entries[k].empty())
+      return false;
+  scaffold.ok = true;
+  return true;
+}
+
+// ptxas step: kernel text + shader function -> one sm_100a cubin. Needs no device.
+int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin)
+{
+  if(!parseScaffold())
+    return setError(VB200_ERR_LINK, "embedded kernel scaffold PTX has an unexpected layout");
+  std::string body = shader->e.ptx;
+  for(const char *directive : {".version", ".target", ".address_size"})
+  {
+    const size_t at = body.find(directive);
+    if(at != std::string::npos)
+      body.erase(at, body.find('\n', at) - at);
+  }
+  stripExternFuncs(body);
+  std::string text;
+  text.reserve(scaffold.prologue.size() + scaffold.helpers.size() + body.size() + scaffold.entries[which].size() +
+               scaffold.epilogue.size() + 16);
+  text += scaffold.prologue;
+  text += scaffold.helpers;
+  text += body;
+  text += "\n";
+  text += scaffold.entries[which];
+  text += scaffold.epilogue;
+
+  nvPTXCompilerHandle h;
+  if(nvPTXCompilerCreate(&h, text.size(), text.c_str()) != NVPTXCOMPILE_SUCCESS)
+    return setError(VB200_ERR_LINK, "nvPTXCompilerCreate failed");
+  std::string maxreg;
+  const char *opts[4] = {"--gpu-name=sm_100a", "--generate-line-info", nullptr, nullptr};
+  int nopts = 2;
+  if(const char *mr = getenv("VB200_JIT_MAXRREGCOUNT"))    // tuning aid
+  {
+    maxreg = std::string("--maxrregcount=") + mr;
     opts[nopts++] = maxreg.c_str();
   }
-  if(nvJitLinkCreate(&h, nopts, opts) != NVJITLINK_SUCCESS)
-    return setError(VB200_ERR_LINK, "nvJitLinkCreate failed");
-  auto logOf = [&](std::string &s) {
-    size_t n = 0;
-    if(nvJitLinkGetErrorLogSize(h, &n) == NVJITLINK_SUCCESS && n > 1)
-    {
-      s.resize(n);
-      nvJitLinkGetErrorLog(h, &s[0]);
-    }
-  };
-  nvJitLinkResult r = nvJitLinkAddData(h, NVJITLINK_INPUT_CUBIN, vb200_scaffold_cubin,
-                                       (size_t)vb200_scaffold_cubin_size, "scaffold");
-  if(r == NVJITLINK_SUCCESS)
-    r = nvJitLinkAddData(h, NVJITLINK_INPUT_PTX, vs->e.ptx.c_str(), vs->e.ptx.size() + 1, "vs");
-  if(r == NVJITLINK_SUCCESS)
-    r = nvJitLinkAddData(h, NVJITLINK_INPUT_PTX, fs->e.ptx.c_str(), fs->e.ptx.size() + 1, "fs");
-  if(r == NVJITLINK_SUCCESS)
-    r = nvJitLinkComplete(h);
-  if(r != NVJITLINK_SUCCESS)
+  const nvPTXCompileResult r = nvPTXCompilerCompile(h, nopts, opts);
+  if(r != NVPTXCOMPILE_SUCCESS)
   {
     std::string log;
-    logOf(log);
-    nvJitLinkDestroy(&h);
-    return setError(VB200_ERR_LINK, "nvJitLink failed (%d): %s", (int)r, log.c_str());
+    size_t n = 0;
+    if(nvPTXCompilerGetErrorLogSize(h, &n) == NVPTXCOMPILE_SUCCESS && n > 0)
+    {
+      log.resize(n + 1);
+      nvPTXCompilerGetErrorLog(h, &log[0]);
+    }
+    nvPTXCompilerDestroy(&h);
+    return setError(VB200_ERR_LINK, "ptxas failed on %s (%d): %s", kKernelNames[which], (int)r, log.c_str());
   }
   size_t sz = 0;
-  nvJitLinkGetLinkedCubinSize(h, &sz);
+  nvPTXCompilerGetCompiledProgramSize(h, &sz);
   cubin.resize(sz);
-  nvJitLinkGetLinkedCubin(h, cubin.data());
-  nvJitLinkDestroy(&h);
+  nvPTXCompilerGetCompiledProgram(h, cubin.data());
+  nvPTXCompilerDestroy(&h);
+  if(const char *prefix = getenv("VB200_DUMP_CUBIN"))
+  {
+    // developer aid: keep the cubin for cuobjdump -sass / -res-usage: <prefix>.<kernel>.cubin
+    const std::string path = std::string(prefix) + "." + kKernelNames[which] + ".cubin";
+    if(FILE *f = fopen(path.c_str(), "wb"))
+    {
+      fwrite(cubin.data(), 1, cubin.size(), f);
+      fclose(f);
+    }
+  }
   return VB200_OK;
 }
 
-int linkPipeline(const vb200_entry *vs, const vb200_entry *fs, Pipeline **out)
+// the loaded kernel `which` specialised for `shader`, compiled on first use
+int getKernel(int which, const vb200_entry *shader, cudaKernel_t *out)
 {
-  auto key = std::make_pair(vs->serial, fs->serial);
-  auto it = g.pipelines.find(key);
-  if(it != g.pipelines.end())
+  const auto key = std::make_pair(shader->serial, which);
+  auto it = g.kernels.find(key);
+  if(it != g.kernels.end())
   {
-    *out = &it->second;
+    *out = it->second.kernel;
     return VB200_OK;
   }
   std::vector<char> cubin;
-  int lrc = linkCubin(vs, fs, cubin);
-  if(lrc)
-    return lrc;
-
-  Pipeline p;
-  cudaError_t e = cudaLibraryLoadData(&p.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  int rc = compileKernel(which, shader, cubin);
+  if(rc)
+    return rc;
+  JitKernel jk;
+  cudaError_t e = cudaLibraryLoadData(&jk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if(e != cudaSuccess)
     return setError(VB200_ERR_LINK, "cudaLibraryLoadData failed: %s", cudaGetErrorString(e));
-  e = cudaLibraryGetKernel(&p.k_vertex, p.lib, "vb200_k_vertex");
-  if(e == cudaSuccess)
-    e = cudaLibraryGetKernel(&p.k_tile_ordered, p.lib, "vb200_k_tile_ordered");
-  static const char *resolveNames[5] = {"vb200_k_tile_resolve_min_first", "vb200_k_tile_resolve_min_last",
-                                        "vb200_k_tile_resolve_max_first", "vb200_k_tile_resolve_max_last",
-                                        "vb200_k_tile_resolve_last_wins"};
-  for(int i = 0; i < 5 && e == cudaSuccess; i++)
-    e = cudaLibraryGetKernel(&p.k_tile_resolve[i], p.lib, resolveNames[i]);
+  e = cudaLibraryGetKernel(&jk.kernel, jk.lib, kKernelNames[which]);
   if(e != cudaSuccess)
   {
-    cudaLibraryUnload(p.lib);
-    return setError(VB200_ERR_LINK, "cudaLibraryGetKernel failed: %s", cudaGetErrorString(e));
+    cudaLibraryUnload(jk.lib);
+    return setError(VB200_ERR_LINK, "cudaLibraryGetKernel(%s) failed: %s", kKernelNames[which], cudaGetErrorString(e));
   }
-  uint32_t mask = vs->e.out_slot_mask | fs->e.in_slot_mask;
-  p.nslots = 1;
+  g.kernels.emplace(key, jk);
+  *out = jk.kernel;
+  return VB200_OK;
+}
+
+// interpolant slots a (VS, FS) pair moves per vertex
+uint32_t pipelineSlots(const vb200_entry *vs, const vb200_entry *fs)
+{
+  const uint32_t mask = vs->e.out_slot_mask | fs->e.in_slot_mask;
+  uint32_t nslots = 1;
   for(uint32_t s = 0; s < VB200_MAX_SLOTS; s++)
     if(mask & (1u << s))
-      p.nslots = s + 1;
-  auto ins = g.pipelines.emplace(key, p);
-  *out = &ins.first->second;
-  return VB200_OK;
+      nslots = s + 1;
+  return nslots;
 }
 
 uint32_t formatBytes(uint32_t fmt)
@@ -639,6 +669,11 @@ int checkTarget(const vb200_image *im, const char *what)
 // =================================================================================================
 extern "C" {
 
+const char *vb200_last_tile_kernel(void)
+{
+  return g.lastTileKernel;
+}
+
 int vb200_abi_version(void)
 {
   return VB200_ABI_VERSION;
@@ -684,9 +719,9 @@ void vb200_shutdown(void)
   if(!g.ready)
     return;
   cudaStreamSynchronize(g.stream);
-  for(auto &kv : g.pipelines)
+  for(auto &kv : g.kernels)
     cudaLibraryUnload(kv.second.lib);
-  g.pipelines.clear();
+  g.kernels.clear();
   for(auto &kv : g.mirrors)
   {
     if(kv.second.pinned)
@@ -758,18 +793,18 @@ void vb200_shader_destroy(vb200_shader *shader)
 {
   if(!shader)
     return;
-  // drop pipelines linked from this module's entries
+  // drop the kernels compiled for this module's entries
   for(auto &e : shader->entries)
-    for(auto it = g.pipelines.begin(); it != g.pipelines.end();)
+    for(auto it = g.kernels.begin(); it != g.kernels.end();)
     {
-      if(it->first.first == e->serial || it->first.second == e->serial)
+      if(it->first.first == e->serial)
       {
         if(g.ready)
         {
           cudaStreamSynchronize(g.stream);
           cudaLibraryUnload(it->second.lib);
         }
-        it = g.pipelines.erase(it);
+        it = g.kernels.erase(it);
       }
       else
         ++it;
@@ -781,20 +816,19 @@ int vb200_link_check(const vb200_entry *vs, const vb200_entry *fs, uint64_t *cub
 {
   if(!vs || !fs || vs->e.stage != vb200::STAGE_VERTEX || fs->e.stage != vb200::STAGE_FRAGMENT)
     return setError(VB200_ERR_INVALID, "link_check needs one vertex and one fragment entry");
-  std::vector<char> cubin;
-  int rc = linkCubin(vs, fs, cubin);
-  if(rc == VB200_OK && cubin_size)
-    *cubin_size = cubin.size();
-  if(rc == VB200_OK && getenv("VB200_DUMP_CUBIN"))
+  // every kernel a draw with this pair can launch (a draw itself compiles only the ones it uses)
+  uint64_t total = 0;
+  for(int k = 0; k < K_COUNT; k++)
   {
-    // developer aid: keep the linked cubin for cuobjdump -sass / -res-usage
-    if(FILE *f = fopen(getenv("VB200_DUMP_CUBIN"), "wb"))
-    {
-      fwrite(cubin.data(), 1, cubin.size(), f);
-      fclose(f);
-    }
+    std::vector<char> cubin;
+    int rc = compileKernel(k, k == K_VERTEX ? vs : fs, cubin);
+    if(rc)
+      return rc;
+    total += cubin.size();
   }
-  return rc;
+  if(cubin_size)
+    *cubin_size = total;
+  return VB200_OK;
 }
 
 const char *vb200_entry_ptx(const vb200_entry *entry)
@@ -1121,9 +1155,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     return VB200_OK;
   const uint32_t usedVerts = pl->topology == 3u ? numTris * 3u : numTris + 2u;
 
-  Pipeline *pipe = nullptr;
-  if((rc = linkPipeline(pl->vs, pl->fs, &pipe)))
-    return rc;
+  const uint32_t nslots = pipelineSlots(pl->vs, pl->fs);
 
   // ---- environment (device-side GPUState)
   Vb200Env env;
@@ -1216,7 +1248,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   // tile-list capacity is a guess (the pair total is only known on the device): 4 pairs per triangle
   // covers every triangle smaller than a tile; kernels that find it too small do nothing and are rerun
   const size_t listGuess = std::max<size_t>(g.list.cap, (size_t)numTris * 4 + 65536);
-  if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * pipe->nslots) || !g.setup.reserve(numTris) ||
+  if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * nslots) || !g.setup.reserve(numTris) ||
      !g.triTiles.reserve(numTris) || !g.list.reserve(listGuess) || !g.tileCount.reserve(ntilesPad) ||
      !g.tileOffset.reserve(ntilesPad) || !g.tileCursor.reserve(ntilesPad))
   {
@@ -1269,12 +1301,15 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   vp.count = capacity;
   vp.rv = g.rv.p;
   vp.interps = g.interps.p;
-  vp.nslots = pipe->nslots;
+  vp.nslots = nslots;
   vp.width = W;
   vp.height = H;
   {
+    cudaKernel_t kVertex = nullptr;
+    if((rc = getKernel(K_VERTEX, pl->vs, &kVertex)))
+      return rc;
     void *args[] = {&env, &vp};
-    if((rc = launchKernel(pipe->k_vertex, dim3((capacity + 127) / 128), dim3(128), args)))
+    if((rc = launchKernel(kVertex, dim3((capacity + 127) / 128), dim3(128), args)))
       return rc;
   }
 
@@ -1330,6 +1365,11 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   }
   if(g.optRasterPath == 1)
     resolveMode = -1;
+  const int tileKernelId = resolveMode >= 0 ? K_TILE_RESOLVE + resolveMode : K_TILE_ORDERED;
+  cudaKernel_t kTile = nullptr;
+  if((rc = getKernel(tileKernelId, pl->fs, &kTile)))
+    return rc;
+  g.lastTileKernel = kKernelNames[tileKernelId];
 
   Vb200TileParams tp;
   memset(&tp, 0, sizeof(tp));
@@ -1352,7 +1392,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.rs.src_factor = pl->src_color_blend_factor;
   tp.rs.dst_factor = pl->dst_color_blend_factor;
   tp.rs.blend_op = pl->color_blend_op;
-  tp.rs.nslots = pipe->nslots;
+  tp.rs.nslots = nslots;
   tp.rs.owner_rank = g.ownerRank;
   tp.rs.owner_world = g.ownerWorld;
   tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
@@ -1392,8 +1432,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
       phaseMark(3);
     {
       void *args[] = {&env, &tp};
-      cudaKernel_t k = resolveMode >= 0 ? pipe->k_tile_resolve[resolveMode] : pipe->k_tile_ordered;
-      if((rc = launchKernel(k, dim3(ntiles), dim3(256), args)))
+      if((rc = launchKernel(kTile, dim3(ntiles), dim3(256), args)))
         return rc;
     }
     if(attempt == 1)

@@ -418,7 +418,7 @@ struct TriCoef
 __device__ __forceinline__ uint32_t vb200_depth_key(float d)
 {
   const uint32_t b = __float_as_uint(__fadd_rn(d, 0.0f));    // -0 + 0 = +0; every other value unchanged
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return b ^ ((uint32_t)((int)b >> 31) | 0x80000000u);       // negative: flip all bits; else set the sign bit
 }
 
 template <int MODE>
@@ -582,28 +582,40 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         }
         owner0 = lo;
       }
+      // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
+      // work of step s, so it is issued first each iteration: its shared-memory round trip and the
+      // warp reductions overlap the coverage / depth arithmetic instead of heading the next iteration.
+      uint32_t starts, nextOwner0;
+      {
+        const uint32_t rel = s_start[min(owner0 + 1u + (uint32_t)lane, 256u)] - (firstStep << 5);
+        starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+        nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
+      }
       for(uint32_t step = firstStep; step < lastStep; step++)
       {
         const uint32_t k = step << 5;
-        // lane l looks at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
-        const uint32_t rel = s_start[min(owner0 + 1u + (uint32_t)lane, 256u)] - k;
-        const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-        const uint32_t nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
         const uint32_t g = k + lane;
-        const uint32_t owner = owner0 + __popc(starts & (0xffffffffu >> (31 - lane)));
+        // lane l looked at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
+        const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), 255u);
         owner0 = nextOwner0;
-        if(g >= total)
-          continue;
+        {
+          const uint32_t rel = s_start[min(owner0 + 1u + (uint32_t)lane, 256u)] - (k + 32u);
+          starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+          nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
+        }
+        const bool valid = g < total;
         const int4 c0 = s_coef[owner][0], c1 = s_coef[owner][1], c3 = s_coef[owner][3];
-        const int li = (int)(g - (uint32_t)c3.y);
+        const int li = valid ? (int)(g - (uint32_t)c3.y) : 0;
         const int yq = (int)(((uint32_t)li * (uint32_t)c3.w) >> 16);
         const int b1 = c0.x * li + c0.y * yq + c0.z;
         const int b2 = c0.w * li + c1.x * yq + c1.y;
         const int b0 = c1.z - (b1 + b2);
-        if((b0 | b1 | b2) < 0)
+        const int idx = c1.w + li + yq * c3.z;
+        // the slot's current key is fetched before the depth arithmetic that decides whether it is needed
+        unsigned long long seen = vis[idx];
+        if(!valid || (b0 | b1 | b2) < 0)
           continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
         covered++;
-        const int idx = c1.w + li + yq * c3.z;
         const uint32_t id = (uint32_t)c3.x;
         unsigned long long key;
         if(MODE == VB200_RES_LAST_WINS && !depthTest)
@@ -634,8 +646,15 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
             key = ((unsigned long long)dk << 32) | low;
           }
         }
-        if(key < vis[idx])
-          atomicMin(&vis[idx], key);
+        // 64-bit min in shared memory has no native atomic: CAS until the slot holds a key <= ours
+        // (the common case is no attempt at all, or one that succeeds)
+        while(key < seen)
+        {
+          const unsigned long long prev = atomicCAS(&vis[idx], seen, key);
+          if(prev == seen)
+            break;
+          seen = prev;
+        }
       }
     }
   }
