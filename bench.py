@@ -266,7 +266,6 @@ def run_ours(args, workload: str) -> None:
             color_t = torch.empty(npx, dtype=torch.int32, device="cuda")
         depth_t = torch.empty(npx, dtype=torch.float32, device="cuda")
         bound = scenes.BoundScene(gpu, scene, color_device_ptr=color_t.data_ptr(), depth_device_ptr=depth_t.data_ptr())
-        color_host = torch.empty(npx, dtype=torch.int32, pin_memory=True)
         if not fused:
             slots = L.vb200_tiles_per_rank(scene.width, scene.height, world)
             send = torch.empty(slots * 4096, dtype=torch.uint8, device="cuda")
@@ -363,17 +362,68 @@ def run_ours(args, workload: str) -> None:
     L.vb200_set_option(b"count_fragments", 0)
 
     # ---------------- e2e: host buffers through the C-ABI, copies inside the timed region --------
-    gpu.check(L.vb200_set_sync_mode(0), "set_sync_mode")
     e2e_steps = max(3, min(args.steps, 10))
+    if not multi:
+        gpu.check(L.vb200_set_sync_mode(0), "set_sync_mode")
+    else:
+        # N>1: host<->device traffic is sharded like the frame. Every rank uploads 1/N of each input over
+        # ITS PCIe link and the slices are all-gathered into the HBM mirrors over NVLink (NCCL, in place);
+        # after the exchange every rank holds the whole image and copies its band of rows into one
+        # host buffer shared by all ranks (POSIX shared memory, page-locked in every process).
+        from multiprocessing import shared_memory
+
+        class _DevBytes:    # raw device range -> torch tensor (no copy)
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                                 "version": 2}
+
+        shards = []    # (host array, slice bytes, gathered device tensor, own slice view)
+        for a, is_in in bufs:
+            if not is_in:
+                continue
+            sl = (a.nbytes // world) & ~0xff
+            if sl < (1 << 16):
+                shards.append((a, 0, None, None))
+                continue
+            dev = L.vb200_mem_device_ptr(a.ctypes.data)
+            full = torch.as_tensor(_DevBytes(dev, sl * world), device="cuda")
+            shards.append((a, sl, full, full[rank * sl:(rank + 1) * sl]))
+        shm_name = f"vb200_bench_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=npx * 4)
+        dist.barrier()
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=shm_name)
+            try:    # rank 0 owns the segment; keep this process's resource tracker from unlinking it too
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
+        frame_host = np.ndarray((npx,), dtype=np.int32, buffer=shm.buf)
+        gpu.check(L.vb200_mem_register(frame_host.ctypes.data, frame_host.nbytes), "mem_register(shared frame)")
+        rows = (scene.height + world - 1) // world
+        band = slice(rank * rows * scene.width, min((rank + 1) * rows, scene.height) * scene.width)
+        band_host = torch.from_numpy(frame_host[band])
+        h2d_job = sum(a.nbytes for a, _, _, _ in shards)
+
     def step_e2e():
-        """one frame as an application sees it: inputs come from host memory (uploaded by the library),
-        the finished frame ends up in host memory (N>1: rank 0 reads the assembled image back)."""
+        """one frame as an application sees it: inputs come from host memory, the finished frame ends
+        up in host memory."""
+        if multi:
+            for a, sl, full, mine in shards:
+                if sl == 0:
+                    gpu.check(L.vb200_mem_upload(a.ctypes.data, a.nbytes), "mem_upload")
+                    continue
+                gpu.check(L.vb200_mem_upload(a.ctypes.data + rank * sl, sl), "mem_upload")
+                if a.nbytes > sl * world:    # remainder of the division: a few hundred bytes, every rank
+                    gpu.check(L.vb200_mem_upload(a.ctypes.data + sl * world, a.nbytes - sl * world), "mem_upload")
+                with torch.cuda.stream(ext):
+                    dist.all_gather_into_tensor(full, mine)
         bound.submit()
         if multi:
             exchange()
-            if rank == 0:
-                with torch.cuda.stream(ext):
-                    color_host.copy_(color_t, non_blocking=True)
+            with torch.cuda.stream(ext):
+                band_host.copy_(color_t[band], non_blocking=True)
         gpu.flush()
 
     for _ in range(2):
@@ -387,8 +437,9 @@ def run_ours(args, workload: str) -> None:
         torch.cuda.synchronize()
     t_e2e_local = (time.perf_counter() - t0) / e2e_steps
     st2 = gpu.stats()
-    if multi:
-        st2["d2h_bytes"] += npx * 4 * e2e_steps
+    if multi:    # whole-job bytes (all ranks together move each input and the image exactly once)
+        st2["h2d_bytes"] = h2d_job * e2e_steps
+        st2["d2h_bytes"] = npx * 4 * e2e_steps
     if multi:
         tt = torch.tensor([t_e2e_local], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -397,8 +448,15 @@ def run_ours(args, workload: str) -> None:
         t_e2e = t_e2e_local
     if multi:
         barrier()    # nobody tears down memory that peers may still be storing into
-        final = color_host.numpy().view(np.uint8).reshape(scene.height, scene.width, 4)
+        final = frame_host.copy().view(np.uint8).reshape(scene.height, scene.width, 4)
         img_hash = scenes.image_hash(final, None)
+        L.vb200_mem_unregister.argtypes = [C.c_void_p]
+        L.vb200_mem_unregister(frame_host.ctypes.data)
+        del band_host, frame_host
+        dist.barrier()
+        shm.close()
+        if rank == 0:
+            shm.unlink()
         dist.destroy_process_group()
         if rank != 0:
             return

@@ -393,7 +393,7 @@ struct ScaffoldText
   std::string prologue;    // .version/.target, shared-memory declarations
   std::string helpers;     // vb200_fetch_attr, vb200_sample_tex, vb200_sample_cube
   std::string entries[K_COUNT];
-  std::string epilogue;    // .section .debug_str: names the -lineinfo .loc directives refer to
+  std::string epilogue;    // .file table + .section .debug_str of the -lineinfo .loc directives
 } scaffold;
 
 // removes every `.extern .func ... ;` prototype (the definitions are spliced in instead)
@@ -417,7 +417,10 @@ bool parseScaffold()
   while(!t.empty() && t.back() == '\0')
     t.pop_back();
   stripExternFuncs(t);
-  const size_t dbg = t.find("\n\t.section\t.debug_str");
+  // trailer of the module: the .file table and .debug_str section the -lineinfo .loc directives use
+  size_t dbg = t.find("\n\t.file\t");
+  if(dbg == std::string::npos)
+    dbg = t.find("\n\t.section\t.debug_str");
   if(dbg != std::string::npos)
   {
     scaffold.epilogue = t.substr(dbg + 1);
@@ -471,7 +474,15 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
   text += scaffold.helpers;
   text += body;
   text += "\n";
-  text += scaffold.entries[which];
+  {
+    std::string entry = scaffold.entries[which];
+    // tuning aid: VB200_JIT_MINCTAS=<n> adds .minnctapersm to the tile kernels (occupancy experiments)
+    const char *mc = getenv("VB200_JIT_MINCTAS");
+    const size_t at = entry.find(".maxntid 256, 1, 1");
+    if(mc && which != K_VERTEX && at != std::string::npos)
+      entry.insert(at + strlen(".maxntid 256, 1, 1"), std::string("\n.minnctapersm ") + mc);
+    text += entry;
+  }
   text += scaffold.epilogue;
 
   nvPTXCompilerHandle h;
