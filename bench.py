@@ -245,12 +245,12 @@ def run_ours(args, workload: str) -> None:
     scene = build_scene(workload)
     tris = scene.triangles()
     npx = scene.width * scene.height
-    fused = False
+    fused = multicast = False
     if multi:
         gpu.check(L.vb200_set_tile_owner(rank, world), "set_tile_owner")
         ext = torch.cuda.ExternalStream(L.vb200_stream())
         L.vb200_set_peer_targets.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
-        if args.exchange == "fused":
+        if args.exchange in ("fused", "fused-p2p"):
             try:
                 import torch.distributed._symmetric_memory as symm
                 color_t = symm.empty(npx, dtype=torch.int32, device="cuda")
@@ -259,6 +259,11 @@ def run_ours(args, workload: str) -> None:
                 arr = (C.c_void_p * len(peers))(*peers)
                 gpu.check(L.vb200_set_peer_targets(color_t.data_ptr(), arr, len(peers)), "set_peer_targets")
                 fused = True
+                mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                if mc_ptr and args.exchange != "fused-p2p":
+                    L.vb200_set_multicast_target.argtypes = [C.c_void_p, C.c_void_p]
+                    gpu.check(L.vb200_set_multicast_target(color_t.data_ptr(), mc_ptr), "set_multicast_target")
+                    multicast = True
             except Exception as e:  # symmetric memory unavailable: NCCL all-gather baseline
                 if rank == 0:
                     print(f"bench: fused exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
@@ -496,7 +501,9 @@ def run_ours(args, workload: str) -> None:
         "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[workload], "triangles": tris,
                    "resolution": [scene.width, scene.height], "l2": "flushed (512 MB write) before each timed step",
-                   "parallelism": (f"sort-first x{world}, " + ("fused NVLink peer stores from the tile kernel + barrier"
+                   "parallelism": (f"sort-first x{world}, " + (("fused: one NVSwitch-multicast store per pixel from the tile kernel + barrier"
+                                                                 if multicast else
+                                                                 "fused: NVLink peer stores from the tile kernel + barrier")
                                                                 if fused else "NCCL all-gather of owned tiles"))
                    if multi else "single GPU",
                    "raster_path": ("ordered tiles (forced)" if args.raster_path == "ordered" else
@@ -532,9 +539,10 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "allgather"],
-                    help="N>1: fused = tile kernels store into every rank's image over NVLink peer pointers; "
-                         "allgather = pack + NCCL all-gather + unpack")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "fused-p2p", "allgather"],
+                    help="N>1: fused = tile kernels store into every rank's image over NVLink (one NVSwitch "
+                         "multicast store per pixel when an NVLS mapping is available, else one store per peer); "
+                         "fused-p2p = force per-peer stores; allgather = pack + NCCL all-gather + unpack")
     ap.add_argument("--raster-path", default="auto", choices=["auto", "ordered"],
                     help="diagnostic: force the in-order tile kernel even for order-independent passes")
     args = ap.parse_args()

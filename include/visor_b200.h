@@ -218,6 +218,11 @@ VB200_API uint32_t vb200_tiles_per_rank(uint32_t width, uint32_t height, int wor
  * colour word they produce into all of them over NVLink, so after all ranks finish (one cross-rank
  * barrier) every rank holds the whole image. num_peers = 0 removes the association. */
 VB200_API int vb200_set_peer_targets(const void *local_color_device, void *const *peer_color_device, int num_peers);
+/* Same exchange through the NVSwitch: `multicast_device` is a multicast (NVLS) mapping that spans the
+ * image on ALL ranks (e.g. torch symmetric memory multicast_ptr). Each colour word is then sent once
+ * (multimem.st) and replicated to every rank by the switch, instead of once per peer. Takes
+ * precedence over peer targets; NULL removes the association. */
+VB200_API int vb200_set_multicast_target(const void *local_color_device, void *multicast_device);
 
 /* ---- introspection ----------------------------------------------------------------------- */
 

@@ -50,6 +50,8 @@ struct Vb200TileParams
   // so when every rank's tile kernel has finished, every rank holds the complete image.
   uint32_t num_peers;
   uint32_t *peer_color[7];
+  // ... or ONE store to a multicast (NVLS) mapping of the image: the NVSwitch replicates it to every rank
+  uint32_t *mc_color;
   uint32_t *color;
   float *depth;
   const float4 *interps;

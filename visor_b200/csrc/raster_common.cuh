@@ -94,12 +94,16 @@ __device__ __forceinline__ uint32_t vb200_blend_store(const Vb200RasterState &rs
   return (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
 }
 
-// colour store of the tile kernels: local image + every peer's image (fused sort-first exchange)
+// colour store of the tile kernels: local image + every other rank's image (fused sort-first exchange),
+// through one switch-replicated multicast store when an NVLS mapping is set, else one store per peer
 __device__ __forceinline__ void vb200_store_color(const Vb200TileParams &p, size_t gi, uint32_t v)
 {
   p.color[gi] = v;
-  for(uint32_t r = 0; r < p.num_peers; r++)
-    p.peer_color[r][gi] = v;
+  if(p.mc_color)
+    asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p.mc_color + gi), "r"(v) : "memory");
+  else
+    for(uint32_t r = 0; r < p.num_peers; r++)
+      p.peer_color[r][gi] = v;
 }
 
 __device__ __forceinline__ void vb200_count_fragments(Vb200DrawCounters *c, uint32_t covered, uint32_t shaded)

@@ -156,6 +156,7 @@ struct Context
   int64_t optFuseClears = 1;
   // fused sort-first exchange: colour target (device address on this rank) -> the same image on the peers
   std::map<uint8_t *, std::vector<uint32_t *>> peerTargets;
+  std::map<uint8_t *, uint32_t *> multicastTargets;
   Vb200DrawCounters *counters = nullptr;    // device
   const char *lastTileKernel = "";
   vb200_stats stats;
@@ -1412,8 +1413,11 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.clear_color = clearColorWord;
   tp.clear_depth = clearDepthValue;
   {
+    auto mc = g.multicastTargets.find(colorDev);
     auto pt = g.peerTargets.find(colorDev);
-    if(pt != g.peerTargets.end() && g.ownerWorld > 1)
+    if(mc != g.multicastTargets.end() && g.ownerWorld > 1)
+      tp.mc_color = mc->second;
+    else if(pt != g.peerTargets.end() && g.ownerWorld > 1)
     {
       tp.num_peers = (uint32_t)pt->second.size();
       for(uint32_t r = 0; r < tp.num_peers; r++)
@@ -1443,7 +1447,8 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
       phaseMark(3);
     {
       void *args[] = {&env, &tp};
-      if((rc = launchKernel(kTile, dim3(ntiles), dim3(256), args)))
+      const uint32_t ownedTiles = (ntiles + g.ownerWorld - 1u) / g.ownerWorld;
+      if((rc = launchKernel(kTile, dim3(ownedTiles), dim3(256), args)))
         return rc;
     }
     if(attempt == 1)
@@ -1554,6 +1559,17 @@ int vb200_set_peer_targets(const void *local_color_device, void *const *peer_col
     v.push_back((uint32_t *)peer_color_device[i]);
   }
   g.peerTargets[(uint8_t *)local_color_device] = v;
+  return VB200_OK;
+}
+
+int vb200_set_multicast_target(const void *local_color_device, void *multicast_device)
+{
+  if(!local_color_device)
+    return setError(VB200_ERR_INVALID, "set_multicast_target: NULL image");
+  if(!multicast_device)
+    g.multicastTargets.erase((uint8_t *)local_color_device);
+  else
+    g.multicastTargets[(uint8_t *)local_color_device] = (uint32_t *)multicast_device;
   return VB200_OK;
 }
 

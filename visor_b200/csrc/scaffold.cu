@@ -188,11 +188,13 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   __shared__ uint8_t s_queue[8][128];
   __shared__ float s_unorm[256];    // float(byte) / 255.0f, the reference's destination read (rasterizer.cpp:595-599)
 
-  const uint32_t tile = blockIdx.x;
+  // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
+  // cleared, drawn and published by their owners
+  const uint32_t tile = blockIdx.x * p.rs.owner_world + p.rs.owner_rank;
+  if(tile >= p.rs.tiles_x * p.rs.tiles_y)
+    return;
   if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
     return;
-  if(p.rs.owner_world > 1u && tile % p.rs.owner_world != p.rs.owner_rank)
-    return;    // sort-first: another rank owns (clears, draws and publishes) this tile
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   if(n == 0 && !p.clear_flags)
@@ -444,11 +446,13 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __shared__ uint32_t s_start[257];   // first stream slot of each record; [count] = stream length
   __shared__ uint32_t s_wsum[8];
 
-  const uint32_t tile = blockIdx.x;
+  // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
+  // cleared, drawn and published by their owners
+  const uint32_t tile = blockIdx.x * p.rs.owner_world + p.rs.owner_rank;
+  if(tile >= p.rs.tiles_x * p.rs.tiles_y)
+    return;
   if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
     return;
-  if(p.rs.owner_world > 1u && tile % p.rs.owner_world != p.rs.owner_rank)
-    return;    // sort-first: another rank owns (clears, draws and publishes) this tile
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   const Vb200RasterState &rs = p.rs;
