@@ -56,3 +56,25 @@ print("back-to-back 50 frames: device ms/frame", ms.value / 50, " host enqueue m
 gpu.flush()
 t0 = time.perf_counter(); bound.submit(); t1 = time.perf_counter(); gpu.flush(); t2 = time.perf_counter()
 print("idle GPU: submit returns after %.3f ms, flush after %.3f ms" % ((t1 - t0) * 1e3, (t2 - t0) * 1e3))
+
+# sort-first on ONE GPU: this rank's share of the tile work without any exchange (tail / balance check)
+if len(sys.argv) > 2:
+    L.vb200_set_tile_owner.argtypes = [C.c_int, C.c_int]
+    L.vb200_get_phase_times.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
+    L.vb200_set_option.argtypes = [C.c_char_p, C.c_int64]
+    world = int(sys.argv[2])
+    for r in range(world):
+        L.vb200_set_tile_owner(r, world)
+        for _ in range(3):
+            bound.submit()
+        gpu.flush()
+        L.vb200_set_option(b"time_kernels", 1)
+        gpu.reset_stats()
+        for _ in range(5):
+            L.vb200_l2_flush()
+            bound.submit()
+        gpu.flush()
+        pm = (C.c_double * 5)(); pc = (C.c_uint64 * 5)()
+        L.vb200_get_phase_times(pm, pc, 5)
+        L.vb200_set_option(b"time_kernels", 0)
+        print("world", world, "rank", r, {n: round(pm[i] / max(pc[i], 1), 4) for i, n in enumerate(["clear", "vertex", "setup", "bin", "tiles"])})

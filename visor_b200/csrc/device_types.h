@@ -60,7 +60,16 @@ struct Vb200RasterVertex
   float invw, depth;
 };
 
-// Per-triangle setup record (64 B) written by the setup kernel, read by the tile kernels.
+// Per-triangle record (16 B) written by the setup kernel, read by the tile kernels: the triangle's three
+// post-VS record slots and 1/|area2|. Everything else a tile kernel needs is a 16-byte gather from the
+// L2-resident Vb200RasterVertex array per corner, so a triangle costs 16 B of HBM instead of 64.
+struct Vb200TriRecord
+{
+  uint32_t s0, s1, s2;    // post-VS record slot of each corner
+  float invarea;          // 1.0f / float(|area2|) (rasterizer.cpp:448); undefined for dead triangles
+};
+
+// The same triangle as the tile kernels hold it in registers (record + the three vertex gathers).
 struct Vb200TriSetup
 {
   int32_t x0, y0, x1, y1, x2, y2;    // window coordinates of the three corners
@@ -70,7 +79,7 @@ struct Vb200TriSetup
   float invarea;                     // 1.0f / float(|area2|) (rasterizer.cpp:448); undefined for dead triangles
 };
 #ifdef __cplusplus
-static_assert(sizeof(Vb200TriSetup) == 64, "setup record");
+static_assert(sizeof(Vb200TriRecord) == 16, "triangle record");
 #endif
 
 // Statistics counters. Same-address atomics serialise in the L2 atomic unit (~0.6 ns each), so every

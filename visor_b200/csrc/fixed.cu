@@ -253,11 +253,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
   }
   if(t < p.num_tris)
   {
-    int4 *q = (int4 *)(p.setup + t);
-    q[0] = make_int4(su.x0, su.y0, su.x1, su.y1);
-    q[1] = make_int4(su.x2, su.y2, __float_as_int(su.invw0), __float_as_int(su.invw1));
-    q[2] = make_int4(__float_as_int(su.invw2), __float_as_int(su.d0), __float_as_int(su.d1), __float_as_int(su.d2));
-    q[3] = make_int4((int)su.s0, (int)su.s1, (int)su.s2, __float_as_int(su.invarea));
+    *(int4 *)(p.tri + t) = make_int4((int)su.s0, (int)su.s1, (int)su.s2, __float_as_int(su.invarea));
     p.tri_tiles[t] = alive ? tiles : 0xffffffffu;
   }
   uint32_t *cnt = p.tile_count;

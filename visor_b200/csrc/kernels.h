@@ -13,7 +13,7 @@ struct Vb200SetupParams
   uint32_t base_vertex;     // non-indexed: slot = vertex - base_vertex
   uint32_t capacity;        // number of valid post-VS records
   const Vb200RasterVertex *rv;
-  Vb200TriSetup *setup;
+  Vb200TriRecord *tri;
   uint32_t *tri_tiles;    // packed tile range per triangle (0xffffffff = dead), read by the fill pass
   uint32_t *tile_count;
   Vb200DrawCounters *counters;
@@ -34,7 +34,8 @@ struct Vb200VertexParams
 };
 struct Vb200TileParams
 {
-  const Vb200TriSetup *setup;
+  const Vb200TriRecord *tri;
+  const Vb200RasterVertex *rv;
   const uint32_t *list;
   const uint32_t *tile_offset;
   const uint32_t *tile_count;

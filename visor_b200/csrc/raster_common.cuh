@@ -22,16 +22,18 @@ __device__ __forceinline__ float vb200_ld_f32_unaligned(const uint8_t *p)
   return __uint_as_float(u);
 }
 
-__device__ __forceinline__ Vb200TriSetup vb200_load_setup(const Vb200TriSetup *s)
+__device__ __forceinline__ Vb200TriSetup vb200_load_setup(const Vb200TileParams &p, uint32_t t)
 {
-  // 64-byte record = four 16-byte read-only loads
-  const int4 *q = (const int4 *)s;
-  const int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  // 16-byte triangle record, then one 16-byte read-only gather per corner
+  const int4 q = __ldg((const int4 *)(p.tri + t));
+  const int4 a = __ldg((const int4 *)(p.rv + (uint32_t)q.x));
+  const int4 b = __ldg((const int4 *)(p.rv + (uint32_t)q.y));
+  const int4 c = __ldg((const int4 *)(p.rv + (uint32_t)q.z));
   Vb200TriSetup r;
-  r.x0 = a.x; r.y0 = a.y; r.x1 = a.z; r.y1 = a.w;
-  r.x2 = b.x; r.y2 = b.y; r.invw0 = __int_as_float(b.z); r.invw1 = __int_as_float(b.w);
-  r.invw2 = __int_as_float(c.x); r.d0 = __int_as_float(c.y); r.d1 = __int_as_float(c.z); r.d2 = __int_as_float(c.w);
-  r.s0 = (uint32_t)d.x; r.s1 = (uint32_t)d.y; r.s2 = (uint32_t)d.z; r.invarea = __int_as_float(d.w);
+  r.x0 = a.x; r.y0 = a.y; r.x1 = b.x; r.y1 = b.y; r.x2 = c.x; r.y2 = c.y;
+  r.invw0 = __int_as_float(a.z); r.invw1 = __int_as_float(b.z); r.invw2 = __int_as_float(c.z);
+  r.d0 = __int_as_float(a.w); r.d1 = __int_as_float(b.w); r.d2 = __int_as_float(c.w);
+  r.s0 = (uint32_t)q.x; r.s1 = (uint32_t)q.y; r.s2 = (uint32_t)q.z; r.invarea = __int_as_float(q.w);
   return r;
 }
 

@@ -137,7 +137,7 @@ struct Context
   // scratch
   DevBuf<Vb200RasterVertex> rv;
   DevBuf<float4> interps;
-  DevBuf<Vb200TriSetup> setup;
+  DevBuf<Vb200TriRecord> setup;
   DevBuf<uint32_t> tileCount, tileOffset, tileCursor, list, triTiles;
   uint32_t *range = nullptr;                // device {min,max}
   uint32_t *total = nullptr;                // device
@@ -1339,7 +1339,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.base_vertex = baseVertex;
   sp.capacity = capacity;
   sp.rv = g.rv.p;
-  sp.setup = g.setup.p;
+  sp.tri = g.setup.p;
   sp.tri_tiles = g.triTiles.p;
   sp.tile_count = g.tileCount.p;
   sp.counters = g.counters;
@@ -1385,7 +1385,8 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
 
   Vb200TileParams tp;
   memset(&tp, 0, sizeof(tp));
-  tp.setup = g.setup.p;
+  tp.tri = g.setup.p;
+  tp.rv = g.rv.p;
   tp.tile_offset = g.tileOffset.p;
   tp.tile_count = g.tileCount.p;
   tp.total = g.total;

@@ -236,7 +236,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     if(base + lane < n)
     {
       const uint32_t t = p.list[off + base + lane];
-      const Vb200TriSetup su = vb200_load_setup(p.setup + t);
+      const Vb200TriSetup su = vb200_load_setup(p, t);
       // MinMax + clamp (rasterizer.cpp:428-435); pixels iterate the half-open box [min, max)
       const int minx = max(0, min(su.x0, min(su.x1, su.x2))), miny = max(0, min(su.y0, min(su.y1, su.y2)));
       const int maxx = min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2)));
@@ -515,7 +515,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     if(i < n)
     {
       const uint32_t t = p.list[off + i];
-      const Vb200TriSetup su = vb200_load_setup(p.setup + t);
+      const Vb200TriSetup su = vb200_load_setup(p, t);
       const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
       const int area2 = ABx * ACy - ABy * ACx;
       const int sgn = area2 > 0 ? 1 : -1;
@@ -704,7 +704,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       continue;
     }
     shaded++;
-    const Vb200TriSetup su = vb200_load_setup(p.setup + (id - 1u));
+    const Vb200TriSetup su = vb200_load_setup(p, id - 1u);
     // recompute exactly what the reference computes for this pixel (rasterizer.cpp:303-309,545-558)
     const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
     const int area2 = ABx * ACy - ABy * ACx;
