@@ -27,6 +27,8 @@ FMT_R32G32_SFLOAT = 103
 FMT_R32G32B32_SFLOAT = 106
 FMT_R32G32B32A32_SFLOAT = 109
 FMT_D32_SFLOAT = 126
+FMT_BC2_UNORM_BLOCK = 135
+FMT_BC3_UNORM_BLOCK = 137
 TOPO_LIST, TOPO_STRIP = 3, 4
 FRONT_CCW, FRONT_CW = 0, 1
 CULL_NONE, CULL_FRONT, CULL_BACK = 0, 1, 2

@@ -450,3 +450,16 @@ def random_triangles(width: int, height: int, n: int, seed: int, *, depth_op: in
         idx = np.ascontiguousarray(perm.astype(dt))
         d = Draw(pipe, nv, indexed=True, vbs=[(vb, 0)], ib=(idx, 0, index_type))
     return Scene(f"random_{n}_{seed}", width, height, [d], depth=has_depth)
+
+
+def bc_blocks(rng, w, h, corner_cases=True):
+    """random 16-byte BC blocks for a w x h texture (1 byte per texel, images.cpp:31-33)"""
+    blocks = rng.integers(0, 256, size=((h // 4) * (w // 4), 16), dtype=np.uint8)
+    if corner_cases:
+        blocks[0, 8:12] = [0x34, 0x12, 0x34, 0x12]      # color0 == color1 (BC1 three-colour mode in BC2)
+        blocks[1, 8:12] = [0x00, 0x00, 0xff, 0xff]      # color0 < color1
+        blocks[2, 8:12] = [0xff, 0xff, 0x00, 0x00]      # color0 > color1
+        blocks[3, 0:2] = [10, 200]                      # BC3 alpha0 < alpha1: codes 6/7 -> 0/255
+        blocks[4, 0:2] = [200, 10]                      # BC3 alpha0 > alpha1
+        blocks[5, 0:2] = [77, 77]
+    return np.ascontiguousarray(blocks.reshape(-1))

@@ -92,10 +92,87 @@ uint64_t subresourceOffset(const vb200_image *img, uint32_t mip, uint32_t layer)
   return offs;
 }
 
-// one texel as the cache fill converts it (texture_sampling.cpp:121-133)
+// ---- block-compressed texels ------------------------------------------------------------------
+// Restates the decoder the reference calls for BC2/BC3 (3rdparty/decompress.c, "Anteru" BC decoder),
+// for ONE texel of a 16-byte block instead of the whole 4x4 block.
+// 5:6:5 endpoint expansion (decompress.c:122-134): r = ((t/32 + t)/32) with t = c5*255 + 16 etc.
+void bcEndpoints(uint16_t c, uint32_t rgb[3])
+{
+  uint32_t t = (uint32_t)(c >> 11) * 255 + 16;
+  rgb[0] = (uint8_t)((t / 32 + t) / 32);
+  t = (uint32_t)((c & 0x07E0) >> 5) * 255 + 32;
+  rgb[1] = (uint8_t)((t / 64 + t) / 64);
+  t = (uint32_t)(c & 0x001F) * 255 + 16;
+  rgb[2] = (uint8_t)((t / 32 + t) / 32);
+}
+
+// colour half of a block (8 bytes): decompress.c:111-198 when `threeColourMode` may apply (BC2 goes
+// through DecompressBlockBC1Internal, which keeps BC1's color0 <= color1 mode), :246-316 for BC3
+// (always four colours)
+void bcColour(const byte *blk, int texelIdx, bool bc1Modes, byte rgb[3])
+{
+  const uint16_t color0 = (uint16_t)(blk[0] | (blk[1] << 8)), color1 = (uint16_t)(blk[2] | (blk[3] << 8));
+  uint32_t e0[3], e1[3];
+  bcEndpoints(color0, e0);
+  bcEndpoints(color1, e1);
+  const uint32_t code = (uint32_t)blk[4] | ((uint32_t)blk[5] << 8) | ((uint32_t)blk[6] << 16) | ((uint32_t)blk[7] << 24);
+  const uint32_t pc = (code >> (2 * texelIdx)) & 3u;
+  for(int c = 0; c < 3; c++)
+  {
+    uint32_t v;
+    if(!bc1Modes || color0 > color1)
+      v = pc == 0 ? e0[c] : pc == 1 ? e1[c] : pc == 2 ? (2 * e0[c] + e1[c]) / 3 : (e0[c] + 2 * e1[c]) / 3;
+    else
+      v = pc == 0 ? e0[c] : pc == 1 ? e1[c] : pc == 2 ? (e0[c] + e1[c]) / 2 : 0;
+    rgb[c] = (byte)v;
+  }
+}
+
+// one texel as the cache fill converts it (texture_sampling.cpp:92-133)
 void texel(const vb200_image *tex, uint64_t byteOffs, int x, int y, float out[4])
 {
   const byte *base = (const byte *)tex->pixels + byteOffs;
+  if(tex->format == 135u || tex->format == 137u)    // VK_FORMAT_BC2_UNORM_BLOCK / BC3_UNORM_BLOCK
+  {
+    // texture_sampling.cpp:96-118: block (x>>2, y>>2) of a (width>>2)-block-wide image, 16 B per block
+    const uint32_t widthInBlocks = tex->width >> 2;
+    const byte *blk = base + ((uint64_t)(y >> 2) * widthInBlocks + (uint64_t)(x >> 2)) * 16;
+    const int ti = (y & 3) * 4 + (x & 3);
+    byte rgba[4];
+    if(tex->format == 135u)
+    {
+      // DecompressBlockBC2 (decompress.c:330-350): 4-bit alpha * 17, then the BC1 colour block
+      const uint16_t row = (uint16_t)(blk[2 * (y & 3)] | (blk[2 * (y & 3) + 1] << 8));
+      rgba[3] = (byte)(((row >> (4 * (x & 3))) & 0xF) * 17);
+      bcColour(blk + 8, ti, true, rgba);
+    }
+    else
+    {
+      // DecompressBlockBC3 (decompress.c:233-319): two endpoints + 16 3-bit codes (:89-107)
+      const uint32_t alpha0 = blk[0], alpha1 = blk[1];
+      const byte *packed = blk + 2 + 3 * (ti >> 3);
+      const uint32_t tmp = (uint32_t)packed[0] | ((uint32_t)packed[1] << 8) | ((uint32_t)packed[2] << 16);
+      const int ac = (int)((tmp >> (3 * (ti & 7))) & 7u);
+      uint32_t a;
+      if(ac == 0)
+        a = alpha0;
+      else if(ac == 1)
+        a = alpha1;
+      else if(alpha0 > alpha1)
+        a = ((8 - ac) * alpha0 + (ac - 1) * alpha1) / 7;
+      else if(ac == 6)
+        a = 0;
+      else if(ac == 7)
+        a = 255;
+      else
+        a = ((6 - ac) * alpha0 + (ac - 1) * alpha1) / 5;
+      rgba[3] = (byte)a;
+      bcColour(blk + 8, ti, false, rgba);
+    }
+    for(int c = 0; c < 4; c++)
+      out[c] = float(rgba[c]) / 255.0f;
+    return;
+  }
   const uint32_t bpp = tex->bytes_per_pixel;
   const byte *p = base + ((uint64_t)y * tex->width + x) * bpp;
   for(int c = 0; c < 4; c++)

@@ -183,6 +183,38 @@ def test_sampler_matches_oracle(gpu, vor):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_sampler_block_compressed_and_r8(gpu, vor):
+    """BC2/BC3 decode and the 1-byte-per-pixel linear path on the device texture unit"""
+    rng = np.random.default_rng(11)
+    uv = rng.uniform(0.0, 4.0, size=(30000, 2)).astype(np.float32)
+    for fmt in (abi.FMT_BC2_UNORM_BLOCK, abi.FMT_BC3_UNORM_BLOCK):
+        data = scenes.bc_blocks(rng, 64, 32)
+        im = abi.make_image(data, 64, 32, fmt, bpp=1)
+        a, b = gpu.sample(im, uv), vor.sample(im, uv)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), fmt
+        # an image bound at an odd byte offset (alignment 1, images.cpp:51-56): unaligned block loads
+        shifted = np.zeros(data.size + 3, np.uint8)
+        shifted[3:] = data
+        im2 = abi.make_image(shifted[3:], 64, 32, fmt, bpp=1)
+        c = gpu.sample(im2, uv)
+        assert np.array_equal(c.view(np.uint32), b.view(np.uint32)), fmt
+    r8 = rng.integers(0, 256, size=(32 * 16 + 4,), dtype=np.uint8)
+    im = abi.make_image(r8, 32, 16, abi.FMT_R8_UNORM, bpp=1)
+    uv[:, 1] = uv[:, 1] % 0.9
+    a, b = gpu.sample(im, uv), vor.sample(im, uv)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("fmt", [abi.FMT_BC2_UNORM_BLOCK, abi.FMT_BC3_UNORM_BLOCK])
+def test_block_compressed_textured_scene(gpu, vor, fmt):
+    """the C2 cube with its texture stored as BC2 / BC3 blocks"""
+    sc = scenes.c2_cube(640, 360)
+    d = sc.draws[0]
+    s, b, _, _, _, _, _, layers = d.textures[0]
+    d.textures = [(s, b, scenes.bc_blocks(np.random.default_rng(21), 128, 64), 128, 64, fmt, 1, layers)]
+    _check(gpu, vor, sc)
+
+
 def test_cube_map_scene(gpu, vor):
     from harness import shaders
     rng = np.random.default_rng(4)

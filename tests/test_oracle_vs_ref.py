@@ -84,6 +84,33 @@ def test_sampler_2d_and_cube(vor, vref):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_sampler_block_compressed_and_r8(vor, vref):
+    """BC2/BC3 (3rdparty/decompress.c via texture_sampling.cpp:93-118) and the 1-byte-per-pixel linear
+    path, bit for bit against the reference's own decoder"""
+    rng = np.random.default_rng(11)
+    uv = rng.uniform(0.0, 4.0, size=(6000, 2)).astype(np.float32)
+    for fmt in (abi.FMT_BC2_UNORM_BLOCK, abi.FMT_BC3_UNORM_BLOCK):
+        data = scenes.bc_blocks(rng, 64, 32)
+        im = abi.make_image(data, 64, 32, fmt, bpp=1)
+        a, b = vref.sample(im, uv), vor.sample(im, uv)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), fmt
+    r8 = rng.integers(0, 256, size=(32 * 16 + 4,), dtype=np.uint8)    # + 4: the reference reads 4 bytes per texel
+    im = abi.make_image(r8, 32, 16, abi.FMT_R8_UNORM, bpp=1)
+    uvr = uv.copy()
+    uvr[:, 1] = uvr[:, 1] % 0.9    # keep away from the last row, whose 4-byte reads leave the image
+    a, b = vref.sample(im, uvr), vor.sample(im, uvr)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("fmt", [abi.FMT_BC2_UNORM_BLOCK, abi.FMT_BC3_UNORM_BLOCK])
+def test_block_compressed_textured_scene(vor, vref, fmt):
+    sc = scenes.c2_cube(320, 180)
+    d = sc.draws[0]
+    s, b, _, _, _, _, _, layers = d.textures[0]
+    d.textures = [(s, b, scenes.bc_blocks(np.random.default_rng(21), 128, 64), 128, 64, fmt, 1, layers)]
+    _same(vor, vref, sc)
+
+
 def test_clear_truncation(vor, vref):
     for col in [(0.2, 0.2, 0.2, 1.0), (0.999, 0.5, 0.0039, 0.25), (1.5, -0.1, 0.7, 2.0)]:
         a = np.zeros((8, 8, 4), np.uint8)

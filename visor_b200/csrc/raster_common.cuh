@@ -124,18 +124,93 @@ __device__ __forceinline__ void vb200_count_fragments(Vb200DrawCounters *c, uint
 }
 
 // ---- texture unit --------------------------------------------------------------------------
-// One texel as CacheCoord converts it (texture_sampling.cpp:121-133): channel c = float(byte[c])/255.0f,
-// address base + (y*width + x)*bpp.  The reference's 4x4 LRU block cache is a pure cache; here the
-// read-only L1/texture path (ld.global.nc) plays that role.
-__device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t width, uint32_t bpp, int x, int y)
+// 5:6:5 endpoint expansion of the BC decoder the reference uses (3rdparty/decompress.c:122-134):
+// ((t/32 + t)/32) with t = c5*255 + 16, ((t/64 + t)/64) with t = c6*255 + 32; packed as 0x00BBGGRR
+__device__ __forceinline__ uint32_t vb200_bc_endpoint(uint32_t c)
 {
-  const uint8_t *p = base + ((size_t)y * width + (size_t)x) * bpp;
-  uint32_t u;
-  if(bpp == 4)
-    u = __ldg((const uint32_t *)p);
+  uint32_t t = (c >> 11) * 255u + 16u;
+  const uint32_t r = ((t >> 5) + t) >> 5;
+  t = ((c >> 5) & 0x3fu) * 255u + 32u;
+  const uint32_t g = ((t >> 6) + t) >> 6;
+  t = (c & 0x1fu) * 255u + 16u;
+  const uint32_t b = ((t >> 5) + t) >> 5;
+  return (r & 0xffu) | ((g & 0xffu) << 8) | ((b & 0xffu) << 16);
+}
+
+// One texel of a BC2/BC3 block (16 B: 8 B alpha + 8 B colour), as DecompressBlockBC2/BC3 produce it
+// (decompress.c:233-350). BC2 goes through the BC1 colour path, which keeps BC1's three-colour mode
+// when color0 <= color1; BC3 always interpolates four colours. Returns packed RGBA bytes.
+__device__ __forceinline__ uint32_t vb200_bc_texel(const uint8_t *blk, bool bc3, int x, int y)
+{
+  uint4 w;
+  if((((uintptr_t)blk) & 15) == 0)
+    w = __ldg((const uint4 *)blk);
+  else    // images may be bound at any byte offset (alignment 1, images.cpp:51-56)
+    w = make_uint4(__float_as_uint(vb200_ld_f32_unaligned(blk)), __float_as_uint(vb200_ld_f32_unaligned(blk + 4)),
+                   __float_as_uint(vb200_ld_f32_unaligned(blk + 8)), __float_as_uint(vb200_ld_f32_unaligned(blk + 12)));
+  const int ti = (y & 3) * 4 + (x & 3);
+  uint32_t alpha;
+  if(!bc3)
+  {
+    const uint32_t row = ((y & 2) ? w.y : w.x) >> ((y & 1) * 16);
+    alpha = ((row >> (4 * (x & 3))) & 0xfu) * 17u;
+  }
   else
-    u = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
-        ((uint32_t)__ldg(p + 3) << 24);
+  {
+    const uint32_t alpha0 = w.x & 0xffu, alpha1 = (w.x >> 8) & 0xffu;
+    // 48 bits of 3-bit codes start at byte 2: two 24-bit groups of eight codes (decompress.c:89-107)
+    const unsigned long long bits = (((unsigned long long)w.y << 32) | w.x) >> 16;
+    const uint32_t ac = (uint32_t)(bits >> (3 * ti)) & 7u;
+    if(ac == 0u)
+      alpha = alpha0;
+    else if(ac == 1u)
+      alpha = alpha1;
+    else if(alpha0 > alpha1)
+      alpha = ((8u - ac) * alpha0 + (ac - 1u) * alpha1) / 7u;
+    else if(ac == 6u)
+      alpha = 0u;
+    else if(ac == 7u)
+      alpha = 255u;
+    else
+      alpha = ((6u - ac) * alpha0 + (ac - 1u) * alpha1) / 5u;
+  }
+  const uint32_t color0 = w.z & 0xffffu, color1 = w.z >> 16;
+  const uint32_t e0 = vb200_bc_endpoint(color0), e1 = vb200_bc_endpoint(color1);
+  const uint32_t pc = (w.w >> (2 * ti)) & 3u;
+  uint32_t rgb = 0;
+#pragma unroll
+  for(int c = 0; c < 3; c++)
+  {
+    const uint32_t a = (e0 >> (8 * c)) & 0xffu, b = (e1 >> (8 * c)) & 0xffu;
+    uint32_t v;
+    if(bc3 || color0 > color1)
+      v = pc == 0u ? a : pc == 1u ? b : pc == 2u ? (2u * a + b) / 3u : (a + 2u * b) / 3u;
+    else
+      v = pc == 0u ? a : pc == 1u ? b : pc == 2u ? (a + b) / 2u : 0u;
+    rgb |= (v & 0xffu) << (8 * c);
+  }
+  return rgb | ((alpha & 0xffu) << 24);
+}
+
+// One texel as CacheCoord converts it (texture_sampling.cpp:92-133): channel c = float(byte[c])/255.0f.
+// Linear formats: address base + (y*width + x)*bpp. BC2/BC3 (VkFormat 135/137): block (x>>2, y>>2) of
+// a (width>>2)-block-wide image, decoded per texel. The reference's 4x4 LRU block cache is a pure
+// cache; here the read-only L1/texture path (ld.global.nc) plays that role.
+__device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t width, uint32_t bpp, uint32_t format,
+                                              int x, int y)
+{
+  uint32_t u;
+  if(format == 135u || format == 137u)
+    u = vb200_bc_texel(base + ((size_t)(y >> 2) * (width >> 2) + (size_t)(x >> 2)) * 16, format == 137u, x, y);
+  else
+  {
+    const uint8_t *p = base + ((size_t)y * width + (size_t)x) * bpp;
+    if(bpp == 4)
+      u = __ldg((const uint32_t *)p);
+    else
+      u = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
+          ((uint32_t)__ldg(p + 3) << 24);
+  }
   return make_float4(__fdiv_rn((float)(u & 0xffu), 255.0f), __fdiv_rn((float)((u >> 8) & 0xffu), 255.0f),
                      __fdiv_rn((float)((u >> 16) & 0xffu), 255.0f), __fdiv_rn((float)(u >> 24), 255.0f));
 }
@@ -144,7 +219,7 @@ __device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t widt
 __device__ __forceinline__ float4 vb200_sample_tex_impl(float u, float v, const Vb200Image *img,
                                                         unsigned long long byteOffs)
 {
-  const uint32_t width = img->width, height = img->height, bpp = img->bpp;
+  const uint32_t width = img->width, height = img->height, bpp = img->bpp, fmt = img->format;
   const uint8_t *base = img->pixels + byteOffs;
   u = __fsub_rn(u, floorf(u));
   v = __fsub_rn(v, floorf(v));
@@ -158,10 +233,10 @@ __device__ __forceinline__ float4 vb200_sample_tex_impl(float u, float v, const 
     iv1 -= (int)height;
   const float fu = __fsub_rn(u, (float)iu0), fv = __fsub_rn(v, (float)iv0);
   const float inv_fu = __fsub_rn(1.0f, fu), inv_fv = __fsub_rn(1.0f, fv);
-  const float4 TL = vb200_texel(base, width, bpp, iu0, iv0);
-  const float4 TR = vb200_texel(base, width, bpp, iu1, iv0);
-  const float4 BL = vb200_texel(base, width, bpp, iu0, iv1);
-  const float4 BR = vb200_texel(base, width, bpp, iu1, iv1);
+  const float4 TL = vb200_texel(base, width, bpp, fmt, iu0, iv0);
+  const float4 TR = vb200_texel(base, width, bpp, fmt, iu1, iv0);
+  const float4 BL = vb200_texel(base, width, bpp, fmt, iu0, iv1);
+  const float4 BR = vb200_texel(base, width, bpp, fmt, iu1, iv1);
   float4 top, bottom, out;
   top.x = __fadd_rn(__fmul_rn(TL.x, inv_fu), __fmul_rn(TR.x, fu));
   top.y = __fadd_rn(__fmul_rn(TL.y, inv_fu), __fmul_rn(TR.y, fu));

@@ -625,8 +625,6 @@ int fillResources(const vb200_draw_state *s, const vb200::ShaderEntry &e, Vb200E
       if(!b->is_image)
         return setError(VB200_ERR_INVALID, "descriptor (%u,%u) is not an image", r.set, r.binding);
       const vb200_image &im = b->image;
-      if(im.format == 135 || im.format == 137)    // BC2 / BC3
-        return setError(VB200_ERR_INVALID, "BC2/BC3 sampling is not implemented on the device path yet");
       if((im.width & 3) || (im.height & 3))
         return setError(VB200_ERR_INVALID, "texture size must be a multiple of 4 (texture_sampling.cpp:123-133)");
       uint8_t *dev;
@@ -1501,8 +1499,6 @@ int vb200_sample(const vb200_image *tex, int cube, uint64_t byte_offset, const f
     return rc;
   if(!tex || !tex->pixels || !uvw || !out_rgba)
     return setError(VB200_ERR_INVALID, "sample: NULL argument");
-  if(tex->format == 135 || tex->format == 137)
-    return setError(VB200_ERR_INVALID, "BC2/BC3 sampling is not implemented on the device path yet");
   if(count == 0)
     return VB200_OK;
   uint8_t *dev;
