@@ -196,6 +196,21 @@ VB200_API int vb200_mem_download(void *host, uint64_t size);       /* HBM mirror
  * replayed as memcpy, cmd_exec.cpp:143-182): orders the write after in-flight uploads of the range and
  * makes later draws re-upload it. */
 VB200_API int vb200_mem_host_write(const void *host, uint64_t size);
+/* Marks a registered range as DEVICE_LOCAL memory (memory type 0, query.cpp:260-266): the application
+ * never maps it, so its HBM mirror is the only copy that matters. It is filled by vb200_copy_* (or
+ * vb200_mem_upload), never re-uploaded per submit and never downloaded by vb200_flush. */
+VB200_API int vb200_mem_set_device_local(void *host, int device_local);
+/* vkCmdCopyBuffer as the reference replays it (cmd_exec.cpp:176-182): memcpy(dst->bytes + dst_offset,
+ * src->bytes + src_offset, size) — performed between the HBM mirrors on the library stream, in
+ * submission order with the draws. In coherent mode the destination is downloaded by vb200_flush like
+ * an attachment, so host memory ends up identical to the reference's. */
+VB200_API int vb200_copy_buffer(const vb200_buffer *src, uint64_t src_offset, const vb200_buffer *dst,
+                                uint64_t dst_offset, uint64_t size);
+/* vkCmdCopyBufferToImage as the reference replays it (cmd_exec.cpp:143-174): one whole, tightly packed
+ * mip level of one array layer; destination offset = CalcSubresourceByteOffset(dst, mip, layer)
+ * (precompiled.cpp:3-36), byte count = max(1,w>>mip) * max(1,h>>mip) * bytes_per_pixel. */
+VB200_API int vb200_copy_buffer_to_image(const vb200_buffer *src, uint64_t buffer_offset, const vb200_image *dst,
+                                         uint32_t mip_level, uint32_t array_layer);
 /* Device address of a mirrored host pointer (NULL if not mirrored); for interop (NCCL, torch). */
 VB200_API void *vb200_mem_device_ptr(const void *host);
 

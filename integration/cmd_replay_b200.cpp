@@ -14,6 +14,19 @@
 
 #include "../include/visor_b200.h"
 
+static void toImage(const VkImage_T *in, vb200_image &out)
+{
+  out.pixels = in->pixels;
+  out.width = in->extent.width;
+  out.height = in->extent.height;
+  out.depth = in->extent.depth;
+  out.image_type = (uint32_t)in->imageType;
+  out.format = (uint32_t)in->format;
+  out.array_layers = in->arrayLayers;
+  out.mip_levels = in->mipLevels;
+  out.bytes_per_pixel = in->bytesPerPixel;
+}
+
 namespace
 {
 // the stream is a packed sequence of {uint16 id}{payload}; payloads are not aligned (cmd_alloc.cpp:59-70)
@@ -107,24 +120,23 @@ void VkCommandBuffer_T::execute() const
       }
       case Command::CopyBuf2Img:
       {
-        // whole tightly packed mip of one layer only (:147-164)
+        // whole tightly packed mip of one layer only (:147-164); performed between the HBM mirrors, in
+        // stream order with the draws
         const cmd::CopyBuf2Img d = take<cmd::CopyBuf2Img>(cur);
-        const uint32_t mip = d.region.imageSubresource.mipLevel;
-        const uint32_t w = std::max(1U, d.dstImage->extent.width >> mip);
-        const uint32_t h = std::max(1U, d.dstImage->extent.height >> mip);
-        const size_t bytes = (size_t)w * h * d.dstImage->bytesPerPixel;
-        byte *dst = d.dstImage->pixels +
-                    CalcSubresourceByteOffset(d.dstImage, mip, d.region.imageSubresource.baseArrayLayer);
-        vb200_mem_host_write(dst, bytes);    // order after in-flight uploads, re-upload on next use
-        memcpy(dst, d.srcBuffer->bytes + d.region.bufferOffset, bytes);
+        vb200_buffer src = {d.srcBuffer->bytes, d.srcBuffer->size};
+        vb200_image dst;
+        toImage(d.dstImage, dst);
+        if(vb200_copy_buffer_to_image(&src, d.region.bufferOffset, &dst, d.region.imageSubresource.mipLevel,
+                                      d.region.imageSubresource.baseArrayLayer) != VB200_OK)
+          printf("vkCmdCopyBufferToImage: %s\n", vb200_last_error());
         break;
       }
       case Command::CopyBuf:
       {
         const cmd::CopyBuf d = take<cmd::CopyBuf>(cur);
-        byte *dst = d.dstBuffer->bytes + d.region.dstOffset;
-        vb200_mem_host_write(dst, d.region.size);
-        memcpy(dst, d.srcBuffer->bytes + d.region.srcOffset, d.region.size);
+        vb200_buffer src = {d.srcBuffer->bytes, d.srcBuffer->size}, dst = {d.dstBuffer->bytes, d.dstBuffer->size};
+        if(vb200_copy_buffer(&src, d.region.srcOffset, &dst, d.region.dstOffset, d.region.size) != VB200_OK)
+          printf("vkCmdCopyBuffer: %s\n", vb200_last_error());
         break;
       }
     }

@@ -4,7 +4,8 @@
  * Semantics are the reference's (memory.cpp:5-41): memory is host memory, vkMapMemory returns
  * bytes + offset, flushes are no-ops, buffers/images alias it at bind time. The only difference is
  * that the allocation is registered with the CUDA library, which page-locks it and creates its HBM
- * mirror, so the per-submit uploads/downloads run at full PCIe speed.
+ * mirror, so the per-submit uploads/downloads run at full PCIe speed; DEVICE_LOCAL allocations (memory
+ * type 0) live in the mirror only.
  */
 #include "precompiled.h"
 
@@ -17,6 +18,10 @@ VKAPI_ATTR VkResult VKAPI_CALL vkAllocateMemory(VkDevice device, const VkMemoryA
   mem->size = pAllocateInfo->allocationSize;
   mem->bytes = new byte[mem->size + 16];    // +16: texel fetches of 1-byte formats read 4 bytes
   vb200_mem_register(mem->bytes, mem->size + 16);
+  // memory type 0 is DEVICE_LOCAL only (query.cpp:246-267): the application cannot map it, so the HBM
+  // mirror is the resource; it is filled by vkCmdCopyBuffer* on the device and never crosses PCIe again
+  if(pAllocateInfo->memoryTypeIndex == 0)
+    vb200_mem_set_device_local(mem->bytes, 1);
   *pMemory = mem;
   return VK_SUCCESS;
 }

@@ -150,11 +150,14 @@ extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_pa
   VkQueue queue = L.queue;
 
   std::vector<VkDeviceMemory> allMem;
-  auto allocFor = [&](VkMemoryRequirements req) -> Mapped {
-    VkMemoryAllocateInfo ai = {VK_STRUCTURE_TYPE_MEMORY_ALLOCATE_INFO, NULL, req.size ? req.size : 16, 1};
+  // memory type 1 = HOST_VISIBLE|COHERENT|CACHED (mapped), type 0 = DEVICE_LOCAL (never mapped), query.cpp:246-267
+  auto allocFor = [&](VkMemoryRequirements req, uint32_t memoryType = 1) -> Mapped {
+    VkMemoryAllocateInfo ai = {VK_STRUCTURE_TYPE_MEMORY_ALLOCATE_INFO, NULL, req.size ? req.size : 16, memoryType};
     Mapped m;
+    m.ptr = NULL;
     vkAllocateMemory(dev, &ai, NULL, &m.mem);
-    vkMapMemory(dev, m.mem, 0, VK_WHOLE_SIZE, 0, &m.ptr);
+    if(memoryType == 1)
+      vkMapMemory(dev, m.mem, 0, VK_WHOLE_SIZE, 0, &m.ptr);
     allMem.push_back(m.mem);
     return m;
   };
@@ -188,7 +191,9 @@ extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_pa
     vkCreateImage(dev, &ii, NULL, out);
     VkMemoryRequirements req;
     vkGetImageMemoryRequirements(dev, *out, &req);
-    Mapped m = allocFor(req);
+    // sampled textures live in DEVICE_LOCAL memory and are filled by vkCmdCopyBufferToImage, as in a real
+    // application; attachments are host-visible because the test reads them back through the mapping
+    Mapped m = allocFor(req, (usage & VK_IMAGE_USAGE_SAMPLED_BIT) ? 0 : 1);
     vkBindImageMemory(dev, *out, m.mem, 0);
     VkImageViewCreateInfo vi = {VK_STRUCTURE_TYPE_IMAGE_VIEW_CREATE_INFO};
     vi.image = *out;

@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): coverage, depth-test outcomes and integer/UNORM 
 bit-exact; shaded colour within 1 UNORM8 LSB — in practice every scene here is required to be
 byte-identical because the shader arithmetic is IEEE-exact in both (no sin/cos/pow in these scenes).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -213,6 +215,70 @@ def test_block_compressed_textured_scene(gpu, vor, fmt):
     s, b, _, _, _, _, _, layers = d.textures[0]
     d.textures = [(s, b, scenes.bc_blocks(np.random.default_rng(21), 128, 64), 128, 64, fmt, 1, layers)]
     _check(gpu, vor, sc)
+
+
+def _copy_api(gpu):
+    L = gpu.lib
+    L.vb200_copy_buffer.argtypes = [C.POINTER(abi.Buffer), C.c_uint64, C.POINTER(abi.Buffer), C.c_uint64, C.c_uint64]
+    L.vb200_copy_buffer_to_image.argtypes = [C.POINTER(abi.Buffer), C.c_uint64, C.POINTER(abi.Image), C.c_uint32,
+                                             C.c_uint32]
+    L.vb200_mem_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.vb200_mem_unregister.argtypes = [C.c_void_p]
+    L.vb200_mem_set_device_local.argtypes = [C.c_void_p, C.c_int]
+    return L
+
+
+def test_copy_buffer_and_copy_buffer_to_image(gpu, vor):
+    """vkCmdCopyBuffer / vkCmdCopyBufferToImage replayed on the device (cmd_exec.cpp:143-182): host memory
+    ends up exactly as the reference's memcpy leaves it, and the copy is ordered with the draws"""
+    L = _copy_api(gpu)
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, size=5000, dtype=np.uint8)
+    dst = np.full(6000, 7, np.uint8)
+    sb, db = abi.make_buffer(src), abi.make_buffer(dst)
+    gpu.check(L.vb200_copy_buffer(C.byref(sb), 100, C.byref(db), 1000, 3000), "copy_buffer")
+    gpu.flush()
+    want = np.full(6000, 7, np.uint8)
+    want[1000:4000] = src[100:3100]
+    assert np.array_equal(dst, want)
+    assert L.vb200_copy_buffer(C.byref(sb), 4000, C.byref(db), 0, 2000) != 0    # source range outside the buffer
+
+    # a 2-layer image with 3 mips (32x16, 16x8, 8x4): CalcSubresourceByteOffset (precompiled.cpp:3-36)
+    chain = 32 * 16 * 4 + 16 * 8 * 4 + 8 * 4 * 4
+    img = np.zeros(2 * chain, np.uint8)
+    im = abi.make_image(img, 32, 16, abi.FMT_R8G8B8A8_UNORM, layers=2, mips=3)
+    gpu.check(L.vb200_copy_buffer_to_image(C.byref(sb), 16, C.byref(im), 1, 1), "copy_buffer_to_image")
+    gpu.flush()
+    want = np.zeros(2 * chain, np.uint8)
+    offs = chain + 32 * 16 * 4
+    want[offs:offs + 16 * 8 * 4] = src[16:16 + 16 * 8 * 4]
+    assert np.array_equal(img, want)
+
+
+def test_device_local_texture_filled_by_copy(gpu, vor):
+    """a texture in DEVICE_LOCAL memory: filled by a device copy from a staging buffer, sampled by the
+    draw, never read from or written to its host shadow"""
+    L = _copy_api(gpu)
+    sc = scenes.c2_cube(640, 360)
+    want_c, want_d = scenes.render(vor, sc)
+    d = sc.draws[0]
+    s, b, tex, tw, th, fmt, bpp, layers = d.textures[0]
+    staging = np.ascontiguousarray(tex).reshape(-1).copy()
+    shadow = np.zeros(staging.size + 16, np.uint8)    # "device local": the host side stays zero
+    gpu.check(L.vb200_mem_register(shadow.ctypes.data, shadow.nbytes), "mem_register")
+    try:
+        gpu.check(L.vb200_mem_set_device_local(shadow.ctypes.data, 1), "set_device_local")
+        sb = abi.make_buffer(staging)
+        im = abi.make_image(shadow, tw, th, fmt, bpp=bpp, layers=layers)
+        gpu.check(L.vb200_copy_buffer_to_image(C.byref(sb), 0, C.byref(im), 0, 0), "copy_buffer_to_image")
+        gpu.flush()                                   # a later submit still finds the texture in HBM
+        d.textures = [(s, b, shadow[:staging.size].reshape(tex.shape), tw, th, fmt, bpp, layers)]
+        for _ in range(2):
+            got_c, got_d = scenes.render(gpu, sc)
+            assert np.array_equal(got_c, want_c) and np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))
+        assert not shadow.any()
+    finally:
+        L.vb200_mem_unregister(shadow.ctypes.data)
 
 
 def test_cube_map_scene(gpu, vor):

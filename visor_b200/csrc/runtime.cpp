@@ -89,6 +89,7 @@ struct Mirror
   uint8_t *dev = nullptr;
   bool pinned = false;       // page-locked by vb200_mem_register (caller guarantees lifetime)
   bool explicitReg = false;
+  bool deviceLocal = false;    // DEVICE_LOCAL memory: the mirror is authoritative, no per-epoch upload/download
   uint64_t lastUse = 0;
   std::vector<std::pair<size_t, size_t>> uploaded;    // (offset, size) uploaded this epoch
   std::vector<std::pair<size_t, size_t>> written;     // (offset, size) written by kernels this epoch
@@ -362,7 +363,7 @@ int resolve(const void *ptr, size_t size, int access, uint8_t **out)
   }
   m->lastUse = g.epoch;
   const size_t off = (uintptr_t)ptr - (uintptr_t)m->host;
-  if(g.syncMode == VB200_SYNC_COHERENT)
+  if(g.syncMode == VB200_SYNC_COHERENT && !m->deviceLocal)
   {
     const bool devNewer = rangeCovered(m->written, off, size);
     if((access & ACC_READ) && !(access & ACC_OVERWRITE) && !devNewer && !rangeCovered(m->uploaded, off, size))
@@ -992,6 +993,81 @@ int vb200_mem_host_write(const void *host, uint64_t size)
   if(pending)
     CU(cudaStreamSynchronize(g.stream));
   return VB200_OK;
+}
+
+int vb200_mem_set_device_local(void *host, int device_local)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  Mirror *m = host ? findMirror(host, 1) : nullptr;
+  if(!m || !m->explicitReg)
+    return setError(VB200_ERR_INVALID, "mem_set_device_local: %p is not inside a registered range", host);
+  m->deviceLocal = device_local != 0;
+  return VB200_OK;
+}
+
+namespace
+{
+int copyBytes(const uint8_t *srcHost, uint8_t *dstHost, uint64_t size, const char *what)
+{
+  if(size == 0)
+    return VB200_OK;
+  if(!srcHost || !dstHost)
+    return setError(VB200_ERR_INVALID, "%s: NULL buffer memory", what);
+  uint8_t *srcDev, *dstDev;
+  int rc = resolve(srcHost, size, ACC_READ, &srcDev);
+  if(rc)
+    return rc;
+  // the whole destination range is overwritten: no upload of its old contents; marked written, so a
+  // coherent-mode flush brings the copy back to host memory
+  if((rc = resolve(dstHost, size, ACC_WRITE | ACC_OVERWRITE, &dstDev)))
+    return rc;
+  CU(cudaMemcpyAsync(dstDev, srcDev, size, cudaMemcpyDeviceToDevice, g.stream));
+  return VB200_OK;
+}
+}    // namespace
+
+int vb200_copy_buffer(const vb200_buffer *src, uint64_t src_offset, const vb200_buffer *dst, uint64_t dst_offset,
+                      uint64_t size)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(!src || !dst)
+    return setError(VB200_ERR_INVALID, "copy_buffer: NULL buffer");
+  if(src_offset + size > src->size || dst_offset + size > dst->size)
+    return setError(VB200_ERR_INVALID, "copy_buffer: range outside the buffer");
+  return copyBytes((const uint8_t *)src->bytes + src_offset, (uint8_t *)dst->bytes + dst_offset, size, "copy_buffer");
+}
+
+int vb200_copy_buffer_to_image(const vb200_buffer *src, uint64_t buffer_offset, const vb200_image *dst,
+                               uint32_t mip_level, uint32_t array_layer)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(!src || !dst || !dst->pixels)
+    return setError(VB200_ERR_INVALID, "copy_buffer_to_image: NULL argument");
+  if(mip_level >= std::max(1u, dst->mip_levels) || array_layer >= std::max(1u, dst->array_layers))
+    return setError(VB200_ERR_INVALID, "copy_buffer_to_image: subresource (%u, %u) outside the image", mip_level,
+                    array_layer);
+  // CalcSubresourceByteOffset (precompiled.cpp:3-36): mips of the layer before this one + whole layers
+  uint32_t mw = dst->width, mh = dst->height;
+  uint64_t offs = 0;
+  for(uint32_t m = 0; m < mip_level; m++)
+  {
+    offs += (uint64_t)(mw * mh * dst->bytes_per_pixel);
+    mw = std::max(1u, mw >> 1);
+    mh = std::max(1u, mh >> 1);
+  }
+  offs += sliceBytes(*dst) * array_layer;
+  const uint32_t w = std::max(1u, dst->width >> mip_level), h = std::max(1u, dst->height >> mip_level);
+  const uint64_t bytes = (uint64_t)w * h * dst->bytes_per_pixel;
+  if(buffer_offset + bytes > src->size)
+    return setError(VB200_ERR_INVALID, "copy_buffer_to_image: source range outside the buffer");
+  return copyBytes((const uint8_t *)src->bytes + buffer_offset, (uint8_t *)dst->pixels + offs, bytes,
+                   "copy_buffer_to_image");
 }
 
 void *vb200_mem_device_ptr(const void *host)
