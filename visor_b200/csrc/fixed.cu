@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(kThreads) k_index_range(const void *ib, uint32
   }
 }
 
-__global__ void k_init_range(uint32_t *range)
+__global__ void k_init_range(uint32_t *range, uint32_t lo, uint32_t hi)
 {
-  range[0] = 0xffffffffu;
-  range[1] = 0u;
+  range[0] = lo;
+  range[1] = hi;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -551,13 +551,19 @@ int launch_clear_u8(uint8_t *dst, uint8_t value, size_t count, cudaStream_t s)
 int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint32_t count, uint32_t *range,
                        cudaStream_t s)
 {
-  k_init_range<<<1, 1, 0, s>>>(range);
+  k_init_range<<<1, 1, 0, s>>>(range, 0xffffffffu, 0u);
   if(!count)
     return 1;
   // one wave: 4 CTAs per SM
   const uint32_t g = (uint32_t)std::min<size_t>((size_t)sm_count() * 4, (count + kThreads - 1) / kThreads);
   k_index_range<<<g ? g : 1, kThreads, 0, s>>>(ib, index_type, first, count, range);
   return 2;
+}
+
+int launch_set_range(uint32_t *range, uint32_t lo, uint32_t hi, cudaStream_t s)
+{
+  k_init_range<<<1, 1, 0, s>>>(range, lo, hi);
+  return 1;
 }
 
 int launch_setup(const Vb200SetupParams &p, cudaStream_t s)

@@ -67,6 +67,7 @@ int launch_clear_u32(uint32_t *dst, uint32_t value, size_t count, cudaStream_t s
 int launch_clear_u8(uint8_t *dst, uint8_t value, size_t count, cudaStream_t s);
 int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint32_t count, uint32_t *range,
                        cudaStream_t s);
+int launch_set_range(uint32_t *range, uint32_t lo, uint32_t hi, cudaStream_t s);
 int launch_setup(const Vb200SetupParams &p, cudaStream_t s);
 int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
                 uint32_t *total, unsigned long long *host_total_dev, uint32_t seq, cudaStream_t s);

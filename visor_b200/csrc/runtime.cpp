@@ -456,43 +456,15 @@ bool parseScaffold()
   return true;
 }
 
-// ptxas step: kernel text + shader function -> one sm_100a cubin. Needs no device.
-int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin)
+// One ptxas run over a complete module. `spills` receives the spill-store bytes ptxas reports.
+int runPtxas(const std::string &text, const char *name, std::vector<char> &cubin, unsigned *spills)
 {
-  if(!parseScaffold())
-    return setError(VB200_ERR_LINK, "embedded kernel scaffold PTX has an unexpected layout");
-  std::string body = shader->e.ptx;
-  for(const char *directive : {".version", ".target", ".address_size"})
-  {
-    const size_t at = body.find(directive);
-    if(at != std::string::npos)
-      body.erase(at, body.find('\n', at) - at);
-  }
-  stripExternFuncs(body);
-  std::string text;
-  text.reserve(scaffold.prologue.size() + scaffold.helpers.size() + body.size() + scaffold.entries[which].size() +
-               scaffold.epilogue.size() + 16);
-  text += scaffold.prologue;
-  text += scaffold.helpers;
-  text += body;
-  text += "\n";
-  {
-    std::string entry = scaffold.entries[which];
-    // tuning aid: VB200_JIT_MINCTAS=<n> adds .minnctapersm to the tile kernels (occupancy experiments)
-    const char *mc = getenv("VB200_JIT_MINCTAS");
-    const size_t at = entry.find(".maxntid 256, 1, 1");
-    if(mc && which != K_VERTEX && at != std::string::npos)
-      entry.insert(at + strlen(".maxntid 256, 1, 1"), std::string("\n.minnctapersm ") + mc);
-    text += entry;
-  }
-  text += scaffold.epilogue;
-
   nvPTXCompilerHandle h;
   if(nvPTXCompilerCreate(&h, text.size(), text.c_str()) != NVPTXCOMPILE_SUCCESS)
     return setError(VB200_ERR_LINK, "nvPTXCompilerCreate failed");
   std::string maxreg;
-  const char *opts[4] = {"--gpu-name=sm_100a", "--generate-line-info", nullptr, nullptr};
-  int nopts = 2;
+  const char *opts[5] = {"--gpu-name=sm_100a", "--generate-line-info", "--verbose", nullptr, nullptr};
+  int nopts = 3;
   if(const char *mr = getenv("VB200_JIT_MAXRREGCOUNT"))    // tuning aid
   {
     maxreg = std::string("--maxrregcount=") + mr;
@@ -509,13 +481,88 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
       nvPTXCompilerGetErrorLog(h, &log[0]);
     }
     nvPTXCompilerDestroy(&h);
-    return setError(VB200_ERR_LINK, "ptxas failed on %s (%d): %s", kKernelNames[which], (int)r, log.c_str());
+    return setError(VB200_ERR_LINK, "ptxas failed on %s (%d): %s", name, (int)r, log.c_str());
+  }
+  if(spills)
+  {
+    // "... N bytes stack frame, N bytes spill stores, N bytes spill loads"
+    *spills = 0;
+    std::string log;
+    size_t n = 0;
+    if(nvPTXCompilerGetInfoLogSize(h, &n) == NVPTXCOMPILE_SUCCESS && n > 0)
+    {
+      log.resize(n + 1);
+      nvPTXCompilerGetInfoLog(h, &log[0]);
+      for(size_t at = log.find(" bytes spill stores"); at != std::string::npos; at = log.find(" bytes spill stores", at + 1))
+      {
+        size_t d = at;
+        while(d > 0 && isdigit((unsigned char)log[d - 1]))
+          d--;
+        *spills += (unsigned)strtoul(log.c_str() + d, nullptr, 10);
+      }
+    }
   }
   size_t sz = 0;
   nvPTXCompilerGetCompiledProgramSize(h, &sz);
   cubin.resize(sz);
   nvPTXCompilerGetCompiledProgram(h, cubin.data());
   nvPTXCompilerDestroy(&h);
+  return VB200_OK;
+}
+
+// ptxas step: kernel text + shader function -> one sm_100a cubin. Needs no device.
+int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin)
+{
+  if(!parseScaffold())
+    return setError(VB200_ERR_LINK, "embedded kernel scaffold PTX has an unexpected layout");
+  std::string body = shader->e.ptx;
+  for(const char *directive : {".version", ".target", ".address_size"})
+  {
+    const size_t at = body.find(directive);
+    if(at != std::string::npos)
+      body.erase(at, body.find('\n', at) - at);
+  }
+  stripExternFuncs(body);
+  // Tile kernels: ask ptxas for five resident CTAs per SM (<= 48 registers at the allocation granule).
+  // Left alone it picks ~50 for the resolve kernels, which the granule rounds up to 56 = four CTAs;
+  // the bound costs a handful of spilled bytes and buys the fifth CTA (measured, resolve kernel: C3
+  // 182 -> 167 us, C5 1086 -> 1010 us; six CTAs spill more and are slower again). Whether a shader
+  // leaves room for that is only known after inlining, so the bound is dropped when ptxas reports
+  // more than a few spilled words. VB200_JIT_MINCTAS overrides (tuning aid).
+  const unsigned kSpillTolerance = 32;
+  int minCtas = which != K_VERTEX ? 5 : 0;
+  bool forced = false;
+  if(const char *mc = getenv("VB200_JIT_MINCTAS"))
+  {
+    minCtas = which != K_VERTEX ? atoi(mc) : 0;
+    forced = true;
+  }
+  for(;;)
+  {
+    std::string text;
+    text.reserve(scaffold.prologue.size() + scaffold.helpers.size() + body.size() + scaffold.entries[which].size() +
+                 scaffold.epilogue.size() + 64);
+    text += scaffold.prologue;
+    text += scaffold.helpers;
+    text += body;
+    text += "\n";
+    std::string entry = scaffold.entries[which];
+    const size_t at = entry.find(".maxntid 256, 1, 1");
+    if(minCtas > 0 && at != std::string::npos)
+      entry.insert(at + strlen(".maxntid 256, 1, 1"), "\n.minnctapersm " + std::to_string(minCtas));
+    text += entry;
+    text += scaffold.epilogue;
+    unsigned spills = 0;
+    int rc = runPtxas(text, kKernelNames[which], cubin, &spills);
+    if(rc)
+      return rc;
+    if(getenv("VB200_JIT_VERBOSE"))
+      fprintf(stderr, "visor_b200 jit: %s minctas=%d spill stores=%u B cubin=%zu B\n", kKernelNames[which], minCtas,
+              spills, cubin.size());
+    if(spills <= kSpillTolerance || minCtas == 0 || forced)
+      break;
+    minCtas = 0;    // the occupancy bound costs real spills with this shader: let ptxas choose
+  }
   if(const char *prefix = getenv("VB200_DUMP_CUBIN"))
   {
     // developer aid: keep the cubin for cuobjdump -sass / -res-usage: <prefix>.<kernel>.cubin
@@ -1304,7 +1351,14 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     if(((uintptr_t)ibDev) & (isz - 1))
       return setError(VB200_ERR_INVALID, "index buffer offset is not aligned to the index size");
     phaseMark(0);
-    g.stats.kernel_launches += vb200::launch_index_range(ibDev, s->ib.index_type, first, usedVerts, g.range, g.stream);
+    // Which vertices to shade. When the bound vertex buffers hold no more vertices than the draw has
+    // indices (meshes: every vertex is referenced several times) all of them are shaded and the pass
+    // over the index buffer that finds [min, max] is skipped (C5: 48 MB of index reads). Otherwise
+    // (a small draw out of a large shared vertex buffer) the range is measured first.
+    if(vertexBound != 0xffffffffu && vertexBound <= usedVerts)
+      g.stats.kernel_launches += vb200::launch_set_range(g.range, 0u, vertexBound - 1u, g.stream);
+    else
+      g.stats.kernel_launches += vb200::launch_index_range(ibDev, s->ib.index_type, first, usedVerts, g.range, g.stream);
     if(vertexBound == 0xffffffffu)
     {
       // no strided attribute bounds the vertex count: read the range back (rare: index-only shaders)
