@@ -102,10 +102,10 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant (tile) kernel, from the
 # `ncu --set full` captures summarised under profiles/ (a profiler cannot run inside the timed bench, so
 # the per-launch figure of the same build and workload is recorded here; null when none was captured).
-NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_c3_resolve.txt, profiles/r01_ncu_c4_ordered.txt (ncu --set full, per launch)"
+NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_c3_kernels.txt, profiles/r01_ncu_c4_tile_ordered.txt (ncu --set full, per launch)"
 NCU_TRAFFIC = {
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 52638976 + 18938112,
-    ("c4", 1, "vb200_k_tile_ordered"): 40868352 + 384768,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 26697000 + 13490000,
+    ("c4", 1, "vb200_k_tile_ordered"): 34472000 + 84480,
 }
 
 
