@@ -285,6 +285,7 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
     // inside the old mirror: it stays allocated until the next flush has drained the stream.
     g.zombies.push_back(old.dev);
     nm.explicitReg |= old.explicitReg;
+    nm.deviceLocal |= old.explicitReg && old.deviceLocal;
     g.mirrors.erase(key);
   }
   if(pin)
@@ -937,14 +938,34 @@ int vb200_mem_register(void *host, uint64_t size)
   if(isDevicePointer(host))
     return VB200_OK;
   Mirror *m = findMirror(host, size);
-  if(m)
+  if(m && m->explicitReg)
+    return VB200_OK;    // a sub-range of an allocation that is already registered
+  // A registration states the exact extent of a live allocation. Automatically created mirrors that
+  // overlap it are caches of whatever used to live at these addresses (the library never learns that an
+  // unregistered array was freed): they must not be promoted — their range, page-locking and residency
+  // flags would then cover unrelated memory. Bring back what they still owe the host, then drop them.
+  const uintptr_t lo = (uintptr_t)host, hi = lo + size;
+  bool owed = false;
+  for(auto &kv : g.mirrors)
   {
-    if(!m->pinned && cudaHostRegister(m->host, m->size, cudaHostRegisterDefault) == cudaSuccess)
-      m->pinned = true;
+    const uintptr_t mlo = (uintptr_t)kv.second.host, mhi = mlo + kv.second.size;
+    if(mlo < hi && lo < mhi && !kv.second.explicitReg && !kv.second.written.empty())
+      owed = true;
+  }
+  if(owed && (rc = vb200_flush()))
+    return rc;
+  for(auto it = g.mirrors.begin(); it != g.mirrors.end();)
+  {
+    const uintptr_t mlo = (uintptr_t)it->second.host, mhi = mlo + it->second.size;
+    if(mlo < hi && lo < mhi && !it->second.explicitReg)
+    {
+      if((rc = materializeClears(it->second.dev, it->second.size)))
+        return rc;
+      g.zombies.push_back(it->second.dev);    // launches in flight may still address it; freed at the next flush
+      it = g.mirrors.erase(it);
+    }
     else
-      cudaGetLastError();
-    m->explicitReg = true;
-    return VB200_OK;
+      ++it;
   }
   return createMirror(host, size, true, &m);
 }
