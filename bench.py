@@ -212,6 +212,24 @@ def run_reference_arm(args, workload: str) -> None:
     print(json.dumps(line))
 
 
+def time_frames(gpu, L, submit, steps: int, warmup: int = 3) -> float:
+    """mean device time (ms) of `steps` frames on this GPU: L2 flushed before each, CUDA events on the
+    library stream around each frame"""
+    ms = C.c_float()
+    for _ in range(warmup):
+        submit()
+    gpu.flush()
+    times = []
+    for _ in range(steps):
+        gpu.check(L.vb200_l2_flush(), "l2_flush")
+        gpu.check(L.vb200_event_record(2), "event")
+        submit()
+        gpu.check(L.vb200_event_record(3), "event")
+        gpu.check(L.vb200_event_elapsed_ms(2, 3, C.byref(ms)), "elapsed")
+        times.append(ms.value)
+    return float(np.mean(times))
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, workload: str) -> None:
     rank = int(os.environ.get("RANK", "0"))
@@ -451,10 +469,19 @@ def run_ours(args, workload: str) -> None:
         t_e2e = float(tt.item())
     else:
         t_e2e = t_e2e_local
+    single = None
     if multi:
         barrier()    # nobody tears down memory that peers may still be storing into
         final = frame_host.copy().view(np.uint8).reshape(scene.height, scene.width, 4)
         img_hash = scenes.image_hash(final, None)
+        # the same workload on ONE of these GPUs (rank 0, tile ownership and exchange off, inputs resident):
+        # the denominator of the parallel efficiency, measured in the same run on the same box
+        if rank == 0:
+            gpu.check(L.vb200_set_tile_owner(0, 1), "set_tile_owner")
+            t1 = time_frames(gpu, L, bound.submit, max(3, min(args.steps, 10)))
+            single = {"value": tris / (t1 * 1e-3) / 1e6, "unit": "Mtri/s", "ms_per_step": t1, "n_gpus": 1,
+                      "note": "same workload, rank 0 alone, same run"}
+            gpu.flush()
         L.vb200_mem_unregister.argtypes = [C.c_void_p]
         L.vb200_mem_unregister(frame_host.ctypes.data)
         del band_host, frame_host
@@ -467,6 +494,27 @@ def run_ours(args, workload: str) -> None:
             return
     else:
         img_hash = scenes.image_hash(bound.color, bound.depth)
+
+    # N=1 run of the default workload: the scaling runs (N>1) use the 8K config, so its single-GPU time
+    # is reported next to the headline for a same-workload scaling curve
+    scaling_base = None
+    if not multi and getattr(args, "auto_workload", False) and workload != "c5":
+        gpu.check(L.vb200_set_sync_mode(1), "set_sync_mode")    # inputs resident in HBM, as for `value`
+        sc5 = build_scene("c5")
+        b5 = scenes.BoundScene(gpu, sc5)
+        for a, is_in in scene_host_buffers(b5):
+            gpu.check(L.vb200_mem_register(a.ctypes.data, a.nbytes), "mem_register")
+            if is_in:
+                gpu.check(L.vb200_mem_upload(a.ctypes.data, a.nbytes), "mem_upload")
+        t5 = time_frames(gpu, L, b5.submit, max(3, min(args.steps, 10)))
+        gpu.flush()
+        scaling_base = {"workload": WORKLOAD_DESC["c5"], "value": sc5.triangles() / (t5 * 1e-3) / 1e6,
+                        "unit": "Mtri/s", "ms_per_step": t5, "n_gpus": 1,
+                        "note": "the N>1 runs of this bench use this workload (sort-first over screen tiles)"}
+        L.vb200_mem_unregister.argtypes = [C.c_void_p]
+        for a, _ in scene_host_buffers(b5):
+            L.vb200_mem_unregister(a.ctypes.data)
+        del b5, sc5
 
     # ---------------- CPU baseline (rank 0, N = 1): the reference's own rasterizer ----------------
     cpu = None
@@ -524,6 +572,10 @@ def run_ours(args, workload: str) -> None:
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
+    if single:
+        line["single_gpu_same_workload"] = single
+    if scaling_base:
+        line["scaling_base"] = scaling_base
     if cpu:
         line["cpu_baseline"] = cpu
     if parity:
@@ -548,6 +600,7 @@ def main() -> None:
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     workload = args.workload
+    args.auto_workload = workload == "auto"
     if workload == "auto":
         workload = "c3" if args.gpus <= 1 else "c5"
     if args.impl == "reference":
