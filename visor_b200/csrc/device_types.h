@@ -106,4 +106,7 @@ struct Vb200RasterState
   uint32_t owner_rank, owner_world;    // sort-first tile ownership (tile % world == rank)
   uint32_t count_fragments;
   uint32_t color_bpp;
+  // resolve kernels: the visibility key's low word carries (triangle id << 8 | record slot), so the
+  // shading pass finds the winner's record in shared memory. Needs triangle ids below 2^24.
+  uint32_t slot_keys;
 };

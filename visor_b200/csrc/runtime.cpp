@@ -1559,6 +1559,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.rs.owner_world = g.ownerWorld;
   tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
   tp.rs.color_bpp = 4;
+  tp.rs.slot_keys = numTris < (1u << 24) - 1u ? 1u : 0u;
   tp.clear_flags = clearFlags;
   tp.clear_color = clearColorWord;
   tp.clear_depth = clearDepthValue;

@@ -413,8 +413,14 @@ struct TriCoef
   int A1, D1, E1, A2;
   int D2, E2, area, base;          // base = (y0 - tileY0)*32 + (x0 - tileX0)
   float invarea, d0, d1, d2;
-  uint32_t id, excl, skip, magic;  // triangle index + 1; first slot in the pixel stream; 32 - w; floor(2^16/w) + 1
+  uint32_t id, excl, skip, magic;  // key id (below); first slot in the pixel stream; 32 - w; floor(2^16/w) + 1
+  float invw0, invw1, invw2;       // what only the shading pass needs: perspective weights ...
+  uint32_t s0, s1, s2, pad;        // ... and the corners' post-VS record slots
 };
+// key id = triangle index + 1, or ((triangle index + 1) << 8 | record slot) when Vb200RasterState::slot_keys
+// is set: ids stay ordered by triangle index, and for a tile whose whole list fits one round (<= 256
+// triangles, the common case) phase B reads the winner's record from shared memory instead of gathering
+// the triangle and its three vertices from global memory again.
 
 // float -> uint32 whose unsigned order equals the float order (-0 == +0); callers exclude NaN
 __device__ __forceinline__ uint32_t vb200_depth_key(float d)
@@ -442,7 +448,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 {
   __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
   __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
-  __shared__ int4 s_coef[256][4];     // TriCoef records of the current round, one per thread
+  __shared__ int4 s_coef[256][6];     // TriCoef records of the current round, one per thread
   __shared__ uint32_t s_start[257];   // first stream slot of each record; [count] = stream length
   __shared__ uint32_t s_wsum[8];
 
@@ -511,7 +517,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const uint32_t i = base + threadIdx.x;
     const uint32_t m = min(256u, n - base);    // records in this round
     uint32_t cnt = 0;
-    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = make_int4(0, 0, 0, 65537);
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = make_int4(0, 0, 0, 65537), r4 = r0, r5 = r0;
     if(i < n)
     {
       const uint32_t t = p.list[off + i];
@@ -533,7 +539,10 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       // floor(li / w) == (li * magic) >> 16 for li < 1024, w <= 32 with magic = floor(65536 / w) + 1
       // (65536/w is either an integer or at least 1/32 away from one: far more than the 2-ulp error
       // of the fast division)
-      r3 = make_int4((int)(t + 1u), 0, VB200_TILE - w, (int)(__float2uint_rz(__fdividef(65536.0f, (float)w)) + 1u));
+      const uint32_t keyId = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
+      r3 = make_int4((int)keyId, 0, VB200_TILE - w, (int)(__float2uint_rz(__fdividef(65536.0f, (float)w)) + 1u));
+      r4 = make_int4(__float_as_int(su.invw0), __float_as_int(su.invw1), __float_as_int(su.invw2), (int)su.s0);
+      r5 = make_int4((int)su.s1, (int)su.s2, 0, 0);
     }
     // block-wide exclusive scan of cnt
     uint32_t incl = cnt;
@@ -562,6 +571,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     s_coef[threadIdx.x][1] = r1;
     s_coef[threadIdx.x][2] = r2;
     s_coef[threadIdx.x][3] = r3;
+    s_coef[threadIdx.x][4] = r4;
+    s_coef[threadIdx.x][5] = r5;
     s_start[threadIdx.x] = (i < n) ? myStart : total;
     if(threadIdx.x == 0)
       s_start[256] = total;
@@ -665,6 +676,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __syncthreads();
 
   // ---- phase B: shade the winner of every pixel, write back
+  const bool recordsInSmem = rs.slot_keys && n <= 256u;    // the only round's records are still staged
 #pragma unroll
   for(int j = 0; j < 4; j++)
   {
@@ -704,27 +716,51 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       continue;
     }
     shaded++;
-    const Vb200TriSetup su = vb200_load_setup(p, id - 1u);
-    // recompute exactly what the reference computes for this pixel (rasterizer.cpp:303-309,545-558)
-    const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
-    const int area2 = ABx * ACy - ABy * ACx;
-    const int sgn = area2 > 0 ? 1 : -1;
-    const int PAx = su.x0 - x, PAy = su.y0 - y;
-    const int ux = ACx * PAy - ACy * PAx, uy = PAx * ABy - PAy * ABx;
-    const int b0 = (area2 - (ux + uy)) * sgn, b1 = ux * sgn, b2 = uy * sgn;
-    float n0 = __fmul_rn((float)b0, su.invarea);
-    float n1 = __fmul_rn((float)b1, su.invarea);
-    float n2 = __fmul_rn((float)b2, su.invarea);
-    const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, su.d0), __fmul_rn(n1, su.d1)), __fmul_rn(n2, su.d2));
-    n0 = __fmul_rn(n0, su.invw0);
-    n1 = __fmul_rn(n1, su.invw1);
-    n2 = __fmul_rn(n2, su.invw2);
+    // the winner's edge values at this pixel, exactly as the reference computes them
+    // (rasterizer.cpp:303-309,545-558; int32 ring arithmetic, so both formulations give the same bits)
+    int b0, b1, b2;
+    float invarea, d0, d1, d2, invw0, invw1, invw2;
+    uint32_t s0, s1, s2;
+    if(recordsInSmem)
+    {
+      const uint32_t slot = id & 255u;
+      const int4 c0 = s_coef[slot][0], c1 = s_coef[slot][1], c2 = s_coef[slot][2], c3 = s_coef[slot][3];
+      const int4 c4 = s_coef[slot][4], c5 = s_coef[slot][5];
+      const int yq = ly - (c1.w >> 5), xr = lane - (c1.w & 31);
+      const int li = yq * (VB200_TILE - c3.z) + xr;
+      b1 = c0.x * li + c0.y * yq + c0.z;
+      b2 = c0.w * li + c1.x * yq + c1.y;
+      b0 = c1.z - (b1 + b2);
+      invarea = __int_as_float(c2.x); d0 = __int_as_float(c2.y); d1 = __int_as_float(c2.z); d2 = __int_as_float(c2.w);
+      invw0 = __int_as_float(c4.x); invw1 = __int_as_float(c4.y); invw2 = __int_as_float(c4.z);
+      s0 = (uint32_t)c4.w; s1 = (uint32_t)c5.x; s2 = (uint32_t)c5.y;
+    }
+    else
+    {
+      const Vb200TriSetup su = vb200_load_setup(p, (rs.slot_keys ? (id >> 8) : id) - 1u);
+      const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
+      const int area2 = ABx * ACy - ABy * ACx;
+      const int sgn = area2 > 0 ? 1 : -1;
+      const int PAx = su.x0 - x, PAy = su.y0 - y;
+      const int ux = ACx * PAy - ACy * PAx, uy = PAx * ABy - PAy * ABx;
+      b0 = (area2 - (ux + uy)) * sgn; b1 = ux * sgn; b2 = uy * sgn;
+      invarea = su.invarea; d0 = su.d0; d1 = su.d1; d2 = su.d2;
+      invw0 = su.invw0; invw1 = su.invw1; invw2 = su.invw2;
+      s0 = su.s0; s1 = su.s1; s2 = su.s2;
+    }
+    float n0 = __fmul_rn((float)b0, invarea);
+    float n1 = __fmul_rn((float)b1, invarea);
+    float n2 = __fmul_rn((float)b2, invarea);
+    const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));
+    n0 = __fmul_rn(n0, invw0);
+    n1 = __fmul_rn(n1, invw1);
+    n2 = __fmul_rn(n2, invw2);
     const float invlen = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(n0, n1), n2));
     n0 = __fmul_rn(n0, invlen);
     n1 = __fmul_rn(n1, invlen);
     n2 = __fmul_rn(n2, invlen);
-    const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)su.s0 * rs.nslots,
-                                p.interps + (size_t)su.s1 * rs.nslots, p.interps + (size_t)su.s2 * rs.nslots);
+    const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)s0 * rs.nslots,
+                                p.interps + (size_t)s1 * rs.nslots, p.interps + (size_t)s2 * rs.nslots);
     const size_t gi = (size_t)y * rs.width + x;
     vb200_store_color(p, gi, vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]));
     if(depthWrite)
