@@ -402,6 +402,38 @@ enum
   VB200_RES_LAST_WINS = 4,    // no test / static test: highest triangle id that passes
 };
 
+// Shared-memory accesses of the resolve kernel's inner loop through explicit 32-bit shared-window
+// addresses. ptxas otherwise re-derives the window base (S2R SR_CgaCtaId + LEA) inside the loop for
+// every access instead of holding it in a register (~8 of 83 instructions per step, plus the S2R latency).
+__device__ __forceinline__ uint32_t vb200_smem_addr(const void *p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t vb200_lds32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 vb200_lds128(uint32_t a)
+{
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long vb200_lds64(uint32_t a)
+{
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long vb200_atoms_cas64(uint32_t a, unsigned long long cmp, unsigned long long val)
+{
+  unsigned long long old;
+  asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
+  return old;
+}
+
 // Per-triangle raster record staged in shared memory (64 B, one per lane of the warp that loaded it).
 // A candidate pixel is addressed by its index li inside the triangle's tile-clipped bbox (row-major,
 // width w): yq = li / w. With everything re-based to that index,
@@ -600,9 +632,10 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
       // work of step s, so it is issued first each iteration: its shared-memory round trip and the
       // warp reductions overlap the coverage / depth arithmetic instead of heading the next iteration.
+      const uint32_t aStart = vb200_smem_addr(s_start), aCoef = vb200_smem_addr(s_coef), aVis = vb200_smem_addr(vis);
       uint32_t starts, nextOwner0;
       {
-        const uint32_t rel = s_start[min(owner0 + 1u + (uint32_t)lane, 256u)] - (firstStep << 5);
+        const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (firstStep << 5);
         starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
         nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
       }
@@ -614,12 +647,13 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), 255u);
         owner0 = nextOwner0;
         {
-          const uint32_t rel = s_start[min(owner0 + 1u + (uint32_t)lane, 256u)] - (k + 32u);
+          const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (k + 32u);
           starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
           nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
         }
         const bool valid = g < total;
-        const int4 c0 = s_coef[owner][0], c1 = s_coef[owner][1], c3 = s_coef[owner][3];
+        const uint32_t aRec = aCoef + owner * (uint32_t)sizeof(s_coef[0]);
+        const int4 c0 = vb200_lds128(aRec), c1 = vb200_lds128(aRec + 16u), c3 = vb200_lds128(aRec + 48u);
         const int li = valid ? (int)(g - (uint32_t)c3.y) : 0;
         const int yq = (int)(((uint32_t)li * (uint32_t)c3.w) >> 16);
         const int b1 = c0.x * li + c0.y * yq + c0.z;
@@ -627,7 +661,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         const int b0 = c1.z - (b1 + b2);
         const int idx = c1.w + li + yq * c3.z;
         // the slot's current key is fetched before the depth arithmetic that decides whether it is needed
-        unsigned long long seen = vis[idx];
+        const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
+        unsigned long long seen = vb200_lds64(aSlot);
         if(!valid || (b0 | b1 | b2) < 0)
           continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
         covered++;
@@ -637,7 +672,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
           key = (unsigned long long)(~id);
         else
         {
-          const int4 c2 = s_coef[owner][2];
+          const int4 c2 = vb200_lds128(aRec + 32u);
           const float invarea = __int_as_float(c2.x);
           const float n0 = __fmul_rn((float)b0, invarea);
           const float n1 = __fmul_rn((float)b1, invarea);
@@ -665,7 +700,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         // (the common case is no attempt at all, or one that succeeds)
         while(key < seen)
         {
-          const unsigned long long prev = atomicCAS(&vis[idx], seen, key);
+          const unsigned long long prev = vb200_atoms_cas64(aSlot, seen, key);
           if(prev == seen)
             break;
           seen = prev;
