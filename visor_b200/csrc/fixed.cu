@@ -128,14 +128,14 @@ __device__ __forceinline__ bool tile_owned(uint32_t tile, uint32_t rank, uint32_
 // mesh land in the same tile, so per-lane atomics on the tile counters would serialise in the L2
 // atomic unit; __match_any_sync lets one lane per (warp, tile) do the atomic for the whole group.
 // Ranges of up to 2x2 tiles (every triangle smaller than a tile) take the matched path; larger ones
-// (full-screen triangles cover thousands of tiles) are spread over the warp, one tile per lane.
+// (full-screen triangles cover thousands of tiles) are spread over the whole CTA, one tile per thread.
+// Must be called by every thread of the CTA (it synchronises).
 template <typename F>
 __device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32_t tiles_x, uint32_t rank,
                                               uint32_t world, uint32_t tri, F f)
 {
   const uint32_t tx0 = tiles & 0xffu, ty0 = (tiles >> 8) & 0xffu, tx1 = (tiles >> 16) & 0xffu, ty1 = tiles >> 24;
   const uint32_t nx = alive ? (tx1 - tx0 + 1u) : 0u, ny = alive ? (ty1 - ty0 + 1u) : 0u;
-  const uint32_t nt = nx * ny;
   const bool big = nx > 2u || ny > 2u;
   const uint32_t lane = threadIdx.x & 31u;
   if(__any_sync(0xffffffffu, alive && !big))
@@ -156,19 +156,32 @@ __device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32
         f(tile, tri, __popc(peers & ((1u << lane) - 1u)), __popc(peers), (uint32_t)(__ffs(peers) - 1) == lane, peers);
     }
   }
-  uint32_t mask = __ballot_sync(0xffffffffu, alive && big);
-  while(mask)
+  // Large ranges: queued in shared memory, then every thread of the CTA takes tiles of each queued
+  // triangle (one warp walking the ~1000 tiles of a cube face alone made the fill pass of a 12-triangle
+  // draw take 36 us: one returning atomic per tile, 32 at a time).
+  __shared__ uint32_t s_big[kThreads][2];
+  __shared__ uint32_t s_nbig;
+  if(threadIdx.x == 0)
+    s_nbig = 0;
+  __syncthreads();
+  if(alive && big)
   {
-    const int src = __ffs(mask) - 1;
-    mask &= mask - 1u;
-    const uint32_t b_tx0 = __shfl_sync(0xffffffffu, tx0, src), b_ty0 = __shfl_sync(0xffffffffu, ty0, src);
-    const uint32_t b_nx = __shfl_sync(0xffffffffu, nx, src), b_nt = __shfl_sync(0xffffffffu, nt, src);
-    const uint32_t b_tri = __shfl_sync(0xffffffffu, tri, src);
-    for(uint32_t k = lane; k < b_nt; k += 32u)
+    const uint32_t slot = atomicAdd(&s_nbig, 1u);
+    s_big[slot][0] = tiles;
+    s_big[slot][1] = tri;
+  }
+  __syncthreads();
+  const uint32_t nbig = s_nbig;
+  for(uint32_t b = 0; b < nbig; b++)
+  {
+    const uint32_t bt = s_big[b][0], b_tri = s_big[b][1];
+    const uint32_t b_tx0 = bt & 0xffu, b_ty0 = (bt >> 8) & 0xffu;
+    const uint32_t b_nx = ((bt >> 16) & 0xffu) - b_tx0 + 1u, b_nt = b_nx * ((bt >> 24) - b_ty0 + 1u);
+    for(uint32_t k = threadIdx.x; k < b_nt; k += kThreads)
     {
       const uint32_t tile = (b_ty0 + k / b_nx) * tiles_x + b_tx0 + k % b_nx;
       if(tile_owned(tile, rank, world))
-        f(tile, b_tri, 0u, 1u, true, 0u);    // distinct tiles per lane: every lane is its own group
+        f(tile, b_tri, 0u, 1u, true, 0u);    // distinct tiles per thread: every thread is its own group
     }
   }
 }
@@ -393,28 +406,31 @@ __device__ __forceinline__ void cmpxchg(uint32_t *a, uint32_t lo, uint32_t hi)
   }
 }
 
-__device__ void bitonic_sort(uint32_t *a, uint32_t n)
+// Force-inlined so that a call on the __shared__ staging array compiles to LDS/STS; strides are powers
+// of two, so every index is shifts and masks.
+__device__ __forceinline__ void bitonic_sort(uint32_t *a, uint32_t n)
 {
-  uint32_t N = 1;
-  while(N < n)
-    N <<= 1;
-  const uint32_t half = N >> 1;
-  for(uint32_t k = 2; k <= N; k <<= 1)
+  uint32_t logN = 0;
+  while((1u << logN) < n)
+    logN++;
+  const uint32_t half = (1u << logN) >> 1;
+  for(uint32_t lk = 1; lk <= logN; lk++)    // k = 1 << lk
   {
-    const uint32_t hk = k >> 1;
+    const uint32_t k = 1u << lk, hk = k >> 1;
     for(uint32_t i = threadIdx.x; i < half; i += blockDim.x)
     {
-      const uint32_t blk = i / hk, pos = i % hk;
-      const uint32_t lo = blk * k + pos, hi = blk * k + (k - 1u - pos);
+      const uint32_t base = (i >> (lk - 1u)) << lk, pos = i & (hk - 1u);
+      const uint32_t lo = base + pos, hi = base + (k - 1u - pos);
       if(hi < n)
         cmpxchg(a, lo, hi);
     }
     __syncthreads();
-    for(uint32_t j = k >> 2; j > 0; j >>= 1)
+    for(uint32_t lj = lk - 1u; lj-- > 0u;)    // j = 1 << lj, from k/4 down to 1
     {
+      const uint32_t j = 1u << lj;
       for(uint32_t i = threadIdx.x; i < half; i += blockDim.x)
       {
-        const uint32_t lo = (i / j) * 2u * j + (i % j), hi = lo + j;
+        const uint32_t lo = ((i >> lj) << (lj + 1u)) + (i & (j - 1u)), hi = lo + j;
         if(hi < n)
           cmpxchg(a, lo, hi);
       }
@@ -429,7 +445,7 @@ __global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_
                                                   const uint32_t *tile_count, const uint32_t *total,
                                                   uint32_t capacity)
 {
-  __shared__ uint32_t s[kSortSmem];
+  __shared__ __align__(16) uint32_t s[kSortSmem];
   if(*total > capacity)
     return;
   const uint32_t tile = blockIdx.x;
@@ -442,7 +458,28 @@ __global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_
     unsorted |= a[i] > a[i + 1u];
   if(!__syncthreads_or(unsorted))
     return;
-  if(n <= kSortSmem)
+  if(n <= 512u)
+  {
+    // short lists (the common case: a few hundred triangles per tile): rank sort. Triangle ids are
+    // unique, so an id's final position is the number of smaller ids; every thread counts that for its
+    // own elements against broadcast reads of the staged list — no barriers, no data-dependent branches.
+    const uint32_t n4 = (n + 3u) & ~3u;
+    for(uint32_t i = threadIdx.x; i < n4; i += blockDim.x)
+      s[i] = i < n ? a[i] : 0xffffffffu;
+    __syncthreads();
+    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+      const uint32_t e = s[i];
+      uint32_t r = 0;
+      for(uint32_t j = 0; j < n4; j += 4u)
+      {
+        const uint4 v = *(const uint4 *)(s + j);
+        r += (v.x < e) + (v.y < e) + (v.z < e) + (v.w < e);
+      }
+      a[r] = e;
+    }
+  }
+  else if(n <= kSortSmem)
   {
     for(uint32_t i = threadIdx.x; i < n; i += blockDim.x)
       s[i] = a[i];

@@ -185,7 +185,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   __shared__ __align__(16) TriSmem s_tri[8][32];
   __shared__ uint32_t s_col[8][128];
   __shared__ float s_dep[8][128];
-  __shared__ uint8_t s_queue[8][128];
+  __shared__ uint16_t s_queue[8][256];    // per-warp fragment ring: (triangle slot << 7) | region pixel
   __shared__ float s_unorm[256];    // float(byte) / 255.0f, the reference's destination read (rasterizer.cpp:595-599)
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
@@ -211,7 +211,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
   uint32_t *wcol = s_col[warp];
   float *wdep = s_dep[warp];
-  uint8_t *wq = s_queue[warp];
+  uint16_t *wq = s_queue[warp];
   TriSmem *wtri = s_tri[warp];
 
   // region pixel i (0..127): x = rx0 + (i & 15), y = ry0 + (i >> 4); lane l loads/tests pixels l + 32j
@@ -228,6 +228,76 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   __syncthreads();    // s_unorm is shared by all warps; after this the warps run independently
   uint32_t covered = 0, shaded = 0;
   const int lx = lane & 15, ly = lane >> 4;    // lane's pixel column / first row inside the region
+  const uint32_t below = (1u << lane) - 1u;
+  uint32_t qhead = 0, qcount = 0;              // the warp's fragment ring (uniform across the lanes)
+
+  // One pass over the first `cnt` (<= 32) queued fragments, one per lane. Fragments of DIFFERENT
+  // triangles share a pass, so two lanes may hold the same pixel (the two triangles of a quad both
+  // cover their common edge). Only the first fragment of each pixel is shaded in this pass; the later
+  // ones go back to the front of the ring, in order, and lead the next pass.
+  auto shade_pass = [&](uint32_t cnt) {
+    const bool mine = (uint32_t)lane < cnt;
+    const uint32_t e = wq[(qhead + (uint32_t)lane) & 255u];
+    const int i = (int)(e & 127u);
+    const uint32_t lanes = __ballot_sync(0xffffffffu, mine);
+    bool first = false;
+    if(mine)
+      first = (__match_any_sync(lanes, i) & below) == 0u;    // no earlier fragment of my pixel in this pass
+    const uint32_t later = __ballot_sync(0xffffffffu, mine && !first);
+    {
+      if(first)
+      {
+        const TriSmem &t = wtri[e >> 7];
+        const int x = i & 15, y = i >> 4;
+        const int b1 = t.A1 * x + t.B1 * y + t.C1, b2 = t.A2 * x + t.B2 * y + t.C2, b0 = t.area - (b1 + b2);
+        // rasterizer.cpp:552-558
+        float n0 = __fmul_rn((float)b0, t.invarea);
+        float n1 = __fmul_rn((float)b1, t.invarea);
+        float n2 = __fmul_rn((float)b2, t.invarea);
+        const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, t.d0), __fmul_rn(n1, t.d1)), __fmul_rn(n2, t.d2));
+        if(!depthTest || vb200_depth_pass(rs.depth_op, pixdepth, wdep[i]))
+        {
+          shaded++;
+          // perspective correction (rasterizer.cpp:581-588)
+          n0 = __fmul_rn(n0, t.invw0);
+          n1 = __fmul_rn(n1, t.invw1);
+          n2 = __fmul_rn(n2, t.invw2);
+          const float invlen = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(n0, n1), n2));
+          n0 = __fmul_rn(n0, invlen);
+          n1 = __fmul_rn(n1, invlen);
+          n2 = __fmul_rn(n2, invlen);
+
+          float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)t.s0 * rs.nslots,
+                                p.interps + (size_t)t.s1 * rs.nslots, p.interps + (size_t)t.s2 * rs.nslots);
+          const uint32_t cur = wcol[i];
+          if(blend)
+          {
+            // blend (rasterizer.cpp:593-672): existing = bytes (2,1,0) / 255.0f from the exact table
+            const float ex = s_unorm[(cur >> 16) & 0xffu], ey = s_unorm[(cur >> 8) & 0xffu], ez = s_unorm[cur & 0xffu];
+            const float oma = __fsub_rn(1.0f, pix.w);
+            const float srcF = vb200_factor_sel(rs.src_factor, pix.w, oma);
+            const float dstF = vb200_factor_sel(rs.dst_factor, pix.w, oma);
+            pix.x = __fadd_rn(__fmul_rn(srcF, pix.x), __fmul_rn(dstF, ex));
+            pix.y = __fadd_rn(__fmul_rn(srcF, pix.y), __fmul_rn(dstF, ey));
+            pix.z = __fadd_rn(__fmul_rn(srcF, pix.z), __fmul_rn(dstF, ez));
+          }
+          // truncating BGR store, alpha byte untouched (rasterizer.cpp:674-676)
+          const uint32_t r = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.x), 255.0f));
+          const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.y), 255.0f));
+          const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.z), 255.0f));
+          wcol[i] = (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
+          if(depthWrite)
+            wdep[i] = pixdepth;
+        }
+      }
+    }
+    const uint32_t keep = __popc(later);
+    if(mine && !first)
+      wq[(qhead + cnt - keep + __popc(later & below)) & 255u] = (uint16_t)e;
+    __syncwarp();    // a later fragment of the same pixel (in a later pass) sees this one; ring updated
+    qhead = (qhead + cnt - keep) & 255u;
+    qcount -= cnt - keep;
+  };
 
   for(uint32_t base = 0; base < n; base += 32u)
   {
@@ -278,7 +348,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     uint32_t hits = __ballot_sync(0xffffffffu, touches);
     __syncwarp();
 
-    // ---- 2./3. surviving triangles in list order
+    // ---- 2. surviving triangles in list order: coverage -> fragment ring
     while(hits)
     {
       const int k = __ffs(hits) - 1;
@@ -302,59 +372,20 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
       if(total == 0u)
         continue;
       covered += (lane == 0) ? total : 0u;
-      // compact the covered pixel indices of the region into the warp's queue (row-major order)
-      const uint32_t below = (1u << lane) - 1u;
-      if(m[0] & (1u << lane)) wq[__popc(m[0] & below)] = (uint8_t)lane;
-      if(m[1] & (1u << lane)) wq[c0 + __popc(m[1] & below)] = (uint8_t)(lane + 32);
-      if(m[2] & (1u << lane)) wq[c1 + __popc(m[2] & below)] = (uint8_t)(lane + 64);
-      if(m[3] & (1u << lane)) wq[c2 + __popc(m[3] & below)] = (uint8_t)(lane + 96);
+      // append the covered pixels (row-major) to the ring, tagged with the triangle's slot
+      const uint32_t tail = qhead + qcount, tag = (uint32_t)k << 7;
+      if(m[0] & (1u << lane)) wq[(tail + __popc(m[0] & below)) & 255u] = (uint16_t)(tag | (uint32_t)lane);
+      if(m[1] & (1u << lane)) wq[(tail + c0 + __popc(m[1] & below)) & 255u] = (uint16_t)(tag | (uint32_t)(lane + 32));
+      if(m[2] & (1u << lane)) wq[(tail + c1 + __popc(m[2] & below)) & 255u] = (uint16_t)(tag | (uint32_t)(lane + 64));
+      if(m[3] & (1u << lane)) wq[(tail + c2 + __popc(m[3] & below)) & 255u] = (uint16_t)(tag | (uint32_t)(lane + 96));
+      qcount += total;
       __syncwarp();
-      for(uint32_t f = lane; f < total; f += 32u)
-      {
-        const int i = wq[f];
-        const int x = i & 15, y = i >> 4;
-        const int b1 = t.A1 * x + t.B1 * y + t.C1, b2 = t.A2 * x + t.B2 * y + t.C2, b0 = t.area - (b1 + b2);
-        // rasterizer.cpp:552-558
-        float n0 = __fmul_rn((float)b0, t.invarea);
-        float n1 = __fmul_rn((float)b1, t.invarea);
-        float n2 = __fmul_rn((float)b2, t.invarea);
-        const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, t.d0), __fmul_rn(n1, t.d1)), __fmul_rn(n2, t.d2));
-        if(depthTest && !vb200_depth_pass(rs.depth_op, pixdepth, wdep[i]))
-          continue;
-        shaded++;
-        // perspective correction (rasterizer.cpp:581-588)
-        n0 = __fmul_rn(n0, t.invw0);
-        n1 = __fmul_rn(n1, t.invw1);
-        n2 = __fmul_rn(n2, t.invw2);
-        const float invlen = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(n0, n1), n2));
-        n0 = __fmul_rn(n0, invlen);
-        n1 = __fmul_rn(n1, invlen);
-        n2 = __fmul_rn(n2, invlen);
-
-        float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)t.s0 * rs.nslots,
-                              p.interps + (size_t)t.s1 * rs.nslots, p.interps + (size_t)t.s2 * rs.nslots);
-        const uint32_t cur = wcol[i];
-        if(blend)
-        {
-          // blend (rasterizer.cpp:593-672): existing = bytes (2,1,0) / 255.0f from the exact table
-          const float ex = s_unorm[(cur >> 16) & 0xffu], ey = s_unorm[(cur >> 8) & 0xffu], ez = s_unorm[cur & 0xffu];
-          const float oma = __fsub_rn(1.0f, pix.w);
-          const float srcF = vb200_factor_sel(rs.src_factor, pix.w, oma);
-          const float dstF = vb200_factor_sel(rs.dst_factor, pix.w, oma);
-          pix.x = __fadd_rn(__fmul_rn(srcF, pix.x), __fmul_rn(dstF, ex));
-          pix.y = __fadd_rn(__fmul_rn(srcF, pix.y), __fmul_rn(dstF, ey));
-          pix.z = __fadd_rn(__fmul_rn(srcF, pix.z), __fmul_rn(dstF, ez));
-        }
-        // truncating BGR store, alpha byte untouched (rasterizer.cpp:674-676)
-        const uint32_t r = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.x), 255.0f));
-        const uint32_t g = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.y), 255.0f));
-        const uint32_t b = (uint32_t)__float2int_rz(__fmul_rn(__saturatef(pix.z), 255.0f));
-        wcol[i] = (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
-        if(depthWrite)
-          wdep[i] = pixdepth;
-      }
-      __syncwarp();    // the next triangle may touch the same pixels / reuse the queue
+      // ---- 3. full 32-fragment passes as soon as the ring holds them
+      while(qcount >= 32u)
+        shade_pass(32u);
     }
+    while(qcount)    // the triangle slots are about to be reused: drain what is left of this batch
+      shade_pass(min(qcount, 32u));
     __syncwarp();    // wtri is overwritten by the next 32 triangles
   }
 
