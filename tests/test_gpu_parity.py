@@ -332,3 +332,101 @@ def test_clear_fusion_variants(gpu, vor):
     _check(gpu, vor, c)
     d = scenes.random_triangles(64, 48, 3, 94, max_size=0.05)   # most tiles untouched: they still get cleared
     _check(gpu, vor, d)
+
+
+def test_draw_edge_cases(gpu, vor):
+    """empty and ragged draws: zero vertices, a trailing partial triangle (dropped, rasterizer.cpp:128-149),
+    a sub-range selected with `first`, an unsupported topology (draws nothing, :235), and an
+    image whose size is not a multiple of the tile"""
+    import copy
+    base = scenes.random_triangles(97, 65, 40, 31)
+    d0 = base.draws[0]
+    variants = []
+    for count, first in [(0, 0), (1, 0), (2, 0), (4, 0), (7, 3), (d0.count - 3, 3), (d0.count, 0)]:
+        sc = copy.deepcopy(base)
+        sc.draws[0].count, sc.draws[0].first = count, first
+        variants.append(sc)
+    sc = copy.deepcopy(base)
+    sc.draws[0].pipe.topology = 1    # VK_PRIMITIVE_TOPOLOGY_LINE_LIST: "Unsupported primitive topology!"
+    variants.append(sc)
+    idx = scenes.random_triangles(97, 65, 40, 32, index_type=abi.INDEX_U16)
+    for count, first in [(0, 0), (5, 1), (idx.draws[0].count - 6, 6)]:
+        sc = copy.deepcopy(idx)
+        sc.draws[0].count, sc.draws[0].first = count, first
+        variants.append(sc)
+    for sc in variants:
+        _check(gpu, vor, sc)
+
+
+def test_sort_first_ownership_and_exchange_kernels(gpu, vor):
+    """tile ownership on ONE GPU: each 'rank' renders only the tiles it owns (tile % world == rank); the
+    union of the owned pixels, the pack -> concatenate -> unpack path (k_tiles_pack/_unpack against the
+    numpy mirror in harness/tiles.py) and the fused path (peer colour stores, here into buffers on the
+    same device) must all reproduce the single-rank image"""
+    from harness import tiles
+    L = gpu.lib
+    L.vb200_set_tile_owner.argtypes = [C.c_int, C.c_int]
+    L.vb200_tiles_pack.argtypes = [C.POINTER(abi.Image), C.c_void_p, C.c_uint64]
+    L.vb200_tiles_unpack.argtypes = [C.POINTER(abi.Image), C.c_void_p, C.c_uint64, C.c_int]
+    L.vb200_tiles_per_rank.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.vb200_tiles_per_rank.restype = C.c_uint32
+    L.vb200_mem_device_ptr.argtypes = [C.c_void_p]
+    L.vb200_mem_device_ptr.restype = C.c_void_p
+    L.vb200_mem_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.vb200_mem_unregister.argtypes = [C.c_void_p]
+    L.vb200_mem_download.argtypes = [C.c_void_p, C.c_uint64]
+    L.vb200_set_peer_targets.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+    W, H, world = 333, 211, 3
+    blend = (abi.BF_SRC_ALPHA, abi.BF_ONE_MINUS_SRC_ALPHA, 0)
+    for kwargs in ({}, {"blend": blend, "depth_write": False}):    # resolve path, ordered path
+        sc = scenes.random_triangles(W, H, 150, 41, **kwargs)
+        want, _ = scenes.render(vor, sc)
+        slots = L.vb200_tiles_per_rank(W, H, world)
+        assert slots == tiles.tiles_per_rank(W, H, world)
+        gathered = np.zeros((world, slots * 4096), np.uint8)
+        union = np.zeros_like(want)
+        peers = [np.zeros((H, W, 4), np.uint8) for _ in range(2)]    # stand-ins for two other ranks' images
+        try:
+            for pbuf in peers + [gathered]:
+                gpu.check(L.vb200_mem_register(pbuf.ctypes.data, pbuf.nbytes), "mem_register")
+            for r in range(world):
+                gpu.check(L.vb200_set_tile_owner(r, world), "set_tile_owner")
+                bound = scenes.BoundScene(gpu, sc)
+                ptrs = (C.c_void_p * 2)(*[L.vb200_mem_device_ptr(pbuf.ctypes.data) for pbuf in peers])
+                dev_color = None
+                bound.submit()    # first submit creates the colour mirror; peer targets are keyed by its device address
+                gpu.flush()
+                dev_color = L.vb200_mem_device_ptr(bound.color.ctypes.data)
+                gpu.check(L.vb200_set_peer_targets(dev_color, ptrs, 2), "set_peer_targets")
+                bound.submit()
+                send = gathered[r]    # registered below: the pack kernel writes device memory
+                gpu.check(L.vb200_tiles_pack(C.byref(bound.color_img), L.vb200_mem_device_ptr(send.ctypes.data),
+                                             send.nbytes), "tiles_pack")
+                gpu.check(L.vb200_mem_download(send.ctypes.data, send.nbytes), "mem_download")
+                gpu.flush()
+                gpu.check(L.vb200_set_peer_targets(dev_color, None, 0), "set_peer_targets")
+                own = tiles.owned_mask(W, H, r, world)
+                assert np.array_equal(bound.color[own], want[own]), f"rank {r}: owned pixels differ"
+                union[own] = bound.color[own]
+                assert np.array_equal(send, tiles.pack(np.where(own[..., None], bound.color, 0).astype(np.uint8), r, world))
+            gpu.check(L.vb200_set_tile_owner(0, 1), "set_tile_owner")
+            assert np.array_equal(union, want)
+            # un-tile the "all-gathered" buffer on the device
+            out = np.zeros((H, W, 4), np.uint8)
+            im = abi.make_image(out, W, H, abi.FMT_B8G8R8A8_UNORM)
+            flat = gathered.reshape(-1)    # already resident in its mirror (the pack kernels wrote it there)
+            gpu.check(L.vb200_tiles_unpack(C.byref(im), L.vb200_mem_device_ptr(flat.ctypes.data), flat.nbytes, world),
+                      "tiles_unpack")
+            gpu.flush()
+            assert np.array_equal(out, want)
+            assert np.array_equal(out, tiles.unpack(flat, W, H, world))
+            # fused exchange: every rank stored its pixels into both "peer" images
+            for pbuf in peers:
+                gpu.check(L.vb200_mem_download(pbuf.ctypes.data, pbuf.nbytes), "mem_download")
+            gpu.flush()
+            for pbuf in peers:
+                assert np.array_equal(pbuf, want)
+        finally:
+            L.vb200_set_tile_owner(0, 1)
+            for pbuf in peers + [gathered]:
+                L.vb200_mem_unregister(pbuf.ctypes.data)

@@ -518,7 +518,12 @@ __global__ void __launch_bounds__(kThreads) k_tiles_pack(const uint32_t *color, 
   const uint32_t k = blockIdx.x;
   const uint32_t tile = rank + k * world;
   if(tile >= ntiles)
+  {
+    // the last slot of a rank that owns one tile fewer: defined contents for the all-gather
+    for(uint32_t i = threadIdx.x; i < VB200_TILE * VB200_TILE; i += blockDim.x)
+      dst[(size_t)k * 1024u + i] = 0u;
     return;
+  }
   const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
   for(uint32_t i = threadIdx.x; i < VB200_TILE * VB200_TILE; i += blockDim.x)
   {
