@@ -21,7 +21,19 @@ SCENES = {
     "c5": lambda: scenes.c5_textured(640, 360, 160, 80, tex_size=128),
     "strip_u16": lambda: scenes.random_triangles(320, 200, 62, 9, topology=abi.TOPO_STRIP, index_type=abi.INDEX_U16),
     "load_op_load": lambda: _no_clear(scenes.random_triangles(200, 120, 50, 3)),
+    "c2_bc2": lambda: _bc_cube(abi.FMT_BC2_UNORM_BLOCK),
+    "c2_bc3": lambda: _bc_cube(abi.FMT_BC3_UNORM_BLOCK),
 }
+
+
+def _bc_cube(fmt):
+    """the C2 cube sampling a block-compressed texture uploaded through a staging buffer +
+    vkCmdCopyBufferToImage into DEVICE_LOCAL memory"""
+    sc = scenes.c2_cube(320, 180)
+    d = sc.draws[0]
+    s, b, _, _, _, _, _, layers = d.textures[0]
+    d.textures = [(s, b, scenes.bc_blocks(np.random.default_rng(21), 128, 64), 128, 64, fmt, 1, layers)]
+    return sc
 
 
 def _no_clear(sc):

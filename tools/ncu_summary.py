@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Developer aid: condense an .ncu-rep (ncu --set full) into the handful of metrics DESIGN.md / bench.py
-quote. usage: tools_ncu_summary.py <report.ncu-rep> [out.txt]"""
+quote. usage: tools/ncu_summary.py <report.ncu-rep> [out.txt]"""
 import csv
 import subprocess
 import sys

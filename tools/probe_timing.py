@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Developer aid (runs on the GPU box): where does a C3 frame's device time go — kernels, the L2 flush's
-write-back, or host enqueue gaps?  usage: python tools_probe_timing.py [workload]"""
+write-back, or host enqueue gaps?  usage: python tools/probe_timing.py [workload]"""
 import ctypes as C, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from harness import abi, scenes
 import bench

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Developer aid: turn gpurun_out/refresh/ (written by tools_refresh_profiles.sh on the GPU box) into the
-committed text/CSV/JSON evidence under profiles/.  usage: python tools_refresh_profiles.py [round_tag]"""
+"""Developer aid: turn gpurun_out/refresh/ (written by tools/refresh_profiles.sh on the GPU box) into the
+committed text/CSV/JSON evidence under profiles/.  usage: python tools/refresh_profiles.py [round_tag]"""
 import csv, json, os, shutil, subprocess, sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-here = os.path.dirname(os.path.abspath(__file__))
+here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))    # repo root
 src = os.path.join(here, "gpurun_out", "refresh")
 dst = os.path.join(here, "profiles")
 
@@ -30,7 +30,7 @@ with open(os.path.join(dst, f"{tag}_launches_c3.csv"), "w") as f:
         w.writerow([r[ii], r[ki], r[vi], r[ui]])
 
 def summary(rep, out):
-    text = subprocess.run([sys.executable, os.path.join(here, "tools_ncu_summary.py"), rep], capture_output=True,
+    text = subprocess.run([sys.executable, os.path.join(here, "tools", "ncu_summary.py"), rep], capture_output=True,
                           text=True).stdout
     open(out, "w").write(text)
 
@@ -41,7 +41,7 @@ def hot_lines(rep, cubin, kernel, out):
     srccsv = rep.replace(".ncu-rep", "_source.csv")
     with open(srccsv, "w") as f:
         subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=f, stderr=subprocess.DEVNULL)
-    text = subprocess.run([sys.executable, os.path.join(here, "tools_sass_lines.py"), srccsv, cubin, kernel, "45"],
+    text = subprocess.run([sys.executable, os.path.join(here, "tools", "sass_lines.py"), srccsv, cubin, kernel, "45"],
                           capture_output=True, text=True).stdout
     open(out, "w").write(text)
 

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Developer aid, runs ON THE GPU BOX (gpurun -- 'bash tools_refresh_profiles.sh'): regenerates the raw
-# material of profiles/ into gpurun_out/refresh/. Afterwards run tools_refresh_profiles.py here.
+# Developer aid, runs ON THE GPU BOX (gpurun -- 'bash tools/refresh_profiles.sh'): regenerates the raw
+# material of profiles/ into gpurun_out/refresh/. Afterwards run tools/refresh_profiles.py here.
 set -u
 O=gpurun_out/refresh
 mkdir -p $O

@@ -1,6 +1,6 @@
 """Developer aid: hammer the deferred-clear scenes to catch rare races (runs on the GPU box)."""
 import sys
-import os; sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from harness import abi, scenes
 gpu = abi.backend("vb200", 0)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Developer aid: join an `ncu --page source --csv` SASS export with `nvdisasm -g` line info of the
 same linked cubin, and rank CUDA source lines by executed warp instructions / stall samples.
-usage: tools_sass_lines.py <ncu_sass.csv> <linked.cubin> <kernel_name> [top_n]
+usage: tools/sass_lines.py <ncu_sass.csv> <linked.cubin> <kernel_name> [top_n]
 (kernel_name is matched as a substring of both the demangled ncu name and the mangled .text section)"""
 import csv, re, subprocess, sys, os
 csvp, cubin, kern = sys.argv[1:4]
@@ -47,7 +47,7 @@ def text(key):
     if not key: return ''
     f, ln = key
     for d in ("visor_b200/csrc",):
-        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), d, f)
+        p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), d, f)
         if os.path.exists(p):
             if p not in srcs: srcs[p] = open(p).read().splitlines()
             return srcs[p][ln - 1].strip()[:95] if ln - 1 < len(srcs[p]) else ''
