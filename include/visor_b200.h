@@ -211,6 +211,16 @@ VB200_API int vb200_copy_buffer(const vb200_buffer *src, uint64_t src_offset, co
  * (precompiled.cpp:3-36), byte count = max(1,w>>mip) * max(1,h>>mip) * bytes_per_pixel. */
 VB200_API int vb200_copy_buffer_to_image(const vb200_buffer *src, uint64_t buffer_offset, const vb200_image *dst,
                                          uint32_t mip_level, uint32_t array_layer);
+/* Present / read-back path (the reference's vkQueuePresentKHR blits the finished swapchain image to the
+ * window, wsi.cpp:86-219; headless, the "window" is host memory). Copies `image` as it is after all work
+ * queued so far to `dst_host` on a SECOND stream and returns at once: the library stream goes on with
+ * the next frame while the copy crosses PCIe. Work that later WRITES the image is ordered after the
+ * copy automatically, so a double-buffered application overlaps fully and a single-buffered one stays
+ * correct. `dst_host` should be page-locked (inside a vb200_mem_register'ed range) for a truly
+ * asynchronous copy. vb200_present_wait blocks until the copy of that ticket has landed;
+ * vb200_flush waits for all of them. */
+VB200_API int vb200_present(const vb200_image *image, void *dst_host, uint64_t dst_size, int *ticket);
+VB200_API int vb200_present_wait(int ticket);
 /* Device address of a mirrored host pointer (NULL if not mirrored); for interop (NCCL, torch). */
 VB200_API void *vb200_mem_device_ptr(const void *host);
 

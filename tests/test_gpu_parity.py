@@ -430,3 +430,40 @@ def test_sort_first_ownership_and_exchange_kernels(gpu, vor):
             L.vb200_set_tile_owner(0, 1)
             for pbuf in peers + [gathered]:
                 L.vb200_mem_unregister(pbuf.ctypes.data)
+
+
+def test_present_is_ordered_against_later_frames(gpu, vor):
+    """vb200_present copies on a second stream; a later frame that overwrites the SAME image (a
+    single-buffered application) must not disturb the copy, and a double-buffered one gets both frames"""
+    L = gpu.lib
+    L.vb200_present.argtypes = [C.POINTER(abi.Image), C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    L.vb200_present_wait.argtypes = [C.c_int]
+    L.vb200_mem_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.vb200_mem_unregister.argtypes = [C.c_void_p]
+    W, H = 1024, 768    # large enough for the copy to still be in flight when the next frame starts
+    sc1 = scenes.random_triangles(W, H, 400, 51)
+    sc2 = scenes.random_triangles(W, H, 400, 52)
+    want1, _ = scenes.render(vor, sc1)
+    want2, _ = scenes.render(vor, sc2)
+    shown = [np.zeros((H, W, 4), np.uint8) for _ in range(2)]
+    try:
+        for a in shown:
+            gpu.check(L.vb200_mem_register(a.ctypes.data, a.nbytes), "mem_register")
+        b1 = scenes.BoundScene(gpu, sc1)
+        b2 = scenes.BoundScene(gpu, sc2, color=b1.color, depth=b1.depth)    # same attachments
+        t1, t2 = C.c_int(), C.c_int()
+        b1.submit()
+        gpu.check(L.vb200_present(C.byref(b1.color_img), shown[0].ctypes.data, shown[0].nbytes, C.byref(t1)), "present")
+        b2.submit()                                                          # overwrites the image being copied
+        gpu.check(L.vb200_present(C.byref(b2.color_img), shown[1].ctypes.data, shown[1].nbytes, C.byref(t2)), "present")
+        gpu.check(L.vb200_present_wait(t1.value), "present_wait")
+        assert np.array_equal(shown[0], want1)
+        gpu.check(L.vb200_present_wait(t2.value), "present_wait")
+        assert np.array_equal(shown[1], want2)
+        gpu.flush()
+        assert np.array_equal(b1.color, want2)                               # coherent mode still downloads
+        assert L.vb200_present(C.byref(b1.color_img), shown[0].ctypes.data, 16, C.byref(t1)) != 0    # too small
+    finally:
+        gpu.flush()
+        for a in shown:
+            L.vb200_mem_unregister(a.ctypes.data)

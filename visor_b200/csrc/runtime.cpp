@@ -160,6 +160,16 @@ struct Context
   std::map<uint8_t *, uint32_t *> multicastTargets;
   Vb200DrawCounters *counters = nullptr;    // device
   const char *lastTileKernel = "";
+  // present path: copies on a second stream, ordered against the library stream with events
+  cudaStream_t copyStream = nullptr;
+  struct Present
+  {
+    cudaEvent_t ready = nullptr, done = nullptr;
+    const uint8_t *dev = nullptr;
+    size_t size = 0;
+    bool active = false;
+  } presents[8];
+  int activePresents = 0;
   vb200_stats stats;
   uint32_t ownerRank = 0, ownerWorld = 1;
   int64_t optRasterPath = 0, optCountFragments = 0, optTimeKernels = 0;
@@ -343,7 +353,21 @@ enum Access
 };
 
 // host (or device) pointer -> device pointer usable by kernels
+int resolveInner(const void *ptr, size_t size, int access, uint8_t **out);
+
+// host pointer (or device pointer) -> device address, with the upload / write bookkeeping of the sync
+// mode; work that will write the range is ordered after present copies still reading it
 int resolve(const void *ptr, size_t size, int access, uint8_t **out)
+{
+  int rc = resolveInner(ptr, size, access, out);
+  if(rc == VB200_OK && g.activePresents && (access & (ACC_WRITE | ACC_OVERWRITE)))
+    for(auto &pr : g.presents)
+      if(pr.active && pr.dev < *out + size && *out < pr.dev + pr.size)
+        CU(cudaStreamWaitEvent(g.stream, pr.done, 0));
+  return rc;
+}
+
+int resolveInner(const void *ptr, size_t size, int access, uint8_t **out)
 {
   *out = nullptr;
   if(!ptr)
@@ -760,6 +784,7 @@ int vb200_init(int device)
   CU(cudaSetDevice(device));
   g.device = device;
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
   CU(cudaMalloc((void **)&g.range, 2 * sizeof(uint32_t)));
   CU(cudaMalloc((void **)&g.total, sizeof(uint32_t)));
   CU(cudaHostAlloc((void **)&g.totalHost, sizeof(unsigned long long), cudaHostAllocMapped));
@@ -800,6 +825,17 @@ void vb200_shutdown(void)
   cudaFreeHost((void *)g.totalHost);
   g.triTiles.release();
   cudaFree(g.counters);
+  for(auto &pr : g.presents)
+  {
+    if(pr.ready)
+      cudaEventDestroy(pr.ready);
+    if(pr.done)
+      cudaEventDestroy(pr.done);
+    pr.ready = pr.done = nullptr;
+    pr.active = false;
+  }
+  g.activePresents = 0;
+  cudaStreamDestroy(g.copyStream);
   cudaStreamDestroy(g.stream);
   g.ready = false;
 }
@@ -983,6 +1019,8 @@ int vb200_mem_unregister(void *host)
     it = g.mirrors.find((uintptr_t)m->host);
   }
   cudaStreamSynchronize(g.stream);
+  if(g.activePresents)
+    cudaStreamSynchronize(g.copyStream);    // a present copy may still be reading this mirror
   for(auto pc = g.pendingClears.begin(); pc != g.pendingClears.end();)    // nobody will ever see them
     pc = (pc->first >= it->second.dev && pc->first < it->second.dev + it->second.size) ? g.pendingClears.erase(pc)
                                                                                          : std::next(pc);
@@ -1138,6 +1176,68 @@ int vb200_copy_buffer_to_image(const vb200_buffer *src, uint64_t buffer_offset, 
                    "copy_buffer_to_image");
 }
 
+int vb200_present(const vb200_image *image, void *dst_host, uint64_t dst_size, int *ticket)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if((rc = checkTarget(image, "present")))
+    return rc;
+  if(!dst_host || !ticket)
+    return setError(VB200_ERR_INVALID, "present: NULL destination or ticket");
+  const size_t bytes = (size_t)image->width * image->height * image->bytes_per_pixel;
+  if(dst_size < bytes)
+    return setError(VB200_ERR_INVALID, "present: destination holds %llu bytes, the image needs %zu",
+                    (unsigned long long)dst_size, bytes);
+  int slot = -1;
+  for(int i = 0; i < 8 && slot < 0; i++)
+    if(!g.presents[i].active)
+      slot = i;
+  if(slot < 0)    // every slot in flight: retire the oldest
+  {
+    slot = 0;
+    CU(cudaEventSynchronize(g.presents[0].done));
+    g.presents[0].active = false;
+    g.activePresents--;
+  }
+  auto &pr = g.presents[slot];
+  if(!pr.ready)
+  {
+    CU(cudaEventCreateWithFlags(&pr.ready, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&pr.done, cudaEventDisableTiming));
+  }
+  uint8_t *dev;
+  if((rc = resolve(image->pixels, bytes, ACC_READ, &dev)))    // also materialises a clear nobody drew over
+    return rc;
+  CU(cudaEventRecord(pr.ready, g.stream));
+  CU(cudaStreamWaitEvent(g.copyStream, pr.ready, 0));
+  CU(cudaMemcpyAsync(dst_host, dev, bytes, cudaMemcpyDeviceToHost, g.copyStream));
+  CU(cudaEventRecord(pr.done, g.copyStream));
+  pr.dev = dev;
+  pr.size = bytes;
+  pr.active = true;
+  g.activePresents++;
+  g.stats.d2h_bytes += bytes;
+  *ticket = slot + 1;
+  return VB200_OK;
+}
+
+int vb200_present_wait(int ticket)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  if(ticket < 1 || ticket > 8)
+    return setError(VB200_ERR_INVALID, "present_wait: bad ticket %d", ticket);
+  auto &pr = g.presents[ticket - 1];
+  if(!pr.active)
+    return VB200_OK;    // already retired (by a flush or by slot reuse)
+  CU(cudaEventSynchronize(pr.done));
+  pr.active = false;
+  g.activePresents--;
+  return VB200_OK;
+}
+
 void *vb200_mem_device_ptr(const void *host)
 {
   if(!g.ready || !host)
@@ -1172,6 +1272,13 @@ int vb200_flush(void)
     }
   }
   CU(cudaStreamSynchronize(g.stream));
+  if(g.activePresents)
+  {
+    CU(cudaStreamSynchronize(g.copyStream));
+    for(auto &pr : g.presents)
+      pr.active = false;
+    g.activePresents = 0;
+  }
   cudaError_t e = cudaGetLastError();
   if(e != cudaSuccess)
   {
