@@ -292,6 +292,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
       }
     }
     const uint32_t keep = __popc(later);
+    __syncwarp();    // every lane has consumed its ring entry before the tail of this pass is rewritten
     if(mine && !first)
       wq[(qhead + cnt - keep + __popc(later & below)) & 255u] = (uint16_t)e;
     __syncwarp();    // a later fragment of the same pixel (in a later pass) sees this one; ring updated
@@ -691,7 +692,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         const int b2 = c0.w * li + c1.x * yq + c1.y;
         const int b0 = c1.z - (b1 + b2);
         const int idx = c1.w + li + yq * c3.z;
-        // the slot's current key is fetched before the depth arithmetic that decides whether it is needed
+        // the slot's current key is fetched before the depth arithmetic that decides whether it is needed.
+        // (A plain read racing with other warps' CAS on purpose — compute-sanitizer racecheck reports it:
+        // keys only ever decrease, so a stale value can only cause a CAS attempt that fails and refreshes it.)
         const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
         unsigned long long seen = vb200_lds64(aSlot);
         if(!valid || (b0 | b1 | b2) < 0)
