@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
       c0 = load_index(p.ib, p.index_type, c0);
       c1 = load_index(p.ib, p.index_type, c1);
       c2 = load_index(p.ib, p.index_type, c2);
-      base = p.range[0];
+      base = p.range ? p.range[0] : p.base_vertex;
     }
     su.s0 = c0 - base;
     su.s1 = c1 - base;
@@ -600,12 +600,6 @@ int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint
   const uint32_t g = (uint32_t)std::min<size_t>((size_t)sm_count() * 4, (count + kThreads - 1) / kThreads);
   k_index_range<<<g ? g : 1, kThreads, 0, s>>>(ib, index_type, first, count, range);
   return 2;
-}
-
-int launch_set_range(uint32_t *range, uint32_t lo, uint32_t hi, cudaStream_t s)
-{
-  k_init_range<<<1, 1, 0, s>>>(range, lo, hi);
-  return 1;
 }
 
 int launch_setup(const Vb200SetupParams &p, cudaStream_t s)

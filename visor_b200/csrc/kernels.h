@@ -9,7 +9,7 @@ struct Vb200SetupParams
 {
   const void *ib;    // device address of ib.buffer->bytes + ib.offset
   uint32_t index_type, indexed, first, num_tris, topology;
-  const uint32_t *range;    // indexed: device {minIndex, maxIndex}; slot = index - minIndex
+  const uint32_t *range;    // indexed: device {minIndex, maxIndex}; slot = index - minIndex (NULL: slot = index - base_vertex)
   uint32_t base_vertex;     // non-indexed: slot = vertex - base_vertex
   uint32_t capacity;        // number of valid post-VS records
   const Vb200RasterVertex *rv;
@@ -31,6 +31,10 @@ struct Vb200VertexParams
   float4 *interps;
   uint32_t nslots;
   uint32_t width, height;
+  // the per-tile counters the setup kernel (next in the stream) accumulates into: zeroed here, which
+  // saves a memset node between the two kernels
+  uint32_t *tile_count;
+  uint32_t tile_count_n;
 };
 struct Vb200TileParams
 {
@@ -67,7 +71,6 @@ int launch_clear_u32(uint32_t *dst, uint32_t value, size_t count, cudaStream_t s
 int launch_clear_u8(uint8_t *dst, uint8_t value, size_t count, cudaStream_t s);
 int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint32_t count, uint32_t *range,
                        cudaStream_t s);
-int launch_set_range(uint32_t *range, uint32_t lo, uint32_t hi, cudaStream_t s);
 int launch_setup(const Vb200SetupParams &p, cudaStream_t s);
 int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
                 uint32_t *total, unsigned long long *host_total_dev, uint32_t seq, cudaStream_t s);

@@ -1465,6 +1465,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   // ---- index buffer / vertex range
   const uint8_t *ibDev = nullptr;
   uint32_t capacity, baseVertex = first;
+  bool shadeAll = false;    // indexed draw that shades vertices [0, capacity): no device-side index range
   if(indexed)
   {
     if(!s->ib.buffer.bytes)
@@ -1483,9 +1484,8 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     // indices (meshes: every vertex is referenced several times) all of them are shaded and the pass
     // over the index buffer that finds [min, max] is skipped (C5: 48 MB of index reads). Otherwise
     // (a small draw out of a large shared vertex buffer) the range is measured first.
-    if(vertexBound != 0xffffffffu && vertexBound <= usedVerts)
-      g.stats.kernel_launches += vb200::launch_set_range(g.range, 0u, vertexBound - 1u, g.stream);
-    else
+    shadeAll = vertexBound != 0xffffffffu && vertexBound <= usedVerts;
+    if(!shadeAll)
       g.stats.kernel_launches += vb200::launch_index_range(ibDev, s->ib.index_type, first, usedVerts, g.range, g.stream);
     if(vertexBound == 0xffffffffu)
     {
@@ -1564,7 +1564,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   if(!indexed)
     phaseMark(0);
   Vb200VertexParams vp;
-  vp.range = indexed ? g.range : nullptr;
+  vp.range = (indexed && !shadeAll) ? g.range : nullptr;
   vp.base_vertex = baseVertex;
   vp.count = capacity;
   vp.rv = g.rv.p;
@@ -1572,6 +1572,8 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   vp.nslots = nslots;
   vp.width = W;
   vp.height = H;
+  vp.tile_count = g.tileCount.p;
+  vp.tile_count_n = ntilesPad;
   {
     cudaKernel_t kVertex = nullptr;
     if((rc = getKernel(K_VERTEX, pl->vs, &kVertex)))
@@ -1591,7 +1593,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.first = first;
   sp.num_tris = numTris;
   sp.topology = pl->topology;
-  sp.range = g.range;
+  sp.range = shadeAll ? nullptr : g.range;
   sp.base_vertex = baseVertex;
   sp.capacity = capacity;
   sp.rv = g.rv.p;
@@ -1607,8 +1609,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.tiles_y = tilesY;
   sp.owner_rank = g.ownerRank;
   sp.owner_world = g.ownerWorld;
-  CU(cudaMemsetAsync(g.tileCount.p, 0, ntilesPad * sizeof(uint32_t), g.stream));
-  g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);
+  g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);    // (the vertex kernel zeroed the tile counters)
 
   // Raster back end. A pass is order-independent ("resolvable") unless it blends or runs
   // NOT_EQUAL against a depth buffer it also writes; see scaffold.cu.

@@ -118,6 +118,8 @@ extern "C" __device__ float4 vb200_sample_cube(float x, float y, float z, const 
 extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_constant__ Vb200Env env,
                                                                const Vb200VertexParams p)
 {
+  for(uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < p.tile_count_n; j += gridDim.x * blockDim.x)
+    p.tile_count[j] = 0u;
   uint32_t base = p.base_vertex, count = p.count;
   if(p.range)
   {
