@@ -151,6 +151,8 @@ __device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32
         if(!tile_owned(tile, rank, world))
           tile = 0xffffffffu;
       }
+      if(!__any_sync(0xffffffffu, tile != 0xffffffffu))
+        continue;    // most triangles touch one tile: the other three quadrants are empty for the whole warp
       const uint32_t peers = __match_any_sync(0xffffffffu, tile);
       if(tile != 0xffffffffu)
         f(tile, tri, __popc(peers & ((1u << lane) - 1u)), __popc(peers), (uint32_t)(__ffs(peers) - 1) == lane, peers);
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
                 });
 }
 
-// exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also resets the fill cursors.
+// exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also points the fill cursors at the offsets.
 // Each thread owns 4*V consecutive counters held in registers (16-byte loads/stores; the arrays are
 // allocated with padding to a multiple of 4096 entries), so the kernel is one load, one block scan,
 // one store.
@@ -326,9 +328,10 @@ __device__ __forceinline__ void scan_body(const uint32_t *tile_count, uint32_t *
       *total = wi;
       if(host_total)
       {
-        // mapped pinned host word the host polls instead of synchronising the stream
+        // mapped pinned host word the host polls instead of synchronising the stream. A posted write,
+        // deliberately not fenced: the CTA would otherwise sit out a PCIe round trip before its final
+        // stores; the host only needs the value eventually (it is checking for list overflow)
         *host_total = ((unsigned long long)seq << 32) | wi;
-        __threadfence_system();
       }
     }
   }
@@ -346,7 +349,7 @@ __device__ __forceinline__ void scan_body(const uint32_t *tile_count, uint32_t *
     o.w = o.z + c[v].z;
     run = o.w + c[v].w;
     *(uint4 *)(tile_offset + begin + 4u * v) = o;
-    *(uint4 *)(tile_cursor + begin + 4u * v) = make_uint4(0, 0, 0, 0);
+    *(uint4 *)(tile_cursor + begin + 4u * v) = o;    // the fill pass appends at cursor++ (starts at the offset)
   }
 }
 
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(kThreads) k_fill(const Vb200SetupParams p, con
                 [=](uint32_t tile, uint32_t tri, uint32_t rank, uint32_t group, bool leader, uint32_t peers) {
                   uint32_t base = 0;
                   if(leader)
-                    base = tile_offset[tile] + atomicAdd(&tile_cursor[tile], group);
+                    base = atomicAdd(&tile_cursor[tile], group);    // cursors start at the tiles' CSR offsets
                   if(peers)
                     base = __shfl_sync(peers, base, __ffs(peers) - 1);
                   const uint32_t pos = base + rank;

@@ -1739,7 +1739,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
       g.stickyCuda = 1;
       return setError(VB200_ERR_CUDA, "out of device memory for %u tile-list entries", pairs);
     }
-    CU(cudaMemsetAsync(g.tileCursor.p, 0, ntiles * sizeof(uint32_t), g.stream));
+    CU(cudaMemcpyAsync(g.tileCursor.p, g.tileOffset.p, ntiles * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
   }
   g.stats.tile_pairs += pairs;
   phaseMark(4);
