@@ -515,7 +515,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
   __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
   __shared__ int4 s_coef[256][6];     // TriCoef records of the current round, one per thread
-  __shared__ uint32_t s_start[257];   // first stream slot of each record; [count] = stream length
+  __shared__ __align__(16) uint32_t s_start[260];   // first stream slot of each record; [count] = stream length
   __shared__ uint32_t s_wsum[8];
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
@@ -648,20 +648,17 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const uint32_t firstStep = (steps * (uint32_t)warp) >> 3, lastStep = (steps * (uint32_t)(warp + 1)) >> 3;
     if(firstStep < lastStep)
     {
-      // record that owns stream slot firstStep*32: last record whose start is <= that slot
+      // record that owns stream slot firstStep*32: the last record whose start is <= that slot. Starts are
+      // increasing and entries past the round's records hold `total` (> k), so it is (number of entries
+      // <= k) - 1: every lane counts eight entries (independent loads) and one warp reduction adds them up
+      // — instead of a dependent eight-step binary search.
       uint32_t owner0;
       {
         const uint32_t k = firstStep << 5;
-        uint32_t lo = 0, hi = m;    // invariant: s_start[lo] <= k < s_start[hi] (s_start[m] = total > k)
-        while(hi - lo > 1u)
-        {
-          const uint32_t mid = (lo + hi) >> 1;
-          if(s_start[mid] <= k)
-            lo = mid;
-          else
-            hi = mid;
-        }
-        owner0 = lo;
+        const uint4 a = *(const uint4 *)(s_start + lane * 8), b4 = *(const uint4 *)(s_start + lane * 8 + 4);
+        const uint32_t mine = (a.x <= k) + (a.y <= k) + (a.z <= k) + (a.w <= k) + (b4.x <= k) + (b4.y <= k) +
+                              (b4.z <= k) + (b4.w <= k);
+        owner0 = __reduce_add_sync(0xffffffffu, mine) - 1u;
       }
       // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
       // work of step s, so it is issued first each iteration: its shared-memory round trip and the
