@@ -369,6 +369,11 @@ UNIT_OPS = ("fadd", "fsub", "fmul", "fdiv", "fneg", "vts", "dot4", "dot3", "fmin
             "transpose", "mxs", "minverse", "sin", "cos", "pow")
 
 
+# opcodes outside the reference's subset (SURVEY.md Appendix B "Not supported"), accepted only when the
+# "extended_spirv" option is on
+EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "floor", "fract")
+
+
 def vs_unit(op: str) -> np.ndarray:
     """in vec4 a@0, b@1, c@2; UBO{mat4 m; mat4 n}@(0,0); gl_Position = a; out vec4 r@0 = op(a,b,c,m,n)."""
     m = Module()
@@ -456,6 +461,23 @@ def vs_unit(op: str) -> np.ndarray:
         r = splat(m.ext(fl, GLSL.Cos, ax))
     elif op == "pow":
         r = m.ext(v4, GLSL.Pow, a, b)
+    elif op in ("select", "fge", "feq", "fne"):
+        bv4 = m.t_vec(m.t_bool(), 4)
+        cmp = {"select": Op.FOrdLessThan, "fge": Op.FOrdGreaterThanEqual, "feq": Op.FOrdEqual,
+               "fne": Op.FOrdNotEqual}[op]
+        r = m.inst(Op.Select, v4, m.inst(cmp, bv4, a, b), a, c)
+    elif op == "isub_bitcast":
+        iv4 = m.t_vec(m.t_int(1), 4)
+        r = m.inst(Op.Bitcast, v4, m.inst(Op.ISub, iv4, m.inst(Op.Bitcast, iv4, a), m.inst(Op.Bitcast, iv4, b)))
+    elif op == "ftos":
+        iv4 = m.t_vec(m.t_int(1), 4)
+        r = m.inst(Op.ConvertSToF, v4, m.inst(Op.ConvertFToS, iv4, a))
+    elif op == "fabs":
+        r = m.ext(v4, GLSL.FAbs, a)
+    elif op == "floor":
+        r = m.ext(v4, GLSL.Floor, a)
+    elif op == "fract":
+        r = m.ext(v4, GLSL.Fract, a)
     else:
         raise ValueError(op)
     m.store(m.access(SC.Output, v4, gl, m.const_i(0)), a)

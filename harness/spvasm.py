@@ -55,9 +55,12 @@ class Op:
     CompositeExtract = 81
     Transpose = 84
     ImageSampleImplicitLod = 87
+    ConvertFToS = 110
     ConvertSToF = 111
+    Bitcast = 124
     FNegate = 127
     IAdd = 128
+    ISub = 130
     FAdd = 129
     FSub = 131
     IMul = 132
@@ -72,9 +75,12 @@ class Op:
     Select = 169
     IEqual = 170
     SLessThan = 177
+    FOrdEqual = 180
+    FOrdNotEqual = 182
     FOrdLessThan = 184
     FOrdGreaterThan = 186
     FOrdLessThanEqual = 188
+    FOrdGreaterThanEqual = 190
     ShiftLeftLogical = 196
     BitwiseAnd = 199
     DPdx = 207
@@ -121,6 +127,9 @@ class BuiltIn:
 
 
 class GLSL:
+    FAbs = 4
+    Floor = 8
+    Fract = 10
     Sin = 13
     Cos = 14
     Pow = 26

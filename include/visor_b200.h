@@ -279,8 +279,12 @@ VB200_API int vb200_abi_version(void);
 /* Name of the tile kernel the most recent vb200_draw launched ("vb200_k_tile_ordered",
  * "vb200_k_tile_resolve_min_first", ...; "" before the first draw). For benchmark reports. */
 VB200_API const char *vb200_last_tile_kernel(void);
-/* Tuning/debug knobs by name ("raster_path": 0 auto, 1 ordered tiles, 2 visibility resolve;
- * "count_fragments": 0/1, "time_kernels": 0/1). Unknown names return VB200_ERR_INVALID. */
+/* Tuning/debug knobs by name ("raster_path": 0 auto, 1 ordered tiles; "count_fragments": 0/1,
+ * "time_kernels": 0/1, "fuse_clears": 0/1). "extended_spirv": 1 makes later vb200_shader_create calls
+ * accept a few opcodes the reference asserts on (OpSelect, OpFOrdGreaterThanEqual, OpFOrdEqual,
+ * OpFOrdNotEqual, OpISub, OpBitcast, OpConvertFToS, GLSL FAbs/Floor/Fract) — off by default, because
+ * with it the front end no longer rejects exactly what CompileFunction rejects (spirv_compile.cpp:1734,
+ * 1888). Unknown names return VB200_ERR_INVALID. */
 VB200_API int vb200_set_option(const char *name, int64_t value);
 
 #ifdef __cplusplus

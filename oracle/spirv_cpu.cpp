@@ -22,6 +22,14 @@
 
 namespace vor
 {
+// Extended mode: a handful of opcodes the reference asserts on (Appendix B "Not supported"), with their
+// SPIR-V semantics. Off by default: the oracle then rejects exactly what the reference rejects.
+static bool g_extended = false;
+void set_extended(bool on)
+{
+  g_extended = on;
+}
+
 namespace
 {
 // SPIR-V 1.1 enumerants used by the reference (values from the public SPIR-V specification).
@@ -41,6 +49,9 @@ enum Op : uint16_t
   OpVariable = 59, OpLoad = 61, OpStore = 62, OpAccessChain = 65, OpDecorate = 71,
   OpMemberDecorate = 72, OpVectorShuffle = 79, OpCompositeConstruct = 80, OpCompositeExtract = 81,
   OpTranspose = 84, OpImageSampleImplicitLod = 87, OpConvertSToF = 111, OpFNegate = 127,
+  // outside the reference's subset: accepted only in extended mode
+  OpConvertFToS = 110, OpBitcast = 124, OpISub = 130, OpSelect = 169, OpFOrdEqual = 180,
+  OpFOrdNotEqual = 182, OpFOrdGreaterThanEqual = 190,
   OpIAdd = 128, OpFAdd = 129, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136,
   OpVectorTimesScalar = 142, OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144,
   OpMatrixTimesVector = 145, OpMatrixTimesMatrix = 146, OpDot = 148, OpIEqual = 170,
@@ -62,7 +73,9 @@ enum : uint32_t
   G_Sin = 13, G_Cos = 14, G_Pow = 26, G_Sqrt = 31, G_InverseSqrt = 32, G_MatrixInverse = 34,
   G_FMin = 37, G_FMax = 40, G_FClamp = 43, G_FMix = 46, G_Length = 66, G_Cross = 68,
   G_Normalize = 69, G_Reflect = 71,
+  G_FAbs = 4, G_Floor = 8, G_Fract = 10,    // extended mode only
 };
+
 
 enum TKind { T_NONE, T_VOID, T_BOOL, T_INT, T_FLOAT, T_VEC, T_MAT, T_ARR, T_STRUCT, T_PTR, T_FUNC, T_IMAGE };
 
@@ -584,6 +597,13 @@ static void parse(Module &m)
               m.valtype[chk(pCode[2])] = chk(pCode[1]);
               cur->insts.push_back(pCode);
               break;
+            case OpConvertFToS: case OpBitcast: case OpISub: case OpSelect: case OpFOrdEqual:
+            case OpFOrdNotEqual: case OpFOrdGreaterThanEqual:
+              if(!g_extended)
+                FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
+              m.valtype[chk(pCode[2])] = chk(pCode[1]);
+              cur->insts.push_back(pCode);
+              break;
             case OpStore: case OpBranch: case OpBranchConditional: case OpReturn:
             case OpReturnValue:
               cur->insts.push_back(pCode);
@@ -820,6 +840,44 @@ struct Interp
         case OpConvertSToF:
           for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
             V[w[2]].f[c] = (float)V[w[3]].i[c];
+          break;
+        // ---- extended mode (plain SPIR-V semantics; not in the reference)
+        case OpFOrdGreaterThanEqual:
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].f[c] >= V[w[4]].f[c];
+          break;
+        case OpFOrdEqual:
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].f[c] == V[w[4]].f[c];
+          break;
+        case OpFOrdNotEqual:    // ordered: false when either operand is NaN
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].f[c] < V[w[4]].f[c] || V[w[3]].f[c] > V[w[4]].f[c];
+          break;
+        case OpSelect:    // component-wise; a scalar condition selects whole operands
+        {
+          const uint32_t k = comps(m, w[1]), kc = ncomp(w[3]);
+          Val r;
+          memset(&r, 0, sizeof(r));
+          for(uint32_t c = 0; c < k; c++)
+            r.u[c] = (V[w[3]].u[kc == 1 ? 0 : c] & 1) ? V[w[4]].u[c] : V[w[5]].u[c];
+          V[w[2]] = r;
+          break;
+        }
+        case OpISub:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].u[c] - V[w[4]].u[c];
+          break;
+        case OpBitcast:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].u[c];
+          break;
+        case OpConvertFToS:    // round toward zero; out-of-range and NaN give INT_MIN (cvttss2si)
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            const float f = V[w[3]].f[c];
+            V[w[2]].i[c] = (f >= -2147483648.0f && f < 2147483648.0f) ? (int32_t)f : INT32_MIN;
+          }
           break;
         // ---- flow control (:1232-1279)
         case OpBranch: pc = fn.labels.at(w[1]); break;
@@ -1067,6 +1125,18 @@ struct Interp
           r.f[c] = xmul * x + a * y;
         }
         break;
+      case G_FAbs:    // extended mode
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = fabsf(ARG(0).f[c]);
+        break;
+      case G_Floor:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = floorf(ARG(0).f[c]);
+        break;
+      case G_Fract:    // x - floor(x)
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = ARG(0).f[c] - floorf(ARG(0).f[c]);
+        break;
       case G_Cos: r.f[0] = cosf(ARG(0).f[0]); break;      // llvm.cos.f32 -> CRT (not reproducible)
       case G_Sin: r.f[0] = sinf(ARG(0).f[0]); break;      // llvm.sin.f32 -> CRT (not reproducible)
       case G_Sqrt: r.f[0] = sqrtf(ARG(0).f[0]); break;    // llvm.sqrt.f32 -> sqrtss (exact)
@@ -1124,6 +1194,10 @@ static void validateExt(const Module &m)
           case G_FMax: case G_FMin: case G_FClamp: case G_FMix: case G_Cos: case G_Sin:
           case G_Sqrt: case G_Normalize: case G_Length: case G_Cross: case G_Pow: case G_Reflect:
           case G_MatrixInverse: break;
+          case G_FAbs: case G_Floor: case G_Fract:
+            if(!g_extended)
+              FAIL("Unhandled GLSL extended instruction %u", w[4]);    // :1734
+            break;
           case G_InverseSqrt:
             if(m.types[w[1]].kind == T_VEC)
               FAIL("vector InverseSqrt crashes the reference (:1619)");

@@ -45,6 +45,8 @@ enum { kVertexFloats = 44 };
 
 // CompileFunction (spirv_compile.cpp:645). NULL + *err on anything the reference would assert on.
 Module *compile(const uint32_t *code, size_t words, std::string *err);
+// accept the extended opcode set (see spirv_cpu.cpp) in subsequent compile() calls; off by default
+void set_extended(bool on);
 // GetFuncPointer (spirv_compile.cpp:2434): entry by OpEntryPoint name.
 const Entry *find_entry(const Module *m, const char *name);
 void destroy(Module *m);

@@ -313,6 +313,17 @@ struct Counters
 
 extern "C" {
 
+// option "extended_spirv": mirror of vb200_set_option for the extended opcode set
+__attribute__((visibility("default"))) int vor_set_option(const char *name, int64_t value)
+{
+  if(name && !strcmp(name, "extended_spirv"))
+  {
+    vor::set_extended(value != 0);
+    return 0;
+  }
+  return 1;
+}
+
 __attribute__((visibility("default"))) int vor_init(int)
 {
   return 0;

@@ -145,6 +145,27 @@ def test_spirv_ops_match_oracle(gpu, vor, op):
     _check(gpu, vor, _unit_scene(op), exact=op not in ("sin", "cos", "pow"))
 
 
+@pytest.mark.parametrize("op", [o for o in __import__("harness.shaders", fromlist=["EXT_UNIT_OPS"]).EXT_UNIT_OPS])
+def test_extended_spirv_ops(gpu, vor, op):
+    """opcodes beyond the reference's subset: refused by default (as CompileFunction refuses them), and with
+    the "extended_spirv" option the PTX they lower to agrees with the CPU interpreter bit for bit"""
+    from harness import shaders
+    gset, oset = gpu.lib.vb200_set_option, vor.lib.vor_set_option
+    gset.argtypes = oset.argtypes = [C.c_char_p, C.c_int64]
+    with pytest.raises(abi.BackendError):
+        gpu.CompileFunction(shaders.vs_unit(op))
+    assert gset(b"extended_spirv", 1) == 0 and oset(b"extended_spirv", 1) == 0
+    try:
+        sc = _unit_scene(op)
+        v = sc.draws[0].vbs[0][0]
+        v[::3, 8:12] = v[::3, 4:8]          # equal operands for the (in)equality tests
+        v[1::3, 4:8] = -v[1::3, 4:8] * 7    # negatives / magnitudes > 1 for floor, fract, fabs, ftos
+        _check(gpu, vor, sc)
+    finally:
+        gset(b"extended_spirv", 0)
+        oset(b"extended_spirv", 0)
+
+
 def test_kitchen_sink_shaders(gpu, vor):
     """function calls, loops, branches, push constants, UBO at (set 1, binding 2), int/flat and matrix
     varyings, through both stages"""

@@ -175,6 +175,57 @@ def test_unit_op_matches_numpy(vor, op):
     vor.DestroyFunction(mod)
 
 
+def _expected_ext(op, a, b, c):
+    f32 = np.float32
+    if op == "select":
+        return np.where(a < b, a, c)
+    if op == "fge":
+        return np.where(a >= b, a, c)
+    if op == "feq":
+        return np.where(a == b, a, c)
+    if op == "fne":
+        return np.where(a != b, a, c)
+    if op == "isub_bitcast":
+        return (a.view(np.int32) - b.view(np.int32)).view(f32)
+    if op == "ftos":
+        return np.trunc(a).astype(np.int32).astype(f32)
+    if op == "fabs":
+        return np.abs(a)
+    if op == "floor":
+        return np.floor(a)
+    if op == "fract":
+        return a - np.floor(a)
+    raise ValueError(op)
+
+
+@pytest.mark.parametrize("op", shaders.EXT_UNIT_OPS)
+def test_extended_op_rejected_by_default_and_matches_numpy_when_enabled(vor, op):
+    """opcodes beyond Appendix B are refused exactly like the reference refuses them
+    (CompileFunction == NULL, spirv_compile.cpp:1734,1888) unless the extended option is on"""
+    setopt = vor.lib.vor_set_option
+    setopt.argtypes = [C.c_char_p, C.c_int64]
+    with pytest.raises(abi.BackendError):
+        vor.CompileFunction(shaders.vs_unit(op))
+    assert setopt(b"extended_spirv", 1) == 0
+    try:
+        verts, ubo = unit_inputs(3)
+        verts[::3, 4:8] = verts[::3, 0:4]    # equal operands for the (in)equality tests
+        mod, st, keep = unit_state(vor, op, verts, ubo)
+        entry = vor.GetFuncPointer(mod, "main")
+        run = vor.lib.vor_run_vertex
+        run.argtypes = [C.POINTER(abi.DrawState), C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+        out = (C.c_float * 44)()
+        for i in range(verts.shape[0]):
+            assert run(C.byref(st), entry, i, out) == 0
+            got = np.frombuffer(out, dtype=f32)[4:8].copy()    # bit patterns (isub produces NaN payloads)
+            a, b, c = verts[i, 0:4], verts[i, 4:8], verts[i, 8:12]
+            exp = np.asarray(_expected_ext(op, a, b, c), dtype=f32)
+            assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (op, i, got, exp)
+        vor.DestroyFunction(mod)
+    finally:
+        setopt(b"extended_spirv", 0)
+
+
 def test_fragment_interpolation_kat(vor):
     """FS input = ((b0*v0 + b1*v1) + b2*v2) + bw*0 per component (spirv_compile.cpp:629-643,2196-2214)."""
     mod = vor.CompileFunction(shaders.fs_color())

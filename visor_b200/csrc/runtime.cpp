@@ -1969,6 +1969,8 @@ int vb200_set_option(const char *name, int64_t value)
     g.optCountFragments = value;
   else if(!strcmp(name, "fuse_clears"))
     g.optFuseClears = value;
+  else if(!strcmp(name, "extended_spirv"))
+    vb200::set_extended_spirv(value != 0);
   else if(!strcmp(name, "time_kernels"))
   {
     g.optTimeKernels = value;

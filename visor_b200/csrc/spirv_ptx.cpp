@@ -46,6 +46,9 @@ enum : uint32_t
   OpFOrdLessThanEqual = 188, OpShiftLeftLogical = 196, OpBitwiseAnd = 199, OpDPdx = 207, OpDPdy = 208,
   OpLoopMerge = 246, OpSelectionMerge = 247, OpLabel = 248, OpBranch = 249, OpBranchConditional = 250,
   OpReturn = 253, OpReturnValue = 254,
+  // outside the reference's subset: accepted only in extended mode
+  OpConvertFToS = 110, OpBitcast = 124, OpISub = 130, OpSelect = 169, OpFOrdEqual = 180, OpFOrdNotEqual = 182,
+  OpFOrdGreaterThanEqual = 190,
 };
 enum : uint32_t
 {
@@ -57,7 +60,13 @@ enum : uint32_t
   Dim_Cube = 3,
   G_Sin = 13, G_Cos = 14, G_Pow = 26, G_Sqrt = 31, G_InverseSqrt = 32, G_MatrixInverse = 34, G_FMin = 37,
   G_FMax = 40, G_FClamp = 43, G_FMix = 46, G_Length = 66, G_Cross = 68, G_Normalize = 69, G_Reflect = 71,
+  G_FAbs = 4, G_Floor = 8, G_Fract = 10,    // extended mode only
 };
+
+// Extended mode (option "extended_spirv"): a handful of opcodes the reference asserts on (SURVEY.md
+// Appendix B "Not supported"), with their plain SPIR-V semantics, so shaders of real applications have a
+// chance to compile. Off by default: the front end then rejects exactly what the reference rejects.
+bool g_extendedSpirv = false;
 
 struct Error
 {
@@ -448,6 +457,12 @@ struct Module
             case OpIMul: case OpIAdd: case OpDPdx: case OpDPdy: case OpExtInst: case OpDot:
             case OpCompositeExtract: case OpCompositeConstruct: case OpVectorShuffle:
             case OpImageSampleImplicitLod: case OpVariable:
+              valtype[id(p[2])] = id(p[1]);
+              break;
+            case OpConvertFToS: case OpBitcast: case OpISub: case OpSelect: case OpFOrdEqual: case OpFOrdNotEqual:
+            case OpFOrdGreaterThanEqual:
+              if(!g_extendedSpirv)
+                fail("Unhandled SPIR-V opcode %u", op);    // :1888
               valtype[id(p[2])] = id(p[1]);
               break;
             case OpLabel: case OpStore: case OpBranch: case OpBranchConditional: case OpReturn:
@@ -981,12 +996,18 @@ struct Emitter
       case OpFOrdGreaterThan:
       case OpSLessThan:
       case OpIEqual:
+      case OpFOrdGreaterThanEqual:    // extended mode
+      case OpFOrdEqual:
+      case OpFOrdNotEqual:
       {
-        const char *ins = op == OpFOrdLessThan        ? "setp.lt.f32"
-                          : op == OpFOrdLessThanEqual ? "setp.le.f32"
-                          : op == OpFOrdGreaterThan   ? "setp.gt.f32"
-                          : op == OpSLessThan         ? "setp.lt.s32"
-                                                      : "setp.eq.s32";
+        const char *ins = op == OpFOrdLessThan           ? "setp.lt.f32"
+                          : op == OpFOrdLessThanEqual    ? "setp.le.f32"
+                          : op == OpFOrdGreaterThan      ? "setp.gt.f32"
+                          : op == OpFOrdGreaterThanEqual ? "setp.ge.f32"
+                          : op == OpFOrdEqual            ? "setp.eq.f32"
+                          : op == OpFOrdNotEqual         ? "setp.ne.f32"    // ordered: false on NaN
+                          : op == OpSLessThan            ? "setp.lt.s32"
+                                                         : "setp.eq.s32";
         std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
         if(a.size() != b.size())
           fail("comparison operand shapes differ");
@@ -1028,6 +1049,54 @@ struct Emitter
         {
           std::string d = R();
           line("cvt.rn.f32.s32 %s, %s;", d.c_str(), s.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      // ---- extended mode (plain SPIR-V semantics; not in the reference)
+      case OpSelect:    // component-wise; a scalar condition selects whole operands
+      {
+        std::vector<std::string> c = regs(w[3]), a = regs(w[4]), b = regs(w[5]);
+        if(a.size() != b.size() || (c.size() != 1 && c.size() != a.size()))
+          fail("OpSelect operand shapes differ");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          std::string d = R();
+          line("selp.b32 %s, %s, %s, %s;", d.c_str(), a[i].c_str(), b[i].c_str(), c[c.size() == 1 ? 0 : i].c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case OpISub:
+      {
+        std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
+        if(a.size() != b.size())
+          fail("integer operand shapes differ");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+          v.r.push_back(f2("sub.s32", a[i], b[i]));
+        break;
+      }
+      case OpBitcast:    // every value lives in .b32 registers: a bitcast is a rename
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &s : a)
+          v.r.push_back(s);
+        break;
+      }
+      case OpConvertFToS:    // round toward zero; NaN and out-of-range give INT_MIN, like cvttss2si on the CPU side
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &s : a)
+        {
+          std::string t = R(), ab = R(), p = P(), d = R();
+          line("cvt.rzi.s32.f32 %s, %s;", t.c_str(), s.c_str());
+          line("abs.f32 %s, %s;", ab.c_str(), s.c_str());
+          line("setp.lt.f32 %s, %s, 0f4F000000;", p.c_str(), ab.c_str());    // |x| < 2^31 (false for NaN)
+          line("selp.b32 %s, %s, 0x80000000, %s;", d.c_str(), t.c_str(), p.c_str());
           v.r.push_back(d);
         }
         break;
@@ -1360,6 +1429,23 @@ struct Emitter
         for(int x = 0; x < 4; x++)
           for(int y = 0; y < 4; y++)
             v.r[x * 4 + y] = a[y * 4 + x];
+        break;
+      }
+      case G_FAbs:    // extended mode
+      case G_Floor:
+      case G_Fract:
+      {
+        if(!g_extendedSpirv)
+          fail("Unhandled GLSL extended instruction %u", w[4]);    // :1734
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string d = R();
+          if(w[4] == G_FAbs)
+            line("abs.f32 %s, %s;", d.c_str(), A(0)[c].c_str());
+          else
+            line("cvt.rmi.f32.f32 %s, %s;", d.c_str(), A(0)[c].c_str());    // floor
+          v.r.push_back(w[4] == G_Fract ? fsub(A(0)[c], d) : d);
+        }
         break;
       }
       default: fail("Unhandled GLSL extended instruction %u", w[4]);    // :1734
@@ -1725,6 +1811,11 @@ struct Emitter
   }
 };
 }    // namespace
+
+void set_extended_spirv(bool on)
+{
+  g_extendedSpirv = on;
+}
 
 ShaderModule *compile_spirv(const uint32_t *code, size_t words, std::string *err)
 {

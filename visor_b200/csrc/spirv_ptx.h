@@ -48,6 +48,8 @@ struct ShaderModule
 // CompileFunction (spirv_compile.cpp:645). Returns NULL and fills *err on anything outside the
 // reference's subset (where the reference asserts).
 ShaderModule *compile_spirv(const uint32_t *code, size_t words, std::string *err);
+// option "extended_spirv": accept a few opcodes beyond the reference's subset in later compile_spirv calls
+void set_extended_spirv(bool on);
 
 // VS descriptors live in Vb200Env::res[0..7], FS descriptors in res[8..15], FS images in images[0..7].
 enum
