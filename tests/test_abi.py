@@ -172,3 +172,19 @@ def test_no_cpu_fallback_without_a_device(lib):
     col = (C.c_float * 4)(0, 0, 0, 1)
     assert lib.vb200_clear_color(C.byref(img), col) == -1
     assert lib.vb200_flush() == -1
+    # ... and so must everything added next to the draw path: device copies, residency, present
+    buf = abi.make_buffer(np.zeros(64, np.uint8))
+    lib.vb200_copy_buffer.argtypes = [C.POINTER(abi.Buffer), C.c_uint64, C.POINTER(abi.Buffer), C.c_uint64, C.c_uint64]
+    lib.vb200_copy_buffer_to_image.argtypes = [C.POINTER(abi.Buffer), C.c_uint64, C.POINTER(abi.Image), C.c_uint32,
+                                               C.c_uint32]
+    lib.vb200_present.argtypes = [C.POINTER(abi.Image), C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+    lib.vb200_mem_set_device_local.argtypes = [C.c_void_p, C.c_int]
+    lib.vb200_mem_register.argtypes = [C.c_void_p, C.c_uint64]
+    ticket = C.c_int()
+    host = np.zeros(64, np.uint8)
+    assert lib.vb200_copy_buffer(C.byref(buf), 0, C.byref(buf), 32, 16) == -1
+    assert lib.vb200_copy_buffer_to_image(C.byref(buf), 0, C.byref(img), 0, 0) == -1
+    assert lib.vb200_present(C.byref(img), host.ctypes.data, host.nbytes, C.byref(ticket)) == -1
+    assert lib.vb200_present_wait(1) == -1
+    assert lib.vb200_mem_register(host.ctypes.data, host.nbytes) == -1
+    assert lib.vb200_mem_set_device_local(host.ctypes.data, 1) == -1
