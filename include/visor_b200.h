@@ -280,7 +280,8 @@ VB200_API int vb200_abi_version(void);
  * "vb200_k_tile_resolve_min_first", ...; "" before the first draw). For benchmark reports. */
 VB200_API const char *vb200_last_tile_kernel(void);
 /* Tuning/debug knobs by name ("raster_path": 0 auto, 1 ordered tiles; "count_fragments": 0/1,
- * "time_kernels": 0/1, "fuse_clears": 0/1). "extended_spirv": 1 makes later vb200_shader_create calls
+ * "time_kernels": 0/1, "fuse_clears": 0/1, "slot_keys": 0/1 — 0 forces the resolve kernels' code path of
+ * draws with 2^24 or more triangles). "extended_spirv": 1 makes later vb200_shader_create calls
  * accept a few opcodes the reference asserts on (OpSelect, OpFOrdGreaterThanEqual, OpFOrdEqual,
  * OpFOrdNotEqual, OpISub, OpBitcast, OpConvertFToS, GLSL FAbs/Floor/Fract) — off by default, because
  * with it the front end no longer rejects exactly what CompileFunction rejects (spirv_compile.cpp:1734,

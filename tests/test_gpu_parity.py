@@ -166,6 +166,24 @@ def test_extended_spirv_ops(gpu, vor, op):
         oset(b"extended_spirv", 0)
 
 
+def test_resolve_without_slot_keys(gpu, vor):
+    """draws with >= 2^24 triangles cannot carry the record slot in the visibility key; the option forces
+    that code path (phase B gathers the winner from global memory) on ordinary scenes"""
+    setopt = gpu.lib.vb200_set_option
+    setopt.argtypes = [C.c_char_p, C.c_int64]
+    assert setopt(b"slot_keys", 0) == 0
+    try:
+        _check(gpu, vor, scenes.c3_mesh(480, 270, 120, 60))
+        for seed, op in enumerate([abi.CMP_LESS, abi.CMP_LEQUAL, abi.CMP_GREATER, abi.CMP_GEQUAL]):
+            sc = scenes.random_triangles(300, 200, 200, 60 + seed, depth_op=op)
+            if op in (abi.CMP_GREATER, abi.CMP_GEQUAL):
+                sc.clear_depth = 0.0
+            _check(gpu, vor, sc)
+        _check(gpu, vor, scenes.random_triangles(300, 200, 200, 70, depth_op=abi.CMP_ALWAYS, depth_write=False))
+    finally:
+        setopt(b"slot_keys", 1)
+
+
 def test_kitchen_sink_shaders(gpu, vor):
     """function calls, loops, branches, push constants, UBO at (set 1, binding 2), int/flat and matrix
     varyings, through both stages"""

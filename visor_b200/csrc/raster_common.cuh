@@ -196,8 +196,15 @@ __device__ __forceinline__ uint32_t vb200_bc_texel(const uint8_t *blk, bool bc3,
 // Linear formats: address base + (y*width + x)*bpp. BC2/BC3 (VkFormat 135/137): block (x>>2, y>>2) of
 // a (width>>2)-block-wide image, decoded per texel. The reference's 4x4 LRU block cache is a pure
 // cache; here the read-only L1/texture path (ld.global.nc) plays that role.
+// float(byte) / 255.0f: an IEEE division per channel in the reference. `lut` (256 floats holding exactly
+// those quotients, in shared memory) replaces the sixteen divisions of a bilinear sample by loads.
+__device__ __forceinline__ float vb200_unorm8(const float *lut, uint32_t b)
+{
+  return lut ? lut[b] : __fdiv_rn((float)b, 255.0f);
+}
+
 __device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t width, uint32_t bpp, uint32_t format,
-                                              int x, int y)
+                                              int x, int y, const float *lut)
 {
   uint32_t u;
   if(format == 135u || format == 137u)
@@ -211,13 +218,13 @@ __device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t widt
       u = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
           ((uint32_t)__ldg(p + 3) << 24);
   }
-  return make_float4(__fdiv_rn((float)(u & 0xffu), 255.0f), __fdiv_rn((float)((u >> 8) & 0xffu), 255.0f),
-                     __fdiv_rn((float)((u >> 16) & 0xffu), 255.0f), __fdiv_rn((float)(u >> 24), 255.0f));
+  return make_float4(vb200_unorm8(lut, u & 0xffu), vb200_unorm8(lut, (u >> 8) & 0xffu),
+                     vb200_unorm8(lut, (u >> 16) & 0xffu), vb200_unorm8(lut, u >> 24));
 }
 
 // sample_tex_wrapped (texture_sampling.cpp:139-184): repeat wrap, bilinear, mip 0, no half-texel offset
 __device__ __forceinline__ float4 vb200_sample_tex_impl(float u, float v, const Vb200Image *img,
-                                                        unsigned long long byteOffs)
+                                                        unsigned long long byteOffs, const float *lut = nullptr)
 {
   const uint32_t width = img->width, height = img->height, bpp = img->bpp, fmt = img->format;
   const uint8_t *base = img->pixels + byteOffs;
@@ -233,10 +240,10 @@ __device__ __forceinline__ float4 vb200_sample_tex_impl(float u, float v, const 
     iv1 -= (int)height;
   const float fu = __fsub_rn(u, (float)iu0), fv = __fsub_rn(v, (float)iv0);
   const float inv_fu = __fsub_rn(1.0f, fu), inv_fv = __fsub_rn(1.0f, fv);
-  const float4 TL = vb200_texel(base, width, bpp, fmt, iu0, iv0);
-  const float4 TR = vb200_texel(base, width, bpp, fmt, iu1, iv0);
-  const float4 BL = vb200_texel(base, width, bpp, fmt, iu0, iv1);
-  const float4 BR = vb200_texel(base, width, bpp, fmt, iu1, iv1);
+  const float4 TL = vb200_texel(base, width, bpp, fmt, iu0, iv0, lut);
+  const float4 TR = vb200_texel(base, width, bpp, fmt, iu1, iv0, lut);
+  const float4 BL = vb200_texel(base, width, bpp, fmt, iu0, iv1, lut);
+  const float4 BR = vb200_texel(base, width, bpp, fmt, iu1, iv1, lut);
   float4 top, bottom, out;
   top.x = __fadd_rn(__fmul_rn(TL.x, inv_fu), __fmul_rn(TR.x, fu));
   top.y = __fadd_rn(__fmul_rn(TL.y, inv_fu), __fmul_rn(TR.y, fu));
@@ -255,7 +262,8 @@ __device__ __forceinline__ float4 vb200_sample_tex_impl(float u, float v, const 
 
 // sample_cube_wrapped (texture_sampling.cpp:186-250): six tests in sequence, later matches win;
 // layer offset = CalcSubresourceByteOffset(tex, 0, face) = face * full-mip-chain size.
-__device__ __forceinline__ float4 vb200_sample_cube_impl(float x, float y, float z, const Vb200Image *img)
+__device__ __forceinline__ float4 vb200_sample_cube_impl(float x, float y, float z, const Vb200Image *img,
+                                                         const float *lut = nullptr)
 {
   const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
   const bool px = x > 0.0f, py = y > 0.0f, pz = z > 0.0f;
@@ -269,5 +277,5 @@ __device__ __forceinline__ float4 vb200_sample_cube_impl(float x, float y, float
   if(!pz && az >= ax && az >= ay) { axis = az; u = -x; v = -y; face = 5; }
   const float su = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(u, axis), 1.0f));
   const float sv = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(v, axis), 1.0f));
-  return vb200_sample_tex_impl(su, sv, img, (unsigned long long)face * img->slice_bytes);
+  return vb200_sample_tex_impl(su, sv, img, (unsigned long long)face * img->slice_bytes, lut);
 }

@@ -155,6 +155,7 @@ struct Context
   };
   std::map<uint8_t *, PendingClear> pendingClears;
   int64_t optFuseClears = 1;
+  int64_t optSlotKeys = 1;    // 0: never put the record slot into the visibility key (the path of draws >= 2^24 triangles)
   // fused sort-first exchange: colour target (device address on this rank) -> the same image on the peers
   std::map<uint8_t *, std::vector<uint32_t *>> peerTargets;
   std::map<uint8_t *, uint32_t *> multicastTargets;
@@ -1667,7 +1668,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.rs.owner_world = g.ownerWorld;
   tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
   tp.rs.color_bpp = 4;
-  tp.rs.slot_keys = numTris < (1u << 24) - 1u ? 1u : 0u;
+  tp.rs.slot_keys = (g.optSlotKeys && numTris < (1u << 24) - 1u) ? 1u : 0u;
   tp.clear_flags = clearFlags;
   tp.clear_color = clearColorWord;
   tp.clear_depth = clearDepthValue;
@@ -1969,6 +1970,8 @@ int vb200_set_option(const char *name, int64_t value)
     g.optCountFragments = value;
   else if(!strcmp(name, "fuse_clears"))
     g.optFuseClears = value;
+  else if(!strcmp(name, "slot_keys"))
+    g.optSlotKeys = value;
   else if(!strcmp(name, "extended_spirv"))
     vb200::set_extended_spirv(value != 0);
   else if(!strcmp(name, "time_kernels"))

@@ -101,13 +101,18 @@ extern "C" __device__ float4 vb200_fetch_attr(const Vb200Env *env, unsigned attr
 // ------------------------------------------------------------------------------------------------
 // texture unit (texture_sampling.cpp) — shared with the stand-alone sampler kernel in fixed.cu
 // ------------------------------------------------------------------------------------------------
+// float(byte) / 255.0f for every byte value (texture_sampling.cpp:121-133, rasterizer.cpp:595-599), filled by
+// each tile kernel before its first barrier: texel conversion and the blend's destination read become
+// shared-memory loads instead of IEEE divisions (sixteen per bilinear sample).
+__shared__ float vb200_s_unorm[256];
+
 extern "C" __device__ float4 vb200_sample_tex(float u, float v, const Vb200Image *img, unsigned long long byteOffs)
 {
-  return vb200_sample_tex_impl(u, v, img, byteOffs);
+  return vb200_sample_tex_impl(u, v, img, byteOffs, vb200_s_unorm);
 }
 extern "C" __device__ float4 vb200_sample_cube(float x, float y, float z, const Vb200Image *img)
 {
-  return vb200_sample_cube_impl(x, y, z, img);
+  return vb200_sample_cube_impl(x, y, z, img, vb200_s_unorm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,7 +193,6 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   __shared__ uint32_t s_col[8][128];
   __shared__ float s_dep[8][128];
   __shared__ uint16_t s_queue[8][256];    // per-warp fragment ring: (triangle slot << 7) | region pixel
-  __shared__ float s_unorm[256];    // float(byte) / 255.0f, the reference's destination read (rasterizer.cpp:595-599)
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
@@ -210,7 +214,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   const bool depthWrite = rs.has_depth && rs.depth_write;
   const bool blend = rs.blend_enable != 0u && rs.blend_op == 0u;    // only ADD is defined (rasterizer.cpp:657-669)
 
-  s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  vb200_s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
   uint32_t *wcol = s_col[warp];
   float *wdep = s_dep[warp];
   uint16_t *wq = s_queue[warp];
@@ -227,7 +231,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     wcol[i] = clearColor ? p.clear_color : (in ? p.color[idx] : 0u);
     wdep[i] = clearDepth ? p.clear_depth : ((in && rs.has_depth) ? p.depth[idx] : 0.0f);
   }
-  __syncthreads();    // s_unorm is shared by all warps; after this the warps run independently
+  __syncthreads();    // vb200_s_unorm is shared by all warps; after this the warps run independently
   uint32_t covered = 0, shaded = 0;
   const int lx = lane & 15, ly = lane >> 4;    // lane's pixel column / first row inside the region
   const uint32_t below = (1u << lane) - 1u;
@@ -275,7 +279,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
           if(blend)
           {
             // blend (rasterizer.cpp:593-672): existing = bytes (2,1,0) / 255.0f from the exact table
-            const float ex = s_unorm[(cur >> 16) & 0xffu], ey = s_unorm[(cur >> 8) & 0xffu], ez = s_unorm[cur & 0xffu];
+            const float ex = vb200_s_unorm[(cur >> 16) & 0xffu], ey = vb200_s_unorm[(cur >> 8) & 0xffu],
+                        ez = vb200_s_unorm[cur & 0xffu];
             const float oma = __fsub_rn(1.0f, pix.w);
             const float srcF = vb200_factor_sel(rs.src_factor, pix.w, oma);
             const float dstF = vb200_factor_sel(rs.dst_factor, pix.w, oma);
@@ -556,6 +561,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
 
+  vb200_s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);    // read in phase B, after the barriers below
   // ---- init: one visibility key per pixel, seeded with the depth already in the buffer
 #pragma unroll
   for(int j = 0; j < 4; j++)
