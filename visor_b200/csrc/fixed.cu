@@ -369,6 +369,11 @@ __global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint3
     scan_body<16>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
 }
 
+// The fill pass is bound by the round trip of its returning atomics (cursor += group), so each thread
+// appends kFillPerThread triangles and keeps that many atomics in flight: the atomics of all of them are
+// issued before the first result is used.
+constexpr int kFillPerThread = 2;
+
 __global__ void __launch_bounds__(kThreads) k_fill(const Vb200SetupParams p, const uint32_t *tile_offset,
                                                   uint32_t *tile_cursor, uint32_t *list, uint32_t capacity,
                                                   const uint32_t *total)
@@ -377,22 +382,70 @@ __global__ void __launch_bounds__(kThreads) k_fill(const Vb200SetupParams p, con
   // do nothing (the tile kernel does the same) and let the host retry with a larger list
   if(*total > capacity)
     return;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t tiles = 0xffffffffu;
-  if(t < p.num_tris)
-    tiles = __ldg(p.tri_tiles + t);
-  const bool alive = tiles != 0xffffffffu;
-  for_each_tile(tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
-                [=](uint32_t tile, uint32_t tri, uint32_t rank, uint32_t group, bool leader, uint32_t peers) {
-                  uint32_t base = 0;
-                  if(leader)
-                    base = atomicAdd(&tile_cursor[tile], group);    // cursors start at the tiles' CSR offsets
-                  if(peers)
-                    base = __shfl_sync(peers, base, __ffs(peers) - 1);
-                  const uint32_t pos = base + rank;
-                  if(pos < capacity)
-                    list[pos] = tri;
-                });
+  const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+  uint32_t tri[kFillPerThread], tiles[kFillPerThread];
+  bool alive[kFillPerThread];
+#pragma unroll
+  for(int k = 0; k < kFillPerThread; k++)
+  {
+    tri[k] = (blockIdx.x * kFillPerThread + k) * blockDim.x + threadIdx.x;
+    tiles[k] = tri[k] < p.num_tris ? __ldg(p.tri_tiles + tri[k]) : 0xffffffffu;
+    alive[k] = tiles[k] != 0xffffffffu;
+  }
+  // ranges of up to 2x2 tiles, quadrant by quadrant (same grouping as for_each_tile's matched path)
+#pragma unroll
+  for(uint32_t q = 0; q < 4u; q++)
+  {
+    const uint32_t qx = q & 1u, qy = q >> 1;
+    uint32_t tile[kFillPerThread], peers[kFillPerThread], base[kFillPerThread];
+    bool any = false;
+#pragma unroll
+    for(int k = 0; k < kFillPerThread; k++)
+    {
+      const uint32_t tx0 = tiles[k] & 0xffu, ty0 = (tiles[k] >> 8) & 0xffu;
+      const uint32_t nx = ((tiles[k] >> 16) & 0xffu) - tx0 + 1u, ny = (tiles[k] >> 24) - ty0 + 1u;
+      tile[k] = 0xffffffffu;
+      if(alive[k] && nx <= 2u && ny <= 2u && qx < nx && qy < ny)
+      {
+        tile[k] = (ty0 + qy) * p.tiles_x + tx0 + qx;
+        if(!tile_owned(tile[k], p.owner_rank, p.owner_world))
+          tile[k] = 0xffffffffu;
+      }
+      any |= tile[k] != 0xffffffffu;
+    }
+    if(!__any_sync(0xffffffffu, any))
+      continue;
+#pragma unroll
+    for(int k = 0; k < kFillPerThread; k++)
+    {
+      peers[k] = __match_any_sync(0xffffffffu, tile[k]);
+      base[k] = 0;
+      if(tile[k] != 0xffffffffu && (uint32_t)(__ffs(peers[k]) - 1) == lane)
+        base[k] = atomicAdd(&tile_cursor[tile[k]], __popc(peers[k]));    // cursors start at the CSR offsets
+    }
+#pragma unroll
+    for(int k = 0; k < kFillPerThread; k++)
+    {
+      base[k] = __shfl_sync(0xffffffffu, base[k], __ffs(peers[k]) - 1);
+      const uint32_t pos = base[k] + __popc(peers[k] & below);
+      if(tile[k] != 0xffffffffu && pos < capacity)
+        list[pos] = tri[k];
+    }
+  }
+  // larger ranges: the CTA-wide walk of for_each_tile (its matched path finds nothing to do here)
+#pragma unroll
+  for(int k = 0; k < kFillPerThread; k++)
+  {
+    const uint32_t nx = ((tiles[k] >> 16) & 0xffu) - (tiles[k] & 0xffu) + 1u;
+    const uint32_t ny = (tiles[k] >> 24) - ((tiles[k] >> 8) & 0xffu) + 1u;
+    const bool big = alive[k] && (nx > 2u || ny > 2u);
+    for_each_tile(tiles[k], big, p.tiles_x, p.owner_rank, p.owner_world, tri[k],
+                  [=](uint32_t tile, uint32_t t, uint32_t, uint32_t, bool, uint32_t) {
+                    const uint32_t pos = atomicAdd(&tile_cursor[tile], 1u);
+                    if(pos < capacity)
+                      list[pos] = t;
+                  });
+  }
 }
 
 // Per-tile sort by triangle id: restores submission order after the unordered atomic append, which
@@ -625,8 +678,8 @@ int launch_fill(const Vb200SetupParams &p, const uint32_t *tile_offset, uint32_t
 {
   if(!p.num_tris)
     return 0;
-  k_fill<<<(p.num_tris + kThreads - 1) / kThreads, kThreads, 0, s>>>(p, tile_offset, tile_cursor, list, capacity,
-                                                                      total);
+  const uint32_t per_cta = kThreads * kFillPerThread;
+  k_fill<<<(p.num_tris + per_cta - 1) / per_cta, kThreads, 0, s>>>(p, tile_offset, tile_cursor, list, capacity, total);
   return 1;
 }
 
