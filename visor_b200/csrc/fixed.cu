@@ -188,95 +188,122 @@ __device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32
   }
 }
 
+// Each thread sets up kSetupPerThread triangles, phase by phase, so that the index loads of all of them
+// and then the vertex gathers of all of them are in flight together (the kernel is a chain of two
+// dependent loads per triangle and little else).
+constexpr int kSetupPerThread = 2;
+
 __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
 {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  bool alive = t < p.num_tris;
-  Vb200TriSetup su;
-  uint32_t tiles = 0xffffffffu;
-  su.invarea = 0.0f;
+  uint32_t t[kSetupPerThread], s0[kSetupPerThread], s1[kSetupPerThread], s2[kSetupPerThread];
+  uint32_t tiles[kSetupPerThread];
+  bool alive[kSetupPerThread];
+  float invarea[kSetupPerThread];
+  int2 va[kSetupPerThread], vb[kSetupPerThread], vc[kSetupPerThread];
 
-  if(alive)
+  // ---- 1. triangle assembly (rasterizer.cpp:128-232): list = (3t, 3t+1, 3t+2); strip alternates
+  // (t, t+1, t+2) / (t+1, t, t+2) to preserve winding; GetIndex (:100-119)
+#pragma unroll
+  for(int k = 0; k < kSetupPerThread; k++)
   {
-    // triangle assembly (rasterizer.cpp:128-232): list = (3t, 3t+1, 3t+2); strip alternates
-    // (t, t+1, t+2) / (t+1, t, t+2) to preserve winding
-    uint32_t c0, c1, c2;
-    if(p.topology == 3u)
+    t[k] = (blockIdx.x * kSetupPerThread + k) * blockDim.x + threadIdx.x;
+    alive[k] = t[k] < p.num_tris;
+    tiles[k] = 0xffffffffu;
+    invarea[k] = 0.0f;
+    s0[k] = s1[k] = s2[k] = 0u;
+    if(alive[k])
     {
-      c0 = p.first + 3u * t;
-      c1 = c0 + 1u;
-      c2 = c0 + 2u;
+      uint32_t c0, c1, c2;
+      if(p.topology == 3u)
+      {
+        c0 = p.first + 3u * t[k];
+        c1 = c0 + 1u;
+        c2 = c0 + 2u;
+      }
+      else
+      {
+        const uint32_t b = p.first + t[k];
+        c0 = (t[k] & 1u) ? b + 1u : b;
+        c1 = (t[k] & 1u) ? b : b + 1u;
+        c2 = b + 2u;
+      }
+      if(p.indexed)
+      {
+        c0 = load_index(p.ib, p.index_type, c0);
+        c1 = load_index(p.ib, p.index_type, c1);
+        c2 = load_index(p.ib, p.index_type, c2);
+      }
+      s0[k] = c0;
+      s1[k] = c1;
+      s2[k] = c2;
     }
-    else
-    {
-      const uint32_t b = p.first + t;
-      c0 = (t & 1u) ? b + 1u : b;
-      c1 = (t & 1u) ? b : b + 1u;
-      c2 = b + 2u;
-    }
-    uint32_t base = p.base_vertex;
-    if(p.indexed)
-    {
-      c0 = load_index(p.ib, p.index_type, c0);
-      c1 = load_index(p.ib, p.index_type, c1);
-      c2 = load_index(p.ib, p.index_type, c2);
-      base = p.range ? p.range[0] : p.base_vertex;
-    }
-    su.s0 = c0 - base;
-    su.s1 = c1 - base;
-    su.s2 = c2 - base;
-    alive = su.s0 < p.capacity && su.s1 < p.capacity && su.s2 < p.capacity;
   }
-  if(alive)
+  const uint32_t base = (p.indexed && p.range) ? p.range[0] : p.base_vertex;
+  // ---- 2. window positions of the three corners (the raster record's first 8 bytes)
+#pragma unroll
+  for(int k = 0; k < kSetupPerThread; k++)
   {
-    const int4 a = __ldg((const int4 *)(p.rv + su.s0));
-    const int4 b = __ldg((const int4 *)(p.rv + su.s1));
-    const int4 c = __ldg((const int4 *)(p.rv + su.s2));
-    su.x0 = a.x; su.y0 = a.y; su.x1 = b.x; su.y1 = b.y; su.x2 = c.x; su.y2 = c.y;
-    su.invw0 = __int_as_float(a.z); su.invw1 = __int_as_float(b.z); su.invw2 = __int_as_float(c.z);
-    su.d0 = __int_as_float(a.w); su.d1 = __int_as_float(b.w); su.d2 = __int_as_float(c.w);
-
-    // double_triarea (rasterizer.cpp:272-275), zero-area skip (:398), facing / cull (:401-424)
-    const int area2 = (su.x1 - su.x0) * (su.y2 - su.y0) - (su.y1 - su.y0) * (su.x2 - su.x0);
-    su.invarea = __fdiv_rn(1.0f, (float)(area2 < 0 ? -area2 : area2));    // rasterizer.cpp:448
-    int flipped = (p.front_face == 1u) ? -area2 : area2;
-    if(area2 == 0)
-      alive = false;
-    else if(flipped > 0 && (p.cull_mode & 1u))
-      alive = false;
-    else if(flipped < 0 && (p.cull_mode & 2u))
-      alive = false;
+    s0[k] -= base;
+    s1[k] -= base;
+    s2[k] -= base;
+    alive[k] = alive[k] && s0[k] < p.capacity && s1[k] < p.capacity && s2[k] < p.capacity;
+    va[k] = vb[k] = vc[k] = make_int2(0, 0);
+    if(alive[k])
+    {
+      va[k] = __ldg((const int2 *)(p.rv + s0[k]));
+      vb[k] = __ldg((const int2 *)(p.rv + s1[k]));
+      vc[k] = __ldg((const int2 *)(p.rv + s2[k]));
+    }
   }
-  // statistics: one atomic per CTA on a spread counter (a per-warp atomic on ONE word costs ~20 us per
-  // million triangles: same-address atomics serialise in L2)
-  const uint32_t survivors = (uint32_t)__syncthreads_count(alive);
+  // ---- 3. double_triarea (rasterizer.cpp:272-275), zero-area skip (:398), facing / cull (:401-424),
+  // MinMax + clamp (:428-435; the pixel loops run over [min, max), :538-540)
+  uint32_t survivors = 0;
+#pragma unroll
+  for(int k = 0; k < kSetupPerThread; k++)
+  {
+    if(alive[k])
+    {
+      const int area2 = (vb[k].x - va[k].x) * (vc[k].y - va[k].y) - (vb[k].y - va[k].y) * (vc[k].x - va[k].x);
+      invarea[k] = __fdiv_rn(1.0f, (float)(area2 < 0 ? -area2 : area2));    // rasterizer.cpp:448
+      const int flipped = (p.front_face == 1u) ? -area2 : area2;
+      if(area2 == 0)
+        alive[k] = false;
+      else if(flipped > 0 && (p.cull_mode & 1u))
+        alive[k] = false;
+      else if(flipped < 0 && (p.cull_mode & 2u))
+        alive[k] = false;
+    }
+    // statistics: one atomic per CTA on a spread counter (a per-warp atomic on ONE word costs ~20 us per
+    // million triangles: same-address atomics serialise in L2)
+    survivors += (uint32_t)__syncthreads_count(alive[k]);
+    if(alive[k])
+    {
+      const int minx = max(0, min(va[k].x, min(vb[k].x, vc[k].x)));
+      const int miny = max(0, min(va[k].y, min(vb[k].y, vc[k].y)));
+      const int maxx = min((int)p.width - 1, max(va[k].x, max(vb[k].x, vc[k].x)));
+      const int maxy = min((int)p.height - 1, max(va[k].y, max(vb[k].y, vc[k].y)));
+      if(minx < maxx && miny < maxy)
+        tiles[k] = (uint32_t)(minx / VB200_TILE) | ((uint32_t)(miny / VB200_TILE) << 8) |
+                   ((uint32_t)((maxx - 1) / VB200_TILE) << 16) | ((uint32_t)((maxy - 1) / VB200_TILE) << 24);
+      else
+        alive[k] = false;
+    }
+    if(t[k] < p.num_tris)
+    {
+      *(int4 *)(p.tri + t[k]) = make_int4((int)s0[k], (int)s1[k], (int)s2[k], __float_as_int(invarea[k]));
+      p.tri_tiles[t[k]] = alive[k] ? tiles[k] : 0xffffffffu;
+    }
+  }
   if(threadIdx.x == 0 && survivors)
     atomicAdd(&p.counters->slot[blockIdx.x & (VB200_COUNTER_SLOTS - 1)].triangles_out, (unsigned long long)survivors);
-
-  if(alive)
-  {
-    // MinMax + clamp (rasterizer.cpp:428-435); the pixel loops run over [min, max) (:538-540)
-    const int minx = max(0, min(su.x0, min(su.x1, su.x2)));
-    const int miny = max(0, min(su.y0, min(su.y1, su.y2)));
-    const int maxx = min((int)p.width - 1, max(su.x0, max(su.x1, su.x2)));
-    const int maxy = min((int)p.height - 1, max(su.y0, max(su.y1, su.y2)));
-    if(minx < maxx && miny < maxy)
-      tiles = (uint32_t)(minx / VB200_TILE) | ((uint32_t)(miny / VB200_TILE) << 8) |
-                 ((uint32_t)((maxx - 1) / VB200_TILE) << 16) | ((uint32_t)((maxy - 1) / VB200_TILE) << 24);
-    else
-      alive = false;
-  }
-  if(t < p.num_tris)
-  {
-    *(int4 *)(p.tri + t) = make_int4((int)su.s0, (int)su.s1, (int)su.s2, __float_as_int(su.invarea));
-    p.tri_tiles[t] = alive ? tiles : 0xffffffffu;
-  }
   uint32_t *cnt = p.tile_count;
-  for_each_tile(tiles, alive, p.tiles_x, p.owner_rank, p.owner_world, t,
-                [cnt](uint32_t tile, uint32_t, uint32_t, uint32_t group, bool leader, uint32_t) {
-                  if(leader)
-                    atomicAdd(&cnt[tile], group);
-                });
+#pragma unroll
+  for(int k = 0; k < kSetupPerThread; k++)
+    for_each_tile(tiles[k], alive[k], p.tiles_x, p.owner_rank, p.owner_world, t[k],
+                  [cnt](uint32_t tile, uint32_t, uint32_t, uint32_t group, bool leader, uint32_t) {
+                    if(leader)
+                      atomicAdd(&cnt[tile], group);
+                  });
 }
 
 // exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also points the fill cursors at the offsets.
@@ -662,7 +689,8 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
 {
   if(!p.num_tris)
     return 0;
-  k_setup<<<(p.num_tris + kThreads - 1) / kThreads, kThreads, 0, s>>>(p);
+  const uint32_t per_cta = kThreads * kSetupPerThread;
+  k_setup<<<(p.num_tris + per_cta - 1) / per_cta, kThreads, 0, s>>>(p);
   return 1;
 }
 
