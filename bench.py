@@ -36,7 +36,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from harness import abi, scenes  # noqa: E402
+from harness import abi, scenes, tiles  # noqa: E402
 
 
 # ------------------------------------------------------------------------------------------------
@@ -404,8 +404,8 @@ def run_ours(args, workload: str) -> None:
         for a, is_in in bufs:
             if not is_in:
                 continue
-            sl = (a.nbytes // world) & ~0xff
-            if sl < (1 << 16):
+            sl, _tail = tiles.upload_shard(a.nbytes, world)
+            if sl == 0:
                 shards.append((a, 0, None, None))
                 continue
             dev = L.vb200_mem_device_ptr(a.ctypes.data)
@@ -424,8 +424,8 @@ def run_ours(args, workload: str) -> None:
                 pass
         frame_host = np.ndarray((npx,), dtype=np.int32, buffer=shm.buf)
         gpu.check(L.vb200_mem_register(frame_host.ctypes.data, frame_host.nbytes), "mem_register(shared frame)")
-        rows = (scene.height + world - 1) // world
-        band = slice(rank * rows * scene.width, min((rank + 1) * rows, scene.height) * scene.width)
+        lo, hi = tiles.row_band(scene.height, rank, world)
+        band = slice(lo * scene.width, hi * scene.width)
         band_host = torch.from_numpy(frame_host[band])
         h2d_job = sum(a.nbytes for a, _, _, _ in shards)
 

@@ -50,3 +50,20 @@ def unpack(gathered: np.ndarray, width: int, height: int, world: int) -> np.ndar
         blk = g[t % world, t // world]
         color[y0:y0 + TILE, x0:x0 + TILE] = blk[:min(TILE, height - y0), :min(TILE, width - x0)]
     return color
+
+
+# ---- sharded host<->device traffic of the N-rank end-to-end path (bench.py) --------------------------------
+def upload_shard(nbytes: int, world: int, min_shard: int = 1 << 16):
+    """How an input of `nbytes` is split over `world` PCIe links: (slice_bytes, tail_bytes). Rank r uploads
+    bytes [r*slice, (r+1)*slice) and the slices are all-gathered; every rank uploads the tail
+    [world*slice, nbytes) itself. slice = 0 means "too small to shard": every rank uploads everything."""
+    sl = (nbytes // world) & ~0xff
+    if sl < min_shard:
+        return 0, nbytes
+    return sl, nbytes - sl * world
+
+
+def row_band(height: int, rank: int, world: int):
+    """rows [lo, hi) of the assembled image that rank downloads into the shared host buffer"""
+    rows = (height + world - 1) // world
+    return min(rank * rows, height), min((rank + 1) * rows, height)
