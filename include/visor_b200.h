@@ -44,7 +44,7 @@ typedef enum vb200_status {
   VB200_ERR_NO_DEVICE = -1,    /* no CUDA device / driver; nothing was computed */
   VB200_ERR_CUDA = -2,         /* a CUDA runtime call failed (sticky)            */
   VB200_ERR_SPIRV = -3,        /* module outside the reference's SPIR-V subset   */
-  VB200_ERR_LINK = -4,         /* nvJitLink / module load failed                 */
+  VB200_ERR_LINK = -4,         /* ptxas / module load failed                     */
   VB200_ERR_INVALID = -5,      /* bad argument / unsupported state               */
   VB200_ERR_NOT_INITIALIZED = -6
 } vb200_status;
@@ -87,8 +87,8 @@ VB200_API vb200_entry *vb200_shader_entry(vb200_shader *shader, const char *name
 VB200_API void vb200_shader_destroy(vb200_shader *shader);
 /* Debug/inspection: PTX text generated for an entry point (owned by the module). */
 VB200_API const char *vb200_entry_ptx(const vb200_entry *entry);
-/* Debug/CI: run only the nvJitLink step for a VS/FS pair (kernel scaffolds + both PTX functions ->
- * sm_100a cubin). Needs no device; reports the size of the linked cubin. */
+/* Debug/CI: run only the compile step for a VS/FS pair (each kernel's PTX + the shader function it calls ->
+ * one sm_100a cubin per kernel, through ptxas). Needs no device; reports the total cubin size. */
 VB200_API int vb200_link_check(const vb200_entry *vs, const vb200_entry *fs, uint64_t *cubin_size);
 /* 0 = vertex, 4 = fragment (spv::ExecutionModel). */
 VB200_API int vb200_entry_stage(const vb200_entry *entry);

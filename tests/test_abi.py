@@ -1,5 +1,5 @@
 """The C-ABI library: loads without a GPU, exports every symbol include/visor_b200.h declares, its
-struct layouts match the ctypes mirror, shaders lower to unfused IEEE PTX that nvJitLink accepts for
+struct layouts match the ctypes mirror, shaders lower to unfused IEEE PTX that ptxas accepts for
 sm_100a, errors are reported (never thrown), and there is NO CPU fallback."""
 import ctypes as C
 import os

@@ -1,8 +1,9 @@
 // scaffold.cu — hand-written sm_100a kernel scaffolds that call the JIT-lowered shader functions.
 //
-// Compiled ONCE at build time to a relocatable cubin (nvcc -rdc=true -cubin, -fmad=false); at
-// pipeline-creation time nvJitLink links it with the PTX of one vertex and one fragment entry point
-// (spirv_ptx.cpp), resolving vb200_vs / vb200_fs.  Replaces:
+// Compiled ONCE at build time to PTX (nvcc -ptx, -fmad=false) and embedded in the library; at the first
+// draw that needs a kernel the runtime splices the PTX of the vertex or fragment entry point it calls
+// (spirv_ptx.cpp: vb200_vs / vb200_fs) into that kernel's text and compiles the module whole with ptxas
+// (runtime.cpp: compileKernel), so the shader is inlined.  Replaces:
 //   ShadeVerts + ToWindow                 rasterizer.cpp:121-253          -> vb200_k_vertex
 //   ProcessTriangles (+FS call, blend)    rasterizer.cpp:522-696          -> vb200_k_tile_ordered
 //   GetVertexAttributeData                spirv_compile.cpp:572-627       -> vb200_fetch_attr
@@ -184,8 +185,8 @@ __device__ __forceinline__ float vb200_factor_sel(uint32_t f, float alpha, float
   return f == 6u ? alpha : (f == 7u ? oneMinusAlpha : (f == 0u ? 0.0f : 1.0f));
 }
 
-// (no min-blocks hint: the linked fragment function's register count is shader dependent and nvJitLink
-// rejects a callee that needs more registers than the kernel's cap)
+// (no min-blocks hint in the source: the runtime adds .minnctapersm at JIT time when the shader at hand
+// leaves room for it, see runtime.cpp: compileKernel)
 extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __grid_constant__ Vb200Env env,
                                                                      const __grid_constant__ Vb200TileParams p)
 {

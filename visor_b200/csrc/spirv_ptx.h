@@ -2,8 +2,8 @@
 //
 // Replaces the LLVM-6 JIT front/back end of the reference (spirv_compile.cpp:645-2432): the same
 // SPIR-V subset is lowered to one `.visible .func` PTX device function per
-// entry point — `vb200_vs` for vertex, `vb200_fs` for fragment entry points — which nvJitLink links
-// into the hand-written kernel scaffolds (scaffold.cu).  Every float operation is emitted with an
+// entry point — `vb200_vs` for vertex, `vb200_fs` for fragment entry points — which the runtime splices
+// into the PTX of the hand-written kernel that calls it (scaffold.cu) and compiles as one module.  Every float operation is emitted with an
 // explicit `.rn` rounding modifier, which ptxas never contracts into FMA, and without `.ftz`, so the
 // arithmetic is IEEE-754 binary32 in the reference's operation order.
 // Host-only code: no CUDA dependency, so it is unit-testable without a GPU.
