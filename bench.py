@@ -104,8 +104,8 @@ class ClockSampler:
 # the per-launch figure of the same build and workload is recorded here; null when none was captured).
 NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_c3_kernels.txt, profiles/r01_ncu_c4_tile_ordered.txt (ncu --set full, per launch)"
 NCU_TRAFFIC = {
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 26697000 + 11731000,
-    ("c4", 1, "vb200_k_tile_ordered"): 34481000 + 238848,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 26701000 + 12613000,
+    ("c4", 1, "vb200_k_tile_ordered"): 34481000 + 559104,
 }
 
 
