@@ -29,127 +29,133 @@ static void toImage(const VkImage_T *in, vb200_image &out)
 
 namespace
 {
-// the stream is a packed sequence of {uint16 id}{payload}; payloads are not aligned (cmd_alloc.cpp:59-70)
-template <typename T>
-T take(const byte *&cur)
+// Replays one command buffer. The stream is a packed sequence of {uint16 id}{payload} with unaligned
+// payloads (cmd_alloc.cpp:59-70); every payload type gets an apply() overload, and run() dispatches on the
+// id. The tracked GPUState does not persist across command buffers (cmd_exec.cpp:20).
+class Replay
 {
-  T v;
-  memcpy(&v, cur, sizeof(T));
-  cur += sizeof(T);
-  return v;
-}
+public:
+  Replay(const byte *begin, const byte *end) : at(begin), stop(end) { memset(&gpu, 0, sizeof(gpu)); }
+
+  void run()
+  {
+    while(at < stop)
+    {
+      Command id;
+      fetch(id);
+      switch(id)
+      {
+#define VB200_CMD(NAME)      \
+  case Command::NAME:        \
+  {                          \
+    cmd::NAME payload;       \
+    fetch(payload);          \
+    apply(payload);          \
+    break;                   \
+  }
+        VB200_CMD(PipelineBarrier)
+        VB200_CMD(BeginRenderPass)
+        VB200_CMD(EndRenderPass)
+        VB200_CMD(BindPipeline)
+        VB200_CMD(BindDescriptorSets)
+        VB200_CMD(BindIB)
+        VB200_CMD(BindVB)
+        VB200_CMD(SetViewport)
+        VB200_CMD(SetScissors)
+        VB200_CMD(PushConstants)
+        VB200_CMD(Draw)
+        VB200_CMD(DrawIndexed)
+        VB200_CMD(CopyBuf2Img)
+        VB200_CMD(CopyBuf)
+#undef VB200_CMD
+      }
+    }
+  }
+
+private:
+  const byte *at, *stop;
+  GPUState gpu;
+
+  template <typename T>
+  void fetch(T &v)
+  {
+    memcpy(&v, at, sizeof(T));
+    at += sizeof(T);
+  }
+
+  // ---- commands without an effect on this path
+  void apply(const cmd::PipelineBarrier &) {}
+  void apply(const cmd::SetScissors &) {}
+  void apply(const cmd::SetViewport &c) { gpu.view = c.view; }    // recorded, never read by the rasterizer
+
+  // ---- render pass: subpass 0, colour attachment 0; clear values are consumed in the order of the
+  // attachments that clear (cmd_exec.cpp:39-61)
+  void apply(const cmd::BeginRenderPass &c)
+  {
+    const VkRenderPass_T::Subpass &sp = c.renderPass->subpasses[0];
+    const VkClearValue *clear = c.clearval;
+    gpu.col[0] = c.framebuffer->attachments[sp.colAttachments[0].idx]->image;
+    if(sp.colAttachments[0].clear)
+      ClearTarget(gpu.col[0], (clear++)->color);
+    if(sp.depthAttachment.idx < 0)
+      return;
+    gpu.depth = c.framebuffer->attachments[sp.depthAttachment.idx]->image;
+    if(sp.depthAttachment.clear)
+      ClearTarget(gpu.depth, (clear++)->depthStencil);
+  }
+  void apply(const cmd::EndRenderPass &) { gpu.col[0] = VK_NULL_HANDLE; }
+
+  // ---- bindings
+  void apply(const cmd::BindPipeline &c) { gpu.pipeline = c.pipeline; }
+  void apply(const cmd::BindDescriptorSets &c) { gpu.sets[c.idx] = c.set; }
+  void apply(const cmd::BindIB &c)
+  {
+    gpu.ib.indexType = c.indexType;
+    gpu.ib.offset = c.offset;
+    gpu.ib.buffer = c.buffer;
+  }
+  void apply(const cmd::BindVB &c)
+  {
+    gpu.vbs[c.slot].offset = c.offset;
+    gpu.vbs[c.slot].buffer = c.buffer;
+  }
+  void apply(const cmd::PushConstants &c) { memcpy(gpu.pushconsts + c.offset, c.values, c.size); }
+
+  // ---- draws: instance counts / vertexOffset are ignored by the reference (cmd_exec.cpp:129-142)
+  void apply(const cmd::Draw &c) { DrawTriangles(gpu, c.vertexCount, c.firstVertex, false); }
+  void apply(const cmd::DrawIndexed &c) { DrawTriangles(gpu, c.indexCount, c.firstIndex, true); }
+
+  // ---- copies (cmd_exec.cpp:143-182: plain memcpys there): performed between the HBM mirrors, in stream
+  // order with the draws. Only whole, tightly packed mips of one layer exist.
+  void apply(const cmd::CopyBuf2Img &c)
+  {
+    vb200_buffer from = {c.srcBuffer->bytes, c.srcBuffer->size};
+    vb200_image to;
+    toImage(c.dstImage, to);
+    const VkImageSubresourceLayers &sub = c.region.imageSubresource;
+    if(vb200_copy_buffer_to_image(&from, c.region.bufferOffset, &to, sub.mipLevel, sub.baseArrayLayer) != VB200_OK)
+      printf("vkCmdCopyBufferToImage: %s\n", vb200_last_error());
+  }
+  void apply(const cmd::CopyBuf &c)
+  {
+    vb200_buffer from = {c.srcBuffer->bytes, c.srcBuffer->size}, to = {c.dstBuffer->bytes, c.dstBuffer->size};
+    if(vb200_copy_buffer(&from, c.region.srcOffset, &to, c.region.dstOffset, c.region.size) != VB200_OK)
+      printf("vkCmdCopyBuffer: %s\n", vb200_last_error());
+  }
+};
 }    // namespace
 
 void VkCommandBuffer_T::execute() const
 {
-  const byte *cur = commandStream.data();
-  const byte *end = cur + commandStream.size();
-
-  GPUState state;    // does not persist across command buffers (cmd_exec.cpp:20)
-  memset(&state, 0, sizeof(state));
-
-  while(cur < end)
-  {
-    switch(take<Command>(cur))
-    {
-      case Command::PipelineBarrier: cur += sizeof(cmd::PipelineBarrier); break;
-      case Command::BeginRenderPass:
-      {
-        // subpass 0, colour attachment 0; clear values consumed in cleared-attachment order (:39-61)
-        const cmd::BeginRenderPass d = take<cmd::BeginRenderPass>(cur);
-        const VkRenderPass_T::Subpass &sub = d.renderPass->subpasses[0];
-        int clearIdx = 0;
-        state.col[0] = d.framebuffer->attachments[sub.colAttachments[0].idx]->image;
-        if(sub.colAttachments[0].clear)
-          ClearTarget(state.col[0], d.clearval[clearIdx++].color);
-        if(sub.depthAttachment.idx >= 0)
-        {
-          state.depth = d.framebuffer->attachments[sub.depthAttachment.idx]->image;
-          if(sub.depthAttachment.clear)
-            ClearTarget(state.depth, d.clearval[clearIdx++].depthStencil);
-        }
-        break;
-      }
-      case Command::EndRenderPass:
-        cur += sizeof(cmd::EndRenderPass);
-        state.col[0] = VK_NULL_HANDLE;
-        break;
-      case Command::BindPipeline: state.pipeline = take<cmd::BindPipeline>(cur).pipeline; break;
-      case Command::BindDescriptorSets:
-      {
-        const cmd::BindDescriptorSets d = take<cmd::BindDescriptorSets>(cur);
-        state.sets[d.idx] = d.set;
-        break;
-      }
-      case Command::BindIB:
-      {
-        const cmd::BindIB d = take<cmd::BindIB>(cur);
-        state.ib.buffer = d.buffer;
-        state.ib.offset = d.offset;
-        state.ib.indexType = d.indexType;
-        break;
-      }
-      case Command::BindVB:
-      {
-        const cmd::BindVB d = take<cmd::BindVB>(cur);
-        state.vbs[d.slot].buffer = d.buffer;
-        state.vbs[d.slot].offset = d.offset;
-        break;
-      }
-      case Command::SetViewport: state.view = take<cmd::SetViewport>(cur).view; break;    // recorded, never read
-      case Command::SetScissors: cur += sizeof(cmd::SetScissors); break;
-      case Command::PushConstants:
-      {
-        const cmd::PushConstants d = take<cmd::PushConstants>(cur);
-        memcpy(state.pushconsts + d.offset, d.values, d.size);
-        break;
-      }
-      case Command::Draw:
-      {
-        // instanceCount / firstInstance ignored (:129-135)
-        const cmd::Draw d = take<cmd::Draw>(cur);
-        DrawTriangles(state, d.vertexCount, d.firstVertex, false);
-        break;
-      }
-      case Command::DrawIndexed:
-      {
-        // vertexOffset / instanceCount ignored (:136-142)
-        const cmd::DrawIndexed d = take<cmd::DrawIndexed>(cur);
-        DrawTriangles(state, d.indexCount, d.firstIndex, true);
-        break;
-      }
-      case Command::CopyBuf2Img:
-      {
-        // whole tightly packed mip of one layer only (:147-164); performed between the HBM mirrors, in
-        // stream order with the draws
-        const cmd::CopyBuf2Img d = take<cmd::CopyBuf2Img>(cur);
-        vb200_buffer src = {d.srcBuffer->bytes, d.srcBuffer->size};
-        vb200_image dst;
-        toImage(d.dstImage, dst);
-        if(vb200_copy_buffer_to_image(&src, d.region.bufferOffset, &dst, d.region.imageSubresource.mipLevel,
-                                      d.region.imageSubresource.baseArrayLayer) != VB200_OK)
-          printf("vkCmdCopyBufferToImage: %s\n", vb200_last_error());
-        break;
-      }
-      case Command::CopyBuf:
-      {
-        const cmd::CopyBuf d = take<cmd::CopyBuf>(cur);
-        vb200_buffer src = {d.srcBuffer->bytes, d.srcBuffer->size}, dst = {d.dstBuffer->bytes, d.dstBuffer->size};
-        if(vb200_copy_buffer(&src, d.region.srcOffset, &dst, d.region.dstOffset, d.region.size) != VB200_OK)
-          printf("vkCmdCopyBuffer: %s\n", vb200_last_error());
-        break;
-      }
-    }
-  }
+  Replay(commandStream.data(), commandStream.data() + commandStream.size()).run();
 }
 
-VKAPI_ATTR VkResult VKAPI_CALL vkQueueSubmit(VkQueue queue, uint32_t submitCount, const VkSubmitInfo *pSubmits,
-                                             VkFence fence)
+// The reference's submit is synchronous and its fences / semaphores / WaitIdle are no-ops
+// (cmd_exec.cpp:187-201, icd_stubs.cpp:64-155): everything must be host-visible when this returns.
+VKAPI_ATTR VkResult VKAPI_CALL vkQueueSubmit(VkQueue, uint32_t submitCount, const VkSubmitInfo *submits, VkFence)
 {
-  for(uint32_t i = 0; i < submitCount; i++)
-    for(uint32_t c = 0; c < pSubmits[i].commandBufferCount; c++)
-      pSubmits[i].pCommandBuffers[c]->execute();
-  // fences/semaphores/WaitIdle are no-ops in the reference (icd_stubs.cpp:64-155): everything must be
-  // host-visible when this returns
+  for(const VkSubmitInfo *s = submits; s != submits + submitCount; s++)
+    for(uint32_t i = 0; i < s->commandBufferCount; i++)
+      s->pCommandBuffers[i]->execute();
   return vb200_flush() == VB200_OK ? VK_SUCCESS : VK_ERROR_DEVICE_LOST;
 }

@@ -11,43 +11,74 @@
 
 #include "../include/visor_b200.h"
 
-VKAPI_ATTR VkResult VKAPI_CALL vkAllocateMemory(VkDevice device, const VkMemoryAllocateInfo *pAllocateInfo,
-                                                const VkAllocationCallbacks *pAllocator, VkDeviceMemory *pMemory)
+namespace
 {
-  VkDeviceMemory mem = new VkDeviceMemory_T;
-  mem->size = pAllocateInfo->allocationSize;
-  mem->bytes = new byte[mem->size + 16];    // +16: texel fetches of 1-byte formats read 4 bytes
-  vb200_mem_register(mem->bytes, mem->size + 16);
+// texel fetches of 1-byte formats read 4 bytes per texel, block loads 16: keep a tail past every allocation
+const size_t kTail = 16;
+// page-aligned host storage: page-locking (cudaHostRegister inside vb200_mem_register) then covers exactly
+// this allocation's pages
+const size_t kAlign = 4096;
+
+byte *hostStorage(VkDeviceSize size, bool deviceLocal)
+{
+  const size_t bytes = ((size_t)size + kTail + kAlign - 1) / kAlign * kAlign;
+  byte *p = (byte *)aligned_alloc(kAlign, bytes);
+  if(!p)
+    return NULL;
+  memset(p, 0, bytes);
+  if(vb200_mem_register(p, size + kTail) != VB200_OK)
+    printf("visor_b200: vkAllocateMemory: %s\n", vb200_last_error());
   // memory type 0 is DEVICE_LOCAL only (query.cpp:246-267): the application cannot map it, so the HBM
   // mirror is the resource; it is filled by vkCmdCopyBuffer* on the device and never crosses PCIe again
-  if(pAllocateInfo->memoryTypeIndex == 0)
-    vb200_mem_set_device_local(mem->bytes, 1);
-  *pMemory = mem;
-  return VK_SUCCESS;
+  else if(deviceLocal)
+    vb200_mem_set_device_local(p, 1);
+  return p;
 }
 
-VKAPI_ATTR void VKAPI_CALL vkFreeMemory(VkDevice device, VkDeviceMemory memory, const VkAllocationCallbacks *pAllocator)
+void releaseStorage(byte *p)
 {
-  if(!memory)
+  if(!p)
     return;
-  vb200_mem_unregister(memory->bytes);
-  delete[] memory->bytes;
-  delete memory;
+  vb200_mem_unregister(p);
+  free(p);
 }
+}    // namespace
 
-VKAPI_ATTR VkResult VKAPI_CALL vkMapMemory(VkDevice device, VkDeviceMemory memory, VkDeviceSize offset,
-                                           VkDeviceSize size, VkMemoryMapFlags flags, void **ppData)
+VKAPI_ATTR VkResult VKAPI_CALL vkAllocateMemory(VkDevice, const VkMemoryAllocateInfo *info, const VkAllocationCallbacks *,
+                                                VkDeviceMemory *out)
 {
-  *ppData = memory->bytes + offset;
+  byte *storage = hostStorage(info->allocationSize, info->memoryTypeIndex == 0);
+  if(!storage)
+    return VK_ERROR_OUT_OF_HOST_MEMORY;
+  *out = new VkDeviceMemory_T;
+  (*out)->size = info->allocationSize;
+  (*out)->bytes = storage;
   return VK_SUCCESS;
 }
 
-VKAPI_ATTR void VKAPI_CALL vkUnmapMemory(VkDevice device, VkDeviceMemory memory)
+VKAPI_ATTR void VKAPI_CALL vkFreeMemory(VkDevice, VkDeviceMemory mem, const VkAllocationCallbacks *)
+{
+  if(mem)
+  {
+    releaseStorage(mem->bytes);
+    delete mem;
+  }
+}
+
+// memory.cpp:22-41: a mapping is the host pointer itself; flushes are no-ops because the library re-reads
+// host memory at the first use after every submit (coherent mode)
+VKAPI_ATTR VkResult VKAPI_CALL vkMapMemory(VkDevice, VkDeviceMemory mem, VkDeviceSize offset, VkDeviceSize, VkMemoryMapFlags,
+                                           void **mapped)
+{
+  *mapped = mem->bytes + offset;
+  return VK_SUCCESS;
+}
+
+VKAPI_ATTR void VKAPI_CALL vkUnmapMemory(VkDevice, VkDeviceMemory)
 {
 }
 
-VKAPI_ATTR VkResult VKAPI_CALL vkFlushMappedMemoryRanges(VkDevice device, uint32_t memoryRangeCount,
-                                                         const VkMappedMemoryRange *pMemoryRanges)
+VKAPI_ATTR VkResult VKAPI_CALL vkFlushMappedMemoryRanges(VkDevice, uint32_t, const VkMappedMemoryRange *)
 {
-  return VK_SUCCESS;    // coherent: the library re-reads host memory at the first use after every submit
+  return VK_SUCCESS;
 }
