@@ -109,6 +109,14 @@ NCU_TRAFFIC = {
 }
 
 
+# warp instructions one launch of the tile kernel executes (ncu smsp__inst_executed.sum, same captures): the
+# kernel is bound by instruction issue, not by HBM, so the bench also reports its issue-slot utilisation
+NCU_WARP_INSTRUCTIONS = {
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 124.32e6,
+    ("c4", 1, "vb200_k_tile_ordered"): 297.15e6,
+}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -595,6 +603,16 @@ def run_ours(args, workload: str) -> None:
     achieved = tile_bytes / (tiles_ms * 1e-3) / 1e9 if tiles_ms > 0 else 0.0
     frame_bytes = scene.algorithmic_bytes()
     frame_gbs = frame_bytes / (t_step * 1e-3) / 1e9
+    # secondary limiter: issue-slot utilisation of the tile kernel = warp instructions per
+    # launch (ncu) / its live duration / (4 schedulers x SMs x SM clock)
+    issue_info = None
+    winstr = NCU_WARP_INSTRUCTIONS.get((workload, world, tile_kernel))
+    if winstr and tiles_ms > 0:
+        sm_mhz = clocks.summary().get("sm_mhz") or 1965.0
+        peak_issue = 4 * 148 * sm_mhz * 1e6
+        issue_info = {"warp_instructions": winstr, "achieved_ginstr_s": winstr / (tiles_ms * 1e-3) / 1e9,
+                      "peak_ginstr_s": peak_issue / 1e9, "frac": winstr / (tiles_ms * 1e-3) / peak_issue,
+                      "source": NCU_TRAFFIC_SOURCE}
     line = {
         "metric": "triangle throughput", "value": tris / (t_step * 1e-3) / 1e6, "unit": "Mtri/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step,
@@ -618,7 +636,8 @@ def run_ours(args, workload: str) -> None:
                      "traffic_source": NCU_TRAFFIC_SOURCE if (workload, world, tile_kernel) in NCU_TRAFFIC else None,
                      "kernel": tile_kernel,
                      "algorithmic_bytes": tile_bytes, "kernel_ms": tiles_ms, "peak_source": peak_src,
-                     "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_gbs, "frac": frame_gbs / peak}},
+                     "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_gbs, "frac": frame_gbs / peak},
+                     "issue": issue_info},
         "e2e": {"value": tris / t_e2e / 1e6, "unit": "Mtri/s", "ms_per_step": t_e2e * 1e3,
                 "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps, "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
                 "steps": e2e_steps, "host_buffers": {"inputs": in_bytes, "attachments": out_bytes}},
