@@ -408,7 +408,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
       const size_t idx = (size_t)y * rs.width + x;
       vb200_store_color(p, idx, wcol[i]);
       if(depthWrite || (clearDepth && rs.has_depth))
-        p.depth[idx] = wdep[i];
+        __stcs(p.depth + idx, wdep[i]);
     }
   }
   if(rs.count_fragments)
@@ -552,7 +552,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
           if(clearColor)
             vb200_store_color(p, gi, p.clear_color);
           if(clearDepth && rs.has_depth)
-            p.depth[gi] = p.clear_depth;
+            __stcs(p.depth + gi, p.clear_depth);
         }
       }
     }
@@ -786,7 +786,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         if(clearColor)
           vb200_store_color(p, gi, p.clear_color);
         if(clearDepth && rs.has_depth)
-          p.depth[gi] = p.clear_depth;
+          __stcs(p.depth + gi, p.clear_depth);
       }
       continue;
     }
@@ -839,9 +839,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const size_t gi = (size_t)y * rs.width + x;
     vb200_store_color(p, gi, vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]));
     if(depthWrite)
-      p.depth[gi] = pixdepth;
+      __stcs(p.depth + gi, pixdepth);
     else if(clearDepth && rs.has_depth)
-      p.depth[gi] = p.clear_depth;
+      __stcs(p.depth + gi, p.clear_depth);
   }
   if(rs.count_fragments)
     vb200_count_fragments(p.counters, covered, shaded);
