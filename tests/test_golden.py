@@ -14,7 +14,7 @@ from tests.golden.make_golden import SCENES, crop
 with open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")) as f:
     GOLDEN = json.load(f)["scenes"]
 
-SMALL = [n for n in GOLDEN if "3840" not in n and "200000" not in n]
+SMALL = [n for n in GOLDEN if "3840" not in n and "200000" not in n and "7680" not in n]
 FULL = [n for n in GOLDEN if n not in SMALL]
 
 
