@@ -239,11 +239,18 @@ def test_sampler_block_compressed_and_r8(gpu, vor):
         im2 = abi.make_image(shifted[3:], 64, 32, fmt, bpp=1)
         c = gpu.sample(im2, uv)
         assert np.array_equal(c.view(np.uint32), b.view(np.uint32)), fmt
+    # 1-byte texels are fetched 4 bytes at a time (texture_sampling.cpp:121-133): the last texels read past the
+    # image. The bytes behind it are mirrored when the allocation is known to extend that far (registered).
     r8 = rng.integers(0, 256, size=(32 * 16 + 4,), dtype=np.uint8)
-    im = abi.make_image(r8, 32, 16, abi.FMT_R8_UNORM, bpp=1)
-    uv[:, 1] = uv[:, 1] % 0.9
-    a, b = gpu.sample(im, uv), vor.sample(im, uv)
-    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    L = _copy_api(gpu)
+    gpu.check(L.vb200_mem_register(r8.ctypes.data, r8.nbytes), "mem_register")
+    try:
+        im = abi.make_image(r8, 32, 16, abi.FMT_R8_UNORM, bpp=1)
+        uv[:, 1] = uv[:, 1] % 0.9
+        a, b = gpu.sample(im, uv), vor.sample(im, uv)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    finally:
+        L.vb200_mem_unregister(r8.ctypes.data)
 
 
 @pytest.mark.parametrize("fmt", [abi.FMT_BC2_UNORM_BLOCK, abi.FMT_BC3_UNORM_BLOCK])
@@ -350,11 +357,159 @@ def test_full_size_c3_properties(gpu):
     assert (d1 <= np.float32(1.0)).all() and untouched.mean() < 0.5
 
 
-def test_tile_list_guess_overflow_is_retried(gpu, vor):
-    """40 near-full-screen triangles at 2048x2048 produce far more (triangle, tile) pairs than the
-    4-per-triangle guess the speculative binning launch is sized for: the no-op + retry path."""
+def test_many_pairs_per_triangle(gpu, vor):
+    """40 near-full-screen triangles at 2048x2048: every triangle is appended to thousands of tile lists
+    (the CTA-wide walk of the binning pass)"""
     sc = scenes.random_triangles(2048, 2048, 40, 80, max_size=1.6, offscreen=0.0)
     _check(gpu, vor, sc)
+
+
+@pytest.mark.parametrize("cap", [1, 3, 40])
+def test_tile_list_overflow_falls_back_to_range_scan(gpu, vor, cap):
+    """A tile that receives more triangles than its list holds is rasterised from the packed per-triangle
+    tile ranges instead (exact and in submission order, no host round trip). `tile_list_cap` shrinks the
+    lists so that most / some tiles take that path: small and large triangles, one and several rounds of
+    256 triangles per tile, both tile back ends."""
+    gpu.lib.vb200_set_option.argtypes = [C.c_char_p, C.c_int64]
+    assert gpu.lib.vb200_set_option(b"tile_list_cap", cap) == 0
+    try:
+        _check(gpu, vor, scenes.c3_mesh(640, 360, 250, 125))              # ~10 triangles per tile... up to hundreds
+        _check(gpu, vor, scenes.c3_mesh(96, 64, 250, 125))                # thousands of triangles per tile: many rounds
+        _check(gpu, vor, scenes.c4_particles(320, 200, 6000))
+        big = scenes.random_triangles(500, 300, 12, 60, max_size=1.5)
+        big.draws += scenes.random_triangles(500, 300, 3000, 61, max_size=0.02, depth_op=abi.CMP_LEQUAL).draws
+        _check(gpu, vor, big)
+    finally:
+        gpu.lib.vb200_set_option(b"tile_list_cap", 0)
+
+
+def _render_with(be, sc, color0=None, depth0=None):
+    """render `sc` into attachments with given initial contents (loadOp LOAD when the scene has no clears)"""
+    col = np.full((sc.height, sc.width, 4), 0xCD, np.uint8) if color0 is None else color0.copy()
+    dep = depth0.copy() if depth0 is not None else None
+    return scenes.BoundScene(be, sc, color=col, depth=dep).run()
+
+
+@pytest.mark.parametrize("op", [abi.CMP_LESS, abi.CMP_LEQUAL, abi.CMP_GREATER, abi.CMP_GEQUAL, abi.CMP_EQUAL,
+                                abi.CMP_NOTEQUAL, abi.CMP_ALWAYS, abi.CMP_NEVER])
+@pytest.mark.parametrize("write", [True, False])
+def test_nan_already_in_the_depth_buffer(gpu, vor, op, write):
+    """NaN depth left in the attachment (an uncleared image, or an ALWAYS+write draw with degenerate
+    vertices): every ordered comparison against it fails and the pixel keeps its contents; NOT_EQUAL and
+    ALWAYS pass (rasterizer.cpp:562-576)."""
+    sc = scenes.random_triangles(200, 120, 120, 600 + op, depth_op=op, depth_write=write)
+    sc.clear_depth = None
+    rng = np.random.default_rng(op)
+    depth0 = rng.uniform(0.2, 0.8, size=(120, 200)).astype(np.float32)
+    depth0[rng.random((120, 200)) < 0.3] = np.float32("nan")
+    depth0[5:9, 7:30] = np.float32("-nan")
+    a_c, a_d = _render_with(gpu, sc, depth0=depth0)
+    b_c, b_d = _render_with(vor, sc, depth0=depth0)
+    assert np.array_equal(a_d.view(np.uint32), b_d.view(np.uint32))
+    assert np.array_equal(a_c, b_c)
+
+
+def test_geometry_in_the_last_tile_of_an_8192_target(gpu, vor):
+    """tile (255, 255) of an 8192 x 8192 target: its packed tile range is all ones in every byte, which
+    must not be mistaken for the dead-triangle marker"""
+    W = H = 8192
+    px = np.array([[8165, 8165], [8190, 8170], [8170, 8191],      # inside the last tile
+                   [8100, 8100], [8191, 8120], [8120, 8191],      # straddles the last 3x3 tiles
+                   [10, 10], [40, 12], [12, 40]], dtype=np.float64)
+    v = np.zeros((9, 8), np.float32)
+    v[:, 0] = (px[:, 0] + 0.5) / W * 2 - 1
+    v[:, 1] = -((px[:, 1] + 0.5) / H * 2 - 1)
+    v[:, 2], v[:, 3] = 0.5, 1.0
+    v[:, 4:8] = np.random.default_rng(1).uniform(0, 1, size=(9, 4))
+    from harness import shaders
+    pipe = scenes.PipelineDesc(shaders.vs_passthrough(), shaders.fs_color(),
+                               [(0, abi.FMT_R32G32B32A32_SFLOAT, 32, 0, 0), (1, abi.FMT_R32G32B32A32_SFLOAT, 32, 16, 0)])
+    sc = scenes.Scene("last_tile", W, H, [scenes.Draw(pipe, 9, vbs=[(v, 0)])], depth=False)
+    a, _ = scenes.render(gpu, sc)
+    b, _ = scenes.render(vor, sc)
+    assert (a[8160:, 8160:] != np.array([51, 51, 51, 255], np.uint8)).any()
+    assert np.array_equal(a, b)
+
+
+def test_clear_target_truncation_and_one_byte_targets(gpu, vor):
+    """ClearTarget: byte(f * 255.0f) wraps for out-of-range and negative colours exactly as the x86
+    truncating convert does (rasterizer.cpp:341-345); a 1-byte-per-pixel target is memset with the red
+    channel (:347-350); other pixel sizes are left alone"""
+    for col in [(0.2, 0.2, 0.2, 1.0), (0.999, 0.5, 0.0039, 0.25), (1.5, -0.1, 0.7, 2.0), (-3.7, 300.0, 1e12, -1e12),
+                (float("nan"), float("inf"), -0.0, 1.0039)]:
+        for (w, h) in [(8, 8), (333, 77)]:
+            a = np.full((h, w, 4), 9, np.uint8)
+            b = np.full((h, w, 4), 9, np.uint8)
+            gpu.ClearTarget(abi.make_image(a, w, h, abi.FMT_B8G8R8A8_UNORM), col)
+            gpu.flush()
+            vor.ClearTarget(abi.make_image(b, w, h, abi.FMT_B8G8R8A8_UNORM), col)
+            assert np.array_equal(a, b), col
+            a1 = np.full((h, w), 9, np.uint8)
+            b1 = np.full((h, w), 9, np.uint8)
+            gpu.ClearTarget(abi.make_image(a1, w, h, abi.FMT_R8_UNORM, bpp=1), col)
+            gpu.flush()
+            vor.ClearTarget(abi.make_image(b1, w, h, abi.FMT_R8_UNORM, bpp=1), col)
+            assert np.array_equal(a1, b1), col
+    a2 = np.full((8, 8, 2), 9, np.uint8)
+    gpu.ClearTarget(abi.make_image(a2, 8, 8, 0, bpp=2), (1.0, 1.0, 1.0, 1.0))
+    gpu.flush()
+    assert (a2 == 9).all()
+
+
+def test_results_of_the_same_submit_are_not_overwritten_by_uploads(gpu, vor):
+    """coherent (host pointer) memory, no flush between the operations: (a) vkCmdCopyBufferToImage into a
+    host-visible image that the next draw samples, (b) an image rendered by one draw and sampled by the
+    next, (c) a vertex buffer partly filled by vkCmdCopyBuffer and then read whole by a draw. Each reader
+    must see the device-side result, and the flush must bring back exactly what the reference's host
+    memory would hold."""
+    L = _copy_api(gpu)
+    # (a)
+    sc = scenes.c2_cube(320, 180)
+    want_c, want_d = scenes.render(vor, sc)
+    d = sc.draws[0]
+    s, b, tex, tw, th, fmt, bpp, layers = d.textures[0]
+    staging = np.ascontiguousarray(tex).reshape(-1).copy()
+    image = np.zeros(staging.size, np.uint8)             # host-visible, not registered, stale on the host
+    im = abi.make_image(image, tw, th, fmt, bpp=bpp, layers=layers)
+    sb = abi.make_buffer(staging)
+    d.textures = [(s, b, image.reshape(tex.shape), tw, th, fmt, bpp, layers)]
+    bound = scenes.BoundScene(gpu, sc)
+    gpu.check(L.vb200_copy_buffer_to_image(C.byref(sb), 0, C.byref(im), 0, 0), "copy_buffer_to_image")
+    got_c, got_d = bound.run()
+    assert np.array_equal(got_c, want_c) and np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))
+    assert np.array_equal(image, staging)
+    # (b)
+    def two_pass(be):
+        first = scenes.random_triangles(64, 64, 60, 77, has_depth=False, depth_op=abi.CMP_ALWAYS)
+        second = scenes.c2_cube(320, 180)
+        target = np.full((64, 64, 4), 0xCD, np.uint8)
+        dd = second.draws[0]
+        s_, b_, _, _, _, fmt_, bpp_, layers_ = dd.textures[0]
+        dd.textures = [(s_, b_, target, 64, 64, fmt_, bpp_, layers_)]
+        b1 = scenes.BoundScene(be, first, color=target)
+        b2 = scenes.BoundScene(be, second)
+        b1.submit()
+        b2.submit()
+        be.flush()
+        return target, b2.color, b2.depth
+    for x, y in zip(two_pass(gpu), two_pass(vor)):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    # (c)
+    full = scenes.random_triangles(200, 120, 80, 78)
+    want_c, want_d = scenes.render(vor, full)
+    vfull = full.draws[0].vbs[0][0]
+    good = vfull.copy()
+    half = (good.nbytes // 2) & ~31
+    stale = good.copy()
+    stale.view(np.uint8).reshape(-1)[:half] = 0xEE        # first half only arrives through the copy
+    full.draws[0].vbs = [(stale, 0)]
+    stagebuf = good.view(np.uint8).reshape(-1)[:half].copy()
+    bound = scenes.BoundScene(gpu, full)
+    gpu.check(L.vb200_copy_buffer(C.byref(abi.make_buffer(stagebuf)), 0, C.byref(abi.make_buffer(stale)), 0, half),
+              "copy_buffer")
+    got_c, got_d = bound.run()
+    assert np.array_equal(got_c, want_c) and np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))
+    assert np.array_equal(stale, good)
 
 
 def test_clear_fusion_variants(gpu, vor):

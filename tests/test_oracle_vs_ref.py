@@ -112,12 +112,19 @@ def test_block_compressed_textured_scene(vor, vref, fmt):
 
 
 def test_clear_truncation(vor, vref):
-    for col in [(0.2, 0.2, 0.2, 1.0), (0.999, 0.5, 0.0039, 0.25), (1.5, -0.1, 0.7, 2.0)]:
+    for col in [(0.2, 0.2, 0.2, 1.0), (0.999, 0.5, 0.0039, 0.25), (1.5, -0.1, 0.7, 2.0), (-3.7, 300.0, 1e12, -1e12),
+                (float("nan"), float("inf"), -0.0, 1.0039)]:
         a = np.zeros((8, 8, 4), np.uint8)
         b = np.zeros((8, 8, 4), np.uint8)
         vref.ClearTarget(abi.make_image(a, 8, 8, abi.FMT_B8G8R8A8_UNORM), col)
         vor.ClearTarget(abi.make_image(b, 8, 8, abi.FMT_B8G8R8A8_UNORM), col)
         assert np.array_equal(a, b)
+        # 1 byte per pixel: memset with the red channel (rasterizer.cpp:347-350)
+        a1 = np.full((8, 8), 9, np.uint8)
+        b1 = np.full((8, 8), 9, np.uint8)
+        vref.ClearTarget(abi.make_image(a1, 8, 8, abi.FMT_R8_UNORM, bpp=1), col)
+        vor.ClearTarget(abi.make_image(b1, 8, 8, abi.FMT_R8_UNORM, bpp=1), col)
+        assert np.array_equal(a1, b1)
 
 
 def test_threaded_reference_is_not_the_oracle():

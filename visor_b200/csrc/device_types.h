@@ -6,6 +6,10 @@
 #include <stdint.h>
 
 #define VB200_TILE 32            // screen tile edge in pixels (the reference's blockSize, rasterizer.cpp:454)
+// Packed tile range of a triangle: tx0 | ty0 << 8 | tx1 << 16 | ty1 << 24 (inclusive). A live range has
+// tx0 <= tx1, so a value with tx0 > tx1 can never be one: it marks culled / off-screen triangles. (All
+// ones would collide with a triangle that lies entirely in tile (255, 255) of an 8192 x 8192 target.)
+#define VB200_TILES_DEAD 0x000000ffu
 #define VB200_MAX_SLOTS 10       // interpolant float4 slots per vertex (VertexCacheEntry::interps, gpu.h:56)
 #define VB200_MAX_RES 16         // descriptor slots a pipeline may reference
 #define VB200_MAX_IMAGES 8
@@ -89,7 +93,7 @@ struct Vb200DrawCounters
 {
   struct alignas(128) Slot
   {
-    unsigned long long triangles_out, fragments_covered, fragments_shaded, pad;
+    unsigned long long triangles_out, fragments_covered, fragments_shaded, tile_pairs;
   } slot[VB200_COUNTER_SLOTS];
 };
 

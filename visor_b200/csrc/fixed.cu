@@ -5,8 +5,9 @@
 //                                 DrawTriangles setup / cull / bbox
 //   K3  binning                   the per-triangle 32x32 block      rasterizer.cpp:454-515
 //                                 split + FIFO queue, restated as
-//                                 per-screen-tile ordered lists:
-//                                 count -> exclusive scan -> fill -> per-tile sort by triangle id
+//                                 per-screen-tile lists appended by
+//                                 the setup kernel itself (+ per-tile
+//                                 sort by triangle id for the in-order path)
 //   K5' stand-alone sampler       sample_tex_wrapped/_cube_wrapped texture_sampling.cpp:139-250
 //   K6  tile pack / unpack        (sort-first multi-GPU; no reference equivalent)
 #include <algorithm>
@@ -116,81 +117,22 @@ __global__ void k_init_range(uint32_t *range, uint32_t lo, uint32_t hi)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 + K3 count/fill share the triangle -> tile-range traversal.
+// K2 + K3: triangle assembly, setup, cull, bbox AND binning, one pass over the triangles.
+//
+// Binning appends a surviving triangle's id straight to the list of every 32x32 tile its bbox touches
+// (the reference's per-triangle block split + FIFO push, rasterizer.cpp:454-485). Every tile owns a
+// fixed window of list_cap entries; the per-tile counter doubles as the append cursor and counts every
+// append, so a tile that received more than list_cap triangles is recognisable afterwards and its tile
+// kernel CTA falls back to scanning the packed tile ranges (tri_tiles) — exact, no host involvement.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool tile_owned(uint32_t tile, uint32_t rank, uint32_t world)
 {
   return world <= 1u || (tile % world) == rank;
 }
 
-// Visit every owned tile of the inclusive range packed in `tiles`, handing `f` a group of lanes that
-// target the SAME tile: f(tile, tri, rank_in_group, group_size, is_leader). Neighbouring triangles of a
-// mesh land in the same tile, so per-lane atomics on the tile counters would serialise in the L2
-// atomic unit; __match_any_sync lets one lane per (warp, tile) do the atomic for the whole group.
-// Ranges of up to 2x2 tiles (every triangle smaller than a tile) take the matched path; larger ones
-// (full-screen triangles cover thousands of tiles) are spread over the whole CTA, one tile per thread.
-// Must be called by every thread of the CTA (it synchronises).
-template <typename F>
-__device__ __forceinline__ void for_each_tile(uint32_t tiles, bool alive, uint32_t tiles_x, uint32_t rank,
-                                              uint32_t world, uint32_t tri, F f)
-{
-  const uint32_t tx0 = tiles & 0xffu, ty0 = (tiles >> 8) & 0xffu, tx1 = (tiles >> 16) & 0xffu, ty1 = tiles >> 24;
-  const uint32_t nx = alive ? (tx1 - tx0 + 1u) : 0u, ny = alive ? (ty1 - ty0 + 1u) : 0u;
-  const bool big = nx > 2u || ny > 2u;
-  const uint32_t lane = threadIdx.x & 31u;
-  if(__any_sync(0xffffffffu, alive && !big))
-  {
-#pragma unroll
-    for(uint32_t q = 0; q < 4u; q++)
-    {
-      const uint32_t qx = q & 1u, qy = q >> 1;
-      uint32_t tile = 0xffffffffu;
-      if(alive && !big && qx < nx && qy < ny)
-      {
-        tile = (ty0 + qy) * tiles_x + tx0 + qx;
-        if(!tile_owned(tile, rank, world))
-          tile = 0xffffffffu;
-      }
-      if(!__any_sync(0xffffffffu, tile != 0xffffffffu))
-        continue;    // most triangles touch one tile: the other three quadrants are empty for the whole warp
-      const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-      if(tile != 0xffffffffu)
-        f(tile, tri, __popc(peers & ((1u << lane) - 1u)), __popc(peers), (uint32_t)(__ffs(peers) - 1) == lane, peers);
-    }
-  }
-  // Large ranges: queued in shared memory, then every thread of the CTA takes tiles of each queued
-  // triangle (one warp walking the ~1000 tiles of a cube face alone made the fill pass of a 12-triangle
-  // draw take 36 us: one returning atomic per tile, 32 at a time).
-  __shared__ uint32_t s_big[kThreads][2];
-  __shared__ uint32_t s_nbig;
-  if(threadIdx.x == 0)
-    s_nbig = 0;
-  __syncthreads();
-  if(alive && big)
-  {
-    const uint32_t slot = atomicAdd(&s_nbig, 1u);
-    s_big[slot][0] = tiles;
-    s_big[slot][1] = tri;
-  }
-  __syncthreads();
-  const uint32_t nbig = s_nbig;
-  for(uint32_t b = 0; b < nbig; b++)
-  {
-    const uint32_t bt = s_big[b][0], b_tri = s_big[b][1];
-    const uint32_t b_tx0 = bt & 0xffu, b_ty0 = (bt >> 8) & 0xffu;
-    const uint32_t b_nx = ((bt >> 16) & 0xffu) - b_tx0 + 1u, b_nt = b_nx * ((bt >> 24) - b_ty0 + 1u);
-    for(uint32_t k = threadIdx.x; k < b_nt; k += kThreads)
-    {
-      const uint32_t tile = (b_ty0 + k / b_nx) * tiles_x + b_tx0 + k % b_nx;
-      if(tile_owned(tile, rank, world))
-        f(tile, b_tri, 0u, 1u, true, 0u);    // distinct tiles per thread: every thread is its own group
-    }
-  }
-}
-
-// Each thread sets up kSetupPerThread triangles, phase by phase, so that the index loads of all of them
-// and then the vertex gathers of all of them are in flight together (the kernel is a chain of two
-// dependent loads per triangle and little else).
+// Each thread sets up kSetupPerThread triangles, phase by phase, so that the index loads of all of them,
+// then the vertex gathers of all of them, then the returning cursor atomics of all of them are in flight
+// together (the kernel is a chain of three dependent memory operations per triangle and little else).
 constexpr int kSetupPerThread = 2;
 
 __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
@@ -200,6 +142,12 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
   bool alive[kSetupPerThread];
   float invarea[kSetupPerThread];
   int2 va[kSetupPerThread], vb[kSetupPerThread], vc[kSetupPerThread];
+  // ranges above 2x2 tiles are queued here and walked by the whole CTA (a full-screen triangle covers
+  // thousands of tiles: one thread appending to all of them would take tens of microseconds)
+  __shared__ uint32_t s_big[kThreads * kSetupPerThread][2];
+  __shared__ uint32_t s_nbig, s_pairs;
+  if(threadIdx.x == 0)
+    s_nbig = s_pairs = 0;    // visible after the first __syncthreads_count below
 
   // ---- 1. triangle assembly (rasterizer.cpp:128-232): list = (3t, 3t+1, 3t+2); strip alternates
   // (t, t+1, t+2) / (t+1, t, t+2) to preserve winding; GetIndex (:100-119)
@@ -208,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
   {
     t[k] = (blockIdx.x * kSetupPerThread + k) * blockDim.x + threadIdx.x;
     alive[k] = t[k] < p.num_tris;
-    tiles[k] = 0xffffffffu;
+    tiles[k] = VB200_TILES_DEAD;
     invarea[k] = 0.0f;
     s0[k] = s1[k] = s2[k] = 0u;
     if(alive[k])
@@ -236,6 +184,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
       s0[k] = c0;
       s1[k] = c1;
       s2[k] = c2;
+      alive[k] = c0 < p.vertex_bound && c1 < p.vertex_bound && c2 < p.vertex_bound;
     }
   }
   const uint32_t base = (p.indexed && p.range) ? p.range[0] : p.base_vertex;
@@ -288,190 +237,114 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
       else
         alive[k] = false;
     }
-    if(t[k] < p.num_tris)
-    {
-      *(int4 *)(p.tri + t[k]) = make_int4((int)s0[k], (int)s1[k], (int)s2[k], __float_as_int(invarea[k]));
-      p.tri_tiles[t[k]] = alive[k] ? tiles[k] : 0xffffffffu;
-    }
   }
-  if(threadIdx.x == 0 && survivors)
-    atomicAdd(&p.counters->slot[blockIdx.x & (VB200_COUNTER_SLOTS - 1)].triangles_out, (unsigned long long)survivors);
-  uint32_t *cnt = p.tile_count;
+
+  // ---- 4. binning. Neighbouring triangles of a mesh land in the same tile, so per-lane atomics on the
+  // tile cursors would serialise in the L2 atomic unit: __match_any_sync groups the lanes of a warp that
+  // target the same tile and one lane per group reserves room for all of them. Ranges of up to 2x2 tiles
+  // (every triangle smaller than a tile) are handled quadrant by quadrant; the cursor atomics of both of a
+  // thread's triangles are issued before either result is used.
+  const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+  uint32_t nx[kSetupPerThread], ny[kSetupPerThread];
+  bool used[kSetupPerThread];    // some tile of this rank needs the triangle
+  uint32_t mypairs = 0;
 #pragma unroll
   for(int k = 0; k < kSetupPerThread; k++)
-    for_each_tile(tiles[k], alive[k], p.tiles_x, p.owner_rank, p.owner_world, t[k],
-                  [cnt](uint32_t tile, uint32_t, uint32_t, uint32_t group, bool leader, uint32_t) {
-                    if(leader)
-                      atomicAdd(&cnt[tile], group);
-                  });
-}
-
-// exclusive scan of the per-tile counts (<= 65536 tiles) by one CTA; also points the fill cursors at the offsets.
-// Each thread owns 4*V consecutive counters held in registers (16-byte loads/stores; the arrays are
-// allocated with padding to a multiple of 4096 entries), so the kernel is one load, one block scan,
-// one store.
-template <int V>
-__device__ __forceinline__ void scan_body(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor,
-                                          uint32_t ntiles, uint32_t *total, volatile unsigned long long *host_total,
-                                          uint32_t seq)
-{
-  __shared__ uint32_t warp_sums[32];
-  const uint32_t begin = threadIdx.x * 4u * V;
-  uint4 c[V];
-  uint32_t sum = 0;
-#pragma unroll
-  for(int v = 0; v < V; v++)
   {
-    c[v] = (begin + 4u * v < ntiles) ? *(const uint4 *)(tile_count + begin + 4u * v) : make_uint4(0, 0, 0, 0);
-    // entries past ntiles inside the last vector are padding and hold 0
-    sum += c[v].x + c[v].y + c[v].z + c[v].w;
+    nx[k] = alive[k] ? ((tiles[k] >> 16) & 0xffu) - (tiles[k] & 0xffu) + 1u : 0u;
+    ny[k] = alive[k] ? (tiles[k] >> 24) - ((tiles[k] >> 8) & 0xffu) + 1u : 0u;
+    used[k] = false;
   }
-  uint32_t incl = sum;
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-#pragma unroll
-  for(int o = 1; o < 32; o <<= 1)
-  {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if(lane >= (uint32_t)o)
-      incl += v;
-  }
-  if(lane == 31u)
-    warp_sums[warp] = incl;
-  __syncthreads();
-  if(warp == 0)
-  {
-    const uint32_t w = warp_sums[lane];
-    uint32_t wi = w;
-#pragma unroll
-    for(int o = 1; o < 32; o <<= 1)
-    {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-      if(lane >= (uint32_t)o)
-        wi += v;
-    }
-    warp_sums[lane] = wi - w;    // exclusive
-    if(lane == 31u)
-    {
-      *total = wi;
-      if(host_total)
-      {
-        // mapped pinned host word the host polls instead of synchronising the stream. A posted write,
-        // deliberately not fenced: the CTA would otherwise sit out a PCIe round trip before its final
-        // stores; the host only needs the value eventually (it is checking for list overflow)
-        *host_total = ((unsigned long long)seq << 32) | wi;
-      }
-    }
-  }
-  __syncthreads();
-  uint32_t run = warp_sums[warp] + incl - sum;
-#pragma unroll
-  for(int v = 0; v < V; v++)
-  {
-    if(begin + 4u * v >= ntiles)
-      break;
-    uint4 o;
-    o.x = run;
-    o.y = o.x + c[v].x;
-    o.z = o.y + c[v].y;
-    o.w = o.z + c[v].z;
-    run = o.w + c[v].w;
-    *(uint4 *)(tile_offset + begin + 4u * v) = o;
-    *(uint4 *)(tile_cursor + begin + 4u * v) = o;    // the fill pass appends at cursor++ (starts at the offset)
-  }
-}
-
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t *tile_count, uint32_t *tile_offset,
-                                              uint32_t *tile_cursor, uint32_t ntiles, uint32_t *total,
-                                              volatile unsigned long long *host_total, uint32_t seq)
-{
-  if(ntiles <= 4096u)
-    scan_body<1>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
-  else if(ntiles <= 8192u)
-    scan_body<2>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
-  else if(ntiles <= 16384u)
-    scan_body<4>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
-  else if(ntiles <= 32768u)
-    scan_body<8>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
-  else
-    scan_body<16>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total, seq);
-}
-
-// The fill pass is bound by the round trip of its returning atomics (cursor += group), so each thread
-// appends kFillPerThread triangles and keeps that many atomics in flight: the atomics of all of them are
-// issued before the first result is used.
-constexpr int kFillPerThread = 2;
-
-__global__ void __launch_bounds__(kThreads) k_fill(const Vb200SetupParams p, const uint32_t *tile_offset,
-                                                  uint32_t *tile_cursor, uint32_t *list, uint32_t capacity,
-                                                  const uint32_t *total)
-{
-  // speculative launch: the host sized `list` before the pair total was known; if it does not fit,
-  // do nothing (the tile kernel does the same) and let the host retry with a larger list
-  if(*total > capacity)
-    return;
-  const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-  uint32_t tri[kFillPerThread], tiles[kFillPerThread];
-  bool alive[kFillPerThread];
-#pragma unroll
-  for(int k = 0; k < kFillPerThread; k++)
-  {
-    tri[k] = (blockIdx.x * kFillPerThread + k) * blockDim.x + threadIdx.x;
-    tiles[k] = tri[k] < p.num_tris ? __ldg(p.tri_tiles + tri[k]) : 0xffffffffu;
-    alive[k] = tiles[k] != 0xffffffffu;
-  }
-  // ranges of up to 2x2 tiles, quadrant by quadrant (same grouping as for_each_tile's matched path)
 #pragma unroll
   for(uint32_t q = 0; q < 4u; q++)
   {
     const uint32_t qx = q & 1u, qy = q >> 1;
-    uint32_t tile[kFillPerThread], peers[kFillPerThread], base[kFillPerThread];
+    uint32_t tile[kSetupPerThread], peers[kSetupPerThread], pos[kSetupPerThread];
     bool any = false;
 #pragma unroll
-    for(int k = 0; k < kFillPerThread; k++)
+    for(int k = 0; k < kSetupPerThread; k++)
     {
-      const uint32_t tx0 = tiles[k] & 0xffu, ty0 = (tiles[k] >> 8) & 0xffu;
-      const uint32_t nx = ((tiles[k] >> 16) & 0xffu) - tx0 + 1u, ny = (tiles[k] >> 24) - ty0 + 1u;
       tile[k] = 0xffffffffu;
-      if(alive[k] && nx <= 2u && ny <= 2u && qx < nx && qy < ny)
+      if(nx[k] <= 2u && ny[k] <= 2u && qx < nx[k] && qy < ny[k])
       {
-        tile[k] = (ty0 + qy) * p.tiles_x + tx0 + qx;
+        tile[k] = (((tiles[k] >> 8) & 0xffu) + qy) * p.tiles_x + (tiles[k] & 0xffu) + qx;
         if(!tile_owned(tile[k], p.owner_rank, p.owner_world))
           tile[k] = 0xffffffffu;
       }
       any |= tile[k] != 0xffffffffu;
     }
     if(!__any_sync(0xffffffffu, any))
-      continue;
+      continue;    // most triangles touch one tile: the other three quadrants are empty for the whole warp
 #pragma unroll
-    for(int k = 0; k < kFillPerThread; k++)
+    for(int k = 0; k < kSetupPerThread; k++)
     {
       peers[k] = __match_any_sync(0xffffffffu, tile[k]);
-      base[k] = 0;
+      pos[k] = 0;
       if(tile[k] != 0xffffffffu && (uint32_t)(__ffs(peers[k]) - 1) == lane)
-        base[k] = atomicAdd(&tile_cursor[tile[k]], __popc(peers[k]));    // cursors start at the CSR offsets
+        pos[k] = atomicAdd(&p.tile_count[tile[k]], (uint32_t)__popc(peers[k]));
     }
 #pragma unroll
-    for(int k = 0; k < kFillPerThread; k++)
+    for(int k = 0; k < kSetupPerThread; k++)
     {
-      base[k] = __shfl_sync(0xffffffffu, base[k], __ffs(peers[k]) - 1);
-      const uint32_t pos = base[k] + __popc(peers[k] & below);
-      if(tile[k] != 0xffffffffu && pos < capacity)
-        list[pos] = tri[k];
+      pos[k] = __shfl_sync(0xffffffffu, pos[k], __ffs(peers[k]) - 1) + __popc(peers[k] & below);
+      if(tile[k] != 0xffffffffu)
+      {
+        used[k] = true;
+        mypairs++;
+        if(pos[k] < p.list_cap)
+          p.list[(size_t)(tile[k] / p.owner_world) * p.list_cap + pos[k]] = t[k];
+      }
     }
   }
-  // larger ranges: the CTA-wide walk of for_each_tile (its matched path finds nothing to do here)
 #pragma unroll
-  for(int k = 0; k < kFillPerThread; k++)
+  for(int k = 0; k < kSetupPerThread; k++)
+    if(alive[k] && (nx[k] > 2u || ny[k] > 2u))
+    {
+      used[k] = true;
+      const uint32_t slot = atomicAdd(&s_nbig, 1u);
+      s_big[slot][0] = tiles[k];
+      s_big[slot][1] = t[k];
+    }
+  // ---- 5. the 16-byte triangle record (only of triangles this rank will rasterise: with sort-first
+  // ownership that is 1/world of them) and the packed tile range (of all: the tile kernels' fallback list)
+#pragma unroll
+  for(int k = 0; k < kSetupPerThread; k++)
+    if(t[k] < p.num_tris)
+    {
+      if(used[k])
+        *(int4 *)(p.tri + t[k]) = make_int4((int)s0[k], (int)s1[k], (int)s2[k], __float_as_int(invarea[k]));
+      p.tri_tiles[t[k]] = alive[k] ? tiles[k] : VB200_TILES_DEAD;
+    }
+  __syncthreads();
+  const uint32_t nbig = s_nbig;
+  for(uint32_t b = 0; b < nbig; b++)
   {
-    const uint32_t nx = ((tiles[k] >> 16) & 0xffu) - (tiles[k] & 0xffu) + 1u;
-    const uint32_t ny = (tiles[k] >> 24) - ((tiles[k] >> 8) & 0xffu) + 1u;
-    const bool big = alive[k] && (nx > 2u || ny > 2u);
-    for_each_tile(tiles[k], big, p.tiles_x, p.owner_rank, p.owner_world, tri[k],
-                  [=](uint32_t tile, uint32_t t, uint32_t, uint32_t, bool, uint32_t) {
-                    const uint32_t pos = atomicAdd(&tile_cursor[tile], 1u);
-                    if(pos < capacity)
-                      list[pos] = t;
-                  });
+    const uint32_t bt = s_big[b][0], b_tri = s_big[b][1];
+    const uint32_t b_tx0 = bt & 0xffu, b_ty0 = (bt >> 8) & 0xffu;
+    const uint32_t b_nx = ((bt >> 16) & 0xffu) - b_tx0 + 1u, b_nt = b_nx * ((bt >> 24) - b_ty0 + 1u);
+    for(uint32_t k = threadIdx.x; k < b_nt; k += kThreads)
+    {
+      const uint32_t tile = (b_ty0 + k / b_nx) * p.tiles_x + b_tx0 + k % b_nx;
+      if(tile_owned(tile, p.owner_rank, p.owner_world))
+      {
+        const uint32_t pos = atomicAdd(&p.tile_count[tile], 1u);
+        mypairs++;
+        if(pos < p.list_cap)
+          p.list[(size_t)(tile / p.owner_world) * p.list_cap + pos] = b_tri;
+      }
+    }
+  }
+  mypairs = __reduce_add_sync(0xffffffffu, mypairs);
+  if(lane == 0 && mypairs)
+    atomicAdd(&s_pairs, mypairs);
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    Vb200DrawCounters::Slot &c = p.counters->slot[blockIdx.x & (VB200_COUNTER_SLOTS - 1)];
+    if(survivors)
+      atomicAdd(&c.triangles_out, (unsigned long long)survivors);
+    if(s_pairs)
+      atomicAdd(&c.tile_pairs, (unsigned long long)s_pairs);
   }
 }
 
@@ -524,18 +397,17 @@ __device__ __forceinline__ void bitonic_sort(uint32_t *a, uint32_t n)
 
 constexpr uint32_t kSortSmem = 8192;    // entries (32 KB)
 
-__global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_t *tile_offset,
-                                                  const uint32_t *tile_count, const uint32_t *total,
-                                                  uint32_t capacity)
+__global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_t *tile_count, uint32_t list_cap,
+                                                  uint32_t rank, uint32_t world, uint32_t ntiles)
 {
   __shared__ __align__(16) uint32_t s[kSortSmem];
-  if(*total > capacity)
+  const uint32_t tile = blockIdx.x * world + rank;    // the grid holds the tiles this rank owns
+  if(tile >= ntiles)
     return;
-  const uint32_t tile = blockIdx.x;
   const uint32_t n = tile_count[tile];
-  if(n < 2u)
+  if(n < 2u || n > list_cap)    // an overflowed list is not used: the tile kernel scans tri_tiles, in order
     return;
-  uint32_t *a = list + tile_offset[tile];
+  uint32_t *a = list + (size_t)blockIdx.x * list_cap;
   int unsorted = 0;
   for(uint32_t i = threadIdx.x; i + 1u < n; i += blockDim.x)
     unsorted |= a[i] > a[i + 1u];
@@ -694,27 +566,10 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
   return 1;
 }
 
-int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
-                uint32_t *total, unsigned long long *host_total_dev, uint32_t seq, cudaStream_t s)
+int launch_sort(uint32_t *list, const uint32_t *tile_count, uint32_t list_cap, uint32_t rank, uint32_t world,
+                uint32_t ntiles, cudaStream_t s)
 {
-  k_scan<<<1, 1024, 0, s>>>(tile_count, tile_offset, tile_cursor, ntiles, total, host_total_dev, seq);
-  return 1;
-}
-
-int launch_fill(const Vb200SetupParams &p, const uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t *list,
-                uint32_t capacity, const uint32_t *total, cudaStream_t s)
-{
-  if(!p.num_tris)
-    return 0;
-  const uint32_t per_cta = kThreads * kFillPerThread;
-  k_fill<<<(p.num_tris + per_cta - 1) / per_cta, kThreads, 0, s>>>(p, tile_offset, tile_cursor, list, capacity, total);
-  return 1;
-}
-
-int launch_sort(uint32_t *list, const uint32_t *tile_offset, const uint32_t *tile_count, uint32_t ntiles,
-                const uint32_t *total, uint32_t capacity, cudaStream_t s)
-{
-  k_sort<<<ntiles, kThreads, 0, s>>>(list, tile_offset, tile_count, total, capacity);
+  k_sort<<<(ntiles + world - 1) / world, kThreads, 0, s>>>(list, tile_count, list_cap, rank, world, ntiles);
   return 1;
 }
 

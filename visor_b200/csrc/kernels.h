@@ -12,10 +12,18 @@ struct Vb200SetupParams
   const uint32_t *range;    // indexed: device {minIndex, maxIndex}; slot = index - minIndex (NULL: slot = index - base_vertex)
   uint32_t base_vertex;     // non-indexed: slot = vertex - base_vertex
   uint32_t capacity;        // number of valid post-VS records
+  uint32_t vertex_bound;    // indexed draws: vertices the bound buffers hold; an index at or above it kills the triangle
   const Vb200RasterVertex *rv;
   Vb200TriRecord *tri;
-  uint32_t *tri_tiles;    // packed tile range per triangle (0xffffffff = dead), read by the fill pass
+  uint32_t *tri_tiles;    // packed tile range per triangle (VB200_TILES_DEAD = dead): the tile kernels' fallback list
+  // Binning is one pass: the setup kernel appends each surviving triangle straight into the list of every
+  // tile its bbox touches. Tile t (owned slot t / owner_world) has room for list_cap ids at
+  // list[slot * list_cap]; tile_count[t] counts EVERY append, so a count above list_cap says "this list is
+  // incomplete" and the tile kernel then finds its triangles by scanning tri_tiles instead (exact, in order,
+  // no host round trip and no retry).
   uint32_t *tile_count;
+  uint32_t *list;
+  uint32_t list_cap;
   Vb200DrawCounters *counters;
   uint32_t front_face, cull_mode;
   uint32_t width, height, tiles_x, tiles_y, owner_rank, owner_world;
@@ -27,6 +35,7 @@ struct Vb200VertexParams
   const uint32_t *range;
   uint32_t base_vertex;
   uint32_t count;
+  uint32_t vertex_bound;    // vertices the bound vertex buffers hold (0xffffffff: unbounded): nothing beyond is fetched
   Vb200RasterVertex *rv;
   float4 *interps;
   uint32_t nslots;
@@ -40,11 +49,11 @@ struct Vb200TileParams
 {
   const Vb200TriRecord *tri;
   const Vb200RasterVertex *rv;
-  const uint32_t *list;
-  const uint32_t *tile_offset;
-  const uint32_t *tile_count;
-  const uint32_t *total;      // (triangle, tile) pairs binned; > list_capacity = speculative launch must no-op
-  uint32_t list_capacity;
+  const uint32_t *list;         // per-tile lists: tile t's ids start at list[(t / owner_world) * list_cap]
+  const uint32_t *tile_count;   // appends per tile; > list_cap: the list is incomplete, scan tri_tiles instead
+  const uint32_t *tri_tiles;    // packed tile range per triangle (VB200_TILES_DEAD = dead)
+  uint32_t list_cap;
+  uint32_t num_tris;
   // pending ClearTarget()s folded into this launch: bit 0 colour, bit 1 depth. The kernel then takes the
   // attachment's prior contents from these constants instead of loading them and writes EVERY pixel of
   // every tile (including tiles no triangle touches), so no separate clear kernel runs.
@@ -72,12 +81,8 @@ int launch_clear_u8(uint8_t *dst, uint8_t value, size_t count, cudaStream_t s);
 int launch_index_range(const void *ib, uint32_t index_type, uint32_t first, uint32_t count, uint32_t *range,
                        cudaStream_t s);
 int launch_setup(const Vb200SetupParams &p, cudaStream_t s);
-int launch_scan(const uint32_t *tile_count, uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t ntiles,
-                uint32_t *total, unsigned long long *host_total_dev, uint32_t seq, cudaStream_t s);
-int launch_fill(const Vb200SetupParams &p, const uint32_t *tile_offset, uint32_t *tile_cursor, uint32_t *list,
-                uint32_t capacity, const uint32_t *total, cudaStream_t s);
-int launch_sort(uint32_t *list, const uint32_t *tile_offset, const uint32_t *tile_count, uint32_t ntiles,
-                const uint32_t *total, uint32_t capacity, cudaStream_t s);
+int launch_sort(uint32_t *list, const uint32_t *tile_count, uint32_t list_cap, uint32_t rank, uint32_t world,
+                uint32_t ntiles, cudaStream_t s);
 int launch_sample(const Vb200Image &img, int cube, uint64_t byte_offset, const float *uvw, float4 *out,
                   size_t count, cudaStream_t s);
 int launch_tiles_pack(const uint32_t *color, uint32_t width, uint32_t height, uint32_t rank, uint32_t world,

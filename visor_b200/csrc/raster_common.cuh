@@ -37,6 +37,13 @@ __device__ __forceinline__ Vb200TriSetup vb200_load_setup(const Vb200TileParams 
   return r;
 }
 
+// does the packed inclusive tile range (tx0 | ty0 << 8 | tx1 << 16 | ty1 << 24) contain tile (tx, ty)?
+// VB200_TILES_DEAD has tx0 = 255 > tx1 = 0 and contains nothing.
+__device__ __forceinline__ bool vb200_tile_in_range(uint32_t tiles, uint32_t tx, uint32_t ty)
+{
+  return tx >= (tiles & 0xffu) && tx <= ((tiles >> 16) & 0xffu) && ty >= ((tiles >> 8) & 0xffu) && ty <= (tiles >> 24);
+}
+
 // rasterizer.cpp:562-576
 __device__ __forceinline__ bool vb200_depth_pass(uint32_t op, float pixdepth, float curdepth)
 {

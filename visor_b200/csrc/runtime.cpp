@@ -5,7 +5,7 @@
 // (SPIR-V -> PTX -> ptxas -> cudaLibrary) and the launch sequence that replaces DrawTriangles
 // (rasterizer.cpp:363-520):
 //
-//   [index range] -> K1 vertex (JIT) -> K2 setup+count -> scan -> fill -> per-tile sort -> K4 tiles (JIT)
+//   [index range] -> K1 vertex (JIT) -> K2 setup + binning -> [per-tile sort] -> K4 tiles (JIT)
 //
 // There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point
 // returns VB200_ERR_NO_DEVICE.
@@ -82,6 +82,76 @@ struct JitKernel
   cudaKernel_t kernel = nullptr;
 };
 
+// Set of disjoint half-open byte intervals [lo, hi) of a mirror, kept sorted and merged.
+struct IntervalSet
+{
+  std::vector<std::pair<size_t, size_t>> v;    // (lo, hi)
+  bool empty() const { return v.empty(); }
+  void clear() { v.clear(); }
+  void add(size_t lo, size_t hi)
+  {
+    if(lo >= hi)
+      return;
+    std::vector<std::pair<size_t, size_t>> out;
+    out.reserve(v.size() + 1);
+    size_t i = 0;
+    for(; i < v.size() && v[i].second < lo; i++)
+      out.push_back(v[i]);
+    for(; i < v.size() && v[i].first <= hi; i++)    // overlapping or touching: absorb
+    {
+      lo = std::min(lo, v[i].first);
+      hi = std::max(hi, v[i].second);
+    }
+    out.push_back({lo, hi});
+    for(; i < v.size(); i++)
+      out.push_back(v[i]);
+    v.swap(out);
+  }
+  // removes [lo, hi); returns whether anything was removed
+  bool remove(size_t lo, size_t hi)
+  {
+    bool hit = false;
+    std::vector<std::pair<size_t, size_t>> out;
+    for(auto &r : v)
+    {
+      if(r.second <= lo || r.first >= hi)
+      {
+        out.push_back(r);
+        continue;
+      }
+      hit = true;
+      if(r.first < lo)
+        out.push_back({r.first, lo});
+      if(r.second > hi)
+        out.push_back({hi, r.second});
+    }
+    v.swap(out);
+    return hit;
+  }
+  // the parts of [lo, hi) that lie in neither this set nor `other`, in order
+  std::vector<std::pair<size_t, size_t>> gaps(size_t lo, size_t hi, const IntervalSet &other) const
+  {
+    IntervalSet u = *this;
+    for(auto &r : other.v)
+      u.add(r.first, r.second);
+    std::vector<std::pair<size_t, size_t>> out;
+    size_t at = lo;
+    for(auto &r : u.v)
+    {
+      if(r.second <= at)
+        continue;
+      if(r.first >= hi)
+        break;
+      if(r.first > at)
+        out.push_back({at, r.first});
+      at = std::max(at, r.second);
+    }
+    if(at < hi)
+      out.push_back({at, hi});
+    return out;
+  }
+};
+
 struct Mirror
 {
   uint8_t *host = nullptr;
@@ -91,8 +161,12 @@ struct Mirror
   bool explicitReg = false;
   bool deviceLocal = false;    // DEVICE_LOCAL memory: the mirror is authoritative, no per-epoch upload/download
   uint64_t lastUse = 0;
-  std::vector<std::pair<size_t, size_t>> uploaded;    // (offset, size) uploaded this epoch
-  std::vector<std::pair<size_t, size_t>> written;     // (offset, size) written by kernels this epoch
+  // coherent mode, this epoch (= since the last flush): bytes the device copy already holds from the host
+  // (uploaded) and bytes device work produced, which a flush brings back (written). A read uploads exactly
+  // the bytes of its range that are in neither set, so results produced earlier in the same submit (a
+  // rendered or copied-to image that is sampled afterwards, a partially copied buffer) are never overwritten
+  // with stale host data.
+  IntervalSet uploaded, written;
 };
 
 template <typename T>
@@ -139,12 +213,8 @@ struct Context
   DevBuf<Vb200RasterVertex> rv;
   DevBuf<float4> interps;
   DevBuf<Vb200TriRecord> setup;
-  DevBuf<uint32_t> tileCount, tileOffset, tileCursor, list, triTiles;
+  DevBuf<uint32_t> tileCount, list, triTiles;
   uint32_t *range = nullptr;                // device {min,max}
-  uint32_t *total = nullptr;                // device
-  volatile unsigned long long *totalHost = nullptr;    // mapped pinned: (draw seq << 32) | pair total
-  unsigned long long *totalHostDev = nullptr;          // its device address
-  uint32_t drawSeq = 0;
   // ClearTarget()s not yet executed: device address of the attachment -> fill word and pixel count.
   // The next draw into the attachment folds them into its tile kernel; anything else that touches the
   // memory (another reader, a download) materialises them with the fill kernel first.
@@ -156,6 +226,7 @@ struct Context
   std::map<uint8_t *, PendingClear> pendingClears;
   int64_t optFuseClears = 1;
   int64_t optSlotKeys = 1;    // 0: never put the record slot into the visibility key (the path of draws >= 2^24 triangles)
+  int64_t optTileListCap = 0; // > 0: entries per tile list (testing aid: a tiny value forces the tile kernels' fallback scan)
   // fused sort-first exchange: colour target (device address on this rank) -> the same image on the peers
   std::map<uint8_t *, std::vector<uint32_t *>> peerTargets;
   std::map<uint8_t *, uint32_t *> multicastTargets;
@@ -279,6 +350,9 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
   nm.host = (uint8_t *)lo;
   nm.size = hi - lo;
   CU(cudaMalloc((void **)&nm.dev, std::max<size_t>(nm.size + 16, 256)));
+  // 16 bytes of slack behind every mirror, zeroed: texel fetches of formats narrower than 4 bytes read 4 bytes
+  // per texel and may look up to 3 bytes past the end of an image that ends the mirror
+  CU(cudaMemsetAsync(nm.dev + nm.size, 0, std::max<size_t>(nm.size + 16, 256) - nm.size, g.stream));
   for(uintptr_t key : victims)
   {
     Mirror &old = g.mirrors[key];
@@ -286,10 +360,11 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
       return mrc;
     // keep device-side contents (attachments may hold results not yet downloaded)
     CU(cudaMemcpyAsync(nm.dev + ((uintptr_t)old.host - lo), old.dev, old.size, cudaMemcpyDeviceToDevice, g.stream));
-    for(auto &w : old.written)
-      nm.written.push_back({w.first + ((uintptr_t)old.host - lo), w.second});
-    for(auto &u : old.uploaded)
-      nm.uploaded.push_back({u.first + ((uintptr_t)old.host - lo), u.second});
+    const size_t shift = (uintptr_t)old.host - lo;
+    for(auto &w : old.written.v)
+      nm.written.add(w.first + shift, w.second + shift);
+    for(auto &u : old.uploaded.v)
+      nm.uploaded.add(u.first + shift, u.second + shift);
     if(old.pinned)
       cudaHostUnregister(old.host);
     // Launches already enqueued (and the draw being assembled right now) may hold device addresses
@@ -335,14 +410,6 @@ int materializeClears(const uint8_t *dev, size_t bytes)
   }
   CU(cudaGetLastError());
   return VB200_OK;
-}
-
-bool rangeCovered(const std::vector<std::pair<size_t, size_t>> &v, size_t off, size_t size)
-{
-  for(auto &r : v)
-    if(off >= r.first && off + size <= r.first + r.second)
-      return true;
-  return false;
 }
 
 enum Access
@@ -391,15 +458,18 @@ int resolveInner(const void *ptr, size_t size, int access, uint8_t **out)
   const size_t off = (uintptr_t)ptr - (uintptr_t)m->host;
   if(g.syncMode == VB200_SYNC_COHERENT && !m->deviceLocal)
   {
-    const bool devNewer = rangeCovered(m->written, off, size);
-    if((access & ACC_READ) && !(access & ACC_OVERWRITE) && !devNewer && !rangeCovered(m->uploaded, off, size))
+    if((access & ACC_READ) && !(access & ACC_OVERWRITE))
     {
-      CU(cudaMemcpyAsync(m->dev + off, ptr, size, cudaMemcpyHostToDevice, g.stream));
-      g.stats.h2d_bytes += size;
-      m->uploaded.push_back({off, size});
+      for(auto &gap : m->uploaded.gaps(off, off + size, m->written))
+      {
+        CU(cudaMemcpyAsync(m->dev + gap.first, m->host + gap.first, gap.second - gap.first, cudaMemcpyHostToDevice,
+                           g.stream));
+        g.stats.h2d_bytes += gap.second - gap.first;
+        m->uploaded.add(gap.first, gap.second);
+      }
     }
-    if((access & (ACC_WRITE | ACC_OVERWRITE)) && !devNewer)
-      m->written.push_back({off, size});
+    if(access & (ACC_WRITE | ACC_OVERWRITE))
+      m->written.add(off, off + size);
   }
   *out = m->dev + off;
   if(!(access & ACC_KEEP_PENDING) && !g.pendingClears.empty())
@@ -555,7 +625,7 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
   // 182 -> 167 us, C5 1086 -> 1010 us; six CTAs spill more and are slower again). Whether a shader
   // leaves room for that is only known after inlining, so the bound is dropped when ptxas reports
   // more than a few spilled words. VB200_JIT_MINCTAS overrides (tuning aid).
-  const unsigned kSpillTolerance = 32;
+  const unsigned kSpillTolerance = 64;
   int minCtas = which != K_VERTEX ? 5 : 0;
   bool forced = false;
   if(const char *mc = getenv("VB200_JIT_MINCTAS"))
@@ -678,6 +748,16 @@ uint64_t imageBytes(const vb200_image &im)
   return sz;
 }
 
+// Bytes of a sampled image to make resident. Texel fetches of formats narrower than 4 bytes read 4 bytes
+// per texel (texture_sampling.cpp:121-133), so the last texels look up to 3 bytes past the image, at
+// whatever follows it in the same allocation. Those bytes are mirrored only when they are known to exist:
+// when the image lies inside an already mirrored (registered) range that extends that far. The library
+// never reads host memory beyond what the caller described.
+size_t sampledExtent(const void *pixels, uint64_t bytes)
+{
+  return (size_t)bytes + (findMirror(pixels, (size_t)bytes + 4) ? 4 : 0);
+}
+
 const vb200_binding *findBinding(const vb200_draw_state *s, uint32_t set, uint32_t binding)
 {
   for(uint32_t i = 0; i < s->num_bindings; i++)
@@ -702,7 +782,7 @@ int fillResources(const vb200_draw_state *s, const vb200::ShaderEntry &e, Vb200E
       if((im.width & 3) || (im.height & 3))
         return setError(VB200_ERR_INVALID, "texture size must be a multiple of 4 (texture_sampling.cpp:123-133)");
       uint8_t *dev;
-      int rc = resolve(im.pixels, imageBytes(im) + 4, ACC_READ, &dev);    // +4: bpp<4 reads 4 bytes per texel
+      int rc = resolve(im.pixels, sampledExtent(im.pixels, imageBytes(im)), ACC_READ, &dev);
       if(rc)
         return rc;
       Vb200Image &d = env.images[r.slot];
@@ -787,10 +867,6 @@ int vb200_init(int device)
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
   CU(cudaMalloc((void **)&g.range, 2 * sizeof(uint32_t)));
-  CU(cudaMalloc((void **)&g.total, sizeof(uint32_t)));
-  CU(cudaHostAlloc((void **)&g.totalHost, sizeof(unsigned long long), cudaHostAllocMapped));
-  *g.totalHost = 0;
-  CU(cudaHostGetDevicePointer((void **)&g.totalHostDev, (void *)g.totalHost, 0));
   CU(cudaMalloc((void **)&g.counters, sizeof(Vb200DrawCounters)));
   CU(cudaMemsetAsync(g.counters, 0, sizeof(Vb200DrawCounters), g.stream));
   memset(&g.stats, 0, sizeof(g.stats));
@@ -818,12 +894,8 @@ void vb200_shutdown(void)
   g.interps.release();
   g.setup.release();
   g.tileCount.release();
-  g.tileOffset.release();
-  g.tileCursor.release();
   g.list.release();
   cudaFree(g.range);
-  cudaFree(g.total);
-  cudaFreeHost((void *)g.totalHost);
   g.triTiles.release();
   cudaFree(g.counters);
   for(auto &pr : g.presents)
@@ -1085,17 +1157,8 @@ int vb200_mem_host_write(const void *host, uint64_t size)
     const uintptr_t mlo = (uintptr_t)m.host, mhi = mlo + m.size;
     if(mlo >= hi || lo >= mhi)
       continue;
-    for(auto it = m.uploaded.begin(); it != m.uploaded.end();)
-    {
-      const uintptr_t ulo = mlo + it->first, uhi = ulo + it->second;
-      if(ulo < hi && lo < uhi)
-      {
-        pending = true;
-        it = m.uploaded.erase(it);
-      }
-      else
-        ++it;
-    }
+    const size_t rlo = (size_t)(std::max(lo, mlo) - mlo), rhi = (size_t)(std::min(hi, mhi) - mlo);
+    pending |= m.uploaded.remove(rlo, rhi);
   }
   if(pending)
     CU(cudaStreamSynchronize(g.stream));
@@ -1265,10 +1328,10 @@ int vb200_flush(void)
     for(auto &kv : g.mirrors)
     {
       Mirror &m = kv.second;
-      for(auto &w : m.written)
+      for(auto &w : m.written.v)
       {
-        CU(cudaMemcpyAsync(m.host + w.first, m.dev + w.first, w.second, cudaMemcpyDeviceToHost, g.stream));
-        g.stats.d2h_bytes += w.second;
+        CU(cudaMemcpyAsync(m.host + w.first, m.dev + w.first, w.second - w.first, cudaMemcpyDeviceToHost, g.stream));
+        g.stats.d2h_bytes += w.second - w.first;
       }
     }
   }
@@ -1472,7 +1535,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     if(!s->ib.buffer.bytes)
       return setError(VB200_ERR_INVALID, "indexed draw without an index buffer");
     const uint32_t isz = s->ib.index_type == 0u ? 2u : 4u;
-    if(s->ib.offset + (uint64_t)(first + usedVerts) * isz > s->ib.buffer.size)
+    if(s->ib.offset + ((uint64_t)first + usedVerts) * isz > s->ib.buffer.size)
       return setError(VB200_ERR_INVALID, "index range lies outside the index buffer");
     uint8_t *dev;
     if((rc = resolve(s->ib.buffer.bytes, s->ib.buffer.size, ACC_READ, &dev)))
@@ -1513,13 +1576,20 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   const uint32_t W = s->color.width, H = s->color.height;
   const uint32_t tilesX = (W + VB200_TILE - 1) / VB200_TILE, tilesY = (H + VB200_TILE - 1) / VB200_TILE;
   const uint32_t ntiles = tilesX * tilesY;
-  const uint32_t ntilesPad = (ntiles + 4095u) & ~4095u;    // the scan kernel moves 16-byte vectors
-  // tile-list capacity is a guess (the pair total is only known on the device): 4 pairs per triangle
-  // covers every triangle smaller than a tile; kernels that find it too small do nothing and are rerun
-  const size_t listGuess = std::max<size_t>(g.list.cap, (size_t)numTris * 4 + 65536);
+  const uint32_t ownedTiles = (ntiles + g.ownerWorld - 1u) / g.ownerWorld;
+  // Entries per tile list: a power of two of at least four times the average load (a perspective mesh puts
+  // several times the average into its far tiles), within [256, 4096]. It is only a performance knob: a
+  // tile that receives more triangles than that is rasterised from the packed tile ranges instead.
+  uint32_t listCap = 256;
+  {
+    const uint64_t want = 4ull * numTris / std::max(1u, ntiles) + 64;
+    while(listCap < want && listCap < 4096u)
+      listCap <<= 1;
+    if(g.optTileListCap > 0)
+      listCap = (uint32_t)std::min<int64_t>(g.optTileListCap, 1 << 20);
+  }
   if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * nslots) || !g.setup.reserve(numTris) ||
-     !g.triTiles.reserve(numTris) || !g.list.reserve(listGuess) || !g.tileCount.reserve(ntilesPad) ||
-     !g.tileOffset.reserve(ntilesPad) || !g.tileCursor.reserve(ntilesPad))
+     !g.triTiles.reserve(numTris) || !g.list.reserve((size_t)ownedTiles * listCap) || !g.tileCount.reserve(ntiles))
   {
     g.stickyCuda = 1;
     return setError(VB200_ERR_CUDA, "out of device memory for draw scratch");
@@ -1568,13 +1638,14 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   vp.range = (indexed && !shadeAll) ? g.range : nullptr;
   vp.base_vertex = baseVertex;
   vp.count = capacity;
+  vp.vertex_bound = vertexBound;
   vp.rv = g.rv.p;
   vp.interps = g.interps.p;
   vp.nslots = nslots;
   vp.width = W;
   vp.height = H;
   vp.tile_count = g.tileCount.p;
-  vp.tile_count_n = ntilesPad;
+  vp.tile_count_n = ntiles;
   {
     cudaKernel_t kVertex = nullptr;
     if((rc = getKernel(K_VERTEX, pl->vs, &kVertex)))
@@ -1597,10 +1668,13 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.range = shadeAll ? nullptr : g.range;
   sp.base_vertex = baseVertex;
   sp.capacity = capacity;
+  sp.vertex_bound = indexed ? vertexBound : 0xffffffffu;
   sp.rv = g.rv.p;
   sp.tri = g.setup.p;
   sp.tri_tiles = g.triTiles.p;
   sp.tile_count = g.tileCount.p;
+  sp.list = g.list.p;
+  sp.list_cap = listCap;
   sp.counters = g.counters;
   sp.front_face = pl->front_face;
   sp.cull_mode = pl->cull_mode;
@@ -1611,6 +1685,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.owner_rank = g.ownerRank;
   sp.owner_world = g.ownerWorld;
   g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);    // (the vertex kernel zeroed the tile counters)
+  phaseMark(2);
 
   // Raster back end. A pass is order-independent ("resolvable") unless it blends or runs
   // NOT_EQUAL against a depth buffer it also writes; see scaffold.cu.
@@ -1645,9 +1720,11 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   memset(&tp, 0, sizeof(tp));
   tp.tri = g.setup.p;
   tp.rv = g.rv.p;
-  tp.tile_offset = g.tileOffset.p;
+  tp.list = g.list.p;
+  tp.list_cap = listCap;
   tp.tile_count = g.tileCount.p;
-  tp.total = g.total;
+  tp.tri_tiles = g.triTiles.p;
+  tp.num_tris = numTris;
   tp.color = (uint32_t *)colorDev;
   tp.depth = (float *)depthDev;
   tp.interps = g.interps.p;
@@ -1685,64 +1762,17 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     }
   }
 
-  // ---- K3 + K4, launched speculatively: scan publishes the pair total to a mapped host word; fill,
-  // sort and the tile kernel are enqueued right behind it against the guessed list capacity and turn
-  // into no-ops if the total does not fit. The host polls the word while the GPU works; only on a
-  // miss (never for triangles smaller than a tile) the list is grown and the three are enqueued again.
-  phaseMark(2);
-  const uint32_t seq = ++g.drawSeq;
-  g.stats.kernel_launches += vb200::launch_scan(g.tileCount.p, g.tileOffset.p, g.tileCursor.p, ntiles, g.total,
-                                                g.totalHostDev, seq, g.stream);
-  uint32_t pairs = 0;
-  for(int attempt = 0; attempt < 2; attempt++)
+  // ---- K3' + K4. The ordered path needs each tile's list in submission order (the appends of the setup
+  // kernel arrive in any order); nothing here waits for the device.
+  if(resolveMode < 0)
+    g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileCount.p, listCap, g.ownerRank, g.ownerWorld, ntiles,
+                                                  g.stream);
+  phaseMark(3);
   {
-    const uint32_t listCap = (uint32_t)std::min<size_t>(g.list.cap, 0xffffffffu);
-    tp.list = g.list.p;
-    tp.list_capacity = listCap;
-    g.stats.kernel_launches += vb200::launch_fill(sp, g.tileOffset.p, g.tileCursor.p, g.list.p, listCap, g.total, g.stream);
-    if(resolveMode < 0)    // ordered path needs each tile's list in submission order
-      g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileOffset.p, g.tileCount.p, ntiles, g.total, listCap,
-                                                    g.stream);
-    if(attempt == 0)
-      phaseMark(3);
-    {
-      void *args[] = {&env, &tp};
-      const uint32_t ownedTiles = (ntiles + g.ownerWorld - 1u) / g.ownerWorld;
-      if((rc = launchKernel(kTile, dim3(ownedTiles), dim3(256), args)))
-        return rc;
-    }
-    if(attempt == 1)
-      break;
-    // wait for the scan's total (the GPU keeps running the kernels queued behind it)
-    for(uint64_t spins = 0;; spins++)
-    {
-      const unsigned long long v = *g.totalHost;
-      if((uint32_t)(v >> 32) == seq)
-      {
-        pairs = (uint32_t)v;
-        break;
-      }
-      if((spins & 0xfff) == 0xfff)
-      {
-        cudaError_t q = cudaStreamQuery(g.stream);
-        if(q != cudaSuccess && q != cudaErrorNotReady)
-          CU(q);
-        if(q == cudaSuccess && (uint32_t)(*g.totalHost >> 32) != seq)
-          return setError(VB200_ERR_CUDA, "binning total was never published");
-      }
-    }
-    if(pairs <= listCap)
-      break;
-    // guessed capacity too small: the speculative kernels did nothing; grow and go again
-    CU(cudaStreamSynchronize(g.stream));
-    if(!g.list.reserve((size_t)pairs + pairs / 4))
-    {
-      g.stickyCuda = 1;
-      return setError(VB200_ERR_CUDA, "out of device memory for %u tile-list entries", pairs);
-    }
-    CU(cudaMemcpyAsync(g.tileCursor.p, g.tileOffset.p, ntiles * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g.stream));
+    void *args[] = {&env, &tp};
+    if((rc = launchKernel(kTile, dim3(ownedTiles), dim3(256), args)))
+      return rc;
   }
-  g.stats.tile_pairs += pairs;
   phaseMark(4);
   phaseAccumulate(VB200_PHASE_VERTEX, 0, 1);
   phaseAccumulate(VB200_PHASE_SETUP, 1, 2);
@@ -1764,7 +1794,7 @@ int vb200_sample(const vb200_image *tex, int cube, uint64_t byte_offset, const f
     return VB200_OK;
   uint8_t *dev;
   uint64_t bytes = cube ? sliceBytes(*tex) * 6 : imageBytes(*tex);
-  if((rc = resolve(tex->pixels, bytes + 4, ACC_READ, &dev)))
+  if((rc = resolve(tex->pixels, sampledExtent(tex->pixels, bytes), ACC_READ, &dev)))
     return rc;
   Vb200Image d;
   d.pixels = dev;
@@ -1893,9 +1923,10 @@ int vb200_get_stats(vb200_stats *out)
   CU(cudaMemcpyAsync(&c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   *out = g.stats;
-  out->triangles_out = out->fragments_covered = out->fragments_shaded = 0;
+  out->triangles_out = out->fragments_covered = out->fragments_shaded = out->tile_pairs = 0;
   for(int i = 0; i < VB200_COUNTER_SLOTS; i++)
   {
+    out->tile_pairs += c.slot[i].tile_pairs;
     out->triangles_out += c.slot[i].triangles_out;
     out->fragments_covered += c.slot[i].fragments_covered;
     out->fragments_shaded += c.slot[i].fragments_shaded;
@@ -1972,6 +2003,8 @@ int vb200_set_option(const char *name, int64_t value)
     g.optFuseClears = value;
   else if(!strcmp(name, "slot_keys"))
     g.optSlotKeys = value;
+  else if(!strcmp(name, "tile_list_cap"))
+    g.optTileListCap = value;
   else if(!strcmp(name, "extended_spirv"))
     vb200::set_extended_spirv(value != 0);
   else if(!strcmp(name, "time_kernels"))

@@ -135,6 +135,10 @@ extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_co
     base = lo;
     const uint32_t span = hi - lo + 1u;
     count = span < count ? span : count;
+    // a malformed index beyond the bound vertex buffers must not make the fetch run past them
+    if(lo >= p.vertex_bound)
+      return;
+    count = min(count, p.vertex_bound - lo);
   }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= count)
@@ -194,19 +198,22 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   __shared__ uint32_t s_col[8][128];
   __shared__ float s_dep[8][128];
   __shared__ uint16_t s_queue[8][256];    // per-warp fragment ring: (triangle slot << 7) | region pixel
+  __shared__ uint32_t s_wids[8][64];      // per-warp id queue of the fallback scan (overflowed tile list)
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
   const uint32_t tile = blockIdx.x * p.rs.owner_world + p.rs.owner_rank;
   if(tile >= p.rs.tiles_x * p.rs.tiles_y)
     return;
-  if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
-    return;
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   if(n == 0 && !p.clear_flags)
     return;
-  const uint32_t off = p.tile_offset[tile];
+  // More appends than the tile's list holds: the list is incomplete. The warp then finds the tile's
+  // triangles by scanning the packed tile ranges of the whole draw, which also yields them in submission order.
+  const bool scanList = n > p.list_cap;
+  const uint32_t *list = p.list + (size_t)blockIdx.x * p.list_cap;
+  uint32_t scanPos = 0, scanQueued = 0;
   const Vb200RasterState &rs = p.rs;
   const uint32_t tx = tile % rs.tiles_x, ty = tile / rs.tiles_x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -312,9 +319,39 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   {
     // ---- 1. load + setup 32 triangles, keep those whose bbox touches this warp's region
     bool touches = false;
-    if(base + lane < n)
+    bool have = base + lane < n;
+    uint32_t t = 0;
+    if(!scanList)
     {
-      const uint32_t t = p.list[off + base + lane];
+      if(have)
+        t = list[base + lane];
+    }
+    else
+    {
+      uint32_t *ids = s_wids[warp];
+      while(scanQueued < 32u && scanPos < p.num_tris)
+      {
+        const uint32_t idx = scanPos + (uint32_t)lane;
+        const bool match = idx < p.num_tris && vb200_tile_in_range(__ldg(p.tri_tiles + idx), tx, ty);
+        const uint32_t mm = __ballot_sync(0xffffffffu, match);
+        if(match)
+          ids[scanQueued + __popc(mm & below)] = idx;
+        scanQueued += __popc(mm);
+        scanPos += 32u;
+      }
+      __syncwarp();
+      have = (uint32_t)lane < scanQueued;
+      t = have ? ids[lane] : 0u;
+      const uint32_t rest = scanQueued - min(scanQueued, 32u);    // < 32: they move to the front
+      const uint32_t mv = (uint32_t)lane < rest ? ids[32 + lane] : 0u;
+      __syncwarp();
+      if((uint32_t)lane < rest)
+        ids[lane] = mv;
+      __syncwarp();
+      scanQueued = rest;
+    }
+    if(have)
+    {
       const Vb200TriSetup su = vb200_load_setup(p, t);
       // MinMax + clamp (rasterizer.cpp:428-435); pixels iterate the half-open box [min, max)
       const int minx = max(0, min(su.x0, min(su.x1, su.x2))), miny = max(0, min(su.y0, min(su.y1, su.y2)));
@@ -474,21 +511,20 @@ __device__ __forceinline__ unsigned long long vb200_atoms_cas64(uint32_t a, unsi
   return old;
 }
 
-// Per-triangle raster record staged in shared memory (64 B, one per lane of the warp that loaded it).
-// A candidate pixel is addressed by its index li inside the triangle's tile-clipped bbox (row-major,
-// width w): yq = li / w. With everything re-based to that index,
-//   b1 = A1*li + D1*yq + E1,  b2 = A2*li + D2*yq + E2,  b0 = |area2| - (b1 + b2)
-//   tile pixel index = base + li + yq*(32 - w)
-// so phase A never reconstructs x or y. (Same int32 ring arithmetic as rasterizer.cpp:303-309.)
-struct TriCoef
-{
-  int A1, D1, E1, A2;
-  int D2, E2, area, base;          // base = (y0 - tileY0)*32 + (x0 - tileX0)
-  float invarea, d0, d1, d2;
-  uint32_t id, excl, skip, magic;  // key id (below); first slot in the pixel stream; 32 - w; floor(2^16/w) + 1
-  float invw0, invw1, invw2;       // what only the shading pass needs: perspective weights ...
-  uint32_t s0, s1, s2, pad;        // ... and the corners' post-VS record slots
-};
+// Records of one round (up to 256 triangles of the tile's list, one per thread), staged in shared memory
+// as a structure of 16-byte arrays: a gather of one field group by the 8 lanes of a quarter warp touches
+// 8 different 16-byte bank groups unless two of them ask for records a multiple of 8 apart (the 96-byte
+// array-of-structures records this replaces collided four ways: 9.5 M bank conflicts per C3 frame).
+//   e1 = {A1, B1, C1, A2}         b1 = A1*x + B1*y + C1      x, y: pixel inside the tile (0..31)
+//   e2 = {B2, C2, |area2|, box}   b2 = A2*x + B2*y + C2,  b0 = |area2| - (b1 + b2)
+//                                 box = x0 | y0 << 8 | w << 16 | h << 24: the tile-clipped bbox
+//   z  = {1/|area2|, d0, d1, d2}
+//   pw = {invw0, invw1, invw2, s0}
+//   sv = {s1, s2}
+// all indexed by the thread that set the triangle up, and for the streamed triangles, indexed by their rank
+// in the stream:
+//   st = {first stream slot, magic | record slot << 16, key id, box}
+// (Same int32 ring arithmetic as barycentric(), rasterizer.cpp:303-309, with barymul folded in.)
 // key id = triangle index + 1, or ((triangle index + 1) << 8 | record slot) when Vb200RasterState::slot_keys
 // is set: ids stay ordered by triangle index, and for a tile whose whole list fits one round (<= 256
 // triangles, the common case) phase B reads the winner's record from shared memory instead of gathering
@@ -506,13 +542,63 @@ __device__ __forceinline__ unsigned long long vb200_existing_key(float e)
 {
   if(MODE == VB200_RES_LAST_WINS)
     return ~0ull;
+  // low word when nothing has won the pixel: 0 (.._FIRST: ids are >= 1) or ~0 (.._LAST: ~id is < ~0)
+  const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? 0u : 0xffffffffu;
   if(e != e)
-    return 0ull;    // NaN in the depth buffer: every comparison fails, nothing can replace it
+    return (unsigned long long)low;    // NaN in the depth buffer: every comparison fails. High word 0 lies
+                                       // below every fragment's depth key, so nothing replaces it, and the
+                                       // low word still reads "no winner" in phase B
   uint32_t k = vb200_depth_key(e);
   if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
     k = ~k;
-  const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? 0u : 0xffffffffu;
   return ((unsigned long long)k << 32) | low;
+}
+
+// Visibility key of one covered fragment (barycentric numerators b0..b2). False: it cannot win (NaN depth,
+// or it fails the test against the depth the pass does not modify).
+template <int MODE>
+__device__ __forceinline__ bool vb200_fragment_key(int b0, int b1, int b2, float invarea, float d0, float d1, float d2,
+                                                   uint32_t id, bool depthTest, uint32_t depthOp, const float *s_depth,
+                                                   int idx, unsigned long long &key)
+{
+  if(MODE == VB200_RES_LAST_WINS && !depthTest)
+  {
+    key = (unsigned long long)(~id);
+    return true;
+  }
+  // rasterizer.cpp:552-558
+  const float n0 = __fmul_rn((float)b0, invarea);
+  const float n1 = __fmul_rn((float)b1, invarea);
+  const float n2 = __fmul_rn((float)b2, invarea);
+  const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));
+  if(MODE == VB200_RES_LAST_WINS)
+  {
+    key = (unsigned long long)(~id);
+    return vb200_depth_pass(depthOp, pixdepth, s_depth[idx]);
+  }
+  if(pixdepth != pixdepth)
+    return false;    // NaN never passes an ordered comparison
+  uint32_t dk = vb200_depth_key(pixdepth);
+  if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
+    dk = ~dk;
+  const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? id : ~id;
+  key = ((unsigned long long)dk << 32) | low;
+  return true;
+}
+
+// 64-bit min in shared memory has no native atomic: CAS until the slot holds a key <= ours (the common
+// case is no attempt at all, or one that succeeds). `seen` is a plain read that may race with other
+// warps' CAS on purpose (compute-sanitizer racecheck reports it): keys only ever decrease, so a stale
+// value can only cause a CAS attempt that fails and refreshes it.
+__device__ __forceinline__ void vb200_vis_min(uint32_t aSlot, unsigned long long seen, unsigned long long key)
+{
+  while(key < seen)
+  {
+    const unsigned long long prev = vb200_atoms_cas64(aSlot, seen, key);
+    if(prev == seen)
+      break;
+    seen = prev;
+  }
 }
 
 template <int MODE>
@@ -520,16 +606,16 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 {
   __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
   __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
-  __shared__ int4 s_coef[256][6];     // TriCoef records of the current round, one per thread
-  __shared__ __align__(16) uint32_t s_start[260];   // first stream slot of each record; [count] = stream length
+  __shared__ int4 s_e1[256], s_e2[256], s_z[256], s_pw[256], s_st[256];    // records of the current round
+  __shared__ int2 s_sv[256];
+  __shared__ __align__(16) uint32_t s_start[260];   // first stream slot of each streamed record; rest = stream length
   __shared__ uint32_t s_wsum[8];
+  __shared__ uint32_t s_ids[512];    // id queue of the fallback scan (overflowed tile list)
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
   const uint32_t tile = blockIdx.x * p.rs.owner_world + p.rs.owner_rank;
   if(tile >= p.rs.tiles_x * p.rs.tiles_y)
-    return;
-  if(*p.total > p.list_capacity)    // speculative launch whose list did not fit: the host reruns it
     return;
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
@@ -558,7 +644,11 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     }
     return;
   }
-  const uint32_t off = p.tile_offset[tile];
+  // More appends than the tile's list holds: the list is incomplete. The CTA then finds the tile's
+  // triangles by scanning the packed tile ranges of the whole draw (exact; needs no host round trip).
+  const bool scanList = n > p.list_cap;
+  const uint32_t *list = p.list + (size_t)blockIdx.x * p.list_cap;
+  uint32_t scanPos = 0, scanQueued = 0;
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
 
@@ -578,47 +668,104 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       s_depth[ly * VB200_TILE + lane] = e;
   }
 
-  // ---- phase A: coverage + visibility.
-  // Up to 256 triangles of the list per round, one per thread. Their tile-clipped bboxes are laid end
-  // to end into ONE stream of candidate pixels (block-wide exclusive prefix sum of the pixel counts),
-  // which is cut into 32-pixel steps; warp w takes the w-th eighth of the steps, so every warp does the
-  // same amount of work whatever the triangle sizes are and all 32 lanes test a pixel every step.
-  // Every listed triangle has a non-empty clipped bbox (the binning walked exactly these pixel ranges).
+  // ---- phase A: coverage + visibility, up to 256 triangles of the list per round, one per thread.
+  //  * A triangle whose tile-clipped bbox is at most 8x8 pixels (every triangle of a dense mesh) stays with
+  //    its thread: the thread walks the bbox rows with incremental edge functions into a 64-bit coverage
+  //    mask (five instructions per candidate pixel, no cross-lane traffic), then visits only the covered
+  //    pixels: depth, key, merge.
+  //  * Larger ones are streamed: their bboxes are laid end to end into ONE stream of candidate pixels
+  //    (block-wide exclusive prefix sum of the pixel counts), cut into 32-pixel steps; warp w takes the
+  //    w-th eighth of the steps, so every warp does the same amount of work whatever the sizes are.
+  // Winners are resolved with a 64-bit (depth key, triangle id) min in shared memory: no global atomics,
+  // and the lists need no sorting.
+  // Every listed triangle has a non-empty clipped bbox (the binning walked exactly these tile ranges).
+  const uint32_t aVis = vb200_smem_addr(vis);
   uint32_t covered = 0, shaded = 0;
   for(uint32_t base = 0; base < n; base += 256u)
   {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t m = min(256u, n - base);    // records in this round
-    uint32_t cnt = 0;
-    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0, r2 = r0, r3 = make_int4(0, 0, 0, 65537), r4 = r0, r5 = r0;
-    if(i < n)
+    uint32_t m = min(256u, n - base);    // records in this round
+    uint32_t t = 0;
+    if(!scanList)
     {
-      const uint32_t t = p.list[off + i];
+      if(threadIdx.x < m)
+        t = list[base + threadIdx.x];
+    }
+    else
+    {
+      // fallback: gather the next m ids, in order, from the packed tile ranges
+      while(scanQueued < m && scanPos < p.num_tris)
+      {
+        const uint32_t idx = scanPos + threadIdx.x;
+        const bool match = idx < p.num_tris && vb200_tile_in_range(__ldg(p.tri_tiles + idx), tx, ty);
+        const uint32_t mm = __ballot_sync(0xffffffffu, match);
+        __syncthreads();    // the previous pass is done with s_wsum / s_ids
+        if(lane == 0)
+          s_wsum[warp] = __popc(mm);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for(int q = 0; q < 8; q++)
+        {
+          const uint32_t v = s_wsum[q];
+          before += (q < warp) ? v : 0u;
+          total += v;
+        }
+        if(match)
+          s_ids[scanQueued + before + __popc(mm & ((1u << lane) - 1u))] = idx;
+        scanQueued += total;
+        scanPos += 256u;
+      }
+      __syncthreads();
+      m = min(m, scanQueued);
+      if(threadIdx.x < m)
+        t = s_ids[threadIdx.x];
+      const uint32_t rest = scanQueued - m;    // < 256: they move to the front of the queue
+      const uint32_t mv = threadIdx.x < rest ? s_ids[m + threadIdx.x] : 0u;
+      __syncthreads();
+      if(threadIdx.x < rest)
+        s_ids[threadIdx.x] = mv;
+      scanQueued = rest;
+    }
+    const bool have = threadIdx.x < m;
+    int A1 = 0, B1 = 0, C1 = 0, A2 = 0, B2 = 0, C2 = 0, area = 0;
+    int box = 0 | (0 << 8) | (1 << 16) | (1 << 24);
+    float invarea = 0.0f, d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    int4 rpw = make_int4(0, 0, 0, 0);
+    int2 rsv = make_int2(0, 0);
+    bool big = false;
+    if(have)
+    {
       const Vb200TriSetup su = vb200_load_setup(p, t);
       const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
       const int area2 = ABx * ACy - ABy * ACx;
       const int sgn = area2 > 0 ? 1 : -1;
+      // MinMax + clamp (rasterizer.cpp:428-435), clipped to the tile; pixels iterate the half-open box
       const int x0 = max(max(0, min(su.x0, min(su.x1, su.x2))), tileX0);
       const int y0 = max(max(0, min(su.y0, min(su.y1, su.y2))), tileY0);
       const int x1 = min(min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2))), tileX0 + VB200_TILE);
       const int y1 = min(min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2))), tileY0 + VB200_TILE);
-      const int w = max(x1 - x0, 1), h = max(y1 - y0, 1);
-      cnt = (uint32_t)(w * h);
-      const int A1 = sgn * ACy, B1 = -sgn * ACx, C1 = sgn * (ACx * su.y0 - ACy * su.x0);
-      const int A2 = -sgn * ABy, B2 = sgn * ABx, C2 = sgn * (ABy * su.x0 - ABx * su.y0);
-      r0 = make_int4(A1, B1 - A1 * w, C1 + A1 * x0 + B1 * y0, A2);
-      r1 = make_int4(B2 - A2 * w, C2 + A2 * x0 + B2 * y0, sgn * area2, (y0 - tileY0) * VB200_TILE + (x0 - tileX0));
-      r2 = make_int4(__float_as_int(su.invarea), __float_as_int(su.d0), __float_as_int(su.d1), __float_as_int(su.d2));
-      // floor(li / w) == (li * magic) >> 16 for li < 1024, w <= 32 with magic = floor(65536 / w) + 1
-      // (65536/w is either an integer or at least 1/32 away from one: far more than the 2-ulp error
-      // of the fast division)
-      const uint32_t keyId = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
-      r3 = make_int4((int)keyId, 0, VB200_TILE - w, (int)(__float2uint_rz(__fdividef(65536.0f, (float)w)) + 1u));
-      r4 = make_int4(__float_as_int(su.invw0), __float_as_int(su.invw1), __float_as_int(su.invw2), (int)su.s0);
-      r5 = make_int4((int)su.s1, (int)su.s2, 0, 0);
+      const int bw = max(x1 - x0, 1), bh = max(y1 - y0, 1);
+      box = (x0 - tileX0) | ((y0 - tileY0) << 8) | (bw << 16) | (bh << 24);
+      // barycentric() (rasterizer.cpp:303-309) with barymul = sign(area2) folded in, re-based to the tile
+      A1 = sgn * ACy;
+      B1 = -sgn * ACx;
+      C1 = sgn * (ACx * su.y0 - ACy * su.x0) + A1 * tileX0 + B1 * tileY0;
+      A2 = -sgn * ABy;
+      B2 = sgn * ABx;
+      C2 = sgn * (ABy * su.x0 - ABx * su.y0) + A2 * tileX0 + B2 * tileY0;
+      area = sgn * area2;
+      invarea = su.invarea;
+      d0 = su.d0;
+      d1 = su.d1;
+      d2 = su.d2;
+      rpw = make_int4(__float_as_int(su.invw0), __float_as_int(su.invw1), __float_as_int(su.invw2), (int)su.s0);
+      rsv = make_int2((int)su.s1, (int)su.s2);
+      big = bw > 8 || bh > 8;
     }
-    // block-wide exclusive scan of cnt
-    uint32_t incl = cnt;
+    const uint32_t keyId = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
+    // block-wide exclusive scan of (streamed triangle ? 1 : 0) << 20 | candidate pixels (<= 2^18 per round)
+    const uint32_t mine = big ? ((1u << 20) | (uint32_t)(((box >> 16) & 0xff) * ((uint32_t)box >> 24))) : 0u;
+    uint32_t incl = mine;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1)
     {
@@ -626,124 +773,169 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       if(lane >= o)
         incl += v;
     }
-    __syncthreads();    // previous round (or the init) is done with s_coef / s_start / s_wsum
+    __syncthreads();    // previous round (or the init) is done with the records / s_start / s_wsum
     if(lane == 31)
       s_wsum[warp] = incl;
+    if(have)
+    {
+      s_e1[threadIdx.x] = make_int4(A1, B1, C1, A2);
+      s_e2[threadIdx.x] = make_int4(B2, C2, area, box);
+      s_z[threadIdx.x] = make_int4(__float_as_int(invarea), __float_as_int(d0), __float_as_int(d1), __float_as_int(d2));
+      s_pw[threadIdx.x] = rpw;
+      s_sv[threadIdx.x] = rsv;
+    }
     __syncthreads();
-    uint32_t wbase = 0, total = 0;
+    uint32_t wbase = 0, wtotal = 0;
 #pragma unroll
     for(int q = 0; q < 8; q++)
     {
       const uint32_t v = s_wsum[q];
       wbase += (q < warp) ? v : 0u;
-      total += v;
+      wtotal += v;
     }
-    const uint32_t myStart = wbase + incl - cnt;
-    r3.y = (int)myStart;
-    s_coef[threadIdx.x][0] = r0;
-    s_coef[threadIdx.x][1] = r1;
-    s_coef[threadIdx.x][2] = r2;
-    s_coef[threadIdx.x][3] = r3;
-    s_coef[threadIdx.x][4] = r4;
-    s_coef[threadIdx.x][5] = r5;
-    s_start[threadIdx.x] = (i < n) ? myStart : total;
-    if(threadIdx.x == 0)
-      s_start[256] = total;
-    __syncthreads();
-
-    const uint32_t steps = (total + 31u) >> 5;
-    const uint32_t firstStep = (steps * (uint32_t)warp) >> 3, lastStep = (steps * (uint32_t)(warp + 1)) >> 3;
-    if(firstStep < lastStep)
+    const uint32_t nBig = wtotal >> 20, total = wtotal & 0xfffffu;
+    if(nBig)
     {
-      // record that owns stream slot firstStep*32: the last record whose start is <= that slot. Starts are
-      // increasing and entries past the round's records hold `total` (> k), so it is (number of entries
-      // <= k) - 1: every lane counts eight entries (independent loads) and one warp reduction adds them up
-      // — instead of a dependent eight-step binary search.
-      uint32_t owner0;
+      // s_start[r] = first stream slot of the r-th streamed record; entries from nBig on hold the stream length
+      if(big)
       {
-        const uint32_t k = firstStep << 5;
-        const uint4 a = *(const uint4 *)(s_start + lane * 8), b4 = *(const uint4 *)(s_start + lane * 8 + 4);
-        const uint32_t mine = (a.x <= k) + (a.y <= k) + (a.z <= k) + (a.w <= k) + (b4.x <= k) + (b4.y <= k) +
-                              (b4.z <= k) + (b4.w <= k);
-        owner0 = __reduce_add_sync(0xffffffffu, mine) - 1u;
+        const uint32_t excl = wbase + incl - mine;
+        const uint32_t rank = excl >> 20, myStart = excl & 0xfffffu, bw = ((uint32_t)box >> 16) & 0xffu;
+        s_start[rank] = myStart;
+        // floor(li / w) == (li * magic) >> 15 for li < 1024, w <= 32 with magic = ceil(32768 / w): the
+        // product overshoots li / w by less than 1024 / 32768 = 1/32 <= 1/w, and is exact for powers of two
+        s_st[rank] = make_int4((int)myStart, (int)(((32768u + bw - 1u) / bw) | (threadIdx.x << 16)), (int)keyId, box);
       }
-      // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
-      // work of step s, so it is issued first each iteration: its shared-memory round trip and the
-      // warp reductions overlap the coverage / depth arithmetic instead of heading the next iteration.
-      const uint32_t aStart = vb200_smem_addr(s_start), aCoef = vb200_smem_addr(s_coef), aVis = vb200_smem_addr(vis);
-      uint32_t starts, nextOwner0;
+      if(threadIdx.x >= nBig)
+        s_start[threadIdx.x] = total;
+      if(threadIdx.x == 0)
+        s_start[256] = total;
+      __syncthreads();
+
+      const uint32_t steps = (total + 31u) >> 5;
+      const uint32_t firstStep = (steps * (uint32_t)warp) >> 3, lastStep = (steps * (uint32_t)(warp + 1)) >> 3;
+      if(firstStep < lastStep)
       {
-        const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (firstStep << 5);
-        starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-        nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
-      }
-      for(uint32_t step = firstStep; step < lastStep; step++)
-      {
-        const uint32_t k = step << 5;
-        const uint32_t g = k + lane;
-        // lane l looked at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
-        const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), 255u);
-        owner0 = nextOwner0;
+        // record that owns stream slot firstStep*32: the last record whose start is <= that slot. Starts are
+        // strictly increasing (every streamed record is non-empty) and entries past them hold `total` (> k),
+        // so it is (number of entries <= k) - 1: every lane counts eight entries (independent loads) and one
+        // warp reduction adds them up — instead of a dependent eight-step binary search.
+        uint32_t owner0;
         {
-          const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (k + 32u);
+          const uint32_t k = firstStep << 5;
+          const uint4 a = *(const uint4 *)(s_start + lane * 8), b4 = *(const uint4 *)(s_start + lane * 8 + 4);
+          const uint32_t cnt = (a.x <= k) + (a.y <= k) + (a.z <= k) + (a.w <= k) + (b4.x <= k) + (b4.y <= k) +
+                               (b4.z <= k) + (b4.w <= k);
+          owner0 = __reduce_add_sync(0xffffffffu, cnt) - 1u;
+        }
+        // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
+        // work of step s, so it is issued first each iteration: its shared-memory round trip and the
+        // warp reductions overlap the coverage / depth arithmetic instead of heading the next iteration.
+        const uint32_t aStart = vb200_smem_addr(s_start), aE1 = vb200_smem_addr(s_e1), aE2 = vb200_smem_addr(s_e2),
+                       aZ = vb200_smem_addr(s_z), aSt = vb200_smem_addr(s_st);
+        uint32_t starts, nextOwner0;
+        {
+          const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (firstStep << 5);
           starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
           nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
         }
-        const bool valid = g < total;
-        const uint32_t aRec = aCoef + owner * (uint32_t)sizeof(s_coef[0]);
-        const int4 c0 = vb200_lds128(aRec), c1 = vb200_lds128(aRec + 16u), c3 = vb200_lds128(aRec + 48u);
-        const int li = valid ? (int)(g - (uint32_t)c3.y) : 0;
-        const int yq = (int)(((uint32_t)li * (uint32_t)c3.w) >> 16);
-        const int b1 = c0.x * li + c0.y * yq + c0.z;
-        const int b2 = c0.w * li + c1.x * yq + c1.y;
-        const int b0 = c1.z - (b1 + b2);
-        const int idx = c1.w + li + yq * c3.z;
-        // the slot's current key is fetched before the depth arithmetic that decides whether it is needed.
-        // (A plain read racing with other warps' CAS on purpose — compute-sanitizer racecheck reports it:
-        // keys only ever decrease, so a stale value can only cause a CAS attempt that fails and refreshes it.)
-        const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
-        unsigned long long seen = vb200_lds64(aSlot);
-        if(!valid || (b0 | b1 | b2) < 0)
-          continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
-        covered++;
-        const uint32_t id = (uint32_t)c3.x;
-        unsigned long long key;
-        if(MODE == VB200_RES_LAST_WINS && !depthTest)
-          key = (unsigned long long)(~id);
-        else
+        for(uint32_t step = firstStep; step < lastStep; step++)
         {
-          const int4 c2 = vb200_lds128(aRec + 32u);
-          const float invarea = __int_as_float(c2.x);
-          const float n0 = __fmul_rn((float)b0, invarea);
-          const float n1 = __fmul_rn((float)b1, invarea);
-          const float n2 = __fmul_rn((float)b2, invarea);
-          const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, __int_as_float(c2.y)), __fmul_rn(n1, __int_as_float(c2.z))),
-                                           __fmul_rn(n2, __int_as_float(c2.w)));
-          if(MODE == VB200_RES_LAST_WINS)
+          const uint32_t k = step << 5;
+          const uint32_t g = k + lane;
+          // lane l looked at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
+          const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), 255u);
+          owner0 = nextOwner0;
           {
-            if(!vb200_depth_pass(rs.depth_op, pixdepth, s_depth[idx]))
-              continue;
-            key = (unsigned long long)(~id);
+            const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (k + 32u);
+            starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+            nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
           }
-          else
+          const bool valid = g < total;
+          const int4 c3 = vb200_lds128(aSt + owner * 16u);
+          const uint32_t o16 = ((uint32_t)c3.y >> 16) * 16u;    // the record's slot (the thread that set it up)
+          const int4 c0 = vb200_lds128(aE1 + o16), c1 = vb200_lds128(aE2 + o16);
+          // candidate li of the record's bbox (row-major, width w): row yq = li / w, column li - yq*w
+          const int li = valid ? (int)(g - (uint32_t)c3.x) : 0;
+          const int w = (c3.w >> 16) & 0xff;
+          const int yq = (int)(((uint32_t)li * ((uint32_t)c3.y & 0xffffu)) >> 15);
+          const int x = (c3.w & 0xff) + li - yq * w, y = ((c3.w >> 8) & 0xff) + yq;
+          const int b1 = c0.x * x + c0.y * y + c0.z;
+          const int b2 = c0.w * x + c1.x * y + c1.y;
+          const int b0 = c1.z - (b1 + b2);
+          // (lanes past the end of the stream may look at a record slot nobody wrote: keep their index inside the tile)
+          const int idx = (y * VB200_TILE + x) & (VB200_TILE * VB200_TILE - 1);
+          // the slot's current key is fetched before the depth arithmetic that decides whether it is needed
+          const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
+          const unsigned long long seen = vb200_lds64(aSlot);
+          if(!valid || (b0 | b1 | b2) < 0)
+            continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
+          covered++;
+          float ia = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+          if(MODE != VB200_RES_LAST_WINS || depthTest)
           {
-            if(pixdepth != pixdepth)
-              continue;    // NaN never passes an ordered comparison
-            uint32_t dk = vb200_depth_key(pixdepth);
-            if(MODE == VB200_RES_MAX_FIRST || MODE == VB200_RES_MAX_LAST)
-              dk = ~dk;
-            const uint32_t low = (MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST) ? id : ~id;
-            key = ((unsigned long long)dk << 32) | low;
+            const int4 c2 = vb200_lds128(aZ + o16);
+            ia = __int_as_float(c2.x);
+            e0 = __int_as_float(c2.y);
+            e1 = __int_as_float(c2.z);
+            e2 = __int_as_float(c2.w);
           }
+          unsigned long long key;
+          if(vb200_fragment_key<MODE>(b0, b1, b2, ia, e0, e1, e2, (uint32_t)c3.z, depthTest, rs.depth_op, s_depth, idx, key))
+            vb200_vis_min(aSlot, seen, key);
         }
-        // 64-bit min in shared memory has no native atomic: CAS until the slot holds a key <= ours
-        // (the common case is no attempt at all, or one that succeeds)
-        while(key < seen)
+      }
+    }
+    if(have && !big)
+    {
+      // ---- per-thread path. Coverage mask of the (at most 8x8) clipped bbox: bit 8*y + x, rows 0..3 in
+      // mlo, rows 4..7 in mhi. A row is walked right to left so that the sign bit pushed in at step i ends
+      // up at position 7 - i = its column; columns past the bbox are masked off afterwards.
+      const int A0 = -(A1 + A2), B0 = -(B1 + B2);
+      const int bx0 = box & 0xff, by0 = (box >> 8) & 0xff, bh = (int)((uint32_t)box >> 24);
+      int r1 = A1 * (bx0 + 7) + B1 * by0 + C1, r2 = A2 * (bx0 + 7) + B2 * by0 + C2, r0 = area - (r1 + r2);
+      const uint32_t colmask = (1u << ((box >> 16) & 0xff)) - 1u;
+      uint32_t mlo = 0, mhi = 0;
+      for(int y = 0; y < bh; y++)
+      {
+        int e0 = r0, e1 = r1, e2 = r2;
+        uint32_t row = 0;
+#pragma unroll
+        for(int x = 0; x < 8; x++)
         {
-          const unsigned long long prev = vb200_atoms_cas64(aSlot, seen, key);
-          if(prev == seen)
-            break;
-          seen = prev;
+          row = __funnelshift_l((uint32_t)(e0 | e1 | e2), row, 1);    // row << 1 | (some edge function < 0)
+          e0 -= A0;
+          e1 -= A1;
+          e2 -= A2;
+        }
+        row = ~row & colmask;    // covered iff all three >= 0 (rasterizer.cpp:549)
+        const uint32_t sh = 8u * ((uint32_t)y & 3u);
+        if(y < 4)
+          mlo |= row << sh;
+        else
+          mhi |= row << sh;
+        r0 += B0;
+        r1 += B1;
+        r2 += B2;
+      }
+      // ---- the covered pixels only
+#pragma unroll 1
+      for(int half = 0; half < 2; half++)
+      {
+        uint32_t mask = half ? mhi : mlo;
+        while(mask)
+        {
+          const int bit = __ffs((int)mask) - 1;
+          mask &= mask - 1u;
+          const int x = bx0 + (bit & 7), y = by0 + (bit >> 3) + 4 * half;
+          const int b1 = A1 * x + B1 * y + C1, b2 = A2 * x + B2 * y + C2, b0 = area - (b1 + b2);
+          const int idx = y * VB200_TILE + x;
+          covered++;
+          unsigned long long key;
+          if(!vb200_fragment_key<MODE>(b0, b1, b2, invarea, d0, d1, d2, keyId, depthTest, rs.depth_op, s_depth, idx, key))
+            continue;
+          const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
+          vb200_vis_min(aSlot, vb200_lds64(aSlot), key);
         }
       }
     }
@@ -798,13 +990,11 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     uint32_t s0, s1, s2;
     if(recordsInSmem)
     {
-      const uint32_t slot = id & 255u;
-      const int4 c0 = s_coef[slot][0], c1 = s_coef[slot][1], c2 = s_coef[slot][2], c3 = s_coef[slot][3];
-      const int4 c4 = s_coef[slot][4], c5 = s_coef[slot][5];
-      const int yq = ly - (c1.w >> 5), xr = lane - (c1.w & 31);
-      const int li = yq * (VB200_TILE - c3.z) + xr;
-      b1 = c0.x * li + c0.y * yq + c0.z;
-      b2 = c0.w * li + c1.x * yq + c1.y;
+      const uint32_t slot = id & 255u;    // the thread that set the winner up
+      const int4 c0 = s_e1[slot], c1 = s_e2[slot], c2 = s_z[slot], c4 = s_pw[slot];
+      const int2 c5 = s_sv[slot];
+      b1 = c0.x * lane + c0.y * ly + c0.z;
+      b2 = c0.w * lane + c1.x * ly + c1.y;
       b0 = c1.z - (b1 + b2);
       invarea = __int_as_float(c2.x); d0 = __int_as_float(c2.y); d1 = __int_as_float(c2.z); d2 = __int_as_float(c2.w);
       invw0 = __int_as_float(c4.x); invw1 = __int_as_float(c4.y); invw2 = __int_as_float(c4.z);
