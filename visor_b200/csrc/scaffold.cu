@@ -521,9 +521,7 @@ __device__ __forceinline__ unsigned long long vb200_atoms_cas64(uint32_t a, unsi
 //   z  = {1/|area2|, d0, d1, d2}
 //   pw = {invw0, invw1, invw2, s0}
 //   sv = {s1, s2}
-// all indexed by the thread that set the triangle up, and for the streamed triangles, indexed by their rank
-// in the stream:
-//   st = {first stream slot, magic | record slot << 16, key id, box}
+//   key = key id (below)
 // (Same int32 ring arithmetic as barycentric(), rasterizer.cpp:303-309, with barymul folded in.)
 // key id = triangle index + 1, or ((triangle index + 1) << 8 | record slot) when Vb200RasterState::slot_keys
 // is set: ids stay ordered by triangle index, and for a tile whose whole list fits one round (<= 256
@@ -606,9 +604,11 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 {
   __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
   __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
-  __shared__ int4 s_e1[256], s_e2[256], s_z[256], s_pw[256], s_st[256];    // records of the current round
+  __shared__ int4 s_e1[256], s_e2[256], s_z[256], s_pw[256];    // records of the current round
   __shared__ int2 s_sv[256];
-  __shared__ __align__(16) uint32_t s_start[260];   // first stream slot of each streamed record; rest = stream length
+  __shared__ uint32_t s_key[256];
+  __shared__ __align__(16) uint32_t s_start[260];   // first stream row of each record; past the records: stream length
+  __shared__ uint2 s_run[8][32];                    // per warp: the covered runs of the 32 rows of the current step
   __shared__ uint32_t s_wsum[8];
   __shared__ uint32_t s_ids[512];    // id queue of the fallback scan (overflowed tile list)
 
@@ -668,18 +668,23 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       s_depth[ly * VB200_TILE + lane] = e;
   }
 
-  // ---- phase A: coverage + visibility, up to 256 triangles of the list per round, one per thread.
-  //  * A triangle whose tile-clipped bbox is at most 8x8 pixels (every triangle of a dense mesh) stays with
-  //    its thread: the thread walks the bbox rows with incremental edge functions into a 64-bit coverage
-  //    mask (five instructions per candidate pixel, no cross-lane traffic), then visits only the covered
-  //    pixels: depth, key, merge.
-  //  * Larger ones are streamed: their bboxes are laid end to end into ONE stream of candidate pixels
-  //    (block-wide exclusive prefix sum of the pixel counts), cut into 32-pixel steps; warp w takes the
-  //    w-th eighth of the steps, so every warp does the same amount of work whatever the sizes are.
+  // ---- phase A: coverage + visibility, up to 256 triangles of the list per round.
+  //  1. one thread per triangle: load, edge setup, tile-clipped bbox -> record in shared memory;
+  //  2. the ROWS of all bboxes are laid end to end into one stream (block-wide exclusive prefix sum of the
+  //     bbox heights), cut into 32-row steps; warp w takes the w-th eighth of the steps, so every warp does
+  //     the same amount of work whatever the triangle sizes are. A lane owns one row of one triangle: it
+  //     walks the row with incremental edge functions into a coverage mask (five instructions per
+  //     candidate pixel, no cross-lane traffic). The covered pixels of a row are one run [xa, xa + L);
+  //  3. the warp lays the runs of its 32 rows end to end (warp prefix sum of L) and visits only COVERED
+  //     pixels, 32 at a time, every lane busy: depth, key, merge into the pixel's visibility slot.
   // Winners are resolved with a 64-bit (depth key, triangle id) min in shared memory: no global atomics,
   // and the lists need no sorting.
   // Every listed triangle has a non-empty clipped bbox (the binning walked exactly these tile ranges).
-  const uint32_t aVis = vb200_smem_addr(vis);
+  // shared-window addresses of the arrays the inner loops gather from, pinned in registers (left alone, ptxas
+  // re-derives each base inside the loops: S2R SR_CgaCtaId + LEA per access)
+  uint32_t aVis = vb200_smem_addr(vis), aStart = vb200_smem_addr(s_start), aE1 = vb200_smem_addr(s_e1),
+           aE2 = vb200_smem_addr(s_e2), aZ = vb200_smem_addr(s_z), aKey = vb200_smem_addr(s_key);
+  asm volatile("" : "+r"(aVis), "+r"(aStart), "+r"(aE1), "+r"(aE2), "+r"(aZ), "+r"(aKey));
   uint32_t covered = 0, shaded = 0;
   for(uint32_t base = 0; base < n; base += 256u)
   {
@@ -727,12 +732,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       scanQueued = rest;
     }
     const bool have = threadIdx.x < m;
-    int A1 = 0, B1 = 0, C1 = 0, A2 = 0, B2 = 0, C2 = 0, area = 0;
-    int box = 0 | (0 << 8) | (1 << 16) | (1 << 24);
-    float invarea = 0.0f, d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-    int4 rpw = make_int4(0, 0, 0, 0);
+    int4 re1 = make_int4(0, 0, 0, 0), re2 = make_int4(0, 0, 0, (1 << 16) | (1 << 24)), rz = re1, rpw = re1;
     int2 rsv = make_int2(0, 0);
-    bool big = false;
     if(have)
     {
       const Vb200TriSetup su = vb200_load_setup(p, t);
@@ -745,26 +746,17 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       const int x1 = min(min((int)rs.width - 1, max(su.x0, max(su.x1, su.x2))), tileX0 + VB200_TILE);
       const int y1 = min(min((int)rs.height - 1, max(su.y0, max(su.y1, su.y2))), tileY0 + VB200_TILE);
       const int bw = max(x1 - x0, 1), bh = max(y1 - y0, 1);
-      box = (x0 - tileX0) | ((y0 - tileY0) << 8) | (bw << 16) | (bh << 24);
       // barycentric() (rasterizer.cpp:303-309) with barymul = sign(area2) folded in, re-based to the tile
-      A1 = sgn * ACy;
-      B1 = -sgn * ACx;
-      C1 = sgn * (ACx * su.y0 - ACy * su.x0) + A1 * tileX0 + B1 * tileY0;
-      A2 = -sgn * ABy;
-      B2 = sgn * ABx;
-      C2 = sgn * (ABy * su.x0 - ABx * su.y0) + A2 * tileX0 + B2 * tileY0;
-      area = sgn * area2;
-      invarea = su.invarea;
-      d0 = su.d0;
-      d1 = su.d1;
-      d2 = su.d2;
+      const int A1 = sgn * ACy, B1 = -sgn * ACx, A2 = -sgn * ABy, B2 = sgn * ABx;
+      re1 = make_int4(A1, B1, sgn * (ACx * su.y0 - ACy * su.x0) + A1 * tileX0 + B1 * tileY0, A2);
+      re2 = make_int4(B2, sgn * (ABy * su.x0 - ABx * su.y0) + A2 * tileX0 + B2 * tileY0, sgn * area2,
+                      (x0 - tileX0) | ((y0 - tileY0) << 8) | (bw << 16) | (bh << 24));
+      rz = make_int4(__float_as_int(su.invarea), __float_as_int(su.d0), __float_as_int(su.d1), __float_as_int(su.d2));
       rpw = make_int4(__float_as_int(su.invw0), __float_as_int(su.invw1), __float_as_int(su.invw2), (int)su.s0);
       rsv = make_int2((int)su.s1, (int)su.s2);
-      big = bw > 8 || bh > 8;
     }
-    const uint32_t keyId = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
-    // block-wide exclusive scan of (streamed triangle ? 1 : 0) << 20 | candidate pixels (<= 2^18 per round)
-    const uint32_t mine = big ? ((1u << 20) | (uint32_t)(((box >> 16) & 0xff) * ((uint32_t)box >> 24))) : 0u;
+    // block-wide exclusive scan of the bbox heights (<= 32 rows each)
+    const uint32_t mine = have ? ((uint32_t)re2.w >> 24) : 0u;
     uint32_t incl = mine;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1)
@@ -776,166 +768,170 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     __syncthreads();    // previous round (or the init) is done with the records / s_start / s_wsum
     if(lane == 31)
       s_wsum[warp] = incl;
-    if(have)
-    {
-      s_e1[threadIdx.x] = make_int4(A1, B1, C1, A2);
-      s_e2[threadIdx.x] = make_int4(B2, C2, area, box);
-      s_z[threadIdx.x] = make_int4(__float_as_int(invarea), __float_as_int(d0), __float_as_int(d1), __float_as_int(d2));
-      s_pw[threadIdx.x] = rpw;
-      s_sv[threadIdx.x] = rsv;
-    }
+    s_e1[threadIdx.x] = re1;
+    s_e2[threadIdx.x] = re2;
+    s_z[threadIdx.x] = rz;
+    s_pw[threadIdx.x] = rpw;
+    s_sv[threadIdx.x] = rsv;
+    s_key[threadIdx.x] = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
     __syncthreads();
-    uint32_t wbase = 0, wtotal = 0;
+    uint32_t wbase = 0, total = 0;
 #pragma unroll
     for(int q = 0; q < 8; q++)
     {
       const uint32_t v = s_wsum[q];
       wbase += (q < warp) ? v : 0u;
-      wtotal += v;
+      total += v;
     }
-    const uint32_t nBig = wtotal >> 20, total = wtotal & 0xfffffu;
-    if(nBig)
-    {
-      // s_start[r] = first stream slot of the r-th streamed record; entries from nBig on hold the stream length
-      if(big)
-      {
-        const uint32_t excl = wbase + incl - mine;
-        const uint32_t rank = excl >> 20, myStart = excl & 0xfffffu, bw = ((uint32_t)box >> 16) & 0xffu;
-        s_start[rank] = myStart;
-        // floor(li / w) == (li * magic) >> 15 for li < 1024, w <= 32 with magic = ceil(32768 / w): the
-        // product overshoots li / w by less than 1024 / 32768 = 1/32 <= 1/w, and is exact for powers of two
-        s_st[rank] = make_int4((int)myStart, (int)(((32768u + bw - 1u) / bw) | (threadIdx.x << 16)), (int)keyId, box);
-      }
-      if(threadIdx.x >= nBig)
-        s_start[threadIdx.x] = total;
-      if(threadIdx.x == 0)
-        s_start[256] = total;
-      __syncthreads();
+    // s_start[r] = first row of record r in the stream; entries past the round's records hold its length
+    s_start[threadIdx.x] = have ? wbase + incl - mine : total;
+    if(threadIdx.x == 0)
+      s_start[256] = total;
+    __syncthreads();
 
-      const uint32_t steps = (total + 31u) >> 5;
-      const uint32_t firstStep = (steps * (uint32_t)warp) >> 3, lastStep = (steps * (uint32_t)(warp + 1)) >> 3;
-      if(firstStep < lastStep)
+    const uint32_t steps = (total + 31u) >> 5;
+    const uint32_t firstStep = (steps * (uint32_t)warp) >> 3, lastStep = (steps * (uint32_t)(warp + 1)) >> 3;
+    if(firstStep < lastStep)
+    {
+      // record that owns stream row firstStep*32: the last record whose start is <= that row. Starts are
+      // strictly increasing (every record has at least one row) and entries past them hold `total` (> k),
+      // so it is (number of entries <= k) - 1: every lane counts eight entries (independent loads) and one
+      // warp reduction adds them up — instead of a dependent eight-step binary search.
+      uint32_t owner0;
       {
-        // record that owns stream slot firstStep*32: the last record whose start is <= that slot. Starts are
-        // strictly increasing (every streamed record is non-empty) and entries past them hold `total` (> k),
-        // so it is (number of entries <= k) - 1: every lane counts eight entries (independent loads) and one
-        // warp reduction adds them up — instead of a dependent eight-step binary search.
-        uint32_t owner0;
+        const uint32_t k = firstStep << 5;
+        const uint4 a = *(const uint4 *)(s_start + lane * 8), b4 = *(const uint4 *)(s_start + lane * 8 + 4);
+        const uint32_t cnt = (a.x <= k) + (a.y <= k) + (a.z <= k) + (a.w <= k) + (b4.x <= k) + (b4.y <= k) +
+                             (b4.z <= k) + (b4.w <= k);
+        owner0 = __reduce_add_sync(0xffffffffu, cnt) - 1u;
+      }
+      // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
+      // work of step s, so it is issued first each iteration: its shared-memory round trip and the
+      // warp reductions overlap the coverage arithmetic instead of heading the next iteration.
+      uint32_t starts, nextOwner0;
+      {
+        const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (firstStep << 5);
+        starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+        nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
+      }
+      for(uint32_t step = firstStep; step < lastStep; step++)
+      {
+        const uint32_t k = step << 5;
+        const uint32_t g = k + lane;
+        // lane l looked at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
+        const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), 255u);
+        owner0 = nextOwner0;
         {
-          const uint32_t k = firstStep << 5;
-          const uint4 a = *(const uint4 *)(s_start + lane * 8), b4 = *(const uint4 *)(s_start + lane * 8 + 4);
-          const uint32_t cnt = (a.x <= k) + (a.y <= k) + (a.z <= k) + (a.w <= k) + (b4.x <= k) + (b4.y <= k) +
-                               (b4.z <= k) + (b4.w <= k);
-          owner0 = __reduce_add_sync(0xffffffffu, cnt) - 1u;
-        }
-        // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
-        // work of step s, so it is issued first each iteration: its shared-memory round trip and the
-        // warp reductions overlap the coverage / depth arithmetic instead of heading the next iteration.
-        const uint32_t aStart = vb200_smem_addr(s_start), aE1 = vb200_smem_addr(s_e1), aE2 = vb200_smem_addr(s_e2),
-                       aZ = vb200_smem_addr(s_z), aSt = vb200_smem_addr(s_st);
-        uint32_t starts, nextOwner0;
-        {
-          const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (firstStep << 5);
+          const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (k + 32u);
           starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
           nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
         }
-        for(uint32_t step = firstStep; step < lastStep; step++)
+        // ---- 2. this lane's row: row (g - start) of record `owner`
+        const bool valid = g < total;
+        const uint32_t o16 = owner * 16u;
+        const int4 c0 = vb200_lds128(aE1 + o16), c1 = vb200_lds128(aE2 + o16);
+        const uint32_t row = valid ? g - vb200_lds32(aStart + 4u * owner) : 0u;
+        const int bx0 = c1.w & 0xff, w = (c1.w >> 16) & 0xff;
+        const int y = ((c1.w >> 8) & 0xff) + (int)row;
+        // edge functions at the row's last column, walked right to left: the sign bit pushed in at step i
+        // ends up at bit (wmax - 1 - i); shifting the surplus of a narrower row out leaves column c at bit c
+        const int xr = bx0 + w - 1;
+        int e1 = c0.x * xr + c0.y * y + c0.z, e2 = c0.w * xr + c1.x * y + c1.y, e0 = c1.z - (e1 + e2);
+        const int A0 = -(c0.x + c0.w);
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, valid ? (uint32_t)w : 0u);
+        uint32_t outside = 0;
+#pragma unroll 4
+        for(uint32_t i = 0; i < wmax; i++)
         {
-          const uint32_t k = step << 5;
-          const uint32_t g = k + lane;
-          // lane l looked at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
-          const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), 255u);
-          owner0 = nextOwner0;
-          {
-            const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (k + 32u);
-            starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-            nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
-          }
-          const bool valid = g < total;
-          const int4 c3 = vb200_lds128(aSt + owner * 16u);
-          const uint32_t o16 = ((uint32_t)c3.y >> 16) * 16u;    // the record's slot (the thread that set it up)
-          const int4 c0 = vb200_lds128(aE1 + o16), c1 = vb200_lds128(aE2 + o16);
-          // candidate li of the record's bbox (row-major, width w): row yq = li / w, column li - yq*w
-          const int li = valid ? (int)(g - (uint32_t)c3.x) : 0;
-          const int w = (c3.w >> 16) & 0xff;
-          const int yq = (int)(((uint32_t)li * ((uint32_t)c3.y & 0xffffu)) >> 15);
-          const int x = (c3.w & 0xff) + li - yq * w, y = ((c3.w >> 8) & 0xff) + yq;
-          const int b1 = c0.x * x + c0.y * y + c0.z;
-          const int b2 = c0.w * x + c1.x * y + c1.y;
-          const int b0 = c1.z - (b1 + b2);
-          // (lanes past the end of the stream may look at a record slot nobody wrote: keep their index inside the tile)
-          const int idx = (y * VB200_TILE + x) & (VB200_TILE * VB200_TILE - 1);
+          outside = __funnelshift_l((uint32_t)(e0 | e1 | e2), outside, 1);    // << 1 | (some edge function < 0)
+          e0 -= A0;
+          e1 -= c0.x;
+          e2 -= c0.w;
+        }
+        // covered iff all three >= 0 (rasterizer.cpp:549), inside the row's w columns
+        const uint32_t cov = valid ? (~(outside >> (wmax - (uint32_t)w)) & (0xffffffffu >> (32 - w))) : 0u;
+        const uint32_t L = __popc(cov);
+        const int first = __ffs((int)cov) - 1;
+        covered += L;
+        // The three half-planes cut an interval out of the row, so the covered pixels are one run: first ..
+        // first + L - 1. (Only wrapped int32 arithmetic on out-of-domain geometry could break that; such a row
+        // is walked bit by bit instead, see below.)
+        const bool ragged = L != 0u && (cov >> first) != (0xffffffffu >> (32 - L));
+        // ---- 3. the runs of the warp's rows end to end; rows without coverage drop out
+        const uint32_t nzmask = __ballot_sync(0xffffffffu, L != 0u && !ragged);
+        uint32_t end = (L != 0u && !ragged) ? L : 0u;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1)
+        {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, end, o);
+          if(lane >= o)
+            end += v;
+        }
+        const uint32_t hits = __shfl_sync(0xffffffffu, end, 31);
+        const uint32_t nrec = __popc(nzmask);
+        __syncwarp();    // the previous step's lookups in s_run are done
+        if(L != 0u && !ragged)
+          s_run[warp][__popc(nzmask & ((1u << lane) - 1u))] =
+              make_uint2(end - L, owner | ((uint32_t)y << 8) | ((uint32_t)(bx0 + first) << 13));
+        __syncwarp();
+        // run r starts at hit s_run[r].x; lane r keeps that start for the owner lookups of the hit steps
+        const uint32_t runStart = (uint32_t)lane < nrec ? s_run[warp][lane].x : 0xffffffffu;
+        for(uint32_t hb = 0; hb < hits; hb += 32u)
+        {
+          // run that owns hit hb (the last one starting at or before it), then one more per run that begins
+          // inside (hb, hb + lane]
+          const uint32_t rel = runStart - hb;
+          const uint32_t ownerBase = __popc(__ballot_sync(0xffffffffu, runStart <= hb)) - 1u;
+          const uint32_t begins = __reduce_or_sync(0xffffffffu, (rel - 1u) < 31u ? (1u << rel) : 0u);
+          const uint32_t r = min(ownerBase + __popc(begins & (0xffffffffu >> (31 - lane))), 31u);
+          const uint2 run = s_run[warp][r];
+          const uint32_t h = hb + lane;
+          const uint32_t slot16 = (run.y & 255u) * 16u;
+          const int4 t0 = vb200_lds128(aE1 + slot16), t1 = vb200_lds128(aE2 + slot16);
+          const int py = (run.y >> 8) & 31, px = (int)((run.y >> 13) + (h - run.x)) & 31;
+          const int b1 = t0.x * px + t0.y * py + t0.z;
+          const int b2 = t0.w * px + t1.x * py + t1.y;
+          const int b0 = t1.z - (b1 + b2);
+          const int idx = py * VB200_TILE + px;
           // the slot's current key is fetched before the depth arithmetic that decides whether it is needed
           const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
           const unsigned long long seen = vb200_lds64(aSlot);
-          if(!valid || (b0 | b1 | b2) < 0)
-            continue;    // covered iff all three >= 0 (rasterizer.cpp:549)
-          covered++;
-          float ia = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
+          if(h >= hits)
+            continue;
+          float ia = 0.0f, z0 = 0.0f, z1 = 0.0f, z2 = 0.0f;
           if(MODE != VB200_RES_LAST_WINS || depthTest)
           {
-            const int4 c2 = vb200_lds128(aZ + o16);
+            const int4 c2 = vb200_lds128(aZ + slot16);
             ia = __int_as_float(c2.x);
-            e0 = __int_as_float(c2.y);
-            e1 = __int_as_float(c2.z);
-            e2 = __int_as_float(c2.w);
+            z0 = __int_as_float(c2.y);
+            z1 = __int_as_float(c2.z);
+            z2 = __int_as_float(c2.w);
           }
           unsigned long long key;
-          if(vb200_fragment_key<MODE>(b0, b1, b2, ia, e0, e1, e2, (uint32_t)c3.z, depthTest, rs.depth_op, s_depth, idx, key))
+          if(vb200_fragment_key<MODE>(b0, b1, b2, ia, z0, z1, z2, vb200_lds32(aKey + (slot16 >> 2)), depthTest,
+                                      rs.depth_op, s_depth, idx, key))
             vb200_vis_min(aSlot, seen, key);
         }
-      }
-    }
-    if(have && !big)
-    {
-      // ---- per-thread path. Coverage mask of the (at most 8x8) clipped bbox: bit 8*y + x, rows 0..3 in
-      // mlo, rows 4..7 in mhi. A row is walked right to left so that the sign bit pushed in at step i ends
-      // up at position 7 - i = its column; columns past the bbox are masked off afterwards.
-      const int A0 = -(A1 + A2), B0 = -(B1 + B2);
-      const int bx0 = box & 0xff, by0 = (box >> 8) & 0xff, bh = (int)((uint32_t)box >> 24);
-      int r1 = A1 * (bx0 + 7) + B1 * by0 + C1, r2 = A2 * (bx0 + 7) + B2 * by0 + C2, r0 = area - (r1 + r2);
-      const uint32_t colmask = (1u << ((box >> 16) & 0xff)) - 1u;
-      uint32_t mlo = 0, mhi = 0;
-      for(int y = 0; y < bh; y++)
-      {
-        int e0 = r0, e1 = r1, e2 = r2;
-        uint32_t row = 0;
-#pragma unroll
-        for(int x = 0; x < 8; x++)
+        if(__any_sync(0xffffffffu, ragged))
         {
-          row = __funnelshift_l((uint32_t)(e0 | e1 | e2), row, 1);    // row << 1 | (some edge function < 0)
-          e0 -= A0;
-          e1 -= A1;
-          e2 -= A2;
-        }
-        row = ~row & colmask;    // covered iff all three >= 0 (rasterizer.cpp:549)
-        const uint32_t sh = 8u * ((uint32_t)y & 3u);
-        if(y < 4)
-          mlo |= row << sh;
-        else
-          mhi |= row << sh;
-        r0 += B0;
-        r1 += B1;
-        r2 += B2;
-      }
-      // ---- the covered pixels only
-#pragma unroll 1
-      for(int half = 0; half < 2; half++)
-      {
-        uint32_t mask = half ? mhi : mlo;
-        while(mask)
-        {
-          const int bit = __ffs((int)mask) - 1;
-          mask &= mask - 1u;
-          const int x = bx0 + (bit & 7), y = by0 + (bit >> 3) + 4 * half;
-          const int b1 = A1 * x + B1 * y + C1, b2 = A2 * x + B2 * y + C2, b0 = area - (b1 + b2);
-          const int idx = y * VB200_TILE + x;
-          covered++;
-          unsigned long long key;
-          if(!vb200_fragment_key<MODE>(b0, b1, b2, invarea, d0, d1, d2, keyId, depthTest, rs.depth_op, s_depth, idx, key))
-            continue;
-          const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
-          vb200_vis_min(aSlot, vb200_lds64(aSlot), key);
+          // out-of-domain geometry only: this lane's row has holes; visit its set bits one by one
+          uint32_t bits = ragged ? cov : 0u;
+          const int4 c2 = vb200_lds128(aZ + o16);
+          const uint32_t id = vb200_lds32(aKey + 4u * owner);
+          while(bits)
+          {
+            const int px = bx0 + __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            const int b1 = c0.x * px + c0.y * y + c0.z, b2 = c0.w * px + c1.x * y + c1.y, b0 = c1.z - (b1 + b2);
+            const int idx = (y * VB200_TILE + px) & (VB200_TILE * VB200_TILE - 1);
+            unsigned long long key;
+            if(vb200_fragment_key<MODE>(b0, b1, b2, __int_as_float(c2.x), __int_as_float(c2.y), __int_as_float(c2.z),
+                                        __int_as_float(c2.w), id, depthTest, rs.depth_op, s_depth, idx, key))
+            {
+              const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
+              vb200_vis_min(aSlot, vb200_lds64(aSlot), key);
+            }
+          }
         }
       }
     }
