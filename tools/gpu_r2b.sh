@@ -1,13 +1,20 @@
 #!/bin/bash
 # round-2 iteration script (runs on the GPU box): tests, bench, ncu of the C3 tile kernel
+# usage: tools/gpu_r2b.sh <outdir name> [variant ...]   (variants: visor_b200/build/scaffold_<v>.ptx)
 set -u
 O=gpurun_out/${1:-r2b}
+shift
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1
 echo "pytest rc=$?" >> $O/pytest.log
 tail -4 $O/pytest.log
 for w in c3 c2 c4 c5; do
   timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_$w.json 2> $O/bench_$w.err
+done
+for v in "$@"; do
+  for w in c3 c5; do
+    VB200_SCAFFOLD_PTX=visor_b200/build/scaffold_$v.ptx timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_${w}_$v.json 2> $O/bench_${w}_$v.err
+  done
 done
 VB200_DUMP_CUBIN=$O/c3 timeout 900 ncu --set full --clock-control none --import-source on \
     -k regex:"resolve|k_setup|k_vertex" -s 30 -c 3 -o $O/prof_c3 -f \

@@ -111,8 +111,13 @@ __device__ __forceinline__ void vb200_store_color(const Vb200TileParams &p, size
   if(p.mc_color)
     asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p.mc_color + gi), "r"(v) : "memory");
   else
+  {
+    // (not unrolled: this function is inlined at every store of the tile kernels, and ptxas turned the
+    // seven-peer loop into ~170 instructions per site, a third of the resolve kernels' code)
+#pragma unroll 1
     for(uint32_t r = 0; r < p.num_peers; r++)
       p.peer_color[r][gi] = v;
+  }
 }
 
 __device__ __forceinline__ void vb200_count_fragments(Vb200DrawCounters *c, uint32_t covered, uint32_t shaded)

@@ -512,6 +512,21 @@ bool parseScaffold()
     return scaffold.ok;
   scaffold.parsed = true;
   std::string t(vb200_scaffold_ptx, (size_t)vb200_scaffold_ptx_size);
+  if(const char *path = getenv("VB200_SCAFFOLD_PTX"))
+  {
+    // tuning aid: kernel scaffolds from a PTX file (a variant of scaffold.cu built with other -D switches,
+    // `make -C visor_b200 variants`) instead of the embedded text
+    if(FILE *f = fopen(path, "rb"))
+    {
+      t.clear();
+      char buf[65536];
+      size_t got;
+      while((got = fread(buf, 1, sizeof(buf), f)) > 0)
+        t.append(buf, got);
+      fclose(f);
+      fprintf(stderr, "visor_b200: kernel scaffolds from %s (%zu bytes)\n", path, t.size());
+    }
+  }
   while(!t.empty() && t.back() == '\0')
     t.pop_back();
   stripExternFuncs(t);

@@ -19,6 +19,13 @@
 #include "kernels.h"
 #include "raster_common.cuh"
 
+// tuning switches (see `make variants`)
+#define VB200_PRAGMA(x) _Pragma(#x)
+#define VB200_UNROLL(n) VB200_PRAGMA(unroll n)
+#ifndef VB200_PB_UNROLL
+#define VB200_PB_UNROLL 4    // rows of the resolve kernels' shading pass in flight per thread
+#endif
+
 extern "C" __device__ float4 vb200_vs(const Vb200Env *env, unsigned vid, float4 *interps_out);
 extern "C" __device__ float4 vb200_fs(const Vb200Env *env, float b0, float b1, float b2, const float4 *v0,
                                       const float4 *v1, const float4 *v2);
@@ -608,7 +615,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __shared__ int2 s_sv[256];
   __shared__ uint32_t s_key[256];
   __shared__ __align__(16) uint32_t s_start[260];   // first stream row of each record; past the records: stream length
-  __shared__ uint2 s_run[8][32];                    // per warp: the covered runs of the 32 rows of the current step
+  __shared__ uint2 s_run[8][64];                    // per warp: the covered runs of the 64 rows of the current step
   __shared__ uint32_t s_wsum[8];
   __shared__ uint32_t s_ids[512];    // id queue of the fallback scan (overflowed tile list)
 
@@ -670,12 +677,12 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 
   // ---- phase A: coverage + visibility, up to 256 triangles of the list per round.
   //  1. one thread per triangle: load, edge setup, tile-clipped bbox -> record in shared memory;
-  //  2. the ROWS of all bboxes are laid end to end into one stream (block-wide exclusive prefix sum of the
-  //     bbox heights), cut into 32-row steps; warp w takes the w-th eighth of the steps, so every warp does
-  //     the same amount of work whatever the triangle sizes are. A lane owns one row of one triangle: it
-  //     walks the row with incremental edge functions into a coverage mask (five instructions per
+  //  2. the ROW PAIRS of all bboxes are laid end to end into one stream (block-wide exclusive prefix sum of
+  //     ceil(height / 2)), cut into 32-unit steps; warp w takes the w-th eighth of the steps, so every warp
+  //     does the same amount of work whatever the triangle sizes are. A lane owns two consecutive rows of one
+  //     triangle: it walks them with incremental edge functions into coverage masks (five instructions per
   //     candidate pixel, no cross-lane traffic). The covered pixels of a row are one run [xa, xa + L);
-  //  3. the warp lays the runs of its 32 rows end to end (warp prefix sum of L) and visits only COVERED
+  //  3. the warp lays the runs of its 64 rows end to end (warp prefix sum of L) and visits only COVERED
   //     pixels, 32 at a time, every lane busy: depth, key, merge into the pixel's visibility slot.
   // Winners are resolved with a 64-bit (depth key, triangle id) min in shared memory: no global atomics,
   // and the lists need no sorting.
@@ -755,8 +762,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       rpw = make_int4(__float_as_int(su.invw0), __float_as_int(su.invw1), __float_as_int(su.invw2), (int)su.s0);
       rsv = make_int2((int)su.s1, (int)su.s2);
     }
-    // block-wide exclusive scan of the bbox heights (<= 32 rows each)
-    const uint32_t mine = have ? ((uint32_t)re2.w >> 24) : 0u;
+    // block-wide exclusive scan of the stream units: a unit is a pair of consecutive bbox rows (<= 16 per record)
+    const uint32_t mine = have ? (((uint32_t)re2.w >> 24) + 1u) >> 1 : 0u;
     uint32_t incl = mine;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1)
@@ -826,40 +833,53 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
           starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
           nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
         }
-        // ---- 2. this lane's row: row (g - start) of record `owner`
+        // ---- 2. this lane's unit: rows 2u and 2u + 1 (if the bbox has it) of record `owner`, u = g - start
         const bool valid = g < total;
         const uint32_t o16 = owner * 16u;
         const int4 c0 = vb200_lds128(aE1 + o16), c1 = vb200_lds128(aE2 + o16);
-        const uint32_t row = valid ? g - vb200_lds32(aStart + 4u * owner) : 0u;
+        const uint32_t unit = valid ? g - vb200_lds32(aStart + 4u * owner) : 0u;
         const int bx0 = c1.w & 0xff, w = (c1.w >> 16) & 0xff;
-        const int y = ((c1.w >> 8) & 0xff) + (int)row;
-        // edge functions at the row's last column, walked right to left: the sign bit pushed in at step i
+        const int y = ((c1.w >> 8) & 0xff) + 2 * (int)unit;
+        const bool second = valid && 2u * unit + 1u < ((uint32_t)c1.w >> 24);
+        // edge functions at the rows' last column, walked right to left: the sign bit pushed in at step i
         // ends up at bit (wmax - 1 - i); shifting the surplus of a narrower row out leaves column c at bit c
         const int xr = bx0 + w - 1;
         int e1 = c0.x * xr + c0.y * y + c0.z, e2 = c0.w * xr + c1.x * y + c1.y, e0 = c1.z - (e1 + e2);
+        int f1 = e1 + c0.y, f2 = e2 + c1.x, f0 = c1.z - (f1 + f2);    // the row below
         const int A0 = -(c0.x + c0.w);
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, valid ? (uint32_t)w : 0u);
-        uint32_t outside = 0;
-#pragma unroll 4
+        uint32_t outA = 0, outB = 0;
+#pragma unroll 2
         for(uint32_t i = 0; i < wmax; i++)
         {
-          outside = __funnelshift_l((uint32_t)(e0 | e1 | e2), outside, 1);    // << 1 | (some edge function < 0)
+          outA = __funnelshift_l((uint32_t)(e0 | e1 | e2), outA, 1);    // << 1 | (some edge function < 0)
+          outB = __funnelshift_l((uint32_t)(f0 | f1 | f2), outB, 1);
           e0 -= A0;
           e1 -= c0.x;
           e2 -= c0.w;
+          f0 -= A0;
+          f1 -= c0.x;
+          f2 -= c0.w;
         }
         // covered iff all three >= 0 (rasterizer.cpp:549), inside the row's w columns
-        const uint32_t cov = valid ? (~(outside >> (wmax - (uint32_t)w)) & (0xffffffffu >> (32 - w))) : 0u;
-        const uint32_t L = __popc(cov);
-        const int first = __ffs((int)cov) - 1;
-        covered += L;
-        // The three half-planes cut an interval out of the row, so the covered pixels are one run: first ..
+        const uint32_t colmask = 0xffffffffu >> (32 - w);
+        const uint32_t covA = valid ? (~(outA >> (wmax - (uint32_t)w)) & colmask) : 0u;
+        const uint32_t covB = second ? (~(outB >> (wmax - (uint32_t)w)) & colmask) : 0u;
+        uint32_t LA = __popc(covA), LB = __popc(covB);
+        const int firstA = __ffs((int)covA) - 1, firstB = __ffs((int)covB) - 1;
+        covered += LA + LB;
+        // The three half-planes cut an interval out of a row, so its covered pixels are one run: first ..
         // first + L - 1. (Only wrapped int32 arithmetic on out-of-domain geometry could break that; such a row
         // is walked bit by bit instead, see below.)
-        const bool ragged = L != 0u && (cov >> first) != (0xffffffffu >> (32 - L));
+        const bool raggedA = LA != 0u && (covA >> firstA) != (0xffffffffu >> (32 - LA));
+        const bool raggedB = LB != 0u && (covB >> firstB) != (0xffffffffu >> (32 - LB));
+        if(raggedA)
+          LA = 0;
+        if(raggedB)
+          LB = 0;
         // ---- 3. the runs of the warp's rows end to end; rows without coverage drop out
-        const uint32_t nzmask = __ballot_sync(0xffffffffu, L != 0u && !ragged);
-        uint32_t end = (L != 0u && !ragged) ? L : 0u;
+        const uint32_t nzA = __ballot_sync(0xffffffffu, LA != 0u), nzB = __ballot_sync(0xffffffffu, LB != 0u);
+        uint32_t end = LA + LB;
 #pragma unroll
         for(int o = 1; o < 32; o <<= 1)
         {
@@ -868,22 +888,29 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
             end += v;
         }
         const uint32_t hits = __shfl_sync(0xffffffffu, end, 31);
-        const uint32_t nrec = __popc(nzmask);
+        const uint32_t nrec = __popc(nzA) + __popc(nzB);
+        const uint32_t below = (1u << lane) - 1u;
+        const uint32_t rank = __popc(nzA & below) + __popc(nzB & below);
         __syncwarp();    // the previous step's lookups in s_run are done
-        if(L != 0u && !ragged)
-          s_run[warp][__popc(nzmask & ((1u << lane) - 1u))] =
-              make_uint2(end - L, owner | ((uint32_t)y << 8) | ((uint32_t)(bx0 + first) << 13));
+        if(LA != 0u)
+          s_run[warp][rank] = make_uint2(end - LA - LB, owner | ((uint32_t)y << 8) | ((uint32_t)(bx0 + firstA) << 13));
+        if(LB != 0u)
+          s_run[warp][rank + (LA != 0u)] =
+              make_uint2(end - LB, owner | ((uint32_t)(y + 1) << 8) | ((uint32_t)(bx0 + firstB) << 13));
         __syncwarp();
-        // run r starts at hit s_run[r].x; lane r keeps that start for the owner lookups of the hit steps
-        const uint32_t runStart = (uint32_t)lane < nrec ? s_run[warp][lane].x : 0xffffffffu;
+        // run r starts at hit s_run[r].x; lane l keeps the starts of runs l and l + 32 for the owner lookups
+        const uint32_t runStart0 = (uint32_t)lane < nrec ? s_run[warp][lane].x : 0xffffffffu;
+        const uint32_t runStart1 = (uint32_t)lane + 32u < nrec ? s_run[warp][lane + 32].x : 0xffffffffu;
         for(uint32_t hb = 0; hb < hits; hb += 32u)
         {
           // run that owns hit hb (the last one starting at or before it), then one more per run that begins
           // inside (hb, hb + lane]
-          const uint32_t rel = runStart - hb;
-          const uint32_t ownerBase = __popc(__ballot_sync(0xffffffffu, runStart <= hb)) - 1u;
-          const uint32_t begins = __reduce_or_sync(0xffffffffu, (rel - 1u) < 31u ? (1u << rel) : 0u);
-          const uint32_t r = min(ownerBase + __popc(begins & (0xffffffffu >> (31 - lane))), 31u);
+          const uint32_t rel0 = runStart0 - hb, rel1 = runStart1 - hb;
+          const uint32_t ownerBase = __popc(__ballot_sync(0xffffffffu, runStart0 <= hb)) +
+                                     __popc(__ballot_sync(0xffffffffu, runStart1 <= hb)) - 1u;
+          const uint32_t begins = __reduce_or_sync(0xffffffffu, ((rel0 - 1u) < 31u ? (1u << rel0) : 0u) |
+                                                                    ((rel1 - 1u) < 31u ? (1u << rel1) : 0u));
+          const uint32_t r = min(ownerBase + __popc(begins & (0xffffffffu >> (31 - lane))), 63u);
           const uint2 run = s_run[warp][r];
           const uint32_t h = hb + lane;
           const uint32_t slot16 = (run.y & 255u) * 16u;
@@ -912,24 +939,29 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
                                       rs.depth_op, s_depth, idx, key))
             vb200_vis_min(aSlot, seen, key);
         }
-        if(__any_sync(0xffffffffu, ragged))
+        if(__any_sync(0xffffffffu, raggedA || raggedB))
         {
-          // out-of-domain geometry only: this lane's row has holes; visit its set bits one by one
-          uint32_t bits = ragged ? cov : 0u;
+          // out-of-domain geometry only: a row with holes; its set bits are visited one by one
           const int4 c2 = vb200_lds128(aZ + o16);
           const uint32_t id = vb200_lds32(aKey + 4u * owner);
-          while(bits)
+          for(int rowSel = 0; rowSel < 2; rowSel++)
           {
-            const int px = bx0 + __ffs((int)bits) - 1;
-            bits &= bits - 1u;
-            const int b1 = c0.x * px + c0.y * y + c0.z, b2 = c0.w * px + c1.x * y + c1.y, b0 = c1.z - (b1 + b2);
-            const int idx = (y * VB200_TILE + px) & (VB200_TILE * VB200_TILE - 1);
-            unsigned long long key;
-            if(vb200_fragment_key<MODE>(b0, b1, b2, __int_as_float(c2.x), __int_as_float(c2.y), __int_as_float(c2.z),
-                                        __int_as_float(c2.w), id, depthTest, rs.depth_op, s_depth, idx, key))
+            uint32_t bits = rowSel ? (raggedB ? covB : 0u) : (raggedA ? covA : 0u);
+            const int py = y + rowSel;
+            while(bits)
             {
-              const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
-              vb200_vis_min(aSlot, vb200_lds64(aSlot), key);
+              const int px = bx0 + __ffs((int)bits) - 1;
+              bits &= bits - 1u;
+              const int b1 = c0.x * px + c0.y * py + c0.z, b2 = c0.w * px + c1.x * py + c1.y, b0 = c1.z - (b1 + b2);
+              const int idx = (py * VB200_TILE + px) & (VB200_TILE * VB200_TILE - 1);
+              unsigned long long key;
+              if(vb200_fragment_key<MODE>(b0, b1, b2, __int_as_float(c2.x), __int_as_float(c2.y),
+                                          __int_as_float(c2.z), __int_as_float(c2.w), id, depthTest, rs.depth_op,
+                                          s_depth, idx, key))
+              {
+                const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
+                vb200_vis_min(aSlot, vb200_lds64(aSlot), key);
+              }
             }
           }
         }
@@ -940,7 +972,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 
   // ---- phase B: shade the winner of every pixel, write back
   const bool recordsInSmem = rs.slot_keys && n <= 256u;    // the only round's records are still staged
-#pragma unroll
+  VB200_UNROLL(VB200_PB_UNROLL)
   for(int j = 0; j < 4; j++)
   {
     const int ly = warp + 8 * j;
