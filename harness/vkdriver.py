@@ -65,7 +65,16 @@ def _driver():
         _lib = C.CDLL(DRIVER)
         _lib.vkd_run.argtypes = [C.c_char_p, C.POINTER(SceneDesc), C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lib.vkd_run.restype = C.c_int
+        _lib.vkd_frame_seconds.argtypes = [C.POINTER(C.c_double), C.c_int]
+        _lib.vkd_frame_seconds.restype = C.c_int
     return _lib
+
+
+def frame_seconds(n: int):
+    """host wall clock around vkQueueSubmit + vkQueueWaitIdle of each of the (up to n) frames of the last run()"""
+    buf = (C.c_double * max(n, 1))()
+    got = _driver().vkd_frame_seconds(buf, n)
+    return [buf[i] for i in range(got)]
 
 
 def run(icd_path: str, scene: Scene, frames: int = 1, serial_reference: bool = True

@@ -84,9 +84,20 @@ struct Loaded
   VkInstance inst;
   VkDevice dev;
   VkQueue queue;
+  bool serial;
 };
 std::map<std::string, Loaded> g_loaded;
+std::vector<double> g_frame_seconds;    // vkQueueSubmit + vkQueueWaitIdle of every frame of the last vkd_run
 }    // namespace
+
+// per-frame submit times of the last vkd_run (host wall clock around vkQueueSubmit + vkQueueWaitIdle)
+extern "C" __attribute__((visibility("default"))) int vkd_frame_seconds(double *out, int n)
+{
+  int i = 0;
+  for(; i < n && i < (int)g_frame_seconds.size(); i++)
+    out[i] = g_frame_seconds[i];
+  return i;
+}
 
 extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_path, const vkd_scene *sc, int frames,
                                                               int serial_reference, double *submit_seconds)
@@ -127,14 +138,6 @@ extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_pa
   {
     VkInstanceCreateInfo ici = {VK_STRUCTURE_TYPE_INSTANCE_CREATE_INFO};
     vkCreateInstance(&ici, NULL, &L.inst);
-    if(serial_reference)
-    {
-      // the reference's vkCreateInstance spawns its 7 racy workers (icd_stubs.cpp:12); joining them
-      // puts it in the deterministic serial-drain mode. For the CUDA ICD it is a flush.
-      void (*shutdownThreads)() = (void (*)())dlsym(c.lib, "_Z21ShutdownRasterThreadsv");
-      if(shutdownThreads)
-        shutdownThreads();
-    }
     uint32_t npd = 1;
     VkPhysicalDevice pd;
     vkEnumeratePhysicalDevices(L.inst, &npd, &pd);
@@ -145,6 +148,16 @@ extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_pa
     dci.pQueueCreateInfos = &qci;
     vkCreateDevice(pd, &dci, NULL, &L.dev);
     vkGetDeviceQueue(L.dev, 0, 0, &L.queue);
+  }
+  if(serial_reference && !L.serial)
+  {
+    // the reference's vkCreateInstance spawns its 7 racy workers (icd_stubs.cpp:12); joining them
+    // puts it in the deterministic serial-drain mode. For the CUDA ICD it is a flush.
+    // (One way only: a process that wants the threaded mode timed must run it before any serial call.)
+    void (*shutdownThreads)() = (void (*)())dlsym(c.lib, "_Z21ShutdownRasterThreadsv");
+    if(shutdownThreads)
+      shutdownThreads();
+    L.serial = true;
   }
   VkDevice dev = L.dev;
   VkQueue queue = L.queue;
@@ -491,6 +504,7 @@ extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_pa
   si.commandBufferCount = 1;
   si.pCommandBuffers = &cb;
   double best = 1e30;
+  g_frame_seconds.clear();
   for(int f = 0; f < frames; f++)
   {
     if(f > 0 && !sc->clear_color_enable)
@@ -506,6 +520,7 @@ extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_pa
     if(r != VK_SUCCESS)
       return -20;
     best = dt < best ? dt : best;
+    g_frame_seconds.push_back(dt);
   }
   if(submit_seconds)
     *submit_seconds = best;

@@ -33,6 +33,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("c2")
+    # same config keys as the product arm prints (bench.py: workload_config), --steps/--warmup honoured as given
+    assert set(d["config"]) == {"workload", "triangles", "resolution", "l2", "parallelism", "raster_path"}
+    assert d["steps"] == 2 and d["warmup"] == 1
+    assert "vkQueueSubmit" in d["reference_arm"]["timing"] and "interpreted" in d["reference_arm"]["shader_stage"]
+    assert d["reference_arm"]["modes"]["serial"]["frames"] == 2
 
 
 @pytest.mark.skipif(not abi.available("vref"), reason="oracle/_ref/libvisor_ref.so not built")

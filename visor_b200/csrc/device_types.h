@@ -102,6 +102,7 @@ struct Vb200RasterState
 {
   uint32_t width, height;
   uint32_t tiles_x, tiles_y;
+  uint32_t tiles_x_magic;    // floor(2^32 / tiles_x) + 1: tile / tiles_x == __umulhi(tile, magic) for tile < 65536
   uint32_t depth_op;         // VkCompareOp; 7 (ALWAYS) or no depth image -> no test
   uint32_t depth_write;
   uint32_t has_depth;

@@ -69,6 +69,7 @@ struct Vb200TileParams
   uint32_t *color;
   float *depth;
   const float4 *interps;
+  const float *unorm;    // 256 floats: float(i) / 255.0f, the exact quotients (texture_sampling.cpp:121-133, rasterizer.cpp:595-599)
   Vb200DrawCounters *counters;
   Vb200RasterState rs;
 };

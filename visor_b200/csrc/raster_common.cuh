@@ -104,10 +104,13 @@ __device__ __forceinline__ uint32_t vb200_blend_store(const Vb200RasterState &rs
 }
 
 // colour store of the tile kernels: local image + every other rank's image (fused sort-first exchange),
-// through one switch-replicated multicast store when an NVLS mapping is set, else one store per peer
-__device__ __forceinline__ void vb200_store_color(const Vb200TileParams &p, size_t gi, uint32_t v)
+// through one switch-replicated multicast store when an NVLS mapping is set, else one store per peer.
+// `remote` (uniform: some exchange target is set) keeps the single-GPU path at one store and one branch.
+__device__ __forceinline__ void vb200_store_color(const Vb200TileParams &p, uint32_t gi, uint32_t v, bool remote)
 {
   __stcs(p.color + gi, v);    // streaming store: the frame must not sweep the geometry out of L2
+  if(!remote)
+    return;
   if(p.mc_color)
     asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p.mc_color + gi), "r"(v) : "memory");
   else

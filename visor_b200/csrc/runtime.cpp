@@ -231,6 +231,7 @@ struct Context
   std::map<uint8_t *, std::vector<uint32_t *>> peerTargets;
   std::map<uint8_t *, uint32_t *> multicastTargets;
   Vb200DrawCounters *counters = nullptr;    // device
+  float *unorm = nullptr;                   // device: float(i) / 255.0f for every byte value
   const char *lastTileKernel = "";
   // present path: copies on a second stream, ordered against the library stream with events
   cudaStream_t copyStream = nullptr;
@@ -882,6 +883,13 @@ int vb200_init(int device)
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
   CU(cudaMalloc((void **)&g.range, 2 * sizeof(uint32_t)));
+  {
+    float table[256];
+    for(int i = 0; i < 256; i++)
+      table[i] = (float)i / 255.0f;    // IEEE single division, as the reference's float(byte) / 255.0f
+    CU(cudaMalloc((void **)&g.unorm, sizeof(table)));
+    CU(cudaMemcpy(g.unorm, table, sizeof(table), cudaMemcpyHostToDevice));
+  }
   CU(cudaMalloc((void **)&g.counters, sizeof(Vb200DrawCounters)));
   CU(cudaMemsetAsync(g.counters, 0, sizeof(Vb200DrawCounters), g.stream));
   memset(&g.stats, 0, sizeof(g.stats));
@@ -913,6 +921,7 @@ void vb200_shutdown(void)
   cudaFree(g.range);
   g.triTiles.release();
   cudaFree(g.counters);
+  cudaFree(g.unorm);
   for(auto &pr : g.presents)
   {
     if(pr.ready)
@@ -1748,6 +1757,8 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.rs.height = H;
   tp.rs.tiles_x = tilesX;
   tp.rs.tiles_y = tilesY;
+  tp.rs.tiles_x_magic = (uint32_t)(0x100000000ull / tilesX) + 1u;
+  tp.unorm = g.unorm;
   tp.rs.depth_op = pl->depth_compare_op;
   tp.rs.depth_write = depthWrite ? 1u : 0u;
   tp.rs.has_depth = depthDev ? 1u : 0u;

@@ -23,7 +23,7 @@
 #define VB200_PRAGMA(x) _Pragma(#x)
 #define VB200_UNROLL(n) VB200_PRAGMA(unroll n)
 #ifndef VB200_PB_UNROLL
-#define VB200_PB_UNROLL 4    // rows of the resolve kernels' shading pass in flight per thread
+#define VB200_PB_UNROLL 1
 #endif
 
 extern "C" __device__ float4 vb200_vs(const Vb200Env *env, unsigned vid, float4 *interps_out);
@@ -222,14 +222,14 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   const uint32_t *list = p.list + (size_t)blockIdx.x * p.list_cap;
   uint32_t scanPos = 0, scanQueued = 0;
   const Vb200RasterState &rs = p.rs;
-  const uint32_t tx = tile % rs.tiles_x, ty = tile / rs.tiles_x;
+  const uint32_t ty = __umulhi(tile, rs.tiles_x_magic), tx = tile - ty * rs.tiles_x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rx0 = (int)(tx * VB200_TILE) + (warp & 1) * 16, ry0 = (int)(ty * VB200_TILE) + (warp >> 1) * 8;
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
   const bool blend = rs.blend_enable != 0u && rs.blend_op == 0u;    // only ADD is defined (rasterizer.cpp:657-669)
 
-  vb200_s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  vb200_s_unorm[threadIdx.x] = __ldg(p.unorm + threadIdx.x);
   uint32_t *wcol = s_col[warp];
   float *wdep = s_dep[warp];
   uint16_t *wq = s_queue[warp];
@@ -450,7 +450,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     if(x < (int)rs.width && y < (int)rs.height)
     {
       const size_t idx = (size_t)y * rs.width + x;
-      vb200_store_color(p, idx, wcol[i]);
+      vb200_store_color(p, (uint32_t)idx, wcol[i], p.mc_color != nullptr || p.num_peers != 0u);
       if(depthWrite || (clearDepth && rs.has_depth))
         __stcs(p.depth + idx, wdep[i]);
     }
@@ -627,8 +627,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   const Vb200RasterState &rs = p.rs;
-  const uint32_t tx = tile % rs.tiles_x, ty = tile / rs.tiles_x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ty = __umulhi(tile, rs.tiles_x_magic), tx = tile - ty * rs.tiles_x;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  asm volatile("" : "+r"(lane), "+r"(warp));    // (kept in registers: ptxas otherwise re-reads %tid inside the loops)
   const int tileX0 = (int)(tx * VB200_TILE), tileY0 = (int)(ty * VB200_TILE);
   if(n == 0)
   {
@@ -641,9 +642,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         const int x = tileX0 + lane, y = tileY0 + warp + 8 * j;
         if(x < (int)rs.width && y < (int)rs.height)
         {
-          const size_t gi = (size_t)y * rs.width + x;
+          const uint32_t gi = (uint32_t)y * rs.width + (uint32_t)x;
           if(clearColor)
-            vb200_store_color(p, gi, p.clear_color);
+            vb200_store_color(p, gi, p.clear_color, p.mc_color != nullptr || p.num_peers != 0u);
           if(clearDepth && rs.has_depth)
             __stcs(p.depth + gi, p.clear_depth);
         }
@@ -659,7 +660,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
 
-  vb200_s_unorm[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);    // read in phase B, after the barriers below
+  vb200_s_unorm[threadIdx.x] = __ldg(p.unorm + threadIdx.x);    // read in phase B, after the barriers below
   // ---- init: one visibility key per pixel, seeded with the depth already in the buffer
 #pragma unroll
   for(int j = 0; j < 4; j++)
@@ -782,15 +783,10 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     s_sv[threadIdx.x] = rsv;
     s_key[threadIdx.x] = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
     __syncthreads();
-    uint32_t wbase = 0, total = 0;
-#pragma unroll
-    for(int q = 0; q < 8; q++)
-    {
-      const uint32_t v = s_wsum[q];
-      wbase += (q < warp) ? v : 0u;
-      total += v;
-    }
-    // s_start[r] = first row of record r in the stream; entries past the round's records hold its length
+    const uint32_t wsum = lane < 8 ? s_wsum[lane] : 0u;
+    const uint32_t total = __reduce_add_sync(0xffffffffu, wsum);
+    const uint32_t wbase = __reduce_add_sync(0xffffffffu, lane < warp ? wsum : 0u);
+    // s_start[r] = first unit of record r in the stream; entries past the round's records hold its length
     s_start[threadIdx.x] = have ? wbase + incl - mine : total;
     if(threadIdx.x == 0)
       s_start[256] = total;
@@ -970,97 +966,109 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   }
   __syncthreads();
 
-  // ---- phase B: shade the winner of every pixel, write back
+  // ---- phase B: shade the winner of every pixel, write back. Thread (warp, lane) owns pixel column `lane`
+  // of rows warp, warp + 8, warp + 16, warp + 24.
   const bool recordsInSmem = rs.slot_keys && n <= 256u;    // the only round's records are still staged
-  VB200_UNROLL(VB200_PB_UNROLL)
-  for(int j = 0; j < 4; j++)
-  {
-    const int ly = warp + 8 * j;
-    const int x = tileX0 + lane, y = tileY0 + ly;
-    const unsigned long long key = vis[ly * VB200_TILE + lane];
-    const uint32_t low = (uint32_t)key;
-    bool won;
-    uint32_t id;
-    if(MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST)
+  const bool remote = p.mc_color != nullptr || p.num_peers != 0u;
+  uint32_t aPw = vb200_smem_addr(s_pw), aSv = vb200_smem_addr(s_sv);
+  asm volatile("" : "+r"(aPw), "+r"(aSv));
+  const bool xin = tileX0 + lane < (int)rs.width;
+  const uint32_t rowStep = 8u * rs.width;    // pixel offsets fit 32 bits (targets are at most 8192 x 8192)
+  // `record(id, ly, y)`: the winner's barycentric numerators at the pixel and its per-triangle constants
+  auto shade_rows = [&](auto record) {
+    uint32_t gi = (uint32_t)(tileY0 + warp) * rs.width + (uint32_t)(tileX0 + lane);
+    VB200_UNROLL(VB200_PB_UNROLL)
+    for(int j = 0; j < 4; j++, gi += rowStep)
     {
-      won = low != 0u;
-      id = low;
-    }
-    else if(MODE == VB200_RES_LAST_WINS)
-    {
-      won = key != ~0ull;
-      id = ~low;
-    }
-    else
-    {
-      won = low != 0xffffffffu;
-      id = ~low;
-    }
-    if(x >= (int)rs.width || y >= (int)rs.height)
-      continue;
-    if(!won)
-    {
-      if(p.clear_flags)
+      const int ly = warp + 8 * j;
+      const unsigned long long key = vb200_lds64(aVis + 8u * (uint32_t)(ly * VB200_TILE + lane));
+      const uint32_t low = (uint32_t)key;
+      bool won;
+      uint32_t id;
+      if(MODE == VB200_RES_MIN_FIRST || MODE == VB200_RES_MAX_FIRST)
       {
-        const size_t gi = (size_t)y * rs.width + x;
+        won = low != 0u;
+        id = low;
+      }
+      else if(MODE == VB200_RES_LAST_WINS)
+      {
+        won = key != ~0ull;
+        id = ~low;
+      }
+      else
+      {
+        won = low != 0xffffffffu;
+        id = ~low;
+      }
+      if(!xin || tileY0 + ly >= (int)rs.height)
+        continue;
+      if(!won)
+      {
         if(clearColor)
-          vb200_store_color(p, gi, p.clear_color);
+          vb200_store_color(p, gi, p.clear_color, remote);
         if(clearDepth && rs.has_depth)
           __stcs(p.depth + gi, p.clear_depth);
+        continue;
       }
-      continue;
+      shaded++;
+      int b0, b1, b2;
+      float invarea, d0, d1, d2, invw0, invw1, invw2;
+      uint32_t s0, s1, s2;
+      record(id, ly, b0, b1, b2, invarea, d0, d1, d2, invw0, invw1, invw2, s0, s1, s2);
+      // rasterizer.cpp:552-558, 581-588
+      float n0 = __fmul_rn((float)b0, invarea);
+      float n1 = __fmul_rn((float)b1, invarea);
+      float n2 = __fmul_rn((float)b2, invarea);
+      const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));
+      n0 = __fmul_rn(n0, invw0);
+      n1 = __fmul_rn(n1, invw1);
+      n2 = __fmul_rn(n2, invw2);
+      // 1.0f / x, correctly rounded (the dedicated reciprocal is a shorter sequence than the general division
+      // and returns the same bits: both are the IEEE-rounded quotient)
+      const float invlen = __frcp_rn(__fadd_rn(__fadd_rn(n0, n1), n2));
+      n0 = __fmul_rn(n0, invlen);
+      n1 = __fmul_rn(n1, invlen);
+      n2 = __fmul_rn(n2, invlen);
+      const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)s0 * rs.nslots,
+                                  p.interps + (size_t)s1 * rs.nslots, p.interps + (size_t)s2 * rs.nslots);
+      vb200_store_color(p, gi, vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]), remote);
+      if(depthWrite)
+        __stcs(p.depth + gi, pixdepth);
+      else if(clearDepth && rs.has_depth)
+        __stcs(p.depth + gi, p.clear_depth);
     }
-    shaded++;
-    // the winner's edge values at this pixel, exactly as the reference computes them
-    // (rasterizer.cpp:303-309,545-558; int32 ring arithmetic, so both formulations give the same bits)
-    int b0, b1, b2;
-    float invarea, d0, d1, d2, invw0, invw1, invw2;
-    uint32_t s0, s1, s2;
-    if(recordsInSmem)
-    {
-      const uint32_t slot = id & 255u;    // the thread that set the winner up
-      const int4 c0 = s_e1[slot], c1 = s_e2[slot], c2 = s_z[slot], c4 = s_pw[slot];
-      const int2 c5 = s_sv[slot];
+  };
+  if(recordsInSmem)
+    shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
+                   float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
+      // the winner's edge values at this pixel from its staged record (int32 ring arithmetic, so this and
+      // the reference's formulation, rasterizer.cpp:303-309,545-558, give the same bits)
+      const uint32_t slot16 = (id & 255u) * 16u;    // slot = the thread that set the winner up
+      const int4 c0 = vb200_lds128(aE1 + slot16), c1 = vb200_lds128(aE2 + slot16), c2 = vb200_lds128(aZ + slot16),
+                 c4 = vb200_lds128(aPw + slot16);
+      const unsigned long long c5 = vb200_lds64(aSv + (slot16 >> 1));
       b1 = c0.x * lane + c0.y * ly + c0.z;
       b2 = c0.w * lane + c1.x * ly + c1.y;
       b0 = c1.z - (b1 + b2);
       invarea = __int_as_float(c2.x); d0 = __int_as_float(c2.y); d1 = __int_as_float(c2.z); d2 = __int_as_float(c2.w);
       invw0 = __int_as_float(c4.x); invw1 = __int_as_float(c4.y); invw2 = __int_as_float(c4.z);
-      s0 = (uint32_t)c4.w; s1 = (uint32_t)c5.x; s2 = (uint32_t)c5.y;
-    }
-    else
-    {
+      s0 = (uint32_t)c4.w; s1 = (uint32_t)c5; s2 = (uint32_t)(c5 >> 32);
+    });
+  else
+    shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
+                   float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
+      // several rounds: the record is gathered again, edge values exactly as rasterizer.cpp:303-309,545-558
       const Vb200TriSetup su = vb200_load_setup(p, (rs.slot_keys ? (id >> 8) : id) - 1u);
       const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
       const int area2 = ABx * ACy - ABy * ACx;
       const int sgn = area2 > 0 ? 1 : -1;
-      const int PAx = su.x0 - x, PAy = su.y0 - y;
+      const int PAx = su.x0 - (tileX0 + lane), PAy = su.y0 - (tileY0 + ly);
       const int ux = ACx * PAy - ACy * PAx, uy = PAx * ABy - PAy * ABx;
       b0 = (area2 - (ux + uy)) * sgn; b1 = ux * sgn; b2 = uy * sgn;
       invarea = su.invarea; d0 = su.d0; d1 = su.d1; d2 = su.d2;
       invw0 = su.invw0; invw1 = su.invw1; invw2 = su.invw2;
       s0 = su.s0; s1 = su.s1; s2 = su.s2;
-    }
-    float n0 = __fmul_rn((float)b0, invarea);
-    float n1 = __fmul_rn((float)b1, invarea);
-    float n2 = __fmul_rn((float)b2, invarea);
-    const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));
-    n0 = __fmul_rn(n0, invw0);
-    n1 = __fmul_rn(n1, invw1);
-    n2 = __fmul_rn(n2, invw2);
-    const float invlen = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(n0, n1), n2));
-    n0 = __fmul_rn(n0, invlen);
-    n1 = __fmul_rn(n1, invlen);
-    n2 = __fmul_rn(n2, invlen);
-    const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)s0 * rs.nslots,
-                                p.interps + (size_t)s1 * rs.nslots, p.interps + (size_t)s2 * rs.nslots);
-    const size_t gi = (size_t)y * rs.width + x;
-    vb200_store_color(p, gi, vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]));
-    if(depthWrite)
-      __stcs(p.depth + gi, pixdepth);
-    else if(clearDepth && rs.has_depth)
-      __stcs(p.depth + gi, p.clear_depth);
-  }
+    });
   if(rs.count_fragments)
     vb200_count_fragments(p.counters, covered, shaded);
 }
