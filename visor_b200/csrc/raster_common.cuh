@@ -22,6 +22,17 @@ __device__ __forceinline__ float vb200_ld_f32_unaligned(const uint8_t *p)
   return __uint_as_float(u);
 }
 
+// a triangle as the tile kernels use it, from its 16-byte record q and the three raster vertices a, b, c
+__device__ __forceinline__ Vb200TriSetup vb200_unpack_setup(const int4 &q, const int4 &a, const int4 &b, const int4 &c)
+{
+  Vb200TriSetup r;
+  r.x0 = a.x; r.y0 = a.y; r.x1 = b.x; r.y1 = b.y; r.x2 = c.x; r.y2 = c.y;
+  r.invw0 = __int_as_float(a.z); r.invw1 = __int_as_float(b.z); r.invw2 = __int_as_float(c.z);
+  r.d0 = __int_as_float(a.w); r.d1 = __int_as_float(b.w); r.d2 = __int_as_float(c.w);
+  r.s0 = (uint32_t)q.x; r.s1 = (uint32_t)q.y; r.s2 = (uint32_t)q.z; r.invarea = __int_as_float(q.w);
+  return r;
+}
+
 __device__ __forceinline__ Vb200TriSetup vb200_load_setup(const Vb200TileParams &p, uint32_t t)
 {
   // 16-byte triangle record, then one 16-byte read-only gather per corner

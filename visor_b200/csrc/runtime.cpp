@@ -80,6 +80,7 @@ struct JitKernel
 {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kernel = nullptr;
+  unsigned threads = 0;    // CTA size the kernel was written for (.maxntid of its entry)
 };
 
 // Set of disjoint half-open byte intervals [lo, hi) of a mirror, kept sorted and merged.
@@ -622,6 +623,16 @@ int runPtxas(const std::string &text, const char *name, std::vector<char> &cubin
   return VB200_OK;
 }
 
+// CTA size a kernel of the scaffold was written for: the .maxntid directive of its entry (__launch_bounds__)
+unsigned kernelThreads(int which)
+{
+  if(!parseScaffold())
+    return 0;
+  const std::string &entry = scaffold.entries[which];
+  const size_t at = entry.find(".maxntid ");
+  return at == std::string::npos ? 0u : (unsigned)strtoul(entry.c_str() + at + strlen(".maxntid "), nullptr, 10);
+}
+
 // ptxas step: kernel text + shader function -> one sm_100a cubin. Needs no device.
 int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin)
 {
@@ -635,14 +646,16 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
       body.erase(at, body.find('\n', at) - at);
   }
   stripExternFuncs(body);
-  // Tile kernels: ask ptxas for five resident CTAs per SM (<= 48 registers at the allocation granule).
-  // Left alone it picks ~50 for the resolve kernels, which the granule rounds up to 56 = four CTAs;
-  // the bound costs a handful of spilled bytes and buys the fifth CTA (measured, resolve kernel: C3
-  // 182 -> 167 us, C5 1086 -> 1010 us; six CTAs spill more and are slower again). Whether a shader
-  // leaves room for that is only known after inlining, so the bound is dropped when ptxas reports
-  // more than a few spilled words. VB200_JIT_MINCTAS overrides (tuning aid).
+  // Tile kernels: a bound on the resident CTAs per SM (.minnctapersm) makes ptxas fit the register
+  // allocation granule instead of landing just above it. Whether a shader leaves room for that is only
+  // known after inlining, so the bound is dropped when ptxas reports more than a few spilled words.
+  // VB200_JIT_MINCTAS overrides (tuning aid).
   const unsigned kSpillTolerance = 64;
-  int minCtas = which != K_VERTEX ? 5 : 0;
+  const unsigned threads = kernelThreads(which);
+  // resident CTAs asked of ptxas: 40 warps per SM for the ordered kernel (48 registers), 32 for the resolve
+  // kernels (64 registers: measured on B200, C3 tile kernel 138.9 -> 135.5 us and C5 878 -> 832 us against
+  // 40 warps at 48 registers with a few spilled words; 48 warps at 40 registers: 144 / 975 us)
+  int minCtas = which == K_VERTEX || !threads ? 0 : (int)((which == K_TILE_ORDERED ? 1280u : 1024u) / threads);
   bool forced = false;
   if(const char *mc = getenv("VB200_JIT_MINCTAS"))
   {
@@ -659,9 +672,10 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
     text += body;
     text += "\n";
     std::string entry = scaffold.entries[which];
-    const size_t at = entry.find(".maxntid 256, 1, 1");
-    if(minCtas > 0 && at != std::string::npos)
-      entry.insert(at + strlen(".maxntid 256, 1, 1"), "\n.minnctapersm " + std::to_string(minCtas));
+    const size_t at = entry.find(".maxntid ");
+    const size_t eol = at == std::string::npos ? at : entry.find('\n', at);
+    if(minCtas > 0 && eol != std::string::npos)
+      entry.insert(eol, "\n.minnctapersm " + std::to_string(minCtas));
     text += entry;
     text += scaffold.epilogue;
     unsigned spills = 0;
@@ -689,13 +703,15 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
 }
 
 // the loaded kernel `which` specialised for `shader`, compiled on first use
-int getKernel(int which, const vb200_entry *shader, cudaKernel_t *out)
+int getKernel(int which, const vb200_entry *shader, cudaKernel_t *out, unsigned *threads = nullptr)
 {
   const auto key = std::make_pair(shader->serial, which);
   auto it = g.kernels.find(key);
   if(it != g.kernels.end())
   {
     *out = it->second.kernel;
+    if(threads)
+      *threads = it->second.threads;
     return VB200_OK;
   }
   std::vector<char> cubin;
@@ -712,8 +728,11 @@ int getKernel(int which, const vb200_entry *shader, cudaKernel_t *out)
     cudaLibraryUnload(jk.lib);
     return setError(VB200_ERR_LINK, "cudaLibraryGetKernel(%s) failed: %s", kKernelNames[which], cudaGetErrorString(e));
   }
+  jk.threads = kernelThreads(which);
   g.kernels.emplace(key, jk);
   *out = jk.kernel;
+  if(threads)
+    *threads = jk.threads;
   return VB200_OK;
 }
 
@@ -1736,8 +1755,11 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     resolveMode = -1;
   const int tileKernelId = resolveMode >= 0 ? K_TILE_RESOLVE + resolveMode : K_TILE_ORDERED;
   cudaKernel_t kTile = nullptr;
-  if((rc = getKernel(tileKernelId, pl->fs, &kTile)))
+  unsigned tileThreads = 256;
+  if((rc = getKernel(tileKernelId, pl->fs, &kTile, &tileThreads)))
     return rc;
+  if(!tileThreads)
+    return setError(VB200_ERR_LINK, "kernel scaffold without a CTA size");
   g.lastTileKernel = kKernelNames[tileKernelId];
 
   Vb200TileParams tp;
@@ -1796,7 +1818,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   phaseMark(3);
   {
     void *args[] = {&env, &tp};
-    if((rc = launchKernel(kTile, dim3(ownedTiles), dim3(256), args)))
+    if((rc = launchKernel(kTile, dim3(ownedTiles), dim3(tileThreads), args)))
       return rc;
   }
   phaseMark(4);

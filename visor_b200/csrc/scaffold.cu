@@ -22,6 +22,15 @@
 // tuning switches (see `make variants`)
 #define VB200_PRAGMA(x) _Pragma(#x)
 #define VB200_UNROLL(n) VB200_PRAGMA(unroll n)
+#ifndef VB200_RESOLVE_THREADS
+// CTA size of the resolve kernels = triangles set up per round. A tile of a dense mesh holds ~100 triangles
+// and ~10 steps of the row stream: four warps per tile keep the set-up lanes busy and the spread between the
+// first and the last warp to finish the stream small (with eight, a third of all warp time was barrier wait).
+#define VB200_RESOLVE_THREADS 128
+#endif
+#ifndef VB200_TICKETS
+#define VB200_TICKETS 0    // resolve kernels: dynamic hand-out of the row stream's steps (measured: no gain over the fixed split)
+#endif
 #ifndef VB200_PB_UNROLL
 #define VB200_PB_UNROLL 1
 #endif
@@ -609,15 +618,17 @@ __device__ __forceinline__ void vb200_vis_min(uint32_t aSlot, unsigned long long
 template <int MODE>
 __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, const Vb200TileParams &p)
 {
+  constexpr int RT = VB200_RESOLVE_THREADS, RW = RT / 32;    // threads / warps of a CTA = triangles per round
   __shared__ unsigned long long vis[VB200_TILE * VB200_TILE];
   __shared__ float s_depth[MODE == VB200_RES_LAST_WINS ? VB200_TILE * VB200_TILE : 1];
-  __shared__ int4 s_e1[256], s_e2[256], s_z[256], s_pw[256];    // records of the current round
-  __shared__ int2 s_sv[256];
-  __shared__ uint32_t s_key[256];
-  __shared__ __align__(16) uint32_t s_start[260];   // first stream row of each record; past the records: stream length
-  __shared__ uint2 s_run[8][64];                    // per warp: the covered runs of the 64 rows of the current step
-  __shared__ uint32_t s_wsum[8];
-  __shared__ uint32_t s_ids[512];    // id queue of the fallback scan (overflowed tile list)
+  __shared__ int4 s_e1[RT], s_e2[RT], s_z[RT], s_pw[RT];    // records of the current round
+  __shared__ int2 s_sv[RT];
+  __shared__ uint32_t s_key[RT];
+  __shared__ __align__(16) uint32_t s_start[RT + 4];   // first stream row of each record; past the records: stream length
+  __shared__ uint2 s_run[RW][64];                    // per warp: the covered runs of the 64 rows of the current step
+  __shared__ uint32_t s_wsum[RW];
+  __shared__ uint32_t s_ticket;    // next unclaimed step of the row stream
+  __shared__ uint32_t s_ids[2 * RT];    // id queue of the fallback scan (overflowed tile list)
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
@@ -637,9 +648,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     if(p.clear_flags)
     {
 #pragma unroll
-      for(int j = 0; j < 4; j++)
+      for(int j = 0; j < VB200_TILE / RW; j++)
       {
-        const int x = tileX0 + lane, y = tileY0 + warp + 8 * j;
+        const int x = tileX0 + lane, y = tileY0 + warp + RW * j;
         if(x < (int)rs.width && y < (int)rs.height)
         {
           const uint32_t gi = (uint32_t)y * rs.width + (uint32_t)x;
@@ -660,22 +671,6 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   const bool depthTest = rs.has_depth && rs.depth_op != 7u;
   const bool depthWrite = rs.has_depth && rs.depth_write;
 
-  vb200_s_unorm[threadIdx.x] = __ldg(p.unorm + threadIdx.x);    // read in phase B, after the barriers below
-  // ---- init: one visibility key per pixel, seeded with the depth already in the buffer
-#pragma unroll
-  for(int j = 0; j < 4; j++)
-  {
-    const int ly = warp + 8 * j;
-    const int x = tileX0 + lane, y = tileY0 + ly;
-    const bool in = x < (int)rs.width && y < (int)rs.height;
-    float e = 0.0f;
-    if(MODE != VB200_RES_LAST_WINS || depthTest)
-      e = clearDepth ? p.clear_depth : (in ? p.depth[(size_t)y * rs.width + x] : 0.0f);
-    vis[ly * VB200_TILE + lane] = vb200_existing_key<MODE>(e);
-    if(MODE == VB200_RES_LAST_WINS)
-      s_depth[ly * VB200_TILE + lane] = e;
-  }
-
   // ---- phase A: coverage + visibility, up to 256 triangles of the list per round.
   //  1. one thread per triangle: load, edge setup, tile-clipped bbox -> record in shared memory;
   //  2. the ROW PAIRS of all bboxes are laid end to end into one stream (block-wide exclusive prefix sum of
@@ -694,9 +689,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
            aE2 = vb200_smem_addr(s_e2), aZ = vb200_smem_addr(s_z), aKey = vb200_smem_addr(s_key);
   asm volatile("" : "+r"(aVis), "+r"(aStart), "+r"(aE1), "+r"(aE2), "+r"(aZ), "+r"(aKey));
   uint32_t covered = 0, shaded = 0;
-  for(uint32_t base = 0; base < n; base += 256u)
+  for(uint32_t base = 0; base < n; base += RT)
   {
-    uint32_t m = min(256u, n - base);    // records in this round
+    uint32_t m = min((uint32_t)RT, n - base);    // records in this round
     uint32_t t = 0;
     if(!scanList)
     {
@@ -717,7 +712,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         __syncthreads();
         uint32_t before = 0, total = 0;
 #pragma unroll
-        for(int q = 0; q < 8; q++)
+        for(int q = 0; q < RW; q++)
         {
           const uint32_t v = s_wsum[q];
           before += (q < warp) ? v : 0u;
@@ -726,13 +721,13 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         if(match)
           s_ids[scanQueued + before + __popc(mm & ((1u << lane) - 1u))] = idx;
         scanQueued += total;
-        scanPos += 256u;
+        scanPos += RT;
       }
       __syncthreads();
       m = min(m, scanQueued);
       if(threadIdx.x < m)
         t = s_ids[threadIdx.x];
-      const uint32_t rest = scanQueued - m;    // < 256: they move to the front of the queue
+      const uint32_t rest = scanQueued - m;    // < RT: they move to the front of the queue
       const uint32_t mv = threadIdx.x < rest ? s_ids[m + threadIdx.x] : 0u;
       __syncthreads();
       if(threadIdx.x < rest)
@@ -742,9 +737,38 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     const bool have = threadIdx.x < m;
     int4 re1 = make_int4(0, 0, 0, 0), re2 = make_int4(0, 0, 0, (1 << 16) | (1 << 24)), rz = re1, rpw = re1;
     int2 rsv = make_int2(0, 0);
+    // the three dependent loads of a triangle (list entry above, record, corners) are in flight while the
+    // first round initialises the tile below
+    int4 rq = make_int4(0, 0, 0, 0), ra = rq, rb = rq, rc = rq;
     if(have)
     {
-      const Vb200TriSetup su = vb200_load_setup(p, t);
+      rq = __ldg((const int4 *)(p.tri + t));
+      ra = __ldg((const int4 *)(p.rv + (uint32_t)rq.x));
+      rb = __ldg((const int4 *)(p.rv + (uint32_t)rq.y));
+      rc = __ldg((const int4 *)(p.rv + (uint32_t)rq.z));
+    }
+    if(base == 0u)
+    {
+      for(int i = threadIdx.x; i < 256; i += RT)
+        vb200_s_unorm[i] = __ldg(p.unorm + i);    // read in phase B, after the barriers below
+      // ---- init: one visibility key per pixel, seeded with the depth already in the buffer
+    #pragma unroll
+      for(int j = 0; j < VB200_TILE / RW; j++)
+      {
+        const int ly = warp + RW * j;
+        const int x = tileX0 + lane, y = tileY0 + ly;
+        const bool in = x < (int)rs.width && y < (int)rs.height;
+        float e = 0.0f;
+        if(MODE != VB200_RES_LAST_WINS || depthTest)
+          e = clearDepth ? p.clear_depth : (in ? p.depth[(size_t)y * rs.width + x] : 0.0f);
+        vis[ly * VB200_TILE + lane] = vb200_existing_key<MODE>(e);
+        if(MODE == VB200_RES_LAST_WINS)
+          s_depth[ly * VB200_TILE + lane] = e;
+      }
+    }
+    if(have)
+    {
+      const Vb200TriSetup su = vb200_unpack_setup(rq, ra, rb, rc);
       const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
       const int area2 = ABx * ACy - ABy * ACx;
       const int sgn = area2 > 0 ? 1 : -1;
@@ -783,52 +807,58 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     s_sv[threadIdx.x] = rsv;
     s_key[threadIdx.x] = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
     __syncthreads();
-    const uint32_t wsum = lane < 8 ? s_wsum[lane] : 0u;
+    const uint32_t wsum = lane < RW ? s_wsum[lane] : 0u;
     const uint32_t total = __reduce_add_sync(0xffffffffu, wsum);
     const uint32_t wbase = __reduce_add_sync(0xffffffffu, lane < warp ? wsum : 0u);
     // s_start[r] = first unit of record r in the stream; entries past the round's records hold its length
     s_start[threadIdx.x] = have ? wbase + incl - mine : total;
     if(threadIdx.x == 0)
-      s_start[256] = total;
+    {
+      s_start[RT] = total;
+      s_ticket = 0;
+    }
     __syncthreads();
 
     const uint32_t steps = (total + 31u) >> 5;
-    const uint32_t firstStep = (steps * (uint32_t)warp) >> 3, lastStep = (steps * (uint32_t)(warp + 1)) >> 3;
-    if(firstStep < lastStep)
+    // VB200_TICKETS: steps handed out dynamically (a ticket counter in shared memory) instead of warp w taking
+    // the w-th share of them. A step's cost depends on how many pixels its rows cover, so a fixed split lets
+    // the warps arrive at the barrier behind the stream up to a step's worth of work apart.
     {
-      // record that owns stream row firstStep*32: the last record whose start is <= that row. Starts are
-      // strictly increasing (every record has at least one row) and entries past them hold `total` (> k),
-      // so it is (number of entries <= k) - 1: every lane counts eight entries (independent loads) and one
-      // warp reduction adds them up — instead of a dependent eight-step binary search.
-      uint32_t owner0;
+#if VB200_TICKETS
+      for(;;)
       {
-        const uint32_t k = firstStep << 5;
-        const uint4 a = *(const uint4 *)(s_start + lane * 8), b4 = *(const uint4 *)(s_start + lane * 8 + 4);
-        const uint32_t cnt = (a.x <= k) + (a.y <= k) + (a.z <= k) + (a.w <= k) + (b4.x <= k) + (b4.y <= k) +
-                             (b4.z <= k) + (b4.w <= k);
-        owner0 = __reduce_add_sync(0xffffffffu, cnt) - 1u;
-      }
-      // The owner bookkeeping of step s+1 (which records begin inside it) is independent of the pixel
-      // work of step s, so it is issued first each iteration: its shared-memory round trip and the
-      // warp reductions overlap the coverage arithmetic instead of heading the next iteration.
-      uint32_t starts, nextOwner0;
+        uint32_t step = 0;
+        if(lane == 0)
+          step = atomicAdd(&s_ticket, 1u);
+        step = __shfl_sync(0xffffffffu, step, 0);
+        if(step >= steps)
+          break;
+#else
+      const uint32_t lastStep = (steps * (uint32_t)(warp + 1)) / RW;
+      for(uint32_t step = (steps * (uint32_t)warp) / RW; step < lastStep; step++)
       {
-        const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (firstStep << 5);
-        starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-        nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
-      }
-      for(uint32_t step = firstStep; step < lastStep; step++)
-      {
+#endif
         const uint32_t k = step << 5;
         const uint32_t g = k + lane;
-        // lane l looked at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
-        const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), 255u);
-        owner0 = nextOwner0;
+        // record that owns stream unit k: the last record whose start is <= k. Starts are strictly increasing
+        // (every record has at least one unit) and entries past them hold `total` (> k), so it is (number
+        // of entries <= k) - 1: every lane counts its share of the entries (independent loads) and one warp
+        // reduction adds them up — instead of a dependent binary search.
+        uint32_t owner0;
         {
-          const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, 256u)) - (k + 32u);
-          starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
-          nextOwner0 = owner0 + __popc(__ballot_sync(0xffffffffu, rel <= 32u));
+          uint32_t cnt = 0;
+#pragma unroll
+          for(int q = 0; q < RT / 128; q++)
+          {
+            const uint4 a = *(const uint4 *)(s_start + lane * (RT / 32) + 4 * q);
+            cnt += (a.x <= k) + (a.y <= k) + (a.z <= k) + (a.w <= k);
+          }
+          owner0 = __reduce_add_sync(0xffffffffu, cnt) - 1u;
         }
+        // lane l looks at the start of record owner0+1+l: those that begin inside (k, k+32) split the step
+        const uint32_t rel = vb200_lds32(aStart + 4u * min(owner0 + 1u + (uint32_t)lane, (uint32_t)RT)) - k;
+        const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+        const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), (uint32_t)RT - 1u);
         // ---- 2. this lane's unit: rows 2u and 2u + 1 (if the bbox has it) of record `owner`, u = g - start
         const bool valid = g < total;
         const uint32_t o16 = owner * 16u;
@@ -888,34 +918,37 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         const uint32_t below = (1u << lane) - 1u;
         const uint32_t rank = __popc(nzA & below) + __popc(nzB & below);
         __syncwarp();    // the previous step's lookups in s_run are done
+        // a run = {its first hit, record slot | tile pixel index of its first pixel << 8}
         if(LA != 0u)
-          s_run[warp][rank] = make_uint2(end - LA - LB, owner | ((uint32_t)y << 8) | ((uint32_t)(bx0 + firstA) << 13));
+          s_run[warp][rank] = make_uint2(end - LA - LB, owner | ((uint32_t)(y * VB200_TILE + bx0 + firstA) << 8));
         if(LB != 0u)
           s_run[warp][rank + (LA != 0u)] =
-              make_uint2(end - LB, owner | ((uint32_t)(y + 1) << 8) | ((uint32_t)(bx0 + firstB) << 13));
+              make_uint2(end - LB, owner | ((uint32_t)((y + 1) * VB200_TILE + bx0 + firstB) << 8));
         __syncwarp();
         // run r starts at hit s_run[r].x; lane l keeps the starts of runs l and l + 32 for the owner lookups
         const uint32_t runStart0 = (uint32_t)lane < nrec ? s_run[warp][lane].x : 0xffffffffu;
         const uint32_t runStart1 = (uint32_t)lane + 32u < nrec ? s_run[warp][lane + 32].x : 0xffffffffu;
+        // Hit h of a step that starts at hit hb belongs to run ownerBase + (number of runs that begin in
+        // (hb, h]), where ownerBase is the run that owns hb itself: run 0 for the first step (it starts at hit
+        // 0 and every run is non-empty), and for the next step the current one plus every run that begins in
+        // (hb, hb + 32]. `begins` has bit r - 1 set when a run begins at hb + r.
+        uint32_t ownerBase = 0;
         for(uint32_t hb = 0; hb < hits; hb += 32u)
         {
-          // run that owns hit hb (the last one starting at or before it), then one more per run that begins
-          // inside (hb, hb + lane]
-          const uint32_t rel0 = runStart0 - hb, rel1 = runStart1 - hb;
-          const uint32_t ownerBase = __popc(__ballot_sync(0xffffffffu, runStart0 <= hb)) +
-                                     __popc(__ballot_sync(0xffffffffu, runStart1 <= hb)) - 1u;
-          const uint32_t begins = __reduce_or_sync(0xffffffffu, ((rel0 - 1u) < 31u ? (1u << rel0) : 0u) |
-                                                                    ((rel1 - 1u) < 31u ? (1u << rel1) : 0u));
-          const uint32_t r = min(ownerBase + __popc(begins & (0xffffffffu >> (31 - lane))), 63u);
+          const uint32_t rel0 = runStart0 - hb - 1u, rel1 = runStart1 - hb - 1u;
+          const uint32_t begins =
+              __reduce_or_sync(0xffffffffu, (rel0 < 32u ? (1u << rel0) : 0u) | (rel1 < 32u ? (1u << rel1) : 0u));
+          const uint32_t r = min(ownerBase + __popc(begins & below), 63u);
+          ownerBase += __popc(begins);
           const uint2 run = s_run[warp][r];
           const uint32_t h = hb + lane;
-          const uint32_t slot16 = (run.y & 255u) * 16u;
+          const uint32_t slot16 = (run.y & (RT - 1u)) * 16u;
           const int4 t0 = vb200_lds128(aE1 + slot16), t1 = vb200_lds128(aE2 + slot16);
-          const int py = (run.y >> 8) & 31, px = (int)((run.y >> 13) + (h - run.x)) & 31;
+          const int idx = (int)((run.y >> 8) + (h - run.x)) & (VB200_TILE * VB200_TILE - 1);
+          const int px = idx & 31, py = idx >> 5;
           const int b1 = t0.x * px + t0.y * py + t0.z;
           const int b2 = t0.w * px + t1.x * py + t1.y;
           const int b0 = t1.z - (b1 + b2);
-          const int idx = py * VB200_TILE + px;
           // the slot's current key is fetched before the depth arithmetic that decides whether it is needed
           const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
           const unsigned long long seen = vb200_lds64(aSlot);
@@ -967,20 +1000,20 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __syncthreads();
 
   // ---- phase B: shade the winner of every pixel, write back. Thread (warp, lane) owns pixel column `lane`
-  // of rows warp, warp + 8, warp + 16, warp + 24.
-  const bool recordsInSmem = rs.slot_keys && n <= 256u;    // the only round's records are still staged
+  // of rows warp, warp + RW, warp + 2 RW, ...
+  const bool recordsInSmem = rs.slot_keys && n <= (uint32_t)RT;    // the only round's records are still staged
   const bool remote = p.mc_color != nullptr || p.num_peers != 0u;
   uint32_t aPw = vb200_smem_addr(s_pw), aSv = vb200_smem_addr(s_sv);
   asm volatile("" : "+r"(aPw), "+r"(aSv));
   const bool xin = tileX0 + lane < (int)rs.width;
-  const uint32_t rowStep = 8u * rs.width;    // pixel offsets fit 32 bits (targets are at most 8192 x 8192)
+  const uint32_t rowStep = (uint32_t)RW * rs.width;    // pixel offsets fit 32 bits (targets are at most 8192 x 8192)
   // `record(id, ly, y)`: the winner's barycentric numerators at the pixel and its per-triangle constants
   auto shade_rows = [&](auto record) {
     uint32_t gi = (uint32_t)(tileY0 + warp) * rs.width + (uint32_t)(tileX0 + lane);
     VB200_UNROLL(VB200_PB_UNROLL)
-    for(int j = 0; j < 4; j++, gi += rowStep)
+    for(int j = 0; j < VB200_TILE / RW; j++, gi += rowStep)
     {
-      const int ly = warp + 8 * j;
+      const int ly = warp + RW * j;
       const unsigned long long key = vb200_lds64(aVis + 8u * (uint32_t)(ly * VB200_TILE + lane));
       const uint32_t low = (uint32_t)key;
       bool won;
@@ -1043,7 +1076,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
                    float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
       // the winner's edge values at this pixel from its staged record (int32 ring arithmetic, so this and
       // the reference's formulation, rasterizer.cpp:303-309,545-558, give the same bits)
-      const uint32_t slot16 = (id & 255u) * 16u;    // slot = the thread that set the winner up
+      const uint32_t slot16 = (id & (RT - 1u)) * 16u;    // slot = the thread that set the winner up
       const int4 c0 = vb200_lds128(aE1 + slot16), c1 = vb200_lds128(aE2 + slot16), c2 = vb200_lds128(aZ + slot16),
                  c4 = vb200_lds128(aPw + slot16);
       const unsigned long long c5 = vb200_lds64(aSv + (slot16 >> 1));
@@ -1074,8 +1107,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 }
 
 #define VB200_RESOLVE_KERNEL(NAME, MODE)                                                              \
-  extern "C" __global__ void __launch_bounds__(256) NAME(const __grid_constant__ Vb200Env env,       \
-                                                         const __grid_constant__ Vb200TileParams p) \
+  extern "C" __global__ void __launch_bounds__(VB200_RESOLVE_THREADS)                                \
+      NAME(const __grid_constant__ Vb200Env env, const __grid_constant__ Vb200TileParams p)          \
   {                                                                                                   \
     vb200_tile_resolve_body<MODE>(env, p);                                                            \
   }
