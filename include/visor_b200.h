@@ -249,6 +249,33 @@ VB200_API int vb200_set_peer_targets(const void *local_color_device, void *const
  * precedence over peer targets; NULL removes the association. */
 VB200_API int vb200_set_multicast_target(const void *local_color_device, void *multicast_device);
 
+/* ---- sort-first over the GPUs of one node, one process per GPU (no framework in the data plane) ----
+ * vb200_mgpu_init joins the calling process to `session` (any string shared by the `world` <= 8 processes,
+ * e.g. the launcher's port number) as `rank`, running on CUDA device `device`: it bootstraps over abstract
+ * unix-domain sockets, calls vb200_set_tile_owner(rank, world) and sets up the device-side barrier. All
+ * vb200_mgpu_* calls below except _info and _push are COLLECTIVE: every rank makes them in the same order.
+ * vb200_mgpu_alloc returns this rank's copy of a symmetric buffer (one allocation per rank, all of them
+ * mapped into every rank; where the NVSwitch supports it also one multicast mapping). A colour target that
+ * lies in a symmetric buffer gets the fused exchange: the tile kernels store every pixel into all ranks'
+ * copies (one multimem.st, or one store per peer), so after vb200_mgpu_barrier every rank holds the image.
+ * vb200_mgpu_barrier enqueues a cross-rank barrier on the library stream (it gives up after ~2 s if a
+ * rank never arrives; the next call then reports it).
+ * vb200_mgpu_push replicates bytes [p, p + bytes) of this rank's copy of a symmetric buffer to the same
+ * range of every other rank (offset and size multiples of 16).
+ * With option "mgpu_mirrors" = 1 the HBM mirrors of ranges registered afterwards (vb200_mem_register, a
+ * collective then) are symmetric buffers: colour targets in host memory get the fused exchange,
+ * vb200_flush ends with the barrier, and vb200_mgpu_upload(host, size) uploads a frame input in slices —
+ * each rank sends 1/world of it over its own PCIe link and pushes that slice to the others over NVLink
+ * (follow the uploads of a frame with one vb200_mgpu_barrier before drawing). Depth is not exchanged. */
+VB200_API int vb200_mgpu_init(int rank, int world, int device, const char *session);
+VB200_API int vb200_mgpu_shutdown(void);
+VB200_API int vb200_mgpu_info(int *rank, int *world, int *multicast);
+VB200_API int vb200_mgpu_alloc(uint64_t bytes, void **local_device);
+VB200_API int vb200_mgpu_free(void *local_device);
+VB200_API int vb200_mgpu_barrier(void);
+VB200_API int vb200_mgpu_push(const void *local_device, uint64_t bytes);
+VB200_API int vb200_mgpu_upload(const void *host, uint64_t size);
+
 /* ---- introspection ----------------------------------------------------------------------- */
 
 typedef struct vb200_stats { /* counters of the reference (rasterizer.cpp:517-519,693-695) + timing */
@@ -281,7 +308,9 @@ VB200_API int vb200_abi_version(void);
 VB200_API const char *vb200_last_tile_kernel(void);
 /* Tuning/debug knobs by name ("raster_path": 0 auto, 1 ordered tiles; "count_fragments": 0/1,
  * "time_kernels": 0/1, "fuse_clears": 0/1, "slot_keys": 0/1 — 0 forces the resolve kernels' code path of
- * draws with 2^24 or more triangles). "extended_spirv": 1 makes later vb200_shader_create calls
+ * draws with 2^24 or more triangles; "tile_list_cap": entries per tile list, 0 = automatic — a tiny value
+ * forces the tile kernels' fallback for overflowed lists; "mgpu_mirrors": see vb200_mgpu_init).
+ * "extended_spirv": 1 makes later vb200_shader_create calls
  * accept a few opcodes the reference asserts on (OpSelect, OpFOrdGreaterThanEqual, OpFOrdEqual,
  * OpFOrdNotEqual, OpISub, OpBitcast, OpConvertFToS, GLSL FAbs/Floor/Fract) — off by default, because
  * with it the front end no longer rejects exactly what CompileFunction rejects (spirv_compile.cpp:1734,

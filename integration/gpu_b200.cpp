@@ -44,9 +44,30 @@ static void toImage(const VkImage_T *in, vb200_image &out)
 }
 
 // ---- spirv_compile.h -------------------------------------------------------------------------
+// Which GPU, and whether this process is one rank of a sort-first group, comes from the environment the way
+// launchers (torchrun, mpirun, a shell loop) already provide it:
+//   VISOR_B200_DEVICE, else LOCAL_RANK      CUDA device of this process (default 0)
+//   VISOR_B200_SESSION + RANK + WORLD_SIZE  join a sort-first group of WORLD_SIZE processes running the same
+//                                           application: screen tiles are split across the ranks, every rank's
+//                                           framebuffer memory receives the whole image at vkQueueSubmit
+static int envInt(const char *name, int fallback)
+{
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : fallback;
+}
+
 void InitLLVM()
 {
-  if(vb200_init(0) != VB200_OK)
+  const int device = envInt("VISOR_B200_DEVICE", envInt("LOCAL_RANK", 0));
+  const char *session = getenv("VISOR_B200_SESSION");
+  const int world = envInt("WORLD_SIZE", 1);
+  if(session && *session && world > 1)
+  {
+    if(vb200_mgpu_init(envInt("RANK", 0), world, device, session) != VB200_OK ||
+       vb200_set_option("mgpu_mirrors", 1) != VB200_OK)
+      reportError("vb200_mgpu_init");
+  }
+  else if(vb200_init(device) != VB200_OK)
     reportError("vb200_init");
 }
 

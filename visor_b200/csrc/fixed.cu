@@ -505,6 +505,55 @@ __global__ void __launch_bounds__(kThreads) k_tiles_unpack(uint32_t *color, uint
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K7: sort-first plumbing between the GPUs of one node (no reference equivalent)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_mgpu_barrier(const Vb200PeerSet flags, uint32_t rank, uint32_t world,
+                                                    uint32_t epoch, uint32_t *timed_out)
+{
+  const uint32_t p = threadIdx.x;
+  if(p >= world)
+    return;
+  // everything this GPU wrote before (earlier kernels of the stream, including their stores into peer and
+  // multicast mappings) is ordered before the flag
+  __threadfence_system();
+  volatile uint32_t *theirs = (volatile uint32_t *)flags.peer[p] + rank;
+  *theirs = epoch;
+  __threadfence_system();
+  volatile uint32_t *mine = (volatile uint32_t *)flags.peer[rank] + p;
+  const long long t0 = clock64();
+  while((int32_t)(*mine - epoch) < 0)
+  {
+    if(clock64() - t0 > 4000000000ll)    // ~2 s at 2 GHz
+    {
+      *timed_out = 1u;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(kThreads) k_mgpu_push(const Vb200PeerSet bufs, uint4 *multicast, uint32_t rank,
+                                                       uint32_t world, size_t first16, size_t count16)
+{
+  const uint4 *src = (const uint4 *)bufs.peer[rank] + first16;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count16; i += stride)
+  {
+    const uint4 v = src[i];
+    if(multicast)
+      asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(multicast + first16 + i),
+                   "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                   "f"(__uint_as_float(v.w))
+                   : "memory");
+    else
+      for(uint32_t r = 0; r < world; r++)
+        if(r != rank)
+          ((uint4 *)bufs.peer[r])[first16 + i] = v;
+  }
+}
+
 int sm_count()
 {
   static int n = 0;
@@ -590,6 +639,23 @@ int launch_tiles_pack(const uint32_t *color, uint32_t width, uint32_t height, ui
   const uint32_t ntiles = tiles_x * tiles_y;
   const uint32_t slots = (ntiles + world - 1) / world;
   k_tiles_pack<<<slots, kThreads, 0, s>>>(color, width, height, tiles_x, ntiles, rank, world, dst);
+  return 1;
+}
+
+int launch_mgpu_barrier(const Vb200PeerSet &flags, uint32_t rank, uint32_t world, uint32_t epoch, uint32_t *timed_out,
+                        cudaStream_t s)
+{
+  k_mgpu_barrier<<<1, 32, 0, s>>>(flags, rank, world, epoch, timed_out);
+  return 1;
+}
+
+int launch_mgpu_push(const Vb200PeerSet &bufs, void *multicast, uint32_t rank, uint32_t world, uint64_t offset,
+                     uint64_t bytes, cudaStream_t s)
+{
+  if(!bytes)
+    return 0;
+  // callers pass 16-byte aligned ranges (slices of mirrors are cut at multiples of 16)
+  k_mgpu_push<<<grid_for(bytes / 16, 4), kThreads, 0, s>>>(bufs, (uint4 *)multicast, rank, world, offset / 16, bytes / 16);
   return 1;
 }
 

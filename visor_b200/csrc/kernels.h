@@ -90,4 +90,19 @@ int launch_tiles_pack(const uint32_t *color, uint32_t width, uint32_t height, ui
                       uint32_t *dst, cudaStream_t s);
 int launch_tiles_unpack(uint32_t *color, uint32_t width, uint32_t height, uint32_t world, uint32_t slots_per_rank,
                         const uint32_t *src, cudaStream_t s);
+// sort-first multi-GPU plumbing (mgpu.cpp). Every rank holds the same symmetric buffers; peer[r] is rank r's copy
+// mapped into this GPU's address space (peer[own rank] = the local copy).
+struct Vb200PeerSet
+{
+  void *peer[8];
+};
+// cross-rank barrier on the stream: every rank writes `epoch` into slot `rank` of every rank's flag array, then
+// waits until its own array shows `epoch` in every slot. Gives up after ~2 s and raises *timed_out (a peer that
+// never arrives must not hang the GPU).
+int launch_mgpu_barrier(const Vb200PeerSet &flags, uint32_t rank, uint32_t world, uint32_t epoch, uint32_t *timed_out,
+                        cudaStream_t s);
+// copy bytes [offset, offset + bytes) of the local copy of a symmetric buffer to the same range on every other rank:
+// one multicast store per 16 bytes when `multicast` (an NVSwitch mapping of the buffer) is given, else one store per peer
+int launch_mgpu_push(const Vb200PeerSet &bufs, void *multicast, uint32_t rank, uint32_t world, uint64_t offset,
+                     uint64_t bytes, cudaStream_t s);
 }    // namespace vb200

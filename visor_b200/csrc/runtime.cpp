@@ -25,6 +25,7 @@
 #include "../../include/visor_b200.h"
 #include "device_types.h"
 #include "kernels.h"
+#include "runtime_internal.h"
 #include "spirv_ptx.h"
 
 extern "C" const char vb200_scaffold_ptx[];
@@ -228,9 +229,17 @@ struct Context
   int64_t optFuseClears = 1;
   int64_t optSlotKeys = 1;    // 0: never put the record slot into the visibility key (the path of draws >= 2^24 triangles)
   int64_t optTileListCap = 0; // > 0: entries per tile list (testing aid: a tiny value forces the tile kernels' fallback scan)
-  // fused sort-first exchange: colour target (device address on this rank) -> the same image on the peers
-  std::map<uint8_t *, std::vector<uint32_t *>> peerTargets;
-  std::map<uint8_t *, uint32_t *> multicastTargets;
+  // fused sort-first exchange: a device range on this rank that holds colour targets -> the same range on the
+  // peers (mapped here) and/or an NVSwitch multicast mapping of it
+  struct ExchangeRange
+  {
+    size_t bytes = 0;
+    bool exact = false;    // caller-managed association (vb200_set_peer_targets): only a target that starts here
+    std::vector<uint8_t *> peers;
+    uint8_t *multicast = nullptr;
+  };
+  std::map<uint8_t *, ExchangeRange> exchange;
+  int64_t optMgpuMirrors = 0;    // mirrors of registered host ranges are symmetric buffers (collective registration)
   Vb200DrawCounters *counters = nullptr;    // device
   float *unorm = nullptr;                   // device: float(i) / 255.0f for every byte value
   const char *lastTileKernel = "";
@@ -306,6 +315,16 @@ int requireReady()
   return VB200_OK;
 }
 
+void freeMirrorMemory(uint8_t *dev)
+{
+  if(!dev)
+    return;
+  if(vb200::mgpu_is_symmetric(dev))
+    vb200::mgpu_sym_free(dev);
+  else
+    cudaFree(dev);
+}
+
 bool isDevicePointer(const void *p)
 {
   cudaPointerAttributes a;
@@ -351,10 +370,20 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
   Mirror nm;
   nm.host = (uint8_t *)lo;
   nm.size = hi - lo;
-  CU(cudaMalloc((void **)&nm.dev, std::max<size_t>(nm.size + 16, 256)));
+  const size_t devBytes = std::max<size_t>(nm.size + 16, 256);
+  if(pin && g.optMgpuMirrors && vb200::mgpu_active())
+  {
+    // sort-first mode: the mirror of a registered range is a symmetric buffer (same allocation on every rank,
+    // all of them mapped here), so that colour targets inside it get the fused exchange and inputs can be
+    // uploaded in slices. Collective: every rank registers the same ranges in the same order.
+    if(int arc = vb200::mgpu_sym_alloc(devBytes, &nm.dev))
+      return arc;
+  }
+  else
+    CU(cudaMalloc((void **)&nm.dev, devBytes));
   // 16 bytes of slack behind every mirror, zeroed: texel fetches of formats narrower than 4 bytes read 4 bytes
   // per texel and may look up to 3 bytes past the end of an image that ends the mirror
-  CU(cudaMemsetAsync(nm.dev + nm.size, 0, std::max<size_t>(nm.size + 16, 256) - nm.size, g.stream));
+  CU(cudaMemsetAsync(nm.dev + nm.size, 0, devBytes - nm.size, g.stream));
   for(uintptr_t key : victims)
   {
     Mirror &old = g.mirrors[key];
@@ -865,6 +894,44 @@ int checkTarget(const vb200_image *im, const char *what)
 }
 }    // namespace
 
+namespace vb200
+{
+int set_error(int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+cudaStream_t library_stream()
+{
+  return g.ready ? g.stream : nullptr;
+}
+int library_device()
+{
+  return g.device;
+}
+void count_launches(int n)
+{
+  g.stats.kernel_launches += (uint64_t)n;
+}
+void set_exchange_range(uint8_t *local, size_t bytes, const std::vector<uint8_t *> &peers, uint8_t *multicast)
+{
+  Context::ExchangeRange &r = g.exchange[local];
+  r.bytes = bytes;
+  r.exact = false;
+  r.peers = peers;
+  r.multicast = multicast;
+}
+void clear_exchange_range(uint8_t *local)
+{
+  g.exchange.erase(local);
+}
+}    // namespace vb200
+
 // =================================================================================================
 extern "C" {
 
@@ -929,7 +996,7 @@ void vb200_shutdown(void)
   {
     if(kv.second.pinned)
       cudaHostUnregister(kv.second.host);
-    cudaFree(kv.second.dev);
+    freeMirrorMemory(kv.second.dev);
   }
   g.mirrors.clear();
   g.rv.release();
@@ -1142,7 +1209,7 @@ int vb200_mem_unregister(void *host)
                                                                                          : std::next(pc);
   if(it->second.pinned)
     cudaHostUnregister(it->second.host);
-  cudaFree(it->second.dev);
+  freeMirrorMemory(it->second.dev);
   g.mirrors.erase(it);
   return VB200_OK;
 }
@@ -1164,6 +1231,40 @@ int vb200_mem_upload(const void *host, uint64_t size)
   const size_t off = (uintptr_t)host - (uintptr_t)m->host;
   CU(cudaMemcpyAsync(m->dev + off, host, size, cudaMemcpyHostToDevice, g.stream));
   g.stats.h2d_bytes += size;
+  return VB200_OK;
+}
+
+int vb200_mgpu_upload(const void *host, uint64_t size)
+{
+  int rc = requireReady();
+  if(rc)
+    return rc;
+  int rank = 0, world = 1;
+  vb200_mgpu_info(&rank, &world, nullptr);
+  Mirror *m = findMirror(host, size);
+  if(world <= 1 || !m || !vb200::mgpu_is_symmetric(m->dev))
+    return setError(VB200_ERR_INVALID, "mgpu_upload: the range is not mirrored in a symmetric buffer "
+                                       "(vb200_mgpu_init, option mgpu_mirrors, vb200_mem_register)");
+  const size_t off = (uintptr_t)host - (uintptr_t)m->host;
+  if(off & 15)
+    return setError(VB200_ERR_INVALID, "mgpu_upload: the range must start 16-byte aligned inside its registration");
+  // every rank sends 1/world of the bytes over ITS PCIe link and replicates that slice to the other ranks over
+  // NVLink; the few bytes left over by the division are uploaded by everybody
+  const size_t slice = (size / (size_t)world) & ~(size_t)15;
+  const uint8_t *src = (const uint8_t *)host;
+  if(slice)
+  {
+    CU(cudaMemcpyAsync(m->dev + off + rank * slice, src + rank * slice, slice, cudaMemcpyHostToDevice, g.stream));
+    g.stats.h2d_bytes += slice;
+    if((rc = vb200_mgpu_push(m->dev + off + rank * slice, slice)))
+      return rc;
+  }
+  const size_t done = slice * (size_t)world;
+  if(done < size)
+  {
+    CU(cudaMemcpyAsync(m->dev + off + done, src + done, size - done, cudaMemcpyHostToDevice, g.stream));
+    g.stats.h2d_bytes += size - done;
+  }
   return VB200_OK;
 }
 
@@ -1366,6 +1467,13 @@ int vb200_flush(void)
     if((rc = materializeClears(it->first, it->second.count * 4)))
       return rc;
   }
+  if(g.optMgpuMirrors && vb200::mgpu_active())
+  {
+    // sort-first with symmetric mirrors (the ICD's mode): every rank's tile kernels have stored their pixels
+    // into all ranks' colour targets; one cross-rank barrier and every rank holds, and downloads, the whole image
+    if((rc = vb200_mgpu_barrier()))
+      return rc;
+  }
   if(g.syncMode == VB200_SYNC_COHERENT)
   {
     for(auto &kv : g.mirrors)
@@ -1377,6 +1485,12 @@ int vb200_flush(void)
         g.stats.d2h_bytes += w.second - w.first;
       }
     }
+  }
+  if(g.optMgpuMirrors && vb200::mgpu_active())
+  {
+    // ... and nobody starts storing the next frame into a peer that is still copying this one out
+    if((rc = vb200_mgpu_barrier()))
+      return rc;
   }
   CU(cudaStreamSynchronize(g.stream));
   if(g.activePresents)
@@ -1393,7 +1507,7 @@ int vb200_flush(void)
     return setError(VB200_ERR_CUDA, "asynchronous CUDA error: %s", cudaGetErrorString(e));
   }
   for(uint8_t *z : g.zombies)
-    cudaFree(z);
+    freeMirrorMemory(z);
   g.zombies.clear();
   // new epoch: host memory is authoritative again
   size_t autoBytes = 0;
@@ -1412,7 +1526,7 @@ int vb200_flush(void)
     {
       if(!it->second.explicitReg && it->second.lastUse + 4 < g.epoch)
       {
-        cudaFree(it->second.dev);
+        freeMirrorMemory(it->second.dev);
         it = g.mirrors.erase(it);
       }
       else
@@ -1797,16 +1911,24 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.clear_flags = clearFlags;
   tp.clear_color = clearColorWord;
   tp.clear_depth = clearDepthValue;
+  if(g.ownerWorld > 1)
   {
-    auto mc = g.multicastTargets.find(colorDev);
-    auto pt = g.peerTargets.find(colorDev);
-    if(mc != g.multicastTargets.end() && g.ownerWorld > 1)
-      tp.mc_color = mc->second;
-    else if(pt != g.peerTargets.end() && g.ownerWorld > 1)
+    auto it = g.exchange.upper_bound(colorDev);
+    if(it != g.exchange.begin())
     {
-      tp.num_peers = (uint32_t)pt->second.size();
-      for(uint32_t r = 0; r < tp.num_peers; r++)
-        tp.peer_color[r] = pt->second[r];
+      --it;
+      const size_t off = (size_t)(colorDev - it->first);
+      if(it->second.exact ? off == 0 : off + (size_t)W * H * 4 <= it->second.bytes)
+      {
+        if(it->second.multicast)
+          tp.mc_color = (uint32_t *)(it->second.multicast + off);
+        else
+        {
+          tp.num_peers = (uint32_t)std::min<size_t>(it->second.peers.size(), 7);
+          for(uint32_t r = 0; r < tp.num_peers; r++)
+            tp.peer_color[r] = (uint32_t *)(it->second.peers[r] + off);
+        }
+      }
     }
   }
 
@@ -1882,19 +2004,28 @@ int vb200_set_peer_targets(const void *local_color_device, void *const *peer_col
 {
   if(!local_color_device || num_peers < 0 || num_peers > 7 || (num_peers && !peer_color_device))
     return setError(VB200_ERR_INVALID, "set_peer_targets: bad arguments (at most 7 peers)");
+  uint8_t *local = (uint8_t *)local_color_device;
   if(num_peers == 0)
   {
-    g.peerTargets.erase((uint8_t *)local_color_device);
+    auto it = g.exchange.find(local);
+    if(it != g.exchange.end())
+    {
+      it->second.peers.clear();
+      if(!it->second.multicast)
+        g.exchange.erase(it);
+    }
     return VB200_OK;
   }
-  std::vector<uint32_t *> v;
+  std::vector<uint8_t *> v;
   for(int i = 0; i < num_peers; i++)
   {
     if(!peer_color_device[i])
       return setError(VB200_ERR_INVALID, "set_peer_targets: NULL peer pointer");
-    v.push_back((uint32_t *)peer_color_device[i]);
+    v.push_back((uint8_t *)peer_color_device[i]);
   }
-  g.peerTargets[(uint8_t *)local_color_device] = v;
+  Context::ExchangeRange &r = g.exchange[local];
+  r.exact = true;
+  r.peers = v;
   return VB200_OK;
 }
 
@@ -1902,10 +2033,21 @@ int vb200_set_multicast_target(const void *local_color_device, void *multicast_d
 {
   if(!local_color_device)
     return setError(VB200_ERR_INVALID, "set_multicast_target: NULL image");
+  uint8_t *local = (uint8_t *)local_color_device;
   if(!multicast_device)
-    g.multicastTargets.erase((uint8_t *)local_color_device);
-  else
-    g.multicastTargets[(uint8_t *)local_color_device] = (uint32_t *)multicast_device;
+  {
+    auto it = g.exchange.find(local);
+    if(it != g.exchange.end())
+    {
+      it->second.multicast = nullptr;
+      if(it->second.peers.empty())
+        g.exchange.erase(it);
+    }
+    return VB200_OK;
+  }
+  Context::ExchangeRange &r = g.exchange[local];
+  r.exact = true;
+  r.multicast = (uint8_t *)multicast_device;
   return VB200_OK;
 }
 
@@ -2053,6 +2195,8 @@ int vb200_set_option(const char *name, int64_t value)
     g.optSlotKeys = value;
   else if(!strcmp(name, "tile_list_cap"))
     g.optTileListCap = value;
+  else if(!strcmp(name, "mgpu_mirrors"))
+    g.optMgpuMirrors = value;
   else if(!strcmp(name, "extended_spirv"))
     vb200::set_extended_spirv(value != 0);
   else if(!strcmp(name, "time_kernels"))
