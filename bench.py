@@ -320,30 +320,32 @@ def run_ours(args, workload: str) -> None:
     npx = scene.width * scene.height
     fused = multicast = False
     if multi:
-        gpu.check(L.vb200_set_tile_owner(rank, world), "set_tile_owner")
         ext = torch.cuda.ExternalStream(L.vb200_stream())
-        L.vb200_set_peer_targets.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+        L.vb200_mgpu_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.vb200_mgpu_info.argtypes = [C.POINTER(C.c_int)] * 3
+        L.vb200_mgpu_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+        L.vb200_mgpu_upload.argtypes = [C.c_void_p, C.c_uint64]
         if args.exchange in ("fused", "fused-p2p"):
-            try:
-                import torch.distributed._symmetric_memory as symm
-                color_t = symm.empty(npx, dtype=torch.int32, device="cuda")
-                hdl = symm.rendezvous(color_t, dist.group.WORLD)
-                peers = [int(hdl.buffer_ptrs[r]) for r in range(world) if r != rank]
-                arr = (C.c_void_p * len(peers))(*peers)
-                gpu.check(L.vb200_set_peer_targets(color_t.data_ptr(), arr, len(peers)), "set_peer_targets")
-                fused = True
-                mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
-                if mc_ptr and args.exchange != "fused-p2p":
-                    L.vb200_set_multicast_target.argtypes = [C.c_void_p, C.c_void_p]
-                    gpu.check(L.vb200_set_multicast_target(color_t.data_ptr(), mc_ptr), "set_multicast_target")
-                    multicast = True
-            except Exception as e:  # symmetric memory unavailable: NCCL all-gather baseline
-                if rank == 0:
-                    print(f"bench: fused exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
-        if not fused:
+            # the product's own multi-GPU layer: bootstrap, symmetric colour image (NVSwitch multicast mapping
+            # where available), device-side barrier, sliced input upload. torch.distributed above serves the
+            # harness only (timing all-reduce, the NCCL all-gather baseline).
+            if args.exchange == "fused-p2p":
+                os.environ["VB200_MGPU_NO_MULTICAST"] = "1"
+            session = "bench" + os.environ.get("MASTER_PORT", "0")
+            gpu.check(L.vb200_mgpu_init(rank, world, local, session.encode()), "mgpu_init")
+            mc = C.c_int()
+            L.vb200_mgpu_info(None, None, C.byref(mc))
+            fused, multicast = True, bool(mc.value)
+            gpu.check(L.vb200_set_option(b"mgpu_mirrors", 1), "set_option")    # inputs: symmetric mirrors
+            cptr, dptr = C.c_void_p(), C.c_void_p()
+            gpu.check(L.vb200_mgpu_alloc(npx * 4, C.byref(cptr)), "mgpu_alloc")
+            color_ptr = cptr.value
+        else:
+            gpu.check(L.vb200_set_tile_owner(rank, world), "set_tile_owner")
             color_t = torch.empty(npx, dtype=torch.int32, device="cuda")
+            color_ptr = color_t.data_ptr()
         depth_t = torch.empty(npx, dtype=torch.float32, device="cuda")
-        bound = scenes.BoundScene(gpu, scene, color_device_ptr=color_t.data_ptr(), depth_device_ptr=depth_t.data_ptr())
+        bound = scenes.BoundScene(gpu, scene, color_device_ptr=color_ptr, depth_device_ptr=depth_t.data_ptr())
         if not fused:
             slots = L.vb200_tiles_per_rank(scene.width, scene.height, world)
             send = torch.empty(slots * 4096, dtype=torch.uint8, device="cuda")
@@ -362,14 +364,14 @@ def run_ours(args, workload: str) -> None:
         """sort-first assemble on the library stream. fused: the tile kernels already stored every pixel
         into all ranks' images over NVLink, only a cross-rank barrier is left. all-gather: owned colour
         tiles -> NCCL all-gather -> un-tile."""
+        if fused:
+            gpu.check(L.vb200_mgpu_barrier(), "mgpu_barrier")
+            return
         with torch.cuda.stream(ext):
-            if fused:
-                hdl.barrier()
-            else:
-                gpu.check(L.vb200_tiles_pack(C.byref(bound.color_img), send.data_ptr(), send.numel()), "tiles_pack")
-                dist.all_gather_into_tensor(recv, send)
-                gpu.check(L.vb200_tiles_unpack(C.byref(bound.color_img), recv.data_ptr(), recv.numel(), world),
-                          "tiles_unpack")
+            gpu.check(L.vb200_tiles_pack(C.byref(bound.color_img), send.data_ptr(), send.numel()), "tiles_pack")
+            dist.all_gather_into_tensor(recv, send)
+            gpu.check(L.vb200_tiles_unpack(C.byref(bound.color_img), recv.data_ptr(), recv.numel(), world),
+                      "tiles_unpack")
 
     def barrier():
         gpu.flush()
@@ -445,27 +447,14 @@ def run_ours(args, workload: str) -> None:
         gpu.check(L.vb200_set_sync_mode(0), "set_sync_mode")
     else:
         # N>1: host<->device traffic is sharded like the frame. Every rank uploads 1/N of each input over
-        # ITS PCIe link and the slices are all-gathered into the HBM mirrors over NVLink (NCCL, in place);
-        # after the exchange every rank holds the whole image and copies its band of rows into one
-        # host buffer shared by all ranks (POSIX shared memory, page-locked in every process).
+        # ITS PCIe link and the slices are replicated into all ranks' HBM mirrors over NVLink (the product's
+        # vb200_mgpu_upload; NCCL all-gather in the baseline mode); after the exchange every rank holds the whole
+        # image and copies its band of rows into one host buffer shared by all ranks (POSIX shared memory,
+        # page-locked in every process).
         from multiprocessing import shared_memory
 
-        class _DevBytes:    # raw device range -> torch tensor (no copy)
-            def __init__(self, ptr, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
-                                                 "version": 2}
-
-        shards = []    # (host array, slice bytes, gathered device tensor, own slice view)
-        for a, is_in in bufs:
-            if not is_in:
-                continue
-            sl, _tail = tiles.upload_shard(a.nbytes, world)
-            if sl == 0:
-                shards.append((a, 0, None, None))
-                continue
-            dev = L.vb200_mem_device_ptr(a.ctypes.data)
-            full = torch.as_tensor(_DevBytes(dev, sl * world), device="cuda")
-            shards.append((a, sl, full, full[rank * sl:(rank + 1) * sl]))
+        inputs = [a for a, is_in in bufs if is_in]
+        h2d_job = sum(a.nbytes for a in inputs)
         shm_name = f"vb200_bench_{os.environ.get('MASTER_PORT', '0')}"
         if rank == 0:
             shm = shared_memory.SharedMemory(name=shm_name, create=True, size=npx * 4)
@@ -478,15 +467,52 @@ def run_ours(args, workload: str) -> None:
             except Exception:
                 pass
         frame_host = np.ndarray((npx,), dtype=np.int32, buffer=shm.buf)
+        if fused:
+            gpu.check(L.vb200_set_option(b"mgpu_mirrors", 0), "set_option")    # page-locking only, no mirror needed
         gpu.check(L.vb200_mem_register(frame_host.ctypes.data, frame_host.nbytes), "mem_register(shared frame)")
         lo, hi = tiles.row_band(scene.height, rank, world)
         band = slice(lo * scene.width, hi * scene.width)
-        band_host = torch.from_numpy(frame_host[band])
-        h2d_job = sum(a.nbytes for a, _, _, _ in shards)
+        band_bytes = (hi - lo) * scene.width * 4
+        if fused:
+            # this rank's band of the finished image, as an image of its own for vb200_present
+            band_img = abi.Image.from_buffer_copy(bound.color_img)
+            band_img.pixels = color_ptr + lo * scene.width * 4
+            band_img.height = hi - lo
+            L.vb200_present.argtypes = [C.POINTER(abi.Image), C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]
+        else:
+            class _DevBytes:    # raw device range -> torch tensor (no copy)
+                def __init__(self, ptr, nbytes):
+                    self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                                     "version": 2}
+
+            shards = []    # (host array, slice bytes, gathered device tensor, own slice view)
+            for a in inputs:
+                sl, _tail = tiles.upload_shard(a.nbytes, world)
+                if sl == 0:
+                    shards.append((a, 0, None, None))
+                    continue
+                dev = L.vb200_mem_device_ptr(a.ctypes.data)
+                full = torch.as_tensor(_DevBytes(dev, sl * world), device="cuda")
+                shards.append((a, sl, full, full[rank * sl:(rank + 1) * sl]))
+            band_host = torch.from_numpy(frame_host[band])
 
     def step_e2e():
         """one frame as an application sees it: inputs come from host memory, the finished frame ends
         up in host memory."""
+        if multi and fused:
+            # every rank sends 1/N of each input over its own PCIe link and replicates the slice to the other
+            # ranks over NVLink (vb200_mgpu_upload); one barrier later all mirrors are complete — and every
+            # rank has finished copying out the previous frame, so the tile kernels may store into peers again
+            for a in inputs:
+                gpu.check(L.vb200_mgpu_upload(a.ctypes.data, a.nbytes), "mgpu_upload")
+            gpu.check(L.vb200_mgpu_barrier(), "mgpu_barrier")
+            bound.submit()
+            exchange()
+            t = C.c_int()
+            gpu.check(L.vb200_present(C.byref(band_img), frame_host.ctypes.data + lo * scene.width * 4, band_bytes,
+                                      C.byref(t)), "present")
+            gpu.flush()
+            return
         if multi:
             for a, sl, full, mine in shards:
                 if sl == 0:
@@ -539,7 +565,9 @@ def run_ours(args, workload: str) -> None:
             gpu.flush()
         L.vb200_mem_unregister.argtypes = [C.c_void_p]
         L.vb200_mem_unregister(frame_host.ctypes.data)
-        del band_host, frame_host
+        if not fused:
+            del band_host
+        del frame_host
         dist.barrier()
         shm.close()
         if rank == 0:
@@ -674,12 +702,15 @@ def run_ours(args, workload: str) -> None:
         "fragments": {"covered": st["fragments_covered"], "shaded": st["fragments_shaded"],
                       "triangles_out": st["triangles_out"], "tile_pairs": st["tile_pairs"]},
         "phase_ms": phase,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((workload, world, tile_kernel)),
+        # N > 1: `achieved` is the whole job's (all ranks' tile kernels together write the frame once), so the
+        # fraction is taken against the N GPUs' combined peak
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "n_gpus": world,
+                     "frac": achieved / (peak * world), "traffic": NCU_TRAFFIC.get((workload, world, tile_kernel)),
                      "traffic_source": NCU_TRAFFIC_SOURCE if (workload, world, tile_kernel) in NCU_TRAFFIC else None,
                      "kernel": tile_kernel,
                      "algorithmic_bytes": tile_bytes, "kernel_ms": tiles_ms, "peak_source": peak_src,
-                     "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_gbs, "frac": frame_gbs / peak},
+                     "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_gbs,
+                               "frac": frame_gbs / (peak * world)},
                      "issue": issue_info},
         "e2e": {"value": tris / t_e2e / 1e6, "unit": "Mtri/s", "ms_per_step": t_e2e * 1e3,
                 "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps, "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
