@@ -10,6 +10,7 @@
 //                                 sort by triangle id for the in-order path)
 //   K5' stand-alone sampler       sample_tex_wrapped/_cube_wrapped texture_sampling.cpp:139-250
 //   K6  tile pack / unpack        (sort-first multi-GPU; no reference equivalent)
+#include <stdlib.h>
 #include <algorithm>
 #include "kernels.h"
 #include "raster_common.cuh"
@@ -133,8 +134,7 @@ __device__ __forceinline__ bool tile_owned(uint32_t tile, uint32_t rank, uint32_
 // Each thread sets up kSetupPerThread triangles, phase by phase, so that the index loads of all of them,
 // then the vertex gathers of all of them, then the returning cursor atomics of all of them are in flight
 // together (the kernel is a chain of three dependent memory operations per triangle and little else).
-constexpr int kSetupPerThread = 2;
-
+template <int kSetupPerThread>
 __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
 {
   uint32_t t[kSetupPerThread], s0[kSetupPerThread], s1[kSetupPerThread], s2[kSetupPerThread];
@@ -145,9 +145,10 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
   // ranges above 2x2 tiles are queued here and walked by the whole CTA (a full-screen triangle covers
   // thousands of tiles: one thread appending to all of them would take tens of microseconds)
   __shared__ uint32_t s_big[kThreads * kSetupPerThread][2];
-  __shared__ uint32_t s_nbig, s_pairs;
+  __shared__ uint32_t s_nbig;
   if(threadIdx.x == 0)
-    s_nbig = s_pairs = 0;    // visible after the first __syncthreads_count below
+    s_nbig = 0;
+  __syncthreads();
 
   // ---- 1. triangle assembly (rasterizer.cpp:128-232): list = (3t, 3t+1, 3t+2); strip alternates
   // (t, t+1, t+2) / (t+1, t, t+2) to preserve winding; GetIndex (:100-119)
@@ -222,9 +223,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
       else if(flipped < 0 && (p.cull_mode & 2u))
         alive[k] = false;
     }
-    // statistics: one atomic per CTA on a spread counter (a per-warp atomic on ONE word costs ~20 us per
-    // million triangles: same-address atomics serialise in L2)
-    survivors += (uint32_t)__syncthreads_count(alive[k]);
+    survivors += alive[k] ? 1u : 0u;
     if(alive[k])
     {
       const int minx = max(0, min(va[k].x, min(vb[k].x, vc[k].x)));
@@ -334,17 +333,17 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
       }
     }
   }
+  // statistics: one atomic pair per warp on counters spread over 32 slots (per-warp atomics on ONE word cost
+  // ~20 us per million triangles: same-address atomics serialise in L2)
   mypairs = __reduce_add_sync(0xffffffffu, mypairs);
-  if(lane == 0 && mypairs)
-    atomicAdd(&s_pairs, mypairs);
-  __syncthreads();
-  if(threadIdx.x == 0)
+  survivors = __reduce_add_sync(0xffffffffu, survivors);
+  if(lane == 0)
   {
-    Vb200DrawCounters::Slot &c = p.counters->slot[blockIdx.x & (VB200_COUNTER_SLOTS - 1)];
+    Vb200DrawCounters::Slot &c = p.counters->slot[(blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) & (VB200_COUNTER_SLOTS - 1)];
     if(survivors)
       atomicAdd(&c.triangles_out, (unsigned long long)survivors);
-    if(s_pairs)
-      atomicAdd(&c.tile_pairs, (unsigned long long)s_pairs);
+    if(mypairs)
+      atomicAdd(&c.tile_pairs, (unsigned long long)mypairs);
   }
 }
 
@@ -610,8 +609,17 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
 {
   if(!p.num_tris)
     return 0;
-  const uint32_t per_cta = kThreads * kSetupPerThread;
-  k_setup<<<(p.num_tris + per_cta - 1) / per_cta, kThreads, 0, s>>>(p);
+  // triangles per thread: 2 (default) or 4 (VB200_SETUP_PER_THREAD, tuning aid)
+  static const int perThread = []() {
+    const char *e = getenv("VB200_SETUP_PER_THREAD");
+    return e && atoi(e) == 4 ? 4 : 2;
+  }();
+  const uint32_t per_cta = kThreads * (uint32_t)perThread;
+  const uint32_t grid = (p.num_tris + per_cta - 1) / per_cta;
+  if(perThread == 4)
+    k_setup<4><<<grid, kThreads, 0, s>>>(p);
+  else
+    k_setup<2><<<grid, kThreads, 0, s>>>(p);
   return 1;
 }
 
