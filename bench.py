@@ -102,18 +102,22 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant (tile) kernel, from the
 # `ncu --set full` captures summarised under profiles/ (a profiler cannot run inside the timed bench, so
 # the per-launch figure of the same build and workload is recorded here; null when none was captured).
-NCU_TRAFFIC_SOURCE = "profiles/r01_ncu_c3_kernels.txt, profiles/r01_ncu_c4_tile_ordered.txt (ncu --set full, per launch)"
+NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_c{2,3,4,5}_kernels.txt (ncu --set full, per launch)"
 NCU_TRAFFIC = {
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 26701000 + 12613000,
-    ("c4", 1, "vb200_k_tile_ordered"): 34481000 + 559104,
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): 400640 + 0,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 27101000 + 12592000,
+    ("c4", 1, "vb200_k_tile_ordered"): 34586000 + 311808,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 148528000 + 209909000,
 }
 
 
 # warp instructions one launch of the tile kernel executes (ncu smsp__inst_executed.sum, same captures): the
 # kernel is bound by instruction issue, not by HBM, so the bench also reports its issue-slot utilisation
 NCU_WARP_INSTRUCTIONS = {
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 124.32e6,
-    ("c4", 1, "vb200_k_tile_ordered"): 297.15e6,
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): 10.30e6,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 96.75e6,
+    ("c4", 1, "vb200_k_tile_ordered"): 305.96e6,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 668.41e6,
 }
 
 

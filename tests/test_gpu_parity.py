@@ -14,19 +14,15 @@ from harness import abi, scenes
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "ordered", "binned"], autouse=True)
+@pytest.fixture(params=["auto", "ordered"], autouse=True)
 def raster_path(request, gpu):
-    """Every scene runs through all raster back ends: "auto" picks the visibility-resolve kernel when the
-    pass is order independent (small triangles then take the direct visibility path of the setup kernel),
-    "binned" is the same with every triangle binned (direct path off), "ordered" forces the in-order kernel
-    (exact for any state)."""
+    """Every scene runs through both tile back ends: "auto" picks the visibility-resolve kernel when the
+    pass is order independent, "ordered" forces the in-order kernel (exact for any state)."""
     import ctypes as C
     gpu.lib.vb200_set_option.argtypes = [C.c_char_p, C.c_int64]
     assert gpu.lib.vb200_set_option(b"raster_path", 1 if request.param == "ordered" else 0) == 0
-    assert gpu.lib.vb200_set_option(b"direct_visibility", 0 if request.param == "binned" else 1) == 0
     yield request.param
     gpu.lib.vb200_set_option(b"raster_path", 0)
-    gpu.lib.vb200_set_option(b"direct_visibility", 1)
 
 
 def _check(gpu, vor, sc, exact=True):
@@ -186,34 +182,6 @@ def test_resolve_without_slot_keys(gpu, vor):
         _check(gpu, vor, scenes.random_triangles(300, 200, 200, 70, depth_op=abi.CMP_ALWAYS, depth_write=False))
     finally:
         setopt(b"slot_keys", 1)
-
-
-@pytest.mark.parametrize("max_pixels", [1, 6, 20, 256])
-def test_direct_and_binned_triangles_mix(gpu, vor, raster_path, max_pixels):
-    """the size threshold of the direct visibility path decides per triangle; whatever it is, direct fragments
-    (64-bit atomic min in L2, by the setup kernel) and binned ones (tile kernel) must resolve to the same
-    winners as the serial reference, including ties, NaN-free max/min modes, several draws into one target
-    and keys without the record slot"""
-    if raster_path != "auto":
-        pytest.skip("direct path only exists on the auto path")
-    setopt = gpu.lib.vb200_set_option
-    setopt.argtypes = [C.c_char_p, C.c_int64]
-    assert setopt(b"direct_max_pixels", max_pixels) == 0
-    try:
-        _check(gpu, vor, scenes.c3_mesh(480, 270, 120, 60))
-        _check(gpu, vor, scenes.c5_textured(480, 270, 90, 45, tex_size=64))
-        for seed, op in enumerate([abi.CMP_LESS, abi.CMP_LEQUAL, abi.CMP_GREATER, abi.CMP_GEQUAL]):
-            sc = scenes.random_triangles(300, 200, 400, 80 + seed, depth_op=op, max_size=0.06)
-            if op in (abi.CMP_GREATER, abi.CMP_GEQUAL):
-                sc.clear_depth = 0.0
-            _check(gpu, vor, sc)
-        _check(gpu, vor, scenes.random_triangles(300, 200, 400, 90, depth_op=abi.CMP_ALWAYS, depth_write=False, max_size=0.05))
-        _check(gpu, vor, scenes.random_triangles(333, 211, 300, 91, depth_op=abi.CMP_LESS, depth_write=False, max_size=0.05))
-        assert setopt(b"slot_keys", 0) == 0
-        _check(gpu, vor, scenes.random_triangles(300, 200, 400, 92, depth_op=abi.CMP_LEQUAL, max_size=0.06))
-    finally:
-        setopt(b"slot_keys", 1)
-        setopt(b"direct_max_pixels", 64)
 
 
 def test_kitchen_sink_shaders(gpu, vor):

@@ -24,12 +24,12 @@ for r in rows[2:]:
     name = r[h.index("Kernel Name")]
     lines.append(f"== {name}")
     for i, n in enumerate(h):
-        if n in WANT or ("warp_issue_stalled" in n and n.endswith("per_warp_active.pct")):
+        if n in WANT or ("issue_stalled" in n and n.endswith("per_issue_active.ratio")):
             try:
                 v = float(r[i].replace(",", ""))
             except ValueError:
                 continue
-            if "stalled" in n and v < 2.0:
+            if "stalled" in n and v < 0.3:
                 continue
             lines.append(f"  {n:75s} {v:16.3f} {units[i]}")
 text = "\n".join(lines) + "\n"

@@ -238,23 +238,6 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     }
   }
 
-  // ---- 3b. direct visibility path: a small triangle is not binned; it is rasterised below (step 6)
-  bool direct[kSetupPerThread];
-#pragma unroll
-  for(int k = 0; k < kSetupPerThread; k++)
-  {
-    direct[k] = false;
-    if(alive[k] && p.direct_mode)
-    {
-      const int minx = max(0, min(va[k].x, min(vb[k].x, vc[k].x)));
-      const int miny = max(0, min(va[k].y, min(vb[k].y, vc[k].y)));
-      const int maxx = min((int)p.width - 1, max(va[k].x, max(vb[k].x, vc[k].x)));
-      const int maxy = min((int)p.height - 1, max(va[k].y, max(vb[k].y, vc[k].y)));
-      const int w = maxx - minx, h = maxy - miny;
-      direct[k] = w <= 16 && h <= 16 && (uint32_t)(w * h) <= p.direct_max_pixels;
-    }
-  }
-
   // ---- 4. binning. Neighbouring triangles of a mesh land in the same tile, so per-lane atomics on the
   // tile cursors would serialise in the L2 atomic unit: __match_any_sync groups the lanes of a warp that
   // target the same tile and one lane per group reserves room for all of them. Ranges of up to 2x2 tiles
@@ -270,29 +253,6 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     nx[k] = alive[k] ? ((tiles[k] >> 16) & 0xffu) - (tiles[k] & 0xffu) + 1u : 0u;
     ny[k] = alive[k] ? (tiles[k] >> 24) - ((tiles[k] >> 8) & 0xffu) + 1u : 0u;
     used[k] = false;
-  }
-  // direct triangles (<= 2 x 2 tiles): flag the owned tiles they touch instead of appending to their lists
-  uint32_t dslot[kSetupPerThread][4];    // owned-tile slot of each quadrant of the tile range, ~0: not this rank's
-#pragma unroll
-  for(int k = 0; k < kSetupPerThread; k++)
-  {
-#pragma unroll
-    for(uint32_t q = 0; q < 4u; q++)
-    {
-      dslot[k][q] = 0xffffffffu;
-      if(direct[k] && (q & 1u) < nx[k] && (q >> 1) < ny[k])
-      {
-        const uint32_t tile = (((tiles[k] >> 8) & 0xffu) + (q >> 1)) * p.tiles_x + (tiles[k] & 0xffu) + (q & 1u);
-        if(tile_owned(tile, p.owner_rank, p.owner_world))
-        {
-          dslot[k][q] = tile / p.owner_world;
-          p.tile_direct[tile] = 1u;    // (plain store of the same value by many threads)
-          used[k] = true;
-        }
-      }
-    }
-    if(direct[k])
-      nx[k] = ny[k] = 0u;    // takes no part in the binning below
   }
 #pragma unroll
   for(uint32_t q = 0; q < 4u; q++)
@@ -352,8 +312,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     {
       if(used[k])
         *(int4 *)(p.tri + t[k]) = make_int4((int)s0[k], (int)s1[k], (int)s2[k], __float_as_int(invarea[k]));
-      // (a direct triangle is dead to the tile kernels' fallback scan: its fragments are already merged)
-      p.tri_tiles[t[k]] = (alive[k] && !direct[k]) ? tiles[k] : VB200_TILES_DEAD;
+      p.tri_tiles[t[k]] = alive[k] ? tiles[k] : VB200_TILES_DEAD;
     }
   __syncthreads();
   const uint32_t nbig = s_nbig;
@@ -373,87 +332,6 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
           p.list[(size_t)(tile / p.owner_world) * p.list_cap + pos] = b_tri;
       }
     }
-  }
-  // ---- 6. direct visibility path: coverage (barycentric(), rasterizer.cpp:282-310,542-549), depth
-  // (:551-558) and the visibility key of every covered pixel of the small triangles, merged with one 64-bit
-  // atomic min per fragment. Same key as the tile kernels' phase A, so the two paths mix freely.
-  uint32_t dcovered = 0;
-#pragma unroll
-  for(int k = 0; k < kSetupPerThread; k++)
-  {
-    if(!(direct[k] && used[k]))
-      continue;
-    const int minx = max(0, min(va[k].x, min(vb[k].x, vc[k].x)));
-    const int miny = max(0, min(va[k].y, min(vb[k].y, vc[k].y)));
-    const int maxx = min((int)p.width - 1, max(va[k].x, max(vb[k].x, vc[k].x)));
-    const int maxy = min((int)p.height - 1, max(va[k].y, max(vb[k].y, vc[k].y)));
-    const int ABx = vb[k].x - va[k].x, ABy = vb[k].y - va[k].y, ACx = vc[k].x - va[k].x, ACy = vc[k].y - va[k].y;
-    const int area2 = ABx * ACy - ABy * ACx;
-    const int sgn = area2 > 0 ? 1 : -1;
-    // b1 = A1*x + B1*y + C1, b2 = A2*x + B2*y + C2, b0 = |area2| - (b1 + b2): barymul folded in (int32 ring)
-    const int A1 = sgn * ACy, B1 = -sgn * ACx, A2 = -sgn * ABy, B2 = sgn * ABx, area = sgn * area2;
-    int r1 = sgn * (ACx * va[k].y - ACy * va[k].x) + A1 * minx + B1 * miny;
-    int r2 = sgn * (ABy * va[k].x - ABx * va[k].y) + A2 * minx + B2 * miny;
-    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-    if(!(p.direct_mode & VB200_DIRECT_NO_DEPTH))
-    {
-      d0 = __ldg(&p.rv[s0[k]].depth);
-      d1 = __ldg(&p.rv[s1[k]].depth);
-      d2 = __ldg(&p.rv[s2[k]].depth);
-    }
-    const uint32_t id = p.slot_keys ? (((t[k] + 1u) << 8) | 0x80u) : (t[k] + 1u);
-    const uint32_t low = (p.direct_mode & VB200_DIRECT_LAST) ? ~id : id;
-    const uint32_t maxMask = (p.direct_mode & VB200_DIRECT_MAX) ? 0xffffffffu : 0u;
-    const int tx0 = minx >> 5, ty0 = miny >> 5;
-    const int total = (maxx - minx) * (maxy - miny);
-    int x = minx, y = miny, e1 = r1, e2 = r2;
-    for(int i = 0; i < total; i++)
-    {
-      const int e0 = area - (e1 + e2);
-      if((e0 | e1 | e2) >= 0)    // covered iff all three >= 0 (rasterizer.cpp:549)
-      {
-        dcovered++;
-        const uint32_t q = (uint32_t)((x >> 5) != tx0) | ((uint32_t)((y >> 5) != ty0) << 1);
-        const uint32_t slot = q < 2u ? (q ? dslot[k][1] : dslot[k][0]) : (q == 2u ? dslot[k][2] : dslot[k][3]);
-        if(slot != 0xffffffffu)
-        {
-          uint32_t dk = 0u;
-          bool ok = true;
-          if(!(p.direct_mode & VB200_DIRECT_NO_DEPTH))
-          {
-            // rasterizer.cpp:552-558
-            const float n0 = __fmul_rn((float)e0, invarea[k]);
-            const float n1 = __fmul_rn((float)e1, invarea[k]);
-            const float n2 = __fmul_rn((float)e2, invarea[k]);
-            const float pixdepth = __fadd_rn(__fadd_rn(__fmul_rn(n0, d0), __fmul_rn(n1, d1)), __fmul_rn(n2, d2));
-            ok = pixdepth == pixdepth;    // NaN never passes an ordered comparison
-            dk = vb200_depth_key(pixdepth) ^ maxMask;
-          }
-          if(ok)
-            atomicMin(p.vis_keys + ((size_t)slot * (VB200_TILE * VB200_TILE) + (uint32_t)((y & 31) * VB200_TILE + (x & 31))),
-                      ((unsigned long long)dk << 32) | low);
-        }
-      }
-      x++;
-      e1 += A1;
-      e2 += A2;
-      if(x == maxx)
-      {
-        x = minx;
-        y++;
-        r1 += B1;
-        r2 += B2;
-        e1 = r1;
-        e2 = r2;
-      }
-    }
-  }
-  if(p.count_fragments)
-  {
-    dcovered = __reduce_add_sync(0xffffffffu, dcovered);
-    if(lane == 0 && dcovered)
-      atomicAdd(&p.counters->slot[(blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) & (VB200_COUNTER_SLOTS - 1)].fragments_covered,
-                (unsigned long long)dcovered);
   }
   // statistics: one atomic pair per warp on counters spread over 32 slots (per-warp atomics on ONE word cost
   // ~20 us per million triangles: same-address atomics serialise in L2)

@@ -27,22 +27,7 @@ struct Vb200SetupParams
   Vb200DrawCounters *counters;
   uint32_t front_face, cull_mode;
   uint32_t width, height, tiles_x, tiles_y, owner_rank, owner_world;
-  // Direct visibility path (order-independent passes only, see scaffold.cu "K4 (resolve)"): a triangle whose
-  // clamped bbox is at most 16 x 16 and direct_max_pixels pixels is not binned. The setup kernel rasterises it
-  // itself and merges each covered pixel's (depth key, triangle id) into vis_keys with a 64-bit atomic min in
-  // L2; the tile kernel seeds its visibility slots from there. vis_keys is tile-major (owned tile slot * 1024 +
-  // (y & 31) * 32 + (x & 31)), all ones = empty; tile_direct[t] != 0 says tile t received such fragments.
-  unsigned long long *vis_keys;
-  uint32_t *tile_direct;
-  uint32_t direct_mode;          // 0: off; VB200_DIRECT_* bits
-  uint32_t direct_max_pixels;
-  uint32_t slot_keys;            // key id = (triangle + 1) << 8 | 0x80 (see Vb200RasterState::slot_keys)
-  uint32_t count_fragments;
 };
-#define VB200_DIRECT_ON 1u
-#define VB200_DIRECT_MAX 2u       // GREATER / GREATER_OR_EQUAL: the largest depth wins (depth key inverted)
-#define VB200_DIRECT_LAST 4u      // ties go to the last triangle (id inverted)
-#define VB200_DIRECT_NO_DEPTH 8u  // no depth test: the key is the inverted id alone
 
 // parameter blocks of scaffold.cu (must match the definitions there)
 struct Vb200VertexParams
@@ -69,11 +54,6 @@ struct Vb200TileParams
   const uint32_t *tri_tiles;    // packed tile range per triangle (VB200_TILES_DEAD = dead)
   uint32_t list_cap;
   uint32_t num_tris;
-  // direct visibility path (Vb200SetupParams): keys the setup kernel merged for this rank's tiles, and the
-  // per-tile "has direct fragments" flags. NULL: the path is off for this draw. The tile kernel puts every
-  // key it consumes back to all ones, so the buffer is empty again when the draw ends.
-  unsigned long long *vis_keys;
-  const uint32_t *tile_direct;
   // pending ClearTarget()s folded into this launch: bit 0 colour, bit 1 depth. The kernel then takes the
   // attachment's prior contents from these constants instead of loading them and writes EVERY pixel of
   // every tile (including tiles no triangle touches), so no separate clear kernel runs.

@@ -48,13 +48,6 @@ __device__ __forceinline__ Vb200TriSetup vb200_load_setup(const Vb200TileParams 
   return r;
 }
 
-// float -> uint32 whose unsigned order equals the float order (-0 == +0); callers exclude NaN
-__device__ __forceinline__ uint32_t vb200_depth_key(float d)
-{
-  const uint32_t b = __float_as_uint(__fadd_rn(d, 0.0f));    // -0 + 0 = +0; every other value unchanged
-  return b ^ ((uint32_t)((int)b >> 31) | 0x80000000u);       // negative: flip all bits; else set the sign bit
-}
-
 // does the packed inclusive tile range (tx0 | ty0 << 8 | tx1 << 16 | ty1 << 24) contain tile (tx, ty)?
 // VB200_TILES_DEAD has tx0 = 255 > tx1 = 0 and contains nothing.
 __device__ __forceinline__ bool vb200_tile_in_range(uint32_t tiles, uint32_t tx, uint32_t ty)

@@ -216,10 +216,6 @@ struct Context
   DevBuf<float4> interps;
   DevBuf<Vb200TriRecord> setup;
   DevBuf<uint32_t> tileCount, list, triTiles;
-  // direct visibility path: one 64-bit key per pixel of this rank's tiles, all ones between draws
-  DevBuf<unsigned long long> visKeys;
-  int64_t optDirect = 1;             // 0: every triangle is binned
-  int64_t optDirectMaxPixels = 64;   // bbox pixels up to which a triangle takes the direct path
   uint32_t *range = nullptr;                // device {min,max}
   // ClearTarget()s not yet executed: device address of the attachment -> fill word and pixel count.
   // The next draw into the attachment folds them into its tile kernel; anything else that touches the
@@ -1031,7 +1027,6 @@ void vb200_shutdown(void)
   g.list.release();
   cudaFree(g.range);
   g.triTiles.release();
-  g.visKeys.release();
   cudaFree(g.counters);
   cudaFree(g.unorm);
   for(auto &pr : g.presents)
@@ -1772,7 +1767,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
       listCap = (uint32_t)std::min<int64_t>(g.optTileListCap, 1 << 20);
   }
   if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * nslots) || !g.setup.reserve(numTris) ||
-     !g.triTiles.reserve(numTris) || !g.list.reserve((size_t)ownedTiles * listCap) || !g.tileCount.reserve(2 * (size_t)ntiles))
+     !g.triTiles.reserve(numTris) || !g.list.reserve((size_t)ownedTiles * listCap) || !g.tileCount.reserve(ntiles))
   {
     g.stickyCuda = 1;
     return setError(VB200_ERR_CUDA, "out of device memory for draw scratch");
@@ -1846,25 +1841,6 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     return setError(VB200_ERR_LINK, "kernel scaffold without a CTA size");
   g.lastTileKernel = kKernelNames[tileKernelId];
 
-  // Direct visibility path: in an order-independent pass with min/max-depth or last-wins semantics (not the
-  // static-test flavour of last-wins, which needs the stored depth per fragment) the setup kernel rasterises
-  // small triangles itself instead of binning them.
-  uint32_t directMode = 0;
-  if(g.optDirect && resolveMode >= 0 && !(resolveMode == 4 && depthTest))
-    directMode = VB200_DIRECT_ON | ((resolveMode == 2 || resolveMode == 3) ? VB200_DIRECT_MAX : 0u) |
-                 ((resolveMode == 1 || resolveMode == 3 || resolveMode == 4) ? VB200_DIRECT_LAST : 0u) |
-                 (resolveMode == 4 ? VB200_DIRECT_NO_DEPTH : 0u);
-  if(directMode)
-  {
-    const size_t before = g.visKeys.cap;
-    if(!g.visKeys.reserve((size_t)ownedTiles * VB200_TILE * VB200_TILE))
-    {
-      g.stickyCuda = 1;
-      return setError(VB200_ERR_CUDA, "out of device memory for the visibility keys");
-    }
-    if(g.visKeys.cap != before)    // new storage: every key starts out empty; the tile kernels keep it that way
-      CU(cudaMemsetAsync(g.visKeys.p, 0xff, g.visKeys.cap * sizeof(unsigned long long), g.stream));
-  }
   const bool slotKeys = g.optSlotKeys && numTris < (1u << 24) - 1u;
 
   // ---- K1: vertex stage
@@ -1881,7 +1857,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   vp.width = W;
   vp.height = H;
   vp.tile_count = g.tileCount.p;
-  vp.tile_count_n = 2u * ntiles;    // the appends per tile, then the "has direct fragments" flags
+  vp.tile_count_n = ntiles;
   {
     cudaKernel_t kVertex = nullptr;
     if((rc = getKernel(K_VERTEX, pl->vs, &kVertex)))
@@ -1920,12 +1896,6 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   sp.tiles_y = tilesY;
   sp.owner_rank = g.ownerRank;
   sp.owner_world = g.ownerWorld;
-  sp.vis_keys = directMode ? g.visKeys.p : nullptr;
-  sp.tile_direct = g.tileCount.p + ntiles;
-  sp.direct_mode = directMode;
-  sp.direct_max_pixels = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(g.optDirectMaxPixels, 256));
-  sp.slot_keys = slotKeys ? 1u : 0u;
-  sp.count_fragments = g.optCountFragments ? 1u : 0u;
   g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);    // (the vertex kernel zeroed the tile counters)
   phaseMark(2);
 
@@ -1961,8 +1931,6 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
   tp.rs.color_bpp = 4;
   tp.rs.slot_keys = slotKeys ? 1u : 0u;
-  tp.vis_keys = directMode ? g.visKeys.p : nullptr;
-  tp.tile_direct = g.tileCount.p + ntiles;
   tp.clear_flags = clearFlags;
   tp.clear_color = clearColorWord;
   tp.clear_depth = clearDepthValue;
@@ -2246,10 +2214,6 @@ int vb200_set_option(const char *name, int64_t value)
     g.optCountFragments = value;
   else if(!strcmp(name, "fuse_clears"))
     g.optFuseClears = value;
-  else if(!strcmp(name, "direct_visibility"))
-    g.optDirect = value;
-  else if(!strcmp(name, "direct_max_pixels"))
-    g.optDirectMaxPixels = value;
   else if(!strcmp(name, "slot_keys"))
     g.optSlotKeys = value;
   else if(!strcmp(name, "tile_list_cap"))

@@ -544,6 +544,13 @@ __device__ __forceinline__ unsigned long long vb200_atoms_cas64(uint32_t a, unsi
 // triangles, the common case) phase B reads the winner's record from shared memory instead of gathering
 // the triangle and its three vertices from global memory again.
 
+// float -> uint32 whose unsigned order equals the float order (-0 == +0); callers exclude NaN
+__device__ __forceinline__ uint32_t vb200_depth_key(float d)
+{
+  const uint32_t b = __float_as_uint(__fadd_rn(d, 0.0f));    // -0 + 0 = +0; every other value unchanged
+  return b ^ ((uint32_t)((int)b >> 31) | 0x80000000u);       // negative: flip all bits; else set the sign bit
+}
+
 template <int MODE>
 __device__ __forceinline__ unsigned long long vb200_existing_key(float e)
 {
@@ -635,11 +642,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   asm volatile("" : "+r"(lane), "+r"(warp));    // (kept in registers: ptxas otherwise re-reads %tid inside the loops)
   const int tileX0 = (int)(tx * VB200_TILE), tileY0 = (int)(ty * VB200_TILE);
-  // direct visibility path: the setup kernel has already merged the fragments of small triangles into this
-  // tile's keys in global memory (kernels.h: Vb200SetupParams::vis_keys)
-  const bool direct = p.vis_keys != nullptr && p.tile_direct[tile] != 0u;
-  unsigned long long *gkeys = p.vis_keys + (size_t)blockIdx.x * (VB200_TILE * VB200_TILE);
-  if(n == 0 && !direct)
+  if(n == 0)
   {
     // no triangle touches this tile: it only has to receive the folded clears
     if(p.clear_flags)
@@ -686,35 +689,6 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
            aE2 = vb200_smem_addr(s_e2), aZ = vb200_smem_addr(s_z), aKey = vb200_smem_addr(s_key);
   asm volatile("" : "+r"(aVis), "+r"(aStart), "+r"(aE1), "+r"(aE2), "+r"(aZ), "+r"(aKey));
   uint32_t covered = 0, shaded = 0;
-  // ---- init: one visibility key per pixel, seeded with the depth already in the buffer and with what the
-  // direct path merged for the pixel (both are keys of the same order: the smaller one holds the pixel). A
-  // consumed direct key is put back to "empty" for the next draw.
-  auto init_tile = [&]() {
-    for(int i = threadIdx.x; i < 256; i += RT)
-      vb200_s_unorm[i] = __ldg(p.unorm + i);    // read in phase B, after the barriers below
-    unsigned long long gk[VB200_TILE / RW];
-#pragma unroll
-    for(int j = 0; j < VB200_TILE / RW; j++)
-      gk[j] = direct ? gkeys[(warp + RW * j) * VB200_TILE + lane] : ~0ull;
-#pragma unroll
-    for(int j = 0; j < VB200_TILE / RW; j++)
-    {
-      const int ly = warp + RW * j;
-      const int x = tileX0 + lane, y = tileY0 + ly;
-      const bool in = x < (int)rs.width && y < (int)rs.height;
-      float e = 0.0f;
-      if(MODE != VB200_RES_LAST_WINS || depthTest)
-        e = clearDepth ? p.clear_depth : (in ? p.depth[(size_t)y * rs.width + x] : 0.0f);
-      const unsigned long long ek = vb200_existing_key<MODE>(e);
-      vis[ly * VB200_TILE + lane] = gk[j] < ek ? gk[j] : ek;
-      if(gk[j] != ~0ull)
-        gkeys[ly * VB200_TILE + lane] = ~0ull;
-      if(MODE == VB200_RES_LAST_WINS)
-        s_depth[ly * VB200_TILE + lane] = e;
-    }
-  };
-  if(n == 0)
-    init_tile();    // only direct fragments: no round runs
   for(uint32_t base = 0; base < n; base += RT)
   {
     uint32_t m = min((uint32_t)RT, n - base);    // records in this round
@@ -774,7 +748,24 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       rc = __ldg((const int4 *)(p.rv + (uint32_t)rq.z));
     }
     if(base == 0u)
-      init_tile();
+    {
+      for(int i = threadIdx.x; i < 256; i += RT)
+        vb200_s_unorm[i] = __ldg(p.unorm + i);    // read in phase B, after the barriers below
+      // ---- init: one visibility key per pixel, seeded with the depth already in the buffer
+    #pragma unroll
+      for(int j = 0; j < VB200_TILE / RW; j++)
+      {
+        const int ly = warp + RW * j;
+        const int x = tileX0 + lane, y = tileY0 + ly;
+        const bool in = x < (int)rs.width && y < (int)rs.height;
+        float e = 0.0f;
+        if(MODE != VB200_RES_LAST_WINS || depthTest)
+          e = clearDepth ? p.clear_depth : (in ? p.depth[(size_t)y * rs.width + x] : 0.0f);
+        vis[ly * VB200_TILE + lane] = vb200_existing_key<MODE>(e);
+        if(MODE == VB200_RES_LAST_WINS)
+          s_depth[ly * VB200_TILE + lane] = e;
+      }
+    }
     if(have)
     {
       const Vb200TriSetup su = vb200_unpack_setup(rq, ra, rb, rc);
@@ -1010,8 +1001,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 
   // ---- phase B: shade the winner of every pixel, write back. Thread (warp, lane) owns pixel column `lane`
   // of rows warp, warp + RW, warp + 2 RW, ...
-  // the only round's records are still staged (slots are 7 bits: bit 7 of a key id marks a direct winner)
-  const bool recordsInSmem = rs.slot_keys && n != 0u && n <= (uint32_t)RT && RT <= 128;
+  const bool recordsInSmem = rs.slot_keys && n <= (uint32_t)RT;    // the only round's records are still staged
   const bool remote = p.mc_color != nullptr || p.num_peers != 0u;
   uint32_t aPw = vb200_smem_addr(s_pw), aSv = vb200_smem_addr(s_sv);
   asm volatile("" : "+r"(aPw), "+r"(aSv));
@@ -1081,10 +1071,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         __stcs(p.depth + gi, p.clear_depth);
     }
   };
-  shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
-                 float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
-    if(recordsInSmem && !(id & 0x80u))
-    {
+  if(recordsInSmem)
+    shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
+                   float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
       // the winner's edge values at this pixel from its staged record (int32 ring arithmetic, so this and
       // the reference's formulation, rasterizer.cpp:303-309,545-558, give the same bits)
       const uint32_t slot16 = (id & (RT - 1u)) * 16u;    // slot = the thread that set the winner up
@@ -1097,11 +1086,11 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       invarea = __int_as_float(c2.x); d0 = __int_as_float(c2.y); d1 = __int_as_float(c2.z); d2 = __int_as_float(c2.w);
       invw0 = __int_as_float(c4.x); invw1 = __int_as_float(c4.y); invw2 = __int_as_float(c4.z);
       s0 = (uint32_t)c4.w; s1 = (uint32_t)c5; s2 = (uint32_t)(c5 >> 32);
-    }
-    else
-    {
-      // a winner of the direct path (slot bit 7), or of an earlier round: the record is gathered again, edge
-      // values exactly as rasterizer.cpp:303-309,545-558
+    });
+  else
+    shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
+                   float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
+      // several rounds: the record is gathered again, edge values exactly as rasterizer.cpp:303-309,545-558
       const Vb200TriSetup su = vb200_load_setup(p, (rs.slot_keys ? (id >> 8) : id) - 1u);
       const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
       const int area2 = ABx * ACy - ABy * ACx;
@@ -1112,8 +1101,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       invarea = su.invarea; d0 = su.d0; d1 = su.d1; d2 = su.d2;
       invw0 = su.invw0; invw1 = su.invw1; invw2 = su.invw2;
       s0 = su.s0; s1 = su.s1; s2 = su.s2;
-    }
-  });
+    });
   if(rs.count_fragments)
     vb200_count_fragments(p.counters, covered, shaded);
 }
