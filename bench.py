@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — throughput of visor's draw-execution hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1..c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1..c6]
 
 A "step" is one pass of the hot path over one synthetic frame: ClearTarget(colour), ClearTarget(depth),
 DrawTriangles — the reference's own operator sequence for a render pass (cmd_exec.cpp:35-142).
@@ -136,6 +136,7 @@ def build_scene(workload: str) -> scenes.Scene:
         "c3": lambda: scenes.c3_mesh(),
         "c4": lambda: scenes.c4_particles(),
         "c5": lambda: scenes.c5_textured(),
+        "c6": lambda: scenes.c6_many_draws(),
     }[workload]()
 
 
@@ -145,6 +146,7 @@ WORKLOAD_DESC = {
     "c3": "c3: 1M-triangle indexed mesh, per-vertex lighting, depth LESS+write, 3840x2160",
     "c4": "c4: 200k alpha-blended quads (400k triangles), ~8x overdraw, 1920x1080",
     "c5": "c5: 4M-triangle textured lit mesh, depth LESS+write, 7680x4320",
+    "c6": "c6 (diagnostic, not a BASELINE config): the c3 mesh recorded as 1000 indexed draws of 1000 triangles",
 }
 
 
@@ -741,7 +743,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c1", "c2", "c3", "c4", "c5", "c6"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="fused", choices=["fused", "fused-p2p", "allgather"],
                     help="N>1: fused = tile kernels store into every rank's image over NVLink (one NVSwitch "

@@ -452,6 +452,29 @@ def random_triangles(width: int, height: int, n: int, seed: int, *, depth_op: in
     return Scene(f"random_{n}_{seed}", width, height, [d], depth=has_depth)
 
 
+def split_draws(scene: Scene, parts: int, *, order: Optional[Sequence[int]] = None) -> Scene:
+    """The same scene with its (single, triangle-list) draw cut into `parts` vkCmdDraw*s of consecutive
+    triangle ranges out of the same buffers, as an application that draws a mesh chunk by chunk would
+    record it (the reference replays them one after the other, cmd_exec.cpp:129-142). `order`: a
+    permutation of the parts (submission order matters for blended and equal-depth fragments)."""
+    import dataclasses
+    (d,) = scene.draws
+    assert d.pipe.topology == abi.TOPO_LIST
+    tris = d.count // 3
+    cuts = [tris * i // parts for i in range(parts + 1)]
+    chunks = [(cuts[i], cuts[i + 1]) for i in range(parts) if cuts[i + 1] > cuts[i]]
+    if order is not None:
+        chunks = [chunks[i] for i in order if i < len(chunks)]
+    draws = [dataclasses.replace(d, first=d.first + 3 * a, count=3 * (b - a)) for a, b in chunks]
+    return dataclasses.replace(scene, name=f"{scene.name}_x{len(draws)}", draws=draws)
+
+
+def c6_many_draws(width: int = 3840, height: int = 2160, draws: int = 1000, qx: int = 1000, qy: int = 500) -> Scene:
+    """Diagnostic workload (not a BASELINE config): the C3 mesh recorded as `draws` indexed draws of
+    consecutive index ranges, same pipeline and bindings."""
+    return split_draws(c3_mesh(width, height, qx, qy), draws)
+
+
 def bc_blocks(rng, w, h, corner_cases=True):
     """random 16-byte BC blocks for a w x h texture (1 byte per texel, images.cpp:31-33)"""
     blocks = rng.integers(0, 256, size=((h // 4) * (w // 4), 16), dtype=np.uint8)

@@ -184,6 +184,52 @@ def test_resolve_without_slot_keys(gpu, vor):
         setopt(b"slot_keys", 1)
 
 
+def test_many_draws_are_batched_and_keep_submission_order(gpu, vor):
+    """consecutive draws with one pipeline and one set of bindings are rasterised as ONE batch (one vertex,
+    setup and tile pass); triangle ids keep the submission order across draws, so blended and equal-depth
+    results equal the reference's draw-by-draw replay (cmd_exec.cpp:129-142)"""
+    import ctypes as C
+    # indexed mesh cut into 40 draws (together they reference every vertex: one shared vertex span)
+    sc = scenes.split_draws(scenes.c3_mesh(480, 270, 120, 60), 40)
+    gpu.reset_stats()
+    _check(gpu, vor, sc)
+    st = gpu.stats()
+    assert st["draws"] == 40
+    assert st["kernel_launches"] <= 4, st    # vertex + setup (+ sort) + tiles for all 40 draws
+    # a few small indexed draws out of a large buffer: host-measured spans, draws submitted out of order
+    _check(gpu, vor, scenes.split_draws(scenes.c3_mesh(480, 270, 120, 60), 40, order=[31, 3, 17, 4, 5]))
+    # non-indexed draws, blended (order dependent) and depth-tested with ties, shuffled submission order
+    rng = np.random.default_rng(5)
+    for kw in (dict(blend=(abi.BF_SRC_ALPHA, abi.BF_ONE_MINUS_SRC_ALPHA, 0), depth_op=abi.CMP_ALWAYS, depth_write=False),
+               dict(depth_op=abi.CMP_LEQUAL), dict(depth_op=abi.CMP_LESS), dict(depth_op=abi.CMP_NOTEQUAL)):
+        base = scenes.random_triangles(300, 200, 240, 33, **kw)
+        _check(gpu, vor, scenes.split_draws(base, 24, order=list(rng.permutation(24))))
+    # indexed u16 draws through a shuffled vertex buffer
+    base = scenes.random_triangles(300, 200, 120, 34, index_type=abi.INDEX_U16)
+    _check(gpu, vor, scenes.split_draws(base, 12, order=list(rng.permutation(12))))
+    # every draw by itself gives the same image
+    setopt = gpu.lib.vb200_set_option
+    setopt.argtypes = [C.c_char_p, C.c_int64]
+    assert setopt(b"batch_draws", 0) == 0
+    try:
+        _check(gpu, vor, scenes.split_draws(scenes.c3_mesh(480, 270, 120, 60), 7))
+    finally:
+        setopt(b"batch_draws", 1)
+
+
+def test_state_changes_split_batches(gpu, vor):
+    """draws whose pipeline, bindings or targets differ cannot share a batch; the sequence must still give the
+    reference's image (second pipeline: other cull mode and depth op on the same targets)"""
+    import dataclasses
+    a = scenes.random_triangles(320, 240, 150, 41, depth_op=abi.CMP_LESS)
+    b2 = scenes.random_triangles(320, 240, 150, 42, depth_op=abi.CMP_GEQUAL, cull=abi.CULL_BACK)
+    c = scenes.random_triangles(320, 240, 150, 43, depth_op=abi.CMP_LESS,
+                                blend=(abi.BF_SRC_ALPHA, abi.BF_ONE_MINUS_SRC_ALPHA, 0))
+    parts = [scenes.split_draws(x, 5).draws for x in (a, b2, c)]
+    draws = [d for trio in zip(*parts) for d in trio] + parts[0][:2]
+    _check(gpu, vor, dataclasses.replace(a, name="interleaved_pipelines", draws=draws))
+
+
 def test_kitchen_sink_shaders(gpu, vor):
     """function calls, loops, branches, push constants, UBO at (set 1, binding 2), int/flat and matrix
     varyings, through both stages"""
@@ -222,6 +268,21 @@ def test_sampler_matches_oracle(gpu, vor):
     d = rng.normal(size=(20000, 3)).astype(np.float32)
     a, b = gpu.sample(cim, d, cube=True), vor.sample(cim, d, cube=True)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_unorm8_conversion_is_the_ieee_quotient(gpu):
+    """texel conversion float(byte) / 255.0f (texture_sampling.cpp:121-133) is computed without a division on
+    the device (one Newton step); sampling exactly at the texel origins returns the conversion itself
+    (weights 1 and 0), so all 256 byte values are compared with the IEEE single-precision quotient"""
+    tex = np.arange(256, dtype=np.uint8).repeat(4).reshape(1, 256, 4).repeat(4, axis=0).copy()    # 256 x 4, RGBA = (b,b,b,b)
+    tex[:, :, 1] = 255 - tex[:, :, 1]
+    tex[:, :, 2] = (tex[:, :, 2].astype(np.uint16) * 7 % 256).astype(np.uint8)
+    img = abi.make_image(tex, 256, 4, abi.FMT_R8G8B8A8_UNORM)
+    uvw = np.zeros((256, 2), dtype=np.float32)
+    uvw[:, 0] = np.arange(256, dtype=np.float32) / np.float32(256.0)    # exact: u * 256 is the integer texel column
+    out = gpu.sample(img, uvw)
+    want = tex[0].astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
 
 
 def test_sampler_block_compressed_and_r8(gpu, vor):

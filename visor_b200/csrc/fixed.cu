@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
   __syncthreads();
 
   // ---- 1. triangle assembly (rasterizer.cpp:128-232): list = (3t, 3t+1, 3t+2); strip alternates
-  // (t, t+1, t+2) / (t+1, t, t+2) to preserve winding; GetIndex (:100-119)
+  // (t, t+1, t+2) / (t+1, t, t+2) to preserve winding; GetIndex (:100-119). In a batch of several draws the
+  // triangle's draw is the last one whose tri_base is <= t (a handful of L1-resident probes).
+  Vb200VertexSpan span[kSetupPerThread];
 #pragma unroll
   for(int k = 0; k < kSetupPerThread; k++)
   {
@@ -160,43 +162,73 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     tiles[k] = VB200_TILES_DEAD;
     invarea[k] = 0.0f;
     s0[k] = s1[k] = s2[k] = 0u;
+    span[k] = p.span0;
     if(alive[k])
     {
+      Vb200BatchDraw d = p.draw0;
+      if(p.draws)
+      {
+        uint32_t lo = 0, hi = p.num_draws;    // invariant: draws[lo].tri_base <= t < draws[hi].tri_base
+        while(hi - lo > 1u)
+        {
+          const uint32_t mid = (lo + hi) >> 1;
+          if(__ldg(&p.draws[mid].tri_base) <= t[k])
+            lo = mid;
+          else
+            hi = mid;
+        }
+        d = p.draws[lo];
+        span[k] = p.spans[d.span];
+      }
+      const uint32_t local = t[k] - d.tri_base;
       uint32_t c0, c1, c2;
       if(p.topology == 3u)
       {
-        c0 = p.first + 3u * t[k];
+        c0 = d.first + 3u * local;
         c1 = c0 + 1u;
         c2 = c0 + 2u;
       }
       else
       {
-        const uint32_t b = p.first + t[k];
-        c0 = (t[k] & 1u) ? b + 1u : b;
-        c1 = (t[k] & 1u) ? b : b + 1u;
+        const uint32_t b = d.first + local;
+        c0 = (local & 1u) ? b + 1u : b;
+        c1 = (local & 1u) ? b : b + 1u;
         c2 = b + 2u;
       }
-      if(p.indexed)
+      if(d.ib)
       {
-        c0 = load_index(p.ib, p.index_type, c0);
-        c1 = load_index(p.ib, p.index_type, c1);
-        c2 = load_index(p.ib, p.index_type, c2);
+        c0 = load_index(d.ib, d.index_type, c0);
+        c1 = load_index(d.ib, d.index_type, c1);
+        c2 = load_index(d.ib, d.index_type, c2);
+        // a malformed index beyond the bound vertex buffers kills the triangle
+        alive[k] = c0 < p.vertex_bound && c1 < p.vertex_bound && c2 < p.vertex_bound;
       }
       s0[k] = c0;
       s1[k] = c1;
       s2[k] = c2;
-      alive[k] = c0 < p.vertex_bound && c1 < p.vertex_bound && c2 < p.vertex_bound;
     }
   }
-  const uint32_t base = (p.indexed && p.range) ? p.range[0] : p.base_vertex;
+  if(p.range)    // the lone draw whose span was measured on the device: [min, max], at most span0.count records
+  {
+    const uint32_t lo = p.range[0], hi = p.range[1];
+#pragma unroll
+    for(int k = 0; k < kSetupPerThread; k++)
+    {
+      span[k].src_base = lo;
+      span[k].count = hi >= lo ? min(hi - lo + 1u, span[k].count) : 0u;
+    }
+  }
   // ---- 2. window positions of the three corners (the raster record's first 8 bytes)
 #pragma unroll
   for(int k = 0; k < kSetupPerThread; k++)
   {
-    s0[k] -= base;
-    s1[k] -= base;
-    s2[k] -= base;
-    alive[k] = alive[k] && s0[k] < p.capacity && s1[k] < p.capacity && s2[k] < p.capacity;
+    s0[k] -= span[k].src_base;
+    s1[k] -= span[k].src_base;
+    s2[k] -= span[k].src_base;
+    alive[k] = alive[k] && s0[k] < span[k].count && s1[k] < span[k].count && s2[k] < span[k].count;
+    s0[k] += span[k].slot_base;
+    s1[k] += span[k].slot_base;
+    s2[k] += span[k].slot_base;
     va[k] = vb[k] = vc[k] = make_int2(0, 0);
     if(alive[k])
     {

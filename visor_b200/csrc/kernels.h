@@ -5,13 +5,37 @@
 #include <stdint.h>
 #include "device_types.h"
 
+// A batch = consecutive vkCmdDraw*s of one submit that share pipeline, bindings and attachments (the reference
+// replays them one by one, cmd_exec.cpp:129-142). They are rasterised together: ONE vertex kernel over the
+// batch's vertex spans, ONE setup/binning kernel over all its triangles (triangle id = tri_base + local index,
+// so ids keep submission order across draws) and ONE tile pass.
+struct Vb200VertexSpan    // a run of source vertices shaded into consecutive post-VS record slots
+{
+  uint32_t src_base;      // first source vertex (vertex index, or index value for indexed draws)
+  uint32_t count;
+  uint32_t slot_base;     // first post-VS record slot
+  uint32_t pad;
+};
+struct Vb200BatchDraw
+{
+  const void *ib;         // device address of ib.buffer->bytes + ib.offset; NULL: non-indexed draw
+  uint32_t index_type, first, num_tris, tri_base;
+  uint32_t span;          // the vertex span that holds the draw's corners
+  uint32_t pad;
+};
+
 struct Vb200SetupParams
 {
-  const void *ib;    // device address of ib.buffer->bytes + ib.offset
-  uint32_t index_type, indexed, first, num_tris, topology;
-  const uint32_t *range;    // indexed: device {minIndex, maxIndex}; slot = index - minIndex (NULL: slot = index - base_vertex)
-  uint32_t base_vertex;     // non-indexed: slot = vertex - base_vertex
-  uint32_t capacity;        // number of valid post-VS records
+  // the batch: draw0/span0 are used in place of the tables when those are NULL (a batch of one draw)
+  const Vb200BatchDraw *draws;
+  const Vb200VertexSpan *spans;
+  uint32_t num_draws;
+  Vb200BatchDraw draw0;
+  Vb200VertexSpan span0;
+  // an indexed draw out of a much larger vertex buffer, too big to measure on the host, is always alone in its
+  // batch: device {minIndex, maxIndex} (k_index_range); its span is [min, max], clipped to span0.count records
+  const uint32_t *range;
+  uint32_t num_tris, topology;    // triangles of the whole batch
   uint32_t vertex_bound;    // indexed draws: vertices the bound buffers hold; an index at or above it kills the triangle
   const Vb200RasterVertex *rv;
   Vb200TriRecord *tri;
@@ -32,9 +56,11 @@ struct Vb200SetupParams
 // parameter blocks of scaffold.cu (must match the definitions there)
 struct Vb200VertexParams
 {
-  const uint32_t *range;
-  uint32_t base_vertex;
-  uint32_t count;
+  const Vb200VertexSpan *spans;    // NULL: span0 alone
+  uint32_t num_spans;
+  Vb200VertexSpan span0;
+  const uint32_t *range;           // device {minIndex, maxIndex}: span0 = [min, max] clipped to span0.count records
+  uint32_t count;                  // records to shade (all spans)
   uint32_t vertex_bound;    // vertices the bound vertex buffers hold (0xffffffff: unbounded): nothing beyond is fetched
   Vb200RasterVertex *rv;
   float4 *interps;

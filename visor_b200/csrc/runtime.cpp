@@ -201,8 +201,55 @@ struct DevBuf
   }
 };
 
+// A batch of recorded draws (see kernels.h: Vb200BatchDraw). The key is everything that must be uniform across
+// one launch of the vertex, setup and tile kernels; it is compared bytewise.
+struct BatchKey
+{
+  Vb200Env env;
+  uint64_t vs, fs;    // serials of the shader entries
+  uint32_t topology, frontFace, cullMode, depthOp, depthWrite, blend[4];
+  uint8_t *colorDev, *depthDev;
+  uint32_t width, height, vertexBound, nslots;
+  int tileKernelId;
+};
+struct Batch
+{
+  enum SpanKind
+  {
+    SPAN_HOST,       // vertices [spanBase, spanBase + spanCount): non-indexed draws, ranges read back
+    SPAN_INDEXED,    // the same, measured from host-readable indices; may still be widened to SPAN_ALL
+    SPAN_ALL,        // indexed, references every bound vertex several times: all bound vertices
+    SPAN_DEVICE,     // indexed, range only measurable on the device
+  };
+  struct Draw
+  {
+    Vb200BatchDraw dev;
+    int kind;
+    uint32_t spanBase, spanCount, usedVerts;
+  };
+  bool active = false, closed = false, ran = false;
+  BatchKey key;
+  cudaKernel_t kVertex = nullptr, kTile = nullptr;
+  unsigned tileThreads = 0;
+  uint32_t clearFlags = 0, clearColorWord = 0;
+  float clearDepthValue = 0.0f;
+  std::vector<Draw> draws;
+  uint64_t numTris = 0, numVerts = 0;
+  void reset()
+  {
+    active = closed = ran = false;
+    kVertex = kTile = nullptr;
+    tileThreads = 0;
+    clearFlags = clearColorWord = 0;
+    clearDepthValue = 0.0f;
+    draws.clear();
+    numTris = numVerts = 0;
+  }
+};
+
 struct Context
 {
+  Batch batch;
   bool ready = false;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -217,6 +264,9 @@ struct Context
   DevBuf<Vb200TriRecord> setup;
   DevBuf<uint32_t> tileCount, list, triTiles;
   uint32_t *range = nullptr;                // device {min,max}
+  DevBuf<Vb200BatchDraw> batchDraws;        // device tables of a batch of several draws
+  DevBuf<Vb200VertexSpan> batchSpans;
+  int64_t optBatchDraws = 1;                // 0: every draw is rasterised by itself, as the reference replays them
   // ClearTarget()s not yet executed: device address of the attachment -> fill word and pixel count.
   // The next draw into the attachment folds them into its tile kernel; anything else that touches the
   // memory (another reader, a download) materialises them with the fill kernel first.
@@ -302,7 +352,10 @@ void phaseAccumulate(int phase, int a, int b)
     }                                                                                                  \
   } while(0)
 
-int requireReady()
+int flushBatch();    // launches the kernels of the draws recorded so far (below, next to vb200_draw)
+int flushBatchKeepOpen();
+
+int requireReadyKeepBatch()
 {
   if(!g.ready)
   {
@@ -313,6 +366,13 @@ int requireReady()
   if(g.stickyCuda)
     return setError(VB200_ERR_CUDA, "a previous CUDA error is sticky: %s", g_error.c_str());
   return VB200_OK;
+}
+
+// Every entry point but vb200_draw starts here: whatever it does is ordered after the draws recorded before it.
+int requireReady()
+{
+  int rc = requireReadyKeepBatch();
+  return rc ? rc : flushBatch();
 }
 
 void freeMirrorMemory(uint8_t *dev)
@@ -908,6 +968,8 @@ int set_error(int code, const char *fmt, ...)
 }
 cudaStream_t library_stream()
 {
+  if(g.ready)
+    flushBatch();    // whoever enqueues on the stream next comes after the recorded draws
   return g.ready ? g.stream : nullptr;
 }
 int library_device()
@@ -931,6 +993,309 @@ void clear_exchange_range(uint8_t *local)
   g.exchange.erase(local);
 }
 }    // namespace vb200
+
+// ---- batches of draws -------------------------------------------------------------------------
+// (declared here, next to their only writer; Context holds one)
+namespace
+{
+// Launches the kernels for draws [first, last) of the recorded batch as ONE vertex / setup / tile pass.
+int runBatch(size_t first, size_t last, bool foldClears)
+{
+  Batch &b = g.batch;
+  const BatchKey &k = b.key;
+  int rc;
+  // ---- vertex spans. Indexed draws that together reference at least as many indices as the bound buffers
+  // hold vertices (meshes; many sub-mesh draws out of one buffer) share ONE span over all bound vertices: no
+  // pass over the index buffer, every vertex shaded once for the whole batch. Otherwise each draw keeps the
+  // span measured for it.
+  uint64_t idxVerts = 0, idxSpan = 0;
+  bool wantAll = false, deviceRange = false;
+  for(size_t i = first; i < last; i++)
+  {
+    const Batch::Draw &d = b.draws[i];
+    if(d.kind == Batch::SPAN_ALL)
+      wantAll = true;
+    if(d.kind != Batch::SPAN_HOST)
+      idxVerts += d.usedVerts;
+    if(d.kind == Batch::SPAN_INDEXED)
+      idxSpan += d.spanCount;
+    if(d.kind == Batch::SPAN_DEVICE)
+      deviceRange = true;
+  }
+  if(deviceRange && last - first > 1)
+  {
+    // index data only the device can read: worth one shared span when the draws reference enough of the buffer
+    if(wantAll || idxVerts >= k.vertexBound / 4u)
+      wantAll = true;
+  }
+  else if(deviceRange)
+    wantAll = wantAll || idxVerts >= k.vertexBound;
+  else if(idxVerts >= k.vertexBound || idxSpan >= k.vertexBound)
+    wantAll = true;
+  if(deviceRange && !wantAll && last - first > 1)
+  {
+    // several draws whose ranges only the device can measure and that use a small part of a large buffer:
+    // one at a time (each measures its own range on the device)
+    for(size_t i = first; i < last; i++)
+      if((rc = runBatch(i, i + 1, foldClears && i == first)))
+        return rc;
+    return VB200_OK;
+  }
+  std::vector<Vb200VertexSpan> spans;
+  std::vector<Vb200BatchDraw> draws;
+  spans.reserve(last - first);
+  draws.reserve(last - first);
+  uint32_t records = 0, numTris = 0;
+  int allSpan = -1;
+  const uint32_t *rangeDev = nullptr;
+  for(size_t i = first; i < last; i++)
+  {
+    const Batch::Draw &d = b.draws[i];
+    Vb200BatchDraw dd = d.dev;
+    dd.tri_base = numTris;
+    numTris += dd.num_tris;
+    const bool all = d.kind == Batch::SPAN_ALL || (wantAll && d.kind != Batch::SPAN_HOST);
+    if(all)
+    {
+      if(allSpan < 0)
+      {
+        allSpan = (int)spans.size();
+        spans.push_back({0u, k.vertexBound, records, 0u});
+        records += k.vertexBound;
+      }
+      dd.span = (uint32_t)allSpan;
+    }
+    else if(d.kind == Batch::SPAN_DEVICE)
+    {
+      // alone in its batch: span0 = [min, max] of its indices (k_index_range), at most vertexBound records
+      g.stats.kernel_launches += vb200::launch_index_range(dd.ib, dd.index_type, dd.first, d.usedVerts, g.range, g.stream);
+      rangeDev = g.range;
+      dd.span = (uint32_t)spans.size();
+      spans.push_back({0u, k.vertexBound, records, 0u});
+      records += k.vertexBound;
+    }
+    else
+    {
+      // a span equal to the previous one is shared (the same vertices drawn again)
+      if(!spans.empty() && (int)spans.size() - 1 != allSpan && spans.back().src_base == d.spanBase &&
+         spans.back().count == d.spanCount)
+        dd.span = (uint32_t)spans.size() - 1u;
+      else
+      {
+        dd.span = (uint32_t)spans.size();
+        spans.push_back({d.spanBase, d.spanCount, records, 0u});
+        records += d.spanCount;
+      }
+    }
+    draws.push_back(dd);
+  }
+  if(records == 0 || numTris == 0)
+    return VB200_OK;
+
+  // ---- scratch
+  const uint32_t W = k.width, H = k.height;
+  const uint32_t tilesX = (W + VB200_TILE - 1) / VB200_TILE, tilesY = (H + VB200_TILE - 1) / VB200_TILE;
+  const uint32_t ntiles = tilesX * tilesY;
+  const uint32_t ownedTiles = (ntiles + g.ownerWorld - 1u) / g.ownerWorld;
+  // Entries per tile list: a power of two of at least four times the average load (a perspective mesh puts
+  // several times the average into its far tiles), within [256, 4096]. It is only a performance knob: a
+  // tile that receives more triangles than that is rasterised from the packed tile ranges instead.
+  uint32_t listCap = 256;
+  {
+    const uint64_t want = 4ull * numTris / std::max(1u, ntiles) + 64;
+    while(listCap < want && listCap < 4096u)
+      listCap <<= 1;
+    if(g.optTileListCap > 0)
+      listCap = (uint32_t)std::min<int64_t>(g.optTileListCap, 1 << 20);
+  }
+  const bool tables = draws.size() > 1;
+  if(!g.rv.reserve(records) || !g.interps.reserve((size_t)records * k.nslots) || !g.setup.reserve(numTris) ||
+     !g.triTiles.reserve(numTris) || !g.list.reserve((size_t)ownedTiles * listCap) || !g.tileCount.reserve(ntiles) ||
+     (tables && (!g.batchDraws.reserve(draws.size()) || !g.batchSpans.reserve(spans.size()))))
+  {
+    g.stickyCuda = 1;
+    return setError(VB200_ERR_CUDA, "out of device memory for draw scratch");
+  }
+  if(tables)
+  {
+    // (pageable source: the copy is staged by the driver before the call returns)
+    CU(cudaMemcpyAsync(g.batchDraws.p, draws.data(), draws.size() * sizeof(Vb200BatchDraw), cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(g.batchSpans.p, spans.data(), spans.size() * sizeof(Vb200VertexSpan), cudaMemcpyHostToDevice, g.stream));
+  }
+
+  // ---- K1: vertex stage
+  phaseMark(0);
+  Vb200VertexParams vp;
+  memset(&vp, 0, sizeof(vp));
+  vp.spans = (tables && spans.size() > 1) ? g.batchSpans.p : nullptr;
+  vp.num_spans = (uint32_t)spans.size();
+  vp.span0 = spans[0];
+  vp.range = rangeDev;
+  vp.count = records;
+  vp.vertex_bound = k.vertexBound;
+  vp.rv = g.rv.p;
+  vp.interps = g.interps.p;
+  vp.nslots = k.nslots;
+  vp.width = W;
+  vp.height = H;
+  vp.tile_count = g.tileCount.p;
+  vp.tile_count_n = ntiles;
+  Vb200Env env = k.env;
+  {
+    void *args[] = {&env, &vp};
+    if((rc = launchKernel(b.kVertex, dim3((records + 127) / 128), dim3(128), args)))
+      return rc;
+  }
+
+  // ---- K2: setup + binning
+  phaseMark(1);
+  Vb200SetupParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.draws = tables ? g.batchDraws.p : nullptr;
+  sp.spans = tables ? g.batchSpans.p : nullptr;
+  sp.num_draws = (uint32_t)draws.size();
+  sp.draw0 = draws[0];
+  sp.span0 = spans[0];
+  sp.range = rangeDev;
+  sp.num_tris = numTris;
+  sp.topology = k.topology;
+  sp.vertex_bound = k.vertexBound;
+  sp.rv = g.rv.p;
+  sp.tri = g.setup.p;
+  sp.tri_tiles = g.triTiles.p;
+  sp.tile_count = g.tileCount.p;
+  sp.list = g.list.p;
+  sp.list_cap = listCap;
+  sp.counters = g.counters;
+  sp.front_face = k.frontFace;
+  sp.cull_mode = k.cullMode;
+  sp.width = W;
+  sp.height = H;
+  sp.tiles_x = tilesX;
+  sp.tiles_y = tilesY;
+  sp.owner_rank = g.ownerRank;
+  sp.owner_world = g.ownerWorld;
+  g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);    // (the vertex kernel zeroed the tile counters)
+  phaseMark(2);
+
+  g.lastTileKernel = kKernelNames[k.tileKernelId];
+  Vb200TileParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.tri = g.setup.p;
+  tp.rv = g.rv.p;
+  tp.list = g.list.p;
+  tp.list_cap = listCap;
+  tp.tile_count = g.tileCount.p;
+  tp.tri_tiles = g.triTiles.p;
+  tp.num_tris = numTris;
+  tp.color = (uint32_t *)k.colorDev;
+  tp.depth = (float *)k.depthDev;
+  tp.interps = g.interps.p;
+  tp.counters = g.counters;
+  tp.rs.width = W;
+  tp.rs.height = H;
+  tp.rs.tiles_x = tilesX;
+  tp.rs.tiles_y = tilesY;
+  tp.rs.tiles_x_magic = (uint32_t)(0x100000000ull / tilesX) + 1u;
+  tp.unorm = g.unorm;
+  tp.rs.depth_op = k.depthOp;
+  tp.rs.depth_write = k.depthWrite;
+  tp.rs.has_depth = k.depthDev ? 1u : 0u;
+  tp.rs.blend_enable = k.blend[0];
+  tp.rs.src_factor = k.blend[1];
+  tp.rs.dst_factor = k.blend[2];
+  tp.rs.blend_op = k.blend[3];
+  tp.rs.nslots = k.nslots;
+  tp.rs.owner_rank = g.ownerRank;
+  tp.rs.owner_world = g.ownerWorld;
+  tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
+  tp.rs.color_bpp = 4;
+  tp.rs.slot_keys = (g.optSlotKeys && numTris < (1u << 24) - 1u) ? 1u : 0u;
+  if(foldClears)
+  {
+    tp.clear_flags = b.clearFlags;
+    tp.clear_color = b.clearColorWord;
+    tp.clear_depth = b.clearDepthValue;
+  }
+  if(g.ownerWorld > 1)
+  {
+    auto it = g.exchange.upper_bound(k.colorDev);
+    if(it != g.exchange.begin())
+    {
+      --it;
+      const size_t off = (size_t)(k.colorDev - it->first);
+      if(it->second.exact ? off == 0 : off + (size_t)W * H * 4 <= it->second.bytes)
+      {
+        if(it->second.multicast)
+          tp.mc_color = (uint32_t *)(it->second.multicast + off);
+        else
+        {
+          tp.num_peers = (uint32_t)std::min<size_t>(it->second.peers.size(), 7);
+          for(uint32_t r = 0; r < tp.num_peers; r++)
+            tp.peer_color[r] = (uint32_t *)(it->second.peers[r] + off);
+        }
+      }
+    }
+  }
+
+  // ---- K3' + K4. The ordered path needs each tile's list in submission order (the appends of the setup
+  // kernel arrive in any order); nothing here waits for the device.
+  if(k.tileKernelId == K_TILE_ORDERED)
+    g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileCount.p, listCap, g.ownerRank, g.ownerWorld, ntiles,
+                                                  g.stream);
+  phaseMark(3);
+  {
+    void *args[] = {&env, &tp};
+    if((rc = launchKernel(b.kTile, dim3(ownedTiles), dim3(b.tileThreads), args)))
+      return rc;
+  }
+  phaseMark(4);
+  phaseAccumulate(VB200_PHASE_VERTEX, 0, 1);
+  phaseAccumulate(VB200_PHASE_SETUP, 1, 2);
+  phaseAccumulate(VB200_PHASE_BIN, 2, 3);
+  phaseAccumulate(VB200_PHASE_TILES, 3, 4);
+  CU(cudaGetLastError());
+  return VB200_OK;
+}
+
+// runs what has been recorded; the batch stays open for more draws with the same key
+int flushBatchKeepOpen()
+{
+  Batch &b = g.batch;
+  if(!b.active || b.draws.empty())
+    return VB200_OK;
+  const int rc = runBatch(0, b.draws.size(), !b.ran);
+  b.ran = true;
+  b.draws.clear();
+  b.numTris = b.numVerts = 0;
+  return rc;
+}
+
+int flushBatch()
+{
+  Batch &b = g.batch;
+  if(!b.active)
+    return VB200_OK;
+  b.active = false;    // (first: runBatch's helpers must not re-enter)
+  int rc = VB200_OK;
+  if(!b.draws.empty())
+    rc = runBatch(0, b.draws.size(), !b.ran);
+  else if(!b.ran && b.clearFlags)
+  {
+    // the clears this batch took over were never folded into a tile kernel: put them back
+    if(b.clearFlags & 1u)
+      g.pendingClears[b.key.colorDev] = {b.clearColorWord, (size_t)b.key.width * b.key.height};
+    if(b.clearFlags & 2u)
+    {
+      uint32_t bits;
+      memcpy(&bits, &b.clearDepthValue, 4);
+      g.pendingClears[b.key.depthDev] = {bits, (size_t)b.key.width * b.key.height};
+    }
+  }
+  b.reset();
+  return rc;
+}
+}    // namespace
 
 // =================================================================================================
 extern "C" {
@@ -1009,6 +1374,7 @@ void vb200_shutdown(void)
 {
   if(!g.ready)
     return;
+  flushBatch();
   cudaStreamSynchronize(g.stream);
   for(auto &kv : g.kernels)
     cudaLibraryUnload(kv.second.lib);
@@ -1027,6 +1393,8 @@ void vb200_shutdown(void)
   g.list.release();
   cudaFree(g.range);
   g.triTiles.release();
+  g.batchDraws.release();
+  g.batchSpans.release();
   cudaFree(g.counters);
   cudaFree(g.unorm);
   for(auto &pr : g.presents)
@@ -1046,6 +1414,8 @@ void vb200_shutdown(void)
 
 void *vb200_stream(void)
 {
+  if(g.ready)
+    flushBatch();    // work the caller enqueues comes after the recorded draws
   return g.ready ? (void *)g.stream : nullptr;
 }
 
@@ -1092,6 +1462,8 @@ void vb200_shader_destroy(vb200_shader *shader)
 {
   if(!shader)
     return;
+  if(g.ready)
+    flushBatch();    // recorded draws may still need them
   // drop the kernels compiled for this module's entries
   for(auto &e : shader->entries)
     for(auto it = g.kernels.begin(); it != g.kernels.end();)
@@ -1162,6 +1534,8 @@ int vb200_entry_resource(const vb200_entry *entry, int index, uint32_t *set, uin
 // ---- residency -------------------------------------------------------------------------------
 int vb200_set_sync_mode(int mode)
 {
+  if(g.ready)
+    flushBatch();
   if(mode != VB200_SYNC_COHERENT && mode != VB200_SYNC_EXPLICIT)
     return setError(VB200_ERR_INVALID, "unknown sync mode %d", mode);
   g.syncMode = mode;
@@ -1212,6 +1586,8 @@ int vb200_mem_register(void *host, uint64_t size)
 
 int vb200_mem_unregister(void *host)
 {
+  if(g.ready)
+    flushBatch();
   if(!g.ready)
     return VB200_OK;
   auto it = g.mirrors.find((uintptr_t)host);
@@ -1618,7 +1994,7 @@ int vb200_clear_depth(const vb200_image *target, float depth)
 
 int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int indexed)
 {
-  int rc = requireReady();
+  int rc = requireReadyKeepBatch();
   if(rc)
     return rc;
   if(!s || !s->pipeline)
@@ -1704,10 +2080,9 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     return rc;
   memcpy(env.push, s->pushconsts, 128);
 
-  // ---- index buffer / vertex range
+  // ---- index buffer
   const uint8_t *ibDev = nullptr;
-  uint32_t capacity, baseVertex = first;
-  bool shadeAll = false;    // indexed draw that shades vertices [0, capacity): no device-side index range
+  const uint8_t *ibHost = nullptr;    // the same indices in host memory, when the host copy is known to be current
   if(indexed)
   {
     if(!s->ib.buffer.bytes)
@@ -1721,59 +2096,25 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     ibDev = dev + s->ib.offset;
     if(((uintptr_t)ibDev) & (isz - 1))
       return setError(VB200_ERR_INVALID, "index buffer offset is not aligned to the index size");
-    phaseMark(0);
-    // Which vertices to shade. When the bound vertex buffers hold no more vertices than the draw has
-    // indices (meshes: every vertex is referenced several times) all of them are shaded and the pass
-    // over the index buffer that finds [min, max] is skipped (C5: 48 MB of index reads). Otherwise
-    // (a small draw out of a large shared vertex buffer) the range is measured first.
-    shadeAll = vertexBound != 0xffffffffu && vertexBound <= usedVerts;
-    if(!shadeAll)
-      g.stats.kernel_launches += vb200::launch_index_range(ibDev, s->ib.index_type, first, usedVerts, g.range, g.stream);
-    if(vertexBound == 0xffffffffu)
+    if(g.syncMode == VB200_SYNC_COHERENT && !isDevicePointer(s->ib.buffer.bytes))
     {
-      // no strided attribute bounds the vertex count: read the range back (rare: index-only shaders)
-      uint32_t r2[2];
-      CU(cudaMemcpyAsync(r2, g.range, 8, cudaMemcpyDeviceToHost, g.stream));
-      CU(cudaStreamSynchronize(g.stream));
-      capacity = r2[1] >= r2[0] ? r2[1] - r2[0] + 1u : 0u;
+      // coherent mode: host memory is authoritative unless device work of this submit wrote the range
+      Mirror *m = findMirror(s->ib.buffer.bytes, s->ib.buffer.size);
+      if(m && !m->deviceLocal)
+      {
+        const size_t lo = (uintptr_t)s->ib.buffer.bytes - (uintptr_t)m->host + s->ib.offset + (size_t)first * isz;
+        IntervalSet none;
+        auto clean = m->written.gaps(lo, lo + (size_t)usedVerts * isz, none);
+        if(clean.size() == 1 && clean[0].first == lo && clean[0].second == lo + (size_t)usedVerts * isz)
+          ibHost = (const uint8_t *)s->ib.buffer.bytes + s->ib.offset + (size_t)first * isz;
+      }
     }
-    else
-      capacity = vertexBound;
-    baseVertex = 0;
   }
-  else
-  {
-    capacity = usedVerts;
-    if(vertexBound != 0xffffffffu && (uint64_t)first + usedVerts > vertexBound)
-      return setError(VB200_ERR_INVALID, "draw reads vertices beyond the bound vertex buffers");
-  }
-  if(capacity == 0)
-    return VB200_OK;
-
-  // ---- scratch
-  const uint32_t W = s->color.width, H = s->color.height;
-  const uint32_t tilesX = (W + VB200_TILE - 1) / VB200_TILE, tilesY = (H + VB200_TILE - 1) / VB200_TILE;
-  const uint32_t ntiles = tilesX * tilesY;
-  const uint32_t ownedTiles = (ntiles + g.ownerWorld - 1u) / g.ownerWorld;
-  // Entries per tile list: a power of two of at least four times the average load (a perspective mesh puts
-  // several times the average into its far tiles), within [256, 4096]. It is only a performance knob: a
-  // tile that receives more triangles than that is rasterised from the packed tile ranges instead.
-  uint32_t listCap = 256;
-  {
-    const uint64_t want = 4ull * numTris / std::max(1u, ntiles) + 64;
-    while(listCap < want && listCap < 4096u)
-      listCap <<= 1;
-    if(g.optTileListCap > 0)
-      listCap = (uint32_t)std::min<int64_t>(g.optTileListCap, 1 << 20);
-  }
-  if(!g.rv.reserve(capacity) || !g.interps.reserve((size_t)capacity * nslots) || !g.setup.reserve(numTris) ||
-     !g.triTiles.reserve(numTris) || !g.list.reserve((size_t)ownedTiles * listCap) || !g.tileCount.reserve(ntiles))
-  {
-    g.stickyCuda = 1;
-    return setError(VB200_ERR_CUDA, "out of device memory for draw scratch");
-  }
+  else if(vertexBound != 0xffffffffu && (uint64_t)first + usedVerts > vertexBound)
+    return setError(VB200_ERR_INVALID, "draw reads vertices beyond the bound vertex buffers");
 
   // ---- targets
+  const uint32_t W = s->color.width, H = s->color.height;
   uint8_t *colorDev, *depthDev = nullptr;
   if((rc = resolve(s->color.pixels, (size_t)W * H * 4, ACC_READ | ACC_WRITE | ACC_KEEP_PENDING, &colorDev)))
     return rc;
@@ -1782,32 +2123,6 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   if(hasDepth && (depthTest || depthWrite))
     if((rc = resolve(s->depth.pixels, (size_t)W * H * 4, ACC_READ | ACC_WRITE | ACC_KEEP_PENDING, &depthDev)))
       return rc;
-  // deferred clears of exactly these attachments are folded into the tile kernel (single GPU only:
-  // with sort-first ownership a rank does not write every tile); anything else is materialised now
-  uint32_t clearFlags = 0, clearColorWord = 0;
-  float clearDepthValue = 0.0f;
-  {
-    auto take = [&](uint8_t *dev, uint32_t bit, uint32_t *word) {
-      auto it = g.pendingClears.find(dev);
-      // with sort-first ownership a rank clears only the tiles it owns: colour of the others arrives from
-      // their owners (peer stores or the all-gather), their depth is never read on this rank
-      if(it != g.pendingClears.end() && it->second.count == (size_t)W * H)
-      {
-        clearFlags |= bit;
-        *word = it->second.value;
-        g.pendingClears.erase(it);
-      }
-    };
-    uint32_t depthBits = 0;
-    take(colorDev, 1u, &clearColorWord);
-    if(depthDev)
-      take(depthDev, 2u, &depthBits);
-    memcpy(&clearDepthValue, &depthBits, 4);
-    if((rc = materializeClears(colorDev, (size_t)W * H * 4)))
-      return rc;
-    if(depthDev && (rc = materializeClears(depthDev, (size_t)W * H * 4)))
-      return rc;
-  }
 
   // Raster back end. A pass is order-independent ("resolvable") unless it blends or runs
   // NOT_EQUAL against a depth buffer it also writes; see scaffold.cu.
@@ -1832,146 +2147,133 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   }
   if(g.optRasterPath == 1)
     resolveMode = -1;
-  const int tileKernelId = resolveMode >= 0 ? K_TILE_RESOLVE + resolveMode : K_TILE_ORDERED;
-  cudaKernel_t kTile = nullptr;
-  unsigned tileThreads = 256;
-  if((rc = getKernel(tileKernelId, pl->fs, &kTile, &tileThreads)))
-    return rc;
-  if(!tileThreads)
-    return setError(VB200_ERR_LINK, "kernel scaffold without a CTA size");
-  g.lastTileKernel = kKernelNames[tileKernelId];
 
-  const bool slotKeys = g.optSlotKeys && numTris < (1u << 24) - 1u;
-
-  // ---- K1: vertex stage
-  if(!indexed)
-    phaseMark(0);
-  Vb200VertexParams vp;
-  vp.range = (indexed && !shadeAll) ? g.range : nullptr;
-  vp.base_vertex = baseVertex;
-  vp.count = capacity;
-  vp.vertex_bound = vertexBound;
-  vp.rv = g.rv.p;
-  vp.interps = g.interps.p;
-  vp.nslots = nslots;
-  vp.width = W;
-  vp.height = H;
-  vp.tile_count = g.tileCount.p;
-  vp.tile_count_n = ntiles;
-  {
-    cudaKernel_t kVertex = nullptr;
-    if((rc = getKernel(K_VERTEX, pl->vs, &kVertex)))
+  // ---- the batch this draw joins (kernels.h: Vb200BatchDraw). Everything that is uniform across a kernel
+  // launch is part of the key; a draw with another key ends the recorded batch and starts the next.
+  BatchKey key;
+  memset(&key, 0, sizeof(key));
+  key.env = env;
+  key.vs = pl->vs->serial;
+  key.fs = pl->fs->serial;
+  key.topology = pl->topology;
+  key.frontFace = pl->front_face;
+  key.cullMode = pl->cull_mode;
+  key.depthOp = pl->depth_compare_op;
+  key.depthWrite = depthWrite ? 1u : 0u;
+  key.blend[0] = pl->blend_enable ? 1u : 0u;
+  key.blend[1] = pl->src_color_blend_factor;
+  key.blend[2] = pl->dst_color_blend_factor;
+  key.blend[3] = pl->color_blend_op;
+  key.colorDev = colorDev;
+  key.depthDev = depthDev;
+  key.width = W;
+  key.height = H;
+  key.vertexBound = vertexBound;
+  key.nslots = nslots;
+  key.tileKernelId = resolveMode >= 0 ? K_TILE_RESOLVE + resolveMode : K_TILE_ORDERED;
+  Batch &b = g.batch;
+  if(b.active && (b.closed || !g.optBatchDraws || memcmp(&b.key, &key, sizeof(key)) != 0 || b.draws.size() >= 8192 ||
+                  b.numTris + (uint64_t)numTris >= (1u << 24) - 1u || b.numVerts + (uint64_t)usedVerts >= (1u << 30)))
+    if((rc = flushBatch()))
       return rc;
-    void *args[] = {&env, &vp};
-    if((rc = launchKernel(kVertex, dim3((capacity + 127) / 128), dim3(128), args)))
-      return rc;
-  }
-
-  // ---- K2: setup + per-tile counts
-  phaseMark(1);
-  Vb200SetupParams sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.ib = ibDev;
-  sp.index_type = s->ib.index_type;
-  sp.indexed = indexed ? 1u : 0u;
-  sp.first = first;
-  sp.num_tris = numTris;
-  sp.topology = pl->topology;
-  sp.range = shadeAll ? nullptr : g.range;
-  sp.base_vertex = baseVertex;
-  sp.capacity = capacity;
-  sp.vertex_bound = indexed ? vertexBound : 0xffffffffu;
-  sp.rv = g.rv.p;
-  sp.tri = g.setup.p;
-  sp.tri_tiles = g.triTiles.p;
-  sp.tile_count = g.tileCount.p;
-  sp.list = g.list.p;
-  sp.list_cap = listCap;
-  sp.counters = g.counters;
-  sp.front_face = pl->front_face;
-  sp.cull_mode = pl->cull_mode;
-  sp.width = W;
-  sp.height = H;
-  sp.tiles_x = tilesX;
-  sp.tiles_y = tilesY;
-  sp.owner_rank = g.ownerRank;
-  sp.owner_world = g.ownerWorld;
-  g.stats.kernel_launches += vb200::launch_setup(sp, g.stream);    // (the vertex kernel zeroed the tile counters)
-  phaseMark(2);
-
-  Vb200TileParams tp;
-  memset(&tp, 0, sizeof(tp));
-  tp.tri = g.setup.p;
-  tp.rv = g.rv.p;
-  tp.list = g.list.p;
-  tp.list_cap = listCap;
-  tp.tile_count = g.tileCount.p;
-  tp.tri_tiles = g.triTiles.p;
-  tp.num_tris = numTris;
-  tp.color = (uint32_t *)colorDev;
-  tp.depth = (float *)depthDev;
-  tp.interps = g.interps.p;
-  tp.counters = g.counters;
-  tp.rs.width = W;
-  tp.rs.height = H;
-  tp.rs.tiles_x = tilesX;
-  tp.rs.tiles_y = tilesY;
-  tp.rs.tiles_x_magic = (uint32_t)(0x100000000ull / tilesX) + 1u;
-  tp.unorm = g.unorm;
-  tp.rs.depth_op = pl->depth_compare_op;
-  tp.rs.depth_write = depthWrite ? 1u : 0u;
-  tp.rs.has_depth = depthDev ? 1u : 0u;
-  tp.rs.blend_enable = pl->blend_enable ? 1u : 0u;
-  tp.rs.src_factor = pl->src_color_blend_factor;
-  tp.rs.dst_factor = pl->dst_color_blend_factor;
-  tp.rs.blend_op = pl->color_blend_op;
-  tp.rs.nslots = nslots;
-  tp.rs.owner_rank = g.ownerRank;
-  tp.rs.owner_world = g.ownerWorld;
-  tp.rs.count_fragments = g.optCountFragments ? 1u : 0u;
-  tp.rs.color_bpp = 4;
-  tp.rs.slot_keys = slotKeys ? 1u : 0u;
-  tp.clear_flags = clearFlags;
-  tp.clear_color = clearColorWord;
-  tp.clear_depth = clearDepthValue;
-  if(g.ownerWorld > 1)
+  if(!b.active)
   {
-    auto it = g.exchange.upper_bound(colorDev);
-    if(it != g.exchange.begin())
-    {
-      --it;
-      const size_t off = (size_t)(colorDev - it->first);
-      if(it->second.exact ? off == 0 : off + (size_t)W * H * 4 <= it->second.bytes)
+    b.reset();
+    b.key = key;
+    if((rc = getKernel(K_VERTEX, pl->vs, &b.kVertex)))
+      return rc;
+    if((rc = getKernel(key.tileKernelId, pl->fs, &b.kTile, &b.tileThreads)))
+      return rc;
+    if(!b.tileThreads)
+      return setError(VB200_ERR_LINK, "kernel scaffold without a CTA size");
+    // deferred clears of exactly these attachments are folded into the tile kernel; anything else that
+    // overlaps them is materialised now
+    auto take = [&](uint8_t *dev, uint32_t bit, uint32_t *word) {
+      auto it = g.pendingClears.find(dev);
+      // with sort-first ownership a rank clears only the tiles it owns: colour of the others arrives from
+      // their owners (peer stores or the all-gather), their depth is never read on this rank
+      if(it != g.pendingClears.end() && it->second.count == (size_t)W * H)
       {
-        if(it->second.multicast)
-          tp.mc_color = (uint32_t *)(it->second.multicast + off);
-        else
-        {
-          tp.num_peers = (uint32_t)std::min<size_t>(it->second.peers.size(), 7);
-          for(uint32_t r = 0; r < tp.num_peers; r++)
-            tp.peer_color[r] = (uint32_t *)(it->second.peers[r] + off);
-        }
+        b.clearFlags |= bit;
+        *word = it->second.value;
+        g.pendingClears.erase(it);
       }
-    }
+    };
+    uint32_t depthBits = 0;
+    take(colorDev, 1u, &b.clearColorWord);
+    if(depthDev)
+      take(depthDev, 2u, &depthBits);
+    memcpy(&b.clearDepthValue, &depthBits, 4);
+    if((rc = materializeClears(colorDev, (size_t)W * H * 4)))
+      return rc;
+    if(depthDev && (rc = materializeClears(depthDev, (size_t)W * H * 4)))
+      return rc;
+    b.active = true;
   }
 
-  // ---- K3' + K4. The ordered path needs each tile's list in submission order (the appends of the setup
-  // kernel arrive in any order); nothing here waits for the device.
-  if(resolveMode < 0)
-    g.stats.kernel_launches += vb200::launch_sort(g.list.p, g.tileCount.p, listCap, g.ownerRank, g.ownerWorld, ntiles,
-                                                  g.stream);
-  phaseMark(3);
+  // ---- the draw's vertex span
+  Batch::Draw d;
+  memset(&d, 0, sizeof(d));
+  d.dev.ib = ibDev;
+  d.dev.index_type = s->ib.index_type;
+  d.dev.first = first;
+  d.dev.num_tris = numTris;
+  d.dev.tri_base = (uint32_t)b.numTris;
+  d.usedVerts = usedVerts;
+  if(!indexed)
   {
-    void *args[] = {&env, &tp};
-    if((rc = launchKernel(kTile, dim3(ownedTiles), dim3(tileThreads), args)))
-      return rc;
+    d.kind = Batch::SPAN_HOST;
+    d.spanBase = first;
+    d.spanCount = usedVerts;
   }
-  phaseMark(4);
-  phaseAccumulate(VB200_PHASE_VERTEX, 0, 1);
-  phaseAccumulate(VB200_PHASE_SETUP, 1, 2);
-  phaseAccumulate(VB200_PHASE_BIN, 2, 3);
-  phaseAccumulate(VB200_PHASE_TILES, 3, 4);
-  CU(cudaGetLastError());
+  else if(vertexBound == 0xffffffffu)
+  {
+    // no strided attribute bounds the vertex count (rare: index-only shaders): measure the range now and
+    // read it back
+    if((rc = flushBatchKeepOpen()))
+      return rc;
+    g.stats.kernel_launches += vb200::launch_index_range(ibDev, s->ib.index_type, first, usedVerts, g.range, g.stream);
+    uint32_t r2[2];
+    CU(cudaMemcpyAsync(r2, g.range, 8, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    if(r2[1] < r2[0])
+      return VB200_OK;
+    d.kind = Batch::SPAN_HOST;
+    d.spanBase = r2[0];
+    d.spanCount = r2[1] - r2[0] + 1u;
+  }
+  else if(vertexBound <= usedVerts)
+    d.kind = Batch::SPAN_ALL;    // a mesh: every bound vertex is referenced several times, all are shaded
+  else if(ibHost && usedVerts <= (1u << 16))
+  {
+    // a small draw out of a larger vertex buffer, indices readable on the host: measure [min, max] here
+    uint32_t lo = 0xffffffffu, hi = 0;
+    if(s->ib.index_type == 0u)
+      for(uint32_t i = 0; i < usedVerts; i++)
+      {
+        uint16_t v;
+        memcpy(&v, ibHost + 2 * (size_t)i, 2);
+        lo = std::min<uint32_t>(lo, v);
+        hi = std::max<uint32_t>(hi, v);
+      }
+    else
+      for(uint32_t i = 0; i < usedVerts; i++)
+      {
+        uint32_t v;
+        memcpy(&v, ibHost + 4 * (size_t)i, 4);
+        lo = std::min(lo, v);
+        hi = std::max(hi, v);
+      }
+    d.kind = Batch::SPAN_INDEXED;
+    d.spanBase = lo;
+    // (indices at or beyond vertexBound kill their triangle in the setup kernel; nothing beyond is shaded)
+    d.spanCount = lo < vertexBound ? std::min(hi, vertexBound - 1u) - lo + 1u : 0u;
+  }
+  else
+    d.kind = Batch::SPAN_DEVICE;    // measured by k_index_range when the batch runs
+  b.draws.push_back(d);
+  b.numTris += numTris;
+  b.numVerts += usedVerts;
   return VB200_OK;
 }
 
@@ -2016,6 +2318,8 @@ int vb200_sample(const vb200_image *tex, int cube, uint64_t byte_offset, const f
 // ---- multi-GPU ---------------------------------------------------------------------------------
 int vb200_set_tile_owner(int rank, int world)
 {
+  if(g.ready)
+    flushBatch();
   if(world < 1 || rank < 0 || rank >= world)
     return setError(VB200_ERR_INVALID, "bad tile owner %d/%d", rank, world);
   g.ownerRank = (uint32_t)rank;
@@ -2025,6 +2329,8 @@ int vb200_set_tile_owner(int rank, int world)
 
 int vb200_set_peer_targets(const void *local_color_device, void *const *peer_color_device, int num_peers)
 {
+  if(g.ready)
+    flushBatch();
   if(!local_color_device || num_peers < 0 || num_peers > 7 || (num_peers && !peer_color_device))
     return setError(VB200_ERR_INVALID, "set_peer_targets: bad arguments (at most 7 peers)");
   uint8_t *local = (uint8_t *)local_color_device;
@@ -2054,6 +2360,8 @@ int vb200_set_peer_targets(const void *local_color_device, void *const *peer_col
 
 int vb200_set_multicast_target(const void *local_color_device, void *multicast_device)
 {
+  if(g.ready)
+    flushBatch();
   if(!local_color_device)
     return setError(VB200_ERR_INVALID, "set_multicast_target: NULL image");
   uint8_t *local = (uint8_t *)local_color_device;
@@ -2149,6 +2457,8 @@ int vb200_get_stats(vb200_stats *out)
 
 void vb200_reset_stats(void)
 {
+  if(g.ready)
+    flushBatch();
   memset(&g.stats, 0, sizeof(g.stats));
   if(g.ready)
     cudaMemsetAsync(g.counters, 0, sizeof(Vb200DrawCounters), g.stream);
@@ -2208,12 +2518,16 @@ int vb200_set_option(const char *name, int64_t value)
 {
   if(!name)
     return setError(VB200_ERR_INVALID, "set_option: NULL name");
+  if(g.ready)
+    flushBatch();    // recorded draws run under the settings they were recorded with
   if(!strcmp(name, "raster_path"))
     g.optRasterPath = value;
   else if(!strcmp(name, "count_fragments"))
     g.optCountFragments = value;
   else if(!strcmp(name, "fuse_clears"))
     g.optFuseClears = value;
+  else if(!strcmp(name, "batch_draws"))
+    g.optBatchDraws = value;
   else if(!strcmp(name, "slot_keys"))
     g.optSlotKeys = value;
   else if(!strcmp(name, "tile_list_cap"))

@@ -142,24 +142,35 @@ extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_co
 {
   for(uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < p.tile_count_n; j += gridDim.x * blockDim.x)
     p.tile_count[j] = 0u;
-  uint32_t base = p.base_vertex, count = p.count;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  Vb200VertexSpan sp = p.span0;
+  uint32_t count = p.count;
   if(p.range)
   {
+    // the lone draw whose span is measured on the device (k_index_range): vertices [min, max], never beyond
+    // the bound vertex buffers (a malformed index must not make the fetch run past them)
     const uint32_t lo = p.range[0], hi = p.range[1];
-    if(hi < lo)
+    if(hi < lo || lo >= p.vertex_bound)
       return;
-    base = lo;
-    const uint32_t span = hi - lo + 1u;
-    count = span < count ? span : count;
-    // a malformed index beyond the bound vertex buffers must not make the fetch run past them
-    if(lo >= p.vertex_bound)
-      return;
-    count = min(count, p.vertex_bound - lo);
+    sp.src_base = lo;
+    count = min(min(hi - lo + 1u, count), p.vertex_bound - lo);
   }
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= count)
     return;
-  const float4 pos = vb200_vs(&env, base + i, p.interps + (size_t)i * p.nslots);
+  if(p.spans)
+  {
+    uint32_t lo = 0, hi = p.num_spans;    // the last span whose slot_base is <= i (empty spans never match)
+    while(hi - lo > 1u)
+    {
+      const uint32_t mid = (lo + hi) >> 1;
+      if(__ldg(&p.spans[mid].slot_base) <= i)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    sp = p.spans[lo];
+  }
+  const float4 pos = vb200_vs(&env, sp.src_base + (i - sp.slot_base), p.interps + (size_t)i * p.nslots);
 
   Vb200RasterVertex rv;
   // ToWindow (rasterizer.cpp:248-249):
@@ -192,11 +203,11 @@ extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_co
 struct TriSmem    // 80 B
 {
   int A1, B1, C1, A2;
-  int B2, C2, area, box;    // box: bbox clipped to the region, region-relative: x0 | x1<<8 | y0<<16 | y1<<24 (half open)
+  int B2, C2, area, box;    // box: bbox clipped to the region, region-relative: x0 | y0 << 8 | width << 16 | pixels << 24
   float invarea, invw0, invw1, invw2;
   float d0, d1, d2;
   uint32_t s0;
-  uint32_t s1, s2, pad0, pad1;
+  uint32_t s1, s2, wrecip, pad1;    // wrecip = ceil(65536 / width): p / width == (p * wrecip) >> 16 for p < 4096
 };
 
 // blend factor (rasterizer.cpp:601-653) as selects on the uniform factor enum
@@ -238,7 +249,9 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
   const bool depthWrite = rs.has_depth && rs.depth_write;
   const bool blend = rs.blend_enable != 0u && rs.blend_op == 0u;    // only ADD is defined (rasterizer.cpp:657-669)
 
+#if !VB200_UNORM_NEWTON
   vb200_s_unorm[threadIdx.x] = __ldg(p.unorm + threadIdx.x);
+#endif
   uint32_t *wcol = s_col[warp];
   float *wdep = s_dep[warp];
   uint16_t *wq = s_queue[warp];
@@ -255,9 +268,12 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
     wcol[i] = clearColor ? p.clear_color : (in ? p.color[idx] : 0u);
     wdep[i] = clearDepth ? p.clear_depth : ((in && rs.has_depth) ? p.depth[idx] : 0.0f);
   }
+#if !VB200_UNORM_NEWTON
   __syncthreads();    // vb200_s_unorm is shared by all warps; after this the warps run independently
+#else
+  __syncwarp();    // a warp's region is its own: the warps run independently from the start
+#endif
   uint32_t covered = 0, shaded = 0;
-  const int lx = lane & 15, ly = lane >> 4;    // lane's pixel column / first row inside the region
   const uint32_t below = (1u << lane) - 1u;
   uint32_t qhead = 0, qcount = 0;              // the warp's fragment ring (uniform across the lanes)
 
@@ -303,8 +319,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
           if(blend)
           {
             // blend (rasterizer.cpp:593-672): existing = bytes (2,1,0) / 255.0f from the exact table
-            const float ex = vb200_s_unorm[(cur >> 16) & 0xffu], ey = vb200_s_unorm[(cur >> 8) & 0xffu],
-                        ez = vb200_s_unorm[cur & 0xffu];
+            const float ex = vb200_unorm8(vb200_s_unorm, (cur >> 16) & 0xffu),
+                        ey = vb200_unorm8(vb200_s_unorm, (cur >> 8) & 0xffu), ez = vb200_unorm8(vb200_s_unorm, cur & 0xffu);
             const float oma = __fsub_rn(1.0f, pix.w);
             const float srcF = vb200_factor_sel(rs.src_factor, pix.w, oma);
             const float dstF = vb200_factor_sel(rs.dst_factor, pix.w, oma);
@@ -392,7 +408,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
         s.B2 = sgn * ABx;
         s.C2 = sgn * (ABy * su.x0 - ABx * su.y0) + s.A2 * rx0 + s.B2 * ry0;
         s.area = sgn * area2;
-        s.box = bx0 | (bx1 << 8) | (by0 << 16) | (by1 << 24);
+        const int bw = bx1 - bx0;    // 1..16; the box holds at most 16 x 8 = 128 pixels
+        s.box = bx0 | (by0 << 8) | (bw << 16) | ((bw * (by1 - by0)) << 24);
         s.invarea = su.invarea;
         s.invw0 = su.invw0;
         s.invw1 = su.invw1;
@@ -403,7 +420,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
         s.s0 = su.s0;
         s.s1 = su.s1;
         s.s2 = su.s2;
-        s.pad0 = s.pad1 = 0;
+        s.wrecip = (65536u + (uint32_t)bw - 1u) / (uint32_t)bw;
+        s.pad1 = 0;
         wtri[lane] = s;
       }
     }
@@ -416,30 +434,34 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
       const int k = __ffs(hits) - 1;
       hits &= hits - 1u;
       const TriSmem &t = wtri[k];
-      const int bx0 = t.box & 0xff, bx1 = (t.box >> 8) & 0xff, by0 = (t.box >> 16) & 0xff, by1 = (int)((uint32_t)t.box >> 24);
-      const int e1 = t.A1 * lx + t.B1 * ly + t.C1, e2 = t.A2 * lx + t.B2 * ly + t.C2;
-      const bool xin = lx >= bx0 && lx < bx1;
-      uint32_t m[4];
+      // The pixels of the triangle's clipped bbox (row-major, at most 128), 32 per pass, one per lane: a
+      // particle-sized box takes one or two ballots where testing the whole 16x8 region always took four.
+      const int bx0 = t.box & 0xff, by0 = (t.box >> 8) & 0xff, bw = (t.box >> 16) & 0xff;
+      const uint32_t npx = (uint32_t)t.box >> 24;
+      const uint32_t tag = (uint32_t)k << 7;
+      uint32_t tail = qhead + qcount, total = 0;
 #pragma unroll
-      for(int j = 0; j < 4; j++)
+      for(uint32_t j = 0; j < 4u; j++)
       {
-        const int y = ly + 2 * j;
-        const int b1 = e1 + 2 * j * t.B1, b2 = e2 + 2 * j * t.B2;
+        if(32u * j >= npx)
+          break;
+        const uint32_t pi = (uint32_t)lane + 32u * j;
+        const int dy = (int)((pi * t.wrecip) >> 16), dx = (int)pi - dy * bw;
+        const int x = bx0 + dx, y = by0 + dy;
+        const int b1 = t.A1 * x + t.B1 * y + t.C1, b2 = t.A2 * x + t.B2 * y + t.C2;
         const int b0 = t.area - (b1 + b2);
-        // covered iff all three >= 0 (rasterizer.cpp:549), inside the half-open clipped bbox
-        const bool inside = ((b0 | b1 | b2) >= 0) && xin && y >= by0 && y < by1;
-        m[j] = __ballot_sync(0xffffffffu, inside);
+        // covered iff all three >= 0 (rasterizer.cpp:549)
+        const bool inside = pi < npx && ((b0 | b1 | b2) >= 0);
+        const uint32_t m = __ballot_sync(0xffffffffu, inside);
+        // append the covered pixels to the ring, tagged with the triangle's slot
+        if(inside)
+          wq[(tail + __popc(m & below)) & 255u] = (uint16_t)(tag | (uint32_t)(y * 16 + x));
+        tail += __popc(m);
+        total += __popc(m);
       }
-      const uint32_t c0 = __popc(m[0]), c1 = c0 + __popc(m[1]), c2 = c1 + __popc(m[2]), total = c2 + __popc(m[3]);
       if(total == 0u)
         continue;
       covered += (lane == 0) ? total : 0u;
-      // append the covered pixels (row-major) to the ring, tagged with the triangle's slot
-      const uint32_t tail = qhead + qcount, tag = (uint32_t)k << 7;
-      if(m[0] & (1u << lane)) wq[(tail + __popc(m[0] & below)) & 255u] = (uint16_t)(tag | (uint32_t)lane);
-      if(m[1] & (1u << lane)) wq[(tail + c0 + __popc(m[1] & below)) & 255u] = (uint16_t)(tag | (uint32_t)(lane + 32));
-      if(m[2] & (1u << lane)) wq[(tail + c1 + __popc(m[2] & below)) & 255u] = (uint16_t)(tag | (uint32_t)(lane + 64));
-      if(m[3] & (1u << lane)) wq[(tail + c2 + __popc(m[3] & below)) & 255u] = (uint16_t)(tag | (uint32_t)(lane + 96));
       qcount += total;
       __syncwarp();
       // ---- 3. full 32-fragment passes as soon as the ring holds them
@@ -749,8 +771,10 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     }
     if(base == 0u)
     {
+#if !VB200_UNORM_NEWTON
       for(int i = threadIdx.x; i < 256; i += RT)
         vb200_s_unorm[i] = __ldg(p.unorm + i);    // read in phase B, after the barriers below
+#endif
       // ---- init: one visibility key per pixel, seeded with the depth already in the buffer
     #pragma unroll
       for(int j = 0; j < VB200_TILE / RW; j++)
