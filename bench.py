@@ -36,7 +36,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from harness import abi, scenes, tiles  # noqa: E402
+from harness import abi, scenes, tiles, vkdriver  # noqa: E402
 
 
 # ------------------------------------------------------------------------------------------------
@@ -223,7 +223,6 @@ def run_reference_arm(args, workload: str) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from harness import vkdriver
     if not (abi.available("vref") and vkdriver.available()):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference ICD + Vulkan driver) not built"}))
         return
@@ -724,6 +723,34 @@ def run_ours(args, workload: str) -> None:
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
+    if len(scene.draws) > 1 and not multi:
+        # many-draw frames: the timed step contains the host-side recording of every draw (this harness calls the
+        # C-ABI from Python through ctypes); split it into the time the host spends issuing the calls, what an
+        # empty ctypes call costs, and the device time of the batch (sum of the kernel phases)
+        n_draws = len(scene.draws)
+        t0 = time.perf_counter()
+        bound.submit()
+        t_rec = time.perf_counter() - t0
+        gpu.check(L.vb200_flush(), "flush")
+        t0 = time.perf_counter()
+        for _ in range(n_draws):
+            L.vb200_abi_version()
+        t_null = time.perf_counter() - t0
+        line["many_draws"] = {"draws": n_draws, "host_record_ms": t_rec * 1e3, "host_record_us_per_draw": t_rec / n_draws * 1e6,
+                              "empty_ctypes_call_us": t_null / n_draws * 1e6,
+                              "device_ms": sum(v for k, v in phase.items()),
+                              "note": "ms_per_step = host recording of all draws + one batch on the device"}
+        if vkdriver.available() and os.path.exists(vkdriver.ICD_CUDA):
+            # the same command buffer through the CUDA ICD (visor's own vkCmdDrawIndexed recording, C++ replay, no
+            # Python per draw; coherent memory: uploads and read-back inside), next to the mesh as ONE draw
+            gpu.check(L.vb200_set_sync_mode(0), "set_sync_mode")
+            import dataclasses
+            one = dataclasses.replace(scene, draws=[dataclasses.replace(scene.draws[0], first=0, count=sum(d.count for d in scene.draws))])
+            icd = {}
+            for tag, sc_ in (("many_draws", scene), ("one_draw", one)):
+                vkdriver.run(vkdriver.ICD_CUDA, sc_, frames=6)
+                icd[tag + "_ms"] = float(np.mean(vkdriver.frame_seconds(6)[1:])) * 1e3
+            line["many_draws"]["cuda_icd_queue_submit"] = icd
     if pipelined:
         line["e2e_pipelined"] = pipelined
     if single:

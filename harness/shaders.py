@@ -369,6 +369,11 @@ UNIT_OPS = ("fadd", "fsub", "fmul", "fdiv", "fneg", "vts", "dot4", "dot3", "fmin
             "transpose", "mxs", "minverse", "sin", "cos", "pow")
 
 
+# memory-model cases of the reference's subset that are not single arithmetic opcodes: run-time indices into
+# function-local arrays and vectors (OpAccessChain -> GEP, spirv_compile.cpp:1301-1318)
+MEM_UNIT_OPS = ("dynidx",)
+
+
 # opcodes outside the reference's subset (SURVEY.md Appendix B "Not supported"), accepted only when the
 # "extended_spirv" option is on
 EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "floor", "fract")
@@ -391,6 +396,7 @@ def vs_unit(op: str) -> np.ndarray:
     N = m.load(mat4, m.access(SC.Uniform, mat4, ubo, m.const_i(1)))
     a3, b3 = m.shuffle(v3, a, a, 0, 1, 2), m.shuffle(v3, b, b, 0, 1, 2)
     ax, bx = m.extract(fl, a, 0), m.extract(fl, b, 0)
+    extra_iface = []
 
     def splat(s):
         return m.construct(v4, s, s, s, s)
@@ -472,6 +478,30 @@ def vs_unit(op: str) -> np.ndarray:
     elif op == "ftos":
         iv4 = m.t_vec(m.t_int(1), 4)
         r = m.inst(Op.ConvertSToF, v4, m.inst(Op.ConvertFToS, iv4, a))
+    elif op == "dynidx":
+        # i = gl_VertexIndex & 3, j = (gl_VertexIndex * 3) & 3
+        # vec4 arr[4] = {a, b, c, a + b};  float fa[4] = {a.x, b.y, c.z, a.w};  vec4 vv = b;
+        # fa[i] = c.x;  r = arr[i] + vec4(fa[1], fa[j], vv[i], fa[1])
+        it = m.t_int(1)
+        vidx = m.builtin_input(it, BuiltIn.VertexIndex, "gl_VertexIndex")
+        extra_iface.append(vidx)
+        vi = m.load(it, vidx)
+        i = m.inst(Op.BitwiseAnd, it, vi, m.const_i(3))
+        j = m.inst(Op.BitwiseAnd, it, m.inst(Op.IMul, it, vi, m.const_i(3)), m.const_i(3))
+        arr = m.local(m.t_array(v4, 4))
+        for k, val in enumerate((a, b, c, m.inst(Op.FAdd, v4, a, b))):
+            m.store(m.access(SC.Function, v4, arr, m.const_i(k)), val)
+        fa = m.local(m.t_array(fl, 4))
+        for k, (src, comp) in enumerate(((a, 0), (b, 1), (c, 2), (a, 3))):
+            m.store(m.access(SC.Function, fl, fa, m.const_i(k)), m.extract(fl, src, comp))
+        vv = m.local(v4)
+        m.store(vv, b)
+        m.store(m.access(SC.Function, fl, fa, i), m.extract(fl, c, 0))
+        x = m.load(v4, m.access(SC.Function, v4, arr, i))
+        s1 = m.load(fl, m.access(SC.Function, fl, fa, m.const_i(1)))
+        t1 = m.load(fl, m.access(SC.Function, fl, fa, j))
+        comp = m.load(fl, m.access(SC.Function, fl, vv, i))
+        r = m.inst(Op.FAdd, v4, x, m.construct(v4, s1, t1, comp, s1))
     elif op == "fabs":
         r = m.ext(v4, GLSL.FAbs, a)
     elif op == "floor":
@@ -482,4 +512,4 @@ def vs_unit(op: str) -> np.ndarray:
         raise ValueError(op)
     m.store(m.access(SC.Output, v4, gl, m.const_i(0)), a)
     m.store(out, r)
-    return _finish(m, VERTEX, f, [ia, ib, ic, out, gl])
+    return _finish(m, VERTEX, f, [ia, ib, ic, out, gl] + extra_iface)

@@ -14,7 +14,7 @@ from .scenes import Scene
 ROOT = abi.ROOT
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "libvk_driver.so")
 ICD_REF = os.path.join(ROOT, "oracle", "_ref", "libvisor_ref.so")
-ICD_CUDA = os.path.join(ROOT, "oracle", "_ref", "libvisor_b200_icd.so")
+ICD_CUDA = os.path.join(ROOT, "integration", "libvisor_b200_icd.so")
 
 
 class Attr(C.Structure):

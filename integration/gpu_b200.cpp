@@ -7,7 +7,7 @@
  * descriptors.cpp, ...) is compiled unmodified; they only ever call the functions defined here
  * (cmd_exec.cpp:48,59,133,140; icd_stubs.cpp:12-13,20; shaders.cpp:11,23,81,85).
  *
- * Compiled against the reference's own headers (-I<visor> ; on Linux with -include oracle/ref/shim.h).
+ * Compiled against the reference's own headers (-I<visor> ; on Linux with -include integration/linux/shim.h).
  * It contains no rasterisation, sampling or shader code: it only re-packs the reference's host structs
  * (GPUState, VkPipeline_T, VkImage_T, VkBuffer_T, VkDescriptorSet_T) into the ABI's PODs.
  */

@@ -1,8 +1,9 @@
 /*
- * oracle/ref/shim.h — force-included (-include) before every UNMODIFIED reference translation unit
+ * integration/linux/shim.h — force-included (-include) before every UNMODIFIED reference translation unit
  * so the MSVC-flavoured sources compile with g++ on Linux.  It only supplies
- * headers the reference gets implicitly from <windows.h>/MSVC and neutralises __declspec.
- * TEST INFRASTRUCTURE ONLY.
+ * headers the reference gets implicitly from <windows.h>/MSVC and neutralises __declspec. Used by the
+ * Linux build of the CUDA ICD (integration/Makefile) and by the checker's build of the reference
+ * (oracle/Makefile).
  */
 #pragma once
 #include <string.h>

@@ -1,9 +1,9 @@
 /*
- * oracle/ref/wsi_headless.cpp — headless stand-in for wsi.cpp (Win32 GDI swapchain, not buildable
+ * integration/linux/wsi_headless.cpp — headless stand-in for wsi.cpp (Win32 GDI swapchain, not buildable
  * on Linux). icd_interface.cpp:23-26,41-45 takes the address of these entry points; rendering tests use
- * plain VkImages bound to host-visible memory, never a swapchain. Shared by the reference build
- * (oracle/_ref/libvisor_ref.so) and the CUDA ICD build (oracle/_ref/libvisor_b200_icd.so).
- * TEST/INTEGRATION INFRASTRUCTURE; contains no reference code.
+ * plain VkImages bound to host-visible memory, never a swapchain. Part of the Linux build of the CUDA ICD
+ * (integration/libvisor_b200_icd.so); the checker's build of the reference (oracle/_ref/libvisor_ref.so)
+ * compiles it too. Contains no reference code.
  */
 #include "precompiled.h"
 

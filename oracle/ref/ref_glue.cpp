@@ -204,7 +204,7 @@ void DestroyFunction(LLVMFunction *func)
   delete func;
 }
 
-// 3. headless WSI: oracle/ref/wsi_headless.cpp (shared with the CUDA ICD build)
+// 3. headless WSI: integration/linux/wsi_headless.cpp (the CUDA ICD's Linux build supplies it)
 
 // ---------------------------------------------------------------------------------------------
 // 4. vref_*: visor_b200.h-shaped adapter onto the reference operators

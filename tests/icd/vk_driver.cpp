@@ -7,12 +7,13 @@
  * vkCmdCopyBufferToImage, descriptor sets, render pass, graphics pipeline, command buffer,
  * vkQueueSubmit; then reads the attachments through the mapped pointers.  The same scene is run
  * through the reference ICD (oracle/_ref/libvisor_ref.so) and the CUDA ICD
- * (oracle/_ref/libvisor_b200_icd.so).  Compiled against the reference's vendored vulkan.h (v42).
+ * (integration/libvisor_b200_icd.so).  Compiled against the reference's vendored vulkan.h (v42).
  * TEST INFRASTRUCTURE.
  */
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 #include <chrono>
 #include <map>
@@ -300,6 +301,19 @@ extern "C" __attribute__((visibility("default"))) int vkd_run(const char *icd_pa
   {
     const vkd_draw &d = sc->draws[di];
     DrawObjs &o = objs[di];
+    // a draw that differs from an earlier one only in its vertex/index range uses that draw's objects, as an
+    // application drawing a mesh chunk by chunk would (same buffers, descriptor sets and pipeline)
+    {
+      uint32_t same = di;
+      for(uint32_t dj = 0; dj < di && same == di; dj++)
+        if(memcmp(&sc->draws[dj], &d, offsetof(vkd_draw, count)) == 0)
+          same = dj;
+      if(same != di)
+      {
+        o = objs[same];
+        continue;
+      }
+    }
     memset(o.vb, 0, sizeof(o.vb));
     o.ib = VK_NULL_HANDLE;
     for(int i = 0; i < 4; i++)

@@ -112,7 +112,7 @@ def test_shaders_lower_to_ieee_ptx_and_link_for_sm100a(lib, name):
     lib.vb200_shader_destroy(m2)
 
 
-@pytest.mark.parametrize("op", shaders.UNIT_OPS)
+@pytest.mark.parametrize("op", shaders.UNIT_OPS + shaders.MEM_UNIT_OPS)
 def test_unit_op_shaders_compile(lib, op):
     mod, e = _entry(lib, shaders.vs_unit(op))
     assert b"vb200_vs" in lib.vb200_entry_ptx(e)

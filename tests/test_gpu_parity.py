@@ -139,7 +139,7 @@ def _unit_scene(op, seed=0):
     return scenes.Scene(f"unit_{op}", 256, 160, [d], depth=False)
 
 
-@pytest.mark.parametrize("op", [o for o in __import__("harness.shaders", fromlist=["UNIT_OPS"]).UNIT_OPS])
+@pytest.mark.parametrize("op", [o for o in (lambda sh: sh.UNIT_OPS + sh.MEM_UNIT_OPS)(__import__("harness.shaders", fromlist=["UNIT_OPS"]))])
 def test_spirv_ops_match_oracle(gpu, vor, op):
     # sin/cos/pow are libm in the oracle and approx units on the GPU: covered by the 1-LSB colour bar
     _check(gpu, vor, _unit_scene(op), exact=op not in ("sin", "cos", "pow"))

@@ -4,7 +4,7 @@ against
   * the reference ICD  — every reference .cpp unmodified (oracle/_ref/libvisor_ref.so), and
   * the CUDA ICD       — the reference's ICD surface (icd_interface/cmd_record/shaders/images/... unmodified)
                          with rasterizer.cpp, texture_sampling.cpp, spirv_compile.cpp, cmd_exec.cpp, memory.cpp
-                         replaced by integration/*.cpp over the C-ABI (oracle/_ref/libvisor_b200_icd.so).
+                         replaced by integration/*.cpp over the C-ABI (integration/libvisor_b200_icd.so).
 """
 import numpy as np
 import pytest

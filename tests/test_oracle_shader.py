@@ -175,6 +175,28 @@ def test_unit_op_matches_numpy(vor, op):
     vor.DestroyFunction(mod)
 
 
+def test_dynamic_indices_into_local_arrays(vor):
+    """OpAccessChain with run-time indices into function-local arrays and vectors (a GEP in the reference,
+    spirv_compile.cpp:1301-1318): loads and stores through them, against a numpy restatement"""
+    verts, ubo = unit_inputs(11)
+    mod, st, keep = unit_state(vor, "dynidx", verts, ubo)
+    entry = vor.GetFuncPointer(mod, "main")
+    run = vor.lib.vor_run_vertex
+    run.argtypes = [C.POINTER(abi.DrawState), C.c_void_p, C.c_uint32, C.POINTER(C.c_float)]
+    out = (C.c_float * 44)()
+    for n in range(verts.shape[0]):
+        assert run(C.byref(st), entry, n, out) == 0
+        got = np.array(out[4:8], dtype=f32)
+        a, b, c = verts[n, 0:4], verts[n, 4:8], verts[n, 8:12]
+        i, j = n & 3, (n * 3) & 3
+        arr = [a, b, c, (a + b).astype(f32)]
+        fa = [a[0], b[1], c[2], a[3]]
+        fa[i] = c[0]
+        exp = (arr[i] + np.array([fa[1], fa[j], b[i], fa[1]], dtype=f32)).astype(f32)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (n, got, exp)
+    vor.DestroyFunction(mod)
+
+
 def _expected_ext(op, a, b, c):
     f32 = np.float32
     if op == "select":

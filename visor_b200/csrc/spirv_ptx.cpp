@@ -124,6 +124,11 @@ struct Ptr
   // VAR
   std::shared_ptr<VarStorage> var;
   uint32_t off = 0;
+  // VAR with run-time indices (OpAccessChain -> GEP with a non-constant index, spirv_compile.cpp:1301-1318): the
+  // element lives at off + dynReg, dynReg = sum of index * stride over the dynamic levels (strides in scalars);
+  // loads and stores go through a select tree over the possible positions
+  std::string dynReg;
+  std::vector<std::pair<uint32_t, uint32_t>> dynDims;    // (stride, count) per dynamic level
   // MEM
   std::string addr;
   int64_t constOff = 0;
@@ -678,7 +683,30 @@ struct Emitter
     Value v;
     v.type = tid;
     v.defined = true;
-    if(p.kind == Ptr::VAR)
+    if(p.kind == Ptr::VAR && !p.dynReg.empty())
+    {
+      // select tree over the positions the run-time index can take (an index outside the array reads the
+      // first element here; the reference's GEP reads whatever lies there)
+      const uint32_t n = flat(tid);
+      const std::vector<uint32_t> pos = dynPositions(p, n);
+      if(isBoolTy(tid))
+        fail("dynamically indexed bool variables are not supported");
+      for(uint32_t i = 0; i < n; i++)
+      {
+        std::string d = R();
+        line("mov.b32 %s, %s;", d.c_str(), p.var->regs[p.off + pos[0] + i].c_str());
+        v.r.push_back(d);
+      }
+      for(size_t k = 1; k < pos.size(); k++)
+      {
+        std::string pr = P();
+        line("setp.eq.s32 %s, %s, %u;", pr.c_str(), p.dynReg.c_str(), pos[k]);
+        for(uint32_t i = 0; i < n; i++)
+          line("selp.b32 %s, %s, %s, %s;", v.r[i].c_str(), p.var->regs[p.off + pos[k] + i].c_str(), v.r[i].c_str(),
+               pr.c_str());
+      }
+    }
+    else if(p.kind == Ptr::VAR)
     {
       uint32_t n = flat(tid);
       if(p.off + n > p.var->regs.size())
@@ -708,10 +736,48 @@ struct Emitter
     return v;
   }
 
+  // offsets (in scalars, relative to p.off) a dynamically indexed pointer can address, for an access of n scalars
+  std::vector<uint32_t> dynPositions(const Ptr &p, uint32_t n)
+  {
+    std::vector<uint32_t> pos = {0};
+    for(auto &d : p.dynDims)
+    {
+      std::vector<uint32_t> next;
+      for(uint32_t base : pos)
+        for(uint32_t k = 0; k < d.second; k++)
+          next.push_back(base + k * d.first);
+      pos.swap(next);
+      if(pos.size() > 256)
+        fail("dynamically indexed variable with more than 256 possible positions");
+    }
+    for(uint32_t at : pos)
+      if(p.off + at + n > p.var->regs.size())
+        fail("dynamic access out of variable bounds");
+    return pos;
+  }
+
   void storePtr(const Ptr &p, const Value &val)
   {
     if(p.kind != Ptr::VAR)
       fail("stores to buffer memory are not supported (UBO/push constants are read-only)");
+    if(!p.dynReg.empty())
+    {
+      // every position the run-time index can take keeps its value unless the index selects it
+      const uint32_t n = (uint32_t)val.r.size();
+      if(isBoolTy(val.type))
+        fail("dynamically indexed bool variables are not supported");
+      for(uint32_t at : dynPositions(p, n))
+      {
+        std::string pr = P();
+        line("setp.eq.s32 %s, %s, %u;", pr.c_str(), p.dynReg.c_str(), at);
+        for(uint32_t i = 0; i < n; i++)
+        {
+          const std::string &dst = p.var->regs[p.off + at + i];
+          line("selp.b32 %s, %s, %s, %s;", dst.c_str(), val.r[i].c_str(), dst.c_str(), pr.c_str());
+        }
+      }
+      return;
+    }
     if(p.off + val.r.size() > p.var->regs.size())
       fail("store out of variable bounds");
     bool b = isBoolTy(val.type);
@@ -878,10 +944,23 @@ struct Emitter
         if(p.kind == Ptr::VAR)
         {
           if(!isC)
-            fail("dynamic indexing of register-promoted variables is not supported");
-          if(c >= t.count)
-            fail("constant index out of range");
-          p.off += c * fl;
+          {
+            // run-time index into a register-promoted variable: accumulate index * stride
+            const std::string &ix = regs(idxId, 1)[0];
+            std::string d = R();
+            if(p.dynReg.empty())
+              line("mul.lo.s32 %s, %s, %u;", d.c_str(), ix.c_str(), fl);
+            else
+              line("mad.lo.s32 %s, %s, %u, %s;", d.c_str(), ix.c_str(), fl, p.dynReg.c_str());
+            p.dynReg = d;
+            p.dynDims.push_back({fl, t.count});
+          }
+          else
+          {
+            if(c >= t.count)
+              fail("constant index out of range");
+            p.off += c * fl;
+          }
         }
         else if(isC)
           p.constOff += (int64_t)c * stride;
