@@ -109,6 +109,20 @@ struct IntervalSet
       out.push_back(v[i]);
     v.swap(out);
   }
+  bool covers(size_t lo, size_t hi) const    // [lo, hi) lies inside one interval (intervals are merged)
+  {
+    for(auto &r : v)
+      if(r.first <= lo && hi <= r.second)
+        return true;
+    return lo >= hi;
+  }
+  bool overlaps(size_t lo, size_t hi) const
+  {
+    for(auto &r : v)
+      if(r.first < hi && lo < r.second)
+        return true;
+    return false;
+  }
   // removes [lo, hi); returns whether anything was removed
   bool remove(size_t lo, size_t hi)
   {
@@ -226,6 +240,7 @@ struct Batch
     Vb200BatchDraw dev;
     int kind;
     uint32_t spanBase, spanCount, usedVerts;
+    const uint8_t *ibHost;    // SPAN_INDEXED: the draw's indices in host memory
   };
   bool active = false, closed = false, ran = false;
   BatchKey key;
@@ -549,7 +564,9 @@ int resolveInner(const void *ptr, size_t size, int access, uint8_t **out)
   const size_t off = (uintptr_t)ptr - (uintptr_t)m->host;
   if(g.syncMode == VB200_SYNC_COHERENT && !m->deviceLocal)
   {
-    if((access & ACC_READ) && !(access & ACC_OVERWRITE))
+    // (a frame of many draws resolves the same ranges over and over: the common case is "already there")
+    if((access & ACC_READ) && !(access & ACC_OVERWRITE) && !m->uploaded.covers(off, off + size) &&
+       !m->written.covers(off, off + size))
     {
       for(auto &gap : m->uploaded.gaps(off, off + size, m->written))
       {
@@ -559,7 +576,7 @@ int resolveInner(const void *ptr, size_t size, int access, uint8_t **out)
         m->uploaded.add(gap.first, gap.second);
       }
     }
-    if(access & (ACC_WRITE | ACC_OVERWRITE))
+    if((access & (ACC_WRITE | ACC_OVERWRITE)) && !m->written.covers(off, off + size))
       m->written.add(off, off + size);
   }
   *out = m->dev + off;
@@ -1017,11 +1034,37 @@ int runBatch(size_t first, size_t last, bool foldClears)
       wantAll = true;
     if(d.kind != Batch::SPAN_HOST)
       idxVerts += d.usedVerts;
-    if(d.kind == Batch::SPAN_INDEXED)
-      idxSpan += d.spanCount;
     if(d.kind == Batch::SPAN_DEVICE)
       deviceRange = true;
   }
+  if(!wantAll && idxVerts < k.vertexBound)
+    for(size_t i = first; i < last; i++)
+    {
+      Batch::Draw &d = b.draws[i];
+      if(d.kind != Batch::SPAN_INDEXED)
+        continue;
+      uint32_t lo = 0xffffffffu, hi = 0;
+      if(d.dev.index_type == 0u)
+        for(uint32_t j = 0; j < d.usedVerts; j++)
+        {
+          uint16_t v;
+          memcpy(&v, d.ibHost + 2 * (size_t)j, 2);
+          lo = std::min<uint32_t>(lo, v);
+          hi = std::max<uint32_t>(hi, v);
+        }
+      else
+        for(uint32_t j = 0; j < d.usedVerts; j++)
+        {
+          uint32_t v;
+          memcpy(&v, d.ibHost + 4 * (size_t)j, 4);
+          lo = std::min(lo, v);
+          hi = std::max(hi, v);
+        }
+      d.spanBase = lo;
+      // (indices at or beyond vertexBound kill their triangle in the setup kernel; nothing beyond is shaded)
+      d.spanCount = lo < k.vertexBound ? std::min(hi, k.vertexBound - 1u) - lo + 1u : 0u;
+      idxSpan += d.spanCount;
+    }
   if(deviceRange && last - first > 1)
   {
     // index data only the device can read: worth one shared span when the draws reference enough of the buffer
@@ -2103,9 +2146,7 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
       if(m && !m->deviceLocal)
       {
         const size_t lo = (uintptr_t)s->ib.buffer.bytes - (uintptr_t)m->host + s->ib.offset + (size_t)first * isz;
-        IntervalSet none;
-        auto clean = m->written.gaps(lo, lo + (size_t)usedVerts * isz, none);
-        if(clean.size() == 1 && clean[0].first == lo && clean[0].second == lo + (size_t)usedVerts * isz)
+        if(!m->written.overlaps(lo, lo + (size_t)usedVerts * isz))
           ibHost = (const uint8_t *)s->ib.buffer.bytes + s->ib.offset + (size_t)first * isz;
       }
     }
@@ -2246,28 +2287,10 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
     d.kind = Batch::SPAN_ALL;    // a mesh: every bound vertex is referenced several times, all are shaded
   else if(ibHost && usedVerts <= (1u << 16))
   {
-    // a small draw out of a larger vertex buffer, indices readable on the host: measure [min, max] here
-    uint32_t lo = 0xffffffffu, hi = 0;
-    if(s->ib.index_type == 0u)
-      for(uint32_t i = 0; i < usedVerts; i++)
-      {
-        uint16_t v;
-        memcpy(&v, ibHost + 2 * (size_t)i, 2);
-        lo = std::min<uint32_t>(lo, v);
-        hi = std::max<uint32_t>(hi, v);
-      }
-    else
-      for(uint32_t i = 0; i < usedVerts; i++)
-      {
-        uint32_t v;
-        memcpy(&v, ibHost + 4 * (size_t)i, 4);
-        lo = std::min(lo, v);
-        hi = std::max(hi, v);
-      }
+    // a small draw out of a larger vertex buffer, indices readable on the host: [min, max] is measured there
+    // when the batch runs, and only if the batch's draws do not reference the whole buffer anyway
     d.kind = Batch::SPAN_INDEXED;
-    d.spanBase = lo;
-    // (indices at or beyond vertexBound kill their triangle in the setup kernel; nothing beyond is shaded)
-    d.spanCount = lo < vertexBound ? std::min(hi, vertexBound - 1u) - lo + 1u : 0u;
+    d.ibHost = ibHost;
   }
   else
     d.kind = Batch::SPAN_DEVICE;    // measured by k_index_range when the batch runs
