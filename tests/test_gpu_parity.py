@@ -573,6 +573,40 @@ def test_results_of_the_same_submit_are_not_overwritten_by_uploads(gpu, vor):
     assert np.array_equal(stale, good)
 
 
+def test_mirror_merge_in_the_middle_of_a_frame(gpu, vor):
+    """Host ranges are mirrored on first use and mirrors of overlapping ranges are merged (the merged mirror
+    lives at a new device address). A draw recorded into the open batch but not launched yet must not be left
+    behind writing the old mirror: frame 2's second draw reads a vertex buffer that straddles the end of the
+    stale mirror frame 1 left behind, and that stale mirror also holds frame 2's attachments."""
+    w, h = 200, 120
+    pool = np.zeros(4 << 20, np.uint8)
+    img_bytes = w * h * 4
+    # frame 1: one large range (as an application's earlier, larger swapchain image would leave behind)
+    first = scenes.random_triangles(512, 256, 40, 81, has_depth=False, depth_op=abi.CMP_ALWAYS)
+    big_color = pool[:512 * 256 * 4].reshape(256, 512, 4)
+    scenes.BoundScene(gpu, first, color=big_color).run()
+    stale_end = big_color.nbytes
+    # frame 2: attachments inside that range; draw 1 (clears folded in) and draw 2 from different vertex buffers
+    a = scenes.random_triangles(w, h, 12, 82, max_size=1.5)
+    b = scenes.random_triangles(w, h, 300, 83, max_size=0.05)
+    vb_b = b.draws[0].vbs[0][0]
+    lo = (stale_end - 64) & ~31                       # straddles the end of frame 1's mirror
+    dst = pool[lo:lo + vb_b.nbytes].view(vb_b.dtype).reshape(vb_b.shape)
+    dst[...] = vb_b
+    want_scene = scenes.random_triangles(w, h, 12, 82, max_size=1.5)
+    want_scene.draws += scenes.random_triangles(w, h, 300, 83, max_size=0.05).draws
+    want_c, want_d = scenes.render(vor, want_scene)
+    b.draws[0].vbs = [(dst, 0)]
+    a.draws += b.draws
+    color = pool[:img_bytes].reshape(h, w, 4)
+    depth = pool[img_bytes:2 * img_bytes].view(np.float32).reshape(h, w)
+    color[...] = 0xCD
+    depth[...] = 0.75
+    got_c, got_d = scenes.BoundScene(gpu, a, color=color, depth=depth).run()
+    assert np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))
+    assert np.array_equal(got_c, want_c)
+
+
 def test_clear_fusion_variants(gpu, vor):
     """deferred clears: consumed by the first draw, materialised for a second target/draw, depth clear
     without a depth-using pipeline, colour cleared but depth loaded"""

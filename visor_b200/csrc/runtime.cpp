@@ -442,6 +442,11 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
       hi = std::max(hi, mhi);
     }
   }
+  // Draws recorded into the open batch but not launched yet hold device addresses inside the mirrors about
+  // to be replaced (attachments included): they run first, so that the copies below carry their results over.
+  if(!victims.empty())
+    if(int frc = flushBatchKeepOpen())
+      return frc;
   Mirror nm;
   nm.host = (uint8_t *)lo;
   nm.size = hi - lo;

@@ -34,6 +34,12 @@
 #ifndef VB200_PB_UNROLL
 #define VB200_PB_UNROLL 1
 #endif
+#ifndef VB200_STAGE_INTERPS
+// resolve kernels: corners' interpolants of a one-round tile staged in shared memory (one gather per triangle
+// instead of one per pixel). Measured and left off: C2 -5 %, C3 +0.5 %, C5 +4 % (the 5 KB it adds per CTA come
+// out of the L1 the texture fetches live in; the kernel is bound by l1tex wavefronts either way).
+#define VB200_STAGE_INTERPS 0
+#endif
 
 extern "C" __device__ float4 vb200_vs(const Vb200Env *env, unsigned vid, float4 *interps_out);
 extern "C" __device__ float4 vb200_fs(const Vb200Env *env, float b0, float b1, float b2, const float4 *v0,
@@ -121,7 +127,11 @@ extern "C" __device__ float4 vb200_fetch_attr(const Vb200Env *env, unsigned attr
 // float(byte) / 255.0f for every byte value (texture_sampling.cpp:121-133, rasterizer.cpp:595-599), filled by
 // each tile kernel before its first barrier: texel conversion and the blend's destination read become
 // shared-memory loads instead of IEEE divisions (sixteen per bilinear sample).
+#if !VB200_UNORM_NEWTON
 __shared__ float vb200_s_unorm[256];
+#else
+#define vb200_s_unorm ((const float *)nullptr)    // the Newton variant of vb200_unorm8 never reads the table
+#endif
 
 extern "C" __device__ float4 vb200_sample_tex(float u, float v, const Vb200Image *img, unsigned long long byteOffs)
 {
@@ -650,7 +660,12 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __shared__ uint2 s_run[RW][64];                    // per warp: the covered runs of the 64 rows of the current step
   __shared__ uint32_t s_wsum[RW];
   __shared__ uint32_t s_ticket;    // next unclaimed step of the row stream
-  __shared__ uint32_t s_ids[2 * RT];    // id queue of the fallback scan (overflowed tile list)
+  // Interpolants of the staged records' corners, [corner][record slot], for pipelines with one interpolant slot:
+  // phase B then reads a winner's three float4 from shared memory instead of gathering them from L1/L2 once per
+  // PIXEL (the gather is done once per triangle, by the thread that sets the record up). The id queue of the
+  // fallback scan (overflowed tile list: several rounds, nothing staged) lives in the same bytes.
+  __shared__ int4 s_int[VB200_STAGE_INTERPS ? 3 * RT : RT / 2];
+  uint32_t *const s_ids = (uint32_t *)s_int;
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
@@ -660,6 +675,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   const Vb200RasterState &rs = p.rs;
+  // the tile's whole list fits one round: the records (and, with one slot, the interpolants) stay staged for phase B
+  const bool recordsInSmem = rs.slot_keys && n <= (uint32_t)RT;
+  const bool stagedInterps = VB200_STAGE_INTERPS && recordsInSmem && rs.nslots == 1u;
   const uint32_t ty = __umulhi(tile, rs.tiles_x_magic), tx = tile - ty * rs.tiles_x;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   asm volatile("" : "+r"(lane), "+r"(warp));    // (kept in registers: ptxas otherwise re-reads %tid inside the loops)
@@ -769,6 +787,13 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       rb = __ldg((const int4 *)(p.rv + (uint32_t)rq.y));
       rc = __ldg((const int4 *)(p.rv + (uint32_t)rq.z));
     }
+    int4 ri0 = make_int4(0, 0, 0, 0), ri1 = ri0, ri2 = ri0;
+    if(stagedInterps && have)
+    {
+      ri0 = __ldg((const int4 *)(p.interps + (uint32_t)rq.x));
+      ri1 = __ldg((const int4 *)(p.interps + (uint32_t)rq.y));
+      ri2 = __ldg((const int4 *)(p.interps + (uint32_t)rq.z));
+    }
     if(base == 0u)
     {
 #if !VB200_UNORM_NEWTON
@@ -829,6 +854,14 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     s_z[threadIdx.x] = rz;
     s_pw[threadIdx.x] = rpw;
     s_sv[threadIdx.x] = rsv;
+#if VB200_STAGE_INTERPS
+    if(stagedInterps)
+    {
+      s_int[threadIdx.x] = ri0;
+      s_int[RT + threadIdx.x] = ri1;
+      s_int[2 * RT + threadIdx.x] = ri2;
+    }
+#endif
     s_key[threadIdx.x] = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
     __syncthreads();
     const uint32_t wsum = lane < RW ? s_wsum[lane] : 0u;
@@ -1025,7 +1058,6 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 
   // ---- phase B: shade the winner of every pixel, write back. Thread (warp, lane) owns pixel column `lane`
   // of rows warp, warp + RW, warp + 2 RW, ...
-  const bool recordsInSmem = rs.slot_keys && n <= (uint32_t)RT;    // the only round's records are still staged
   const bool remote = p.mc_color != nullptr || p.num_peers != 0u;
   uint32_t aPw = vb200_smem_addr(s_pw), aSv = vb200_smem_addr(s_sv);
   asm volatile("" : "+r"(aPw), "+r"(aSv));
@@ -1070,8 +1102,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       shaded++;
       int b0, b1, b2;
       float invarea, d0, d1, d2, invw0, invw1, invw2;
-      uint32_t s0, s1, s2;
-      record(id, ly, b0, b1, b2, invarea, d0, d1, d2, invw0, invw1, invw2, s0, s1, s2);
+      const float4 *v0, *v1, *v2;
+      record(id, ly, b0, b1, b2, invarea, d0, d1, d2, invw0, invw1, invw2, v0, v1, v2);
       // rasterizer.cpp:552-558, 581-588
       float n0 = __fmul_rn((float)b0, invarea);
       float n1 = __fmul_rn((float)b1, invarea);
@@ -1086,8 +1118,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       n0 = __fmul_rn(n0, invlen);
       n1 = __fmul_rn(n1, invlen);
       n2 = __fmul_rn(n2, invlen);
-      const float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)s0 * rs.nslots,
-                                  p.interps + (size_t)s1 * rs.nslots, p.interps + (size_t)s2 * rs.nslots);
+      const float4 pix = vb200_fs(&env, n0, n1, n2, v0, v1, v2);
       vb200_store_color(p, gi, vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]), remote);
       if(depthWrite)
         __stcs(p.depth + gi, pixdepth);
@@ -1095,25 +1126,46 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         __stcs(p.depth + gi, p.clear_depth);
     }
   };
+  // the winner's edge values at this pixel from its staged record (int32 ring arithmetic, so this and the
+  // reference's formulation, rasterizer.cpp:303-309,545-558, give the same bits)
+  auto staged_record = [&](uint32_t slot16, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1,
+                           float &d2, float &invw0, float &invw1, float &invw2, uint32_t &s0) {
+    const int4 c0 = vb200_lds128(aE1 + slot16), c1 = vb200_lds128(aE2 + slot16), c2 = vb200_lds128(aZ + slot16),
+               c4 = vb200_lds128(aPw + slot16);
+    b1 = c0.x * lane + c0.y * ly + c0.z;
+    b2 = c0.w * lane + c1.x * ly + c1.y;
+    b0 = c1.z - (b1 + b2);
+    invarea = __int_as_float(c2.x); d0 = __int_as_float(c2.y); d1 = __int_as_float(c2.z); d2 = __int_as_float(c2.w);
+    invw0 = __int_as_float(c4.x); invw1 = __int_as_float(c4.y); invw2 = __int_as_float(c4.z);
+    s0 = (uint32_t)c4.w;
+  };
+#if VB200_STAGE_INTERPS
+  if(stagedInterps)
+    shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
+                   float &invw0, float &invw1, float &invw2, const float4 *&v0, const float4 *&v1, const float4 *&v2) {
+      const uint32_t slot = id & (RT - 1u);    // slot = the thread that set the winner up
+      uint32_t s0;
+      staged_record(slot * 16u, ly, b0, b1, b2, invarea, d0, d1, d2, invw0, invw1, invw2, s0);
+      v0 = (const float4 *)(s_int + slot);
+      v1 = (const float4 *)(s_int + RT + slot);
+      v2 = (const float4 *)(s_int + 2 * RT + slot);
+    });
+  else
+#endif
   if(recordsInSmem)
     shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
-                   float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
-      // the winner's edge values at this pixel from its staged record (int32 ring arithmetic, so this and
-      // the reference's formulation, rasterizer.cpp:303-309,545-558, give the same bits)
-      const uint32_t slot16 = (id & (RT - 1u)) * 16u;    // slot = the thread that set the winner up
-      const int4 c0 = vb200_lds128(aE1 + slot16), c1 = vb200_lds128(aE2 + slot16), c2 = vb200_lds128(aZ + slot16),
-                 c4 = vb200_lds128(aPw + slot16);
+                   float &invw0, float &invw1, float &invw2, const float4 *&v0, const float4 *&v1, const float4 *&v2) {
+      const uint32_t slot16 = (id & (RT - 1u)) * 16u;
+      uint32_t s0;
+      staged_record(slot16, ly, b0, b1, b2, invarea, d0, d1, d2, invw0, invw1, invw2, s0);
       const unsigned long long c5 = vb200_lds64(aSv + (slot16 >> 1));
-      b1 = c0.x * lane + c0.y * ly + c0.z;
-      b2 = c0.w * lane + c1.x * ly + c1.y;
-      b0 = c1.z - (b1 + b2);
-      invarea = __int_as_float(c2.x); d0 = __int_as_float(c2.y); d1 = __int_as_float(c2.z); d2 = __int_as_float(c2.w);
-      invw0 = __int_as_float(c4.x); invw1 = __int_as_float(c4.y); invw2 = __int_as_float(c4.z);
-      s0 = (uint32_t)c4.w; s1 = (uint32_t)c5; s2 = (uint32_t)(c5 >> 32);
+      v0 = p.interps + (size_t)s0 * rs.nslots;
+      v1 = p.interps + (size_t)(uint32_t)c5 * rs.nslots;
+      v2 = p.interps + (size_t)(uint32_t)(c5 >> 32) * rs.nslots;
     });
   else
     shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
-                   float &invw0, float &invw1, float &invw2, uint32_t &s0, uint32_t &s1, uint32_t &s2) {
+                   float &invw0, float &invw1, float &invw2, const float4 *&v0, const float4 *&v1, const float4 *&v2) {
       // several rounds: the record is gathered again, edge values exactly as rasterizer.cpp:303-309,545-558
       const Vb200TriSetup su = vb200_load_setup(p, (rs.slot_keys ? (id >> 8) : id) - 1u);
       const int ABx = su.x1 - su.x0, ABy = su.y1 - su.y0, ACx = su.x2 - su.x0, ACy = su.y2 - su.y0;
@@ -1124,7 +1176,9 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       b0 = (area2 - (ux + uy)) * sgn; b1 = ux * sgn; b2 = uy * sgn;
       invarea = su.invarea; d0 = su.d0; d1 = su.d1; d2 = su.d2;
       invw0 = su.invw0; invw1 = su.invw1; invw2 = su.invw2;
-      s0 = su.s0; s1 = su.s1; s2 = su.s2;
+      v0 = p.interps + (size_t)su.s0 * rs.nslots;
+      v1 = p.interps + (size_t)su.s1 * rs.nslots;
+      v2 = p.interps + (size_t)su.s2 * rs.nslots;
     });
   if(rs.count_fragments)
     vb200_count_fragments(p.counters, covered, shaded);
