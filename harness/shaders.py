@@ -53,6 +53,41 @@ def fs_color() -> np.ndarray:
     return _finish(m, FRAGMENT, f, [col, o])
 
 
+def fs_color_kill(threshold: float = 0.5, in_callee: bool = False) -> np.ndarray:
+    """in vec4 col@0; if(col.x < threshold) discard; out vec4 o@0 = col.   (extended mode: OpKill)
+    in_callee: the discard sits in a helper function the entry point calls (the kill must end the invocation,
+    not just the helper)."""
+    m = Module()
+    v4, fl, bt, void = m.t_fvec(4), m.t_float(), m.t_bool(), m.t_void()
+    col = m.input(v4, 0, "col")
+    o = m.output(v4, 0, "o")
+
+    def test_and_kill(c):
+        kill, merge = m.new_id(), m.new_id()
+        cond = m.inst(Op.FOrdLessThan, bt, m.extract(fl, c, 0), m.const_f(threshold))
+        m.stmt(Op.SelectionMerge, merge, 0)
+        m.stmt(Op.BranchConditional, cond, kill, merge)
+        m.label(kill)
+        m.stmt(Op.Kill)
+        m.label(merge)
+
+    helper = None
+    if in_callee:
+        helper, (hp,) = m.begin_function(void, m.t_func(void, v4), [v4])
+        m.label()
+        test_and_kill(hp)
+        m.ret()
+        m.end_function()
+    f = _main(m)
+    c = m.load(v4, col)
+    if in_callee:
+        m.inst(Op.FunctionCall, void, helper, c)
+    else:
+        test_and_kill(c)
+    m.store(o, c)
+    return _finish(m, FRAGMENT, f, [col, o])
+
+
 # ------------------------------------------------------------------ C2: textured cube
 def vs_mvp_uv() -> np.ndarray:
     """UBO{mat4 mvp}@(0,0); in vec4 pos@0, vec2 uv@1; gl_Position = mvp*pos; out vec2 uv@0."""
@@ -376,7 +411,10 @@ MEM_UNIT_OPS = ("dynidx",)
 
 # opcodes outside the reference's subset (SURVEY.md Appendix B "Not supported"), accepted only when the
 # "extended_spirv" option is on
-EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "floor", "fract")
+EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "floor", "fract",
+                "roundeven", "trunc", "ceil", "fsign", "radians", "degrees", "step", "smoothstep", "fma",
+                "distance3", "faceforward3", "refract3", "int_minmax", "uint_minmax", "int_abs_sign", "phi_loop",
+                "phi_swap")
 
 
 def vs_unit(op: str) -> np.ndarray:
@@ -502,6 +540,90 @@ def vs_unit(op: str) -> np.ndarray:
         t1 = m.load(fl, m.access(SC.Function, fl, fa, j))
         comp = m.load(fl, m.access(SC.Function, fl, vv, i))
         r = m.inst(Op.FAdd, v4, x, m.construct(v4, s1, t1, comp, s1))
+    elif op in ("roundeven", "trunc", "ceil", "fsign", "radians", "degrees"):
+        code = {"roundeven": GLSL.RoundEven, "trunc": GLSL.Trunc, "ceil": GLSL.Ceil, "fsign": GLSL.FSign,
+                "radians": GLSL.Radians, "degrees": GLSL.Degrees}[op]
+        arg = a
+        if op in ("roundeven", "trunc", "ceil"):
+            arg = m.inst(Op.FMul, v4, a, m.const_fvec(3.5, 2.5, 7.25, 0.5))    # ties and magnitudes above 1
+        r = m.ext(v4, code, arg)
+        if op in ("roundeven", "trunc", "ceil", "degrees"):
+            r = m.inst(Op.FMul, v4, r, m.const_fvec(0.125, 0.125, 0.125, 0.125))
+            if op == "degrees":
+                r = m.inst(Op.FMul, v4, r, m.const_fvec(0.125, 0.125, 0.125, 0.125))
+    elif op == "step":
+        r = m.ext(v4, GLSL.Step, a, b)
+    elif op == "smoothstep":
+        r = m.ext(v4, GLSL.SmoothStep, a, b, c)
+    elif op == "fma":
+        r = m.ext(v4, GLSL.Fma, a, b, c)
+    elif op == "distance3":
+        r = splat(m.ext(fl, GLSL.Distance, a3, b3))
+    elif op == "faceforward3":
+        c3 = m.shuffle(v3, c, c, 0, 1, 2)
+        r = pad3(m.ext(v3, GLSL.FaceForward, a3, b3, m.inst(Op.FSub, v3, c3, a3)))
+    elif op == "refract3":
+        r = pad3(m.ext(v3, GLSL.Refract, m.ext(v3, GLSL.Normalize, a3), m.ext(v3, GLSL.Normalize, b3),
+                       m.extract(fl, c, 0)))
+    elif op in ("int_minmax", "uint_minmax", "int_abs_sign"):
+        signed = op != "uint_minmax"
+        it = m.t_int(1 if signed else 0)
+        iv4 = m.t_vec(it, 4)
+        sv4 = m.t_vec(m.t_int(1), 4)
+        # integers from the floats: (int)(x * 64) - 24 (negative values included), reinterpreted when unsigned
+        def ints(x):
+            k = m.inst(Op.ConvertFToS, sv4, m.inst(Op.FMul, v4, x, m.const_fvec(64.0, 64.0, 64.0, 64.0)))
+            k = m.inst(Op.ISub, sv4, k, m.inst(Op.ConvertFToS, sv4, m.const_fvec(24.0, 24.0, 24.0, 24.0)))
+            return k if signed else m.inst(Op.Bitcast, iv4, k)
+        ia_, ib_, ic_ = ints(a), ints(b), ints(c)
+        if op == "int_abs_sign":
+            x = m.inst(Op.IAdd, iv4, m.ext(iv4, GLSL.SAbs, ia_), m.ext(iv4, GLSL.SSign, ib_))
+        else:
+            lo = m.ext(iv4, GLSL.SMin if signed else GLSL.UMin, ia_, ib_)
+            hi = m.ext(iv4, GLSL.SMax if signed else GLSL.UMax, ia_, ib_)
+            cl = m.ext(iv4, GLSL.SClamp if signed else GLSL.UClamp, ic_, lo, hi)
+            x = m.inst(Op.IAdd, iv4, m.inst(Op.IAdd, iv4, lo, hi), cl)
+        x = m.inst(Op.BitwiseAnd, iv4, x, m.inst(Op.Bitcast, iv4, m.inst(Op.ConvertFToS, sv4, m.const_fvec(255.0, 255.0, 255.0, 255.0))))
+        xs = x if signed else m.inst(Op.Bitcast, sv4, x)
+        r = m.inst(Op.FMul, v4, m.inst(Op.ConvertSToF, v4, xs), m.const_fvec(1 / 256.0, 1 / 256.0, 1 / 256.0, 1 / 256.0))
+    elif op in ("phi_loop", "phi_swap"):
+        # for(i = 0, acc = a, other = b; i < n; i++) { acc = acc * 0.5 + other * c; [swap: (acc, other) = (other, acc)] }
+        # written in SSA form with OpPhi, as a real compiler's output has it (n = 3 + (int(a.x * 8) & 3))
+        it = m.t_int(1)
+        bt = m.t_bool()
+        n = m.inst(Op.IAdd, it, m.const_i(3), m.inst(Op.BitwiseAnd, it, m.inst(Op.ConvertFToS, it,
+                   m.inst(Op.FMul, fl, ax, m.const_f(8.0))), m.const_i(3)))
+        entry = m.cur_label
+        head, body, cont, merge = m.new_id(), m.new_id(), m.new_id(), m.new_id()
+        m.stmt(Op.Branch, head)
+        m.label(head)
+        i_phi, acc_phi, oth_phi = m.new_id(), m.new_id(), m.new_id()
+        i_next, acc_next, oth_next = m.new_id(), m.new_id(), m.new_id()
+        m.raw(Op.Phi, it, i_phi, m.const_i(0), entry, i_next, cont)
+        if op == "phi_swap":
+            # acc takes the OLD value of the other phi of the same block: the copies of an edge are parallel
+            m.raw(Op.Phi, v4, acc_phi, a, entry, oth_phi, cont)
+            m.raw(Op.Phi, v4, oth_phi, b, entry, oth_next, cont)
+        else:
+            m.raw(Op.Phi, v4, acc_phi, a, entry, acc_next, cont)
+            m.raw(Op.Phi, v4, oth_phi, b, entry, oth_next, cont)
+        cond = m.inst(Op.SLessThan, bt, i_phi, n)
+        m.stmt(Op.LoopMerge, merge, cont, 0)
+        m.stmt(Op.BranchConditional, cond, body, merge)
+        m.label(body)
+        half = m.inst(Op.FMul, v4, acc_phi, m.const_fvec(0.5, 0.5, 0.5, 0.5))
+        val = m.inst(Op.FAdd, v4, half, m.inst(Op.FMul, v4, oth_phi, c))
+        m.stmt(Op.Branch, cont)
+        m.label(cont)
+        if op == "phi_swap":
+            m.raw(Op.FAdd, v4, oth_next, val, m.const_fvec(0.0, 0.0, 0.0, 0.0))
+        else:
+            m.raw(Op.FAdd, v4, acc_next, val, m.const_fvec(0.0, 0.0, 0.0, 0.0))
+            m.raw(Op.FAdd, v4, oth_next, oth_phi, m.const_fvec(0.0, 0.0, 0.0, 0.0))
+        m.raw(Op.IAdd, it, i_next, i_phi, m.const_i(1))
+        m.stmt(Op.Branch, head)
+        m.label(merge)
+        r = m.inst(Op.FMul, v4, m.inst(Op.FAdd, v4, acc_phi, oth_phi), m.const_fvec(0.25, 0.25, 0.25, 0.25))
     elif op == "fabs":
         r = m.ext(v4, GLSL.FAbs, a)
     elif op == "floor":

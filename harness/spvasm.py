@@ -85,6 +85,7 @@ class Op:
     BitwiseAnd = 199
     DPdx = 207
     DPdy = 208
+    Phi = 245
     LoopMerge = 246
     SelectionMerge = 247
     Label = 248
@@ -127,9 +128,29 @@ class BuiltIn:
 
 
 class GLSL:
+    RoundEven = 2
+    Trunc = 3
     FAbs = 4
+    SAbs = 5
+    FSign = 6
+    SSign = 7
     Floor = 8
+    Ceil = 9
     Fract = 10
+    Radians = 11
+    Degrees = 12
+    UMin = 38
+    SMin = 39
+    UMax = 41
+    SMax = 42
+    UClamp = 44
+    SClamp = 45
+    Step = 48
+    SmoothStep = 49
+    Fma = 50
+    Distance = 67
+    FaceForward = 70
+    Refract = 72
     Sin = 13
     Cos = 14
     Pow = 26
@@ -359,7 +380,13 @@ class Module:
     def label(self, i: int | None = None) -> int:
         i = i if i is not None else self.new_id()
         self._emit("funcs", Op.Label, i)
+        self.cur_label = i
         return i
+
+    def raw(self, opcode: int, result_t: int, result_id: int, *operands: int) -> int:
+        """Like inst(), with a result id the caller reserved earlier (OpPhi operands refer to later ids)."""
+        self._emit("funcs", opcode, result_t, result_id, *operands)
+        return result_id
 
     def inst(self, opcode: int, result_t: int, *operands: int) -> int:
         """Emit an instruction with (result type, result id) and return the result id."""

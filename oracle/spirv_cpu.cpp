@@ -51,7 +51,7 @@ enum Op : uint16_t
   OpTranspose = 84, OpImageSampleImplicitLod = 87, OpConvertSToF = 111, OpFNegate = 127,
   // outside the reference's subset: accepted only in extended mode
   OpConvertFToS = 110, OpBitcast = 124, OpISub = 130, OpSelect = 169, OpFOrdEqual = 180,
-  OpFOrdNotEqual = 182, OpFOrdGreaterThanEqual = 190,
+  OpFOrdNotEqual = 182, OpFOrdGreaterThanEqual = 190, OpPhi = 245, OpKill = 252,
   OpIAdd = 128, OpFAdd = 129, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136,
   OpVectorTimesScalar = 142, OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144,
   OpMatrixTimesVector = 145, OpMatrixTimesMatrix = 146, OpDot = 148, OpIEqual = 170,
@@ -73,7 +73,11 @@ enum : uint32_t
   G_Sin = 13, G_Cos = 14, G_Pow = 26, G_Sqrt = 31, G_InverseSqrt = 32, G_MatrixInverse = 34,
   G_FMin = 37, G_FMax = 40, G_FClamp = 43, G_FMix = 46, G_Length = 66, G_Cross = 68,
   G_Normalize = 69, G_Reflect = 71,
-  G_FAbs = 4, G_Floor = 8, G_Fract = 10,    // extended mode only
+  // extended mode only
+  G_RoundEven = 2, G_Trunc = 3, G_FAbs = 4, G_SAbs = 5, G_FSign = 6, G_SSign = 7, G_Floor = 8, G_Ceil = 9,
+  G_Fract = 10, G_Radians = 11, G_Degrees = 12, G_UMin = 38, G_SMin = 39, G_UMax = 41, G_SMax = 42,
+  G_UClamp = 44, G_SClamp = 45, G_Step = 48, G_SmoothStep = 49, G_Fma = 50, G_Distance = 67, G_FaceForward = 70,
+  G_Refract = 72,
 };
 
 
@@ -598,10 +602,15 @@ static void parse(Module &m)
               cur->insts.push_back(pCode);
               break;
             case OpConvertFToS: case OpBitcast: case OpISub: case OpSelect: case OpFOrdEqual:
-            case OpFOrdNotEqual: case OpFOrdGreaterThanEqual:
+            case OpFOrdNotEqual: case OpFOrdGreaterThanEqual: case OpPhi:
               if(!g_extended)
                 FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
               m.valtype[chk(pCode[2])] = chk(pCode[1]);
+              cur->insts.push_back(pCode);
+              break;
+            case OpKill:
+              if(!g_extended)
+                FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
               cur->insts.push_back(pCode);
               break;
             case OpStore: case OpBranch: case OpBranchConditional: case OpReturn:
@@ -737,6 +746,7 @@ struct State
   std::vector<uint8_t> arena;
   size_t top = 0;
   std::vector<uint8_t> globals;
+  bool killed = false;    // extended mode: the invocation executed OpKill
 
   uint8_t *alloc(uint32_t size, uint32_t align)
   {
@@ -791,6 +801,7 @@ struct Interp
 
     size_t pc = 0;
     const size_t n = fn.insts.size();
+    uint32_t curLabel = 0, prevLabel = 0;    // for OpPhi (extended mode)
     while(pc < n)
     {
       const uint32_t *w = fn.insts[pc++];
@@ -798,7 +809,41 @@ struct Interp
       const uint16_t op = w[0] & 0xffff;
       switch(op)
       {
-        case OpLabel: break;
+        case OpLabel:
+          prevLabel = curLabel;
+          curLabel = w[1];
+          break;
+        case OpPhi:    // extended mode: all phis of a block read their operands before any of them is written
+        {
+          size_t first = pc - 1, last = first;
+          while(last + 1 < n && (fn.insts[last + 1][0] & 0xffff) == OpPhi)
+            last++;
+          std::vector<Val> fresh(last - first + 1);
+          for(size_t i = first; i <= last; i++)
+          {
+            const uint32_t *ph = fn.insts[i];
+            const uint16_t pwc = ph[0] >> 16;
+            bool found = false;
+            for(uint16_t j = 3; j + 1 < pwc; j += 2)
+              if(ph[j + 1] == prevLabel)
+              {
+                fresh[i - first] = V[ph[j]];
+                found = true;
+              }
+            if(!found)
+            {
+              fprintf(stderr, "vor: OpPhi without an operand for predecessor %u\n", prevLabel);
+              abort();
+            }
+          }
+          for(size_t i = first; i <= last; i++)
+            V[fn.insts[i][2]] = fresh[i - first];
+          pc = last + 1;
+          break;
+        }
+        case OpKill:
+          st.killed = true;
+          return;
         case OpVariable:    // :1097-1107
         {
           const Type &pt = m.types[m.types[w[1]].elem];
@@ -891,6 +936,8 @@ struct Interp
           Val r;
           memset(&r, 0, sizeof(r));
           exec(callee, a, &r);
+          if(st.killed)
+            return;
           V[w[2]] = r;
           break;
         }
@@ -1137,6 +1184,119 @@ struct Interp
         for(uint32_t c = 0; c < k; c++)
           r.f[c] = ARG(0).f[c] - floorf(ARG(0).f[c]);
         break;
+      // ---- the rest is extended mode only: GLSL.std.450 with its plain semantics
+      case G_RoundEven:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = nearbyintf(ARG(0).f[c]);    // default rounding mode: to nearest even
+        break;
+      case G_Trunc:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = truncf(ARG(0).f[c]);
+        break;
+      case G_Ceil:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = ceilf(ARG(0).f[c]);
+        break;
+      case G_SAbs:
+        for(uint32_t c = 0; c < k; c++)
+          r.u[c] = ARG(0).i[c] < 0 ? 0u - ARG(0).u[c] : ARG(0).u[c];
+        break;
+      case G_FSign:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = ARG(0).f[c] > 0.0f ? 1.0f : (ARG(0).f[c] < 0.0f ? -1.0f : 0.0f);
+        break;
+      case G_SSign:
+        for(uint32_t c = 0; c < k; c++)
+          r.i[c] = ARG(0).i[c] > 0 ? 1 : (ARG(0).i[c] < 0 ? -1 : 0);
+        break;
+      case G_Radians:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = ARG(0).f[c] * 0.017453292519943295f;
+        break;
+      case G_Degrees:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = ARG(0).f[c] * 57.29577951308232f;
+        break;
+      case G_UMin:
+        for(uint32_t c = 0; c < k; c++)
+          r.u[c] = ARG(0).u[c] < ARG(1).u[c] ? ARG(0).u[c] : ARG(1).u[c];
+        break;
+      case G_SMin:
+        for(uint32_t c = 0; c < k; c++)
+          r.i[c] = ARG(0).i[c] < ARG(1).i[c] ? ARG(0).i[c] : ARG(1).i[c];
+        break;
+      case G_UMax:
+        for(uint32_t c = 0; c < k; c++)
+          r.u[c] = ARG(0).u[c] > ARG(1).u[c] ? ARG(0).u[c] : ARG(1).u[c];
+        break;
+      case G_SMax:
+        for(uint32_t c = 0; c < k; c++)
+          r.i[c] = ARG(0).i[c] > ARG(1).i[c] ? ARG(0).i[c] : ARG(1).i[c];
+        break;
+      case G_UClamp:    // min(max(x, lo), hi)
+        for(uint32_t c = 0; c < k; c++)
+        {
+          uint32_t v = ARG(0).u[c] > ARG(1).u[c] ? ARG(0).u[c] : ARG(1).u[c];
+          r.u[c] = v < ARG(2).u[c] ? v : ARG(2).u[c];
+        }
+        break;
+      case G_SClamp:
+        for(uint32_t c = 0; c < k; c++)
+        {
+          int32_t v = ARG(0).i[c] > ARG(1).i[c] ? ARG(0).i[c] : ARG(1).i[c];
+          r.i[c] = v < ARG(2).i[c] ? v : ARG(2).i[c];
+        }
+        break;
+      case G_Step:    // x < edge ? 0 : 1
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = ARG(1).f[c] < ARG(0).f[c] ? 0.0f : 1.0f;
+        break;
+      case G_SmoothStep:
+        for(uint32_t c = 0; c < k; c++)
+        {
+          float num = ARG(2).f[c] - ARG(0).f[c], den = ARG(1).f[c] - ARG(0).f[c];
+          float q = num / den;
+          float u = (q < 1.0f) ? q : 1.0f;
+          float t = (u > 0.0f) ? u : 0.0f;
+          float tt = t * t, two = 2.0f * t, rest = 3.0f - two;
+          r.f[c] = tt * rest;
+        }
+        break;
+      case G_Fma:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = fmaf(ARG(0).f[c], ARG(1).f[c], ARG(2).f[c]);
+        break;
+      case G_Distance:
+      {
+        uint32_t n = comps(m, m.valtype[w[5]]);
+        float d[4] = {0, 0, 0, 0};
+        for(uint32_t c = 0; c < n; c++)
+          d[c] = ARG(0).f[c] - ARG(1).f[c];
+        r.f[0] = sqrtf(dotN(d, d, n));
+        break;
+      }
+      case G_FaceForward:    // dot(Nref, I) < 0 ? N : -N
+      {
+        uint32_t n = comps(m, m.valtype[w[5]]);
+        float dd = dotN(ARG(2).f, ARG(1).f, n);
+        for(uint32_t c = 0; c < n; c++)
+          r.f[c] = dd < 0.0f ? ARG(0).f[c] : -0.0f - ARG(0).f[c];
+        break;
+      }
+      case G_Refract:    // k = 1 - eta*eta*(1 - d*d), d = dot(N, I); k < 0 ? 0 : eta*I - (eta*d + sqrt(k))*N
+      {
+        uint32_t n = comps(m, m.valtype[w[5]]);
+        float eta = ARG(2).f[0];
+        float d = dotN(ARG(1).f, ARG(0).f, n);
+        float dd = d * d, om = 1.0f - dd, ee = eta * eta, eo = ee * om, kk = 1.0f - eo;
+        float ed = eta * d, sq = sqrtf(kk), t = ed + sq;
+        for(uint32_t c = 0; c < n; c++)
+        {
+          float ei = eta * ARG(0).f[c], tn = t * ARG(1).f[c];
+          r.f[c] = kk < 0.0f ? 0.0f : ei - tn;
+        }
+        break;
+      }
       case G_Cos: r.f[0] = cosf(ARG(0).f[0]); break;      // llvm.cos.f32 -> CRT (not reproducible)
       case G_Sin: r.f[0] = sinf(ARG(0).f[0]); break;      // llvm.sin.f32 -> CRT (not reproducible)
       case G_Sqrt: r.f[0] = sqrtf(ARG(0).f[0]); break;    // llvm.sqrt.f32 -> sqrtss (exact)
@@ -1194,7 +1354,10 @@ static void validateExt(const Module &m)
           case G_FMax: case G_FMin: case G_FClamp: case G_FMix: case G_Cos: case G_Sin:
           case G_Sqrt: case G_Normalize: case G_Length: case G_Cross: case G_Pow: case G_Reflect:
           case G_MatrixInverse: break;
-          case G_FAbs: case G_Floor: case G_Fract:
+          case G_FAbs: case G_Floor: case G_Fract: case G_RoundEven: case G_Trunc: case G_Ceil: case G_SAbs:
+          case G_FSign: case G_SSign: case G_Radians: case G_Degrees: case G_UMin: case G_SMin: case G_UMax:
+          case G_SMax: case G_UClamp: case G_SClamp: case G_Step: case G_SmoothStep: case G_Fma: case G_Distance:
+          case G_FaceForward: case G_Refract:
             if(!g_extended)
               FAIL("Unhandled GLSL extended instruction %u", w[4]);    // :1734
             break;
@@ -1458,13 +1621,14 @@ void run_vertex(const Entry *e, const ShaderEnv &env, uint32_t vertexIndex, floa
   }
 }
 
-void run_fragment(const Entry *e, const ShaderEnv &env, float pixdepth, const float bary[4],
+bool run_fragment(const Entry *e, const ShaderEnv &env, float pixdepth, const float bary[4],
                   const float *tri, float out[4])
 {
   (void)pixdepth;
   const Module &m = *e->mod;
   State &st = stateFor(&m);
   st.top = 0;
+  st.killed = false;
 
   auto interps = [&](int vert, uint32_t loc) { return tri + vert * kVertexFloats + 4 + 4 * loc; };
   // CreateDot(loadedBary, (v0,v1,v2,0), 4) (:2202-2211)
@@ -1516,6 +1680,8 @@ void run_fragment(const Entry *e, const ShaderEnv &env, float pixdepth, const fl
 
   Interp in{m, st, env};
   in.exec(m.funcs.at(e->func), NULL, NULL);
+  if(st.killed)
+    return true;
 
   for(const ExternalBinding &ext : m.externals)
   {
@@ -1541,5 +1707,6 @@ void run_fragment(const Entry *e, const ShaderEnv &env, float pixdepth, const fl
       abort();
     }
   }
+  return false;
 }
 }    // namespace vor

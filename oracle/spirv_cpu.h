@@ -56,7 +56,8 @@ int entry_stage(const Entry *e);    // 0 vertex, 4 fragment
 // Slots the shader does not write are left untouched in `out`.
 void run_vertex(const Entry *e, const ShaderEnv &env, uint32_t vertexIndex, float out[kVertexFloats]);
 // The exported FS wrapper (spirv_compile.cpp:2118-2366): void fs(state, pixdepth, bary, tri[3], out).
-void run_fragment(const Entry *e, const ShaderEnv &env, float pixdepth, const float bary[4],
+// Returns true when the invocation executed OpKill (extended mode only; `out` is then left untouched).
+bool run_fragment(const Entry *e, const ShaderEnv &env, float pixdepth, const float bary[4],
                   const float *tri /* 3 x kVertexFloats */, float out[4]);
 
 // GetVertexAttributeData's format switch (spirv_compile.cpp:576-626) on an already-resolved pointer.

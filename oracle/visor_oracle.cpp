@@ -611,7 +611,9 @@ __attribute__((visibility("default"))) int vor_draw(const vb200_draw_state *s, i
         n[2] *= invlen;
 
         float pix[4] = {0, 0, 0, 0};
-        vor::run_fragment(fs, env, pixdepth, n, (const float *)vsout, pix);
+        // (extended mode only, no reference counterpart: a discarded fragment writes neither colour nor depth)
+        if(vor::run_fragment(fs, env, pixdepth, n, (const float *)vsout, pix))
+          continue;
 
         byte *px = bits + pidx * bpp;
         if(pipe->blend_enable)

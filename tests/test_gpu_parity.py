@@ -166,6 +166,29 @@ def test_extended_spirv_ops(gpu, vor, op):
         oset(b"extended_spirv", 0)
 
 
+@pytest.mark.parametrize("variant", ["depth", "blend", "callee"])
+def test_discard_in_the_fragment_shader(gpu, vor, variant):
+    """extended mode, OpKill: a discarded fragment writes neither colour nor depth. The colour a pixel ends up with
+    is that of the last fragment that passed and was KEPT, so such shaders always run on the in-order tile kernel
+    (also when the pass would otherwise be order independent)."""
+    from harness import shaders
+    gset, oset = gpu.lib.vb200_set_option, vor.lib.vor_set_option
+    gset.argtypes = oset.argtypes = [C.c_char_p, C.c_int64]
+    with pytest.raises(abi.BackendError):
+        gpu.CompileFunction(shaders.fs_color_kill())
+    assert gset(b"extended_spirv", 1) == 0 and oset(b"extended_spirv", 1) == 0
+    try:
+        blend = (abi.BF_SRC_ALPHA, abi.BF_ONE_MINUS_SRC_ALPHA, 0) if variant == "blend" else None
+        sc = scenes.random_triangles(300, 200, 300, 17, blend=blend)
+        sc.draws[0].pipe.fs = shaders.fs_color_kill(0.45, in_callee=(variant == "callee"))
+        _check(gpu, vor, sc)
+        gpu.lib.vb200_last_tile_kernel.restype = C.c_char_p
+        assert gpu.lib.vb200_last_tile_kernel() == b"vb200_k_tile_ordered"
+    finally:
+        gset(b"extended_spirv", 0)
+        oset(b"extended_spirv", 0)
+
+
 def test_resolve_without_slot_keys(gpu, vor):
     """draws with >= 2^24 triangles cannot carry the record slot in the visibility key; the option forces
     that code path (phase B gathers the winner from global memory) on ordinary scenes"""

@@ -217,6 +217,70 @@ def _expected_ext(op, a, b, c):
         return np.floor(a)
     if op == "fract":
         return a - np.floor(a)
+    if op in ("roundeven", "trunc", "ceil"):
+        x = (a * np.array([3.5, 2.5, 7.25, 0.5], f32)).astype(f32)
+        fn = {"roundeven": np.rint, "trunc": np.trunc, "ceil": np.ceil}[op]
+        return (fn(x).astype(f32) * f32(0.125)).astype(f32)
+    if op == "fsign":
+        return np.where(a > 0, f32(1), np.where(a < 0, f32(-1), f32(0))).astype(f32)
+    if op == "radians":
+        return (a * f32(0.017453292519943295)).astype(f32)
+    if op == "degrees":
+        return ((a * f32(57.29577951308232)).astype(f32) * f32(0.125)).astype(f32) * f32(0.125)
+    if op == "step":
+        return np.where(b < a, f32(0), f32(1)).astype(f32)
+    if op == "smoothstep":
+        with np.errstate(all="ignore"):
+            q = ((c - a).astype(f32) / (b - a).astype(f32)).astype(f32)
+        u = np.where(q < 1, q, f32(1)).astype(f32)
+        t = np.where(u > 0, u, f32(0)).astype(f32)
+        return ((t * t).astype(f32) * (f32(3) - (f32(2) * t).astype(f32)).astype(f32)).astype(f32)
+    if op == "fma":
+        return np.array([np.float64(x) * np.float64(y) + np.float64(z) for x, y, z in zip(a, b, c)]).astype(f32)
+    def dot3(x, y):    # CreateDot order: ((x0*y0 + x1*y1) + x2*y2)
+        return f32(f32(f32(x[0] * y[0]) + f32(x[1] * y[1])) + f32(x[2] * y[2]))
+    if op == "distance3":
+        d = (a[:3] - b[:3]).astype(f32)
+        return np.full(4, np.sqrt(dot3(d, d)), f32)
+    if op == "faceforward3":
+        nref = (c[:3] - a[:3]).astype(f32)
+        dd = dot3(nref, b[:3])
+        r = a[:3] if dd < 0 else (f32(-0.0) - a[:3]).astype(f32)
+        return np.array([r[0], r[1], r[2], 0.0], f32)
+    if op == "refract3":
+        def normalize(v):
+            inv = f32(f32(1.0) / np.sqrt(dot3(v, v)))
+            return (v * inv).astype(f32)
+        I, N, eta = normalize(a[:3]), normalize(b[:3]), c[0]
+        d = dot3(N, I)
+        kk = f32(f32(1) - f32(f32(eta * eta) * f32(f32(1) - f32(d * d))))
+        if kk < 0:
+            return np.zeros(4, f32)
+        t = f32(f32(eta * d) + np.sqrt(kk))
+        r = ((eta * I).astype(f32) - (t * N).astype(f32)).astype(f32)
+        return np.array([r[0], r[1], r[2], 0.0], f32)
+    if op in ("int_minmax", "uint_minmax", "int_abs_sign"):
+        def ints(x):
+            return np.trunc((x * f32(64)).astype(f32)).astype(np.int64) - 24
+        ia, ib, ic = ints(a), ints(b), ints(c)
+        if op == "int_abs_sign":
+            x = np.abs(ia) + np.sign(ib)
+        else:
+            if op == "uint_minmax":
+                ia, ib, ic = ia & 0xffffffff, ib & 0xffffffff, ic & 0xffffffff
+            lo, hi = np.minimum(ia, ib), np.maximum(ia, ib)
+            x = lo + hi + np.minimum(np.maximum(ic, lo), hi)
+        return ((x & 255).astype(f32) * f32(1 / 256.0)).astype(f32)
+    if op in ("phi_loop", "phi_swap"):
+        n = 3 + (int(np.trunc(f32(a[0] * f32(8.0)))) & 3)
+        acc, oth = a.copy(), b.copy()
+        for _ in range(n):
+            val = ((acc * f32(0.5)).astype(f32) + (oth * c).astype(f32)).astype(f32)
+            if op == "phi_swap":
+                acc, oth = oth, (val + f32(0)).astype(f32)
+            else:
+                acc, oth = (val + f32(0)).astype(f32), (oth + f32(0)).astype(f32)
+        return ((acc + oth).astype(f32) * f32(0.25)).astype(f32)
     raise ValueError(op)
 
 
@@ -315,3 +379,37 @@ def test_vertex_output_padding_rules(vor):
     assert o[5][2] == o[5][0] and o[5][3] == o[5][0]             # vec2 @4 padded with .x
     assert o[5][0] == push[1] and o[5][1] == ubo[34]             # shuffle(k, s, 1, 6) = (k.y, s.z)
     assert np.array_equal(o[9], push)                            # mat4 @5..8: last column = k
+
+
+@pytest.mark.parametrize("in_callee", [False, True])
+def test_discard_leaves_colour_and_depth_untouched(vor, in_callee):
+    """extended mode, OpKill (no reference counterpart: CompileFunction asserts on it, spirv_compile.cpp:1888):
+    refused by default; when enabled a discarded fragment writes neither colour nor depth, every other pixel is
+    what the same scene gives without the discard. Known answer: the discard tests the interpolated red against
+    0.5, and the scene without it tells the red every fragment has."""
+    from harness import scenes
+    setopt = vor.lib.vor_set_option
+    setopt.argtypes = [C.c_char_p, C.c_int64]
+    with pytest.raises(abi.BackendError):
+        vor.CompileFunction(shaders.fs_color_kill(0.5, in_callee))
+    assert setopt(b"extended_spirv", 1) == 0
+    try:
+        def scene(kill):
+            sc = scenes.random_triangles(160, 96, 1, 5, max_size=1.9, perspective=False, offscreen=0.0)
+            if kill:
+                sc.draws[0].pipe.fs = shaders.fs_color_kill(0.5, in_callee)
+            return sc
+        plain_c, plain_d = scenes.render(vor, scene(False))
+        kill_c, kill_d = scenes.render(vor, scene(True))
+        covered = plain_d != np.float32(1.0)              # the one triangle's pixels (cleared depth is 1.0)
+        red = plain_c[..., 2]                             # BGRA bytes: byte(red * 255)
+        assert covered.sum() > 1000
+        killed = covered & (red < 127)
+        kept = covered & (red > 127)
+        assert killed.sum() > 100 and kept.sum() > 100
+        clear_c = scenes.render(vor, scenes.random_triangles(160, 96, 1, 5, max_size=0.0))[0][0, 0]
+        assert (kill_c[killed] == clear_c).all() and (kill_d[killed] == np.float32(1.0)).all()
+        assert np.array_equal(kill_c[kept], plain_c[kept]) and np.array_equal(kill_d[kept], plain_d[kept])
+        assert np.array_equal(kill_c[~covered], plain_c[~covered])
+    finally:
+        setopt(b"extended_spirv", 0)

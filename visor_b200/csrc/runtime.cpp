@@ -2193,6 +2193,10 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   }
   if(g.optRasterPath == 1)
     resolveMode = -1;
+  // a fragment shader that may discard (OpKill, extended mode): the colour a pixel ends up with is that of the
+  // last fragment that passed AND was kept, which only the in-order kernel knows
+  if(pl->fs->e.uses_kill)
+    resolveMode = -1;
 
   // ---- the batch this draw joins (kernels.h: Vb200BatchDraw). Everything that is uniform across a kernel
   // launch is part of the key; a draw with another key ends the recorded batch and starts the next.

@@ -42,8 +42,17 @@
 #endif
 
 extern "C" __device__ float4 vb200_vs(const Vb200Env *env, unsigned vid, float4 *interps_out);
-extern "C" __device__ float4 vb200_fs(const Vb200Env *env, float b0, float b1, float b2, const float4 *v0,
-                                      const float4 *v1, const float4 *v2);
+// The fragment entry point's result: the colour and, for shaders with OpKill (extended mode), whether the
+// invocation was discarded. Returned by value: after ptxas has inlined the shader both are plain registers, and
+// for a shader without OpKill `killed` is the constant 0 (the tests on it fold away).
+struct __align__(16) Vb200FsOut
+{
+  float4 color;
+  uint32_t killed;
+  uint32_t pad[3];
+};
+extern "C" __device__ Vb200FsOut vb200_fs(const Vb200Env *env, float b0, float b1, float b2, const float4 *v0,
+                                          const float4 *v1, const float4 *v2);
 
 // ------------------------------------------------------------------------------------------------
 // GetVertexAttributeData (spirv_compile.cpp:572-627)
@@ -323,9 +332,15 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
           n1 = __fmul_rn(n1, invlen);
           n2 = __fmul_rn(n2, invlen);
 
-          float4 pix = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)t.s0 * rs.nslots,
-                                p.interps + (size_t)t.s1 * rs.nslots, p.interps + (size_t)t.s2 * rs.nslots);
+          const Vb200FsOut fo = vb200_fs(&env, n0, n1, n2, p.interps + (size_t)t.s0 * rs.nslots,
+                                         p.interps + (size_t)t.s1 * rs.nslots, p.interps + (size_t)t.s2 * rs.nslots);
+          float4 pix = fo.color;
           const uint32_t cur = wcol[i];
+          // a discarded fragment (OpKill, extended mode) leaves colour and depth as they are
+          if(fo.killed)
+            ;
+          else
+          {
           if(blend)
           {
             // blend (rasterizer.cpp:593-672): existing = bytes (2,1,0) / 255.0f from the exact table
@@ -345,6 +360,7 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
           wcol[i] = (cur & 0xff000000u) | (r << 16) | (g << 8) | b;
           if(depthWrite)
             wdep[i] = pixdepth;
+          }
         }
       }
     }
@@ -1118,7 +1134,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       n0 = __fmul_rn(n0, invlen);
       n1 = __fmul_rn(n1, invlen);
       n2 = __fmul_rn(n2, invlen);
-      const float4 pix = vb200_fs(&env, n0, n1, n2, v0, v1, v2);
+      const float4 pix = vb200_fs(&env, n0, n1, n2, v0, v1, v2).color;    // (no OpKill here: runtime.cpp sends those shaders to the ordered kernel)
       vb200_store_color(p, gi, vb200_blend_store(rs, pix, clearColor ? p.clear_color : p.color[gi]), remote);
       if(depthWrite)
         __stcs(p.depth + gi, pixdepth);

@@ -48,7 +48,7 @@ enum : uint32_t
   OpReturn = 253, OpReturnValue = 254,
   // outside the reference's subset: accepted only in extended mode
   OpConvertFToS = 110, OpBitcast = 124, OpISub = 130, OpSelect = 169, OpFOrdEqual = 180, OpFOrdNotEqual = 182,
-  OpFOrdGreaterThanEqual = 190,
+  OpFOrdGreaterThanEqual = 190, OpPhi = 245, OpKill = 252,
 };
 enum : uint32_t
 {
@@ -60,7 +60,11 @@ enum : uint32_t
   Dim_Cube = 3,
   G_Sin = 13, G_Cos = 14, G_Pow = 26, G_Sqrt = 31, G_InverseSqrt = 32, G_MatrixInverse = 34, G_FMin = 37,
   G_FMax = 40, G_FClamp = 43, G_FMix = 46, G_Length = 66, G_Cross = 68, G_Normalize = 69, G_Reflect = 71,
-  G_FAbs = 4, G_Floor = 8, G_Fract = 10,    // extended mode only
+  // extended mode only
+  G_RoundEven = 2, G_Trunc = 3, G_FAbs = 4, G_SAbs = 5, G_FSign = 6, G_SSign = 7, G_Floor = 8, G_Ceil = 9,
+  G_Fract = 10, G_Radians = 11, G_Degrees = 12, G_UMin = 38, G_SMin = 39, G_UMax = 41, G_SMax = 42,
+  G_UClamp = 44, G_SClamp = 45, G_Step = 48, G_SmoothStep = 49, G_Fma = 50, G_Distance = 67, G_FaceForward = 70,
+  G_Refract = 72,
 };
 
 // Extended mode (option "extended_spirv"): a handful of opcodes the reference asserts on (SURVEY.md
@@ -465,10 +469,14 @@ struct Module
               valtype[id(p[2])] = id(p[1]);
               break;
             case OpConvertFToS: case OpBitcast: case OpISub: case OpSelect: case OpFOrdEqual: case OpFOrdNotEqual:
-            case OpFOrdGreaterThanEqual:
+            case OpFOrdGreaterThanEqual: case OpPhi:
               if(!g_extendedSpirv)
                 fail("Unhandled SPIR-V opcode %u", op);    // :1888
               valtype[id(p[2])] = id(p[1]);
+              break;
+            case OpKill:
+              if(!g_extendedSpirv)
+                fail("Unhandled SPIR-V opcode %u", op);    // :1888
               break;
             case OpLabel: case OpStore: case OpBranch: case OpBranchConditional: case OpReturn:
             case OpReturnValue: break;
@@ -506,8 +514,17 @@ struct Emitter
     std::string retLabel;
     std::vector<std::string> retRegs;
     std::string ret64;
+    // extended mode, OpPhi: the copies each predecessor block performs on its way out, keyed by predecessor
+    struct PhiMove
+    {
+      uint32_t block, phi, value;    // the phi's block, its result id, the incoming value id
+    };
+    std::map<uint32_t, std::vector<PhiMove>> phi;
+    uint32_t curLabel = 0;
   };
   std::vector<Frame> frames;
+  std::string killReg, killLabel;    // extended mode, OpKill (fragment entry points only)
+  int nEdge = 0;
 
   Emitter(Module &mod, int st, ShaderEntry *e) : m(mod), stage(st), info(e) { vals.resize(m.bound); }
 
@@ -900,6 +917,25 @@ struct Emitter
     }
     frames.push_back(fr);
 
+    {
+      // OpPhi (extended mode): result registers exist before the first predecessor is emitted; every
+      // predecessor copies its value into them right before it branches (emitEdge)
+      uint32_t block = 0;
+      for(const uint32_t *w : fn.body)
+      {
+        const uint32_t wc = w[0] >> 16, op = w[0] & 0xffff;
+        if(op == OpLabel)
+          block = w[1];
+        else if(op == OpPhi)
+        {
+          if(wc < 5 || ((wc - 3) & 1))
+            fail("malformed OpPhi");
+          defRegs(w[2], w[1]);
+          for(uint32_t i = 3; i + 1 < wc; i += 2)
+            frames.back().phi[w[i + 1]].push_back({block, w[2], w[i]});
+        }
+      }
+    }
     for(const uint32_t *w : fn.body)
       emitInst(w);
 
@@ -982,17 +1018,81 @@ struct Emitter
     return p;
   }
 
+  // the phi copies of the edge (current block -> `to`), as one parallel copy: all sources are read into
+  // temporaries before any phi register is written (a phi may be another phi's source)
+  bool edgeHasPhis(const Frame &fr, uint32_t to) const
+  {
+    auto it = fr.phi.find(fr.curLabel);
+    if(it == fr.phi.end())
+      return false;
+    for(const Frame::PhiMove &mv : it->second)
+      if(mv.block == to)
+        return true;
+    return false;
+  }
+  void emitEdge(const Frame &fr, uint32_t to)
+  {
+    auto it = fr.phi.find(fr.curLabel);
+    if(it == fr.phi.end())
+      return;
+    std::vector<std::pair<std::string, std::string>> copies;    // (phi register, temporary)
+    std::vector<bool> pred;
+    for(const Frame::PhiMove &mv : it->second)
+    {
+      if(mv.block != to)
+        continue;
+      const Value &src = use(mv.value), &dst = use(mv.phi);
+      if(src.r.size() != dst.r.size())
+        fail("OpPhi operand shape mismatch");
+      const bool b = isBoolTy(dst.type);
+      for(size_t i = 0; i < src.r.size(); i++)
+      {
+        std::string t = b ? P() : R();
+        line(b ? "mov.pred %s, %s;" : "mov.b32 %s, %s;", t.c_str(), src.r[i].c_str());
+        copies.push_back({dst.r[i], t});
+        pred.push_back(b);
+      }
+    }
+    for(size_t i = 0; i < copies.size(); i++)
+      line(pred[i] ? "mov.pred %s, %s;" : "mov.b32 %s, %s;", copies[i].first.c_str(), copies[i].second.c_str());
+  }
+
   void emitInst(const uint32_t *w)
   {
     const uint32_t wc = w[0] >> 16, op = w[0] & 0xffff;
     Frame &fr = frames.back();
     switch(op)
     {
-      case OpLabel: out += label(fr.inl, w[1]) + ":\n"; break;
-      case OpBranch: line("bra %s;", label(fr.inl, w[1]).c_str()); break;
+      case OpLabel:
+        out += label(fr.inl, w[1]) + ":\n";
+        fr.curLabel = w[1];
+        break;
+      case OpBranch:
+        emitEdge(fr, w[1]);
+        line("bra %s;", label(fr.inl, w[1]).c_str());
+        break;
       case OpBranchConditional:
+        if(edgeHasPhis(fr, w[2]) || edgeHasPhis(fr, w[3]))
+        {
+          const std::string taken = "$LE" + std::to_string(nEdge++);
+          line("@%s bra %s;", regs(w[1], 1)[0].c_str(), taken.c_str());
+          emitEdge(fr, w[3]);
+          line("bra %s;", label(fr.inl, w[3]).c_str());
+          out += taken + ":\n";
+          emitEdge(fr, w[2]);
+          line("bra %s;", label(fr.inl, w[2]).c_str());
+          break;
+        }
         line("@%s bra %s;", regs(w[1], 1)[0].c_str(), label(fr.inl, w[2]).c_str());
         line("bra %s;", label(fr.inl, w[3]).c_str());
+        break;
+      case OpPhi: break;    // registers allocated by emitFunction, written by the predecessors
+      case OpKill:    // extended mode: the invocation ends here; the wrapper reports it to the tile kernel
+        if(killLabel.empty())
+          fail("OpKill outside a fragment shader");
+        info->uses_kill = true;
+        line("mov.b32 %s, 1;", killReg.c_str());
+        line("bra %s;", killLabel.c_str());
         break;
       case OpReturn: line("bra %s;", fr.retLabel.c_str()); break;
       case OpReturnValue:
@@ -1396,6 +1496,10 @@ struct Emitter
       if(wc != n)
         fail("extended instruction operand count");
     };
+    auto needExt = [&](uint32_t inst) {
+      if(!g_extendedSpirv)
+        fail("Unhandled GLSL extended instruction %u", inst);    // :1734
+    };
     Value v;
     v.type = w[1];
     v.defined = true;
@@ -1524,6 +1628,137 @@ struct Emitter
           else
             line("cvt.rmi.f32.f32 %s, %s;", d.c_str(), A(0)[c].c_str());    // floor
           v.r.push_back(w[4] == G_Fract ? fsub(A(0)[c], d) : d);
+        }
+        break;
+      }
+      // ---- the rest is extended mode only: GLSL.std.450 with its plain semantics, every float step an
+      // explicit .rn operation in the order the CPU interpreter (oracle/spirv_cpu.cpp) performs it
+      case G_RoundEven: case G_Trunc: case G_Ceil:
+      {
+        needExt(w[4]);
+        const char *ins = w[4] == G_RoundEven ? "cvt.rni.f32.f32" : w[4] == G_Trunc ? "cvt.rzi.f32.f32" : "cvt.rpi.f32.f32";
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string d = R();
+          line("%s %s, %s;", ins, d.c_str(), A(0)[c].c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case G_SAbs:
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string d = R();
+          line("abs.s32 %s, %s;", d.c_str(), A(0)[c].c_str());
+          v.r.push_back(d);
+        }
+        break;
+      case G_FSign: case G_SSign:    // x > 0 ? 1 : x < 0 ? -1 : 0 (NaN and -0 give 0)
+      {
+        needExt(w[4]);
+        const bool f = w[4] == G_FSign;
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string pp = P(), pn = P(), t = R(), d = R();
+          line("%s %s, %s, %s;", f ? "setp.gt.f32" : "setp.gt.s32", pp.c_str(), A(0)[c].c_str(), f ? fimm(0.0f).c_str() : "0");
+          line("%s %s, %s, %s;", f ? "setp.lt.f32" : "setp.lt.s32", pn.c_str(), A(0)[c].c_str(), f ? fimm(0.0f).c_str() : "0");
+          line("selp.b32 %s, %s, %s, %s;", t.c_str(), f ? fimm(-1.0f).c_str() : "-1", f ? fimm(0.0f).c_str() : "0", pn.c_str());
+          line("selp.b32 %s, %s, %s, %s;", d.c_str(), f ? fimm(1.0f).c_str() : "1", t.c_str(), pp.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case G_Radians: case G_Degrees:    // x * RN(pi/180), x * RN(180/pi)
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+          v.r.push_back(fmul(A(0)[c], fimm(w[4] == G_Radians ? 0.017453292519943295f : 57.29577951308232f)));
+        break;
+      case G_UMin: case G_SMin: case G_UMax: case G_SMax:
+      {
+        needExt(w[4]);
+        const char *ins = w[4] == G_UMin ? "min.u32" : w[4] == G_SMin ? "min.s32" : w[4] == G_UMax ? "max.u32" : "max.s32";
+        for(uint32_t c = 0; c < k; c++)
+          v.r.push_back(f2(ins, A(0)[c], A(1)[c]));
+        break;
+      }
+      case G_UClamp: case G_SClamp:    // min(max(x, lo), hi)
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+          v.r.push_back(f2(w[4] == G_UClamp ? "min.u32" : "min.s32",
+                           f2(w[4] == G_UClamp ? "max.u32" : "max.s32", A(0)[c], A(1)[c]), A(2)[c]));
+        break;
+      case G_Step:    // x < edge ? 0 : 1
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string pp = P(), d = R();
+          line("setp.lt.f32 %s, %s, %s;", pp.c_str(), A(1)[c].c_str(), A(0)[c].c_str());
+          line("selp.b32 %s, %s, %s, %s;", d.c_str(), fimm(0.0f).c_str(), fimm(1.0f).c_str(), pp.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      case G_SmoothStep:    // t = clamp((x - e0) / (e1 - e0), 0, 1) in FClamp's select form; (t*t) * (3 - 2*t)
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string q = fdiv(fsub(A(2)[c], A(0)[c]), fsub(A(1)[c], A(0)[c]));
+          std::string pu = P(), u = R(), pl = P(), t = R();
+          line("setp.lt.f32 %s, %s, %s;", pu.c_str(), q.c_str(), fimm(1.0f).c_str());
+          line("selp.b32 %s, %s, %s, %s;", u.c_str(), q.c_str(), fimm(1.0f).c_str(), pu.c_str());
+          line("setp.gt.f32 %s, %s, %s;", pl.c_str(), u.c_str(), fimm(0.0f).c_str());
+          line("selp.b32 %s, %s, %s, %s;", t.c_str(), u.c_str(), fimm(0.0f).c_str(), pl.c_str());
+          v.r.push_back(fmul(fmul(t, t), fsub(fimm(3.0f), fmul(fimm(2.0f), t))));
+        }
+        break;
+      case G_Fma:    // fused: one rounding
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string d = R();
+          line("fma.rn.f32 %s, %s, %s, %s;", d.c_str(), A(0)[c].c_str(), A(1)[c].c_str(), A(2)[c].c_str());
+          v.r.push_back(d);
+        }
+        break;
+      case G_Distance:    // length(a - b)
+      {
+        needExt(w[4]);
+        const uint32_t n = (uint32_t)A(0).size();
+        std::vector<std::string> d;
+        for(uint32_t c = 0; c < n; c++)
+          d.push_back(fsub(A(0)[c], A(1)[c]));
+        v.r.push_back(fsqrt(dot(d, d, n)));
+        break;
+      }
+      case G_FaceForward:    // dot(Nref, I) < 0 ? N : -N
+      {
+        needExt(w[4]);
+        const uint32_t n = (uint32_t)A(0).size();
+        std::string dd = dot(A(2), A(1), n), pp = P();
+        line("setp.lt.f32 %s, %s, %s;", pp.c_str(), dd.c_str(), fimm(0.0f).c_str());
+        for(uint32_t c = 0; c < n; c++)
+        {
+          std::string neg = fsub(fimm(-0.0f), A(0)[c]), d = R();
+          line("selp.b32 %s, %s, %s, %s;", d.c_str(), A(0)[c].c_str(), neg.c_str(), pp.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case G_Refract:    // k = 1 - eta*eta*(1 - d*d), d = dot(N, I); k < 0 ? 0 : eta*I - (eta*d + sqrt(k))*N
+      {
+        needExt(w[4]);
+        const uint32_t n = (uint32_t)A(0).size();
+        const std::string &eta = A(2)[0];
+        std::string d = dot(A(1), A(0), n);
+        std::string kk = fsub(fimm(1.0f), fmul(fmul(eta, eta), fsub(fimm(1.0f), fmul(d, d))));
+        std::string pp = P();
+        line("setp.lt.f32 %s, %s, %s;", pp.c_str(), kk.c_str(), fimm(0.0f).c_str());
+        std::string t = fadd(fmul(eta, d), fsqrt(kk));
+        for(uint32_t c = 0; c < n; c++)
+        {
+          std::string val = fsub(fmul(eta, A(0)[c]), fmul(t, A(1)[c])), r = R();
+          line("selp.b32 %s, %s, %s, %s;", r.c_str(), fimm(0.0f).c_str(), val.c_str(), pp.c_str());
+          v.r.push_back(r);
         }
         break;
       }
@@ -1789,6 +2024,9 @@ struct Emitter
     line("ld.param.u64 %s, [vb200_fs_param_4];", v0.c_str());
     line("ld.param.u64 %s, [vb200_fs_param_5];", v1.c_str());
     line("ld.param.u64 %s, [vb200_fs_param_6];", v2.c_str());
+    killReg = R();
+    killLabel = "$LFSEND";
+    line("mov.b32 %s, 0;", killReg.c_str());
     setupGlobals();
     for(const External &ext : m.externals)
     {
@@ -1832,6 +2070,7 @@ struct Emitter
     }
 
     emitFunction(fn, {}, NULL);
+    out += killLabel + ":\n";
 
     std::vector<std::string> o = {imm(0), imm(0), imm(0), imm(0)};
     for(const External &ext : m.externals)
@@ -1852,6 +2091,7 @@ struct Emitter
         fail("Unsupported builtin output in a fragment shader");    // :2358
     }
     line("st.param.v4.b32 [func_retval0], {%s,%s,%s,%s};", o[0].c_str(), o[1].c_str(), o[2].c_str(), o[3].c_str());
+    line("st.param.b32 [func_retval0+16], %s;", killReg.c_str());    // Vb200FsOut::killed
     line("ret;");
   }
 
@@ -1876,7 +2116,7 @@ struct Emitter
       s += "\n.visible .func (.param .align 16 .b8 func_retval0[16]) vb200_vs\n(\n"
            "  .param .b64 vb200_vs_param_0,\n  .param .b32 vb200_vs_param_1,\n  .param .b64 vb200_vs_param_2\n)\n{\n";
     else
-      s += "\n.visible .func (.param .align 16 .b8 func_retval0[16]) vb200_fs\n(\n"
+      s += "\n.visible .func (.param .align 16 .b8 func_retval0[32]) vb200_fs\n(\n"
            "  .param .b64 vb200_fs_param_0,\n  .param .b32 vb200_fs_param_1,\n  .param .b32 vb200_fs_param_2,\n"
            "  .param .b32 vb200_fs_param_3,\n  .param .b64 vb200_fs_param_4,\n  .param .b64 vb200_fs_param_5,\n"
            "  .param .b64 vb200_fs_param_6\n)\n{\n";

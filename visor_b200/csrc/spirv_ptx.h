@@ -38,6 +38,7 @@ struct ShaderEntry
   uint32_t out_slot_mask = 0;             // VS: interpolant slots written
   uint32_t in_slot_mask = 0;              // FS: interpolant slots read
   bool uses_push = false;
+  bool uses_kill = false;                 // FS (extended mode): contains OpKill -> only the ordered tile kernel is exact
 };
 
 struct ShaderModule
