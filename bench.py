@@ -99,6 +99,25 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def nvlink_kib(index: int):
+    """(tx, rx) NVLink payload counters of one GPU in KiB, summed over its links (NVML field values), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        tx_id = getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
+        rx_id = getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(tx_id, 0xffffffff), (rx_id, 0xffffffff)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal))
+        return tuple(out)
+    except Exception:
+        return None
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant (tile) kernel, from the
 # `ncu --set full` captures summarised under profiles/ (a profiler cannot run inside the timed bench, so
 # the per-launch figure of the same build and workload is recorded here; null when none was captured).
@@ -408,6 +427,10 @@ def run_ours(args, workload: str) -> None:
             gpu.check(L.vb200_l2_flush(), "l2_flush")
             if multi:
                 dist.barrier()
+                if fused:
+                    # the host barrier releases the ranks tens of microseconds apart; a device-side barrier in front
+                    # of the start event lines the GPUs up, so that the step times the frame and not that skew
+                    gpu.check(L.vb200_mgpu_barrier(), "mgpu_barrier")
             gpu.check(L.vb200_event_record(0), "event")
             step_device()
             gpu.check(L.vb200_event_record(1), "event")
@@ -445,6 +468,22 @@ def run_ours(args, workload: str) -> None:
         dist.all_reduce(cnt)
         st["fragments_covered"], st["fragments_shaded"], st["tile_pairs"] = (int(v) for v in cnt.tolist())
     L.vb200_set_option(b"count_fragments", 0)
+
+    # N > 1: what the exchange really moves, read from the GPU's own NVLink counters (NVML, no profiler): payload
+    # bytes this rank sent and received per frame over a run of frames long enough for the counters to tick
+    nvlink = None
+    if multi:
+        n_nv = 200
+        barrier()
+        c0 = nvlink_kib(local)
+        for _ in range(n_nv):
+            step_device()
+        barrier()
+        time.sleep(0.05)
+        c1 = nvlink_kib(local)
+        if c0 and c1:
+            nvlink = {"tx_bytes_per_frame": (c1[0] - c0[0]) * 1024 // n_nv, "rx_bytes_per_frame": (c1[1] - c0[1]) * 1024 // n_nv,
+                      "frames": n_nv, "rank": rank, "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX, all links of this rank's GPU"}
 
     # ---------------- e2e: host buffers through the C-ABI, copies inside the timed region --------
     e2e_steps = max(3, min(args.steps, 10))
@@ -753,6 +792,8 @@ def run_ours(args, workload: str) -> None:
             line["many_draws"]["cuda_icd_queue_submit"] = icd
     if pipelined:
         line["e2e_pipelined"] = pipelined
+    if nvlink:
+        line["nvlink"] = nvlink
     if single:
         line["single_gpu_same_workload"] = single
     if scaling_base:
