@@ -27,6 +27,7 @@
 #include "kernels.h"
 #include "runtime_internal.h"
 #include "spirv_ptx.h"
+#include "ptx_inline.h"
 
 extern "C" const char vb200_scaffold_ptx[];
 extern "C" const unsigned long long vb200_scaffold_ptx_size;
@@ -757,6 +758,23 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
       body.erase(at, body.find('\n', at) - at);
   }
   stripExternFuncs(body);
+  {
+    // line info for the profiler: the shader's instructions carry no .loc of their own, so after inlining they
+    // would be booked on whatever kernel line happens to precede them in the cubin. They are pinned to line 1 of
+    // scaffold.cu instead (tools/ncu_regions.py, tools/sass_lines.py list that line as "shader, inlined").
+    const size_t f = scaffold.epilogue.find("scaffold.cu\"");
+    const size_t dir = f == std::string::npos ? f : scaffold.epilogue.rfind(".file", f);
+    const size_t open = body.find("\n{\n");
+    if(dir != std::string::npos && open != std::string::npos)
+    {
+      const unsigned long idx = strtoul(scaffold.epilogue.c_str() + dir + 5, nullptr, 10);
+      size_t at = open + 3;
+      while(body.compare(at, 6, "  .reg") == 0)    // after the register declarations
+        at = body.find('\n', at) + 1;
+      if(idx)
+        body.insert(at, "  .loc " + std::to_string(idx) + " 1 0\n");
+    }
+  }
   // Tile kernels: a bound on the resident CTAs per SM (.minnctapersm) makes ptxas fit the register
   // allocation granule instead of landing just above it. Whether a shader leaves room for that is only
   // known after inlining, so the bound is dropped when ptxas reports more than a few spilled words.
@@ -773,16 +791,38 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
     minCtas = which != K_VERTEX ? atoi(mc) : 0;
     forced = true;
   }
+  // ptxas keeps `.func` calls as calls. The shader entry point, and the helpers it calls (attribute fetch, texture
+  // unit), are therefore inlined into the kernel on the PTX text (ptx_inline.cpp), which is what lets ptxas
+  // schedule the shader's loads across the kernel's own arithmetic and allocate registers for the whole.
+  // VB200_JIT_NO_INLINE=1 keeps the calls (A/B measurements).
+  std::string inlinedEntry = scaffold.entries[which];
+  bool needBody = true, needHelpers = true;
+  if(!getenv("VB200_JIT_NO_INLINE"))
+  {
+    int serial = 0;
+    const char *fn = which == K_VERTEX ? "vb200_vs" : "vb200_fs";
+    vb200::ptx_inline_calls(inlinedEntry, body, fn, &serial);
+    needHelpers = false;
+    for(const char *helper : {"vb200_fetch_attr", "vb200_sample_cube", "vb200_sample_tex"})
+    {
+      vb200::ptx_inline_calls(inlinedEntry, scaffold.helpers, helper, &serial);
+      needHelpers |= vb200::ptx_has_call(inlinedEntry, helper);
+    }
+    needBody = vb200::ptx_has_call(inlinedEntry, fn);
+    needHelpers |= needBody;
+  }
   for(;;)
   {
     std::string text;
-    text.reserve(scaffold.prologue.size() + scaffold.helpers.size() + body.size() + scaffold.entries[which].size() +
+    text.reserve(scaffold.prologue.size() + scaffold.helpers.size() + body.size() + inlinedEntry.size() +
                  scaffold.epilogue.size() + 64);
     text += scaffold.prologue;
-    text += scaffold.helpers;
-    text += body;
+    if(needHelpers)
+      text += scaffold.helpers;
+    if(needBody)
+      text += body;
     text += "\n";
-    std::string entry = scaffold.entries[which];
+    std::string entry = inlinedEntry;
     const size_t at = entry.find(".maxntid ");
     const size_t eol = at == std::string::npos ? at : entry.find('\n', at);
     if(minCtas > 0 && eol != std::string::npos)
@@ -790,6 +830,16 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
     text += entry;
     text += scaffold.epilogue;
     unsigned spills = 0;
+    if(const char *prefix = getenv("VB200_DUMP_PTX"))
+    {
+      // developer aid: the module as ptxas gets it: <prefix>.<kernel>.ptx
+      const std::string path = std::string(prefix) + "." + kKernelNames[which] + ".ptx";
+      if(FILE *f = fopen(path.c_str(), "wb"))
+      {
+        fwrite(text.data(), 1, text.size(), f);
+        fclose(f);
+      }
+    }
     int rc = runPtxas(text, kKernelNames[which], cubin, &spills);
     if(rc)
       return rc;
