@@ -34,12 +34,6 @@
 #ifndef VB200_PB_UNROLL
 #define VB200_PB_UNROLL 1
 #endif
-#ifndef VB200_STAGE_INTERPS
-// resolve kernels: corners' interpolants of a one-round tile staged in shared memory (one gather per triangle
-// instead of one per pixel). Measured and left off: C2 -5 %, C3 +0.5 %, C5 +4 % (the 5 KB it adds per CTA come
-// out of the L1 the texture fetches live in; the kernel is bound by l1tex wavefronts either way).
-#define VB200_STAGE_INTERPS 0
-#endif
 
 extern "C" __device__ float4 vb200_vs(const Vb200Env *env, unsigned vid, float4 *interps_out);
 // The fragment entry point's result: the colour and, for shaders with OpKill (extended mode), whether the
@@ -676,12 +670,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   __shared__ uint2 s_run[RW][64];                    // per warp: the covered runs of the 64 rows of the current step
   __shared__ uint32_t s_wsum[RW];
   __shared__ uint32_t s_ticket;    // next unclaimed step of the row stream
-  // Interpolants of the staged records' corners, [corner][record slot], for pipelines with one interpolant slot:
-  // phase B then reads a winner's three float4 from shared memory instead of gathering them from L1/L2 once per
-  // PIXEL (the gather is done once per triangle, by the thread that sets the record up). The id queue of the
-  // fallback scan (overflowed tile list: several rounds, nothing staged) lives in the same bytes.
-  __shared__ int4 s_int[VB200_STAGE_INTERPS ? 3 * RT : RT / 2];
-  uint32_t *const s_ids = (uint32_t *)s_int;
+  __shared__ uint32_t s_ids[2 * RT];    // id queue of the fallback scan (overflowed tile list)
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
@@ -691,9 +680,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
   const uint32_t n = p.tile_count[tile];
   const bool clearColor = (p.clear_flags & 1u) != 0, clearDepth = (p.clear_flags & 2u) != 0;
   const Vb200RasterState &rs = p.rs;
-  // the tile's whole list fits one round: the records (and, with one slot, the interpolants) stay staged for phase B
+  // the tile's whole list fits one round: the records stay staged for phase B
   const bool recordsInSmem = rs.slot_keys && n <= (uint32_t)RT;
-  const bool stagedInterps = VB200_STAGE_INTERPS && recordsInSmem && rs.nslots == 1u;
   const uint32_t ty = __umulhi(tile, rs.tiles_x_magic), tx = tile - ty * rs.tiles_x;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   asm volatile("" : "+r"(lane), "+r"(warp));    // (kept in registers: ptxas otherwise re-reads %tid inside the loops)
@@ -803,13 +791,6 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       rb = __ldg((const int4 *)(p.rv + (uint32_t)rq.y));
       rc = __ldg((const int4 *)(p.rv + (uint32_t)rq.z));
     }
-    int4 ri0 = make_int4(0, 0, 0, 0), ri1 = ri0, ri2 = ri0;
-    if(stagedInterps && have)
-    {
-      ri0 = __ldg((const int4 *)(p.interps + (uint32_t)rq.x));
-      ri1 = __ldg((const int4 *)(p.interps + (uint32_t)rq.y));
-      ri2 = __ldg((const int4 *)(p.interps + (uint32_t)rq.z));
-    }
     if(base == 0u)
     {
 #if !VB200_UNORM_NEWTON
@@ -870,14 +851,6 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     s_z[threadIdx.x] = rz;
     s_pw[threadIdx.x] = rpw;
     s_sv[threadIdx.x] = rsv;
-#if VB200_STAGE_INTERPS
-    if(stagedInterps)
-    {
-      s_int[threadIdx.x] = ri0;
-      s_int[RT + threadIdx.x] = ri1;
-      s_int[2 * RT + threadIdx.x] = ri2;
-    }
-#endif
     s_key[threadIdx.x] = rs.slot_keys ? (((t + 1u) << 8) | threadIdx.x) : (t + 1u);
     __syncthreads();
     const uint32_t wsum = lane < RW ? s_wsum[lane] : 0u;
@@ -1155,19 +1128,6 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     invw0 = __int_as_float(c4.x); invw1 = __int_as_float(c4.y); invw2 = __int_as_float(c4.z);
     s0 = (uint32_t)c4.w;
   };
-#if VB200_STAGE_INTERPS
-  if(stagedInterps)
-    shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
-                   float &invw0, float &invw1, float &invw2, const float4 *&v0, const float4 *&v1, const float4 *&v2) {
-      const uint32_t slot = id & (RT - 1u);    // slot = the thread that set the winner up
-      uint32_t s0;
-      staged_record(slot * 16u, ly, b0, b1, b2, invarea, d0, d1, d2, invw0, invw1, invw2, s0);
-      v0 = (const float4 *)(s_int + slot);
-      v1 = (const float4 *)(s_int + RT + slot);
-      v2 = (const float4 *)(s_int + 2 * RT + slot);
-    });
-  else
-#endif
   if(recordsInSmem)
     shade_rows([&](uint32_t id, int ly, int &b0, int &b1, int &b2, float &invarea, float &d0, float &d1, float &d2,
                    float &invw0, float &invw1, float &invw2, const float4 *&v0, const float4 *&v1, const float4 *&v2) {

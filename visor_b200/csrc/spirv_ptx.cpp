@@ -1996,7 +1996,8 @@ struct Emitter
       fail("interpolant location %u exceeds the 10 slots of VertexCacheEntry", slot);
     info->in_slot_mask |= 1u << slot;
     std::vector<std::string> r = {R(), R(), R(), R()};
-    line("ld.v4.b32 {%s,%s,%s,%s}, [%s+%u];", r[0].c_str(), r[1].c_str(), r[2].c_str(), r[3].c_str(),
+    // the interpolants were written by the vertex kernel, an earlier launch: read-only here (LDG.CONSTANT)
+    line("ld.global.nc.v4.b32 {%s,%s,%s,%s}, [%s+%u];", r[0].c_str(), r[1].c_str(), r[2].c_str(), r[3].c_str(),
          vreg.c_str(), 16 * slot);
     return r;
   }
