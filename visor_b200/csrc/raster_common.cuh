@@ -243,6 +243,12 @@ __device__ __forceinline__ float vb200_unorm8(const float *lut, uint32_t b)
 #endif
 }
 
+__device__ __forceinline__ float4 vb200_unorm8x4(const float *lut, uint32_t u)
+{
+  return make_float4(vb200_unorm8(lut, u & 0xffu), vb200_unorm8(lut, (u >> 8) & 0xffu),
+                     vb200_unorm8(lut, (u >> 16) & 0xffu), vb200_unorm8(lut, u >> 24));
+}
+
 __device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t width, uint32_t bpp, uint32_t format,
                                               int x, int y, const float *lut)
 {
@@ -258,8 +264,7 @@ __device__ __forceinline__ float4 vb200_texel(const uint8_t *base, uint32_t widt
       u = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) |
           ((uint32_t)__ldg(p + 3) << 24);
   }
-  return make_float4(vb200_unorm8(lut, u & 0xffu), vb200_unorm8(lut, (u >> 8) & 0xffu),
-                     vb200_unorm8(lut, (u >> 16) & 0xffu), vb200_unorm8(lut, u >> 24));
+  return vb200_unorm8x4(lut, u);
 }
 
 // sample_tex_wrapped (texture_sampling.cpp:139-184): repeat wrap, bilinear, mip 0, no half-texel offset
@@ -280,10 +285,27 @@ __device__ __forceinline__ float4 vb200_sample_tex_impl(float u, float v, const 
     iv1 -= (int)height;
   const float fu = __fsub_rn(u, (float)iu0), fv = __fsub_rn(v, (float)iv0);
   const float inv_fu = __fsub_rn(1.0f, fu), inv_fv = __fsub_rn(1.0f, fv);
-  const float4 TL = vb200_texel(base, width, bpp, fmt, iu0, iv0, lut);
-  const float4 TR = vb200_texel(base, width, bpp, fmt, iu1, iv0, lut);
-  const float4 BL = vb200_texel(base, width, bpp, fmt, iu0, iv1, lut);
-  const float4 BR = vb200_texel(base, width, bpp, fmt, iu1, iv1, lut);
+  float4 TL, TR, BL, BR;
+  if(bpp == 4u && fmt != 135u && fmt != 137u && (((uintptr_t)base) & 3) == 0)
+  {
+    // the common case decided once per sample instead of once per texel: linear 4-byte texels at an aligned
+    // base. Texel indices fit 32 bits (images are at most 8192 x 8192), one 64-bit address per row.
+    const uint32_t *row0 = (const uint32_t *)base + (uint32_t)iv0 * width;
+    const uint32_t *row1 = (const uint32_t *)base + (uint32_t)iv1 * width;
+    const uint32_t tl = __ldg(row0 + (uint32_t)iu0), tr = __ldg(row0 + (uint32_t)iu1);
+    const uint32_t bl = __ldg(row1 + (uint32_t)iu0), br = __ldg(row1 + (uint32_t)iu1);
+    TL = vb200_unorm8x4(lut, tl);
+    TR = vb200_unorm8x4(lut, tr);
+    BL = vb200_unorm8x4(lut, bl);
+    BR = vb200_unorm8x4(lut, br);
+  }
+  else
+  {
+    TL = vb200_texel(base, width, bpp, fmt, iu0, iv0, lut);
+    TR = vb200_texel(base, width, bpp, fmt, iu1, iv0, lut);
+    BL = vb200_texel(base, width, bpp, fmt, iu0, iv1, lut);
+    BR = vb200_texel(base, width, bpp, fmt, iu1, iv1, lut);
+  }
   float4 top, bottom, out;
   top.x = __fadd_rn(__fmul_rn(TL.x, inv_fu), __fmul_rn(TR.x, fu));
   top.y = __fadd_rn(__fmul_rn(TL.y, inv_fu), __fmul_rn(TR.y, fu));
