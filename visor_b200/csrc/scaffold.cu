@@ -865,7 +865,12 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     }
     __syncthreads();
 
-    const uint32_t steps = (total + 31u) >> 5;
+    // Units per step: 32, one per lane — unless the whole stream is shorter than 32 units per warp (a few large
+    // triangles: one full step would leave all their pixels, up to 64 rows of 32, to a single warp). Then every
+    // warp takes its share of the units, the surplus lanes idle through the row walk, and the hit passes, which
+    // are where the time goes, spread over the CTA.
+    const uint32_t ups = min(32u, max(1u, (total + (uint32_t)RW - 1u) / (uint32_t)RW));
+    const uint32_t steps = ups == 32u ? (total + 31u) >> 5 : (total + ups - 1u) / ups;
     // VB200_TICKETS: steps handed out dynamically (a ticket counter in shared memory) instead of warp w taking
     // the w-th share of them. A step's cost depends on how many pixels its rows cover, so a fixed split lets
     // the warps arrive at the barrier behind the stream up to a step's worth of work apart.
@@ -884,7 +889,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
       for(uint32_t step = (steps * (uint32_t)warp) / RW; step < lastStep; step++)
       {
 #endif
-        const uint32_t k = step << 5;
+        const uint32_t k = step * ups;
         const uint32_t g = k + lane;
         // record that owns stream unit k: the last record whose start is <= k. Starts are strictly increasing
         // (every record has at least one unit) and entries past them hold `total` (> k), so it is (number
@@ -906,7 +911,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
         const uint32_t owner = min(owner0 + __popc(starts & (0xffffffffu >> (31 - lane))), (uint32_t)RT - 1u);
         // ---- 2. this lane's unit: rows 2u and 2u + 1 (if the bbox has it) of record `owner`, u = g - start
-        const bool valid = g < total;
+        const bool valid = (uint32_t)lane < ups && g < total;
         const uint32_t o16 = owner * 16u;
         const int4 c0 = vb200_lds128(aE1 + o16), c1 = vb200_lds128(aE2 + o16);
         const uint32_t unit = valid ? g - vb200_lds32(aStart + 4u * owner) : 0u;
