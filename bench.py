@@ -123,20 +123,20 @@ def nvlink_kib(index: int):
 # the per-launch figure of the same build and workload is recorded here; null when none was captured).
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_c{2,3,4,5}_kernels.txt (ncu --set full, per launch)"
 NCU_TRAFFIC = {
-    ("c2", 1, "vb200_k_tile_resolve_min_first"): 400640 + 0,
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 27101000 + 12592000,
-    ("c4", 1, "vb200_k_tile_ordered"): 34586000 + 311808,
-    ("c5", 1, "vb200_k_tile_resolve_min_first"): 148528000 + 209909000,
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): 404992 + 0,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 27099000 + 10306000,
+    ("c4", 1, "vb200_k_tile_ordered"): 34617000 + 495616,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 149199000 + 209558000,
 }
 
 
 # warp instructions one launch of the tile kernel executes (ncu smsp__inst_executed.sum, same captures): the
 # kernel is bound by instruction issue, not by HBM, so the bench also reports its issue-slot utilisation
 NCU_WARP_INSTRUCTIONS = {
-    ("c2", 1, "vb200_k_tile_resolve_min_first"): 10.30e6,
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 96.75e6,
-    ("c4", 1, "vb200_k_tile_ordered"): 305.96e6,
-    ("c5", 1, "vb200_k_tile_resolve_min_first"): 668.41e6,
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): 8.99e6,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 95.63e6,
+    ("c4", 1, "vb200_k_tile_ordered"): 252.11e6,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 545.73e6,
 }
 
 

@@ -15,7 +15,7 @@ MARKS = {
                 ("__device__ __forceinline__ void vb200_tile_resolve_body", "prologue, empty tiles"),
                 ("for(uint32_t base = 0; base < n; base += RT)", "round: list, record and corner gathers, tile init"),
                 ("const Vb200TriSetup su = vb200_unpack_setup(rq, ra, rb, rc);", "round: edge set-up, scan, staging"),
-                ("const uint32_t steps = (total + 31u) >> 5;", "step: owner lookup"),
+                ("const uint32_t ups = min(32u", "step: owner lookup"),
                 ("---- 2. this lane's unit", "step: unit set-up"),
                 ("const uint32_t wmax = __reduce_max_sync", "step: row walk"),
                 ("const uint32_t colmask =", "step: coverage -> runs"),

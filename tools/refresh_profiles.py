@@ -13,7 +13,8 @@ def last_json(path):
     return json.loads(lines[-1])
 
 for name, out in [("bench_c3", "bench_c3"), ("bench_reference_arm", "bench_reference_arm"), ("bench_c1", "bench_c1"),
-                  ("bench_c2", "bench_c2"), ("bench_c4", "bench_c4"), ("bench_c5", "bench_c5_n1")]:
+                  ("bench_c2", "bench_c2"), ("bench_c4", "bench_c4"), ("bench_c5", "bench_c5_n1"),
+                  ("bench_c6", "bench_c6_many_draws")]:
     p = os.path.join(src, name + ".json")
     if os.path.exists(p):
         json.dump(last_json(p), open(os.path.join(dst, f"{tag}_{out}.json"), "w"), indent=1)
@@ -61,4 +62,18 @@ hot_lines(os.path.join(src, "prof_c5.ncu-rep"), os.path.join(src, "c5.vb200_k_ti
           "resolve_min_first", os.path.join(dst, f"{tag}_ncu_c5_tile_resolve_hot_lines.txt"))
 hot_lines(os.path.join(src, "prof_c4.ncu-rep"), os.path.join(src, "c4.vb200_k_tile_ordered.cubin"),
           "tile_ordered", os.path.join(dst, f"{tag}_ncu_c4_tile_ordered_hot_lines.txt"))
+def regions(rep, cubin, kernel, which, out):
+    srccsv = rep.replace(".ncu-rep", "_source.csv")
+    if not (os.path.exists(srccsv) and os.path.exists(cubin)):
+        return
+    text = subprocess.run([sys.executable, os.path.join(here, "tools", "ncu_regions.py"), srccsv, cubin, kernel, which],
+                          capture_output=True, text=True).stdout
+    open(out, "w").write(text)
+
+regions(os.path.join(src, "prof_c3.ncu-rep"), os.path.join(src, "c3.vb200_k_tile_resolve_min_first.cubin"),
+        "resolve_min_first", "resolve", os.path.join(dst, f"{tag}_ncu_c3_tile_resolve_regions.txt"))
+regions(os.path.join(src, "prof_c5.ncu-rep"), os.path.join(src, "c5.vb200_k_tile_resolve_min_first.cubin"),
+        "resolve_min_first", "resolve", os.path.join(dst, f"{tag}_ncu_c5_tile_resolve_regions.txt"))
+regions(os.path.join(src, "prof_c4.ncu-rep"), os.path.join(src, "c4.vb200_k_tile_ordered.cubin"),
+        "tile_ordered", "ordered", os.path.join(dst, f"{tag}_ncu_c4_tile_ordered_regions.txt"))
 print("profiles/ refreshed:", sorted(os.listdir(dst)))

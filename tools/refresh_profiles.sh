@@ -12,7 +12,7 @@ if [ "${1:-}" != "notest" ]; then
 fi
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_c3.json 2> $O/bench_c3.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
-for w in c1 c2 c4 c5; do
+for w in c1 c2 c4 c5 c6; do
   timeout 900 python bench.py --workload $w --steps 20 --warmup 5 > $O/bench_$w.json 2> $O/bench_$w.err
 done
 for w in c3 c5; do
