@@ -484,6 +484,16 @@ def run_ours(args, workload: str) -> None:
         if c0 and c1:
             nvlink = {"tx_bytes_per_frame": (c1[0] - c0[0]) * 1024 // n_nv, "rx_bytes_per_frame": (c1[1] - c0[1]) * 1024 // n_nv,
                       "frames": n_nv, "rank": rank, "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX, all links of this rank's GPU"}
+        else:
+            # (this pool's boxes answer NVML_ERROR_NOT_SUPPORTED for the link counters.) The traffic of the fused
+            # exchange is fixed by construction: a rank stores each pixel of the tiles it owns once towards the
+            # switch, which replicates it; it receives every other rank's pixels.
+            tiles_x, tiles_y = (scene.width + 31) // 32, (scene.height + 31) // 32
+            own_px = sum(min(32, scene.width - 32 * (t % tiles_x)) * min(32, scene.height - 32 * (t // tiles_x))
+                         for t in range(rank, tiles_x * tiles_y, world)) if fused else 0
+            nvlink = {"tx_bytes_per_frame": own_px * 4 if multicast else own_px * 4 * (world - 1),
+                      "rx_bytes_per_frame": (npx - own_px) * 4, "rank": rank,
+                      "source": "computed from the tile ownership (NVML link counters not supported on this box)"}
 
     # ---------------- e2e: host buffers through the C-ABI, copies inside the timed region --------
     e2e_steps = max(3, min(args.steps, 10))
