@@ -112,6 +112,41 @@ def test_shaders_lower_to_ieee_ptx_and_link_for_sm100a(lib, name):
     lib.vb200_shader_destroy(m2)
 
 
+def test_shader_and_helpers_are_inlined_into_the_kernels(lib, tmp_path, monkeypatch):
+    """ptxas keeps `.func` calls as calls; ptx_inline.cpp inlines the shader entry point and the helpers it calls
+    (attribute fetch, texture unit) on the PTX text instead. The cubins of a textured pipeline must not contain a
+    call to, or a copy of, any of them — only the IEEE division / reciprocal slow paths remain functions."""
+    import shutil
+    import subprocess
+    if shutil.which("nvdisasm") is None:
+        pytest.skip("nvdisasm not on PATH")
+    monkeypatch.setenv("VB200_DUMP_CUBIN", str(tmp_path / "k"))
+    m1, ve = _entry(lib, shaders.vs_lit(True))
+    m2, fe = _entry(lib, shaders.fs_lit_tex())
+    sz = C.c_uint64()
+    assert lib.vb200_link_check(ve, fe, C.byref(sz)) == 0, lib.vb200_last_error()
+    cubins = sorted(tmp_path.glob("k.*.cubin"))
+    assert len(cubins) >= 7        # vertex, ordered, five resolve modes
+    for c in cubins:
+        sass = subprocess.run(["nvdisasm", str(c)], capture_output=True, text=True, check=True).stdout
+        funcs = re.findall(r"\.type\s+(\S+),@function", sass)
+        extra = [f for f in funcs if not f.startswith("vb200_k_") and "slowpath" not in f]
+        assert not extra, (c.name, extra)
+        calls = [l for l in sass.splitlines() if re.search(r"\bCALL\b", l) and "slowpath" not in l]
+        assert not calls, (c.name, calls[:3])
+    # ... and with the switch that keeps the calls (A/B measurements) the functions are back
+    monkeypatch.setenv("VB200_JIT_NO_INLINE", "1")
+    monkeypatch.setenv("VB200_DUMP_CUBIN", str(tmp_path / "n"))
+    m3, ve2 = _entry(lib, shaders.vs_lit(True))
+    m4, fe2 = _entry(lib, shaders.fs_lit_tex())
+    assert lib.vb200_link_check(ve2, fe2, C.byref(sz)) == 0, lib.vb200_last_error()
+    sass = subprocess.run(["nvdisasm", str(tmp_path / "n.vb200_k_tile_ordered.cubin")], capture_output=True, text=True,
+                          check=True).stdout
+    assert "vb200_fs" in sass and "vb200_sample_tex" in sass
+    for m in (m1, m2, m3, m4):
+        lib.vb200_shader_destroy(m)
+
+
 @pytest.mark.parametrize("op", shaders.UNIT_OPS + shaders.MEM_UNIT_OPS)
 def test_unit_op_shaders_compile(lib, op):
     mod, e = _entry(lib, shaders.vs_unit(op))
