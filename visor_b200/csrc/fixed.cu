@@ -126,17 +126,37 @@ __global__ void k_init_range(uint32_t *range, uint32_t lo, uint32_t hi)
 // append, so a tile that received more than list_cap triangles is recognisable afterwards and its tile
 // kernel CTA falls back to scanning the packed tile ranges (tri_tiles) — exact, no host involvement.
 // ------------------------------------------------------------------------------------------------
+// Tile ownership (sort-first): tile t belongs to rank t % world, and is the (t / world)-th tile of its owner.
+// kOwner: 0 = a single GPU (no test at all), 1 = world is a power of two (mask and shift), 2 = any world (the
+// integer division costs ~20 instructions per test; it used to be paid four times per triangle on one GPU too).
+template <int kOwner>
 __device__ __forceinline__ bool tile_owned(uint32_t tile, uint32_t rank, uint32_t world)
 {
-  return world <= 1u || (tile % world) == rank;
+  if(kOwner == 0)
+    return true;
+  if(kOwner == 1)
+    return (tile & (world - 1u)) == rank;
+  return (tile % world) == rank;
+}
+template <int kOwner>
+__device__ __forceinline__ uint32_t tile_slot(uint32_t tile, uint32_t world, uint32_t world_shift)
+{
+  if(kOwner == 0)
+    return tile;
+  if(kOwner == 1)
+    return tile >> world_shift;
+  return tile / world;
 }
 
 // Each thread sets up kSetupPerThread triangles, phase by phase, so that the index loads of all of them,
 // then the vertex gathers of all of them, then the returning cursor atomics of all of them are in flight
 // together (the kernel is a chain of three dependent memory operations per triangle and little else).
-template <int kSetupPerThread>
+// kTables: the batch holds several draws (per-triangle lookup of the draw and its vertex span); a single draw
+// compiles without that code — left in, predicated off, it was a sixth of the instructions the kernel issued.
+template <int kSetupPerThread, bool kTables, int kOwner>
 __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
 {
+  const uint32_t worldShift = kOwner == 1 ? (uint32_t)(__ffs((int)p.owner_world) - 1) : 0u;
   uint32_t t[kSetupPerThread], s0[kSetupPerThread], s1[kSetupPerThread], s2[kSetupPerThread];
   uint32_t tiles[kSetupPerThread];
   bool alive[kSetupPerThread];
@@ -166,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     if(alive[k])
     {
       Vb200BatchDraw d = p.draw0;
-      if(p.draws)
+      if(kTables)
       {
         uint32_t lo = 0, hi = p.num_draws;    // invariant: draws[lo].tri_base <= t < draws[hi].tri_base
         while(hi - lo > 1u)
@@ -246,7 +266,9 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     if(alive[k])
     {
       const int area2 = (vb[k].x - va[k].x) * (vc[k].y - va[k].y) - (vb[k].y - va[k].y) * (vc[k].x - va[k].x);
-      invarea[k] = __fdiv_rn(1.0f, (float)(area2 < 0 ? -area2 : area2));    // rasterizer.cpp:448
+      // 1.0f / float(|area2|) (rasterizer.cpp:448): the dedicated reciprocal returns the same bits as the general
+      // division (both are the correctly rounded quotient) in a shorter sequence
+      invarea[k] = __frcp_rn((float)(area2 < 0 ? -area2 : area2));
       const int flipped = (p.front_face == 1u) ? -area2 : area2;
       if(area2 == 0)
         alive[k] = false;
@@ -299,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
       if(nx[k] <= 2u && ny[k] <= 2u && qx < nx[k] && qy < ny[k])
       {
         tile[k] = (((tiles[k] >> 8) & 0xffu) + qy) * p.tiles_x + (tiles[k] & 0xffu) + qx;
-        if(!tile_owned(tile[k], p.owner_rank, p.owner_world))
+        if(!tile_owned<kOwner>(tile[k], p.owner_rank, p.owner_world))
           tile[k] = 0xffffffffu;
       }
       any |= tile[k] != 0xffffffffu;
@@ -323,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
         used[k] = true;
         mypairs++;
         if(pos[k] < p.list_cap)
-          p.list[(size_t)(tile[k] / p.owner_world) * p.list_cap + pos[k]] = t[k];
+          p.list[(size_t)tile_slot<kOwner>(tile[k], p.owner_world, worldShift) * p.list_cap + pos[k]] = t[k];
       }
     }
   }
@@ -356,12 +378,12 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
     for(uint32_t k = threadIdx.x; k < b_nt; k += kThreads)
     {
       const uint32_t tile = (b_ty0 + k / b_nx) * p.tiles_x + b_tx0 + k % b_nx;
-      if(tile_owned(tile, p.owner_rank, p.owner_world))
+      if(tile_owned<kOwner>(tile, p.owner_rank, p.owner_world))
       {
         const uint32_t pos = atomicAdd(&p.tile_count[tile], 1u);
         mypairs++;
         if(pos < p.list_cap)
-          p.list[(size_t)(tile / p.owner_world) * p.list_cap + pos] = b_tri;
+          p.list[(size_t)tile_slot<kOwner>(tile, p.owner_world, worldShift) * p.list_cap + pos] = b_tri;
       }
     }
   }
@@ -648,10 +670,18 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
   }();
   const uint32_t per_cta = kThreads * (uint32_t)perThread;
   const uint32_t grid = (p.num_tris + per_cta - 1) / per_cta;
-  if(perThread == 4)
-    k_setup<4><<<grid, kThreads, 0, s>>>(p);
-  else
-    k_setup<2><<<grid, kThreads, 0, s>>>(p);
+  const bool tables = p.draws != nullptr;
+  const int owner = p.owner_world <= 1u ? 0 : ((p.owner_world & (p.owner_world - 1u)) == 0u ? 1 : 2);
+#define VB200_SETUP_CASE(N, T, O)                       \
+  if(perThread == N && tables == T && owner == O)       \
+    k_setup<N, T, O><<<grid, kThreads, 0, s>>>(p);
+#define VB200_SETUP_CASES(N) \
+  VB200_SETUP_CASE(N, false, 0) VB200_SETUP_CASE(N, false, 1) VB200_SETUP_CASE(N, false, 2) \
+  VB200_SETUP_CASE(N, true, 0) VB200_SETUP_CASE(N, true, 1) VB200_SETUP_CASE(N, true, 2)
+  VB200_SETUP_CASES(2)
+  VB200_SETUP_CASES(4)
+#undef VB200_SETUP_CASES
+#undef VB200_SETUP_CASE
   return 1;
 }
 
