@@ -223,3 +223,27 @@ def test_no_cpu_fallback_without_a_device(lib):
     assert lib.vb200_present_wait(1) == -1
     assert lib.vb200_mem_register(host.ctypes.data, host.nbytes) == -1
     assert lib.vb200_mem_set_device_local(host.ctypes.data, 1) == -1
+
+
+def test_byte_over_255_in_two_operations_is_the_ieee_quotient():
+    """raster_common.cuh vb200_unorm8: fma(b, r, b*e) with r = RN(1/255), e = RN(1/255 - r) must be the correctly
+    rounded float32 quotient b/255 (what the reference's `float(byte) / 255.0f` yields) for every byte value.
+    Checked with exact rationals; the GPU side compares all 256 against the IEEE division in
+    test_unorm8_conversion_is_the_ieee_quotient."""
+    from fractions import Fraction
+
+    def rn32(x):    # Fraction -> nearest float32, ties to even
+        c = np.float32(float(x))
+        cands = [np.nextafter(c, np.float32(-np.inf)), c, np.nextafter(c, np.float32(np.inf))]
+        return min(cands, key=lambda v: (abs(Fraction(float(v)) - x), int(np.float32(v).view(np.uint32)) & 1))
+
+    src = open(os.path.join(os.path.dirname(HEADER), "..", "visor_b200", "csrc", "raster_common.cuh")).read()
+    r = re.search(r"const float r = ([0-9.eE+-]+)f;", src).group(1)
+    e = re.search(r"const float e = ([0-9.eE+-]+)f;", src).group(1)
+    R, E = Fraction(float(np.float32(r))), Fraction(float(np.float32(e)))
+    assert np.float32(r) == np.float32(1.0) / np.float32(255.0)
+    for b in range(256):
+        t = Fraction(float(rn32(b * E)))
+        got = rn32(b * R + t)
+        want = np.float32(b) / np.float32(255.0)
+        assert np.float32(got).view(np.uint32) == want.view(np.uint32), b

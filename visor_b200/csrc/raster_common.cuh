@@ -230,14 +230,16 @@ __device__ __forceinline__ uint32_t vb200_bc_texel(const uint8_t *blk, bool bc3,
 __device__ __forceinline__ float vb200_unorm8(const float *lut, uint32_t b)
 {
 #if VB200_UNORM_NEWTON
-  // float(b) / 255.0f without a division or a table: q = b * RN(1/255), then one Newton step on the remainder.
-  // The result is the correctly rounded quotient for every byte value (tests/test_gpu_parity.py
-  // test_unorm8_conversion_is_the_ieee_quotient compares all 256 with the IEEE division). A 256-entry table of
-  // the quotients in shared memory costs a 3-4 way bank conflict per lookup on random texels, sixteen lookups
-  // per bilinear sample: 47 M conflicts per C5 frame.
-  const float f = (float)b, r = 0.0039215688593685626983642578125f;    // RN(1/255) = 0x1.010102p-8
-  const float q = __fmul_rn(f, r);
-  return __fmaf_rn(__fmaf_rn(-q, 255.0f, f), r, q);
+  // float(b) / 255.0f without a division or a table. 1/255 = r + e with r = RN(1/255) and e = RN(1/255 - r):
+  // b*r is exact inside the fma and b*e is far below its last bit, so fma(b, r, b*e) is the correctly rounded
+  // quotient for every byte value (tests/test_gpu_parity.py test_unorm8_conversion_is_the_ieee_quotient compares
+  // all 256 with the IEEE division on the GPU, tests/test_abi.py checks the constants with exact rationals).
+  // Two operations per channel; a 256-entry table of the quotients in shared memory costs a 3-4 way bank
+  // conflict per lookup on random texels, sixteen lookups per bilinear sample: 47 M conflicts per C5 frame.
+  const float f = (float)b;
+  const float r = 0.0039215688593685626983642578125f;       // RN(1/255) = 0x1.010102p-8
+  const float e = -2.31917582360630104257e-10f;              // RN(1/255 - r) = -0x1.fdfdfep-33
+  return __fmaf_rn(f, r, __fmul_rn(f, e));
 #else
   return lut ? lut[b] : __fdiv_rn((float)b, 255.0f);
 #endif
