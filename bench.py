@@ -124,19 +124,19 @@ def nvlink_kib(index: int):
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_c{2,3,4,5}_kernels.txt (ncu --set full, per launch)"
 NCU_TRAFFIC = {
     ("c2", 1, "vb200_k_tile_resolve_min_first"): 404992 + 0,
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 27099000 + 10306000,
-    ("c4", 1, "vb200_k_tile_ordered"): 34617000 + 495616,
-    ("c5", 1, "vb200_k_tile_resolve_min_first"): 149199000 + 209558000,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 27098000 + 11232000,
+    ("c4", 1, "vb200_k_tile_ordered"): 34588000 + 209664,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 148692000 + 208273000,
 }
 
 
 # warp instructions one launch of the tile kernel executes (ncu smsp__inst_executed.sum, same captures): the
 # kernel is bound by instruction issue, not by HBM, so the bench also reports its issue-slot utilisation
 NCU_WARP_INSTRUCTIONS = {
-    ("c2", 1, "vb200_k_tile_resolve_min_first"): 8.99e6,
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 95.63e6,
-    ("c4", 1, "vb200_k_tile_ordered"): 252.11e6,
-    ("c5", 1, "vb200_k_tile_resolve_min_first"): 545.73e6,
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): 8.79e6,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 95.64e6,
+    ("c4", 1, "vb200_k_tile_ordered"): 249.20e6,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 530.86e6,
 }
 
 

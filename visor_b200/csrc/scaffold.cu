@@ -192,7 +192,7 @@ extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_co
   rv.y = vb200_cvtt(
       __fmul_rn(__fmul_rn(__fadd_rn(__fdiv_rn(__fmul_rn(pos.y, -1.0f), pos.w), 1.0f), 0.5f), (float)p.height));
   // per-vertex part of setup (rasterizer.cpp:449-452): invw = 1/w, depth = z * invw
-  rv.invw = __fdiv_rn(1.0f, pos.w);
+  rv.invw = __frcp_rn(pos.w);    // 1.0f / w, correctly rounded: the same bits as the general division
   rv.depth = __fmul_rn(pos.z, rv.invw);
   p.rv[i] = rv;
 }
@@ -321,7 +321,9 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
           n0 = __fmul_rn(n0, t.invw0);
           n1 = __fmul_rn(n1, t.invw1);
           n2 = __fmul_rn(n2, t.invw2);
-          const float invlen = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(n0, n1), n2));
+          // 1.0f / x, correctly rounded (the dedicated reciprocal: a shorter sequence than the general division,
+          // the same bits)
+          const float invlen = __frcp_rn(__fadd_rn(__fadd_rn(n0, n1), n2));
           n0 = __fmul_rn(n0, invlen);
           n1 = __fmul_rn(n1, invlen);
           n2 = __fmul_rn(n2, invlen);
