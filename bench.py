@@ -186,7 +186,20 @@ def scene_host_buffers(bound: scenes.BoundScene):
 
 
 # ------------------------------------------------------------------------------------------------
-def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps: int = 1, hash_depth: bool = True):
+def reference_native_shaders(on: bool) -> None:
+    """The reference JITs shaders to native code (LLVM 6, not buildable here). oracle/ref/ref_glue.cpp serves
+    spirv_compile.h with natively compiled C++ equivalents of the bench scenes' shaders (bit-identical to the
+    interpreter, tests/test_oracle_vs_ref.py) or, with 0, with the SPIR-V interpreter for everything."""
+    ref = abi.backend("vref", 0)
+    fn = ref.lib.vref_native_shaders
+    fn.argtypes = [C.c_int]
+    fn(1 if on else 0)
+    # entries are cached per backend and module: drop the reference's so that the setting takes effect
+    scenes._shader_cache.mods = {k: v for k, v in scenes._shader_cache.mods.items() if k[0] != "vref"}
+
+
+def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps: int = 1, hash_depth: bool = True,
+                   interpreted_frames: int = 0):
     """visor's own CPU rasterizer (oracle/_ref) on this box's host cores: threaded as shipped
     (7 workers + main, rasterizer.cpp:8) and serial (the deterministic parity mode)."""
     if not abi.available("vref"):
@@ -212,6 +225,18 @@ def time_reference(scene: scenes.Scene, steps: int, warmup: int, threaded_steps:
             ts.append(time.perf_counter() - t0)
     res["serial"] = {"s_per_frame": float(np.mean(ts)), "mtri_s": tris / float(np.mean(ts)) / 1e6, "threads": 1}
     res["hash"] = scenes.image_hash(b.color, b.depth if hash_depth else None)
+    if interpreted_frames > 0:
+        # the same frame with the shader stage interpreted (what round 1 reported as the CPU baseline)
+        reference_native_shaders(False)
+        bi = scenes.BoundScene(ref, scene)
+        ts = []
+        for _ in range(interpreted_frames):
+            t0 = time.perf_counter()
+            bi.run()
+            ts.append(time.perf_counter() - t0)
+        res["serial_interpreted"] = {"s_per_frame": min(ts), "mtri_s": tris / min(ts) / 1e6, "threads": 1}
+        res["interpreted_hash_equal"] = scenes.image_hash(bi.color, bi.depth if hash_depth else None) == res["hash"]
+        reference_native_shaders(True)
     return res
 
 
@@ -260,6 +285,12 @@ def run_reference_arm(args, workload: str) -> None:
     ts = vkdriver.frame_seconds(warm + steps)[warm:]
     t = float(np.mean(ts))
     modes["serial"] = {"s_per_frame": t, "mtri_s": tris / t / 1e6, "threads": 1, "frames": len(ts)}
+    # the same with the shader stage interpreted (round 1's baseline), one frame, for the record
+    reference_native_shaders(False)
+    vkdriver.run(vkdriver.ICD_REF, scene, frames=1, serial_reference=True)
+    ti = vkdriver.frame_seconds(1)[0]
+    reference_native_shaders(True)
+    interpreted = {"s_per_frame": ti, "mtri_s": tris / ti / 1e6, "threads": 1, "frames": 1}
     best = max(modes, key=lambda k: modes[k]["mtri_s"])
     # headline = the faster mode ("all the host threads it can use"); on the mesh scenes that is the serial one
     head = best
@@ -275,10 +306,11 @@ def run_reference_arm(args, workload: str) -> None:
         "reference_arm": {
             "timing": "host wall clock around vkQueueSubmit + vkQueueWaitIdle of the reference ICD "
                       "(cmd_exec.cpp:187-201 replaying the frame's command buffer)",
-            "shader_stage": "interpreted: the reference's LLVM-6 JIT (spirv_compile.cpp) cannot be built here, "
-                            "its spirv_compile.h interface is served by oracle/spirv_cpu.cpp (SURVEY.md measured "
-                            "~2.5x more Mtri/s for the same rasterizer with natively compiled shaders)",
-            "modes": modes, "fastest_mode": best},
+            "shader_stage": "native: the reference's LLVM-6 JIT (spirv_compile.cpp) cannot be built here; its "
+                            "spirv_compile.h interface is served by natively compiled C++ equivalents of this "
+                            "scene's shaders (oracle/ref/ref_glue.cpp, bit-identical to the SPIR-V interpreter "
+                            "oracle/spirv_cpu.cpp that serves every other module)",
+            "modes": modes, "fastest_mode": best, "serial_with_interpreted_shaders": interpreted},
         "cpu_baseline": {"value": v, "unit": "Mtri/s", "cores": modes[head]["threads"], "kind": "reference",
                          "sample": f"{modes[head]['frames']} full frames through the reference ICD, {head} mode; "
                                    f"serial (1 thread): {modes['serial']['frames']} frames, threaded as shipped "
@@ -712,13 +744,16 @@ def run_ours(args, workload: str) -> None:
     if not args.no_cpu_baseline:
         # N>1: serial mode only (a threaded 8K frame takes ~25 s); the colour image is what is compared
         r = time_reference(scene, 2 if not multi else 1, 0, threaded_steps=0 if multi else 1,
-                           hash_depth=not multi)
+                           hash_depth=not multi, interpreted_frames=0 if multi else 1)
         if r is not None:
             best = max((k for k in ("serial", "threaded") if k in r), key=lambda k: r[k]["mtri_s"])
             cpu = {"value": r[best]["mtri_s"], "unit": "Mtri/s", "cores": r[best]["threads"], "kind": "reference",
                    "sample": f"2 full frames of the same scene, best mode = {best}; serial "
                              f"{r['serial']['mtri_s']:.3f} Mtri/s (1 thread), threaded "
                              f"{r.get('threaded', {}).get('mtri_s', float('nan')):.3f} Mtri/s (8 threads as shipped)",
+                   "shader_stage": "native C++ equivalents of the scene's shaders (oracle/ref/ref_glue.cpp); with the "
+                                   "SPIR-V interpreter instead: "
+                                   f"{r.get('serial_interpreted', {}).get('mtri_s', float('nan')):.3f} Mtri/s",
                    "host_cpus": os.cpu_count()}
             parity = "bit-exact vs reference serial path" if r["hash"] == img_hash else "MISMATCH vs reference"
 

@@ -135,7 +135,176 @@ struct LLVMFunction
 {
   vor::Module *mod = NULL;
   std::map<std::string, std::pair<int, int>> bound;    // name -> (stage, slot)
+  int native = 0;                                      // NS_*: the module is one of the bench shaders
 };
+
+// ---------------------------------------------------------------------------------------------
+// 1b. natively compiled equivalents of the bench scenes' shaders
+//
+// The reference JITs a shader to x86 with LLVM; serving spirv_compile.h with an interpreter handicaps the
+// CPU baseline (SURVEY.md measured ~2.5x between the two on this rasterizer). For the seven shader modules
+// the BASELINE.json scenes use (recognised by a hash of their SPIR-V, native_shader_table.inc), GetFuncPointer
+// hands out a C++ function that performs exactly the interpreter's float operations in the interpreter's
+// order (this file is compiled with -ffp-contract=off, so the bits are the same: test_oracle_vs_ref.py renders
+// every config both ways). Any other module, or VREF_NATIVE_SHADERS=0 / vref_native_shaders(0), runs in the
+// interpreter as before.
+// ---------------------------------------------------------------------------------------------
+enum
+{
+  NS_NONE = 0,
+  NS_VS_PASSTHROUGH,
+  NS_FS_COLOR,
+  NS_VS_MVP_UV,
+  NS_FS_TEXTURE,
+  NS_VS_LIT,
+  NS_VS_LIT_UV,
+  NS_FS_LIT_TEX,
+};
+static const struct
+{
+  uint64_t hash;
+  uint32_t words;
+  int kind;
+} kNativeShaders[] = {
+#include "native_shader_table.inc"
+};
+static int g_nativeShaders = -1;    // -1: from the environment at first use
+static bool nativeShadersOn()
+{
+  if(g_nativeShaders < 0)
+  {
+    const char *e = getenv("VREF_NATIVE_SHADERS");
+    g_nativeShaders = (e && *e == '0') ? 0 : 1;
+  }
+  return g_nativeShaders != 0;
+}
+static int nativeKind(const uint32_t *code, size_t words)
+{
+  uint64_t h = 0xcbf29ce484222325ull;
+  const uint8_t *b = (const uint8_t *)code;
+  for(size_t i = 0; i < words * 4; i++)
+    h = (h ^ b[i]) * 0x100000001b3ull;
+  for(const auto &k : kNativeShaders)
+    if(k.hash == h && k.words == words)
+      return k.kind;
+  return NS_NONE;
+}
+
+// GetVertexAttributeData (spirv_compile.cpp:572-627) as the interpreter's wrapper calls it
+static inline void nsAttr(const GPUState &state, uint32_t vertexIndex, uint32_t attr, float out[4])
+{
+  refVertexAttr((void *)&state, vertexIndex, attr, out);
+}
+// Float4x4TimesFloat4 (spirv_compile.cpp:423-461): out[row] = (((0 + m[0][row] v0) + m[1][row] v1) + ...)
+static inline void nsMatVec(const float *m, const float *v, float *out)
+{
+  for(int row = 0; row < 4; row++)
+  {
+    float acc = 0.0f;
+    for(int col = 0; col < 4; col++)
+      acc += m[col * 4 + row] * v[col];
+    out[row] = acc;
+  }
+}
+// CreateDot(bary, (a, b, c, 0), 4) (spirv_compile.cpp:2196-2211)
+static inline float nsInterp(const float4 &bary, float a, float b, float c)
+{
+  return ((bary.v[0] * a + bary.v[1] * b) + bary.v[2] * c) + bary.v[3] * 0.0f;
+}
+
+static void nsVsPassthrough(const GPUState &state, uint32_t vertexIndex, VertexCacheEntry &out)
+{
+  float pos[4], col[4];
+  nsAttr(state, vertexIndex, 0, pos);
+  nsAttr(state, vertexIndex, 1, col);
+  float *o = (float *)&out;
+  memcpy(o, pos, 16);
+  memcpy(o + 4, col, 16);
+}
+static void nsVsMvpUv(const GPUState &state, uint32_t vertexIndex, VertexCacheEntry &out)
+{
+  float pos[4], uv[4], mvp[16], r[4];
+  nsAttr(state, vertexIndex, 0, pos);
+  nsAttr(state, vertexIndex, 1, uv);
+  memcpy(mvp, refBufferPtr((void *)&state, 0, 0), 64);
+  nsMatVec(mvp, pos, r);
+  float *o = (float *)&out;
+  memcpy(o, r, 16);
+  const float slot[4] = {uv[0], uv[1], uv[0], uv[0]};    // a vec2 output: components past it repeat the first
+  memcpy(o + 4, slot, 16);
+}
+template <bool kUv>
+static void nsVsLit(const GPUState &state, uint32_t vertexIndex, VertexCacheEntry &out)
+{
+  float p[4], n[4], uv[4];
+  nsAttr(state, vertexIndex, 0, p);
+  nsAttr(state, vertexIndex, 1, n);
+  const uint8_t *ubo = refBufferPtr((void *)&state, 0, 0);    // {mat4 mvp; vec4 light; vec4 albedo; vec4 ambient}
+  float mvp[16], light[4], albedo[4], ambient[4], r[4];
+  memcpy(mvp, ubo, 64);
+  memcpy(light, ubo + 64, 16);
+  memcpy(albedo, ubo + 80, 16);
+  memcpy(ambient, ubo + 96, 16);
+  const float p4[4] = {p[0], p[1], p[2], 1.0f};
+  nsMatVec(mvp, p4, r);
+  float ndl = n[0] * light[0];    // CreateDot over three components
+  ndl = ndl + n[1] * light[1];
+  ndl = ndl + n[2] * light[2];
+  ndl = (ndl > 0.0f) ? ndl : 0.0f;    // FMax: select(ogt(a, b), a, b)
+  float col[4];
+  for(int i = 0; i < 4; i++)
+  {
+    const float lit = albedo[i] * ndl;
+    col[i] = lit + ambient[i];
+  }
+  float *o = (float *)&out;
+  memcpy(o, r, 16);
+  memcpy(o + 4, col, 16);
+  if(kUv)
+  {
+    nsAttr(state, vertexIndex, 2, uv);
+    const float slot[4] = {uv[0], uv[1], uv[0], uv[0]};
+    memcpy(o + 8, slot, 16);
+  }
+}
+static void nsFsColor(const GPUState &, float, const float4 &bary, const VertexCacheEntry tri[3], float4 &out)
+{
+  const float *a = (const float *)&tri[0] + 4, *b = (const float *)&tri[1] + 4, *c = (const float *)&tri[2] + 4;
+  for(int i = 0; i < 4; i++)
+    out.v[i] = nsInterp(bary, a[i], b[i], c[i]);
+}
+static void nsFsTexture(const GPUState &state, float, const float4 &bary, const VertexCacheEntry tri[3], float4 &out)
+{
+  const float *a = (const float *)&tri[0] + 4, *b = (const float *)&tri[1] + 4, *c = (const float *)&tri[2] + 4;
+  const float u = nsInterp(bary, a[0], b[0], c[0]), v = nsInterp(bary, a[1], b[1], c[1]);
+  sample_tex_wrapped(u, v, (VkImage)refImage((void *)&state, 0, 1), 0, out);
+}
+static void nsFsLitTex(const GPUState &state, float, const float4 &bary, const VertexCacheEntry tri[3], float4 &out)
+{
+  const float *a = (const float *)&tri[0] + 4, *b = (const float *)&tri[1] + 4, *c = (const float *)&tri[2] + 4;
+  float col[4];
+  for(int i = 0; i < 4; i++)
+    col[i] = nsInterp(bary, a[i], b[i], c[i]);
+  const float u = nsInterp(bary, a[4], b[4], c[4]), v = nsInterp(bary, a[5], b[5], c[5]);
+  float4 t;
+  sample_tex_wrapped(u, v, (VkImage)refImage((void *)&state, 0, 1), 0, t);
+  for(int i = 0; i < 4; i++)
+    out.v[i] = t.v[i] * col[i];
+}
+static Shader nativeShader(int kind)
+{
+  switch(kind)
+  {
+    case NS_VS_PASSTHROUGH: return (Shader)(VertexShader)&nsVsPassthrough;
+    case NS_VS_MVP_UV: return (Shader)(VertexShader)&nsVsMvpUv;
+    case NS_VS_LIT: return (Shader)(VertexShader)&nsVsLit<false>;
+    case NS_VS_LIT_UV: return (Shader)(VertexShader)&nsVsLit<true>;
+    case NS_FS_COLOR: return (Shader)(FragmentShader)&nsFsColor;
+    case NS_FS_TEXTURE: return (Shader)(FragmentShader)&nsFsTexture;
+    case NS_FS_LIT_TEX: return (Shader)(FragmentShader)&nsFsLitTex;
+    default: return NULL;
+  }
+}
 
 void InitLLVM()
 {
@@ -161,6 +330,7 @@ LLVMFunction *CompileFunction(const uint32_t *pCode, size_t codeSize)
   }
   LLVMFunction *f = new LLVMFunction;
   f->mod = m;
+  f->native = nativeShadersOn() ? nativeKind(pCode, codeSize) : NS_NONE;
   return f;
 }
 
@@ -169,6 +339,8 @@ Shader GetFuncPointer(LLVMFunction *func, const char *name)
   const vor::Entry *e = vor::find_entry(func->mod, name);
   if(!e)
     return NULL;
+  if(func->native != NS_NONE && !strcmp(name, "main"))
+    return nativeShader(func->native);
   auto it = func->bound.find(name);
   int stage = vor::entry_stage(e);
   int slot = -1;
@@ -431,4 +603,12 @@ VREF_API int vref_flush(void)
 VREF_API int vref_threads(void)
 {
   return g_threaded ? 8 : 1;
+}
+// 1: modules of the bench shaders compiled from now on run as native code, 0: in the interpreter (section 1b);
+// returns the previous setting
+VREF_API int vref_native_shaders(int on)
+{
+  const int before = nativeShadersOn() ? 1 : 0;
+  g_nativeShaders = on ? 1 : 0;
+  return before;
 }

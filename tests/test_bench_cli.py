@@ -36,8 +36,10 @@ def test_reference_arm_prints_one_json_line():
     # same config keys as the product arm prints (bench.py: workload_config), --steps/--warmup honoured as given
     assert set(d["config"]) == {"workload", "triangles", "resolution", "l2", "parallelism", "raster_path"}
     assert d["steps"] == 2 and d["warmup"] == 1
-    assert "vkQueueSubmit" in d["reference_arm"]["timing"] and "interpreted" in d["reference_arm"]["shader_stage"]
+    # the shader stage runs as native code (the reference JITs it); the interpreted figure is reported next to it
+    assert "vkQueueSubmit" in d["reference_arm"]["timing"] and d["reference_arm"]["shader_stage"].startswith("native")
     assert d["reference_arm"]["modes"]["serial"]["frames"] == 2
+    assert d["reference_arm"]["serial_with_interpreted_shaders"]["mtri_s"] > 0
 
 
 @pytest.mark.skipif(not abi.available("vref"), reason="oracle/_ref/libvisor_ref.so not built")

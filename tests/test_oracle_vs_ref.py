@@ -134,3 +134,46 @@ def test_threaded_reference_is_not_the_oracle():
         pytest.skip("reference build missing")
     ref = abi.backend("vref", 0)
     assert ref.fn("threads")() == 1
+
+
+def test_native_shader_table_is_current():
+    """oracle/ref/native_shader_table.inc (hashes of the bench shaders' SPIR-V, which ref_glue.cpp binds to
+    natively compiled C++ instead of the interpreter) must match what harness/shaders.py generates today;
+    regenerate with `python oracle/ref/gen_native_shader_table.py` and rebuild oracle/_ref."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen", os.path.join(here, "oracle", "ref", "gen_native_shader_table.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    assert open(os.path.join(here, "oracle", "ref", "native_shader_table.inc")).read() == gen.table()
+
+
+@pytest.mark.parametrize("builder", [
+    lambda: scenes.c1_triangle(333, 211),
+    lambda: scenes.c2_cube(640, 360, frame=7),
+    lambda: scenes.c3_mesh(640, 360, 160, 80),
+    lambda: scenes.c4_particles(640, 360, 8000),
+    lambda: scenes.c5_textured(640, 360, 160, 80, tex_size=128),
+])
+def test_native_bench_shaders_equal_the_interpreter(vref, builder):
+    """The reference arm runs the bench scenes' shaders as native code (the reference JITs them with LLVM; an
+    interpreted shader stage would handicap the CPU baseline ~3x): every config must come out bit for bit as
+    with the interpreter behind spirv_compile.h."""
+    import ctypes as C
+    fn = vref.lib.vref_native_shaders
+    fn.argtypes = [C.c_int]
+    out = []
+    before = fn(1)
+    try:
+        for mode in (0, 1):
+            fn(mode)
+            # (entries are cached per backend and module: drop vref's so that the mode takes effect)
+            scenes._shader_cache.mods = {k: v for k, v in scenes._shader_cache.mods.items() if k[0] != "vref"}
+            out.append(scenes.render(vref, builder()))
+    finally:
+        fn(before)
+        scenes._shader_cache.mods = {k: v for k, v in scenes._shader_cache.mods.items() if k[0] != "vref"}
+    (c0, d0), (c1, d1) = out
+    assert np.array_equal(c0, c1)
+    assert (d0 is None and d1 is None) or np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
