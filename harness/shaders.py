@@ -414,7 +414,8 @@ MEM_UNIT_OPS = ("dynidx",)
 EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "floor", "fract",
                 "roundeven", "trunc", "ceil", "fsign", "radians", "degrees", "step", "smoothstep", "fma",
                 "distance3", "faceforward3", "refract3", "int_minmax", "uint_minmax", "int_abs_sign", "phi_loop",
-                "phi_swap")
+                "phi_swap", "int_divmod", "uint_divmod", "shifts_bits", "ucvt", "int_cmp", "logic", "isnan_inf",
+                "switch_phi")
 
 
 def vs_unit(op: str) -> np.ndarray:
@@ -624,6 +625,83 @@ def vs_unit(op: str) -> np.ndarray:
         m.stmt(Op.Branch, head)
         m.label(merge)
         r = m.inst(Op.FMul, v4, m.inst(Op.FAdd, v4, acc_phi, oth_phi), m.const_fvec(0.25, 0.25, 0.25, 0.25))
+    elif op in ("int_divmod", "uint_divmod", "shifts_bits", "int_cmp"):
+        sv4 = m.t_vec(m.t_int(1), 4)
+        uv4 = m.t_vec(m.t_int(0), 4)
+        bv4 = m.t_vec(m.t_bool(), 4)
+
+        def ints(x, scale, bias):    # (int)(x * scale) - bias: negative values and zeros included
+            k = m.inst(Op.ConvertFToS, sv4, m.inst(Op.FMul, v4, x, m.const_fvec(scale, scale, scale, scale)))
+            return m.inst(Op.ISub, sv4, k, m.inst(Op.ConvertFToS, sv4, m.const_fvec(bias, bias, bias, bias)))
+        ia_, ib_ = ints(a, 4000.0, 900.0), ints(b, 9.0, 3.0)    # divisors in -3..6, zero and -1 among them
+        if op == "int_divmod":
+            x = m.inst(Op.IAdd, sv4, m.inst(Op.SDiv, sv4, ia_, ib_),
+                       m.inst(Op.IAdd, sv4, m.inst(Op.IMul, sv4, m.inst(Op.SRem, sv4, ia_, ib_), m.inst(Op.ConvertFToS, sv4, m.const_fvec(7.0, 7.0, 7.0, 7.0))),
+                              m.inst(Op.IMul, sv4, m.inst(Op.SMod, sv4, ia_, ib_), m.inst(Op.ConvertFToS, sv4, m.const_fvec(31.0, 31.0, 31.0, 31.0)))))
+        elif op == "uint_divmod":
+            ua, ub = m.inst(Op.Bitcast, uv4, ia_), m.inst(Op.Bitcast, uv4, m.inst(Op.BitwiseAnd, sv4, ib_, m.inst(Op.ConvertFToS, sv4, m.const_fvec(7.0, 7.0, 7.0, 7.0))))
+            x = m.inst(Op.Bitcast, sv4, m.inst(Op.IAdd, uv4, m.inst(Op.UDiv, uv4, ua, ub), m.inst(Op.UMod, uv4, ua, ub)))
+        elif op == "shifts_bits":
+            sh = m.inst(Op.BitwiseAnd, sv4, ib_, m.inst(Op.ConvertFToS, sv4, m.const_fvec(63.0, 63.0, 63.0, 63.0)))
+            t1 = m.inst(Op.ShiftRightArithmetic, sv4, ia_, sh)
+            t2 = m.inst(Op.Bitcast, sv4, m.inst(Op.ShiftRightLogical, uv4, m.inst(Op.Bitcast, uv4, ia_), m.inst(Op.Bitcast, uv4, sh)))
+            t3 = m.inst(Op.BitwiseXor, sv4, m.inst(Op.BitwiseOr, sv4, t1, ib_), m.inst(Op.Not, sv4, t2))
+            x = m.inst(Op.IAdd, sv4, t3, m.inst(Op.SNegate, sv4, ia_))
+        else:
+            ua, ub = m.inst(Op.Bitcast, uv4, ia_), m.inst(Op.Bitcast, uv4, ib_)
+            one = m.inst(Op.ConvertFToS, sv4, m.const_fvec(1.0, 1.0, 1.0, 1.0))
+            zero = m.inst(Op.ConvertFToS, sv4, m.const_fvec(0.0, 0.0, 0.0, 0.0))
+            x = zero
+            for k, (cmp, l, rr) in enumerate(((Op.INotEqual, ia_, ib_), (Op.UGreaterThan, ua, ub), (Op.SGreaterThan, ia_, ib_),
+                                              (Op.UGreaterThanEqual, ua, ub), (Op.SGreaterThanEqual, ia_, ib_),
+                                              (Op.ULessThan, ua, ub), (Op.ULessThanEqual, ua, ub), (Op.SLessThanEqual, ia_, ib_))):
+                bit = m.inst(Op.Select, sv4, m.inst(cmp, bv4, l, rr), one, zero)
+                wgt = m.inst(Op.ConvertFToS, sv4, m.const_fvec(*([float(1 << k)] * 4)))
+                x = m.inst(Op.IAdd, sv4, x, m.inst(Op.IMul, sv4, bit, wgt))
+        x = m.inst(Op.BitwiseAnd, sv4, x, m.inst(Op.ConvertFToS, sv4, m.const_fvec(255.0, 255.0, 255.0, 255.0)))
+        r = m.inst(Op.FMul, v4, m.inst(Op.ConvertSToF, v4, x), m.const_fvec(1 / 256.0, 1 / 256.0, 1 / 256.0, 1 / 256.0))
+    elif op == "ucvt":
+        uv4 = m.t_vec(m.t_int(0), 4)
+        # a * 3e9 - 1e9: below zero, inside and above the uint range; back to float and scaled into [0, 1)
+        x = m.inst(Op.FSub, v4, m.inst(Op.FMul, v4, a, m.const_fvec(3e9, 3e9, 3e9, 6e9)), m.const_fvec(1e9, 1e9, 1e9, 1e9))
+        u = m.inst(Op.ConvertFToU, uv4, x)
+        r = m.inst(Op.FMul, v4, m.inst(Op.ConvertUToF, v4, u), m.const_fvec(2.0 ** -32, 2.0 ** -32, 2.0 ** -32, 2.0 ** -32))
+    elif op == "logic":
+        bv4 = m.t_vec(m.t_bool(), 4)
+        p_ = m.inst(Op.FOrdLessThan, bv4, a, b)
+        q_ = m.inst(Op.FOrdLessThan, bv4, b, c)
+        t = m.inst(Op.LogicalOr, bv4, m.inst(Op.LogicalAnd, bv4, p_, q_), m.inst(Op.LogicalNot, bv4, m.inst(Op.LogicalEqual, bv4, p_, q_)))
+        t = m.inst(Op.LogicalNotEqual, bv4, t, m.inst(Op.FOrdLessThan, bv4, a, c))
+        r = m.inst(Op.Select, v4, t, a, b)
+    elif op == "isnan_inf":
+        bv4 = m.t_vec(m.t_bool(), 4)
+        zero = m.inst(Op.FSub, v4, a, a)
+        nan = m.inst(Op.FDiv, v4, zero, zero)
+        inf = m.inst(Op.FDiv, v4, b, zero)
+        mixed = m.shuffle(v4, nan, inf, 0, 5, 2, 7)    # (nan, inf, nan, inf)
+        probe = m.shuffle(v4, mixed, a, 0, 1, 6, 7)    # (nan, inf, a.z, a.w)
+        r = m.inst(Op.Select, v4, m.inst(Op.IsNan, bv4, probe), a,
+                   m.inst(Op.Select, v4, m.inst(Op.IsInf, bv4, probe), b, c))
+    elif op == "switch_phi":
+        # switch(int(a.x * 5)) { case 0: r = a; break; case 2: r = b; break; case 3: r = a + b; break; default: r = c; }
+        # with the merge written as OpPhi, as a compiler's output has it
+        it = m.t_int(1)
+        sel = m.inst(Op.ConvertFToS, it, m.inst(Op.FMul, fl, ax, m.const_f(5.0)))
+        c0, c2, c3, dflt, merge = (m.new_id() for _ in range(5))
+        m.stmt(Op.SelectionMerge, merge, 0)
+        m.stmt(Op.Switch, sel, dflt, 0, c0, 2, c2, 3, c3)
+        m.label(c0)
+        m.stmt(Op.Branch, merge)
+        m.label(c2)
+        m.stmt(Op.Branch, merge)
+        m.label(c3)
+        s3 = m.inst(Op.FAdd, v4, a, b)
+        m.stmt(Op.Branch, merge)
+        m.label(dflt)
+        m.stmt(Op.Branch, merge)
+        m.label(merge)
+        r = m.new_id()
+        m.raw(Op.Phi, v4, r, a, c0, b, c2, s3, c3, c, dflt)
     elif op == "fabs":
         r = m.ext(v4, GLSL.FAbs, a)
     elif op == "floor":

@@ -55,8 +55,37 @@ class Op:
     CompositeExtract = 81
     Transpose = 84
     ImageSampleImplicitLod = 87
+    ConvertFToU = 109
     ConvertFToS = 110
     ConvertSToF = 111
+    ConvertUToF = 112
+    SNegate = 126
+    UDiv = 134
+    SDiv = 135
+    UMod = 137
+    SRem = 138
+    SMod = 139
+    IsNan = 156
+    IsInf = 157
+    LogicalEqual = 164
+    LogicalNotEqual = 165
+    LogicalOr = 166
+    LogicalAnd = 167
+    LogicalNot = 168
+    INotEqual = 171
+    UGreaterThan = 172
+    SGreaterThan = 173
+    UGreaterThanEqual = 174
+    SGreaterThanEqual = 175
+    ULessThan = 176
+    ULessThanEqual = 178
+    SLessThanEqual = 179
+    ShiftRightLogical = 194
+    ShiftRightArithmetic = 195
+    BitwiseOr = 197
+    BitwiseXor = 198
+    Not = 200
+    Switch = 251
     Bitcast = 124
     FNegate = 127
     IAdd = 128

@@ -52,6 +52,12 @@ enum Op : uint16_t
   // outside the reference's subset: accepted only in extended mode
   OpConvertFToS = 110, OpBitcast = 124, OpISub = 130, OpSelect = 169, OpFOrdEqual = 180,
   OpFOrdNotEqual = 182, OpFOrdGreaterThanEqual = 190, OpPhi = 245, OpKill = 252,
+  OpConvertFToU = 109, OpConvertUToF = 112, OpSNegate = 126, OpUDiv = 134, OpSDiv = 135, OpUMod = 137, OpSRem = 138,
+  OpSMod = 139, OpIsNan = 156, OpIsInf = 157, OpLogicalEqual = 164, OpLogicalNotEqual = 165, OpLogicalOr = 166,
+  OpLogicalAnd = 167, OpLogicalNot = 168, OpINotEqual = 171, OpUGreaterThan = 172, OpSGreaterThan = 173,
+  OpUGreaterThanEqual = 174, OpSGreaterThanEqual = 175, OpULessThan = 176, OpULessThanEqual = 178,
+  OpSLessThanEqual = 179, OpShiftRightLogical = 194, OpShiftRightArithmetic = 195, OpBitwiseOr = 197,
+  OpBitwiseXor = 198, OpNot = 200, OpSwitch = 251,
   OpIAdd = 128, OpFAdd = 129, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136,
   OpVectorTimesScalar = 142, OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144,
   OpMatrixTimesVector = 145, OpMatrixTimesMatrix = 146, OpDot = 148, OpIEqual = 170,
@@ -603,11 +609,18 @@ static void parse(Module &m)
               break;
             case OpConvertFToS: case OpBitcast: case OpISub: case OpSelect: case OpFOrdEqual:
             case OpFOrdNotEqual: case OpFOrdGreaterThanEqual: case OpPhi:
+            case OpConvertFToU: case OpConvertUToF: case OpSNegate: case OpUDiv: case OpSDiv: case OpUMod: case OpSRem:
+            case OpSMod: case OpIsNan: case OpIsInf: case OpLogicalEqual: case OpLogicalNotEqual: case OpLogicalOr:
+            case OpLogicalAnd: case OpLogicalNot: case OpINotEqual: case OpUGreaterThan: case OpSGreaterThan:
+            case OpUGreaterThanEqual: case OpSGreaterThanEqual: case OpULessThan: case OpULessThanEqual:
+            case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
+            case OpBitwiseXor: case OpNot:
               if(!g_extended)
                 FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
               m.valtype[chk(pCode[2])] = chk(pCode[1]);
               cur->insts.push_back(pCode);
               break;
+            case OpSwitch:
             case OpKill:
               if(!g_extended)
                 FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
@@ -924,6 +937,116 @@ struct Interp
             V[w[2]].i[c] = (f >= -2147483648.0f && f < 2147483648.0f) ? (int32_t)f : INT32_MIN;
           }
           break;
+        // integers, logic, conversions (extended mode): explicit results where SPIR-V leaves them open —
+        // x / 0 = 0, x % 0 = 0, INT_MIN / -1 = INT_MIN, INT_MIN % -1 = 0, shift counts modulo 32, float -> uint
+        // outside [0, 2^32) = 0 — the same as the PTX back end emits
+#define VOR_CMP(OP, FIELD, EXPR)                                  \
+  case OP:                                                        \
+    for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)              \
+    {                                                             \
+      const auto a = V[w[3]].FIELD[c], b = V[w[4]].FIELD[c];      \
+      V[w[2]].u[c] = (EXPR) ? 1u : 0u;                            \
+    }                                                             \
+    break;
+        VOR_CMP(OpINotEqual, u, a != b)
+        VOR_CMP(OpUGreaterThan, u, a > b)
+        VOR_CMP(OpSGreaterThan, i, a > b)
+        VOR_CMP(OpUGreaterThanEqual, u, a >= b)
+        VOR_CMP(OpSGreaterThanEqual, i, a >= b)
+        VOR_CMP(OpULessThan, u, a < b)
+        VOR_CMP(OpULessThanEqual, u, a <= b)
+        VOR_CMP(OpSLessThanEqual, i, a <= b)
+        VOR_CMP(OpLogicalEqual, u, (a & 1u) == (b & 1u))
+        VOR_CMP(OpLogicalNotEqual, u, (a & 1u) != (b & 1u))
+        VOR_CMP(OpLogicalOr, u, ((a | b) & 1u) != 0u)
+        VOR_CMP(OpLogicalAnd, u, ((a & b) & 1u) != 0u)
+#undef VOR_CMP
+        case OpLogicalNot:
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
+            V[w[2]].u[c] = (V[w[3]].u[c] & 1u) ^ 1u;
+          break;
+        case OpIsNan:
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].f[c] != V[w[3]].f[c];
+          break;
+        case OpIsInf:
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
+            V[w[2]].u[c] = (V[w[3]].u[c] & 0x7fffffffu) == 0x7f800000u;
+          break;
+        case OpSNegate:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = 0u - V[w[3]].u[c];
+          break;
+        case OpNot:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = ~V[w[3]].u[c];
+          break;
+        case OpBitwiseOr:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].u[c] | V[w[4]].u[c];
+          break;
+        case OpBitwiseXor:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].u[c] ^ V[w[4]].u[c];
+          break;
+        case OpShiftRightLogical:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = V[w[3]].u[c] >> (V[w[4]].u[c] & 31);
+          break;
+        case OpShiftRightArithmetic:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].i[c] = V[w[3]].i[c] >> (V[w[4]].u[c] & 31);
+          break;
+        case OpUDiv:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = V[w[4]].u[c] ? V[w[3]].u[c] / V[w[4]].u[c] : 0u;
+          break;
+        case OpUMod:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = V[w[4]].u[c] ? V[w[3]].u[c] % V[w[4]].u[c] : 0u;
+          break;
+        case OpSDiv:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            const int32_t a = V[w[3]].i[c], b = V[w[4]].i[c];
+            V[w[2]].i[c] = b == 0 ? 0 : (b == -1 ? (int32_t)(0u - (uint32_t)a) : a / b);
+          }
+          break;
+        case OpSRem:
+        case OpSMod:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            const int32_t a = V[w[3]].i[c], b = V[w[4]].i[c];
+            int32_t r = (b == 0 || b == -1) ? 0 : a % b;
+            if(op == OpSMod && r != 0 && ((r ^ b) < 0))
+              r = (int32_t)((uint32_t)r + (uint32_t)b);
+            V[w[2]].i[c] = r;
+          }
+          break;
+        case OpConvertUToF:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].f[c] = (float)V[w[3]].u[c];
+          break;
+        case OpConvertFToU:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            const float f = V[w[3]].f[c];
+            V[w[2]].u[c] = (f > -1.0f && f < 4294967296.0f) ? (uint32_t)(f < 0.0f ? 0.0f : f) : 0u;
+          }
+          break;
+        case OpSwitch:
+        {
+          const uint32_t sel = V[w[1]].u[0];
+          uint32_t target = w[2];
+          for(uint16_t i = 3; i + 1 < wc; i += 2)
+            if(w[i] == sel)
+            {
+              target = w[i + 1];
+              break;
+            }
+          pc = fn.labels.at(target);
+          break;
+        }
         // ---- flow control (:1232-1279)
         case OpBranch: pc = fn.labels.at(w[1]); break;
         case OpBranchConditional: pc = fn.labels.at((V[w[1]].u[0] & 1) ? w[2] : w[3]); break;
@@ -1397,6 +1520,14 @@ static void validateExt(const Module &m)
       {
         if(!kv.second.labels.count(w[2]) || !kv.second.labels.count(w[3]))
           FAIL("branch to unknown label");
+      }
+      else if(op == OpSwitch)
+      {
+        if(wc < 3 || ((wc - 3) & 1) || !kv.second.labels.count(w[2]))
+          FAIL("malformed OpSwitch");
+        for(uint16_t i = 3; i + 1 < wc; i += 2)
+          if(!kv.second.labels.count(w[i + 1]))
+            FAIL("branch to unknown label");
       }
     }
 }

@@ -271,6 +271,49 @@ def _expected_ext(op, a, b, c):
             lo, hi = np.minimum(ia, ib), np.maximum(ia, ib)
             x = lo + hi + np.minimum(np.maximum(ic, lo), hi)
         return ((x & 255).astype(f32) * f32(1 / 256.0)).astype(f32)
+    if op in ("int_divmod", "uint_divmod", "shifts_bits", "int_cmp"):
+        def ints(x, scale, bias):
+            return np.trunc((x * f32(scale)).astype(f32)).astype(np.int64) - bias
+        ia, ib = ints(a, 4000.0, 900), ints(b, 9.0, 3)
+
+        def wrap(v):    # int64 -> two's complement int32
+            return ((v + 2 ** 31) % 2 ** 32) - 2 ** 31
+
+        def tdiv(x, y):    # C division truncating toward zero
+            return np.where(y == 0, 0, np.sign(x) * np.sign(np.where(y == 0, 1, y)) * (np.abs(x) // np.abs(np.where(y == 0, 1, y))))
+        if op == "int_divmod":
+            q = np.where(ib == 0, 0, np.where(ib == -1, wrap(-ia), tdiv(ia, ib)))
+            rem = np.where((ib == 0) | (ib == -1), 0, ia - tdiv(ia, ib) * ib)
+            mod = np.where((rem != 0) & ((rem ^ ib) < 0), rem + ib, rem)
+            x = wrap(q + wrap(rem * 7) + wrap(mod * 31))
+        elif op == "uint_divmod":
+            ua, ub = ia & 0xffffffff, (ib & 7) & 0xffffffff
+            x = np.where(ub == 0, 0, ua // np.where(ub == 0, 1, ub)) + np.where(ub == 0, 0, ua % np.where(ub == 0, 1, ub))
+        elif op == "shifts_bits":
+            sh = (ib & 63) & 31
+            t1 = ia >> sh
+            t2 = wrap((ia & 0xffffffff) >> sh)
+            t3 = (t1 | ib) ^ wrap(~t2)
+            x = wrap(t3 + wrap(-ia))
+        else:
+            ua, ub = ia & 0xffffffff, ib & 0xffffffff
+            bits = [ia != ib, ua > ub, ia > ib, ua >= ub, ia >= ib, ua < ub, ua <= ub, ia <= ib]
+            x = sum(bt.astype(np.int64) << k for k, bt in enumerate(bits))
+        return ((x & 255).astype(f32) * f32(1 / 256.0)).astype(f32)
+    if op == "ucvt":
+        x = ((a * np.array([3e9, 3e9, 3e9, 6e9], f32)).astype(f32) - f32(1e9)).astype(f32)
+        u = np.where((x > -1) & (x < 4294967296.0), np.trunc(np.maximum(x, 0)), 0).astype(np.uint32)
+        return (u.astype(f32) * f32(2.0 ** -32)).astype(f32)
+    if op == "logic":
+        p_, q_ = a < b, b < c
+        t = (p_ & q_) | ~(p_ == q_)
+        t = t != (a < c)
+        return np.where(t, a, b)
+    if op == "isnan_inf":
+        return np.array([a[0], b[1], c[2], c[3]], f32)
+    if op == "switch_phi":
+        sel = int(np.trunc(f32(a[0] * f32(5.0))))
+        return {0: a, 2: b, 3: (a + b).astype(f32)}.get(sel, c)
     if op in ("phi_loop", "phi_swap"):
         n = 3 + (int(np.trunc(f32(a[0] * f32(8.0)))) & 3)
         acc, oth = a.copy(), b.copy()

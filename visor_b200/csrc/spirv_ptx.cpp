@@ -49,6 +49,12 @@ enum : uint32_t
   // outside the reference's subset: accepted only in extended mode
   OpConvertFToS = 110, OpBitcast = 124, OpISub = 130, OpSelect = 169, OpFOrdEqual = 180, OpFOrdNotEqual = 182,
   OpFOrdGreaterThanEqual = 190, OpPhi = 245, OpKill = 252,
+  OpConvertFToU = 109, OpConvertUToF = 112, OpSNegate = 126, OpUDiv = 134, OpSDiv = 135, OpUMod = 137, OpSRem = 138,
+  OpSMod = 139, OpIsNan = 156, OpIsInf = 157, OpLogicalEqual = 164, OpLogicalNotEqual = 165, OpLogicalOr = 166,
+  OpLogicalAnd = 167, OpLogicalNot = 168, OpINotEqual = 171, OpUGreaterThan = 172, OpSGreaterThan = 173,
+  OpUGreaterThanEqual = 174, OpSGreaterThanEqual = 175, OpULessThan = 176, OpULessThanEqual = 178,
+  OpSLessThanEqual = 179, OpShiftRightLogical = 194, OpShiftRightArithmetic = 195, OpBitwiseOr = 197,
+  OpBitwiseXor = 198, OpNot = 200, OpSwitch = 251,
 };
 enum : uint32_t
 {
@@ -470,10 +476,17 @@ struct Module
               break;
             case OpConvertFToS: case OpBitcast: case OpISub: case OpSelect: case OpFOrdEqual: case OpFOrdNotEqual:
             case OpFOrdGreaterThanEqual: case OpPhi:
+            case OpConvertFToU: case OpConvertUToF: case OpSNegate: case OpUDiv: case OpSDiv: case OpUMod: case OpSRem:
+            case OpSMod: case OpIsNan: case OpIsInf: case OpLogicalEqual: case OpLogicalNotEqual: case OpLogicalOr:
+            case OpLogicalAnd: case OpLogicalNot: case OpINotEqual: case OpUGreaterThan: case OpSGreaterThan:
+            case OpUGreaterThanEqual: case OpSGreaterThanEqual: case OpULessThan: case OpULessThanEqual:
+            case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
+            case OpBitwiseXor: case OpNot:
               if(!g_extendedSpirv)
                 fail("Unhandled SPIR-V opcode %u", op);    // :1888
               valtype[id(p[2])] = id(p[1]);
               break;
+            case OpSwitch:
             case OpKill:
               if(!g_extendedSpirv)
                 fail("Unhandled SPIR-V opcode %u", op);    // :1888
@@ -1277,6 +1290,216 @@ struct Emitter
           line("setp.lt.f32 %s, %s, 0f4F000000;", p.c_str(), ab.c_str());    // |x| < 2^31 (false for NaN)
           line("selp.b32 %s, %s, 0x80000000, %s;", d.c_str(), t.c_str(), p.c_str());
           v.r.push_back(d);
+        }
+        break;
+      }
+      // ---- extended mode, integers, logic and conversions: explicit results where SPIR-V (or the two
+      // machines) leave them open — x / 0 = 0, x % 0 = 0, INT_MIN / -1 = INT_MIN, INT_MIN % -1 = 0, shift counts
+      // taken modulo 32, float -> uint outside [0, 2^32) = 0 — the same in the CPU interpreter
+      case OpINotEqual: case OpUGreaterThan: case OpSGreaterThan: case OpUGreaterThanEqual: case OpSGreaterThanEqual:
+      case OpULessThan: case OpULessThanEqual: case OpSLessThanEqual:
+      {
+        const char *ins = op == OpINotEqual           ? "setp.ne.s32"
+                          : op == OpUGreaterThan      ? "setp.gt.u32"
+                          : op == OpSGreaterThan      ? "setp.gt.s32"
+                          : op == OpUGreaterThanEqual ? "setp.ge.u32"
+                          : op == OpSGreaterThanEqual ? "setp.ge.s32"
+                          : op == OpULessThan         ? "setp.lt.u32"
+                          : op == OpULessThanEqual    ? "setp.le.u32"
+                                                      : "setp.le.s32";
+        std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
+        if(a.size() != b.size())
+          fail("comparison operand shapes differ");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          std::string p = P();
+          line("%s %s, %s, %s;", ins, p.c_str(), a[i].c_str(), b[i].c_str());
+          v.r.push_back(p);
+        }
+        break;
+      }
+      case OpLogicalEqual: case OpLogicalNotEqual: case OpLogicalOr: case OpLogicalAnd:
+      {
+        std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
+        if(a.size() != b.size())
+          fail("logical operand shapes differ");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          std::string p = P();
+          if(op == OpLogicalEqual)
+          {
+            line("xor.pred %s, %s, %s;", p.c_str(), a[i].c_str(), b[i].c_str());
+            line("not.pred %s, %s;", p.c_str(), p.c_str());
+          }
+          else
+            line("%s %s, %s, %s;", op == OpLogicalNotEqual ? "xor.pred" : op == OpLogicalOr ? "or.pred" : "and.pred",
+                 p.c_str(), a[i].c_str(), b[i].c_str());
+          v.r.push_back(p);
+        }
+        break;
+      }
+      case OpLogicalNot:
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &x : a)
+        {
+          std::string p = P();
+          line("not.pred %s, %s;", p.c_str(), x.c_str());
+          v.r.push_back(p);
+        }
+        break;
+      }
+      case OpIsNan: case OpIsInf:
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &x : a)
+        {
+          std::string p = P();
+          if(op == OpIsNan)
+            line("setp.nan.f32 %s, %s, %s;", p.c_str(), x.c_str(), x.c_str());
+          else
+          {
+            std::string ab = R();
+            line("abs.f32 %s, %s;", ab.c_str(), x.c_str());
+            line("setp.eq.f32 %s, %s, 0f7F800000;", p.c_str(), ab.c_str());
+          }
+          v.r.push_back(p);
+        }
+        break;
+      }
+      case OpSNegate: case OpNot:
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &x : a)
+        {
+          std::string d = R();
+          line("%s %s, %s;", op == OpSNegate ? "neg.s32" : "not.b32", d.c_str(), x.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case OpBitwiseOr: case OpBitwiseXor: case OpShiftRightLogical: case OpShiftRightArithmetic:
+      {
+        std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
+        if(a.size() != b.size())
+          fail("integer operand shapes differ");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          if(op == OpBitwiseOr || op == OpBitwiseXor)
+            v.r.push_back(f2(op == OpBitwiseOr ? "or.b32" : "xor.b32", a[i], b[i]));
+          else
+            v.r.push_back(f2(op == OpShiftRightLogical ? "shr.u32" : "shr.s32", a[i], f2("and.b32", b[i], "31")));
+        }
+        break;
+      }
+      case OpUDiv: case OpSDiv: case OpUMod: case OpSRem: case OpSMod:
+      {
+        std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
+        if(a.size() != b.size())
+          fail("integer operand shapes differ");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          const bool sgn = op == OpSDiv || op == OpSRem || op == OpSMod;
+          const bool isDiv = op == OpUDiv || op == OpSDiv;
+          std::string pz = P(), bb = R(), q = R(), r0 = R();
+          line("setp.eq.s32 %s, %s, 0;", pz.c_str(), b[i].c_str());
+          std::string pm;
+          if(sgn)
+          {
+            // the divisor the machine sees is never 0 or -1
+            pm = P();
+            std::string pb = P();
+            line("setp.eq.s32 %s, %s, -1;", pm.c_str(), b[i].c_str());
+            line("or.pred %s, %s, %s;", pb.c_str(), pz.c_str(), pm.c_str());
+            line("selp.b32 %s, 1, %s, %s;", bb.c_str(), b[i].c_str(), pb.c_str());
+          }
+          else
+            line("selp.b32 %s, 1, %s, %s;", bb.c_str(), b[i].c_str(), pz.c_str());
+          line("%s.%s %s, %s, %s;", isDiv ? "div" : "rem", sgn ? "s32" : "u32", q.c_str(), a[i].c_str(), bb.c_str());
+          if(sgn)
+          {
+            // divisor -1: quotient = 0 - a (wraps for INT_MIN), remainder = 0
+            std::string alt = R(), q1 = R();
+            if(isDiv)
+              line("neg.s32 %s, %s;", alt.c_str(), a[i].c_str());
+            else
+              line("mov.b32 %s, 0;", alt.c_str());
+            line("selp.b32 %s, %s, %s, %s;", q1.c_str(), alt.c_str(), q.c_str(), pm.c_str());
+            q = q1;
+          }
+          line("selp.b32 %s, 0, %s, %s;", r0.c_str(), q.c_str(), pz.c_str());
+          if(op == OpSMod)
+          {
+            // the sign of the divisor: r != 0 and r, b of different signs -> r + b
+            std::string x = R(), pn = P(), pnz = P(), pa = P(), rb = R(), r1 = R();
+            line("xor.b32 %s, %s, %s;", x.c_str(), r0.c_str(), b[i].c_str());
+            line("setp.lt.s32 %s, %s, 0;", pn.c_str(), x.c_str());
+            line("setp.ne.s32 %s, %s, 0;", pnz.c_str(), r0.c_str());
+            line("and.pred %s, %s, %s;", pa.c_str(), pn.c_str(), pnz.c_str());
+            line("add.s32 %s, %s, %s;", rb.c_str(), r0.c_str(), b[i].c_str());
+            line("selp.b32 %s, %s, %s, %s;", r1.c_str(), rb.c_str(), r0.c_str(), pa.c_str());
+            r0 = r1;
+          }
+          v.r.push_back(r0);
+        }
+        break;
+      }
+      case OpConvertUToF:
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &x : a)
+        {
+          std::string d = R();
+          line("cvt.rn.f32.u32 %s, %s;", d.c_str(), x.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case OpConvertFToU:    // toward zero inside [0, 2^32); everything else (negative, too large, NaN) gives 0
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &x : a)
+        {
+          std::string t = R(), p = P(), d = R();
+          line("cvt.rzi.u32.f32 %s, %s;", t.c_str(), x.c_str());    // saturates: negative and NaN -> 0
+          line("setp.lt.f32 %s, %s, 0f4F800000;", p.c_str(), x.c_str());    // x < 2^32 (false for NaN)
+          line("selp.b32 %s, %s, 0, %s;", d.c_str(), t.c_str(), p.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case OpSwitch:    // selector, default label, (literal, label)*: a chain of compares; edges with phis get blocks
+      {
+        const std::string &sel = regs(w[1], 1)[0];
+        std::vector<std::pair<std::string, uint32_t>> edges;    // (edge label, target) of the edges that copy phis
+        auto target = [&](uint32_t lbl) {
+          if(!edgeHasPhis(fr, lbl))
+            return label(fr.inl, lbl);
+          std::string e = "$LE" + std::to_string(nEdge++);
+          edges.push_back({e, lbl});
+          return e;
+        };
+        for(uint32_t i = 3; i + 1 < wc; i += 2)
+        {
+          std::string p = P();
+          line("setp.eq.s32 %s, %s, %d;", p.c_str(), sel.c_str(), (int)w[i]);
+          line("@%s bra %s;", p.c_str(), target(w[i + 1]).c_str());
+        }
+        line("bra %s;", target(w[2]).c_str());
+        for(auto &e : edges)
+        {
+          out += e.first + ":\n";
+          emitEdge(fr, e.second);
+          line("bra %s;", label(fr.inl, e.second).c_str());
         }
         break;
       }
