@@ -543,7 +543,13 @@ def run_ours(args, workload: str) -> None:
         h2d_job = sum(a.nbytes for a in inputs)
         shm_name = f"vb200_bench_{os.environ.get('MASTER_PORT', '0')}"
         if rank == 0:
-            shm = shared_memory.SharedMemory(name=shm_name, create=True, size=npx * 4)
+            try:
+                shm = shared_memory.SharedMemory(name=shm_name, create=True, size=npx * 4)
+            except FileExistsError:    # left behind by a run that was killed: take it over
+                stale = shared_memory.SharedMemory(name=shm_name)
+                stale.close()
+                stale.unlink()
+                shm = shared_memory.SharedMemory(name=shm_name, create=True, size=npx * 4)
         dist.barrier()
         if rank != 0:
             shm = shared_memory.SharedMemory(name=shm_name)
