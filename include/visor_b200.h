@@ -311,10 +311,12 @@ VB200_API const char *vb200_last_tile_kernel(void);
  * draws with 2^24 or more triangles; "tile_list_cap": entries per tile list, 0 = automatic — a tiny value
  * forces the tile kernels' fallback for overflowed lists; "mgpu_mirrors": see vb200_mgpu_init).
  * "extended_spirv": 1 makes later vb200_shader_create calls
- * accept a few opcodes the reference asserts on (OpSelect, OpFOrdGreaterThanEqual, OpFOrdEqual,
- * OpFOrdNotEqual, OpISub, OpBitcast, OpConvertFToS, GLSL FAbs/Floor/Fract) — off by default, because
- * with it the front end no longer rejects exactly what CompileFunction rejects (spirv_compile.cpp:1734,
- * 1888). Unknown names return VB200_ERR_INVALID. */
+ * accept opcodes the reference asserts on: OpPhi, OpSwitch, OpKill (discard; such fragment shaders always run
+ * on the in-order tile kernel), OpSelect, the remaining float and integer comparisons, integer division /
+ * remainder / shifts / bit and logic operations, OpBitcast, OpConvertFToS/FToU/UToF, OpIsNan/OpIsInf and 23
+ * GLSL.std.450 instructions (DESIGN.md section 3 lists them and the results fixed where SPIR-V leaves them
+ * open) — off by default, because with it the front end no longer rejects exactly what CompileFunction
+ * rejects (spirv_compile.cpp:1734,1888). Unknown names return VB200_ERR_INVALID. */
 VB200_API int vb200_set_option(const char *name, int64_t value);
 
 #ifdef __cplusplus
