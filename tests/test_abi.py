@@ -247,3 +247,31 @@ def test_byte_over_255_in_two_operations_is_the_ieee_quotient():
         got = rn32(b * R + t)
         want = np.float32(b) / np.float32(255.0)
         assert np.float32(got).view(np.uint32) == want.view(np.uint32), b
+
+
+def test_tile_kernels_keep_their_occupancy(lib, tmp_path, monkeypatch):
+    """The tile kernels are tuned to a number of resident CTAs per SM: the resolve kernels to 8 (64 registers x 128
+    threads, <= 27 KB of shared memory each), the ordered kernel to 5 (48 registers x 256 threads). A change that
+    silently costs a register or a few KB halves nothing visibly but loses 10-20 % on the GPU; pin it where no GPU
+    is needed (C3's and C5's shaders, cuobjdump -res-usage of the JIT cubins)."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    for tag, vs, fs in (("c3", shaders.vs_lit(False), shaders.fs_color()), ("c5", shaders.vs_lit(True), shaders.fs_lit_tex())):
+        monkeypatch.setenv("VB200_DUMP_CUBIN", str(tmp_path / tag))
+        m1, ve = _entry(lib, vs)
+        m2, fe = _entry(lib, fs)
+        sz = C.c_uint64()
+        assert lib.vb200_link_check(ve, fe, C.byref(sz)) == 0, lib.vb200_last_error()
+        for kernel, max_regs, max_smem in (("vb200_k_tile_resolve_min_first", 64, 27 * 1024),
+                                           ("vb200_k_tile_resolve_last_wins", 64, 32 * 1024),
+                                           ("vb200_k_tile_ordered", 64 if tag == "c5" else 48, 40 * 1024),
+                                           ("vb200_k_vertex", 40, 0)):
+            out = subprocess.run(["cuobjdump", "-res-usage", str(tmp_path / f"{tag}.{kernel}.cubin")], capture_output=True,
+                                 text=True, check=True).stdout
+            regs = int(re.search(r"REG:(\d+)", out).group(1))
+            smem = int(re.search(r"SHARED:(\d+)", out).group(1))
+            assert regs <= max_regs, (tag, kernel, regs)
+            assert smem <= max_smem, (tag, kernel, smem)
+        lib.vb200_shader_destroy(m1)
+        lib.vb200_shader_destroy(m2)
