@@ -11,6 +11,7 @@
 //   K5' stand-alone sampler       sample_tex_wrapped/_cube_wrapped texture_sampling.cpp:139-250
 //   K6  tile pack / unpack        (sort-first multi-GPU; no reference equivalent)
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 #include "kernels.h"
 #include "raster_common.cuh"
@@ -126,6 +127,38 @@ __global__ void k_init_range(uint32_t *range, uint32_t lo, uint32_t hi)
 // append, so a tile that received more than list_cap triangles is recognisable afterwards and its tile
 // kernel CTA falls back to scanning the packed tile ranges (tri_tiles) — exact, no host involvement.
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel of the frame's chain (vertex -> setup -> [sort] -> tiles) lets its
+// successor be scheduled early (vb200_pdl_trigger when it starts) and waits for its predecessor's results before it
+// touches them (vb200_pdl_wait; a no-op when the kernel was launched in plain stream order).
+__device__ __forceinline__ void vb200_pdl_trigger()
+{
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+__device__ __forceinline__ void vb200_pdl_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static void launch_dependent(void (*kernel)(KArgs...), uint32_t grid, cudaStream_t s, Args... args)
+{
+  static const bool pdl = getenv("VB200_NO_PDL") == nullptr;
+  if(!pdl)
+  {
+    kernel<<<grid, kThreads, 0, s>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = s;
+  cudaLaunchAttribute attr = {};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Tile ownership (sort-first): tile t belongs to rank t % world, and is the (t / world)-th tile of its owner.
 // kOwner: 0 = a single GPU (no test at all), 1 = world is a power of two (mask and shift), 2 = any world (the
 // integer division costs ~20 instructions per test; it used to be paid four times per triangle on one GPU too).
@@ -157,6 +190,8 @@ template <int kSetupPerThread, bool kTables, int kOwner>
 __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
 {
   const uint32_t worldShift = kOwner == 1 ? (uint32_t)(__ffs((int)p.owner_world) - 1) : 0u;
+  vb200_pdl_trigger();
+  vb200_pdl_wait();    // the vertex kernel's raster records and zeroed tile counters
   uint32_t t[kSetupPerThread], s0[kSetupPerThread], s1[kSetupPerThread], s2[kSetupPerThread];
   uint32_t tiles[kSetupPerThread];
   bool alive[kSetupPerThread];
@@ -454,6 +489,8 @@ __global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_
                                                   uint32_t rank, uint32_t world, uint32_t ntiles)
 {
   __shared__ __align__(16) uint32_t s[kSortSmem];
+  vb200_pdl_trigger();
+  vb200_pdl_wait();    // the setup kernel's lists
   const uint32_t tile = blockIdx.x * world + rank;    // the grid holds the tiles this rank owns
   if(tile >= ntiles)
     return;
@@ -674,7 +711,7 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
   const int owner = p.owner_world <= 1u ? 0 : ((p.owner_world & (p.owner_world - 1u)) == 0u ? 1 : 2);
 #define VB200_SETUP_CASE(N, T, O)                       \
   if(perThread == N && tables == T && owner == O)       \
-    k_setup<N, T, O><<<grid, kThreads, 0, s>>>(p);
+    launch_dependent(k_setup<N, T, O>, grid, s, p);
 #define VB200_SETUP_CASES(N) \
   VB200_SETUP_CASE(N, false, 0) VB200_SETUP_CASE(N, false, 1) VB200_SETUP_CASE(N, false, 2) \
   VB200_SETUP_CASE(N, true, 0) VB200_SETUP_CASE(N, true, 1) VB200_SETUP_CASE(N, true, 2)
@@ -688,7 +725,7 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
 int launch_sort(uint32_t *list, const uint32_t *tile_count, uint32_t list_cap, uint32_t rank, uint32_t world,
                 uint32_t ntiles, cudaStream_t s)
 {
-  k_sort<<<(ntiles + world - 1) / world, kThreads, 0, s>>>(list, tile_count, list_cap, rank, world, ntiles);
+  launch_dependent(k_sort, (ntiles + world - 1) / world, s, list, tile_count, list_cap, rank, world, ntiles);
   return 1;
 }
 

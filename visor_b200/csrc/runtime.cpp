@@ -1009,9 +1009,29 @@ int fillResources(const vb200_draw_state *s, const vb200::ShaderEntry &e, Vb200E
   return VB200_OK;
 }
 
-int launchKernel(cudaKernel_t k, dim3 grid, dim3 block, void **args)
+// `dependent`: the kernel begins with griddepcontrol.wait and only consumes what the kernel launched right before
+// it produced (setup after vertex, tiles after setup/sort): it is launched with programmatic stream
+// serialization, so that its CTAs are scheduled while the predecessor's last wave drains instead of after a
+// launch gap (the predecessor executes griddepcontrol.launch_dependents when it starts). VB200_NO_PDL=1: plain
+// stream order (A/B measurements).
+int launchKernel(cudaKernel_t k, dim3 grid, dim3 block, void **args, bool dependent = false)
 {
-  CU(cudaLaunchKernel((const void *)k, grid, block, args, 0, g.stream));
+  static const bool pdl = getenv("VB200_NO_PDL") == nullptr;
+  if(dependent && pdl)
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = g.stream;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelExC(&cfg, (const void *)k, args));
+  }
+  else
+    CU(cudaLaunchKernel((const void *)k, grid, block, args, 0, g.stream));
   g.stats.kernel_launches++;
   return VB200_OK;
 }
@@ -1344,7 +1364,7 @@ int runBatch(size_t first, size_t last, bool foldClears)
   phaseMark(3);
   {
     void *args[] = {&env, &tp};
-    if((rc = launchKernel(b.kTile, dim3(ownedTiles), dim3(b.tileThreads), args)))
+    if((rc = launchKernel(b.kTile, dim3(ownedTiles), dim3(b.tileThreads), args, true)))
       return rc;
   }
   phaseMark(4);

@@ -153,6 +153,7 @@ extern "C" __device__ float4 vb200_sample_cube(float x, float y, float z, const 
 extern "C" __global__ void __launch_bounds__(128) vb200_k_vertex(const __grid_constant__ Vb200Env env,
                                                                const Vb200VertexParams p)
 {
+  asm volatile("griddepcontrol.launch_dependents;");    // the setup kernel may be scheduled as this grid drains
   for(uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < p.tile_count_n; j += gridDim.x * blockDim.x)
     p.tile_count[j] = 0u;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,6 +243,8 @@ extern "C" __global__ void __launch_bounds__(256) vb200_k_tile_ordered(const __g
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
+  // (launched with programmatic stream serialization behind the setup / sort kernel: wait for its lists)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tile = blockIdx.x * p.rs.owner_world + p.rs.owner_rank;
   if(tile >= p.rs.tiles_x * p.rs.tiles_y)
     return;
@@ -676,6 +679,8 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
 
   // sort-first: the grid holds only the tiles this rank owns (tile % world == rank); the others are
   // cleared, drawn and published by their owners
+  // (launched with programmatic stream serialization behind the setup kernel: wait for its lists)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tile = blockIdx.x * p.rs.owner_world + p.rs.owner_rank;
   if(tile >= p.rs.tiles_x * p.rs.tiles_y)
     return;
