@@ -141,7 +141,7 @@ __device__ __forceinline__ void vb200_pdl_wait()
 template <typename... KArgs, typename... Args>
 static void launch_dependent(void (*kernel)(KArgs...), uint32_t grid, cudaStream_t s, Args... args)
 {
-  static const bool pdl = getenv("VB200_NO_PDL") == nullptr;
+  static bool pdl = getenv("VB200_NO_PDL") == nullptr;
   if(!pdl)
   {
     kernel<<<grid, kThreads, 0, s>>>(args...);
@@ -156,7 +156,14 @@ static void launch_dependent(void (*kernel)(KArgs...), uint32_t grid, cudaStream
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if(e == cudaErrorNotSupported || e == cudaErrorInvalidValue)
+  {
+    // an environment without programmatic launches: plain stream order from now on
+    cudaGetLastError();
+    pdl = false;
+    kernel<<<grid, kThreads, 0, s>>>(args...);
+  }
 }
 
 // Tile ownership (sort-first): tile t belongs to rank t % world, and is the (t / world)-th tile of its owner.

@@ -1016,7 +1016,7 @@ int fillResources(const vb200_draw_state *s, const vb200::ShaderEntry &e, Vb200E
 // stream order (A/B measurements).
 int launchKernel(cudaKernel_t k, dim3 grid, dim3 block, void **args, bool dependent = false)
 {
-  static const bool pdl = getenv("VB200_NO_PDL") == nullptr;
+  static bool pdl = getenv("VB200_NO_PDL") == nullptr;
   if(dependent && pdl)
   {
     cudaLaunchConfig_t cfg = {};
@@ -1028,7 +1028,16 @@ int launchKernel(cudaKernel_t k, dim3 grid, dim3 block, void **args, bool depend
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    CU(cudaLaunchKernelExC(&cfg, (const void *)k, args));
+    const cudaError_t e = cudaLaunchKernelExC(&cfg, (const void *)k, args);
+    if(e == cudaErrorNotSupported || e == cudaErrorInvalidValue)
+    {
+      // an environment without programmatic launches (some virtualised or instrumented set-ups): plain order
+      cudaGetLastError();
+      pdl = false;
+      CU(cudaLaunchKernel((const void *)k, grid, block, args, 0, g.stream));
+    }
+    else
+      CU(e);
   }
   else
     CU(cudaLaunchKernel((const void *)k, grid, block, args, 0, g.stream));
