@@ -198,7 +198,6 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
 {
   const uint32_t worldShift = kOwner == 1 ? (uint32_t)(__ffs((int)p.owner_world) - 1) : 0u;
   vb200_pdl_trigger();
-  vb200_pdl_wait();    // the vertex kernel's raster records and zeroed tile counters
   uint32_t t[kSetupPerThread], s0[kSetupPerThread], s1[kSetupPerThread], s2[kSetupPerThread];
   uint32_t tiles[kSetupPerThread];
   bool alive[kSetupPerThread];
@@ -280,6 +279,10 @@ __global__ void __launch_bounds__(kThreads) k_setup(const Vb200SetupParams p)
       span[k].count = hi >= lo ? min(hi - lo + 1u, span[k].count) : 0u;
     }
   }
+  // Everything above read inputs only (draw table, index buffer, a device-measured range from before the vertex
+  // kernel): with a programmatic launch it ran while the vertex kernel's last wave drained. From here on the
+  // vertex kernel's raster records and zeroed tile counters are needed.
+  vb200_pdl_wait();
   // ---- 2. window positions of the three corners (the raster record's first 8 bytes)
 #pragma unroll
   for(int k = 0; k < kSetupPerThread; k++)
