@@ -140,6 +140,16 @@ NCU_WARP_INSTRUCTIONS = {
 }
 
 
+# what binds the tile kernels instead of HBM (same ncu captures, profiles/r02_ncu_*_kernels.txt): share of the peak
+# the l1tex data pipe (shared-memory + global wavefronts) and the issue slots are busy, per launch
+NCU_SM_LIMITERS = {
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.175, "issue_slots": 0.407},
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.732, "issue_slots": 0.670},
+    ("c4", 1, "vb200_k_tile_ordered"): {"l1tex_data_pipe": 0.461, "issue_slots": 0.781},
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.817, "issue_slots": 0.714},
+}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -806,7 +816,9 @@ def run_ours(args, workload: str) -> None:
                      "algorithmic_bytes": tile_bytes, "kernel_ms": tiles_ms, "peak_source": peak_src,
                      "frame": {"algorithmic_bytes": frame_bytes, "achieved": frame_gbs,
                                "frac": frame_gbs / (peak * world)},
-                     "issue": issue_info},
+                     "issue": issue_info,
+                     # (not HBM: the SM resources the kernel saturates first, from the committed ncu captures)
+                     "sm_limiters_ncu": NCU_SM_LIMITERS.get((workload, world, tile_kernel))},
         "e2e": {"value": tris / t_e2e / 1e6, "unit": "Mtri/s", "ms_per_step": t_e2e * 1e3,
                 "h2d_bytes_per_step": st2["h2d_bytes"] // e2e_steps, "d2h_bytes_per_step": st2["d2h_bytes"] // e2e_steps,
                 "steps": e2e_steps, "host_buffers": {"inputs": in_bytes, "attachments": out_bytes}},
