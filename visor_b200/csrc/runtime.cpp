@@ -805,7 +805,13 @@ int compileKernel(int which, const vb200_entry *shader, std::vector<char> &cubin
     needHelpers = false;
     for(const char *helper : {"vb200_fetch_attr", "vb200_sample_cube", "vb200_sample_tex"})
     {
-      vb200::ptx_inline_calls(inlinedEntry, scaffold.helpers, helper, &serial);
+      // (the texture unit is ~2 800 lines of PTX per copy: a shader with many sample instructions keeps the call,
+      // or the module would take ptxas seconds)
+      size_t sites = 0;
+      for(size_t at = inlinedEntry.find(helper); at != std::string::npos; at = inlinedEntry.find(helper, at + 1))
+        sites++;
+      if(sites <= 12)
+        vb200::ptx_inline_calls(inlinedEntry, scaffold.helpers, helper, &serial);
       needHelpers |= vb200::ptx_has_call(inlinedEntry, helper);
     }
     needBody = vb200::ptx_has_call(inlinedEntry, fn);
