@@ -415,7 +415,7 @@ EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "
                 "roundeven", "trunc", "ceil", "fsign", "radians", "degrees", "step", "smoothstep", "fma",
                 "distance3", "faceforward3", "refract3", "int_minmax", "uint_minmax", "int_abs_sign", "phi_loop",
                 "phi_swap", "int_divmod", "uint_divmod", "shifts_bits", "ucvt", "int_cmp", "logic", "isnan_inf",
-                "switch_phi")
+                "switch_phi", "consts_copy", "composite_insert", "vec_dynamic")
 
 
 def vs_unit(op: str) -> np.ndarray:
@@ -702,6 +702,32 @@ def vs_unit(op: str) -> np.ndarray:
         m.label(merge)
         r = m.new_id()
         m.raw(Op.Phi, v4, r, a, c0, b, c2, s3, c3, c, dflt)
+    elif op == "consts_copy":
+        # r = (true && a.x < b.x) ? copy(a) + null : (false || undef_bool ? c : b + undef_vec * 0)
+        bt = m.t_bool()
+        t_, f_ = m.const_bool(True), m.const_bool(False)
+        cond = m.inst(Op.LogicalAnd, bt, t_, m.inst(Op.FOrdLessThan, bt, ax, bx))
+        a2 = m.inst(Op.FAdd, v4, m.inst(Op.CopyObject, v4, a), m.const_null(v4))
+        m.stmt(Op.Nop)
+        ub = m.inst(Op.LogicalOr, bt, f_, m.inst(Op.Undef, bt))
+        uv = m.inst(Op.FMul, v4, m.undef(v4), m.const_fvec(0.0, 0.0, 0.0, 0.0))
+        alt = m.inst(Op.Select, v4, ub, c, m.inst(Op.FAdd, v4, b, uv))
+        r = m.inst(Op.Select, v4, cond, a2, alt)
+    elif op == "composite_insert":
+        # v = a with .z replaced by b.x; M2 = M with column 1 replaced by v and element [2][3] by c.y; r = col sum
+        v1 = m.inst(Op.CompositeInsert, v4, bx, a, 2)
+        M2 = m.inst(Op.CompositeInsert, mat4, v1, M, 1)
+        M3 = m.inst(Op.CompositeInsert, mat4, m.extract(fl, c, 1), M2, 2, 3)
+        r = col_sum(M3)
+    elif op == "vec_dynamic":
+        # i = int(a.x * 6) (0..5: past the end included); r = insert(b, c[i], (i + 1) & 3) + splat(a[i])
+        it = m.t_int(1)
+        i = m.inst(Op.ConvertFToS, it, m.inst(Op.FMul, fl, ax, m.const_f(6.0)))
+        e = m.inst(Op.VectorExtractDynamic, fl, c, i)
+        j = m.inst(Op.BitwiseAnd, it, m.inst(Op.IAdd, it, i, m.const_i(1)), m.const_i(3))
+        ins = m.inst(Op.VectorInsertDynamic, v4, b, e, j)
+        ins2 = m.inst(Op.VectorInsertDynamic, v4, ins, ax, m.inst(Op.IAdd, it, i, m.const_i(2)))    # may be past the end
+        r = m.inst(Op.FAdd, v4, ins2, splat(m.inst(Op.VectorExtractDynamic, fl, a, i)))
     elif op == "fabs":
         r = m.ext(v4, GLSL.FAbs, a)
     elif op == "floor":

@@ -17,6 +17,8 @@ VERSION_1_0 = 0x00010000
 
 
 class Op:
+    Nop = 0
+    Undef = 1
     Source = 3
     Name = 5
     MemberName = 6
@@ -38,8 +40,11 @@ class Op:
     TypeStruct = 30
     TypePointer = 32
     TypeFunction = 33
+    ConstantTrue = 41
+    ConstantFalse = 42
     Constant = 43
     ConstantComposite = 44
+    ConstantNull = 46
     Function = 54
     FunctionParameter = 55
     FunctionEnd = 56
@@ -50,9 +55,13 @@ class Op:
     AccessChain = 65
     Decorate = 71
     MemberDecorate = 72
+    VectorExtractDynamic = 77
+    VectorInsertDynamic = 78
     VectorShuffle = 79
     CompositeConstruct = 80
     CompositeExtract = 81
+    CompositeInsert = 82
+    CopyObject = 83
     Transpose = 84
     ImageSampleImplicitLod = 87
     ConvertFToU = 109
@@ -311,6 +320,28 @@ class Module:
         return self._type(("simg", dim), Op.TypeSampledImage, self.t_image(dim))
 
     # ---- constants
+    def const_bool(self, v: bool) -> int:
+        key = ("b", bool(v))
+        if key not in self._consts:
+            i = self.new_id()
+            self._emit("types", Op.ConstantTrue if v else Op.ConstantFalse, self.t_bool(), i)
+            self._consts[key] = i
+        return self._consts[key]
+
+    def const_null(self, t: int) -> int:
+        key = ("null", t)
+        if key not in self._consts:
+            i = self.new_id()
+            self._emit("types", Op.ConstantNull, t, i)
+            self._consts[key] = i
+        return self._consts[key]
+
+    def undef(self, t: int) -> int:
+        """module-level OpUndef"""
+        i = self.new_id()
+        self._emit("types", Op.Undef, t, i)
+        return i
+
     def const_f(self, v: float) -> int:
         key = ("f", _f32_bits(v))
         if key not in self._consts:

@@ -58,6 +58,8 @@ enum Op : uint16_t
   OpUGreaterThanEqual = 174, OpSGreaterThanEqual = 175, OpULessThan = 176, OpULessThanEqual = 178,
   OpSLessThanEqual = 179, OpShiftRightLogical = 194, OpShiftRightArithmetic = 195, OpBitwiseOr = 197,
   OpBitwiseXor = 198, OpNot = 200, OpSwitch = 251,
+  OpNop = 0, OpUndef = 1, OpConstantTrue = 41, OpConstantFalse = 42, OpConstantNull = 46, OpVectorExtractDynamic = 77,
+  OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
   OpIAdd = 128, OpFAdd = 129, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136,
   OpVectorTimesScalar = 142, OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144,
   OpMatrixTimesVector = 145, OpMatrixTimesMatrix = 146, OpDot = 148, OpIEqual = 170,
@@ -506,6 +508,21 @@ static void parse(Module &m)
         m.valtype[pCode[2]] = pCode[1];
         break;
       }
+      case OpConstantTrue: case OpConstantFalse: case OpConstantNull: case OpUndef:    // extended mode
+      {
+        if(!g_extended)
+          FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
+        const Type &t = m.types[chk(pCode[1])];
+        const TKind ek = t.kind == T_VEC ? m.types[t.elem].kind : t.kind;
+        if((t.kind != T_VEC && t.kind != T_FLOAT && t.kind != T_INT && t.kind != T_BOOL) ||
+           (ek != T_FLOAT && ek != T_INT && ek != T_BOOL) || ((op == OpConstantTrue || op == OpConstantFalse) && t.kind != T_BOOL))
+          FAIL("constant %u: scalars and vectors of float, int or bool only", op);
+        for(int c = 0; c < 4; c++)
+          m.consts[chk(pCode[2])].u[c] = op == OpConstantTrue ? 1u : 0u;
+        m.isconst[pCode[2]] = 1;
+        m.valtype[pCode[2]] = pCode[1];
+        break;
+      }
       default: break;
     }
     if(op == OpFunction)
@@ -614,11 +631,16 @@ static void parse(Module &m)
             case OpLogicalAnd: case OpLogicalNot: case OpINotEqual: case OpUGreaterThan: case OpSGreaterThan:
             case OpUGreaterThanEqual: case OpSGreaterThanEqual: case OpULessThan: case OpULessThanEqual:
             case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
-            case OpBitwiseXor: case OpNot:
+            case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
+            case OpCompositeInsert: case OpCopyObject:
               if(!g_extended)
                 FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
               m.valtype[chk(pCode[2])] = chk(pCode[1]);
               cur->insts.push_back(pCode);
+              break;
+            case OpNop:
+              if(!g_extended)
+                FAIL("Unhandled SPIR-V opcode %u", op);    // :1888
               break;
             case OpSwitch:
             case OpKill:
@@ -642,6 +664,7 @@ static void parse(Module &m)
           {
             case OpCapability: case OpMemoryModel: case OpExecutionMode: case OpExtInstImport:
             case OpSource: case OpSourceExtension: case OpMemberName: case OpName: case OpEntryPoint:
+            case OpConstantTrue: case OpConstantFalse: case OpConstantNull: case OpUndef:
             case OpDecorate: case OpMemberDecorate: case OpConstantComposite: case OpConstant:
             case OpTypeVoid: case OpTypeBool: case OpTypeInt: case OpTypeFloat: case OpTypeVector:
             case OpTypeArray: case OpTypeMatrix: case OpTypePointer: case OpTypeStruct:
@@ -1034,6 +1057,38 @@ struct Interp
             V[w[2]].u[c] = (f > -1.0f && f < 4294967296.0f) ? (uint32_t)(f < 0.0f ? 0.0f : f) : 0u;
           }
           break;
+        case OpCopyObject: V[w[2]] = V[w[3]]; break;
+        case OpUndef: memset(&V[w[2]], 0, sizeof(Val)); break;
+        case OpCompositeInsert:    // object, composite, indexes
+        {
+          Val r = V[w[4]];
+          if(isAggregate(m, m.valtype[w[4]]))
+          {
+            if(wc == 6)
+              memcpy(&r.u[w[5] * 4], V[w[3]].u, 16);
+            else
+              r.u[w[5] * 4 + w[6]] = V[w[3]].u[0];
+          }
+          else
+            r.u[w[5]] = V[w[3]].u[0];
+          V[w[2]] = r;
+          break;
+        }
+        case OpVectorExtractDynamic:    // an index past the end gives component 0
+        {
+          const uint32_t n = ncomp(w[3]), ix = V[w[4]].u[0];
+          V[w[2]].u[0] = V[w[3]].u[ix < n ? ix : 0];
+          break;
+        }
+        case OpVectorInsertDynamic:    // an index past the end changes nothing
+        {
+          Val r = V[w[3]];
+          const uint32_t n = ncomp(w[3]), ix = V[w[5]].u[0];
+          if(ix < n)
+            r.u[ix] = V[w[4]].u[0];
+          V[w[2]] = r;
+          break;
+        }
         case OpSwitch:
         {
           const uint32_t sel = V[w[1]].u[0];

@@ -197,6 +197,9 @@ def test_dynamic_indices_into_local_arrays(vor):
     vor.DestroyFunction(mod)
 
 
+_UBO_FOR_EXT = None    # the uniform block of the running test (the matrix operand of composite_insert)
+
+
 def _expected_ext(op, a, b, c):
     f32 = np.float32
     if op == "select":
@@ -314,6 +317,26 @@ def _expected_ext(op, a, b, c):
     if op == "switch_phi":
         sel = int(np.trunc(f32(a[0] * f32(5.0))))
         return {0: a, 2: b, 3: (a + b).astype(f32)}.get(sel, c)
+    if op == "consts_copy":
+        return a if a[0] < b[0] else b
+    if op == "composite_insert":
+        M = np.array(_UBO_FOR_EXT[:16], f32).reshape(4, 4).copy()    # M[col][row]
+        v1 = a.copy()
+        v1[2] = b[0]
+        M[1] = v1
+        M[2][3] = c[1]
+        r = M[0].copy()
+        for k in (1, 2, 3):
+            r = (r + M[k]).astype(f32)
+        return r
+    if op == "vec_dynamic":
+        i = int(np.trunc(f32(a[0] * f32(6.0))))
+        e = c[i] if 0 <= i < 4 else c[0]
+        ins = b.copy()
+        ins[(i + 1) & 3] = e
+        if 0 <= i + 2 < 4:
+            ins[i + 2] = a[0]
+        return (ins + (a[i] if 0 <= i < 4 else a[0])).astype(f32)
     if op in ("phi_loop", "phi_swap"):
         n = 3 + (int(np.trunc(f32(a[0] * f32(8.0)))) & 3)
         acc, oth = a.copy(), b.copy()
@@ -338,6 +361,8 @@ def test_extended_op_rejected_by_default_and_matches_numpy_when_enabled(vor, op)
     assert setopt(b"extended_spirv", 1) == 0
     try:
         verts, ubo = unit_inputs(3)
+        global _UBO_FOR_EXT
+        _UBO_FOR_EXT = ubo
         verts[::3, 4:8] = verts[::3, 0:4]    # equal operands for the (in)equality tests
         mod, st, keep = unit_state(vor, op, verts, ubo)
         entry = vor.GetFuncPointer(mod, "main")

@@ -55,6 +55,8 @@ enum : uint32_t
   OpUGreaterThanEqual = 174, OpSGreaterThanEqual = 175, OpULessThan = 176, OpULessThanEqual = 178,
   OpSLessThanEqual = 179, OpShiftRightLogical = 194, OpShiftRightArithmetic = 195, OpBitwiseOr = 197,
   OpBitwiseXor = 198, OpNot = 200, OpSwitch = 251,
+  OpNop = 0, OpUndef = 1, OpConstantTrue = 41, OpConstantFalse = 42, OpConstantNull = 46, OpVectorExtractDynamic = 77,
+  OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
 };
 enum : uint32_t
 {
@@ -411,6 +413,21 @@ struct Module
           valtype[p[2]] = p[1];
           break;
         }
+        case OpConstantTrue: case OpConstantFalse: case OpConstantNull: case OpUndef:    // extended mode
+        {
+          if(!g_extendedSpirv)
+            fail("Unhandled SPIR-V opcode %u", op);    // :1888
+          const Ty &t = types[id(p[1])];
+          const Kind ek = t.kind == K_VEC ? types[t.elem].kind : t.kind;
+          if((t.kind != K_VEC && t.kind != K_FLOAT && t.kind != K_INT && t.kind != K_BOOL) ||
+             (ek != K_FLOAT && ek != K_INT && ek != K_BOOL) || ((op == OpConstantTrue || op == OpConstantFalse) && t.kind != K_BOOL))
+            fail("constant %u: scalars and vectors of float, int or bool only", op);
+          for(uint32_t c = 0; c < 4; c++)
+            constBits[c][id(p[2])] = op == OpConstantTrue ? 1u : 0u;
+          isConst[p[2]] = 1;
+          valtype[p[2]] = p[1];
+          break;
+        }
         case OpCapability: case OpMemoryModel: case OpExecutionMode: case OpSource:
         case OpSourceExtension: case OpName: case OpMemberName: break;
         default: fail("Unhandled SPIR-V opcode %u", op);    // :1888
@@ -481,11 +498,13 @@ struct Module
             case OpLogicalAnd: case OpLogicalNot: case OpINotEqual: case OpUGreaterThan: case OpSGreaterThan:
             case OpUGreaterThanEqual: case OpSGreaterThanEqual: case OpULessThan: case OpULessThanEqual:
             case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
-            case OpBitwiseXor: case OpNot:
+            case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
+            case OpCompositeInsert: case OpCopyObject:
               if(!g_extendedSpirv)
                 fail("Unhandled SPIR-V opcode %u", op);    // :1888
               valtype[id(p[2])] = id(p[1]);
               break;
+            case OpNop:
             case OpSwitch:
             case OpKill:
               if(!g_extendedSpirv)
@@ -1477,6 +1496,94 @@ struct Emitter
         }
         break;
       }
+      case OpNop: break;
+      case OpCopyObject:
+      {
+        const Value &src = use(w[3]);
+        Value v = src;
+        v.type = w[1];
+        vals[m.id(w[2])] = v;
+        break;
+      }
+      case OpUndef:    // any value will do: zero (false)
+      {
+        Value &v = def(w[2], w[1]);
+        const bool pred = isBoolTy(w[1]);
+        for(uint32_t c = 0; c < flat(w[1]); c++)
+        {
+          std::string r = pred ? P() : R();
+          line(pred ? "setp.ne.u32 %s, 0, 0;" : "mov.b32 %s, 0;", r.c_str());
+          v.r.push_back(r);
+        }
+        break;
+      }
+      case OpCompositeInsert:    // object, composite, indexes: the composite with one part replaced
+      {
+        const Value &obj = use(w[3]), &comp = use(w[4]);
+        const Ty &ct = T(comp.type);
+        Value v;
+        v.type = w[1];
+        v.defined = true;
+        v.r = comp.r;
+        size_t at = 0, n = 1;
+        if(ct.kind == K_VEC)
+        {
+          if(wc != 6 || w[5] >= ct.count)
+            fail("OpCompositeInsert index");
+          at = w[5];
+        }
+        else if(ct.kind == K_MAT || ct.kind == K_ARR)
+        {
+          const uint32_t fl = flat(ct.elem);
+          if((wc != 6 && wc != 7) || w[5] >= ct.count || (wc == 7 && w[6] >= fl))
+            fail("OpCompositeInsert index");
+          at = (size_t)w[5] * fl + (wc == 7 ? w[6] : 0u);
+          n = wc == 7 ? 1 : fl;
+        }
+        else
+          fail("OpCompositeInsert into this type is not supported");
+        if(obj.r.size() != n || at + n > v.r.size())
+          fail("OpCompositeInsert operand shape");
+        for(size_t i = 0; i < n; i++)
+          v.r[at + i] = obj.r[i];
+        vals[m.id(w[2])] = v;
+        break;
+      }
+      case OpVectorExtractDynamic:    // vector, index: a select chain; an index past the end gives component 0
+      {
+        const std::vector<std::string> &a = regs(w[3]);
+        const std::string &ix = regs(w[4], 1)[0];
+        const bool pred = isBoolTy(w[1]);
+        if(pred)
+          fail("dynamic access to a vector of booleans is not supported");
+        std::string cur = a[0];
+        for(size_t i = 1; i < a.size(); i++)
+        {
+          std::string p = P(), d = R();
+          line("setp.eq.s32 %s, %s, %zu;", p.c_str(), ix.c_str(), i);
+          line("selp.b32 %s, %s, %s, %s;", d.c_str(), a[i].c_str(), cur.c_str(), p.c_str());
+          cur = d;
+        }
+        Value &v = def(w[2], w[1]);
+        v.r.push_back(cur);
+        break;
+      }
+      case OpVectorInsertDynamic:    // vector, component, index: an index past the end changes nothing
+      {
+        const std::vector<std::string> a = regs(w[3]);
+        const std::string c = regs(w[4], 1)[0], ix = regs(w[5], 1)[0];
+        if(isBoolTy(w[1]))
+          fail("dynamic access to a vector of booleans is not supported");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          std::string p = P(), d = R();
+          line("setp.eq.s32 %s, %s, %zu;", p.c_str(), ix.c_str(), i);
+          line("selp.b32 %s, %s, %s, %s;", d.c_str(), c.c_str(), a[i].c_str(), p.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
       case OpSwitch:    // selector, default label, (literal, label)*: a chain of compares; edges with phis get blocks
       {
         const std::string &sel = regs(w[1], 1)[0];
@@ -2058,10 +2165,14 @@ struct Emitter
       if(m.isConst[i])
       {
         Value &v = def(i, m.valtype[i]);
+        const bool pred = isBoolTy(m.valtype[i]);
         for(uint32_t c = 0; c < flat(m.valtype[i]); c++)
         {
-          std::string r = R();
-          line("mov.b32 %s, %s;", r.c_str(), imm(m.constBits[c][i]).c_str());
+          std::string r = pred ? P() : R();
+          if(pred)
+            line("setp.ne.u32 %s, %u, 0;", r.c_str(), m.constBits[c][i] & 1u);
+          else
+            line("mov.b32 %s, %s;", r.c_str(), imm(m.constBits[c][i]).c_str());
           v.r.push_back(r);
         }
       }
