@@ -630,6 +630,33 @@ def test_mirror_merge_in_the_middle_of_a_frame(gpu, vor):
     assert np.array_equal(got_c, want_c)
 
 
+def test_mirror_merge_inside_one_draw(gpu, vor):
+    """The merge can also happen between two resolves of ONE draw: the colour attachment lies inside the
+    stale mirror of an earlier frame, the depth attachment straddles its end. The colour address taken before
+    the merge points into the retired allocation; the draw must not render there."""
+    w, h = 200, 120
+    img_bytes = w * h * 4
+    for load in (False, True):
+        pool = np.zeros(4 << 20, np.uint8)
+        first = scenes.random_triangles(512, 256, 40, 84, has_depth=False, depth_op=abi.CMP_ALWAYS)
+        big_color = pool[:512 * 256 * 4].reshape(256, 512, 4)
+        scenes.BoundScene(gpu, first, color=big_color).run()
+        stale_end = big_color.nbytes
+        sc = scenes.random_triangles(w, h, 60, 85)
+        want = scenes.random_triangles(w, h, 60, 85)
+        if load:
+            sc.clear_color = sc.clear_depth = want.clear_color = want.clear_depth = None
+        color = pool[:img_bytes].reshape(h, w, 4)
+        lo = (stale_end - img_bytes // 2) & ~255
+        depth = pool[lo:lo + img_bytes].view(np.float32).reshape(h, w)
+        color[...] = 0xCD
+        depth[...] = 0.75
+        want_c, want_d = scenes.render(vor, want)    # (attachments start as 0xCD / 0.75 there too)
+        got_c, got_d = scenes.BoundScene(gpu, sc, color=color, depth=depth).run()
+        assert np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))
+        assert np.array_equal(got_c, want_c)
+
+
 def test_clear_fusion_variants(gpu, vor):
     """deferred clears: consumed by the first draw, materialised for a second target/draw, depth clear
     without a depth-using pipeline, colour cleared but depth loaded"""

@@ -271,6 +271,7 @@ struct Context
   cudaStream_t stream = nullptr;
   int syncMode = VB200_SYNC_COHERENT;
   uint64_t epoch = 1;
+  uint64_t mirrorMerges = 0;    // createMirror calls that replaced existing mirrors
   std::map<uintptr_t, Mirror> mirrors;
   std::vector<uint8_t *> zombies;    // device memory of merged mirrors, freed at the next flush
   std::map<std::pair<uint64_t, int>, JitKernel> kernels;    // (shader entry serial, K_*) -> loaded kernel
@@ -446,8 +447,11 @@ int createMirror(void *host, size_t size, bool pin, Mirror **out)
   // Draws recorded into the open batch but not launched yet hold device addresses inside the mirrors about
   // to be replaced (attachments included): they run first, so that the copies below carry their results over.
   if(!victims.empty())
+  {
     if(int frc = flushBatchKeepOpen())
       return frc;
+    g.mirrorMerges++;    // vb200_draw resolves its ranges again when this moved under it
+  }
   Mirror nm;
   nm.host = (uint8_t *)lo;
   nm.size = hi - lo;
@@ -2199,6 +2203,13 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
       vertexBound = (uint32_t)std::min<uint64_t>(vertexBound, n);
     }
   }
+  // A resolve below may replace mirrors by a merged one (a host range straddling older mirrors): device
+  // addresses taken earlier in this draw would then point into the retired allocations, and what the draw
+  // wrote to an attachment there would never reach the new mirror. Every range has a mirror after the
+  // first pass, so a second pass cannot merge again.
+  const uint64_t mergesBefore = g.mirrorMerges;
+  bool resolvedTwice = false;
+resolveRanges:
   for(uint32_t i = 0; i < 4; i++)
     if(s->vbs[i].buffer.bytes)
     {
@@ -2254,6 +2265,11 @@ int vb200_draw(const vb200_draw_state *s, int num_verts, uint32_t first, int ind
   if(hasDepth && (depthTest || depthWrite))
     if((rc = resolve(s->depth.pixels, (size_t)W * H * 4, ACC_READ | ACC_WRITE | ACC_KEEP_PENDING, &depthDev)))
       return rc;
+  if(g.mirrorMerges != mergesBefore && !resolvedTwice && !getenv("VB200_DEBUG_NO_RERESOLVE"))
+  {
+    resolvedTwice = true;
+    goto resolveRanges;
+  }
 
   // Raster back end. A pass is order-independent ("resolvable") unless it blends or runs
   // NOT_EQUAL against a depth buffer it also writes; see scaffold.cu.
