@@ -313,7 +313,8 @@ VB200_API const char *vb200_last_tile_kernel(void);
  * "extended_spirv": 1 makes later vb200_shader_create calls
  * accept opcodes the reference asserts on: OpPhi, OpSwitch, OpKill (discard; such fragment shaders always run
  * on the in-order tile kernel), OpSelect, the remaining float and integer comparisons, integer division /
- * remainder / shifts / bit and logic operations, OpBitcast, OpConvertFToS/FToU/UToF, OpIsNan/OpIsInf and 23
+ * remainder / shifts / bit and logic operations, OpBitcast, OpConvertFToS/FToU/UToF, OpIsNan/OpIsInf, OpCopyObject, OpUndef, OpConstantNull/True/False,
+ * OpCompositeInsert, OpVectorExtractDynamic/InsertDynamic and 23
  * GLSL.std.450 instructions (DESIGN.md section 3 lists them and the results fixed where SPIR-V leaves them
  * open) — off by default, because with it the front end no longer rejects exactly what CompileFunction
  * rejects (spirv_compile.cpp:1734,1888). Unknown names return VB200_ERR_INVALID. */
