@@ -124,8 +124,8 @@ def nvlink_kib(index: int):
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_c{2,3,4,5}_kernels.txt (ncu --set full, per launch)"
 NCU_TRAFFIC = {
     ("c2", 1, "vb200_k_tile_resolve_min_first"): 404992 + 0,
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 27098000 + 11232000,
-    ("c4", 1, "vb200_k_tile_ordered"): 34588000 + 209664,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 27128000 + 10336000,
+    ("c4", 1, "vb200_k_tile_ordered"): 34586000 + 169728,
     ("c5", 1, "vb200_k_tile_resolve_min_first"): 148692000 + 208273000,
 }
 
@@ -134,8 +134,8 @@ NCU_TRAFFIC = {
 # kernel is bound by instruction issue, not by HBM, so the bench also reports its issue-slot utilisation
 NCU_WARP_INSTRUCTIONS = {
     ("c2", 1, "vb200_k_tile_resolve_min_first"): 8.79e6,
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): 95.64e6,
-    ("c4", 1, "vb200_k_tile_ordered"): 249.20e6,
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): 97.70e6,
+    ("c4", 1, "vb200_k_tile_ordered"): 249.22e6,
     ("c5", 1, "vb200_k_tile_resolve_min_first"): 530.86e6,
 }
 
@@ -144,8 +144,8 @@ NCU_WARP_INSTRUCTIONS = {
 # the l1tex data pipe (shared-memory + global wavefronts) and the issue slots are busy, per launch
 NCU_SM_LIMITERS = {
     ("c2", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.175, "issue_slots": 0.407},
-    ("c3", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.732, "issue_slots": 0.670},
-    ("c4", 1, "vb200_k_tile_ordered"): {"l1tex_data_pipe": 0.461, "issue_slots": 0.781},
+    ("c3", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.652, "issue_slots": 0.698},
+    ("c4", 1, "vb200_k_tile_ordered"): {"l1tex_data_pipe": 0.468, "issue_slots": 0.782},
     ("c5", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.817, "issue_slots": 0.714},
 }
 

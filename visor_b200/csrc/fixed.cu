@@ -495,8 +495,71 @@ __device__ __forceinline__ void bitonic_sort(uint32_t *a, uint32_t n)
 
 constexpr uint32_t kSortSmem = 8192;    // entries (32 KB)
 
+// Lists of up to 512 ids (two per thread, held in registers): stable LSD radix sort, four bits per pass,
+// over as many bits as the largest id of the list has. Element i belongs to chunk i / 32, i.e. to one
+// warp: MATCH.ANY on the digit gives its rank among the chunk's equal digits and, on the first lane of every
+// group, the group's size; a scan over the 16 x 16 (digit-major, chunk-minor) counts turns that into
+// positions. Padding (0xffffffff) has digit 15 in every pass and starts behind everything, so it stays there.
+// The counts of one digit are 17 words apart, not 16: a warp's lanes address them by digit, and 16 would put
+// all even digits into one bank. `s`: 512 keys, 16 x 17 counts, 8 warp totals, 1 word for the OR of all ids.
+__device__ __forceinline__ void radix_sort_512(uint32_t *a, uint32_t n, uint32_t *s)
+{
+  uint32_t *buf = s, *hist = s + 512, *wtot = s + 784, *bitsOr = s + 792;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t below = (1u << lane) - 1u;
+  const bool in0 = tid < n, in1 = tid + 256u < n;
+  uint32_t k0 = in0 ? a[tid] : 0xffffffffu, k1 = in1 ? a[tid + 256u] : 0xffffffffu;
+  if(tid == 0)
+    *bitsOr = 0u;
+  __syncthreads();
+  const uint32_t mine = __reduce_or_sync(0xffffffffu, (in0 ? k0 : 0u) | (in1 ? k1 : 0u));
+  if(lane == 0 && mine)
+    atomicOr(bitsOr, mine);
+  __syncthreads();
+  const uint32_t bits = 32u - (uint32_t)__clz((int)*bitsOr);
+  for(uint32_t shift = 0; shift < bits; shift += 4u)
+  {
+    const uint32_t d0 = (k0 >> shift) & 15u, d1 = (k1 >> shift) & 15u;
+    const uint32_t own = (tid >> 4) * 17u + (tid & 15u);    // this thread's count in the scan
+    hist[own] = 0u;
+    __syncthreads();
+    const uint32_t m0 = __match_any_sync(0xffffffffu, d0), m1 = __match_any_sync(0xffffffffu, d1);
+    const uint32_t r0 = __popc(m0 & below), r1 = __popc(m1 & below);
+    if(r0 == 0u)
+      hist[d0 * 17u + warp] = __popc(m0);
+    if(r1 == 0u)
+      hist[d1 * 17u + warp + 8u] = __popc(m1);
+    __syncthreads();
+    // exclusive scan of the 256 counts, one per thread
+    const uint32_t v = hist[own];
+    uint32_t x = v;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if(lane >= (uint32_t)o)
+        x += y;
+    }
+    if(lane == 31u)
+      wtot[warp] = x;
+    __syncthreads();
+    const uint32_t base = __reduce_add_sync(0xffffffffu, lane < warp ? wtot[lane] : 0u);    // warp < 8
+    hist[own] = base + x - v;
+    __syncthreads();
+    buf[hist[d0 * 17u + warp] + r0] = k0;
+    buf[hist[d1 * 17u + warp + 8u] + r1] = k1;
+    __syncthreads();
+    k0 = buf[tid];
+    k1 = buf[tid + 256u];
+  }
+  if(in0)
+    a[tid] = k0;
+  if(in1)
+    a[tid + 256u] = k1;
+}
+
 __global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_t *tile_count, uint32_t list_cap,
-                                                  uint32_t rank, uint32_t world, uint32_t ntiles)
+                                                  uint32_t rank, uint32_t world, uint32_t ntiles, uint32_t rankSort)
 {
   __shared__ __align__(16) uint32_t s[kSortSmem];
   vb200_pdl_trigger();
@@ -513,9 +576,11 @@ __global__ void __launch_bounds__(kThreads) k_sort(uint32_t *list, const uint32_
     unsorted |= a[i] > a[i + 1u];
   if(!__syncthreads_or(unsorted))
     return;
-  if(n <= 512u)
+  if(n <= 512u && !rankSort)
+    radix_sort_512(a, n, s);
+  else if(n <= 512u)
   {
-    // short lists (the common case: a few hundred triangles per tile): rank sort. Triangle ids are
+    // (the earlier version, kept behind VB200_SORT_RANK=1 for comparison) rank sort. Triangle ids are
     // unique, so an id's final position is the number of smaller ids; every thread counts that for its
     // own elements against broadcast reads of the staged list — no barriers, no data-dependent branches.
     const uint32_t n4 = (n + 3u) & ~3u;
@@ -735,7 +800,8 @@ int launch_setup(const Vb200SetupParams &p, cudaStream_t s)
 int launch_sort(uint32_t *list, const uint32_t *tile_count, uint32_t list_cap, uint32_t rank, uint32_t world,
                 uint32_t ntiles, cudaStream_t s)
 {
-  launch_dependent(k_sort, (ntiles + world - 1) / world, s, list, tile_count, list_cap, rank, world, ntiles);
+  static const uint32_t rankSort = getenv("VB200_SORT_RANK") != nullptr;
+  launch_dependent(k_sort, (ntiles + world - 1) / world, s, list, tile_count, list_cap, rank, world, ntiles, rankSort);
   return 1;
 }
 

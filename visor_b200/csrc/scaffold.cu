@@ -647,6 +647,22 @@ __device__ __forceinline__ bool vb200_fragment_key(int b0, int b1, int b2, float
   return true;
 }
 
+// Where pixel (x, y) of the tile keeps its visibility key. Rows are rotated against each other by
+// 1 << VB200_VIS_SKEW columns: the hits a warp processes together are short runs of rows stacked on top of
+// each other (small triangles), and with plain row-major slots the runs of one triangle would all fall into
+// the same shared-memory banks (a 256-byte row is a whole number of bank cycles).
+#ifndef VB200_VIS_SKEW
+#define VB200_VIS_SKEW 2
+#endif
+__device__ __forceinline__ uint32_t vb200_vis_slot(uint32_t px, uint32_t py)
+{
+#if VB200_VIS_SKEW
+  return (py * VB200_TILE) | ((px + (py << VB200_VIS_SKEW)) & (VB200_TILE - 1u));
+#else
+  return py * VB200_TILE + px;
+#endif
+}
+
 // 64-bit min in shared memory has no native atomic: CAS until the slot holds a key <= ours (the common
 // case is no attempt at all, or one that succeeds). `seen` is a plain read that may race with other
 // warps' CAS on purpose (compute-sanitizer racecheck reports it): keys only ever decrease, so a stale
@@ -814,7 +830,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
         float e = 0.0f;
         if(MODE != VB200_RES_LAST_WINS || depthTest)
           e = clearDepth ? p.clear_depth : (in ? p.depth[(size_t)y * rs.width + x] : 0.0f);
-        vis[ly * VB200_TILE + lane] = vb200_existing_key<MODE>(e);
+        vis[vb200_vis_slot(lane, ly)] = vb200_existing_key<MODE>(e);
         if(MODE == VB200_RES_LAST_WINS)
           s_depth[ly * VB200_TILE + lane] = e;
       }
@@ -1008,7 +1024,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
           const int b2 = t0.w * px + t1.x * py + t1.y;
           const int b0 = t1.z - (b1 + b2);
           // the slot's current key is fetched before the depth arithmetic that decides whether it is needed
-          const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
+          const uint32_t aSlot = aVis + 8u * vb200_vis_slot((uint32_t)px, (uint32_t)py);
           const unsigned long long seen = vb200_lds64(aSlot);
           if(h >= hits)
             continue;
@@ -1046,7 +1062,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
                                           __int_as_float(c2.z), __int_as_float(c2.w), id, depthTest, rs.depth_op,
                                           s_depth, idx, key))
               {
-                const uint32_t aSlot = aVis + 8u * (uint32_t)idx;
+                const uint32_t aSlot = aVis + 8u * vb200_vis_slot((uint32_t)idx & 31u, (uint32_t)idx >> 5);
                 vb200_vis_min(aSlot, vb200_lds64(aSlot), key);
               }
             }
@@ -1071,7 +1087,7 @@ __device__ __forceinline__ void vb200_tile_resolve_body(const Vb200Env &env, con
     for(int j = 0; j < VB200_TILE / RW; j++, gi += rowStep)
     {
       const int ly = warp + RW * j;
-      const unsigned long long key = vb200_lds64(aVis + 8u * (uint32_t)(ly * VB200_TILE + lane));
+      const unsigned long long key = vb200_lds64(aVis + 8u * vb200_vis_slot(lane, ly));
       const uint32_t low = (uint32_t)key;
       bool won;
       uint32_t id;
