@@ -123,30 +123,30 @@ def nvlink_kib(index: int):
 # the per-launch figure of the same build and workload is recorded here; null when none was captured).
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_c{2,3,4,5}_kernels.txt (ncu --set full, per launch)"
 NCU_TRAFFIC = {
-    ("c2", 1, "vb200_k_tile_resolve_min_first"): 404992 + 0,
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): 406272 + 0,
     ("c3", 1, "vb200_k_tile_resolve_min_first"): 27128000 + 10336000,
     ("c4", 1, "vb200_k_tile_ordered"): 34586000 + 169728,
-    ("c5", 1, "vb200_k_tile_resolve_min_first"): 148692000 + 208273000,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 148613000 + 209010000,
 }
 
 
 # warp instructions one launch of the tile kernel executes (ncu smsp__inst_executed.sum, same captures): the
 # kernel is bound by instruction issue, not by HBM, so the bench also reports its issue-slot utilisation
 NCU_WARP_INSTRUCTIONS = {
-    ("c2", 1, "vb200_k_tile_resolve_min_first"): 8.79e6,
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): 8.94e6,
     ("c3", 1, "vb200_k_tile_resolve_min_first"): 97.70e6,
     ("c4", 1, "vb200_k_tile_ordered"): 249.22e6,
-    ("c5", 1, "vb200_k_tile_resolve_min_first"): 530.86e6,
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): 538.96e6,
 }
 
 
 # what binds the tile kernels instead of HBM (same ncu captures, profiles/r02_ncu_*_kernels.txt): share of the peak
 # the l1tex data pipe (shared-memory + global wavefronts) and the issue slots are busy, per launch
 NCU_SM_LIMITERS = {
-    ("c2", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.175, "issue_slots": 0.407},
+    ("c2", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.165, "issue_slots": 0.414},
     ("c3", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.652, "issue_slots": 0.698},
     ("c4", 1, "vb200_k_tile_ordered"): {"l1tex_data_pipe": 0.468, "issue_slots": 0.782},
-    ("c5", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.817, "issue_slots": 0.714},
+    ("c5", 1, "vb200_k_tile_resolve_min_first"): {"l1tex_data_pipe": 0.753, "issue_slots": 0.737},
 }
 
 
