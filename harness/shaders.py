@@ -415,7 +415,11 @@ EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "
                 "roundeven", "trunc", "ceil", "fsign", "radians", "degrees", "step", "smoothstep", "fma",
                 "distance3", "faceforward3", "refract3", "int_minmax", "uint_minmax", "int_abs_sign", "phi_loop",
                 "phi_swap", "int_divmod", "uint_divmod", "shifts_bits", "ucvt", "int_cmp", "logic", "isnan_inf",
-                "switch_phi", "consts_copy", "composite_insert", "vec_dynamic")
+                "switch_phi", "consts_copy", "composite_insert", "vec_dynamic", "frem_fmod", "any_all", "bit_ops",
+                "nminmax", "exp_log", "tan_hyp", "atan_asin")
+# of those, the ones built on transcendental functions: libm in the oracle, the special-function unit on the GPU,
+# compared under the 1-LSB colour bar like sin / cos / pow
+APPROX_EXT_OPS = ("exp_log", "tan_hyp", "atan_asin")
 
 
 def vs_unit(op: str) -> np.ndarray:
@@ -728,6 +732,81 @@ def vs_unit(op: str) -> np.ndarray:
         ins = m.inst(Op.VectorInsertDynamic, v4, b, e, j)
         ins2 = m.inst(Op.VectorInsertDynamic, v4, ins, ax, m.inst(Op.IAdd, it, i, m.const_i(2)))    # may be past the end
         r = m.inst(Op.FAdd, v4, ins2, splat(m.inst(Op.VectorExtractDynamic, fl, a, i)))
+    elif op == "frem_fmod":
+        # x = b * 7.3 (both signs), y = c (> 0) and -c: remainder with the sign of x, modulo with the sign of y
+        x = m.inst(Op.FMul, v4, b, m.const_fvec(7.3, 7.3, 7.3, 7.3))
+        rem = m.inst(Op.FRem, v4, x, c)
+        mod = m.inst(Op.FMod, v4, x, m.inst(Op.FNegate, v4, c))
+        r = m.inst(Op.FAdd, v4, m.inst(Op.FMul, v4, rem, m.const_fvec(0.5, 0.5, 0.5, 0.5)),
+                   m.inst(Op.FMul, v4, mod, m.const_fvec(-0.5, -0.5, -0.5, -0.5)))
+    elif op == "any_all":
+        bt = m.t_bool()
+        bv4 = m.t_vec(bt, 4)
+        any_ = m.inst(Op.Any, bt, m.inst(Op.FOrdLessThan, bv4, a, b))
+        all_ = m.inst(Op.All, bt, m.inst(Op.FOrdLessThanEqual, bv4, c, b))
+        r = m.inst(Op.FAdd, v4, m.inst(Op.FMul, v4, m.inst(Op.Select, v4, any_, b, c), m.const_fvec(0.5, 0.5, 0.5, 0.5)),
+                   m.inst(Op.FMul, v4, m.inst(Op.Select, v4, all_, c, a), m.const_fvec(0.25, 0.25, 0.25, 0.25)))
+    elif op == "bit_ops":
+        sv4 = m.t_vec(m.t_int(1), 4)
+        uv4 = m.t_vec(m.t_int(0), 4)
+
+        def ints(x, scale, bias):
+            k = m.inst(Op.ConvertFToS, sv4, m.inst(Op.FMul, v4, x, m.const_fvec(scale, scale, scale, scale)))
+            return m.inst(Op.ISub, sv4, k, m.inst(Op.ConvertFToS, sv4, m.const_fvec(bias, bias, bias, bias)))
+
+        def ci(val):
+            return m.inst(Op.ConvertFToS, sv4, m.const_fvec(*([float(val)] * 4)))
+        big, small = ints(b, 4000.0, 900.0), ints(c, 9.0, 3.0)    # small: -3..5, zero and -1 among them
+        x = m.inst(Op.BitCount, sv4, big)
+        rv = m.inst(Op.Bitcast, sv4, m.inst(Op.ShiftRightLogical, uv4, m.inst(Op.Bitcast, uv4, m.inst(Op.BitReverse, sv4, big)),
+                                            m.inst(Op.Bitcast, uv4, ci(24))))
+        x = m.inst(Op.IAdd, sv4, x, rv)
+        for code, arg, wgt in ((GLSL.FindILsb, big, 3), (GLSL.FindILsb, small, 5), (GLSL.FindSMsb, big, 7),
+                               (GLSL.FindSMsb, small, 11), (GLSL.FindUMsb, big, 13), (GLSL.FindUMsb, small, 17)):
+            x = m.inst(Op.IAdd, sv4, x, m.inst(Op.IMul, sv4, m.ext(sv4, code, arg), ci(wgt)))
+        x = m.inst(Op.BitwiseAnd, sv4, x, ci(255))
+        r = m.inst(Op.FMul, v4, m.inst(Op.ConvertSToF, v4, x), m.const_fvec(1 / 256.0, 1 / 256.0, 1 / 256.0, 1 / 256.0))
+    elif op == "nminmax":
+        zero = m.inst(Op.FSub, v4, a, a)
+        nan = m.inst(Op.FDiv, v4, zero, zero)
+        probe = m.shuffle(v4, nan, b, 0, 5, 2, 7)    # (nan, b.y, nan, b.w)
+        other = m.shuffle(v4, c, nan, 0, 1, 6, 3)    # (c.x, c.y, nan, c.w): one lane has NaN on both sides
+        lo = m.inst(Op.FMul, v4, c, m.const_fvec(0.5, 0.5, 0.5, 0.5))
+        t1 = m.ext(v4, GLSL.NMin, probe, c)
+        t2 = m.ext(v4, GLSL.NMax, c, probe)
+        t3 = m.ext(v4, GLSL.NClamp, probe, lo, c)
+        t4 = m.ext(v4, GLSL.NMin, probe, other)
+        # NaN survives only where both operands were NaN (lane 2 of t4): replaced through IsNan so the colour is defined
+        bv4 = m.t_vec(m.t_bool(), 4)
+        t4 = m.inst(Op.Select, v4, m.inst(Op.IsNan, bv4, t4), a, t4)
+        r = m.inst(Op.FAdd, v4, m.inst(Op.FAdd, v4, m.inst(Op.FMul, v4, t1, m.const_fvec(0.25, 0.25, 0.25, 0.25)),
+                                       m.inst(Op.FMul, v4, t2, m.const_fvec(0.25, 0.25, 0.25, 0.25))),
+                   m.inst(Op.FAdd, v4, m.inst(Op.FMul, v4, t3, m.const_fvec(0.25, 0.25, 0.25, 0.25)),
+                          m.inst(Op.FMul, v4, t4, m.const_fvec(0.125, 0.125, 0.125, 0.125))))
+    elif op == "exp_log":
+        t = m.inst(Op.FAdd, v4, m.ext(v4, GLSL.FAbs, b), m.const_fvec(0.5, 0.5, 0.5, 0.5))
+        bh = m.inst(Op.FMul, v4, b, m.const_fvec(0.5, 0.5, 0.5, 0.5))
+        terms = ((m.ext(v4, GLSL.Exp, bh), 0.15), (m.ext(v4, GLSL.Exp2, b), 0.1), (m.ext(v4, GLSL.Log, t), 0.08),
+                 (m.ext(v4, GLSL.Log2, t), 0.05))
+        r = m.const_fvec(0.2, 0.2, 0.2, 0.2)
+        for val, wgt in terms:
+            r = m.inst(Op.FAdd, v4, r, m.inst(Op.FMul, v4, val, m.const_fvec(wgt, wgt, wgt, wgt)))
+    elif op == "tan_hyp":
+        t = m.ext(v4, GLSL.Fract, b)
+        terms = ((m.ext(v4, GLSL.Tan, t), 0.15), (m.ext(v4, GLSL.Sinh, t), 0.15), (m.ext(v4, GLSL.Cosh, t), 0.15),
+                 (m.ext(v4, GLSL.Tanh, m.inst(Op.FMul, v4, b, m.const_fvec(3.0, 3.0, 3.0, 3.0))), 0.1))
+        r = m.const_fvec(0.1, 0.1, 0.1, 0.1)
+        for val, wgt in terms:
+            r = m.inst(Op.FAdd, v4, r, m.inst(Op.FMul, v4, val, m.const_fvec(wgt, wgt, wgt, wgt)))
+    elif op == "atan_asin":
+        t = m.inst(Op.FSub, v4, m.inst(Op.FMul, v4, m.ext(v4, GLSL.Fract, b), m.const_fvec(1.8, 1.8, 1.8, 1.8)),
+                   m.const_fvec(0.9, 0.9, 0.9, 0.9))
+        x2 = m.inst(Op.FSub, v4, c, m.const_fvec(0.5, 0.5, 0.5, 0.5))
+        terms = ((m.ext(v4, GLSL.Atan, m.inst(Op.FMul, v4, b, m.const_fvec(3.0, 3.0, 3.0, 3.0))), 0.1),
+                 (m.ext(v4, GLSL.Atan2, b, x2), 0.05), (m.ext(v4, GLSL.Asin, t), 0.1), (m.ext(v4, GLSL.Acos, t), 0.08))
+        r = m.const_fvec(0.4, 0.4, 0.4, 0.4)
+        for val, wgt in terms:
+            r = m.inst(Op.FAdd, v4, r, m.inst(Op.FMul, v4, val, m.const_fvec(wgt, wgt, wgt, wgt)))
     elif op == "fabs":
         r = m.ext(v4, GLSL.FAbs, a)
     elif op == "floor":

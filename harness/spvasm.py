@@ -18,6 +18,12 @@ VERSION_1_0 = 0x00010000
 
 class Op:
     Nop = 0
+    FRem = 140
+    FMod = 141
+    Any = 154
+    All = 155
+    BitReverse = 204
+    BitCount = 205
     Undef = 1
     Source = 3
     Name = 5
@@ -166,6 +172,24 @@ class BuiltIn:
 
 
 class GLSL:
+    Tan = 15
+    Asin = 16
+    Acos = 17
+    Atan = 18
+    Sinh = 19
+    Cosh = 20
+    Tanh = 21
+    Atan2 = 25
+    Exp = 27
+    Log = 28
+    Exp2 = 29
+    Log2 = 30
+    FindILsb = 73
+    FindSMsb = 74
+    FindUMsb = 75
+    NMin = 79
+    NMax = 80
+    NClamp = 81
     RoundEven = 2
     Trunc = 3
     FAbs = 4

@@ -60,6 +60,7 @@ enum Op : uint16_t
   OpBitwiseXor = 198, OpNot = 200, OpSwitch = 251,
   OpNop = 0, OpUndef = 1, OpConstantTrue = 41, OpConstantFalse = 42, OpConstantNull = 46, OpVectorExtractDynamic = 77,
   OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
+  OpFRem = 140, OpFMod = 141, OpAny = 154, OpAll = 155, OpBitReverse = 204, OpBitCount = 205,
   OpIAdd = 128, OpFAdd = 129, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136,
   OpVectorTimesScalar = 142, OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144,
   OpMatrixTimesVector = 145, OpMatrixTimesMatrix = 146, OpDot = 148, OpIEqual = 170,
@@ -86,6 +87,10 @@ enum : uint32_t
   G_Fract = 10, G_Radians = 11, G_Degrees = 12, G_UMin = 38, G_SMin = 39, G_UMax = 41, G_SMax = 42,
   G_UClamp = 44, G_SClamp = 45, G_Step = 48, G_SmoothStep = 49, G_Fma = 50, G_Distance = 67, G_FaceForward = 70,
   G_Refract = 72,
+  G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81,
+  // extended mode, libm here and the special-function unit on the GPU (as Sin/Cos/Pow): 1-LSB colour bar
+  G_Tan = 15, G_Asin = 16, G_Acos = 17, G_Atan = 18, G_Sinh = 19, G_Cosh = 20, G_Tanh = 21, G_Atan2 = 25,
+  G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30,
 };
 
 
@@ -631,6 +636,7 @@ static void parse(Module &m)
             case OpLogicalAnd: case OpLogicalNot: case OpINotEqual: case OpUGreaterThan: case OpSGreaterThan:
             case OpUGreaterThanEqual: case OpSGreaterThanEqual: case OpULessThan: case OpULessThanEqual:
             case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
+            case OpFRem: case OpFMod: case OpAny: case OpAll: case OpBitReverse: case OpBitCount:
             case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
             case OpCompositeInsert: case OpCopyObject:
               if(!g_extended)
@@ -1058,6 +1064,39 @@ struct Interp
           }
           break;
         case OpCopyObject: V[w[2]] = V[w[3]]; break;
+        case OpFRem:    // x - y * trunc(x / y); OpFMod: x - y * floor(x / y); every step rounded on its own
+        case OpFMod:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            const float x = V[w[3]].f[c], y = V[w[4]].f[c];
+            const float q = x / y;
+            const float t = op == OpFRem ? truncf(q) : floorf(q);
+            const float pr = y * t;
+            V[w[2]].f[c] = x - pr;
+          }
+          break;
+        case OpAny:
+        case OpAll:
+        {
+          uint32_t acc = op == OpAll ? 1u : 0u;
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
+            acc = op == OpAll ? (acc & V[w[3]].u[c] & 1u) : (acc | (V[w[3]].u[c] & 1u));
+          V[w[2]].u[0] = acc;
+          break;
+        }
+        case OpBitCount:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+            V[w[2]].u[c] = (uint32_t)__builtin_popcount(V[w[3]].u[c]);
+          break;
+        case OpBitReverse:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            uint32_t x = V[w[3]].u[c], r = 0;
+            for(int b = 0; b < 32; b++, x >>= 1)
+              r = (r << 1) | (x & 1u);
+            V[w[2]].u[c] = r;
+          }
+          break;
         case OpUndef: memset(&V[w[2]], 0, sizeof(Val)); break;
         case OpCompositeInsert:    // object, composite, indexes
         {
@@ -1475,6 +1514,49 @@ struct Interp
         }
         break;
       }
+      case G_FindILsb:    // index of the lowest set bit, -1 for 0
+        for(uint32_t c = 0; c < k; c++)
+          r.i[c] = ARG(0).u[c] ? __builtin_ctz(ARG(0).u[c]) : -1;
+        break;
+      case G_FindSMsb:    // highest bit that differs from the sign; -1 for 0 and -1
+        for(uint32_t c = 0; c < k; c++)
+        {
+          const uint32_t x = ARG(0).i[c] < 0 ? ~ARG(0).u[c] : ARG(0).u[c];
+          r.i[c] = x ? 31 - __builtin_clz(x) : -1;
+        }
+        break;
+      case G_FindUMsb:
+        for(uint32_t c = 0; c < k; c++)
+          r.i[c] = ARG(0).u[c] ? 31 - __builtin_clz(ARG(0).u[c]) : -1;
+        break;
+      case G_NMin: case G_NMax: case G_NClamp:    // a NaN operand yields the other one
+      {
+        auto nsel = [](bool isMin, float x, float y) {
+          if(x != x)
+            return y;
+          if(y != y)
+            return x;
+          return (isMin ? y < x : y > x) ? y : x;
+        };
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = w[4] == G_NClamp ? nsel(true, nsel(false, ARG(0).f[c], ARG(1).f[c]), ARG(2).f[c])
+                                    : nsel(w[4] == G_NMin, ARG(0).f[c], ARG(1).f[c]);
+        break;
+      }
+      // transcendental functions: libm (the GPU uses its special-function unit; neither is the reference's CRT)
+#define VOR_LIBM1(G, fn) \
+      case G: \
+        for(uint32_t c = 0; c < k; c++) \
+          r.f[c] = fn(ARG(0).f[c]); \
+        break;
+      VOR_LIBM1(G_Exp, expf) VOR_LIBM1(G_Exp2, exp2f) VOR_LIBM1(G_Log, logf) VOR_LIBM1(G_Log2, log2f)
+      VOR_LIBM1(G_Tan, tanf) VOR_LIBM1(G_Sinh, sinhf) VOR_LIBM1(G_Cosh, coshf) VOR_LIBM1(G_Tanh, tanhf)
+      VOR_LIBM1(G_Atan, atanf) VOR_LIBM1(G_Asin, asinf) VOR_LIBM1(G_Acos, acosf)
+#undef VOR_LIBM1
+      case G_Atan2:
+        for(uint32_t c = 0; c < k; c++)
+          r.f[c] = atan2f(ARG(0).f[c], ARG(1).f[c]);
+        break;
       case G_Cos: r.f[0] = cosf(ARG(0).f[0]); break;      // llvm.cos.f32 -> CRT (not reproducible)
       case G_Sin: r.f[0] = sinf(ARG(0).f[0]); break;      // llvm.sin.f32 -> CRT (not reproducible)
       case G_Sqrt: r.f[0] = sqrtf(ARG(0).f[0]); break;    // llvm.sqrt.f32 -> sqrtss (exact)
@@ -1535,7 +1617,9 @@ static void validateExt(const Module &m)
           case G_FAbs: case G_Floor: case G_Fract: case G_RoundEven: case G_Trunc: case G_Ceil: case G_SAbs:
           case G_FSign: case G_SSign: case G_Radians: case G_Degrees: case G_UMin: case G_SMin: case G_UMax:
           case G_SMax: case G_UClamp: case G_SClamp: case G_Step: case G_SmoothStep: case G_Fma: case G_Distance:
-          case G_FaceForward: case G_Refract:
+          case G_FaceForward: case G_Refract: case G_FindILsb: case G_FindSMsb: case G_FindUMsb: case G_NMin:
+          case G_NMax: case G_NClamp: case G_Tan: case G_Asin: case G_Acos: case G_Atan: case G_Sinh: case G_Cosh:
+          case G_Tanh: case G_Atan2: case G_Exp: case G_Log: case G_Exp2: case G_Log2:
             if(!g_extended)
               FAIL("Unhandled GLSL extended instruction %u", w[4]);    // :1734
             break;

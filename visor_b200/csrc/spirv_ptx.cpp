@@ -57,6 +57,7 @@ enum : uint32_t
   OpBitwiseXor = 198, OpNot = 200, OpSwitch = 251,
   OpNop = 0, OpUndef = 1, OpConstantTrue = 41, OpConstantFalse = 42, OpConstantNull = 46, OpVectorExtractDynamic = 77,
   OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
+  OpFRem = 140, OpFMod = 141, OpAny = 154, OpAll = 155, OpBitReverse = 204, OpBitCount = 205,
 };
 enum : uint32_t
 {
@@ -73,6 +74,10 @@ enum : uint32_t
   G_Fract = 10, G_Radians = 11, G_Degrees = 12, G_UMin = 38, G_SMin = 39, G_UMax = 41, G_SMax = 42,
   G_UClamp = 44, G_SClamp = 45, G_Step = 48, G_SmoothStep = 49, G_Fma = 50, G_Distance = 67, G_FaceForward = 70,
   G_Refract = 72,
+  G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81,
+  // extended mode, approximate like Sin/Cos/Pow (the oracle calls libm; covered by the 1-LSB colour bar)
+  G_Tan = 15, G_Asin = 16, G_Acos = 17, G_Atan = 18, G_Sinh = 19, G_Cosh = 20, G_Tanh = 21, G_Atan2 = 25,
+  G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30,
 };
 
 // Extended mode (option "extended_spirv"): a handful of opcodes the reference asserts on (SURVEY.md
@@ -499,7 +504,8 @@ struct Module
             case OpUGreaterThanEqual: case OpSGreaterThanEqual: case OpULessThan: case OpULessThanEqual:
             case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
             case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
-            case OpCompositeInsert: case OpCopyObject:
+            case OpCompositeInsert: case OpCopyObject: case OpFRem: case OpFMod: case OpAny: case OpAll:
+            case OpBitReverse: case OpBitCount:
               if(!g_extendedSpirv)
                 fail("Unhandled SPIR-V opcode %u", op);    // :1888
               valtype[id(p[2])] = id(p[1]);
@@ -894,6 +900,38 @@ struct Emitter
     std::string d = R();
     line("sqrt.rn.f32 %s, %s;", d.c_str(), a.c_str());
     return d;
+  }
+  std::string f1(const char *op, const std::string &a)
+  {
+    std::string d = R();
+    line("%s %s, %s;", op, d.c_str(), a.c_str());
+    return d;
+  }
+  // e^x = 2^(x * log2 e) on the special-function unit
+  std::string fexp(const std::string &a) { return f1("ex2.approx.f32", fmul(a, fimm(1.4426950408889634f))); }
+  // atan2(y, x): q = min(|x|, |y|) / max(|x|, |y|) in [0, 1], atan q = q * P(q^2) (degree 7 in q^2, 1.7e-7
+  // absolute), then the octant, the half plane and y's sign; atan2(0, 0) = 0
+  std::string fatan2(const std::string &y, const std::string &x)
+  {
+    static const float kC[8] = {0.9999998807907104f, -0.33331960439682007f, 0.19969235360622406f, -0.14016585052013397f,
+                                0.09906096756458282f, -0.0593671016395092f, 0.02416618913412094f, -0.004668773151934147f};
+    std::string ax = f1("abs.f32", x), ay = f1("abs.f32", y);
+    std::string mx = f2("max.f32", ax, ay), mn = f2("min.f32", ax, ay);
+    std::string pz = P(), q0 = fdiv(mn, mx), q = R();
+    line("setp.eq.f32 %s, %s, %s;", pz.c_str(), mx.c_str(), fimm(0.0f).c_str());
+    line("selp.b32 %s, %s, %s, %s;", q.c_str(), fimm(0.0f).c_str(), q0.c_str(), pz.c_str());
+    std::string t = fmul(q, q), acc = fimm(kC[7]);
+    for(int i = 6; i >= 0; i--)
+      acc = fadd(fmul(acc, t), fimm(kC[i]));
+    std::string r = fmul(acc, q);
+    std::string ps = P(), r1 = R(), pn = P(), r2 = R(), py = P(), r3 = R();
+    line("setp.gt.f32 %s, %s, %s;", ps.c_str(), ay.c_str(), ax.c_str());
+    line("selp.b32 %s, %s, %s, %s;", r1.c_str(), fsub(fimm(1.5707963267948966f), r).c_str(), r.c_str(), ps.c_str());
+    line("setp.lt.f32 %s, %s, %s;", pn.c_str(), x.c_str(), fimm(0.0f).c_str());
+    line("selp.b32 %s, %s, %s, %s;", r2.c_str(), fsub(fimm(3.141592653589793f), r1).c_str(), r1.c_str(), pn.c_str());
+    line("setp.lt.f32 %s, %s, %s;", py.c_str(), y.c_str(), fimm(0.0f).c_str());
+    line("selp.b32 %s, %s, %s, %s;", r3.c_str(), f1("neg.f32", r2).c_str(), r2.c_str(), py.c_str());
+    return r3;
   }
   // CreateDot (:629-643): ((a0*b0 + a1*b1) + a2*b2) + a3*b3
   std::string dot(const std::vector<std::string> &a, const std::vector<std::string> &b, uint32_t n)
@@ -1387,6 +1425,52 @@ struct Emitter
             line("setp.eq.f32 %s, %s, 0f7F800000;", p.c_str(), ab.c_str());
           }
           v.r.push_back(p);
+        }
+        break;
+      }
+      case OpFRem: case OpFMod:    // x - y * trunc(x / y) and x - y * floor(x / y), every step rounded on its own
+      {
+        std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
+        if(a.size() != b.size())
+          fail("float operand shapes differ");
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          std::string q = fdiv(a[i], b[i]), t = R();
+          line("%s %s, %s;", op == OpFRem ? "cvt.rzi.f32.f32" : "cvt.rmi.f32.f32", t.c_str(), q.c_str());
+          v.r.push_back(fsub(a[i], fmul(b[i], t)));
+        }
+        break;
+      }
+      case OpAny: case OpAll:
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        std::string acc = a[0];
+        for(size_t i = 1; i < a.size(); i++)
+        {
+          std::string p = P();
+          line("%s %s, %s, %s;", op == OpAny ? "or.pred" : "and.pred", p.c_str(), acc.c_str(), a[i].c_str());
+          acc = p;
+        }
+        if(a.size() == 1)    // a fresh name, like every other result
+        {
+          std::string p = P();
+          line("mov.pred %s, %s;", p.c_str(), acc.c_str());
+          acc = p;
+        }
+        v.r.push_back(acc);
+        break;
+      }
+      case OpBitReverse: case OpBitCount:
+      {
+        std::vector<std::string> a = regs(w[3]);
+        Value &v = def(w[2], w[1]);
+        for(auto &x : a)
+        {
+          std::string d = R();
+          line("%s %s, %s;", op == OpBitReverse ? "brev.b32" : "popc.b32", d.c_str(), x.c_str());
+          v.r.push_back(d);
         }
         break;
       }
@@ -2092,6 +2176,98 @@ struct Emitter
         }
         break;
       }
+      case G_FindILsb:    // index of the lowest set bit, -1 for 0
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string rv = R(), z = R(), pp = P(), d = R();
+          line("brev.b32 %s, %s;", rv.c_str(), A(0)[c].c_str());
+          line("clz.b32 %s, %s;", z.c_str(), rv.c_str());
+          line("setp.eq.s32 %s, %s, 0;", pp.c_str(), A(0)[c].c_str());
+          line("selp.b32 %s, -1, %s, %s;", d.c_str(), z.c_str(), pp.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      case G_FindSMsb: case G_FindUMsb:    // bfind: -1 when there is no such bit (0; for the signed form also -1)
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string d = R();
+          line("%s %s, %s;", w[4] == G_FindSMsb ? "bfind.s32" : "bfind.u32", d.c_str(), A(0)[c].c_str());
+          v.r.push_back(d);
+        }
+        break;
+      case G_NMin: case G_NMax: case G_NClamp:    // a NaN operand yields the other one; NClamp = NMin(NMax(x, lo), hi)
+      {
+        needExt(w[4]);
+        auto nsel = [&](bool isMin, const std::string &x, const std::string &y) {
+          // isnan(x) ? y : isnan(y) ? x : (y < x [min] / y > x [max]) ? y : x
+          std::string px = P(), py = P(), pc = P(), t = R(), u = R(), d = R();
+          line("setp.nan.f32 %s, %s, %s;", px.c_str(), x.c_str(), x.c_str());
+          line("setp.nan.f32 %s, %s, %s;", py.c_str(), y.c_str(), y.c_str());
+          line("%s %s, %s, %s;", isMin ? "setp.lt.f32" : "setp.gt.f32", pc.c_str(), y.c_str(), x.c_str());
+          line("selp.b32 %s, %s, %s, %s;", t.c_str(), y.c_str(), x.c_str(), pc.c_str());
+          line("selp.b32 %s, %s, %s, %s;", u.c_str(), x.c_str(), t.c_str(), py.c_str());
+          line("selp.b32 %s, %s, %s, %s;", d.c_str(), y.c_str(), u.c_str(), px.c_str());
+          return d;
+        };
+        for(uint32_t c = 0; c < k; c++)
+        {
+          if(w[4] == G_NClamp)
+            v.r.push_back(nsel(true, nsel(false, A(0)[c], A(1)[c]), A(2)[c]));
+          else
+            v.r.push_back(nsel(w[4] == G_NMin, A(0)[c], A(1)[c]));
+        }
+        break;
+      }
+      // ---- transcendental functions: the special-function unit's approximations (2^-22-ish), as Sin/Cos/Pow
+      case G_Exp: case G_Exp2: case G_Log: case G_Log2:
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+          v.r.push_back(w[4] == G_Exp ? fexp(A(0)[c]) : w[4] == G_Exp2 ? f1("ex2.approx.f32", A(0)[c])
+                        : w[4] == G_Log2 ? f1("lg2.approx.f32", A(0)[c])
+                                         : fmul(f1("lg2.approx.f32", A(0)[c]), fimm(0.6931471805599453f)));
+        break;
+      case G_Tan:
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+          v.r.push_back(fdiv(f1("sin.approx.f32", A(0)[c]), f1("cos.approx.f32", A(0)[c])));
+        break;
+      case G_Sinh: case G_Cosh:    // (e^x -/+ e^-x) / 2
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string e = fexp(A(0)[c]), ei = fdiv(fimm(1.0f), e);
+          v.r.push_back(fmul(w[4] == G_Sinh ? fsub(e, ei) : fadd(e, ei), fimm(0.5f)));
+        }
+        break;
+      case G_Tanh:    // (e^2x - 1) / (e^2x + 1); beyond |x| = 9 the quotient is 1 in single precision
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string lim = f2("max.f32", f2("min.f32", A(0)[c], fimm(9.0f)), fimm(-9.0f));
+          std::string e2 = fexp(fadd(lim, lim));
+          v.r.push_back(fdiv(fsub(e2, fimm(1.0f)), fadd(e2, fimm(1.0f))));
+        }
+        break;
+      case G_Atan:
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+          v.r.push_back(fatan2(A(0)[c], fimm(1.0f)));
+        break;
+      case G_Atan2:
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+          v.r.push_back(fatan2(A(0)[c], A(1)[c]));
+        break;
+      case G_Asin: case G_Acos:    // atan2(x, sqrt((1 - x)(1 + x))) and atan2(sqrt((1 - x)(1 + x)), x)
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          std::string s = fsqrt(fmul(fsub(fimm(1.0f), A(0)[c]), fadd(fimm(1.0f), A(0)[c])));
+          v.r.push_back(w[4] == G_Asin ? fatan2(A(0)[c], s) : fatan2(s, A(0)[c]));
+        }
+        break;
       default: fail("Unhandled GLSL extended instruction %u", w[4]);    // :1734
     }
     vals[m.id(w[2])] = v;
