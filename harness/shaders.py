@@ -110,8 +110,9 @@ def vs_mvp_uv() -> np.ndarray:
     return _finish(m, VERTEX, f, [pos, uv, ouv, gl])
 
 
-def fs_texture() -> np.ndarray:
-    """sampler2D tex@(0,1); in vec2 uv@0; out = texture(tex, uv)."""
+def fs_texture(explicit_lod: bool = False) -> np.ndarray:
+    """sampler2D tex@(0,1); in vec2 uv@0; out = texture(tex, uv) — or textureLod(tex, uv, 2.0) (extended mode;
+    the level is ignored like everything else about the sampler: mip 0)."""
     m = Module()
     v4, v2 = m.t_fvec(4), m.t_fvec(2)
     tex = m.sampler2d(0, 1, "tex")
@@ -119,7 +120,10 @@ def fs_texture() -> np.ndarray:
     o = m.output(v4, 0, "o")
     f = _main(m)
     s = m.load(m.t_sampled_image(), tex)
-    c = m.inst(Op.ImageSampleImplicitLod, v4, s, m.load(v2, uv))
+    if explicit_lod:
+        c = m.inst(Op.ImageSampleExplicitLod, v4, s, m.load(v2, uv), 0x2, m.const_f(2.0))    # image operands: Lod
+    else:
+        c = m.inst(Op.ImageSampleImplicitLod, v4, s, m.load(v2, uv))
     m.store(o, c)
     return _finish(m, FRAGMENT, f, [uv, o])
 
@@ -416,7 +420,7 @@ EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "
                 "distance3", "faceforward3", "refract3", "int_minmax", "uint_minmax", "int_abs_sign", "phi_loop",
                 "phi_swap", "int_divmod", "uint_divmod", "shifts_bits", "ucvt", "int_cmp", "logic", "isnan_inf",
                 "switch_phi", "consts_copy", "composite_insert", "vec_dynamic", "frem_fmod", "any_all", "bit_ops",
-                "nminmax", "exp_log", "tan_hyp", "atan_asin")
+                "nminmax", "exp_log", "tan_hyp", "atan_asin", "bitfield", "determinant")
 # of those, the ones built on transcendental functions: libm in the oracle, the special-function unit on the GPU,
 # compared under the 1-LSB colour bar like sin / cos / pow
 APPROX_EXT_OPS = ("exp_log", "tan_hyp", "atan_asin")
@@ -807,6 +811,33 @@ def vs_unit(op: str) -> np.ndarray:
         r = m.const_fvec(0.4, 0.4, 0.4, 0.4)
         for val, wgt in terms:
             r = m.inst(Op.FAdd, v4, r, m.inst(Op.FMul, v4, val, m.const_fvec(wgt, wgt, wgt, wgt)))
+    elif op == "bitfield":
+        it = m.t_int(1)
+        sv4 = m.t_vec(it, 4)
+
+        def ints(x, scale, bias):
+            k = m.inst(Op.ConvertFToS, sv4, m.inst(Op.FMul, v4, x, m.const_fvec(scale, scale, scale, scale)))
+            return m.inst(Op.ISub, sv4, k, m.inst(Op.ConvertFToS, sv4, m.const_fvec(bias, bias, bias, bias)))
+
+        def ci(val):
+            return m.inst(Op.ConvertFToS, sv4, m.const_fvec(*([float(val)] * 4)))
+        big, ins = ints(b, 400000.0, 90000.0), ints(c, 4000.0, 900.0)
+        # offset 0..15 from a.x, count 0..16 from c.x: offset + count <= 31; scalars, as the instruction wants them
+        off = m.inst(Op.BitwiseAnd, it, m.inst(Op.ConvertFToS, it, m.inst(Op.FMul, fl, m.ext(fl, GLSL.FAbs, ax), m.const_f(97.0))),
+                     m.const_i(15))
+        cnt = m.inst(Op.ConvertFToS, it, m.inst(Op.FMul, fl, m.extract(fl, c, 0), m.const_f(16.9)))
+        x = m.inst(Op.BitFieldSExtract, sv4, big, off, cnt)
+        x = m.inst(Op.IAdd, sv4, x, m.inst(Op.IMul, sv4, m.inst(Op.BitFieldUExtract, sv4, big, off, cnt), ci(3)))
+        x = m.inst(Op.IAdd, sv4, x, m.inst(Op.ShiftRightArithmetic, sv4, m.inst(Op.BitFieldInsert, sv4, big, ins, off, cnt), ci(5)))
+        x = m.inst(Op.BitwiseAnd, sv4, x, ci(255))
+        r = m.inst(Op.FMul, v4, m.inst(Op.ConvertSToF, v4, x), m.const_fvec(1 / 256.0, 1 / 256.0, 1 / 256.0, 1 / 256.0))
+    elif op == "determinant":
+        mat3 = m.t_mat(3)
+        c3 = m.shuffle(v3, c, c, 0, 1, 2)
+        M3 = m.construct(mat3, a3, b3, c3)
+        d4m, d4n, d3 = m.ext(fl, GLSL.Determinant, M), m.ext(fl, GLSL.Determinant, N), m.ext(fl, GLSL.Determinant, M3)
+        r = m.inst(Op.FAdd, v4, m.const_fvec(0.5, 0.5, 0.5, 0.5),
+                   m.inst(Op.FMul, v4, m.construct(v4, d4m, d4n, d3, m.inst(Op.FAdd, fl, d4m, d3)), m.const_fvec(8.0, 8.0, 0.4, 0.4)))
     elif op == "fabs":
         r = m.ext(v4, GLSL.FAbs, a)
     elif op == "floor":

@@ -18,6 +18,10 @@ VERSION_1_0 = 0x00010000
 
 class Op:
     Nop = 0
+    ImageSampleExplicitLod = 88
+    BitFieldInsert = 201
+    BitFieldSExtract = 202
+    BitFieldUExtract = 203
     FRem = 140
     FMod = 141
     Any = 154
@@ -172,6 +176,7 @@ class BuiltIn:
 
 
 class GLSL:
+    Determinant = 33
     Tan = 15
     Asin = 16
     Acos = 17

@@ -61,6 +61,7 @@ enum Op : uint16_t
   OpNop = 0, OpUndef = 1, OpConstantTrue = 41, OpConstantFalse = 42, OpConstantNull = 46, OpVectorExtractDynamic = 77,
   OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
   OpFRem = 140, OpFMod = 141, OpAny = 154, OpAll = 155, OpBitReverse = 204, OpBitCount = 205,
+  OpImageSampleExplicitLod = 88, OpBitFieldInsert = 201, OpBitFieldSExtract = 202, OpBitFieldUExtract = 203,
   OpIAdd = 128, OpFAdd = 129, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136,
   OpVectorTimesScalar = 142, OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144,
   OpMatrixTimesVector = 145, OpMatrixTimesMatrix = 146, OpDot = 148, OpIEqual = 170,
@@ -87,7 +88,7 @@ enum : uint32_t
   G_Fract = 10, G_Radians = 11, G_Degrees = 12, G_UMin = 38, G_SMin = 39, G_UMax = 41, G_SMax = 42,
   G_UClamp = 44, G_SClamp = 45, G_Step = 48, G_SmoothStep = 49, G_Fma = 50, G_Distance = 67, G_FaceForward = 70,
   G_Refract = 72,
-  G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81,
+  G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81, G_Determinant = 33,
   // extended mode, libm here and the special-function unit on the GPU (as Sin/Cos/Pow): 1-LSB colour bar
   G_Tan = 15, G_Asin = 16, G_Acos = 17, G_Atan = 18, G_Sinh = 19, G_Cosh = 20, G_Tanh = 21, G_Atan2 = 25,
   G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30,
@@ -637,6 +638,7 @@ static void parse(Module &m)
             case OpUGreaterThanEqual: case OpSGreaterThanEqual: case OpULessThan: case OpULessThanEqual:
             case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
             case OpFRem: case OpFMod: case OpAny: case OpAll: case OpBitReverse: case OpBitCount:
+            case OpImageSampleExplicitLod: case OpBitFieldInsert: case OpBitFieldSExtract: case OpBitFieldUExtract:
             case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
             case OpCompositeInsert: case OpCopyObject:
               if(!g_extended)
@@ -1084,6 +1086,30 @@ struct Interp
           V[w[2]].u[0] = acc;
           break;
         }
+        case OpBitFieldSExtract:    // base, offset, count; offset + count <= 32 (anything else is undefined in SPIR-V)
+        case OpBitFieldUExtract:
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            const uint32_t off = V[w[4]].u[0] & 31u, cnt = V[w[5]].u[0];
+            uint32_t x = 0;
+            if(cnt)
+            {
+              const uint32_t mask = cnt >= 32u ? 0xffffffffu : (1u << cnt) - 1u;
+              x = (V[w[3]].u[c] >> off) & mask;
+              if(op == OpBitFieldSExtract && cnt < 32u && (x >> (cnt - 1u)) & 1u)
+                x |= ~mask;
+            }
+            V[w[2]].u[c] = x;
+          }
+          break;
+        case OpBitFieldInsert:    // base, insert, offset, count
+          for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
+          {
+            const uint32_t off = V[w[5]].u[0] & 31u, cnt = V[w[6]].u[0];
+            const uint32_t mask = (cnt >= 32u ? 0xffffffffu : (1u << cnt) - 1u) << off;
+            V[w[2]].u[c] = (V[w[3]].u[c] & ~mask) | ((V[w[4]].u[c] << off) & mask);
+          }
+          break;
         case OpBitCount:
           for(uint32_t c = 0, k = comps(m, w[1]); c < k; c++)
             V[w[2]].u[c] = (uint32_t)__builtin_popcount(V[w[3]].u[c]);
@@ -1337,6 +1363,7 @@ struct Interp
           break;
         }
         // ---- texture (:1842-1886)
+        case OpImageSampleExplicitLod:    // extended mode: the Lod operand is ignored (mip 0, like every sample)
         case OpImageSampleImplicitLod:
         {
           Val r;
@@ -1543,6 +1570,48 @@ struct Interp
                                     : nsel(w[4] == G_NMin, ARG(0).f[c], ARG(1).f[c]);
         break;
       }
+      case G_Determinant:    // cofactors along row 0; every product and sum rounded on its own, left to right
+      {
+        const Type &mt = m.types[m.valtype[w[5]]];
+        const uint32_t n = mt.count;
+        const float *a = ARG(0).f;    // a[col * 4 + row] for 3x3 and 4x4 alike
+        auto e = [&](uint32_t rr, uint32_t cc) { return a[cc * 4 + rr]; };
+        auto det3 = [&](const uint32_t *rw, const uint32_t *cl) {
+          float p, q2;
+          p = e(rw[1], cl[1]) * e(rw[2], cl[2]); q2 = e(rw[2], cl[1]) * e(rw[1], cl[2]);
+          const float m0 = p - q2;
+          p = e(rw[1], cl[0]) * e(rw[2], cl[2]); q2 = e(rw[2], cl[0]) * e(rw[1], cl[2]);
+          const float m1 = p - q2;
+          p = e(rw[1], cl[0]) * e(rw[2], cl[1]); q2 = e(rw[2], cl[0]) * e(rw[1], cl[1]);
+          const float m2 = p - q2;
+          float d = e(rw[0], cl[0]) * m0;
+          p = e(rw[0], cl[1]) * m1;
+          d = d - p;
+          p = e(rw[0], cl[2]) * m2;
+          return d + p;
+        };
+        if(n == 3)
+        {
+          const uint32_t rw[3] = {0, 1, 2}, cl[3] = {0, 1, 2};
+          r.f[0] = det3(rw, cl);
+        }
+        else
+        {
+          const uint32_t rw[3] = {1, 2, 3};
+          float d = 0.0f;
+          for(uint32_t j = 0; j < 4; j++)
+          {
+            uint32_t cl[3], q = 0;
+            for(uint32_t cc = 0; cc < 4; cc++)
+              if(cc != j)
+                cl[q++] = cc;
+            const float t = e(0, j) * det3(rw, cl);
+            d = j == 0 ? t : (j & 1u) ? d - t : d + t;
+          }
+          r.f[0] = d;
+        }
+        break;
+      }
       // transcendental functions: libm (the GPU uses its special-function unit; neither is the reference's CRT)
 #define VOR_LIBM1(G, fn) \
       case G: \
@@ -1623,6 +1692,15 @@ static void validateExt(const Module &m)
             if(!g_extended)
               FAIL("Unhandled GLSL extended instruction %u", w[4]);    // :1734
             break;
+          case G_Determinant:
+          {
+            if(!g_extended)
+              FAIL("Unhandled GLSL extended instruction %u", w[4]);    // :1734
+            const Type &mt = m.types[m.valtype[w[5]]];
+            if(mt.kind != T_MAT || (mt.count != 3 && mt.count != 4))
+              FAIL("Determinant of 3x3 and 4x4 matrices only");
+            break;
+          }
           case G_InverseSqrt:
             if(m.types[w[1]].kind == T_VEC)
               FAIL("vector InverseSqrt crashes the reference (:1619)");

@@ -190,6 +190,27 @@ def test_discard_in_the_fragment_shader(gpu, vor, variant):
         oset(b"extended_spirv", 0)
 
 
+def test_sample_with_explicit_lod(gpu, vor):
+    """extended mode, OpImageSampleExplicitLod (textureLod): the level is ignored — the sampler reads mip 0 for
+    every instruction, as the reference's does — so the frame equals the one OpImageSampleImplicitLod gives"""
+    from harness import shaders
+    gset, oset = gpu.lib.vb200_set_option, vor.lib.vor_set_option
+    gset.argtypes = oset.argtypes = [C.c_char_p, C.c_int64]
+    with pytest.raises(abi.BackendError):
+        gpu.CompileFunction(shaders.fs_texture(True))
+    assert gset(b"extended_spirv", 1) == 0 and oset(b"extended_spirv", 1) == 0
+    try:
+        sc = scenes.c2_cube(480, 270, tex_size=64)
+        sc.draws[0].pipe.fs = shaders.fs_texture(True)
+        _check(gpu, vor, sc)
+        want, _ = scenes.render(gpu, scenes.c2_cube(480, 270, tex_size=64))
+        got, _ = scenes.render(gpu, sc)
+        assert np.array_equal(got, want)
+    finally:
+        gset(b"extended_spirv", 0)
+        oset(b"extended_spirv", 0)
+
+
 def test_resolve_without_slot_keys(gpu, vor):
     """draws with >= 2^24 triangles cannot carry the record slot in the visibility key; the option forces
     that code path (phase B gathers the winner from global memory) on ordinary scenes"""

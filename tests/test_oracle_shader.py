@@ -386,6 +386,47 @@ def _expected_ext(op, a, b, c):
         q = f32(0.25)
         return (((t1 * q).astype(f32) + (t2 * q).astype(f32)).astype(f32)
                 + ((t3 * q).astype(f32) + (t4 * f32(0.125)).astype(f32)).astype(f32)).astype(f32)
+    if op == "bitfield":
+        def ints(x, scale, bias):
+            return (np.trunc((x * f32(scale)).astype(f32)).astype(np.int64) - bias).astype(np.int32)
+        big, ins = ints(b, 400000.0, 90000), ints(c, 4000.0, 900)
+        off = int(np.trunc(f32(np.abs(a[0]) * f32(97.0)))) & 15
+        cnt = int(np.trunc(f32(c[0] * f32(16.9))))
+        mask = (1 << cnt) - 1
+        out = []
+        for k in range(4):
+            ub, ui = int(big[k]) & 0xffffffff, int(ins[k]) & 0xffffffff
+            ux = (ub >> off) & mask
+            sx = ux - (1 << cnt) if cnt and (ux >> (cnt - 1)) & 1 else ux
+            inserted = (ub & ~(mask << off) & 0xffffffff) | ((ui << off) & (mask << off) & 0xffffffff)
+            if inserted & 0x80000000:
+                inserted -= 1 << 32
+            x = sx + 3 * ux + (inserted >> 5)
+            out.append(f32(x & 255) * f32(1 / 256.0))
+        return np.array(out, f32)
+    if op == "determinant":
+        M = np.array(_UBO_FOR_EXT[:16], f32).reshape(4, 4)     # [col][row]
+        N = np.array(_UBO_FOR_EXT[16:32], f32).reshape(4, 4)
+        M3 = np.array([a[:3], b[:3], c[:3]], f32)              # columns a, b, c
+        def det3(e, rw, cl):
+            m0 = f32(f32(e(rw[1], cl[1]) * e(rw[2], cl[2])) - f32(e(rw[2], cl[1]) * e(rw[1], cl[2])))
+            m1 = f32(f32(e(rw[1], cl[0]) * e(rw[2], cl[2])) - f32(e(rw[2], cl[0]) * e(rw[1], cl[2])))
+            m2 = f32(f32(e(rw[1], cl[0]) * e(rw[2], cl[1])) - f32(e(rw[2], cl[0]) * e(rw[1], cl[1])))
+            d = f32(e(rw[0], cl[0]) * m0)
+            d = f32(d - f32(e(rw[0], cl[1]) * m1))
+            return f32(d + f32(e(rw[0], cl[2]) * m2))
+        def det4(mat):
+            e = lambda r_, c_: mat[c_][r_]
+            d = None
+            for j in range(4):
+                cl = [c_ for c_ in range(4) if c_ != j]
+                t = f32(e(0, j) * det3(e, (1, 2, 3), cl))
+                d = t if j == 0 else (f32(d - t) if j & 1 else f32(d + t))
+            return d
+        d4m, d4n = det4(M), det4(N)
+        d3 = det3(lambda r_, c_: M3[c_][r_], (0, 1, 2), (0, 1, 2))
+        v = np.array([d4m, d4n, d3, f32(d4m + d3)], f32)
+        return (f32(0.5) + (v * np.array([8.0, 8.0, 0.4, 0.4], f32)).astype(f32)).astype(f32)
     if op in ("exp_log", "tan_hyp", "atan_asin"):    # approximate: compared with allclose by the caller
         if op == "exp_log":
             t = (np.abs(b) + f32(0.5)).astype(f32)
@@ -446,6 +487,26 @@ def test_extended_op_rejected_by_default_and_matches_numpy_when_enabled(vor, op)
                 continue
             assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), (op, i, got, exp)
         vor.DestroyFunction(mod)
+    finally:
+        setopt(b"extended_spirv", 0)
+
+
+def test_explicit_lod_sample_equals_implicit(vor):
+    """extended mode: OpImageSampleExplicitLod ignores its Lod operand (mip 0, like every sample of the
+    reference's sampler), refused by default like any opcode outside Appendix B"""
+    from harness import scenes
+    setopt = vor.lib.vor_set_option
+    setopt.argtypes = [C.c_char_p, C.c_int64]
+    with pytest.raises(abi.BackendError):
+        vor.CompileFunction(shaders.fs_texture(True))
+    assert setopt(b"extended_spirv", 1) == 0
+    try:
+        sc = scenes.c2_cube(160, 100, tex_size=32)
+        sc.draws[0].pipe.fs = shaders.fs_texture(True)
+        got, gd = scenes.render(vor, sc)
+        want, wd = scenes.render(vor, scenes.c2_cube(160, 100, tex_size=32))
+        assert np.array_equal(got, want) and np.array_equal(gd, wd)
+        assert (got != 0xCD).any()
     finally:
         setopt(b"extended_spirv", 0)
 

@@ -58,6 +58,7 @@ enum : uint32_t
   OpNop = 0, OpUndef = 1, OpConstantTrue = 41, OpConstantFalse = 42, OpConstantNull = 46, OpVectorExtractDynamic = 77,
   OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
   OpFRem = 140, OpFMod = 141, OpAny = 154, OpAll = 155, OpBitReverse = 204, OpBitCount = 205,
+  OpImageSampleExplicitLod = 88, OpBitFieldInsert = 201, OpBitFieldSExtract = 202, OpBitFieldUExtract = 203,
 };
 enum : uint32_t
 {
@@ -74,7 +75,7 @@ enum : uint32_t
   G_Fract = 10, G_Radians = 11, G_Degrees = 12, G_UMin = 38, G_SMin = 39, G_UMax = 41, G_SMax = 42,
   G_UClamp = 44, G_SClamp = 45, G_Step = 48, G_SmoothStep = 49, G_Fma = 50, G_Distance = 67, G_FaceForward = 70,
   G_Refract = 72,
-  G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81,
+  G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81, G_Determinant = 33,
   // extended mode, approximate like Sin/Cos/Pow (the oracle calls libm; covered by the 1-LSB colour bar)
   G_Tan = 15, G_Asin = 16, G_Acos = 17, G_Atan = 18, G_Sinh = 19, G_Cosh = 20, G_Tanh = 21, G_Atan2 = 25,
   G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30,
@@ -505,7 +506,8 @@ struct Module
             case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
             case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
             case OpCompositeInsert: case OpCopyObject: case OpFRem: case OpFMod: case OpAny: case OpAll:
-            case OpBitReverse: case OpBitCount:
+            case OpBitReverse: case OpBitCount: case OpImageSampleExplicitLod: case OpBitFieldInsert:
+            case OpBitFieldSExtract: case OpBitFieldUExtract:
               if(!g_extendedSpirv)
                 fail("Unhandled SPIR-V opcode %u", op);    // :1888
               valtype[id(p[2])] = id(p[1]);
@@ -1462,6 +1464,35 @@ struct Emitter
         v.r.push_back(acc);
         break;
       }
+      case OpBitFieldSExtract: case OpBitFieldUExtract:    // base, offset, count (scalars for a vector base too)
+      {
+        std::vector<std::string> a = regs(w[3]);
+        const std::string off = regs(w[4], 1)[0], cnt = regs(w[5], 1)[0];
+        Value &v = def(w[2], w[1]);
+        for(auto &x : a)
+        {
+          std::string d = R();
+          line("%s %s, %s, %s, %s;", op == OpBitFieldSExtract ? "bfe.s32" : "bfe.u32", d.c_str(), x.c_str(), off.c_str(),
+               cnt.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
+      case OpBitFieldInsert:    // base, insert, offset, count
+      {
+        std::vector<std::string> a = regs(w[3]), b = regs(w[4]);
+        if(a.size() != b.size())
+          fail("integer operand shapes differ");
+        const std::string off = regs(w[5], 1)[0], cnt = regs(w[6], 1)[0];
+        Value &v = def(w[2], w[1]);
+        for(size_t i = 0; i < a.size(); i++)
+        {
+          std::string d = R();
+          line("bfi.b32 %s, %s, %s, %s, %s;", d.c_str(), b[i].c_str(), a[i].c_str(), off.c_str(), cnt.c_str());
+          v.r.push_back(d);
+        }
+        break;
+      }
       case OpBitReverse: case OpBitCount:
       {
         std::vector<std::string> a = regs(w[3]);
@@ -1883,6 +1914,7 @@ struct Emitter
         break;
       }
       // ---- texture (:1842-1886)
+      case OpImageSampleExplicitLod:    // extended mode: the Lod operand is ignored, the sampler reads mip 0 anyway
       case OpImageSampleImplicitLod:
       {
         const Value &img = use(w[3]);
@@ -2217,6 +2249,45 @@ struct Emitter
             v.r.push_back(nsel(true, nsel(false, A(0)[c], A(1)[c]), A(2)[c]));
           else
             v.r.push_back(nsel(w[4] == G_NMin, A(0)[c], A(1)[c]));
+        }
+        break;
+      }
+      case G_Determinant:    // cofactors along row 0; every product and sum rounded on its own, left to right
+      {
+        needExt(w[4]);
+        const std::vector<std::string> &a = A(0);
+        const uint32_t n = a.size() == 9 ? 3u : a.size() == 16 ? 4u : 0u;
+        if(!n)
+          fail("Determinant of 3x3 and 4x4 matrices only");
+        auto e = [&](uint32_t r, uint32_t c) -> const std::string & { return a[c * n + r]; };
+        // rows r0 < r1 < r2, columns c0 < c1 < c2
+        auto det3 = [&](const uint32_t *rw, const uint32_t *cl) {
+          std::string m0 = fsub(fmul(e(rw[1], cl[1]), e(rw[2], cl[2])), fmul(e(rw[2], cl[1]), e(rw[1], cl[2])));
+          std::string m1 = fsub(fmul(e(rw[1], cl[0]), e(rw[2], cl[2])), fmul(e(rw[2], cl[0]), e(rw[1], cl[2])));
+          std::string m2 = fsub(fmul(e(rw[1], cl[0]), e(rw[2], cl[1])), fmul(e(rw[2], cl[0]), e(rw[1], cl[1])));
+          std::string d = fmul(e(rw[0], cl[0]), m0);
+          d = fsub(d, fmul(e(rw[0], cl[1]), m1));
+          return fadd(d, fmul(e(rw[0], cl[2]), m2));
+        };
+        if(n == 3)
+        {
+          const uint32_t rw[3] = {0, 1, 2}, cl[3] = {0, 1, 2};
+          v.r.push_back(det3(rw, cl));
+        }
+        else
+        {
+          const uint32_t rw[3] = {1, 2, 3};
+          std::string d;
+          for(uint32_t j = 0; j < 4; j++)
+          {
+            uint32_t cl[3], q = 0;
+            for(uint32_t c = 0; c < 4; c++)
+              if(c != j)
+                cl[q++] = c;
+            std::string t = fmul(e(0, j), det3(rw, cl));
+            d = j == 0 ? t : (j & 1u) ? fsub(d, t) : fadd(d, t);
+          }
+          v.r.push_back(d);
         }
         break;
       }
