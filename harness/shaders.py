@@ -420,10 +420,10 @@ EXT_UNIT_OPS = ("select", "fge", "feq", "fne", "isub_bitcast", "ftos", "fabs", "
                 "distance3", "faceforward3", "refract3", "int_minmax", "uint_minmax", "int_abs_sign", "phi_loop",
                 "phi_swap", "int_divmod", "uint_divmod", "shifts_bits", "ucvt", "int_cmp", "logic", "isnan_inf",
                 "switch_phi", "consts_copy", "composite_insert", "vec_dynamic", "frem_fmod", "any_all", "bit_ops",
-                "nminmax", "exp_log", "tan_hyp", "atan_asin", "bitfield", "determinant")
+                "nminmax", "exp_log", "tan_hyp", "atan_asin", "bitfield", "determinant", "funord", "inv_hyp")
 # of those, the ones built on transcendental functions: libm in the oracle, the special-function unit on the GPU,
 # compared under the 1-LSB colour bar like sin / cos / pow
-APPROX_EXT_OPS = ("exp_log", "tan_hyp", "atan_asin")
+APPROX_EXT_OPS = ("exp_log", "tan_hyp", "atan_asin", "inv_hyp")
 
 
 def vs_unit(op: str) -> np.ndarray:
@@ -838,6 +838,26 @@ def vs_unit(op: str) -> np.ndarray:
         d4m, d4n, d3 = m.ext(fl, GLSL.Determinant, M), m.ext(fl, GLSL.Determinant, N), m.ext(fl, GLSL.Determinant, M3)
         r = m.inst(Op.FAdd, v4, m.const_fvec(0.5, 0.5, 0.5, 0.5),
                    m.inst(Op.FMul, v4, m.construct(v4, d4m, d4n, d3, m.inst(Op.FAdd, fl, d4m, d3)), m.const_fvec(8.0, 8.0, 0.4, 0.4)))
+    elif op == "funord":
+        # the six unordered comparisons of (NaN, b.y, b.z, b.w) with c (c == b on every third vertex), as bit weights
+        bv4 = m.t_vec(m.t_bool(), 4)
+        zero = m.inst(Op.FSub, v4, a, a)
+        nan = m.inst(Op.FDiv, v4, zero, zero)
+        probe = m.shuffle(v4, nan, b, 0, 5, 6, 7)
+        r = m.const_fvec(0.0, 0.0, 0.0, 0.0)
+        for k, cmp in enumerate((Op.FUnordEqual, Op.FUnordNotEqual, Op.FUnordLessThan, Op.FUnordGreaterThan,
+                                 Op.FUnordLessThanEqual, Op.FUnordGreaterThanEqual)):
+            wgt = 2.0 ** -(k + 1)
+            r = m.inst(Op.FAdd, v4, r, m.inst(Op.Select, v4, m.inst(cmp, bv4, probe, c), m.const_fvec(wgt, wgt, wgt, wgt),
+                                              m.const_fvec(0.0, 0.0, 0.0, 0.0)))
+    elif op == "inv_hyp":
+        t = m.ext(v4, GLSL.Fract, b)    # [0, 1)
+        terms = ((m.ext(v4, GLSL.Asinh, m.inst(Op.FMul, v4, b, m.const_fvec(2.0, 2.0, 2.0, 2.0))), 0.1),
+                 (m.ext(v4, GLSL.Acosh, m.inst(Op.FAdd, v4, t, m.const_fvec(1.25, 1.25, 1.25, 1.25))), 0.2),
+                 (m.ext(v4, GLSL.Atanh, m.inst(Op.FMul, v4, t, m.const_fvec(0.9, 0.9, 0.9, 0.9))), 0.15))
+        r = m.const_fvec(0.35, 0.35, 0.35, 0.35)
+        for val, wgt in terms:
+            r = m.inst(Op.FAdd, v4, r, m.inst(Op.FMul, v4, val, m.const_fvec(wgt, wgt, wgt, wgt)))
     elif op == "fabs":
         r = m.ext(v4, GLSL.FAbs, a)
     elif op == "floor":

@@ -18,6 +18,12 @@ VERSION_1_0 = 0x00010000
 
 class Op:
     Nop = 0
+    FUnordEqual = 181
+    FUnordNotEqual = 183
+    FUnordLessThan = 185
+    FUnordGreaterThan = 187
+    FUnordLessThanEqual = 189
+    FUnordGreaterThanEqual = 191
     ImageSampleExplicitLod = 88
     BitFieldInsert = 201
     BitFieldSExtract = 202
@@ -177,6 +183,9 @@ class BuiltIn:
 
 class GLSL:
     Determinant = 33
+    Asinh = 22
+    Acosh = 23
+    Atanh = 24
     Tan = 15
     Asin = 16
     Acos = 17

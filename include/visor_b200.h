@@ -315,8 +315,8 @@ VB200_API const char *vb200_last_tile_kernel(void);
  * on the in-order tile kernel), OpSelect, the remaining float and integer comparisons, integer division /
  * remainder / shifts / bit and logic operations, OpBitcast, OpConvertFToS/FToU/UToF, OpIsNan/OpIsInf, OpCopyObject, OpUndef, OpConstantNull/True/False,
  * OpCompositeInsert, OpVectorExtractDynamic/InsertDynamic, OpFRem/OpFMod, OpAny/OpAll, OpBitCount/OpBitReverse,
- * OpBitFieldInsert/SExtract/UExtract, OpImageSampleExplicitLod (level ignored: mip 0) and 42 GLSL.std.450 instructions (DESIGN.md section 3 lists them, the results fixed where SPIR-V leaves
- * them open and the twelve transcendental ones that are approximate like the reference subset's Sin/Cos/Pow) — off by default, because with it the front end no longer rejects exactly what CompileFunction
+ * OpBitFieldInsert/SExtract/UExtract, OpImageSampleExplicitLod (level ignored: mip 0), the OpFUnord* comparisons and 45 GLSL.std.450 instructions (DESIGN.md section 3 lists them, the results fixed where SPIR-V leaves
+ * them open and the fifteen transcendental ones that are approximate like the reference subset's Sin/Cos/Pow) — off by default, because with it the front end no longer rejects exactly what CompileFunction
  * rejects (spirv_compile.cpp:1734,1888). Unknown names return VB200_ERR_INVALID. */
 VB200_API int vb200_set_option(const char *name, int64_t value);
 

@@ -62,6 +62,8 @@ enum Op : uint16_t
   OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
   OpFRem = 140, OpFMod = 141, OpAny = 154, OpAll = 155, OpBitReverse = 204, OpBitCount = 205,
   OpImageSampleExplicitLod = 88, OpBitFieldInsert = 201, OpBitFieldSExtract = 202, OpBitFieldUExtract = 203,
+  OpFUnordEqual = 181, OpFUnordNotEqual = 183, OpFUnordLessThan = 185, OpFUnordGreaterThan = 187,
+  OpFUnordLessThanEqual = 189, OpFUnordGreaterThanEqual = 191,
   OpIAdd = 128, OpFAdd = 129, OpFSub = 131, OpIMul = 132, OpFMul = 133, OpFDiv = 136,
   OpVectorTimesScalar = 142, OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144,
   OpMatrixTimesVector = 145, OpMatrixTimesMatrix = 146, OpDot = 148, OpIEqual = 170,
@@ -91,7 +93,7 @@ enum : uint32_t
   G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81, G_Determinant = 33,
   // extended mode, libm here and the special-function unit on the GPU (as Sin/Cos/Pow): 1-LSB colour bar
   G_Tan = 15, G_Asin = 16, G_Acos = 17, G_Atan = 18, G_Sinh = 19, G_Cosh = 20, G_Tanh = 21, G_Atan2 = 25,
-  G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30,
+  G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30, G_Asinh = 22, G_Acosh = 23, G_Atanh = 24,
 };
 
 
@@ -639,6 +641,8 @@ static void parse(Module &m)
             case OpSLessThanEqual: case OpShiftRightLogical: case OpShiftRightArithmetic: case OpBitwiseOr:
             case OpFRem: case OpFMod: case OpAny: case OpAll: case OpBitReverse: case OpBitCount:
             case OpImageSampleExplicitLod: case OpBitFieldInsert: case OpBitFieldSExtract: case OpBitFieldUExtract:
+            case OpFUnordEqual: case OpFUnordNotEqual: case OpFUnordLessThan: case OpFUnordGreaterThan:
+            case OpFUnordLessThanEqual: case OpFUnordGreaterThanEqual:
             case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
             case OpCompositeInsert: case OpCopyObject:
               if(!g_extended)
@@ -943,6 +947,22 @@ struct Interp
           for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++)
             V[w[2]].u[c] = V[w[3]].f[c] < V[w[4]].f[c] || V[w[3]].f[c] > V[w[4]].f[c];
           break;
+        // unordered comparisons: true when either operand is NaN, i.e. the negation of the opposite ordered one
+#define VOR_UNORD(OP, ORDERED_OPPOSITE) \
+        case OP: \
+          for(uint32_t c = 0, k = ncomp(w[3]); c < k; c++) \
+          { \
+            const float a = V[w[3]].f[c], b = V[w[4]].f[c]; \
+            V[w[2]].u[c] = !(ORDERED_OPPOSITE); \
+          } \
+          break;
+        VOR_UNORD(OpFUnordEqual, a < b || a > b)
+        VOR_UNORD(OpFUnordNotEqual, a == b)
+        VOR_UNORD(OpFUnordLessThan, a >= b)
+        VOR_UNORD(OpFUnordGreaterThan, a <= b)
+        VOR_UNORD(OpFUnordLessThanEqual, a > b)
+        VOR_UNORD(OpFUnordGreaterThanEqual, a < b)
+#undef VOR_UNORD
         case OpSelect:    // component-wise; a scalar condition selects whole operands
         {
           const uint32_t k = comps(m, w[1]), kc = ncomp(w[3]);
@@ -1621,6 +1641,7 @@ struct Interp
       VOR_LIBM1(G_Exp, expf) VOR_LIBM1(G_Exp2, exp2f) VOR_LIBM1(G_Log, logf) VOR_LIBM1(G_Log2, log2f)
       VOR_LIBM1(G_Tan, tanf) VOR_LIBM1(G_Sinh, sinhf) VOR_LIBM1(G_Cosh, coshf) VOR_LIBM1(G_Tanh, tanhf)
       VOR_LIBM1(G_Atan, atanf) VOR_LIBM1(G_Asin, asinf) VOR_LIBM1(G_Acos, acosf)
+      VOR_LIBM1(G_Asinh, asinhf) VOR_LIBM1(G_Acosh, acoshf) VOR_LIBM1(G_Atanh, atanhf)
 #undef VOR_LIBM1
       case G_Atan2:
         for(uint32_t c = 0; c < k; c++)
@@ -1688,7 +1709,8 @@ static void validateExt(const Module &m)
           case G_SMax: case G_UClamp: case G_SClamp: case G_Step: case G_SmoothStep: case G_Fma: case G_Distance:
           case G_FaceForward: case G_Refract: case G_FindILsb: case G_FindSMsb: case G_FindUMsb: case G_NMin:
           case G_NMax: case G_NClamp: case G_Tan: case G_Asin: case G_Acos: case G_Atan: case G_Sinh: case G_Cosh:
-          case G_Tanh: case G_Atan2: case G_Exp: case G_Log: case G_Exp2: case G_Log2:
+          case G_Tanh: case G_Atan2: case G_Exp: case G_Log: case G_Exp2: case G_Log2: case G_Asinh: case G_Acosh:
+          case G_Atanh:
             if(!g_extended)
               FAIL("Unhandled GLSL extended instruction %u", w[4]);    // :1734
             break;

@@ -427,8 +427,21 @@ def _expected_ext(op, a, b, c):
         d3 = det3(lambda r_, c_: M3[c_][r_], (0, 1, 2), (0, 1, 2))
         v = np.array([d4m, d4n, d3, f32(d4m + d3)], f32)
         return (f32(0.5) + (v * np.array([8.0, 8.0, 0.4, 0.4], f32)).astype(f32)).astype(f32)
-    if op in ("exp_log", "tan_hyp", "atan_asin"):    # approximate: compared with allclose by the caller
-        if op == "exp_log":
+    if op == "funord":
+        probe = np.array([np.nan, b[1], b[2], b[3]], f32)
+        r = np.zeros(4, f32)
+        with np.errstate(invalid="ignore"):
+            tests = (~((probe < c) | (probe > c)), ~(probe == c), ~(probe >= c), ~(probe <= c), ~(probe > c), ~(probe < c))
+        for k, t in enumerate(tests):
+            r = (r + np.where(t, f32(2.0 ** -(k + 1)), f32(0))).astype(f32)
+        return r
+    if op in ("exp_log", "tan_hyp", "atan_asin", "inv_hyp"):    # approximate: compared with allclose by the caller
+        if op == "inv_hyp":
+            t = (b - np.floor(b)).astype(f32)
+            terms = ((np.arcsinh((b * f32(2.0)).astype(f32)), 0.1), (np.arccosh((t + f32(1.25)).astype(f32)), 0.2),
+                     (np.arctanh((t * f32(0.9)).astype(f32)), 0.15))
+            r = np.full(4, 0.35, f32)
+        elif op == "exp_log":
             t = (np.abs(b) + f32(0.5)).astype(f32)
             terms = ((np.exp((b * f32(0.5)).astype(f32)), 0.15), (np.exp2(b), 0.1), (np.log(t), 0.08), (np.log2(t), 0.05))
             r = np.full(4, 0.2, f32)

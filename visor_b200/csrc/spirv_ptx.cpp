@@ -59,6 +59,8 @@ enum : uint32_t
   OpVectorInsertDynamic = 78, OpCompositeInsert = 82, OpCopyObject = 83,
   OpFRem = 140, OpFMod = 141, OpAny = 154, OpAll = 155, OpBitReverse = 204, OpBitCount = 205,
   OpImageSampleExplicitLod = 88, OpBitFieldInsert = 201, OpBitFieldSExtract = 202, OpBitFieldUExtract = 203,
+  OpFUnordEqual = 181, OpFUnordNotEqual = 183, OpFUnordLessThan = 185, OpFUnordGreaterThan = 187,
+  OpFUnordLessThanEqual = 189, OpFUnordGreaterThanEqual = 191,
 };
 enum : uint32_t
 {
@@ -78,7 +80,7 @@ enum : uint32_t
   G_FindILsb = 73, G_FindSMsb = 74, G_FindUMsb = 75, G_NMin = 79, G_NMax = 80, G_NClamp = 81, G_Determinant = 33,
   // extended mode, approximate like Sin/Cos/Pow (the oracle calls libm; covered by the 1-LSB colour bar)
   G_Tan = 15, G_Asin = 16, G_Acos = 17, G_Atan = 18, G_Sinh = 19, G_Cosh = 20, G_Tanh = 21, G_Atan2 = 25,
-  G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30,
+  G_Exp = 27, G_Log = 28, G_Exp2 = 29, G_Log2 = 30, G_Asinh = 22, G_Acosh = 23, G_Atanh = 24,
 };
 
 // Extended mode (option "extended_spirv"): a handful of opcodes the reference asserts on (SURVEY.md
@@ -507,7 +509,8 @@ struct Module
             case OpBitwiseXor: case OpNot: case OpUndef: case OpVectorExtractDynamic: case OpVectorInsertDynamic:
             case OpCompositeInsert: case OpCopyObject: case OpFRem: case OpFMod: case OpAny: case OpAll:
             case OpBitReverse: case OpBitCount: case OpImageSampleExplicitLod: case OpBitFieldInsert:
-            case OpBitFieldSExtract: case OpBitFieldUExtract:
+            case OpBitFieldSExtract: case OpBitFieldUExtract: case OpFUnordEqual: case OpFUnordNotEqual:
+            case OpFUnordLessThan: case OpFUnordGreaterThan: case OpFUnordLessThanEqual: case OpFUnordGreaterThanEqual:
               if(!g_extendedSpirv)
                 fail("Unhandled SPIR-V opcode %u", op);    // :1888
               valtype[id(p[2])] = id(p[1]);
@@ -1250,8 +1253,16 @@ struct Emitter
       case OpFOrdGreaterThanEqual:    // extended mode
       case OpFOrdEqual:
       case OpFOrdNotEqual:
+      case OpFUnordEqual: case OpFUnordNotEqual: case OpFUnordLessThan: case OpFUnordGreaterThan:
+      case OpFUnordLessThanEqual: case OpFUnordGreaterThanEqual:    // unordered: true when an operand is NaN
       {
-        const char *ins = op == OpFOrdLessThan           ? "setp.lt.f32"
+        const char *ins = op == OpFUnordEqual              ? "setp.equ.f32"
+                          : op == OpFUnordNotEqual         ? "setp.neu.f32"
+                          : op == OpFUnordLessThan         ? "setp.ltu.f32"
+                          : op == OpFUnordGreaterThan      ? "setp.gtu.f32"
+                          : op == OpFUnordLessThanEqual    ? "setp.leu.f32"
+                          : op == OpFUnordGreaterThanEqual ? "setp.geu.f32"
+                          : op == OpFOrdLessThan           ? "setp.lt.f32"
                           : op == OpFOrdLessThanEqual    ? "setp.le.f32"
                           : op == OpFOrdGreaterThan      ? "setp.gt.f32"
                           : op == OpFOrdGreaterThanEqual ? "setp.ge.f32"
@@ -2319,6 +2330,26 @@ struct Emitter
           std::string lim = f2("max.f32", f2("min.f32", A(0)[c], fimm(9.0f)), fimm(-9.0f));
           std::string e2 = fexp(fadd(lim, lim));
           v.r.push_back(fdiv(fsub(e2, fimm(1.0f)), fadd(e2, fimm(1.0f))));
+        }
+        break;
+      case G_Asinh: case G_Acosh: case G_Atanh:    // through the logarithm, like libm's definitions
+        needExt(w[4]);
+        for(uint32_t c = 0; c < k; c++)
+        {
+          const std::string &x = A(0)[c];
+          auto ln = [&](const std::string &t) { return fmul(f1("lg2.approx.f32", t), fimm(0.6931471805599453f)); };
+          if(w[4] == G_Asinh)    // sign(x) * ln(|x| + sqrt(x^2 + 1))
+          {
+            std::string ax = f1("abs.f32", x);
+            std::string l = ln(fadd(ax, fsqrt(fadd(fmul(ax, ax), fimm(1.0f))))), pn = P(), d = R();
+            line("setp.lt.f32 %s, %s, %s;", pn.c_str(), x.c_str(), fimm(0.0f).c_str());
+            line("selp.b32 %s, %s, %s, %s;", d.c_str(), f1("neg.f32", l).c_str(), l.c_str(), pn.c_str());
+            v.r.push_back(d);
+          }
+          else if(w[4] == G_Acosh)    // ln(x + sqrt(x^2 - 1))
+            v.r.push_back(ln(fadd(x, fsqrt(fsub(fmul(x, x), fimm(1.0f))))));
+          else    // ln((1 + x) / (1 - x)) / 2
+            v.r.push_back(fmul(ln(fdiv(fadd(fimm(1.0f), x), fsub(fimm(1.0f), x))), fimm(0.5f)));
         }
         break;
       case G_Atan:
