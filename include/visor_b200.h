@@ -310,14 +310,16 @@ VB200_API const char *vb200_last_tile_kernel(void);
  * "time_kernels": 0/1, "fuse_clears": 0/1, "slot_keys": 0/1 — 0 forces the resolve kernels' code path of
  * draws with 2^24 or more triangles; "tile_list_cap": entries per tile list, 0 = automatic — a tiny value
  * forces the tile kernels' fallback for overflowed lists; "mgpu_mirrors": see vb200_mgpu_init).
- * "extended_spirv": 1 makes later vb200_shader_create calls
- * accept opcodes the reference asserts on: OpPhi, OpSwitch, OpKill (discard; such fragment shaders always run
- * on the in-order tile kernel), OpSelect, the remaining float and integer comparisons, integer division /
- * remainder / shifts / bit and logic operations, OpBitcast, OpConvertFToS/FToU/UToF, OpIsNan/OpIsInf, OpCopyObject, OpUndef, OpConstantNull/True/False,
- * OpCompositeInsert, OpVectorExtractDynamic/InsertDynamic, OpFRem/OpFMod, OpAny/OpAll, OpBitCount/OpBitReverse,
- * OpBitFieldInsert/SExtract/UExtract, OpImageSampleExplicitLod (level ignored: mip 0), the OpFUnord* comparisons and 45 GLSL.std.450 instructions (DESIGN.md section 3 lists them, the results fixed where SPIR-V leaves
- * them open and the fifteen transcendental ones that are approximate like the reference subset's Sin/Cos/Pow) — off by default, because with it the front end no longer rejects exactly what CompileFunction
- * rejects (spirv_compile.cpp:1734,1888). Unknown names return VB200_ERR_INVALID. */
+ * "extended_spirv": 1 makes later vb200_shader_create calls accept opcodes the reference asserts on: OpPhi,
+ * OpSwitch, OpKill (discard; such fragment shaders always run on the in-order tile kernel), OpSelect, the
+ * remaining ordered and all unordered float comparisons, the remaining integer comparisons, integer division /
+ * remainder / shifts / bit, bit-field and logic operations, OpBitcast, OpConvertFToS/FToU/UToF, OpIsNan/OpIsInf,
+ * OpAny/OpAll, OpFRem/OpFMod, OpCopyObject, OpUndef, OpConstantNull/True/False, OpCompositeInsert,
+ * OpVectorExtractDynamic/InsertDynamic, OpImageSampleExplicitLod (level ignored: mip 0) and 45 GLSL.std.450
+ * instructions (DESIGN.md section 3 lists them, the results fixed where SPIR-V leaves them open, and the
+ * fifteen transcendental ones that are approximate like the reference subset's Sin/Cos/Pow) — off by default,
+ * because with it the front end no longer rejects exactly what CompileFunction rejects
+ * (spirv_compile.cpp:1734,1888). Unknown names return VB200_ERR_INVALID. */
 VB200_API int vb200_set_option(const char *name, int64_t value);
 
 #ifdef __cplusplus
